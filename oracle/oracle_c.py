@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE — ctypes loader for oracle/_build/liboracle.so (the C restatement).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this.  Arrays are numpy uint64 with trailing dimension 4 (field element, LE limbs) or
+8 (G1 affine x||y, Montgomery)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+FR, FQ = 0, 1
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_msm_window_bits.restype = C.c_int
+        _lib.orc_msm_window_bits.argtypes = [C.c_size_t]
+        _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_g1_on_curve.restype = C.c_int
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def int_to_limbs(v: int) -> np.ndarray:
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def limbs_to_int(a) -> int:
+    a = np.asarray(a, dtype=np.uint64).reshape(-1)
+    return sum(int(a[i]) << (64 * i) for i in range(len(a)))
+
+
+def ints_to_array(vals) -> np.ndarray:
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i] = int_to_limbs(v)
+    return out
+
+
+def array_to_ints(a: np.ndarray):
+    a = np.asarray(a, dtype=np.uint64).reshape(-1, 4)
+    return [limbs_to_int(r) for r in a]
+
+
+def fp_binop(name: str, which: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint64)
+    getattr(lib(), name)(C.c_int(which), _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out))
+    return out
+
+
+def fp_unop(name: str, which: int, a: np.ndarray) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint64)
+    getattr(lib(), name)(C.c_int(which), _p(np.ascontiguousarray(a)), _p(out))
+    return out
+
+
+def array_from_mont(which: int, a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().orc_fp_array_from_mont(C.c_int(which), _p(a), C.c_size_t(a.size // 4), _p(out))
+    return out
+
+
+def array_to_mont(which: int, a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().orc_fp_array_to_mont(C.c_int(which), _p(a), C.c_size_t(a.size // 4), _p(out))
+    return out
+
+
+def splitmix_fr(seed: int, n: int, montgomery: bool, first: int = 0) -> np.ndarray:
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_splitmix_fr(C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), C.c_int(int(montgomery)), _p(out))
+    return out
+
+
+def known_dlog_bases(seed: int, n: int, first: int = 0) -> np.ndarray:
+    out = np.empty((n, 8), dtype=np.uint64)
+    lib().orc_g1_known_dlog_bases(C.c_uint64(seed), C.c_size_t(first), C.c_size_t(n), _p(out))
+    return out
+
+
+def g1_on_curve(xy: np.ndarray) -> bool:
+    return bool(lib().orc_g1_on_curve(_p(np.ascontiguousarray(xy, dtype=np.uint64))))
+
+
+def g1_add(a, a_inf, b, b_inf):
+    out = np.zeros(8, dtype=np.uint64)
+    inf = C.c_int(0)
+    lib().orc_g1_add(_p(np.ascontiguousarray(a)), C.c_int(int(a_inf)), _p(np.ascontiguousarray(b)),
+                     C.c_int(int(b_inf)), _p(out), C.byref(inf))
+    return out, bool(inf.value)
+
+
+def g1_mul(p, p_inf, k_canon):
+    out = np.zeros(8, dtype=np.uint64)
+    inf = C.c_int(0)
+    lib().orc_g1_mul(_p(np.ascontiguousarray(p)), C.c_int(int(p_inf)), _p(np.ascontiguousarray(k_canon)),
+                     _p(out), C.byref(inf))
+    return out, bool(inf.value)
+
+
+def msm(bases: np.ndarray, scalars_canon: np.ndarray, naive: bool = False):
+    bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    scalars_canon = np.ascontiguousarray(scalars_canon, dtype=np.uint64)
+    n = min(bases.size // 8, scalars_canon.size // 4)
+    out = np.zeros(8, dtype=np.uint64)
+    inf = C.c_int(0)
+    fn = lib().orc_msm_naive if naive else lib().orc_msm
+    fn(_p(bases), _p(scalars_canon), C.c_size_t(n), _p(out), C.byref(inf))
+    return out, bool(inf.value)
+
+
+def msm_window_bits(n: int) -> int:
+    return lib().orc_msm_window_bits(n)
+
+
+def ntt(data: np.ndarray, inverse: bool = False, coset: bool = False) -> np.ndarray:
+    """Returns a transformed copy (Montgomery in, Montgomery out, natural order)."""
+    out = np.array(data, dtype=np.uint64, copy=True, order="C")
+    n = out.size // 4
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    lib().orc_ntt(_p(out), C.c_uint(log_n), C.c_int(int(inverse)), C.c_int(int(coset)))
+    return out
+
+
+def domain_generator(log_n: int) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_domain_generator(C.c_uint(log_n), _p(out))
+    return out
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
