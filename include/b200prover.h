@@ -1,0 +1,134 @@
+/* libb200prover — C ABI of the B200-native proving backend for the PlonK prover behind
+ * renegade-fi/renegade's crates/circuits.
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this path: its
+ * prover calls Rust crates directly.  Each entry point below names the Rust call it replaces;
+ * INTEGRATION.md shows the `extern "C"` block and the safe wrappers a maintainer adds in a new
+ * `gpu-prover` shim crate (the existing crates deny `unsafe`: circuit-types/src/lib.rs:4).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every handle is opaque and owned by the library;
+ *   - caller owns all host buffers; the library never keeps a caller pointer past return;
+ *   - return 0 on success, negative B200_ERR_* otherwise; never throws, never aborts;
+ *     b200_last_error() returns a thread-local message for the last failure;
+ *   - field element = 4 x uint64 little-endian limbs (32 bytes).  "Montgomery" = a * 2^256 mod p,
+ *     exactly ark-ff's in-memory `Fp256<MontBackend>`; "canonical" = ark-ff `BigInt<4>`;
+ *   - G1 affine point = x || y, 64 bytes, Montgomery — one record of the reference's SRS file
+ *     (crates/circuits/circuit-types/src/primitives/srs.rs:172-182) and the payload of
+ *     `Commitment(G1Affine)`; the identity is flagged separately (and stored as 64 zero bytes);
+ *   - a context serialises the calls made on it; use one context per worker thread (rayon
+ *     workers in native_proof_manager.rs:187-192) or per GPU for concurrency.
+ *   - there is no CPU fallback: without a CUDA device every entry point fails with
+ *     B200_ERR_NO_DEVICE.
+ */
+#ifndef B200PROVER_H
+#define B200PROVER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID (-1)      /* bad argument */
+#define B200_ERR_CUDA (-2)         /* CUDA runtime failure (message has the call) */
+#define B200_ERR_NOMEM (-3)
+#define B200_ERR_FORMAT (-4)       /* malformed .ptau */
+#define B200_ERR_NOT_ON_CURVE (-5) /* srs.rs:179 "point not on curve" */
+#define B200_ERR_NO_DEVICE (-6)
+
+typedef struct b200_ctx b200_ctx;     /* one CUDA device + stream + scratch */
+typedef struct b200_bases b200_bases; /* device-resident G1 bases + window tables (the SRS) */
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  Replaces nothing in the reference (it has no device). */
+int b200_init(int device, b200_ctx** out);
+void b200_shutdown(b200_ctx* ctx);
+const char* b200_last_error(void);
+/* "libb200prover <version> sm_100a" */
+const char* b200_version(void);
+
+/* ---- SRS ------------------------------------------------------------------------------- */
+/* Replaces parse_ptau_file / read_ptau_header / read_ptau_section1 / read_ptau_section2
+ * (srs.rs:63-141): validates magic "ptau", version 1, 11 sections, the Fq modulus and
+ * power >= 17, and returns a pointer INTO `bytes` to the first G1 record and the number of
+ * records available in section 2.  Host-only, no device work. */
+int b200_srs_parse_ptau(const uint8_t* bytes, size_t len, const uint8_t** g1_records,
+                        size_t* n_records);
+
+/* Uploads n affine points (64-byte records) and precomputes their window tables.
+ * Replaces building `UnivariateUniversalParams.powers_of_g` (srs.rs:70) / the `commit_key`
+ * held by `ProvingKey` (traits.rs:850).  window_bits = 0 lets the library choose.
+ * check_on_curve != 0 repeats the reference's `is_on_curve` assertion (srs.rs:178-179) on the
+ * device and fails with B200_ERR_NOT_ON_CURVE. */
+int b200_bases_load(b200_ctx* ctx, const uint8_t* points64, size_t n, int window_bits,
+                    int check_on_curve, b200_bases** out);
+/* Same, from points already in device memory (device pointer). */
+int b200_bases_load_device(b200_ctx* ctx, const void* d_points64, size_t n, int window_bits,
+                           b200_bases** out);
+void b200_bases_free(b200_ctx* ctx, b200_bases* bases);
+size_t b200_bases_len(const b200_bases* bases);
+/* plan[0..3] = window bits c, digits per scalar, physical bucket windows, precomputed tables */
+void b200_bases_plan(const b200_bases* bases, int plan[4]);
+
+/* ---- MSM ------------------------------------------------------------------------------- */
+/* out = sum_{i<n} scalars[i] * bases[base_off + i].
+ * Replaces `VariableBaseMSM::msm_bigint(&bases[..], &scalars[..])` followed by
+ * `.into_affine()` as used by jf-primitives `UnivariateKzgPCS::commit` (reached from
+ * traits.rs:850,996; proof_linking/intent_only.rs:42-47).  scalars_montgomery = 0: canonical
+ * `BigInt<4>` (what msm_bigint takes); 1: Montgomery `Fr` coefficients (what `commit` is
+ * handed) — the conversion is fused into digit extraction.  Scalars must be < r. */
+int b200_msm(b200_ctx* ctx, const b200_bases* bases, size_t base_off, const uint64_t* scalars,
+             size_t n, int scalars_montgomery, uint64_t out_xy[8], int* out_is_identity);
+/* Same with the scalars already resident in device memory (device pointer). */
+int b200_msm_device(b200_ctx* ctx, const b200_bases* bases, size_t base_off,
+                    const void* d_scalars, size_t n, int scalars_montgomery, uint64_t out_xy[8],
+                    int* out_is_identity);
+
+/* Device-side phase timing (CUDA events recorded on the context's stream).  enable != 0 turns
+ * it on for subsequent MSM calls; out_ms (may be NULL) receives the last call's
+ * {total, sort = count+scan+scatter, bucket accumulation, bucket reduction} in ms. */
+int b200_msm_timing(b200_ctx* ctx, int enable, float out_ms[4]);
+
+/* Sum of k affine points on the host (combining per-GPU partial MSM results after the NCCL
+ * gather; ark-ec `Projective += Affine`). */
+int b200_g1_sum_affine(const uint64_t* points_xy, const int* is_identity, size_t k,
+                       uint64_t out_xy[8], int* out_is_identity);
+
+/* ---- NTT ------------------------------------------------------------------------------- */
+/* In-place transform of n = 2^log_n Montgomery Fr elements, natural order in and out.
+ * Replaces Radix2EvaluationDomain::<Fr>::{fft_in_place, ifft_in_place, coset_fft_in_place,
+ * coset_ifft_in_place} (ark-poly 0.4.2; coset shift = Fr::GENERATOR = 5; ifft scales by n^-1). */
+int b200_ntt(b200_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, int coset);
+/* `batch` transforms `stride` elements apart, data in device memory (device pointer). */
+int b200_ntt_device(b200_ctx* ctx, void* d_data, unsigned log_n, int inverse, int coset,
+                    unsigned batch, size_t stride);
+/* Device time (CUDA events around the kernels) of the last b200_ntt_device call, in ms. */
+int b200_ntt_last_ms(b200_ctx* ctx, float* out_ms);
+/* Radix2EvaluationDomain::group_gen (Montgomery). */
+int b200_domain_generator(b200_ctx* ctx, unsigned log_n, uint64_t out[4]);
+
+/* ---- synthetic inputs for benchmarks / parity tests ------------------- */
+/* element i = SplitMix64(seed) outputs 4i..4i+3 as LE limbs, reduced mod r */
+int b200_splitmix_fr_device(b200_ctx* ctx, uint64_t seed, size_t first, size_t n, int montgomery,
+                            void* d_out);
+/* known-discrete-log bases P_i = a_i * G, a_i = splitmix_fr(seed)[first + i]; 64 B records */
+int b200_known_dlog_bases_device(b200_ctx* ctx, uint64_t seed, size_t first, size_t n,
+                                 void* d_out);
+
+/* ---- device self-test ------------------------------------------------------------------ */
+/* Runs `iters` random Fr and Fq products through the production multiplier (IMAD.WIDE chains)
+ * and the word-serial reference multiplier on the device and returns the number of
+ * mismatches in *mismatches (0 expected). */
+int b200_selftest_field(b200_ctx* ctx, uint64_t seed, size_t iters, uint64_t* mismatches);
+/* out[i] = a[i] (op) b[i] on the device; field: 0 = Fr, 1 = Fq; op: 0 mul, 1 add, 2 sub,
+ * 3 inverse of a.  Host buffers, n x 4 limbs (Montgomery).  For parity tests. */
+int b200_field_op(b200_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, size_t n,
+                  uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PROVER_H */

@@ -1,0 +1,83 @@
+"""ctypes binding of libb200prover.so (C ABI in include/b200prover.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C renegade_b200/csrc`.
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible, the
+calls below raise — they never route to the oracle or to any host implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200prover.so")
+
+# every symbol include/b200prover.h declares (tests/test_abi.py checks this list against the
+# header and against the built library)
+EXPORTS = [
+    "b200_init", "b200_shutdown", "b200_last_error", "b200_version",
+    "b200_srs_parse_ptau", "b200_bases_load", "b200_bases_load_device", "b200_bases_free",
+    "b200_bases_len", "b200_bases_plan",
+    "b200_msm", "b200_msm_device", "b200_msm_timing", "b200_g1_sum_affine",
+    "b200_ntt", "b200_ntt_device", "b200_ntt_last_ms", "b200_domain_generator",
+    "b200_splitmix_fr_device", "b200_known_dlog_bases_device",
+    "b200_selftest_field", "b200_field_op",
+]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb200prover error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the proving path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i32, u64, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_version.restype = C.c_char_p
+    lib.b200_init.argtypes = [i32, C.POINTER(vp)]
+    lib.b200_shutdown.argtypes = [vp]
+    lib.b200_shutdown.restype = None
+    lib.b200_srs_parse_ptau.argtypes = [vp, sz, C.POINTER(vp), C.POINTER(sz)]
+    lib.b200_bases_load.argtypes = [vp, vp, sz, i32, i32, C.POINTER(vp)]
+    lib.b200_bases_load_device.argtypes = [vp, vp, sz, i32, C.POINTER(vp)]
+    lib.b200_bases_free.argtypes = [vp, vp]
+    lib.b200_bases_free.restype = None
+    lib.b200_bases_len.argtypes = [vp]
+    lib.b200_bases_len.restype = sz
+    lib.b200_bases_plan.argtypes = [vp, C.POINTER(i32 * 4)]
+    lib.b200_bases_plan.restype = None
+    lib.b200_msm.argtypes = [vp, vp, sz, vp, sz, i32, vp, C.POINTER(i32)]
+    lib.b200_msm_device.argtypes = [vp, vp, sz, vp, sz, i32, vp, C.POINTER(i32)]
+    lib.b200_msm_timing.argtypes = [vp, i32, C.POINTER(C.c_float * 4)]
+    lib.b200_ntt_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.b200_g1_sum_affine.argtypes = [vp, vp, sz, vp, C.POINTER(i32)]
+    lib.b200_ntt.argtypes = [vp, vp, u32, i32, i32]
+    lib.b200_ntt_device.argtypes = [vp, vp, u32, i32, i32, u32, sz]
+    lib.b200_domain_generator.argtypes = [vp, u32, vp]
+    lib.b200_splitmix_fr_device.argtypes = [vp, u64, sz, sz, i32, vp]
+    lib.b200_known_dlog_bases_device.argtypes = [vp, u64, sz, sz, vp]
+    lib.b200_selftest_field.argtypes = [vp, u64, sz, C.POINTER(u64)]
+    lib.b200_field_op.argtypes = [vp, i32, i32, vp, vp, sz, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
+        if fn.restype is C.c_int and name not in ("b200_last_error", "b200_version"):
+            pass
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200Error(rc, (load().b200_last_error() or b"").decode(errors="replace"))

@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's interface for the proving hot path, over the C ABI.
+
+Names follow the Rust surface the reference calls:
+
+  parse_ptau_file                      crates/circuits/circuit-types/src/primitives/srs.rs:63-71
+  UnivariateUniversalParams            jf-primitives (built at srs.rs:70)
+  VariableBaseMSM.msm_bigint           ark-ec 0.4.2 (under UnivariateKzgPCS::commit)
+  UnivariateKzgPCS.commit              jf-primitives (reached from traits.rs:850,996)
+  Radix2EvaluationDomain               ark-poly 0.4.2 (fft / ifft / coset_fft / coset_ifft)
+
+Field elements are numpy uint64 arrays with a trailing dimension of 4 (little-endian limbs,
+Montgomery form unless stated), G1 affine points have a trailing dimension of 8 (x || y).
+All arithmetic runs in libb200prover.so on the GPU; nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+MAX_SRS_POWER = 17
+MAX_SRS_DEGREE = (1 << MAX_SRS_POWER) + 2  # srs.rs:44-47
+
+
+def _ptr(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + stream + scratch (b200_ctx).  Calls on one context are serialised."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_init(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- bases / SRS ------------------------------------------------------------------------
+    def load_bases(self, points, window_bits: int = 0, check_on_curve: bool = False) -> "Bases":
+        """points: (n, 8) uint64 array or bytes of 64-byte records."""
+        if isinstance(points, (bytes, bytearray, memoryview)):
+            buf = np.frombuffer(bytes(points), dtype=np.uint64).reshape(-1, 8)
+        else:
+            buf = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_bases_load(self._h, _ptr(buf), buf.shape[0], window_bits,
+                                             int(check_on_curve), C.byref(h)))
+        return Bases(self, h)
+
+    def load_bases_device(self, d_ptr: int, n: int, window_bits: int = 0) -> "Bases":
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_bases_load_device(self._h, C.c_void_p(d_ptr), n, window_bits, C.byref(h)))
+        return Bases(self, h)
+
+    # ---- MSM --------------------------------------------------------------------------------
+    def msm(self, bases: "Bases", scalars: np.ndarray, montgomery: bool = False, base_off: int = 0):
+        s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_int(0)
+        _lib.check(self._lib.b200_msm(self._h, bases._h, base_off, _ptr(s), s.shape[0], int(montgomery),
+                                      _ptr(out), C.byref(inf)))
+        return out, bool(inf.value)
+
+    def msm_device(self, bases: "Bases", d_scalars: int, n: int, montgomery: bool = False, base_off: int = 0):
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_int(0)
+        _lib.check(self._lib.b200_msm_device(self._h, bases._h, base_off, C.c_void_p(d_scalars), n,
+                                             int(montgomery), _ptr(out), C.byref(inf)))
+        return out, bool(inf.value)
+
+    def msm_timing(self, enable: bool = True) -> dict:
+        """Enable device-side phase timing; returns the last MSM's phases in ms."""
+        arr = (C.c_float * 4)()
+        _lib.check(self._lib.b200_msm_timing(self._h, int(enable), C.byref(arr)))
+        return {"total": arr[0], "sort": arr[1], "accumulate": arr[2], "reduce": arr[3]}
+
+    def ntt_last_ms(self) -> float:
+        v = C.c_float(0)
+        _lib.check(self._lib.b200_ntt_last_ms(self._h, C.byref(v)))
+        return v.value
+
+    def g1_sum_affine(self, points: np.ndarray, is_identity=None):
+        p = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+        flags = None
+        if is_identity is not None:
+            flags = (C.c_int * p.shape[0])(*[int(bool(x)) for x in is_identity])
+        out = np.zeros(8, dtype=np.uint64)
+        inf = C.c_int(0)
+        _lib.check(self._lib.b200_g1_sum_affine(_ptr(p), flags, p.shape[0], _ptr(out), C.byref(inf)))
+        return out, bool(inf.value)
+
+    # ---- NTT --------------------------------------------------------------------------------
+    def ntt(self, data: np.ndarray, inverse: bool = False, coset: bool = False) -> np.ndarray:
+        out = np.array(data, dtype=np.uint64, copy=True, order="C").reshape(-1, 4)
+        n = out.shape[0]
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise ValueError("domain size must be a power of two")
+        _lib.check(self._lib.b200_ntt(self._h, _ptr(out), log_n, int(inverse), int(coset)))
+        return out
+
+    def ntt_device(self, d_ptr: int, log_n: int, inverse: bool = False, coset: bool = False,
+                   batch: int = 1, stride: int | None = None) -> None:
+        stride = (1 << log_n) if stride is None else stride
+        _lib.check(self._lib.b200_ntt_device(self._h, C.c_void_p(d_ptr), log_n, int(inverse), int(coset),
+                                             batch, stride))
+
+    def domain_generator(self, log_n: int) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        _lib.check(self._lib.b200_domain_generator(self._h, log_n, _ptr(out)))
+        return out
+
+    # ---- synthetic inputs (device) ------------------------------------------------------------
+    def splitmix_fr_device(self, seed: int, n: int, d_out: int, montgomery: bool, first: int = 0) -> None:
+        _lib.check(self._lib.b200_splitmix_fr_device(self._h, seed, first, n, int(montgomery), C.c_void_p(d_out)))
+
+    def known_dlog_bases_device(self, seed: int, n: int, d_out: int, first: int = 0) -> None:
+        _lib.check(self._lib.b200_known_dlog_bases_device(self._h, seed, first, n, C.c_void_p(d_out)))
+
+    # ---- self tests -----------------------------------------------------------------------------
+    def selftest_field(self, seed: int, iters: int) -> int:
+        bad = C.c_uint64(0)
+        _lib.check(self._lib.b200_selftest_field(self._h, seed, iters, C.byref(bad)))
+        return bad.value
+
+    def field_op(self, field: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros_like(a)
+        _lib.check(self._lib.b200_field_op(self._h, field, op, _ptr(a), _ptr(b), a.shape[0], _ptr(out)))
+        return out
+
+
+class Bases:
+    """Device-resident G1 bases with their precomputed window tables (b200_bases)."""
+
+    def __init__(self, ctx: Context, handle):
+        self._ctx = ctx
+        self._h = handle
+
+    def __len__(self) -> int:
+        return int(self._ctx._lib.b200_bases_len(self._h))
+
+    @property
+    def plan(self) -> dict:
+        arr = (C.c_int * 4)()
+        self._ctx._lib.b200_bases_plan(self._h, C.byref(arr))
+        return {"window_bits": arr[0], "digits": arr[1], "physical_windows": arr[2], "tables": arr[3]}
+
+    def free(self):
+        if self._h and self._ctx._h:
+            self._ctx._lib.b200_bases_free(self._ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference-shaped interface
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class UnivariateUniversalParams:
+    """jf-primitives `UnivariateUniversalParams<Bn254>` as built at srs.rs:70: the G1 powers
+    live on the device; `powers_of_g_host` keeps the raw 64-byte records for inspection."""
+    powers_of_g: Bases
+    powers_of_g_host: np.ndarray
+
+
+def parse_ptau_file(ctx: Context, data: bytes, window_bits: int = 0,
+                    check_on_curve: bool = True) -> UnivariateUniversalParams:
+    """srs.rs:63-71: header/section checks, MAX_SRS_DEGREE+1 G1 powers, on-curve assertion
+    (srs.rs:178-179, run on the device)."""
+    lib = _lib.load()
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    rec = C.c_void_p()
+    n = C.c_size_t()
+    _lib.check(lib.b200_srs_parse_ptau(C.cast(buf, C.c_void_p), len(data), C.byref(rec), C.byref(n)))
+    need = MAX_SRS_DEGREE + 1
+    if n.value < need:
+        raise _lib.B200Error(-4, f"ptau: only {n.value} G1 records available, need {need}")
+    off = rec.value - C.addressof(buf)
+    host = np.frombuffer(data, dtype=np.uint64, count=need * 8, offset=off).reshape(need, 8).copy()
+    bases = ctx.load_bases(host, window_bits=window_bits, check_on_curve=check_on_curve)
+    return UnivariateUniversalParams(powers_of_g=bases, powers_of_g_host=host)
+
+
+class VariableBaseMSM:
+    """ark-ec 0.4.2 `VariableBaseMSM`."""
+
+    @staticmethod
+    def msm_bigint(ctx: Context, bases: Bases, bigints: np.ndarray):
+        """sum_i bigints[i] * bases[i]; bigints canonical (`BigInt<4>`).  Returns the affine
+        result (x||y Montgomery, identity flag) — what `.into_affine()` yields."""
+        return ctx.msm(bases, bigints, montgomery=False)
+
+
+class UnivariateKzgPCS:
+    """jf-primitives `UnivariateKzgPCS`."""
+
+    @staticmethod
+    def commit(ctx: Context, prover_param: Bases, poly_coeffs: np.ndarray):
+        """Commitment to a dense polynomial given by Montgomery `Fr` coefficients: the
+        Montgomery->canonical conversion jf-primitives does on the CPU
+        (`convert_to_bigints`) is fused into the device digit extraction."""
+        return ctx.msm(prover_param, poly_coeffs, montgomery=True)
+
+
+class Radix2EvaluationDomain:
+    """ark-poly 0.4.2 `Radix2EvaluationDomain<Fr>`: natural order in and out."""
+
+    def __init__(self, ctx: Context, num_coeffs: int):
+        size = 1
+        while size < num_coeffs:
+            size <<= 1
+        self.ctx = ctx
+        self.size = size
+        self.log_size_of_group = size.bit_length() - 1
+        self.group_gen = ctx.domain_generator(self.log_size_of_group)
+
+    def _pad(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4)
+        if x.shape[0] > self.size:
+            raise ValueError("more coefficients than the domain size")
+        if x.shape[0] < self.size:  # ark-poly resizes with zeros
+            x = np.concatenate([x, np.zeros((self.size - x.shape[0], 4), dtype=np.uint64)])
+        return x
+
+    def fft(self, coeffs: np.ndarray) -> np.ndarray:
+        return self.ctx.ntt(self._pad(coeffs), inverse=False, coset=False)
+
+    def ifft(self, evals: np.ndarray) -> np.ndarray:
+        return self.ctx.ntt(self._pad(evals), inverse=True, coset=False)
+
+    def coset_fft(self, coeffs: np.ndarray) -> np.ndarray:
+        return self.ctx.ntt(self._pad(coeffs), inverse=False, coset=True)
+
+    def coset_ifft(self, evals: np.ndarray) -> np.ndarray:
+        return self.ctx.ntt(self._pad(evals), inverse=True, coset=True)

@@ -1,0 +1,121 @@
+// Internal (C++) declarations shared by the CUDA translation units behind the C ABI in
+// include/b200prover.h.  Nothing here is part of the public boundary.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "ec.cuh"
+#include "ff.cuh"
+
+#include "b200prover.h"  // error codes
+
+namespace b200 {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);  // records the message, returns B200_ERR_CUDA
+
+#define B200_CUDA(expr)                                            \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) return ::b200::cuda_fail(_e, #expr); \
+    } while (0)
+
+// Grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(DevBuf)");
+        cap = bytes;
+        return B200_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+// ---- NTT ------------------------------------------------------------------------------------
+struct Domain {
+    unsigned log_n = 0;
+    fe* tw_fwd = nullptr;     // w^k,  k < n/2
+    fe* tw_inv = nullptr;     // w^-k, k < n/2
+    fe* coset_fwd = nullptr;  // g^i,  i < n
+    fe* coset_inv = nullptr;  // g^-i * n^-1
+    fe n_inv;                 // n^-1 (Montgomery)
+    fe group_gen;             // w (Montgomery)
+    ~Domain();
+};
+int domain_create(unsigned log_n, cudaStream_t st, Domain** out);
+int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, unsigned batch,
+               size_t stride, cudaStream_t st);
+
+// ---- MSM ------------------------------------------------------------------------------------
+struct MsmPlan {
+    int c = 0;        // window bits (signed digits in [-2^(c-1), 2^(c-1)])
+    int n_digits = 0; // W = ceil(255 / c)
+    int n_phys = 0;   // physical bucket windows Wp
+    int n_tables = 0; // F = ceil(W / Wp); table j holds 2^(c*Wp*j) * P
+};
+
+struct Bases {
+    size_t n = 0;
+    MsmPlan plan;
+    g1_affine* tables = nullptr;  // n_tables * n affine points, table-major
+    ~Bases() {
+        if (tables) cudaFree(tables);
+    }
+};
+
+struct MsmScratch {
+    DevBuf counts, offsets, cursor, entries, buckets, block_sums, partials, window_sums, scalars;
+    // optional per-phase device timing (CUDA events on the launching stream)
+    bool timing = false;
+    bool ev_init = false;
+    cudaEvent_t ev[5] = {};
+    float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
+    ~MsmScratch() {
+        if (ev_init)
+            for (auto& e : ev) cudaEventDestroy(e);
+    }
+};
+
+MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes);
+int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_on_curve,
+                 cudaStream_t st, Bases** out);
+int bases_create_device(const g1_affine* d_points, size_t n, int c_override, cudaStream_t st,
+                        Bases** out);
+// scalars on device (n x 32 B); result: XYZZ sums of the n_phys windows copied to host and
+// combined there (Horner + one inversion).
+int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, int montgomery,
+               MsmScratch* s, cudaStream_t st, g1_affine* out, int* out_inf);
+// synthetic known-discrete-log bases P_i = a_i * G, a_i = SplitMix64-derived
+int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
+                               cudaStream_t st);
+int splitmix_fr_device(uint64_t seed, size_t first, size_t n, int montgomery, fe* d_out,
+                       cudaStream_t st);
+
+// ---- context --------------------------------------------------------------------------------
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;  // one call at a time per context; callers may hold several contexts
+    std::map<unsigned, Domain*> domains;
+    DevBuf ntt_data, ntt_scratch;
+    cudaEvent_t ntt_ev[2] = {};
+    bool ntt_ev_init = false;
+    float ntt_last_ms = 0.f;  // device time of the last b200_ntt_device call (CUDA events)
+    MsmScratch msm;
+    ~Context();
+};
+
+}  // namespace b200

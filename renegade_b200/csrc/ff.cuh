@@ -1,0 +1,499 @@
+// BN254 prime-field arithmetic for sm_100a: 256-bit Montgomery residues as 8 x u32 limbs.
+//
+// Replaces (on the device) what the reference reaches through ark-ff 0.4.2
+// `Fp<MontBackend<FrConfig,4>,4>` / `FqConfig` (types fixed by
+// /root/reference/crates/constants/src/lib.rs:63-89; constants SURVEY.md §8(a6)).
+// In-memory layout is identical to arkworks': 32 bytes, little-endian limbs, value a*2^256 mod p,
+// so host buffers cross the C ABI without conversion.  One element = one 32-byte DRAM sector;
+// a thread moves it with two 128-bit accesses.
+//
+// The multiplier is word-serial Montgomery (CIOS) on the FMA-pipe integer multiplier
+// (mad.lo.cc / madc.hi.cc carry chains).  No tensor cores: this is wide-integer modular
+// arithmetic, not a contraction.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FF_HD __host__ __device__ __forceinline__
+#define FF_D __device__ __forceinline__
+#else
+#define FF_HD inline
+#define FF_D inline
+#endif
+
+namespace b200 {
+
+struct alignas(16) fe {
+    uint32_t l[8];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Field configurations.  Limb getters are constexpr functions (not arrays) so that, after full
+// unrolling, every modulus limb becomes an instruction immediate in SASS.
+// ---------------------------------------------------------------------------------------------
+struct FrCfg {  // scalar field r
+    static FF_HD constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    static FF_HD constexpr uint32_t one(int i) {  // R mod r
+        constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                   0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    static FF_HD constexpr uint32_t r2(int i) {  // R^2 mod r
+        constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                   0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return v[i];
+    }
+    static constexpr uint32_t inv = 0xefffffffu;  // -r^-1 mod 2^32
+};
+
+struct FqCfg {  // base field q
+    static FF_HD constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    static FF_HD constexpr uint32_t one(int i) {  // R mod q
+        constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                   0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    static FF_HD constexpr uint32_t r2(int i) {  // R^2 mod q
+        constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                                   0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+    static constexpr uint32_t inv = 0xe4866389u;  // -q^-1 mod 2^32
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX carry-chain primitives (device only)
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+namespace ptx {
+FF_D uint32_t add_cc(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+FF_D uint32_t addc_cc(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+FF_D uint32_t addc(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+FF_D uint32_t sub_cc(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+FF_D uint32_t subc_cc(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+FF_D uint32_t subc(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+FF_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+FF_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+FF_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+FF_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+FF_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// (lo,hi) pair helpers: ptxas fuses each lo/hi pair on the same multiplicands into one
+// IMAD.WIDE.U32[.X] with predicate carry-in/out (checked with cuobjdump -sass).
+FF_D void wmul(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+FF_D void wmad_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {  // starts a carry chain
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                 : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+FF_D void wmadc_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {  // continues a carry chain
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;"
+                 : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+}  // namespace ptx
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Basic helpers (host + device)
+// ---------------------------------------------------------------------------------------------
+FF_HD bool fe_is_zero(const fe& a) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x |= a.l[i];
+    return x == 0;
+}
+FF_HD bool fe_eq(const fe& a, const fe& b) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x |= a.l[i] ^ b.l[i];
+    return x == 0;
+}
+FF_HD fe fe_zero() {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = 0;
+    return r;
+}
+template <class C>
+FF_HD fe fe_one() {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = C::one(i);
+    return r;
+}
+template <class C>
+FF_HD fe fe_r2() {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = C::r2(i);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// add / sub / neg / dbl : inputs and outputs fully reduced in [0, p)
+// ---------------------------------------------------------------------------------------------
+template <class C>
+FF_HD fe fe_add(const fe& a, const fe& b) {
+    fe s, t;
+#if defined(__CUDA_ARCH__)
+    s.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) s.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    s.l[7] = ptx::addc(a.l[7], b.l[7]);  // p < 2^254: no carry out of 256 bits
+    t.l[0] = ptx::sub_cc(s.l[0], C::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t.l[i] = ptx::subc_cc(s.l[i], C::mod(i));
+    uint32_t borrow = ptx::subc(0u, 0u);  // 0xffffffff if s < p
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.l[i] = borrow ? s.l[i] : t.l[i];
+    return s;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a.l[i] + b.l[i];
+        s.l[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    int64_t br = 0;
+    for (int i = 0; i < 8; ++i) {
+        int64_t d = (int64_t)s.l[i] - (int64_t)C::mod(i) + br;
+        t.l[i] = (uint32_t)d;
+        br = d >> 32;
+    }
+    return br ? s : t;
+#endif
+}
+
+template <class C>
+FF_HD fe fe_sub(const fe& a, const fe& b) {
+    fe d;
+#if defined(__CUDA_ARCH__)
+    d.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) d.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+    uint32_t mask = ptx::subc(0u, 0u);  // all-ones if a < b
+    d.l[0] = ptx::add_cc(d.l[0], C::mod(0) & mask);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) d.l[i] = ptx::addc_cc(d.l[i], C::mod(i) & mask);
+    d.l[7] = ptx::addc(d.l[7], C::mod(7) & mask);
+    return d;
+#else
+    int64_t br = 0;
+    for (int i = 0; i < 8; ++i) {
+        int64_t v = (int64_t)a.l[i] - (int64_t)b.l[i] + br;
+        d.l[i] = (uint32_t)v;
+        br = v >> 32;
+    }
+    if (br) {
+        uint64_t c = 0;
+        for (int i = 0; i < 8; ++i) {
+            c += (uint64_t)d.l[i] + C::mod(i);
+            d.l[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    return d;
+#endif
+}
+
+template <class C>
+FF_HD fe fe_neg(const fe& a) {
+    return fe_sub<C>(fe_zero(), a);
+}
+template <class C>
+FF_HD fe fe_dbl(const fe& a) {
+    return fe_add<C>(a, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery product a*b*2^-256 mod p, reference variant kept for on-device differential tests.
+// Word-serial CIOS, 8 rounds; because p < 2^254 the
+// running value stays below 2p < 2^255, so the accumulator needs 9 limbs, never 10 ("no-carry"
+// property that ark-ff's MontBackend also exploits).
+// ---------------------------------------------------------------------------------------------
+template <class C>
+FF_HD fe fe_mul_chain(const fe& a, const fe& b) {
+    uint32_t t[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t bi = b.l[i];
+        // t += a * bi  (low halves, then high halves one limb up)
+        t[0] = ptx::mad_lo_cc(a.l[0], bi, t[0]);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) t[j] = ptx::madc_lo_cc(a.l[j], bi, t[j]);
+        t[8] = ptx::addc(0u, 0u);
+        t[1] = ptx::mad_hi_cc(a.l[0], bi, t[1]);
+#pragma unroll
+        for (int j = 1; j < 7; ++j) t[j + 1] = ptx::madc_hi_cc(a.l[j], bi, t[j + 1]);
+        t[8] = ptx::madc_hi(a.l[7], bi, t[8]);
+        // t = (t + m * p) / 2^32
+        const uint32_t m = t[0] * C::inv;
+        (void)ptx::mad_lo_cc(m, C::mod(0), t[0]);  // low limb cancels; keeps the carry
+#pragma unroll
+        for (int j = 1; j < 8; ++j) t[j] = ptx::madc_lo_cc(m, C::mod(j), t[j]);
+        t[8] = ptx::addc(t[8], 0u);
+        t[0] = ptx::mad_hi_cc(m, C::mod(0), t[1]);
+#pragma unroll
+        for (int j = 1; j < 7; ++j) t[j] = ptx::madc_hi_cc(m, C::mod(j), t[j + 1]);
+        t[7] = ptx::madc_hi(m, C::mod(7), t[8]);
+        t[8] = 0;
+    }
+    fe r, s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    s.l[0] = ptx::sub_cc(r.l[0], C::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s.l[i] = ptx::subc_cc(r.l[i], C::mod(i));
+    uint32_t borrow = ptx::subc(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = borrow ? r.l[i] : s.l[i];
+    return r;
+#else
+    for (int i = 0; i < 8; ++i) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 8; ++j) {
+            uint64_t v = (uint64_t)a.l[j] * b.l[i] + t[j] + carry;
+            t[j] = (uint32_t)v;
+            carry = v >> 32;
+        }
+        t[8] = (uint32_t)carry;  // t[8] was 0
+        uint32_t m = t[0] * C::inv;
+        uint64_t v = (uint64_t)m * C::mod(0) + t[0];
+        carry = v >> 32;
+        for (int j = 1; j < 8; ++j) {
+            v = (uint64_t)m * C::mod(j) + t[j] + carry;
+            t[j - 1] = (uint32_t)v;
+            carry = v >> 32;
+        }
+        t[7] = t[8] + (uint32_t)carry;
+        t[8] = 0;
+    }
+    fe r, s;
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    int64_t br = 0;
+    for (int i = 0; i < 8; ++i) {
+        int64_t d = (int64_t)r.l[i] - (int64_t)C::mod(i) + br;
+        s.l[i] = (uint32_t)d;
+        br = d >> 32;
+    }
+    return br ? r : s;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery product, production variant: the same word-serial reduction, but every 32x32->64
+// product is accumulated with ONE IMAD.WIDE.U32.X.  The running value T is split into an
+// "even" array E (aligned at 2^0) and an "odd" array O (aligned at 2^32): products a_j*s with
+// even j land 64-bit-aligned in E, odd j in O, so each carry chain is 4 wide multiply-adds.
+// After a round T/2^32 = O + E[1] + 2^32*E[2..8]: O becomes the next round's even array,
+// E[2..8] its odd array, and the single limb E[1] is folded in with one add.cc whose carry
+// (weight 2^32) enters the odd chain.  Bounds: T < 2p before a round, < 2^288 inside one, so
+// O never carries out of 8 limbs and E needs 9.   ~128 IMAD.WIDE + ~50 other instructions.
+// ---------------------------------------------------------------------------------------------
+template <class C>
+FF_HD fe fe_mul(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t E[9], O[8];
+    {
+        const uint32_t s = b.l[0];
+        ptx::wmul(O[0], O[1], a.l[1], s);
+        ptx::wmul(O[2], O[3], a.l[3], s);
+        ptx::wmul(O[4], O[5], a.l[5], s);
+        ptx::wmul(O[6], O[7], a.l[7], s);
+        ptx::wmul(E[0], E[1], a.l[0], s);
+        ptx::wmul(E[2], E[3], a.l[2], s);
+        ptx::wmul(E[4], E[5], a.l[4], s);
+        ptx::wmul(E[6], E[7], a.l[6], s);
+        const uint32_t m = E[0] * C::inv;
+        ptx::wmad_cc(O[0], O[1], C::mod(1), m);
+        ptx::wmadc_cc(O[2], O[3], C::mod(3), m);
+        ptx::wmadc_cc(O[4], O[5], C::mod(5), m);
+        ptx::wmadc_cc(O[6], O[7], C::mod(7), m);
+        ptx::wmad_cc(E[0], E[1], C::mod(0), m);
+        ptx::wmadc_cc(E[2], E[3], C::mod(2), m);
+        ptx::wmadc_cc(E[4], E[5], C::mod(4), m);
+        ptx::wmadc_cc(E[6], E[7], C::mod(6), m);
+        E[8] = ptx::addc(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        // T/2^32: even' = O (+ E[1] at limb 0), odd' = E[2..8]
+        uint32_t nE[9], nO[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nE[k] = O[k];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) nO[k] = E[k + 2];
+        nO[7] = 0;
+        const uint32_t s = b.l[i];
+        nE[0] = ptx::add_cc(nE[0], E[1]);  // carry has weight 2^32 -> odd chain
+        ptx::wmadc_cc(nO[0], nO[1], a.l[1], s);
+        ptx::wmadc_cc(nO[2], nO[3], a.l[3], s);
+        ptx::wmadc_cc(nO[4], nO[5], a.l[5], s);
+        ptx::wmadc_cc(nO[6], nO[7], a.l[7], s);
+        ptx::wmad_cc(nE[0], nE[1], a.l[0], s);
+        ptx::wmadc_cc(nE[2], nE[3], a.l[2], s);
+        ptx::wmadc_cc(nE[4], nE[5], a.l[4], s);
+        ptx::wmadc_cc(nE[6], nE[7], a.l[6], s);
+        nE[8] = ptx::addc(0u, 0u);
+        const uint32_t m = nE[0] * C::inv;
+        ptx::wmad_cc(nO[0], nO[1], C::mod(1), m);
+        ptx::wmadc_cc(nO[2], nO[3], C::mod(3), m);
+        ptx::wmadc_cc(nO[4], nO[5], C::mod(5), m);
+        ptx::wmadc_cc(nO[6], nO[7], C::mod(7), m);
+        ptx::wmad_cc(nE[0], nE[1], C::mod(0), m);
+        ptx::wmadc_cc(nE[2], nE[3], C::mod(2), m);
+        ptx::wmadc_cc(nE[4], nE[5], C::mod(4), m);
+        ptx::wmadc_cc(nE[6], nE[7], C::mod(6), m);
+        nE[8] = ptx::addc(nE[8], 0u);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = nE[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) O[k] = nO[k];
+    }
+    // result = O + E[1..8]  (< 2p), then one conditional subtraction
+    fe r, t;
+    r.l[0] = ptx::add_cc(O[0], E[1]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) r.l[k] = ptx::addc_cc(O[k], E[k + 1]);
+    r.l[7] = ptx::addc(O[7], E[8]);
+    t.l[0] = ptx::sub_cc(r.l[0], C::mod(0));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t.l[k] = ptx::subc_cc(r.l[k], C::mod(k));
+    const uint32_t borrow = ptx::subc(0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = borrow ? r.l[k] : t.l[k];
+    return r;
+#else
+    return fe_mul_chain<C>(a, b);
+#endif
+}
+
+template <class C>
+FF_HD fe fe_sqr(const fe& a) {
+    return fe_mul<C>(a, a);
+}
+
+template <class C>
+FF_HD fe fe_to_mont(const fe& a) {
+    return fe_mul<C>(a, fe_r2<C>());
+}
+template <class C>
+FF_HD fe fe_from_mont(const fe& a) {
+    fe one = fe_zero();
+    one.l[0] = 1;
+    return fe_mul<C>(a, one);
+}
+
+// a^e for a 256-bit exponent given as 8 limbs (square-and-multiply, MSB first)
+template <class C>
+FF_HD fe fe_pow(const fe& a, const fe& e) {
+    fe acc = fe_one<C>();
+    for (int i = 255; i >= 0; --i) {
+        acc = fe_sqr<C>(acc);
+        if ((e.l[i >> 5] >> (i & 31)) & 1u) acc = fe_mul<C>(acc, a);
+    }
+    return acc;
+}
+
+// Fermat inverse a^(p-2); inv(0) = 0.
+template <class C>
+FF_HD fe fe_inv(const fe& a) {
+    fe e;
+    // p - 2 (p is odd and its low limb is >= 2, so no borrow)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e.l[i] = C::mod(i);
+    e.l[0] -= 2u;
+    return fe_pow<C>(a, e);
+}
+
+// small-integer constant in Montgomery form
+template <class C>
+FF_HD fe fe_from_u32(uint32_t v) {
+    fe x = fe_zero();
+    x.l[0] = v;
+    return fe_to_mont<C>(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit global-memory access: one element = two uint4 (one 32-byte sector)
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+FF_D fe fe_load(const fe* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = q[0], hi = q[1];
+    fe r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+FF_D fe fe_load_ro(const fe* p) {  // read-only path (twiddles, bases)
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    fe r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+FF_D void fe_store(fe* p, const fe& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+#endif
+
+}  // namespace b200

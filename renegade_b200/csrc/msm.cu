@@ -1,0 +1,561 @@
+// Pippenger multi-scalar multiplication on BN254 G1 for sm_100a.
+//
+// Replaces what the reference reaches through jf-primitives `UnivariateKzgPCS::commit` ->
+// ark-ec 0.4.2 `VariableBaseMSM::msm_bigint(&powers_of_g, &coeffs)` (call sites
+// /root/reference/crates/circuits/circuit-types/src/traits.rs:850,996 and
+// circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47; algorithm restated in
+// SURVEY.md App. B).  The result is a group element, so after affine normalisation it is
+// bit-identical to arkworks' whatever the bucket schedule.
+//
+// B200-first design (not arkworks' per-window rayon loop):
+//   * bases are fixed (the SRS), HBM is 180 GB: at load time every base gets its window
+//     multiples 2^(c*j)*P precomputed, so ALL windows share ONE bucket set — no per-window
+//     reduction, no Horner doublings on the device; the tables are gathered at 64 B/point
+//     (two full sectors), well inside the HBM budget of an integer-pipe-bound kernel;
+//   * signed c-bit digits halve the bucket count;
+//   * digits are counting-sorted by bucket (histogram -> scan -> scatter, L2-resident atomics),
+//     then one thread per bucket folds its points with XYZZ mixed additions (8M+2S, no
+//     inversion), prefetching the next 64-byte point while the current addition runs;
+//   * bucket sums are folded with a chunked running sum + block tree; the last few hundred
+//     bytes go to the host, which does the final Horner (only when windows are not fully
+//     precomputed) and the single field inversion.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "device_ctx.h"
+#include "ec.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr uint32_t kIdxBits = 26;  // entry = sign(1) | table(5) | point index(26)
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+constexpr int kReduceChunk = 16;   // buckets per thread in the running-sum reduction
+constexpr int kReduceThreads = 128;
+
+// ---- scalar digits ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t get_bits(const uint32_t* s, int pos, int c) {
+    const int limb = pos >> 5, off = pos & 31;
+    uint32_t v = limb < 8 ? s[limb] >> off : 0u;
+    if (off + c > 32 && limb + 1 < 8) v |= s[limb + 1] << (32 - off);
+    return v & ((1u << c) - 1u);
+}
+
+// Calls f(bucket, code) for every non-zero signed digit of scalar i.
+template <class F>
+__device__ __forceinline__ void for_each_digit(const fe* scalars, size_t i, int montgomery,
+                                               const MsmPlan& pl, uint32_t point_idx, F f) {
+    fe s = fe_load_ro(scalars + i);
+    if (montgomery) s = fe_from_mont<FrCfg>(s);
+    uint32_t limbs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) limbs[k] = s.l[k];
+    const uint32_t half = 1u << (pl.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < pl.n_digits; ++w) {
+        uint32_t raw = get_bits(limbs, w * pl.c, pl.c) + carry;
+        uint32_t neg = 0, mag = raw;
+        if (raw > half) {  // digit = raw - 2^c  (magnitude 2^c - raw, possibly 0 when raw = 2^c)
+            mag = (1u << pl.c) - raw;
+            neg = 1;
+            carry = 1;
+        } else {
+            carry = 0;
+        }
+        if (mag == 0) continue;
+        const uint32_t phys = (uint32_t)(w % pl.n_phys), table = (uint32_t)(w / pl.n_phys);
+        const uint32_t bucket = phys * half + (mag - 1u);
+        f(bucket, (neg << 31) | (table << kIdxBits) | point_idx);
+    }
+}
+
+__global__ void msm_count_kernel(const fe* scalars, size_t n, int montgomery, MsmPlan pl,
+                                 uint32_t* counts) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for_each_digit(scalars, i, montgomery, pl, (uint32_t)i,
+                   [&](uint32_t bucket, uint32_t) { atomicAdd(counts + bucket, 1u); });
+}
+
+__global__ void msm_scatter_kernel(const fe* scalars, size_t n, int montgomery, MsmPlan pl,
+                                   uint32_t base_off, uint32_t* cursor, uint32_t* entries) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for_each_digit(scalars, i, montgomery, pl, (uint32_t)i + base_off,
+                   [&](uint32_t bucket, uint32_t code) {
+                       const uint32_t pos = atomicAdd(cursor + bucket, 1u);
+                       entries[pos] = code;
+                   });
+}
+
+// ---- exclusive scan of the bucket histogram (three small kernels) -----------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < kScanThreads / 32 ? warp_sums[lane] : 0u;
+        uint32_t wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = wi - ws;  // exclusive warp offsets
+        if (lane == kScanThreads / 32 - 1) *total = wi;
+    }
+    __syncthreads();
+    const uint32_t r = incl - v + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+
+__global__ void scan_chunk_sums_kernel(const uint32_t* in, size_t n, uint32_t* chunk_sums) {
+    __shared__ uint32_t total;
+    const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n) s += in[base + k];
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+
+__global__ void scan_chunk_offsets_kernel(uint32_t* chunk_sums, size_t n_chunks) {
+    // single block; serial over tiles of kScanThreads chunks
+    __shared__ uint32_t total;
+    uint32_t running = 0;
+    for (size_t base = 0; base < n_chunks; base += kScanThreads) {
+        const size_t i = base + threadIdx.x;
+        const uint32_t v = i < n_chunks ? chunk_sums[i] : 0u;
+        const uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < n_chunks) chunk_sums[i] = running + ex;
+        running += total;
+        __syncthreads();
+    }
+}
+
+__global__ void scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* chunk_offsets,
+                                  uint32_t* out /* n + 1 */) {
+    __shared__ uint32_t total;
+    const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan(s, &total) + chunk_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+        if (base + k == n - 1) out[n] = ex;
+    }
+}
+
+// ---- bucket accumulation: one thread per bucket ------------------------------------------------
+__device__ __forceinline__ g1_affine load_entry_point(const g1_affine* tables, size_t n,
+                                                      uint32_t code) {
+    const size_t idx = code & kIdxMask, table = (code >> kIdxBits) & 31u;
+    return g1_affine_load_ro(tables + table * n + idx);
+}
+
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ entries,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const g1_affine* __restrict__ tables,
+                                                             size_t n_points, uint32_t n_buckets,
+                                                             g1_xyzz* __restrict__ buckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t e = offsets[b];
+    const uint32_t end = offsets[b + 1];
+    g1_xyzz acc = g1_xyzz_inf();
+    if (e < end) {
+        uint32_t code = entries[e];
+        g1_affine next = load_entry_point(tables, n_points, code);
+        while (true) {
+            g1_affine cur = next;
+            const uint32_t cur_code = code;
+            ++e;
+            if (e < end) {  // prefetch the next point under the current addition
+                code = entries[e];
+                next = load_entry_point(tables, n_points, code);
+            }
+            if (cur_code >> 31) cur.y = fe_neg<FqCfg>(cur.y);
+            acc = g1_add_mixed(acc, cur);
+            if (e >= end) break;
+        }
+    }
+    g1_xyzz_store(buckets + b, acc);
+}
+
+// ---- bucket reduction: sum_k (k+1) * B[k] per physical window -----------------------------------
+// thread t owns buckets [t*K, (t+1)*K): running sum gives A = sum (i+1) B[tK+i] and S = sum B;
+// its contribution is A + (tK) * S.  Contributions are tree-added in shared memory per block.
+__global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyzz* __restrict__ buckets,
+                                                                    uint32_t buckets_per_window,
+                                                                    int c,
+                                                                    g1_xyzz* __restrict__ partials) {
+    __shared__ g1_xyzz sh[kReduceThreads];
+    const uint32_t window = blockIdx.y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t first = t * kReduceChunk;
+    g1_xyzz contrib = g1_xyzz_inf();
+    if (first < buckets_per_window) {
+        const g1_xyzz* B = buckets + (size_t)window * buckets_per_window + first;
+        const uint32_t cnt = min((uint32_t)kReduceChunk, buckets_per_window - first);
+        g1_xyzz run = g1_xyzz_inf(), acc = g1_xyzz_inf();
+        for (int i = (int)cnt - 1; i >= 0; --i) {
+            run = g1_add(run, g1_xyzz_load(B + i));
+            acc = g1_add(acc, run);
+        }
+        // (first) * run by double-and-add; first < 2^(c-1)
+        g1_xyzz scaled = g1_xyzz_inf();
+        for (int bit = c - 2; bit >= 0; --bit) {
+            scaled = g1_dbl(scaled);
+            if ((first >> bit) & 1u) scaled = g1_add(scaled, run);
+        }
+        contrib = g1_add(acc, scaled);
+    }
+    sh[threadIdx.x] = contrib;
+    __syncthreads();
+    for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) sh[threadIdx.x] = g1_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) g1_xyzz_store(partials + (size_t)window * gridDim.x + blockIdx.x, sh[0]);
+}
+
+__global__ void __launch_bounds__(kReduceThreads) msm_reduce_final_kernel(const g1_xyzz* __restrict__ partials,
+                                                                          uint32_t n_partials,
+                                                                          g1_xyzz* __restrict__ window_sums) {
+    __shared__ g1_xyzz sh[kReduceThreads];
+    const uint32_t window = blockIdx.x;
+    g1_xyzz acc = g1_xyzz_inf();
+    for (uint32_t i = threadIdx.x; i < n_partials; i += blockDim.x)
+        acc = g1_add(acc, g1_xyzz_load(partials + (size_t)window * n_partials + i));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) sh[threadIdx.x] = g1_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) g1_xyzz_store(window_sums + window, sh[0]);
+}
+
+// ---- window tables: table[j][i] = 2^(shift*j) * P_i (affine) -------------------------------------
+__global__ void msm_table_kernel(const g1_affine* __restrict__ prev, g1_affine* __restrict__ next,
+                                 size_t n, int shift) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const g1_affine p = g1_affine_load_ro(prev + i);
+    g1_xyzz a = g1_dbl_affine(p);
+    for (int k = 1; k < shift; ++k) a = g1_dbl(a);
+    g1_affine_store(next + i, g1_to_affine(a));
+}
+
+__global__ void g1_on_curve_kernel(const g1_affine* pts, size_t n, uint32_t* bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!g1_affine_on_curve(g1_affine_load_ro(pts + i))) atomicAdd(bad, 1u);
+}
+
+// ---- synthetic inputs: SplitMix64 field elements, known-dlog bases ---------------
+__device__ __forceinline__ uint64_t splitmix_at(uint64_t seed, uint64_t j) {
+    uint64_t z = seed + (j + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ fe splitmix_fr_canon(uint64_t seed, uint64_t i) {
+    fe v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t x = splitmix_at(seed, 4 * i + k);
+        v.l[2 * k] = (uint32_t)x;
+        v.l[2 * k + 1] = (uint32_t)(x >> 32);
+    }
+    // 2^256 / r < 6: a few conditional subtractions reduce mod r
+    for (int it = 0; it < 6; ++it) {
+        bool ge = true;
+        for (int k = 7; k >= 0; --k) {
+            if (v.l[k] != FrCfg::mod(k)) { ge = v.l[k] > FrCfg::mod(k); break; }
+        }
+        if (!ge) break;
+        uint64_t borrow = 0;
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t d = (uint64_t)v.l[k] - FrCfg::mod(k) - borrow;
+            v.l[k] = (uint32_t)d;
+            borrow = (d >> 32) & 1u;
+        }
+    }
+    return v;
+}
+__global__ void splitmix_fr_kernel(uint64_t seed, size_t first, size_t n, int montgomery, fe* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe v = splitmix_fr_canon(seed, first + i);
+    if (montgomery) v = fe_to_mont<FrCfg>(v);
+    fe_store(out + i, v);
+}
+__global__ void known_dlog_bases_kernel(uint64_t seed, size_t first, size_t n, g1_affine* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe a = splitmix_fr_canon(seed, first + i);
+    g1_affine g;
+    g.x = fe_one<FqCfg>();
+    g.y = fe_from_u32<FqCfg>(2);
+    g1_affine_store(out + i, g1_to_affine(g1_mul_bits(g, a, 254)));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
+    MsmPlan best;
+    double best_cost = 1e300;
+    const int c_lo = c_override > 0 ? c_override : 6, c_hi = c_override > 0 ? c_override : 23;
+    for (int c = c_lo; c <= c_hi; ++c) {
+        const int W = (255 + c - 1) / c;
+        if (W > 32) continue;
+        // adds in the bucket phase + (full adds, poorly parallel) in the reduction
+        const double cost = (double)n * W + 4.0 * (double)((size_t)1 << (c - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best.c = c;
+            best.n_digits = W;
+        }
+    }
+    // full precompute (one physical window) unless the tables exceed the memory budget;
+    // B200_MSM_PHYS_WINDOWS forces a split (tuning / test knob for the host Horner path)
+    int phys = 1;
+    if (const char* env = std::getenv("B200_MSM_PHYS_WINDOWS")) {
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= best.n_digits) phys = v;
+    }
+    while (true) {
+        const int tables = (best.n_digits + phys - 1) / phys;
+        if ((double)tables * (double)n * 64.0 <= (double)mem_budget_bytes || phys >= best.n_digits) {
+            best.n_phys = phys;
+            best.n_tables = tables;
+            break;
+        }
+        ++phys;
+    }
+    return best;
+}
+
+static int build_tables(Bases* b, cudaStream_t st) {
+    const int shift = b->plan.c * b->plan.n_phys;
+    const unsigned bs = 128;
+    const unsigned grid = (unsigned)((b->n + bs - 1) / bs);
+    for (int j = 1; j < b->plan.n_tables; ++j) {
+        msm_table_kernel<<<grid, bs, 0, st>>>(b->tables + (size_t)(j - 1) * b->n,
+                                              b->tables + (size_t)j * b->n, b->n, shift);
+    }
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+static size_t table_mem_budget() {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)8 << 30;
+    return free_b / 2;
+}
+
+int bases_create_device(const g1_affine* d_points, size_t n, int c_override, cudaStream_t st,
+                        Bases** out) {
+    if (n == 0 || n > ((size_t)1 << kIdxBits)) {
+        set_error("bases: n must be in [1, 2^26]");
+        return B200_ERR_INVALID;
+    }
+    Bases* b = new Bases();
+    b->n = n;
+    b->plan = msm_choose_plan(n, c_override, table_mem_budget());
+    cudaError_t e = cudaMalloc(&b->tables, (size_t)b->plan.n_tables * n * sizeof(g1_affine));
+    if (e != cudaSuccess) {
+        delete b;
+        return cuda_fail(e, "cudaMalloc(window tables)");
+    }
+    e = cudaMemcpyAsync(b->tables, d_points, n * sizeof(g1_affine), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+        delete b;
+        return cuda_fail(e, "cudaMemcpyAsync(bases)");
+    }
+    int rc = build_tables(b, st);
+    if (rc != B200_OK) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return B200_OK;
+}
+
+int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_on_curve,
+                 cudaStream_t st, Bases** out) {
+    if (n == 0 || n > ((size_t)1 << kIdxBits)) {
+        set_error("bases: n must be in [1, 2^26]");
+        return B200_ERR_INVALID;
+    }
+    g1_affine* d_pts = nullptr;
+    B200_CUDA(cudaMalloc(&d_pts, n * sizeof(g1_affine)));
+    cudaError_t e = cudaMemcpyAsync(d_pts, h_points, n * sizeof(g1_affine), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+        cudaFree(d_pts);
+        return cuda_fail(e, "cudaMemcpyAsync(bases H2D)");
+    }
+    if (check_on_curve) {  // srs.rs:178-179 asserts every SRS point is on the curve
+        uint32_t* d_bad = nullptr;
+        uint32_t h_bad = 0;
+        cudaMalloc(&d_bad, 4);
+        cudaMemsetAsync(d_bad, 0, 4, st);
+        g1_on_curve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pts, n, d_bad);
+        cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        cudaFree(d_bad);
+        if (e != cudaSuccess) {
+            cudaFree(d_pts);
+            return cuda_fail(e, "on-curve check");
+        }
+        if (h_bad) {
+            cudaFree(d_pts);
+            set_error("point not on curve");
+            return B200_ERR_NOT_ON_CURVE;
+        }
+    }
+    int rc = bases_create_device(d_pts, n, c_override, st, out);
+    cudaFree(d_pts);
+    return rc;
+}
+
+static int exclusive_scan_u32(const uint32_t* d_in, size_t n, uint32_t* d_out, DevBuf* chunk_buf,
+                              cudaStream_t st) {
+    const size_t n_chunks = (n + kScanChunk - 1) / kScanChunk;
+    int rc = chunk_buf->reserve(n_chunks * sizeof(uint32_t));
+    if (rc != B200_OK) return rc;
+    uint32_t* chunk = (uint32_t*)chunk_buf->p;
+    scan_chunk_sums_kernel<<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk);
+    scan_chunk_offsets_kernel<<<1, kScanThreads, 0, st>>>(chunk, n_chunks);
+    scan_apply_kernel<<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk, d_out);
+    return B200_OK;
+}
+
+int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, int montgomery,
+               MsmScratch* s, cudaStream_t st, g1_affine* out, int* out_inf) {
+    if (base_off + n > b->n) {
+        set_error("msm: base_off + n exceeds the loaded bases");
+        return B200_ERR_INVALID;
+    }
+    if (n == 0) {
+        out->x = fe_zero();
+        out->y = fe_zero();
+        if (out_inf) *out_inf = 1;
+        return B200_OK;
+    }
+    const MsmPlan& pl = b->plan;
+    const uint32_t half = 1u << (pl.c - 1);
+    const size_t n_buckets = (size_t)pl.n_phys * half;
+    const size_t max_entries = n * (size_t)pl.n_digits;
+    if (max_entries >= ((size_t)1 << 32)) {
+        set_error("msm: n * windows exceeds 2^32 entries");
+        return B200_ERR_INVALID;
+    }
+    int rc;
+    if ((rc = s->counts.reserve(n_buckets * 4)) != B200_OK) return rc;
+    if ((rc = s->offsets.reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
+    if ((rc = s->cursor.reserve(n_buckets * 4)) != B200_OK) return rc;
+    if ((rc = s->entries.reserve(max_entries * 4)) != B200_OK) return rc;
+    if ((rc = s->buckets.reserve(n_buckets * sizeof(g1_xyzz))) != B200_OK) return rc;
+    const uint32_t reduce_threads_needed = (half + kReduceChunk - 1) / kReduceChunk;
+    const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
+    if ((rc = s->partials.reserve((size_t)pl.n_phys * reduce_blocks * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->window_sums.reserve((size_t)pl.n_phys * sizeof(g1_xyzz))) != B200_OK) return rc;
+
+    uint32_t* counts = (uint32_t*)s->counts.p;
+    uint32_t* offsets = (uint32_t*)s->offsets.p;
+    uint32_t* cursor = (uint32_t*)s->cursor.p;
+    uint32_t* entries = (uint32_t*)s->entries.p;
+    g1_xyzz* buckets = (g1_xyzz*)s->buckets.p;
+    g1_xyzz* partials = (g1_xyzz*)s->partials.p;
+    g1_xyzz* window_sums = (g1_xyzz*)s->window_sums.p;
+
+    if (s->timing && !s->ev_init) {
+        for (auto& e : s->ev) B200_CUDA(cudaEventCreate(&e));
+        s->ev_init = true;
+    }
+    if (s->timing) cudaEventRecord(s->ev[0], st);
+    B200_CUDA(cudaMemsetAsync(counts, 0, n_buckets * 4, st));
+    const unsigned bs = 256;
+    const unsigned grid_n = (unsigned)((n + bs - 1) / bs);
+    msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, montgomery, pl, counts);
+    if ((rc = exclusive_scan_u32(counts, n_buckets, offsets, &s->block_sums, st)) != B200_OK) return rc;
+    B200_CUDA(cudaMemcpyAsync(cursor, offsets, n_buckets * 4, cudaMemcpyDeviceToDevice, st));
+    msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, montgomery, pl, (uint32_t)base_off, cursor, entries);
+    if (s->timing) cudaEventRecord(s->ev[1], st);
+    msm_accumulate_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
+        entries, offsets, b->tables, b->n, (uint32_t)n_buckets, buckets);
+    if (s->timing) cudaEventRecord(s->ev[2], st);
+    msm_reduce_kernel<<<dim3(reduce_blocks, pl.n_phys), kReduceThreads, 0, st>>>(buckets, half, pl.c, partials);
+    msm_reduce_final_kernel<<<pl.n_phys, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);
+    B200_CUDA(cudaGetLastError());
+
+    std::vector<g1_xyzz> h_sums(pl.n_phys);
+    if (s->timing) cudaEventRecord(s->ev[3], st);
+    B200_CUDA(cudaMemcpyAsync(h_sums.data(), window_sums, (size_t)pl.n_phys * sizeof(g1_xyzz),
+                              cudaMemcpyDeviceToHost, st));
+    if (s->timing) cudaEventRecord(s->ev[4], st);
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (s->timing) {
+        cudaEventElapsedTime(&s->ms[0], s->ev[0], s->ev[4]);
+        cudaEventElapsedTime(&s->ms[1], s->ev[0], s->ev[1]);
+        cudaEventElapsedTime(&s->ms[2], s->ev[1], s->ev[2]);
+        cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
+    }
+
+    // host epilogue: Horner over the physical windows (none when fully precomputed) and the one
+    // field inversion of the affine normalisation — a few hundred bytes of work.
+    g1_xyzz total = h_sums[pl.n_phys - 1];
+    for (int p = pl.n_phys - 2; p >= 0; --p) {
+        for (int k = 0; k < pl.c; ++k) total = g1_dbl(total);
+        total = g1_add(total, h_sums[p]);
+    }
+    *out = g1_to_affine(total);
+    if (out_inf) *out_inf = g1_xyzz_is_inf(total) ? 1 : 0;
+    return B200_OK;
+}
+
+int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
+                               cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    known_dlog_bases_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, first, n, d_out);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+int splitmix_fr_device(uint64_t seed, size_t first, size_t n, int montgomery, fe* d_out,
+                       cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    splitmix_fr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, first, n, montgomery, d_out);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+}  // namespace b200

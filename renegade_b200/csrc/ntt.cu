@@ -1,0 +1,263 @@
+// Radix-2 NTT / iNTT over the BN254 scalar field for sm_100a.
+//
+// Replaces what the reference reaches through ark-poly 0.4.2
+// `Radix2EvaluationDomain::<Fr>::{fft, ifft, coset_fft, coset_ifft}` (called from the upstream
+// prover behind /root/reference/crates/circuits/circuit-types/src/traits.rs:850,996; semantics
+// restated in SURVEY.md App. B): natural order in, natural order out, ifft scales by n^-1,
+// coset shift g = Fr::GENERATOR = 5.  Outputs are canonical field elements, so a correct NTT
+// is bit-identical to arkworks'.
+//
+// Structure (B200-first, not a translation of arkworks' recursive CPU FFT):
+//   * decimation-in-frequency, log n stages grouped into ceil(log n / 10) passes; a pass keeps
+//     a tile of 1024 elements (32 KB, two 128-bit planes to stay bank-conflict free) in shared
+//     memory, so HBM sees one read + one write of the vector per pass;
+//   * one element is one 32-byte sector, so the strided tile gathers of the upper passes and
+//     the bit-reversed scatter of the last pass are all full-sector transactions;
+//   * twiddles come from an L2-resident table (n/2 elements per direction); coset scaling and
+//     the n^-1 factor are fused into the first load / last store.
+// The kernel is bound by the integer-multiply pipe (≈ log2(n)/2 Montgomery products per
+// element), not by HBM: see DESIGN.md for the roofline.
+#include "device_ctx.h"
+#include "ff.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kTileLog = 10;  // 1024 elements = 32 KB of shared memory per block
+
+struct PassArgs {
+    const fe* in;
+    fe* out;
+    const fe* tw;     // w^k, k < n/2 (forward or inverse roots)
+    const fe* pre;    // optional per-input-index factor (coset_fft: g^i)
+    const fe* post;   // optional per-output-index factor (coset_ifft: g^-i * n^-1)
+    fe post_scalar;   // used when has_post_scalar (ifft: n^-1)
+    int has_post_scalar;
+    int log_n, lo, hi;  // this pass runs butterfly stages hi-1 .. lo
+    int e_log;          // tile = 2^e_log elements
+    size_t batch_stride;  // elements between consecutive transforms of a batch
+};
+
+template <bool FINAL>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
+    extern __shared__ uint4 smem[];
+    const int E = 1 << a.e_log;
+    uint4* plane_lo = smem;
+    uint4* plane_hi = smem + E;
+
+    const int t_log = a.hi - a.lo;    // sub-transform size 2^t_log
+    const int q_log = a.e_log - t_log;  // sub-transforms per tile
+    const uint32_t T_mask = (1u << t_log) - 1u;
+    const uint32_t Q_mask = (1u << q_log) - 1u;
+    const uint32_t lo_mask = (1u << a.lo) - 1u;
+    const uint32_t q_base = blockIdx.x << q_log;
+    const fe* in = a.in + (size_t)blockIdx.y * a.batch_stride;
+    fe* out = a.out + (size_t)blockIdx.y * a.batch_stride;
+
+    // ---- gather the tile -------------------------------------------------------------------
+    for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
+        uint32_t qq, m;
+        if (a.lo == 0) { qq = e >> t_log; m = e & T_mask; }   // idx = q*T + m : contiguous in e
+        else           { m = e >> q_log; qq = e & Q_mask; }   // adjacent sub-transforms adjacent
+        const uint32_t q = q_base + qq;
+        const size_t idx = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & lo_mask);
+        fe v = fe_load(in + idx);
+        if (a.pre) v = fe_mul<FrCfg>(v, fe_load_ro(a.pre + idx));
+        const uint32_t pos = (m << q_log) | qq;
+        plane_lo[pos] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        plane_hi[pos] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+    __syncthreads();
+
+    // ---- butterflies: (x0, x1) -> (x0 + x1, (x0 - x1) * w^(j * n / 2^(s+1))) ----------------
+    for (int sp = t_log - 1; sp >= 0; --sp) {
+        const int s = a.lo + sp;
+        const uint32_t sp_mask = (1u << sp) - 1u;
+        for (uint32_t t = threadIdx.x; t < (uint32_t)(E >> 1); t += blockDim.x) {
+            const uint32_t qq = t & Q_mask;
+            const uint32_t r = t >> q_log;
+            const uint32_t m0 = ((r >> sp) << (sp + 1)) | (r & sp_mask);
+            const uint32_t m1 = m0 + (1u << sp);
+            const uint32_t p0 = (m0 << q_log) | qq, p1 = (m1 << q_log) | qq;
+            const uint32_t lw = (q_base + qq) & lo_mask;
+            const size_t j = ((size_t)(m0 & sp_mask) << a.lo) | lw;
+            const size_t k = j << (a.log_n - s - 1);
+            const fe w = fe_load_ro(a.tw + k);
+            fe x0, x1;
+            uint4 u = plane_lo[p0], v = plane_hi[p0];
+            x0.l[0] = u.x; x0.l[1] = u.y; x0.l[2] = u.z; x0.l[3] = u.w;
+            x0.l[4] = v.x; x0.l[5] = v.y; x0.l[6] = v.z; x0.l[7] = v.w;
+            u = plane_lo[p1]; v = plane_hi[p1];
+            x1.l[0] = u.x; x1.l[1] = u.y; x1.l[2] = u.z; x1.l[3] = u.w;
+            x1.l[4] = v.x; x1.l[5] = v.y; x1.l[6] = v.z; x1.l[7] = v.w;
+            const fe y0 = fe_add<FrCfg>(x0, x1);
+            const fe y1 = fe_mul<FrCfg>(fe_sub<FrCfg>(x0, x1), w);
+            plane_lo[p0] = make_uint4(y0.l[0], y0.l[1], y0.l[2], y0.l[3]);
+            plane_hi[p0] = make_uint4(y0.l[4], y0.l[5], y0.l[6], y0.l[7]);
+            plane_lo[p1] = make_uint4(y1.l[0], y1.l[1], y1.l[2], y1.l[3]);
+            plane_hi[p1] = make_uint4(y1.l[4], y1.l[5], y1.l[6], y1.l[7]);
+        }
+        __syncthreads();
+    }
+
+    // ---- scatter: same index for inner passes, bit-reversed index after the last stage ------
+    for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
+        uint32_t qq, m;
+        if (a.lo == 0) { qq = e >> t_log; m = e & T_mask; }
+        else           { m = e >> q_log; qq = e & Q_mask; }
+        const uint32_t q = q_base + qq;
+        const size_t idx = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & lo_mask);
+        const uint32_t pos = (m << q_log) | qq;
+        const uint4 u = plane_lo[pos], v = plane_hi[pos];
+        fe y;
+        y.l[0] = u.x; y.l[1] = u.y; y.l[2] = u.z; y.l[3] = u.w;
+        y.l[4] = v.x; y.l[5] = v.y; y.l[6] = v.z; y.l[7] = v.w;
+        size_t oi = idx;
+        if (FINAL) {
+            // bit-reverse over log_n bits (log_n <= 32 handled with 64-bit brev)
+            oi = (size_t)(__brevll((unsigned long long)idx) >> (64 - a.log_n));
+            if (a.post) y = fe_mul<FrCfg>(y, fe_load_ro(a.post + oi));
+            else if (a.has_post_scalar) y = fe_mul<FrCfg>(y, a.post_scalar);
+        }
+        fe_store(out + oi, y);
+    }
+}
+
+// table[i] = base^i (Montgomery), i < n: thread i multiplies the pow2[b] = base^(2^b) it needs
+struct PowArgs {
+    fe pow2[32];
+    fe scale;  // every entry is multiplied by this (Montgomery one, or n^-1)
+};
+__global__ void powers_kernel(fe* out, size_t n, PowArgs p) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe acc = p.scale;
+    for (int b = 0; b < 32; ++b)
+        if ((i >> b) & 1) acc = fe_mul<FrCfg>(acc, p.pow2[b]);
+    fe_store(out + i, acc);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static fe host_root_of_unity(unsigned log_n) {
+    // TWO_ADIC_ROOT_OF_UNITY = 5^((r-1)/2^28); squared down to order 2^log_n
+    fe c;
+    const uint32_t canon[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu,
+                               0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+    for (int i = 0; i < 8; ++i) c.l[i] = canon[i];
+    fe w = fe_to_mont<FrCfg>(c);
+    for (unsigned i = log_n; i < 28; ++i) w = fe_sqr<FrCfg>(w);
+    return w;
+}
+
+static void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st) {
+    PowArgs p;
+    p.scale = scale;
+    fe b = base;
+    for (int i = 0; i < 32; ++i) {
+        p.pow2[i] = b;
+        b = fe_sqr<FrCfg>(b);
+    }
+    if (n == 0) return;
+    const unsigned bs = 256;
+    powers_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(d_out, n, p);
+}
+
+Domain::~Domain() {
+    cudaFree(tw_fwd);
+    cudaFree(tw_inv);
+    cudaFree(coset_fwd);
+    cudaFree(coset_inv);
+}
+
+int domain_create(unsigned log_n, cudaStream_t st, Domain** out) {
+    if (log_n > 28) return B200_ERR_INVALID;
+    Domain* d = new Domain();
+    d->log_n = log_n;
+    const size_t n = (size_t)1 << log_n;
+    const size_t half = n > 1 ? n / 2 : 1;
+    if (cudaMalloc(&d->tw_fwd, half * sizeof(fe)) != cudaSuccess ||
+        cudaMalloc(&d->tw_inv, half * sizeof(fe)) != cudaSuccess ||
+        cudaMalloc(&d->coset_fwd, n * sizeof(fe)) != cudaSuccess ||
+        cudaMalloc(&d->coset_inv, n * sizeof(fe)) != cudaSuccess) {
+        delete d;
+        return B200_ERR_CUDA;
+    }
+    const fe one = fe_one<FrCfg>();
+    const fe w = host_root_of_unity(log_n);
+    const fe w_inv = fe_inv<FrCfg>(w);
+    fe nn = fe_zero();
+    nn.l[0] = (uint32_t)(n & 0xffffffffu);
+    nn.l[1] = (uint32_t)(n >> 32);
+    d->n_inv = fe_inv<FrCfg>(fe_to_mont<FrCfg>(nn));
+    const fe g = fe_from_u32<FrCfg>(5);  // Fr::GENERATOR
+    const fe g_inv = fe_inv<FrCfg>(g);
+    fill_powers(d->tw_fwd, half, w, one, st);
+    fill_powers(d->tw_inv, half, w_inv, one, st);
+    fill_powers(d->coset_fwd, n, g, one, st);
+    fill_powers(d->coset_inv, n, g_inv, d->n_inv, st);
+    d->group_gen = w;
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        delete d;
+        return B200_ERR_CUDA;
+    }
+    *out = d;
+    return B200_OK;
+}
+
+// data: batch transforms of n elements, `stride` elements apart, transformed in place.
+// scratch: at least (batch-1)*stride + n elements when log_n > kTileLog.
+int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, unsigned batch,
+               size_t stride, cudaStream_t st) {
+    const int L = (int)d->log_n;
+    if (L == 0 || batch == 0) return B200_OK;  // size-1 transform is the identity (n^-1 = 1)
+    const int P = (L + kTileLog - 1) / kTileLog;
+    const int e_log = L < kTileLog ? L : kTileLog;
+    const int base = L / P, extra = L % P;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10);
+        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10);
+        attr_set = true;
+    }
+    int hi = L;
+    for (int p = 0; p < P; ++p) {
+        const int w = base + (p < extra ? 1 : 0);
+        PassArgs a;
+        a.log_n = L;
+        a.hi = hi;
+        a.lo = hi - w;
+        a.e_log = e_log;
+        a.tw = inverse ? d->tw_inv : d->tw_fwd;
+        a.pre = (p == 0 && coset && !inverse) ? d->coset_fwd : nullptr;
+        a.post = nullptr;
+        a.has_post_scalar = 0;
+        a.post_scalar = d->n_inv;
+        a.batch_stride = stride;
+        const bool final_pass = (p == P - 1);
+        // inner passes run in place; the pass before the last writes to scratch so that the last
+        // (bit-reversing, hence out-of-place) pass lands back in `data`.  A single-pass transform
+        // fits one block, which reads its whole tile before writing, so it is in place too.
+        a.in = (P > 1 && final_pass) ? scratch : data;
+        a.out = (P > 1 && p == P - 2) ? scratch : data;
+        if (final_pass && inverse) {
+            if (coset) a.post = d->coset_inv;
+            else a.has_post_scalar = 1;
+        }
+        const unsigned E = 1u << e_log;
+        unsigned threads = E / 2 < 256 ? E / 2 : 256;
+        if (threads < 32) threads = 32;
+        dim3 grid((unsigned)(((size_t)1 << L) >> e_log), batch);
+        const size_t smem = (size_t)E * 32;
+        if (final_pass) ntt_pass_kernel<true><<<grid, threads, smem, st>>>(a);
+        else ntt_pass_kernel<false><<<grid, threads, smem, st>>>(a);
+        hi -= w;
+    }
+    return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+}  // namespace b200

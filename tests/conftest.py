@@ -1,0 +1,48 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The C restatement (test infrastructure)."""
+    import oracle_c
+    oracle_c.build()
+    return oracle_c
+
+
+@pytest.fixture(scope="session")
+def pyoracle():
+    import bn254_py
+    return bn254_py
+
+
+@pytest.fixture(scope="session")
+def kat():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "kat.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def srs_head():
+    with open(os.path.join(ROOT, "tests", "golden", "srs_head.bin"), "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """GPU context; the extension must be present — no skipping to a CPU path."""
+    import renegade_b200 as rb
+    c = rb.Context(0)
+    yield c
+    c.close()

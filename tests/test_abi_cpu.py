@@ -1,0 +1,107 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/b200prover.h declares, fails loudly without a GPU (no CPU fallback), and its host-only
+entry points (ptau parsing, partial-sum combination) behave like the reference's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200prover.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_matches_binding_list():
+    from renegade_b200 import _lib
+    assert header_symbols() == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from renegade_b200 import _lib
+    lib = _lib.load()
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.b200_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the loud-failure path is the CPU container's")
+    import renegade_b200 as rb
+    from renegade_b200._lib import B200Error
+    with pytest.raises(B200Error) as ei:
+        rb.Context(0)
+    assert ei.value.code == -6 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under renegade_b200/ may import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "renegade_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                for bad in ("oracle_c", "bn254_py", "bn254_oracle", "liboracle", "orc_"):
+                    assert bad not in txt, (f, bad)
+
+
+def test_srs_parse_ptau_host(srs_head):
+    from renegade_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_char * len(srs_head)).from_buffer_copy(srs_head)
+    rec, n = C.c_void_p(), C.c_size_t()
+    rc = lib.b200_srs_parse_ptau(C.cast(buf, C.c_void_p), len(srs_head), C.byref(rec), C.byref(n))
+    assert rc == 0 and n.value == 512
+    assert rec.value - C.addressof(buf) == 80  # section 2 starts at byte 80
+    # error behaviour mirrors srs.rs:74-118 (assertions there, error codes here)
+    for mutate, msg in ((lambda b: b"xtau" + b[4:], "magic"),
+                        (lambda b: b[:4] + (2).to_bytes(4, "little") + b[8:], "version"),
+                        (lambda b: b[:8] + (10).to_bytes(4, "little") + b[12:], "sections"),
+                        (lambda b: b[:28] + b"\x01" + b[29:], "modulus")):
+        bad = mutate(srs_head)
+        bbuf = (C.c_char * len(bad)).from_buffer_copy(bad)
+        rc = lib.b200_srs_parse_ptau(C.cast(bbuf, C.c_void_p), len(bad), C.byref(rec), C.byref(n))
+        assert rc == -4, msg
+        assert msg in lib.b200_last_error().decode().lower()
+
+
+def test_g1_sum_affine_host(oracle, pyoracle):
+    """Host-side combination of per-GPU partial sums vs the oracle."""
+    from renegade_b200.sharded import combine_partials
+    py = pyoracle
+    pts = oracle.known_dlog_bases(0xABCD, 5)
+    rec = np.zeros((6, 9), dtype=np.uint64)
+    rec[:5, :8] = pts
+    rec[5, 8] = 1  # an identity partial
+    out, inf = combine_partials(None, rec)
+    a = py.splitmix_fr(0xABCD, 5)
+    assert not inf and py.decode_g1_mont(out.tobytes(), 0) == py.g1_mul(py.G1_GEN, sum(a) % py.R)
+    # P + (-P) = identity; P + P = 2P
+    neg = pts[0].copy()
+    neg[4:] = oracle.fp_binop("orc_fp_sub", oracle.FQ, np.zeros(4, dtype=np.uint64), pts[0, 4:])
+    rec2 = np.zeros((2, 9), dtype=np.uint64)
+    rec2[0, :8], rec2[1, :8] = pts[0], neg
+    out, inf = combine_partials(None, rec2)
+    assert inf and not out.any()
+    rec2[1, :8] = pts[0]
+    out, inf = combine_partials(None, rec2)
+    assert py.decode_g1_mont(out.tobytes(), 0) == py.g1_mul(py.G1_GEN, 2 * a[0] % py.R)
+
+
+def test_shard_range():
+    from renegade_b200.sharded import shard_range
+    for n in (0, 1, 7, 8, 1000, (1 << 17) + 3):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,155 @@
+"""GPU parity: Pippenger MSM through the C ABI vs the oracle (bit-exact after affine
+normalisation), golden known answers, the reference's SRS points, edge cases, and the
+known-discrete-log property at BASELINE.json's 2^20."""
+import numpy as np
+import pytest
+
+import renegade_b200 as rb
+
+pytestmark = pytest.mark.gpu
+
+
+def H(s):
+    return int(s, 16)
+
+
+def test_known_dlog_golden(ctx, oracle, pyoracle, kat):
+    py = pyoracle
+    for rec in kat["msm_known_dlog"]:
+        n = rec["n"]
+        bases = ctx.load_bases(oracle.known_dlog_bases(0xB200, n), check_on_curve=True)
+        scalars = oracle.splitmix_fr(0x5CA1A8, n, montgomery=False)
+        out, inf = rb.VariableBaseMSM.msm_bigint(ctx, bases, scalars)
+        assert not inf
+        assert py.decode_g1_mont(out.tobytes(), 0) == (H(rec["result"][0]), H(rec["result"][1]))
+
+
+@pytest.mark.parametrize("n,c", [(1, 0), (31, 0), (32, 8), (1000, 0), (1000, 9), (4099, 0), (4099, 13),
+                                 (1 << 14, 0), ((1 << 16) + 3, 0)])
+def test_msm_matches_oracle(ctx, oracle, n, c):
+    pts = oracle.known_dlog_bases(0xB200, n)
+    bases = ctx.load_bases(pts, window_bits=c)
+    s = oracle.splitmix_fr(0x5CA1A8, n, montgomery=False)
+    exp, einf = oracle.msm(pts, s)
+    out, inf = ctx.msm(bases, s, montgomery=False)
+    assert inf == einf and (out == exp).all()
+    # Montgomery scalars (what KZG commit is handed) give the same commitment
+    out2, inf2 = rb.UnivariateKzgPCS.commit(ctx, bases, oracle.array_to_mont(oracle.FR, s))
+    assert inf2 == einf and (out2 == exp).all()
+    # sub-range of the bases
+    if n > 40:
+        off, m = 17, n - 40
+        exp3, _ = oracle.msm(pts[off:off + m], s[:m])
+        out3, _ = ctx.msm(bases, s[:m], base_off=off)
+        assert (out3 == exp3).all()
+
+
+def test_msm_partial_precompute(ctx, oracle, monkeypatch):
+    """More than one physical window (tables not fully precomputed) exercises the host Horner."""
+    n = 2000
+    pts = oracle.known_dlog_bases(0xB200, n)
+    s = oracle.splitmix_fr(0x5CA1A8, n, montgomery=False)
+    exp, _ = oracle.msm(pts, s)
+    import os
+    for phys in ("2", "5"):
+        monkeypatch.setenv("B200_MSM_PHYS_WINDOWS", phys)
+        bases = ctx.load_bases(pts, window_bits=10)
+        assert bases.plan["physical_windows"] == int(phys)
+        out, _ = ctx.msm(bases, s)
+        assert (out == exp).all()
+
+
+def test_msm_on_reference_srs_points(ctx, oracle, pyoracle, kat, srs_head):
+    py = pyoracle
+    params_pts = np.frombuffer(srs_head[80:], dtype=np.uint64).reshape(-1, 8)
+    bases = ctx.load_bases(params_pts, check_on_curve=True)  # srs.rs:178-179 on the device
+    s16 = oracle.ints_to_array([H(v) for v in kat["msm_srs16"]["scalars"]])
+    out, inf = ctx.msm(bases, s16)
+    exp = kat["msm_srs16"]["result"]
+    assert py.decode_g1_mont(out.tobytes(), 0) == (H(exp[0]), H(exp[1]))
+    s = oracle.splitmix_fr(0xFEED, 512, montgomery=False)
+    exp_full, _ = oracle.msm(params_pts, s)
+    out, _ = ctx.msm(bases, s)
+    assert (out == exp_full).all()
+
+
+def test_on_curve_check_rejects(ctx, srs_head):
+    from renegade_b200._lib import B200Error
+    pts = np.frombuffer(srs_head[80:80 + 64 * 64], dtype=np.uint64).reshape(-1, 8).copy()
+    pts[7, 0] ^= np.uint64(1)
+    with pytest.raises(B200Error) as ei:
+        ctx.load_bases(pts, check_on_curve=True)
+    assert ei.value.code == -5 and "not on curve" in str(ei.value)
+
+
+def test_msm_edge_cases(ctx, oracle, pyoracle):
+    py = pyoracle
+    n = 300
+    pts = oracle.known_dlog_bases(0xB200, n)
+    bases = ctx.load_bases(pts)
+    # all-zero scalars -> identity
+    out, inf = ctx.msm(bases, np.zeros((n, 4), dtype=np.uint64))
+    assert inf and not out.any()
+    # empty MSM -> identity
+    out, inf = ctx.msm(bases, np.zeros((0, 4), dtype=np.uint64))
+    assert inf
+    # scalar r-1 everywhere, scalar 1 everywhere
+    for v in (py.R - 1, 1, 2, (1 << 253) + 12345):
+        s = oracle.ints_to_array([v] * n)
+        exp, einf = oracle.msm(pts, s)
+        out, inf = ctx.msm(bases, s)
+        assert inf == einf and (out == exp).all(), hex(v)
+    # duplicate points: same bucket gets P twice (doubling inside the mixed add) and P, -P
+    dup = np.repeat(pts[:3], 4, axis=0)
+    bd = ctx.load_bases(dup)
+    s = oracle.ints_to_array([5, 5, 5, 5, 7, py.R - 7, 9, 9, 1, 1, py.R - 1, py.R - 1])
+    exp, einf = oracle.msm(dup, s)
+    out, inf = ctx.msm(bd, s)
+    assert inf == einf and (out == exp).all()
+    # total cancellation -> identity
+    s2 = oracle.ints_to_array([11, py.R - 11] + [0] * 10)
+    out, inf = ctx.msm(bd, s2)
+    assert inf
+    # identity among the bases (64 zero bytes) is skipped
+    pz = pts[:10].copy()
+    pz[4] = 0
+    bz = ctx.load_bases(pz)
+    s = oracle.splitmix_fr(0x99, 10, montgomery=False)
+    keep = [i for i in range(10) if i != 4]
+    exp, _ = oracle.msm(pz[keep], s[keep])
+    out, _ = ctx.msm(bz, s)
+    assert (out == exp).all()
+
+
+def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle):
+    """BASELINE.json config 2 at full size.  Bases a_i*G are generated on the device, so
+    sum s_i*P_i must equal (sum a_i*s_i mod r)*G — one scalar multiplication checks 2^20
+    terms; the same inputs split in two 'ranks' and recombined give the identical point."""
+    import torch
+    py = pyoracle
+    n = 1 << 20
+    d_pts = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    d_s = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.known_dlog_bases_device(0xB200, n, d_pts.data_ptr())
+    ctx.splitmix_fr_device(0x5CA1A8, n, d_s.data_ptr(), montgomery=False)
+    # device generators agree with the oracle's on a prefix
+    assert (d_pts[:64].cpu().numpy().view(np.uint64) == oracle.known_dlog_bases(0xB200, 64)).all()
+    assert (d_s[:64].cpu().numpy().view(np.uint64) == oracle.splitmix_fr(0x5CA1A8, 64, False)).all()
+    bases = ctx.load_bases_device(d_pts.data_ptr(), n)
+    out, inf = ctx.msm_device(bases, d_s.data_ptr(), n, montgomery=False)
+    a = oracle.array_to_ints(oracle.splitmix_fr(0xB200, n, False))
+    s = oracle.array_to_ints(oracle.splitmix_fr(0x5CA1A8, n, False))
+    k = sum(x * y for x, y in zip(a, s)) % py.R
+    g = np.frombuffer(py.encode_g1_mont(py.G1_GEN), dtype=np.uint64)
+    exp, _ = oracle.g1_mul(g, False, oracle.int_to_limbs(k))
+    assert not inf and (out == exp).all()
+    # two-way shard + combine (the multi-GPU path on one device)
+    from renegade_b200.sharded import combine_partials, shard_range
+    recs = np.zeros((2, 9), dtype=np.uint64)
+    for r in range(2):
+        b, e = shard_range(n, r, 2)
+        xy, pinf = ctx.msm_device(bases, d_s.data_ptr() + 32 * b, e - b, montgomery=False, base_off=b)
+        recs[r, :8], recs[r, 8] = xy, int(pinf)
+    out2, inf2 = combine_partials(ctx, recs)
+    assert not inf2 and (out2 == exp).all()
