@@ -30,7 +30,7 @@ LOG_N = 20
 N_POINTS = 1 << LOG_N
 BYTES_PER_PAIR = 96  # 64 B affine base + 32 B scalar
 SEED_BASES, SEED_SCALARS = 0xB200, 0x5CA1A8
-KERNELS_PER_MSM = 8  # count, 3x scan, scatter, accumulate, reduce, reduce_final
+KERNELS_PER_MSM = 14  # count, 3x scan, scatter, 3x scan, segfill, accumulate, combine, heavy_combine, reduce, reduce_final
 METRIC = "MSM achieved GB/s (algorithmic bytes / time), 2^20-point BN254 G1 Pippenger per GPU"
 
 

@@ -32,6 +32,8 @@ namespace {
 
 constexpr uint32_t kIdxBits = 26;  // entry = sign(1) | table(5) | point index(26)
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+constexpr int kSegLen = 32;        // a bucket is folded in segments of at most this many points
+constexpr int kCombineSeq = 64;    // buckets with more segments than this take the block-tree path
 constexpr int kReduceChunk = 16;   // buckets per thread in the running-sum reduction
 constexpr int kReduceThreads = 128;
 
@@ -123,13 +125,26 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return r;
 }
 
-__global__ void scan_chunk_sums_kernel(const uint32_t* in, size_t n, uint32_t* chunk_sums) {
+// scan inputs: the bucket histogram itself, or the per-bucket segment count derived from offsets
+struct ScanCounts {
+    const uint32_t* p;
+    __device__ __forceinline__ uint32_t operator()(size_t i) const { return p[i]; }
+};
+struct ScanSegCounts {  // ceil(bucket size / kSegLen)
+    const uint32_t* offsets;
+    __device__ __forceinline__ uint32_t operator()(size_t i) const {
+        return (offsets[i + 1] - offsets[i] + (uint32_t)kSegLen - 1u) / (uint32_t)kSegLen;
+    }
+};
+
+template <class In>
+__global__ void scan_chunk_sums_kernel(In in, size_t n, uint32_t* chunk_sums) {
     __shared__ uint32_t total;
     const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
-        if (base + k < n) s += in[base + k];
+        if (base + k < n) s += in(base + k);
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
 }
@@ -148,7 +163,8 @@ __global__ void scan_chunk_offsets_kernel(uint32_t* chunk_sums, size_t n_chunks)
     }
 }
 
-__global__ void scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* chunk_offsets,
+template <class In>
+__global__ void scan_apply_kernel(In in, size_t n, const uint32_t* chunk_offsets,
                                   uint32_t* out /* n + 1 */) {
     __shared__ uint32_t total;
     const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
@@ -156,7 +172,7 @@ __global__ void scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* 
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        v[k] = base + k < n ? in[base + k] : 0u;
+        v[k] = base + k < n ? in(base + k) : 0u;
         s += v[k];
     }
     uint32_t ex = block_exclusive_scan(s, &total) + chunk_offsets[blockIdx.x];
@@ -168,22 +184,41 @@ __global__ void scan_apply_kernel(const uint32_t* in, size_t n, const uint32_t* 
     }
 }
 
-// ---- bucket accumulation: one thread per bucket ------------------------------------------------
+// ---- bucket accumulation ---------------------------------------------------------------------------
+// Buckets are folded in SEGMENTS of at most kSegLen sorted entries (a bucket of k entries is cut
+// into ceil(k / kSegLen) near-equal segments), one thread per segment, so the work per thread is
+// bounded whatever the digit distribution: the top window of a 254-bit scalar, small witness
+// values or repeated scalars all pile points into a few buckets.
 __device__ __forceinline__ g1_affine load_entry_point(const g1_affine* tables, size_t n,
                                                       uint32_t code) {
     const size_t idx = code & kIdxMask, table = (code >> kIdxBits) & 31u;
     return g1_affine_load_ro(tables + table * n + idx);
 }
 
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ entries,
-                                                             const uint32_t* __restrict__ offsets,
-                                                             const g1_affine* __restrict__ tables,
-                                                             size_t n_points, uint32_t n_buckets,
-                                                             g1_xyzz* __restrict__ buckets) {
+// seg_bucket[s] = bucket owning segment s
+__global__ void msm_segfill_kernel(const uint32_t* __restrict__ seg_offsets, uint32_t n_buckets,
+                                   uint32_t* __restrict__ seg_bucket) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
-    uint32_t e = offsets[b];
-    const uint32_t end = offsets[b + 1];
+    const uint32_t s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
+    for (uint32_t s = s0; s < s1; ++s) seg_bucket[s] = b;
+}
+
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ entries,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const uint32_t* __restrict__ seg_offsets,
+                                                             const uint32_t* __restrict__ seg_bucket,
+                                                             const g1_affine* __restrict__ tables,
+                                                             size_t n_points, uint32_t n_buckets,
+                                                             g1_xyzz* __restrict__ seg_sums) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= seg_offsets[n_buckets]) return;  // the grid is sized for the worst case
+    const uint32_t b = seg_bucket[s];
+    const uint32_t j = s - seg_offsets[b], k = seg_offsets[b + 1] - seg_offsets[b];
+    const uint32_t first = offsets[b], cnt = offsets[b + 1] - first;
+    const uint32_t base = cnt / k, rem = cnt % k;  // near-equal split of the bucket
+    uint32_t e = first + j * base + min(j, rem);
+    const uint32_t end = e + base + (j < rem ? 1u : 0u);
     g1_xyzz acc = g1_xyzz_inf();
     if (e < end) {
         uint32_t code = entries[e];
@@ -201,7 +236,52 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
             if (e >= end) break;
         }
     }
+    g1_xyzz_store(seg_sums + s, acc);
+}
+
+// bucket = sum of its segment sums: sequential for ordinary buckets, deferred to a block tree
+// (msm_heavy_combine_kernel) for buckets cut into more than kCombineSeq segments.
+__global__ void __launch_bounds__(128) msm_bucket_combine_kernel(const g1_xyzz* __restrict__ seg_sums,
+                                                                 const uint32_t* __restrict__ seg_offsets,
+                                                                 uint32_t n_buckets,
+                                                                 g1_xyzz* __restrict__ buckets,
+                                                                 uint32_t* __restrict__ heavy_count,
+                                                                 uint32_t* __restrict__ heavy_list) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const uint32_t s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
+    if (s1 - s0 > (uint32_t)kCombineSeq) {
+        heavy_list[atomicAdd(heavy_count, 1u)] = b;
+        return;
+    }
+    g1_xyzz acc = g1_xyzz_inf();
+    if (s0 < s1) {
+        acc = g1_xyzz_load(seg_sums + s0);
+        for (uint32_t s = s0 + 1; s < s1; ++s) acc = g1_add(acc, g1_xyzz_load(seg_sums + s));
+    }
     g1_xyzz_store(buckets + b, acc);
+}
+
+__global__ void __launch_bounds__(kReduceThreads) msm_heavy_combine_kernel(const g1_xyzz* __restrict__ seg_sums,
+                                                                           const uint32_t* __restrict__ seg_offsets,
+                                                                           const uint32_t* __restrict__ heavy_count,
+                                                                           const uint32_t* __restrict__ heavy_list,
+                                                                           g1_xyzz* __restrict__ buckets) {
+    __shared__ g1_xyzz sh[kReduceThreads];
+    for (uint32_t h = blockIdx.x; h < *heavy_count; h += gridDim.x) {
+        const uint32_t b = heavy_list[h];
+        const uint32_t s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
+        g1_xyzz acc = g1_xyzz_inf();
+        for (uint32_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) acc = g1_add(acc, g1_xyzz_load(seg_sums + s));
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
+            if ((int)threadIdx.x < stride) sh[threadIdx.x] = g1_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) g1_xyzz_store(buckets + b, sh[0]);
+        __syncthreads();
+    }
 }
 
 // ---- bucket reduction: sum_k (k+1) * B[k] per physical window -----------------------------------
@@ -446,15 +526,16 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
     return rc;
 }
 
-static int exclusive_scan_u32(const uint32_t* d_in, size_t n, uint32_t* d_out, DevBuf* chunk_buf,
+template <class In>
+static int exclusive_scan_u32(In d_in, size_t n, uint32_t* d_out, DevBuf* chunk_buf,
                               cudaStream_t st) {
     const size_t n_chunks = (n + kScanChunk - 1) / kScanChunk;
     int rc = chunk_buf->reserve(n_chunks * sizeof(uint32_t));
     if (rc != B200_OK) return rc;
     uint32_t* chunk = (uint32_t*)chunk_buf->p;
-    scan_chunk_sums_kernel<<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk);
+    scan_chunk_sums_kernel<In><<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk);
     scan_chunk_offsets_kernel<<<1, kScanThreads, 0, st>>>(chunk, n_chunks);
-    scan_apply_kernel<<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk, d_out);
+    scan_apply_kernel<In><<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk, d_out);
     return B200_OK;
 }
 
@@ -484,6 +565,13 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
     if ((rc = s->cursor.reserve(n_buckets * 4)) != B200_OK) return rc;
     if ((rc = s->entries.reserve(max_entries * 4)) != B200_OK) return rc;
     if ((rc = s->buckets.reserve(n_buckets * sizeof(g1_xyzz))) != B200_OK) return rc;
+    // segments: at most floor(entries / kSegLen) full ones plus one partial per bucket
+    const size_t max_segs = max_entries / kSegLen + n_buckets;
+    const size_t max_heavy = max_segs / (kCombineSeq + 1) + 1;
+    if ((rc = s->seg_offsets.reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
+    if ((rc = s->seg_bucket.reserve(max_segs * 4)) != B200_OK) return rc;
+    if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     const uint32_t reduce_threads_needed = (half + kReduceChunk - 1) / kReduceChunk;
     const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
     if ((rc = s->partials.reserve((size_t)pl.n_phys * reduce_blocks * sizeof(g1_xyzz))) != B200_OK) return rc;
@@ -496,6 +584,11 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
     g1_xyzz* buckets = (g1_xyzz*)s->buckets.p;
     g1_xyzz* partials = (g1_xyzz*)s->partials.p;
     g1_xyzz* window_sums = (g1_xyzz*)s->window_sums.p;
+    uint32_t* seg_offsets = (uint32_t*)s->seg_offsets.p;
+    uint32_t* seg_bucket = (uint32_t*)s->seg_bucket.p;
+    g1_xyzz* seg_sums = (g1_xyzz*)s->seg_sums.p;
+    uint32_t* heavy_count = (uint32_t*)s->heavy.p;
+    uint32_t* heavy_list = heavy_count + 1;
 
     if (s->timing && !s->ev_init) {
         for (auto& e : s->ev) B200_CUDA(cudaEventCreate(&e));
@@ -506,12 +599,19 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
     const unsigned bs = 256;
     const unsigned grid_n = (unsigned)((n + bs - 1) / bs);
     msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, montgomery, pl, counts);
-    if ((rc = exclusive_scan_u32(counts, n_buckets, offsets, &s->block_sums, st)) != B200_OK) return rc;
+    if ((rc = exclusive_scan_u32(ScanCounts{counts}, n_buckets, offsets, &s->block_sums, st)) != B200_OK) return rc;
     B200_CUDA(cudaMemcpyAsync(cursor, offsets, n_buckets * 4, cudaMemcpyDeviceToDevice, st));
     msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, montgomery, pl, (uint32_t)base_off, cursor, entries);
+    if ((rc = exclusive_scan_u32(ScanSegCounts{offsets}, n_buckets, seg_offsets, &s->block_sums, st)) != B200_OK) return rc;
+    msm_segfill_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(seg_offsets, (uint32_t)n_buckets, seg_bucket);
+    B200_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
     if (s->timing) cudaEventRecord(s->ev[1], st);
-    msm_accumulate_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
-        entries, offsets, b->tables, b->n, (uint32_t)n_buckets, buckets);
+    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, st>>>(
+        entries, offsets, seg_offsets, seg_bucket, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
+    msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
+        seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, heavy_count, heavy_list);
+    msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(
+        seg_sums, seg_offsets, heavy_count, heavy_list, buckets);
     if (s->timing) cudaEventRecord(s->ev[2], st);
     msm_reduce_kernel<<<dim3(reduce_blocks, pl.n_phys), kReduceThreads, 0, st>>>(buckets, half, pl.c, partials);
     msm_reduce_final_kernel<<<pl.n_phys, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);

@@ -121,6 +121,23 @@ def test_msm_edge_cases(ctx, oracle, pyoracle):
     assert (out == exp).all()
 
 
+def test_msm_skewed_scalars(ctx, oracle, pyoracle):
+    """Digit distributions that pile points into few buckets: identical scalars (one bucket per
+    window holds every point -> block-tree combine path), small scalars (only the low windows),
+    and a 0/1/small mix like witness values."""
+    py = pyoracle
+    n = 20000
+    pts = oracle.known_dlog_bases(0xB200, n)
+    bases = ctx.load_bases(pts)
+    same = oracle.ints_to_array([0x1234567_89abcdef_0fedcba9_87654321_1234567_89abcdef % py.R] * n)
+    small = oracle.ints_to_array([(i * 2654435761) % 65521 for i in range(n)])
+    mix = oracle.ints_to_array([(0, 1, 1, 2, py.R - 1, 7)[i % 6] for i in range(n)])
+    for s in (same, small, mix):
+        exp, einf = oracle.msm(pts, s)
+        out, inf = ctx.msm(bases, s)
+        assert inf == einf and (out == exp).all()
+
+
 def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle):
     """BASELINE.json config 2 at full size.  Bases a_i*G are generated on the device, so
     sum s_i*P_i must equal (sum a_i*s_i mod r)*G — one scalar multiplication checks 2^20

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 lscpu | grep -E 'Model name|^CPU\(s\)' >> gpurun_out/gpu.txt
-echo "== pytest gpu" ; timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
+echo "== pytest gpu" ; timeout 700 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
 echo "== microbench" ; timeout 120 tools/microbench 2>&1 | tee gpurun_out/microbench.json
 echo "== bench" ; timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.json
 if [ "${1:-}" = "ncu" ]; then
