@@ -157,3 +157,77 @@ def domain_generator(log_n: int) -> np.ndarray:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# TurboPlonk prover / verifier restatement (plonk_oracle.c)
+# ---------------------------------------------------------------------------------------------
+class PlonkProof(C.Structure):
+    """orc_plonk_proof — field order mirrors PlonkProofDef (plonk_proof_def.rs:197-222)."""
+    _fields_ = [
+        ("wires_poly_comms", (C.c_uint64 * 8) * 5),
+        ("prod_perm_poly_comm", C.c_uint64 * 8),
+        ("split_quot_poly_comms", (C.c_uint64 * 8) * 5),
+        ("opening_proof", C.c_uint64 * 8),
+        ("shifted_opening_proof", C.c_uint64 * 8),
+        ("wires_evals", (C.c_uint64 * 4) * 5),
+        ("wire_sigma_evals", (C.c_uint64 * 4) * 4),
+        ("perm_next_eval", C.c_uint64 * 4),
+    ]
+
+    def to_array(self) -> np.ndarray:
+        return np.frombuffer(bytes(self), dtype=np.uint64).copy()
+
+
+class PlonkChallenges(C.Structure):
+    _fields_ = [(n, C.c_uint64 * 4) for n in ("beta", "gamma", "alpha", "zeta", "v", "u")]
+
+
+def keccak256(data: bytes) -> bytes:
+    out = (C.c_uint8 * 32)()
+    lib().orc_keccak256(data, C.c_size_t(len(data)), out)
+    return bytes(out)
+
+
+def srs_from_tau(tau_mont: np.ndarray, n: int) -> np.ndarray:
+    out = np.empty((n, 8), dtype=np.uint64)
+    lib().orc_srs_from_tau(_p(np.ascontiguousarray(tau_mont, dtype=np.uint64)), C.c_size_t(n), _p(out))
+    return out
+
+
+def plonk_preprocess(log_n, selectors, perm, k, srs):
+    n = 1 << log_n
+    selectors = np.ascontiguousarray(selectors, dtype=np.uint64)
+    perm = np.ascontiguousarray(perm, dtype=np.uint64)
+    k = np.ascontiguousarray(k, dtype=np.uint64)
+    srs = np.ascontiguousarray(srs, dtype=np.uint64)
+    sel_c = np.empty((13, n, 4), dtype=np.uint64)
+    sig_c = np.empty((5, n, 4), dtype=np.uint64)
+    sel_comms = np.empty((13, 8), dtype=np.uint64)
+    sig_comms = np.empty((5, 8), dtype=np.uint64)
+    rc = lib().orc_plonk_preprocess(C.c_uint(log_n), _p(selectors), _p(perm), _p(k), _p(srs), _p(sel_c), _p(sig_c),
+                                    _p(sel_comms), _p(sig_comms))
+    assert rc == 0
+    return {"selector_coeffs": sel_c, "sigma_coeffs": sig_c, "selector_comms": sel_comms, "sigma_comms": sig_comms}
+
+
+def plonk_prove(log_n, num_inputs, k, pk, wires, pub_inputs, blinders, srs, want_link_poly=False):
+    n = 1 << log_n
+    proof, ch = PlonkProof(), PlonkChallenges()
+    link = np.zeros((n + 2, 4), dtype=np.uint64) if want_link_poly else None
+    lib().orc_plonk_prove.restype = C.c_int
+    rc = lib().orc_plonk_prove(
+        C.c_uint(log_n), C.c_size_t(num_inputs), _p(np.ascontiguousarray(k, dtype=np.uint64)),
+        _p(pk["selector_coeffs"]), _p(pk["sigma_coeffs"]), _p(pk["selector_comms"]), _p(pk["sigma_comms"]),
+        _p(np.ascontiguousarray(wires, dtype=np.uint64)), _p(np.ascontiguousarray(pub_inputs, dtype=np.uint64)),
+        _p(np.ascontiguousarray(blinders, dtype=np.uint64)), _p(np.ascontiguousarray(srs, dtype=np.uint64)),
+        C.byref(proof), C.byref(ch), _p(link) if link is not None else None)
+    return rc, proof, ch, link
+
+
+def plonk_verify_known_tau(log_n, num_inputs, k, pk, pub_inputs, proof: PlonkProof, tau_mont) -> bool:
+    lib().orc_plonk_verify_known_tau.restype = C.c_int
+    return bool(lib().orc_plonk_verify_known_tau(
+        C.c_uint(log_n), C.c_size_t(num_inputs), _p(np.ascontiguousarray(k, dtype=np.uint64)),
+        _p(pk["selector_comms"]), _p(pk["sigma_comms"]), _p(np.ascontiguousarray(pub_inputs, dtype=np.uint64)),
+        C.byref(proof), _p(np.ascontiguousarray(tau_mont, dtype=np.uint64))))
