@@ -38,9 +38,25 @@ extern "C" {
 #define B200_ERR_FORMAT (-4)       /* malformed .ptau */
 #define B200_ERR_NOT_ON_CURVE (-5) /* srs.rs:179 "point not on curve" */
 #define B200_ERR_NO_DEVICE (-6)
+#define B200_ERR_UNSATISFIED (-7)  /* PlonkError::WrongQuotientPolyDegree: witness does not satisfy the circuit */
 
 typedef struct b200_ctx b200_ctx;     /* one CUDA device + stream + scratch */
 typedef struct b200_bases b200_bases; /* device-resident G1 bases + window tables (the SRS) */
+typedef struct b200_pk b200_pk;       /* device-resident proving key of one circuit */
+
+/* Flat proof, same field order as the reference's `PlonkProof` / `PlonkProofEvaluations`
+ * (crates/relayer-types/types-proofs/src/rkyv_impls/plonk_proof_def.rs:168-222); commitments
+ * are affine x||y Montgomery, evaluations Montgomery Fr; plookup_proof is always None. */
+typedef struct {
+    uint64_t wires_poly_comms[5][8];
+    uint64_t prod_perm_poly_comm[8];
+    uint64_t split_quot_poly_comms[5][8];
+    uint64_t opening_proof[8];
+    uint64_t shifted_opening_proof[8];
+    uint64_t wires_evals[5][4];
+    uint64_t wire_sigma_evals[4][4];
+    uint64_t perm_next_eval[4];
+} b200_proof;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 /* device: CUDA ordinal.  Replaces nothing in the reference (it has no device). */
@@ -117,6 +133,40 @@ int b200_splitmix_fr_device(b200_ctx* ctx, uint64_t seed, size_t first, size_t n
 /* known-discrete-log bases P_i = a_i * G, a_i = splitmix_fr(seed)[first + i]; 64 B records */
 int b200_known_dlog_bases_device(b200_ctx* ctx, uint64_t seed, size_t first, size_t n,
                                  void* d_out);
+
+/* ---- TurboPlonk prover (boundary B2) ------------------------------------ */
+/* Replaces `PlonkKzgSnark::<Bn254>::preprocess(&SYSTEM_SRS, &cs)` (traits.rs:850).
+ * The host (Rust: `cs` after finalize_for_arithmetization) hands over the circuit structure:
+ *   selectors_evals  13 x n selector values over the domain, column order
+ *                    q_lc[0..4] q_mul[0..2] q_hash[0..4] q_o q_c q_ecc (Montgomery);
+ *   perm             5n entries: perm[i*n + j] = i'*n + j', the copy-constraint permutation
+ *                    over wire positions (column i, row j);
+ *   k                the 5 coset representatives `vk.k` (Montgomery);
+ *   num_inputs       public-input gates occupy rows 0..num_inputs-1.
+ * Selector / sigma polynomials, their commitments (the VerifyingKey contents) and the coset
+ * evaluations the quotient needs stay resident on the device.  srs must hold >= n + 3 points. */
+int b200_plonk_preprocess(b200_ctx* ctx, const b200_bases* srs, unsigned log_n, size_t num_inputs,
+                          const uint64_t* selectors_evals, const uint64_t* perm, const uint64_t* k,
+                          b200_pk** out);
+/* VerifyingKey commitments: 13 selector + 5 sigma commitments, 64 B each. */
+int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t* sigma_comms);
+void b200_pk_free(b200_ctx* ctx, b200_pk* pk);
+
+/* Replaces `PlonkKzgSnark::prove_with_link_hint::<_, _, SolidityTranscript>(&mut rng, &circuit,
+ * &pk)` (traits.rs:996).  wires: 5 x n wire values (the witness table after synthesis);
+ * pub_inputs: num_inputs values; blinders: the 17 Fr elements the reference draws from its RNG
+ * (2 per wire polynomial, 3 for the permutation product, 4 for the quotient split), in draw
+ * order, supplied by the caller so both sides can be made deterministic.
+ * link_poly (may be NULL): the (n + 2)-coefficient blinded wire-0 polynomial of
+ * `LinkingHint.linking_wire_poly`; its commitment is proof->wires_poly_comms[0].
+ * challenges (may be NULL): beta, gamma, alpha, zeta, v, u for audit.
+ * Fails with B200_ERR_UNSATISFIED where the reference returns WrongQuotientPolyDegree. */
+int b200_plonk_prove(b200_ctx* ctx, const b200_pk* pk, const uint64_t* wires,
+                     const uint64_t* pub_inputs, const uint64_t* blinders, b200_proof* proof,
+                     uint64_t* link_poly, uint64_t* challenges);
+
+/* Keccak-256 of the transcript (host; exported so the hash can be pinned by known answers). */
+void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
 
 /* ---- device self-test ------------------------------------------------------------------ */
 /* Runs `iters` random Fr and Fq products through the production multiplier (IMAD.WIDE chains)

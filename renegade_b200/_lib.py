@@ -22,6 +22,7 @@ EXPORTS = [
     "b200_ntt", "b200_ntt_device", "b200_ntt_last_ms", "b200_domain_generator",
     "b200_splitmix_fr_device", "b200_known_dlog_bases_device",
     "b200_selftest_field", "b200_field_op",
+    "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_free", "b200_plonk_prove", "b200_keccak256",
 ]
 
 
@@ -70,6 +71,13 @@ def load() -> C.CDLL:
     lib.b200_known_dlog_bases_device.argtypes = [vp, u64, sz, sz, vp]
     lib.b200_selftest_field.argtypes = [vp, u64, sz, C.POINTER(u64)]
     lib.b200_field_op.argtypes = [vp, i32, i32, vp, vp, sz, vp]
+    lib.b200_plonk_preprocess.argtypes = [vp, vp, u32, sz, vp, vp, vp, C.POINTER(vp)]
+    lib.b200_pk_verifying_key.argtypes = [vp, vp, vp]
+    lib.b200_pk_free.argtypes = [vp, vp]
+    lib.b200_pk_free.restype = None
+    lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200_keccak256.argtypes = [C.c_char_p, sz, vp]
+    lib.b200_keccak256.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
         if fn.restype is C.c_int and name not in ("b200_last_error", "b200_version"):

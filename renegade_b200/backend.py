@@ -256,3 +256,96 @@ class Radix2EvaluationDomain:
 
     def coset_ifft(self, evals: np.ndarray) -> np.ndarray:
         return self.ctx.ntt(self._pad(evals), inverse=True, coset=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# TurboPlonk prover (boundary B2)
+# ---------------------------------------------------------------------------------------------
+class B200Proof(C.Structure):
+    """b200_proof: field order of the reference's `PlonkProof` (plonk_proof_def.rs:197-222)."""
+    _fields_ = [
+        ("wires_poly_comms", (C.c_uint64 * 8) * 5),
+        ("prod_perm_poly_comm", C.c_uint64 * 8),
+        ("split_quot_poly_comms", (C.c_uint64 * 8) * 5),
+        ("opening_proof", C.c_uint64 * 8),
+        ("shifted_opening_proof", C.c_uint64 * 8),
+        ("wires_evals", (C.c_uint64 * 4) * 5),
+        ("wire_sigma_evals", (C.c_uint64 * 4) * 4),
+        ("perm_next_eval", C.c_uint64 * 4),
+    ]
+
+    def to_array(self) -> np.ndarray:
+        return np.frombuffer(bytes(self), dtype=np.uint64).copy()
+
+
+@dataclass
+class LinkingHint:
+    """mpc-plonk `LinkingHint` (plonk_proof_def.rs:143-150)."""
+    linking_wire_poly: np.ndarray
+    linking_wire_comm: np.ndarray
+
+
+class ProvingKey:
+    """Device-resident `ProvingKey` + the `VerifyingKey` commitments (b200_pk)."""
+
+    def __init__(self, ctx: Context, handle, log_n: int, num_inputs: int, k: np.ndarray):
+        self._ctx, self._h = ctx, handle
+        self.log_n, self.num_inputs, self.k = log_n, num_inputs, k
+        self.selector_comms = np.zeros((13, 8), dtype=np.uint64)
+        self.sigma_comms = np.zeros((5, 8), dtype=np.uint64)
+        _lib.check(ctx._lib.b200_pk_verifying_key(handle, _ptr(self.selector_comms), _ptr(self.sigma_comms)))
+
+    @property
+    def domain_size(self) -> int:
+        return 1 << self.log_n
+
+    def free(self):
+        if self._h and self._ctx._h:
+            self._ctx._lib.b200_pk_free(self._ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PlonkKzgSnark:
+    """mpc-plonk `PlonkKzgSnark<Bn254>` as called at traits.rs:850 and traits.rs:996."""
+
+    @staticmethod
+    def preprocess(ctx: Context, srs: Bases, log_n: int, num_inputs: int, selectors: np.ndarray,
+                   perm: np.ndarray, k: np.ndarray) -> ProvingKey:
+        sel = np.ascontiguousarray(selectors, dtype=np.uint64).reshape(13, 1 << log_n, 4)
+        pm = np.ascontiguousarray(perm, dtype=np.uint64).reshape(5 << log_n)
+        kk = np.ascontiguousarray(k, dtype=np.uint64).reshape(5, 4)
+        h = C.c_void_p()
+        _lib.check(ctx._lib.b200_plonk_preprocess(ctx._h, srs._h, log_n, num_inputs, _ptr(sel), _ptr(pm), _ptr(kk),
+                                                  C.byref(h)))
+        return ProvingKey(ctx, h, log_n, num_inputs, kk)
+
+    @staticmethod
+    def prove_with_link_hint(ctx: Context, pk: ProvingKey, wires: np.ndarray, pub_inputs: np.ndarray,
+                             blinders: np.ndarray, want_challenges: bool = False):
+        """Returns (proof, LinkingHint[, challenges]).  `blinders` are the 17 field elements the
+        reference draws from `thread_rng()` (traits.rs:994), in draw order."""
+        n = pk.domain_size
+        w = np.ascontiguousarray(wires, dtype=np.uint64).reshape(5, n, 4)
+        pi = np.ascontiguousarray(pub_inputs, dtype=np.uint64).reshape(-1, 4)
+        if pi.shape[0] != pk.num_inputs:
+            raise ValueError("wrong number of public inputs")
+        bl = np.ascontiguousarray(blinders, dtype=np.uint64).reshape(17, 4)
+        proof = B200Proof()
+        link = np.zeros((n + 2, 4), dtype=np.uint64)
+        ch = np.zeros((6, 4), dtype=np.uint64)
+        _lib.check(ctx._lib.b200_plonk_prove(ctx._h, pk._h, _ptr(w), _ptr(pi) if pi.size else None, _ptr(bl),
+                                             C.byref(proof), _ptr(link), _ptr(ch) if want_challenges else None))
+        hint = LinkingHint(linking_wire_poly=link, linking_wire_comm=np.array(proof.wires_poly_comms[0], dtype=np.uint64))
+        return (proof, hint, ch) if want_challenges else (proof, hint)
+
+
+def keccak256(data: bytes) -> bytes:
+    out = (C.c_uint8 * 32)()
+    _lib.load().b200_keccak256(data, len(data), out)
+    return bytes(out)

@@ -8,6 +8,7 @@
 
 #include "b200prover.h"
 #include "device_ctx.h"
+#include "transcript.h"
 
 namespace b200 {
 
@@ -29,7 +30,7 @@ Context::~Context() {
     if (stream) cudaStreamDestroy(stream);
 }
 
-static int get_domain(Context* c, unsigned log_n, Domain** out) {
+int get_domain(Context* c, unsigned log_n, Domain** out) {
     auto it = c->domains.find(log_n);
     if (it != c->domains.end()) {
         *out = it->second;
@@ -109,33 +110,13 @@ __global__ void field_op_kernel(int op, const fe* a, const fe* b, size_t n, fe* 
 
 using namespace b200;
 
-struct b200_ctx {
-    Context c;
-};
-struct b200_bases {
-    Bases* b;
-};
-
-#define B200_TRY try {
-#define B200_CATCH                                   \
-    }                                                \
-    catch (const std::bad_alloc&) {                  \
-        set_error("out of host memory");             \
-        return B200_ERR_NOMEM;                       \
-    }                                                \
-    catch (const std::exception& e) {                \
-        set_error(std::string("exception: ") + e.what()); \
-        return B200_ERR_INVALID;                     \
-    }                                                \
-    catch (...) {                                    \
-        set_error("unknown exception");              \
-        return B200_ERR_INVALID;                     \
-    }
 
 extern "C" {
 
 const char* b200_last_error(void) { return g_last_error.c_str(); }
 const char* b200_version(void) { return "libb200prover 0.1.0 sm_100a"; }
+
+void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) { Keccak256::hash(data, len, out); }
 
 int b200_init(int device, b200_ctx** out) {
     B200_TRY

@@ -56,6 +56,9 @@ struct Domain {
     ~Domain();
 };
 int domain_create(unsigned log_n, cudaStream_t st, Domain** out);
+// out[i] = scale * base^i, i < n (device table, launched on st)
+void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st);
+fe host_root_of_unity(unsigned log_n);
 int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, unsigned batch,
                size_t stride, cudaStream_t st);
 
@@ -116,7 +119,34 @@ struct Context {
     bool ntt_ev_init = false;
     float ntt_last_ms = 0.f;  // device time of the last b200_ntt_device call (CUDA events)
     MsmScratch msm;
+    DevBuf plonk_ws;  // prover workspace (plonk.cu)
     ~Context();
 };
 
+int get_domain(Context* c, unsigned log_n, Domain** out);
+
 }  // namespace b200
+
+// opaque handle types of the C ABI
+struct b200_ctx {
+    b200::Context c;
+};
+struct b200_bases {
+    b200::Bases* b;
+};
+
+#define B200_TRY try {
+#define B200_CATCH                                               \
+    }                                                            \
+    catch (const std::bad_alloc&) {                              \
+        ::b200::set_error("out of host memory");                 \
+        return B200_ERR_NOMEM;                                   \
+    }                                                            \
+    catch (const std::exception& e) {                            \
+        ::b200::set_error(std::string("exception: ") + e.what()); \
+        return B200_ERR_INVALID;                                 \
+    }                                                            \
+    catch (...) {                                                \
+        ::b200::set_error("unknown exception");                  \
+        return B200_ERR_INVALID;                                 \
+    }

@@ -415,8 +415,16 @@ MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
     for (int c = c_lo; c <= c_hi; ++c) {
         const int W = (255 + c - 1) / c;
         if (W > 32) continue;
-        // adds in the bucket phase + (full adds, poorly parallel) in the reduction
-        const double cost = (double)n * W + 4.0 * (double)((size_t)1 << (c - 1));
+        // Cost model fitted to B200 measurements (profiles/r1b_msm_window_sweep.log), in ms:
+        // bucket phase ~ n*W mixed additions at ~5.8e6/ms, digit sort ~ n*W at ~45e6/ms, bucket
+        // reduction ~ a latency floor + 2^(c-1) buckets.  `shrt` = how many bits the top digit of
+        // a 254-bit scalar falls short of a full window: a short top digit piles n / 2^t points
+        // into 2^t buckets (hot atomics in the sort, more segments to combine).
+        const int t = 254 - c * (W - 1);
+        const int shrt = t >= c - 1 ? 0 : (c - 1 - t);
+        const double nw = (double)n * W;
+        const double cost = nw * (1.0 + 0.02 * shrt) / 5.8e6 + nw * (1.0 + 0.1 * shrt) / 45e6 + 0.42 +
+                            (double)((size_t)1 << (c - 1)) / 1.0e6;
         if (cost < best_cost) {
             best_cost = cost;
             best.c = c;

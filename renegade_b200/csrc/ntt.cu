@@ -143,7 +143,7 @@ __global__ void powers_kernel(fe* out, size_t n, PowArgs p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static fe host_root_of_unity(unsigned log_n) {
+fe host_root_of_unity(unsigned log_n) {
     // TWO_ADIC_ROOT_OF_UNITY = 5^((r-1)/2^28); squared down to order 2^log_n
     fe c;
     const uint32_t canon[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu,
@@ -154,7 +154,7 @@ static fe host_root_of_unity(unsigned log_n) {
     return w;
 }
 
-static void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st) {
+void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st) {
     PowArgs p;
     p.scale = scale;
     fe b = base;

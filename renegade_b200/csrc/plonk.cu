@@ -1,0 +1,741 @@
+// TurboPlonk / KZG prover rounds on the device.
+//
+// Replaces what the reference calls at
+//   /root/reference/crates/circuits/circuit-types/src/traits.rs:850
+//       PlonkKzgSnark::<Bn254>::preprocess(&SYSTEM_SRS, &cs)            -> b200_plonk_preprocess
+//   /root/reference/crates/circuits/circuit-types/src/traits.rs:996
+//       PlonkKzgSnark::prove_with_link_hint::<_, _, SolidityTranscript> -> b200_plonk_prove
+// (the algorithm is mpc-jellyfish's TurboPlonk prover, restated in SURVEY.md App. A: 5 wire
+// columns, 13 selectors, quotient over the 8n coset, 5-way split, Keccak transcript).
+//
+// B200-first layout: everything a proof needs that does not depend on the witness is resident in
+// HBM per proving key — selector/sigma coefficients, sigma evaluations, and the 18 coset
+// evaluation vectors over the 8n domain (302 MB at n = 2^16; 180 GB of HBM holds hundreds of
+// keys) — so a proof runs 7 size-8n coset NTTs instead of the reference's 25.  Polynomials never
+// leave the device between rounds; the host sees 13 commitments and 10 evaluations and runs the
+// (serial, few-KB) Keccak transcript between rounds.
+#include <cstring>
+#include <vector>
+
+#include "b200prover.h"
+#include "device_ctx.h"
+#include "transcript.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int NW = 5;    // wire columns (GATE_WIDTH + 1)
+constexpr int NS = 13;   // q_lc[4] q_mul[2] q_hash[4] q_o q_c q_ecc
+constexpr int CH = 64;   // elements per thread in the chunked scans
+
+struct KArr {
+    fe v[NW];
+};
+
+using Fr = FrCfg;
+#define FMUL(a, b) fe_mul<Fr>((a), (b))
+#define FADD(a, b) fe_add<Fr>((a), (b))
+#define FSUB(a, b) fe_sub<Fr>((a), (b))
+
+// ---- key setup ---------------------------------------------------------------------------------
+// sigma_i(w^j) = k_{i'} * w^{j'} where (i', j') is the image of wire position (i, j)
+__global__ void k_sigma_evals(const uint64_t* __restrict__ perm, const fe* __restrict__ dom, size_t n, KArr k,
+                              fe* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NW * n) return;
+    const uint64_t tgt = perm[t];
+    fe_store(out + t, FMUL(k.v[tgt / n], fe_load_ro(dom + tgt % n)));
+}
+
+// out[i] = n * (x_i - 1)   (inverted afterwards: L_1(x) / Z_H(x) = 1 / (n (x - 1)))
+__global__ void k_l1_denominators(const fe* __restrict__ pts, size_t m, fe n_mont, fe* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    fe_store(out + i, FMUL(FSUB(fe_load_ro(pts + i), fe_one<Fr>()), n_mont));
+}
+
+// in-place batch inversion, one Fermat inversion per chunk of 16 (Montgomery's trick inside the chunk)
+__global__ void k_batch_inverse(fe* __restrict__ data, fe* __restrict__ scratch, size_t n) {
+    constexpr int C = 16;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t beg = t * C;
+    if (beg >= n) return;
+    const size_t end = beg + C < n ? beg + C : n;
+    fe run = fe_one<Fr>();
+    for (size_t i = beg; i < end; ++i) {
+        fe_store(scratch + i, run);
+        run = FMUL(run, fe_load(data + i));
+    }
+    fe inv = fe_inv<Fr>(run);
+    for (size_t i = end; i-- > beg;) {
+        const fe d = fe_load(data + i);
+        fe_store(data + i, FMUL(inv, fe_load(scratch + i)));
+        inv = FMUL(inv, d);
+    }
+}
+
+// ---- round 1 / 2 helpers -------------------------------------------------------------------------
+struct BlindArgs {
+    fe b[3];
+    int count;
+};
+// poly += (b0 + b1 X + ...) * (X^n - 1)
+__global__ void k_blind(fe* poly, size_t n, BlindArgs a) {
+    const int i = threadIdx.x;
+    if (i >= a.count) return;
+    fe_store(poly + i, FSUB(fe_load(poly + i), a.b[i]));
+    fe_store(poly + n + i, FADD(fe_load(poly + n + i), a.b[i]));
+}
+
+// per row j: num = prod_i (w_ij + beta k_i w^j + gamma), den = prod_i (w_ij + beta sigma_ij + gamma)
+__global__ void k_perm_num_den(const fe* __restrict__ wires, const fe* __restrict__ sig_evals,
+                               const fe* __restrict__ dom, KArr k, fe beta, fe gamma, size_t n,
+                               fe* __restrict__ num, fe* __restrict__ den) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const fe bw = FMUL(beta, fe_load_ro(dom + j));
+    fe a = fe_one<Fr>(), b = fe_one<Fr>();
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const fe t = FADD(fe_load_ro(wires + i * n + j), gamma);
+        a = FMUL(a, FADD(t, FMUL(k.v[i], bw)));
+        b = FMUL(b, FADD(t, FMUL(beta, fe_load_ro(sig_evals + i * n + j))));
+    }
+    fe_store(num + j, a);
+    fe_store(den + j, b);
+}
+
+// ratio = num / den (den inverted in chunks of 16); result overwrites den
+__global__ void k_ratio(const fe* __restrict__ num, fe* __restrict__ den, fe* __restrict__ scratch, size_t n) {
+    constexpr int C = 16;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t beg = t * C;
+    if (beg >= n) return;
+    const size_t end = beg + C < n ? beg + C : n;
+    fe run = fe_one<Fr>();
+    for (size_t i = beg; i < end; ++i) {
+        fe_store(scratch + i, run);
+        run = FMUL(run, fe_load(den + i));
+    }
+    fe inv = fe_inv<Fr>(run);
+    for (size_t i = end; i-- > beg;) {
+        const fe d = fe_load(den + i);
+        fe_store(den + i, FMUL(fe_load_ro(num + i), FMUL(inv, fe_load(scratch + i))));
+        inv = FMUL(inv, d);
+    }
+}
+
+// exclusive multiplicative scan, chunked: data[j] <- prod_{i<j} data[i]
+__global__ void k_scan_mul_local(fe* __restrict__ data, size_t n, fe* __restrict__ totals) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t beg = t * CH;
+    if (beg >= n) return;
+    const size_t end = beg + CH < n ? beg + CH : n;
+    fe run = fe_one<Fr>();
+    for (size_t i = beg; i < end; ++i) {
+        const fe v = fe_load(data + i);
+        fe_store(data + i, run);
+        run = FMUL(run, v);
+    }
+    fe_store(totals + t, run);
+}
+__global__ void k_scan_mul_apply(fe* __restrict__ data, size_t n, const fe* __restrict__ offs) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || j < CH) return;  // the first chunk's offset is 1
+    fe_store(data + j, FMUL(fe_load(data + j), fe_load_ro(offs + j / CH)));
+}
+
+// ---- Horner suffix scan: S[j] = sum_{i >= j} p[i] z^(i-j) -------------------------------------------
+// S[0] = p(z) (evaluation) and S[1..] are the coefficients of p(X) / (X - z) (synthetic division).
+__global__ void k_horner_local(const fe* __restrict__ p, size_t len, fe z, fe* __restrict__ S, fe* __restrict__ H) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t beg = t * CH;
+    if (beg >= len) return;
+    const size_t end = beg + CH < len ? beg + CH : len;
+    fe run = fe_zero();
+    for (size_t i = end; i-- > beg;) {
+        run = FADD(FMUL(run, z), fe_load_ro(p + i));
+        if (S) fe_store(S + i, run);
+    }
+    fe_store(H + t, run);
+}
+// S[j] += z^(chunk_end - j) * T[chunk + 1]
+__global__ void k_horner_apply(fe* __restrict__ S, size_t len, fe z, const fe* __restrict__ T, size_t n_chunks) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t + 1 >= n_chunks) return;  // the last chunk has no carry
+    const size_t beg = t * CH, end = beg + CH;
+    const fe carry = fe_load_ro(T + t + 1);
+    fe pw = z;
+    for (size_t i = end; i-- > beg;) {
+        fe_store(S + i, FADD(fe_load(S + i), FMUL(pw, carry)));
+        pw = FMUL(pw, z);
+    }
+    (void)len;
+}
+
+// ---- round 3: quotient over the coset g * H_8n ------------------------------------------------------
+struct QuotArgs {
+    const fe* sel;   // 13 x m resident coset evaluations
+    const fe* sig;   // 5 x m
+    const fe* ext;   // 7 x m: wires 0..4, z, public-input polynomial
+    const fe* pts;   // m evaluation points g * w_m^i
+    const fe* l1_inv;  // 1 / (n (x_i - 1))
+    fe* out;
+    size_t m;
+    KArr k;
+    fe beta, gamma, alpha, alpha2;
+    fe zh_inv[8];
+};
+__global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.m) return;
+    const size_t m = a.m;
+    fe w[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) w[j] = fe_load_ro(a.ext + j * m + i);
+    // gate: q_c + pi + sum q_lc w + q_mul0 w0 w1 + q_mul1 w2 w3 + q_ecc w0..w4 + sum q_hash w^5 - q_o w4
+    fe acc = FADD(fe_load_ro(a.sel + 11 * m + i), fe_load_ro(a.ext + 6 * m + i));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        acc = FADD(acc, FMUL(fe_load_ro(a.sel + j * m + i), w[j]));
+        const fe w2 = fe_sqr<Fr>(w[j]);
+        acc = FADD(acc, FMUL(fe_load_ro(a.sel + (6 + j) * m + i), FMUL(fe_sqr<Fr>(w2), w[j])));
+    }
+    const fe w01 = FMUL(w[0], w[1]), w23 = FMUL(w[2], w[3]);
+    acc = FADD(acc, FMUL(fe_load_ro(a.sel + 4 * m + i), w01));
+    acc = FADD(acc, FMUL(fe_load_ro(a.sel + 5 * m + i), w23));
+    acc = FADD(acc, FMUL(fe_load_ro(a.sel + 12 * m + i), FMUL(FMUL(w01, w23), w[4])));
+    acc = FSUB(acc, FMUL(fe_load_ro(a.sel + 10 * m + i), w[4]));
+    // permutation: alpha * ( z prod(w + beta k x + gamma) - z(wx) prod(w + beta sigma + gamma) )
+    const fe zx = fe_load_ro(a.ext + 5 * m + i);
+    const fe zxw = fe_load_ro(a.ext + 5 * m + ((i + 8) & (m - 1)));
+    const fe bx = FMUL(a.beta, fe_load_ro(a.pts + i));
+    fe p1 = zx, p2 = zxw;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const fe t = FADD(w[j], a.gamma);
+        p1 = FMUL(p1, FADD(t, FMUL(a.k.v[j], bx)));
+        p2 = FMUL(p2, FADD(t, FMUL(a.beta, fe_load_ro(a.sig + j * m + i))));
+    }
+    acc = FADD(acc, FMUL(a.alpha, FSUB(p1, p2)));
+    acc = FMUL(acc, a.zh_inv[i & 7]);
+    // alpha^2 (z - 1) L1(x) / Z_H(x)
+    acc = FADD(acc, FMUL(FMUL(a.alpha2, FSUB(zx, fe_one<Fr>())), fe_load_ro(a.l1_inv + i)));
+    fe_store(a.out + i, acc);
+}
+
+// flag bit 0: a coefficient above `deg` is non-zero; bit 1: coefficient `deg` is zero
+__global__ void k_check_degree(const fe* __restrict__ q, size_t deg, size_t m, uint32_t* flag) {
+    const size_t i = deg + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const bool zero = fe_is_zero(fe_load_ro(q + i));
+    if (i == deg) {
+        if (zero) atomicOr(flag, 2u);
+    } else if (!zero) {
+        atomicOr(flag, 1u);
+    }
+}
+
+struct SplitArgs {
+    fe b[4];
+};
+// t_i = quot[i(n+2) .. ) - b_{i-1} + b_i X^(n+2)   (the last chunk has n coefficients)
+__global__ void k_split_quotient(const fe* __restrict__ quot, size_t n, size_t stride, SplitArgs a, fe* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n + 3) return;
+    const size_t len = i < NW - 1 ? n + 2 : n;
+    fe v = j < len ? fe_load_ro(quot + (size_t)i * (n + 2) + j) : fe_zero();
+    if (j == 0 && i > 0) v = FSUB(v, a.b[i - 1]);
+    if (j == n + 2 && i < NW - 1) v = a.b[i];
+    fe_store(out + (size_t)i * stride + j, v);
+}
+
+// ---- round 5: linear combination of polynomials -------------------------------------------------------
+constexpr int kMaxLin = 32;
+struct LinArgs {
+    const fe* p[kMaxLin];
+    uint32_t len[kMaxLin];
+    fe s[kMaxLin];
+    int count;
+};
+__global__ void k_lincomb(LinArgs a, size_t out_len, fe* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= out_len) return;
+    fe acc = fe_zero();
+    for (int t = 0; t < a.count; ++t)
+        if (j < a.len[t]) acc = FADD(acc, FMUL(a.s[t], fe_load_ro(a.p[t] + j)));
+    fe_store(out + j, acc);
+}
+
+inline unsigned grid_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host-side structures
+// ---------------------------------------------------------------------------------------------
+struct ProvingKey {
+    unsigned log_n = 0;
+    size_t n = 0, m = 0, num_inputs = 0;
+    KArr k;
+    const Bases* srs = nullptr;
+    fe *sel_coeffs = nullptr, *sig_coeffs = nullptr, *sig_evals = nullptr;
+    fe *ce_sel = nullptr, *ce_sig = nullptr;
+    fe *dom = nullptr, *coset_pts = nullptr, *l1_inv = nullptr;
+    fe zh_inv[8];
+    fe group_gen;
+    g1_affine sel_comms[NS], sig_comms[NW];
+    ~ProvingKey() {
+        for (fe* p : {sel_coeffs, sig_coeffs, sig_evals, ce_sel, ce_sig, dom, coset_pts, l1_inv})
+            if (p) cudaFree(p);
+    }
+};
+
+static fe host_pow(fe a, uint64_t e) {
+    fe r = fe_one<Fr>();
+    while (e) {
+        if (e & 1) r = FMUL(r, a);
+        a = fe_sqr<Fr>(a);
+        e >>= 1;
+    }
+    return r;
+}
+static fe host_from_u64(uint64_t v) {
+    fe x = fe_zero();
+    x.l[0] = (uint32_t)v;
+    x.l[1] = (uint32_t)(v >> 32);
+    return fe_to_mont<Fr>(x);
+}
+
+// exclusive product scan of `data[0..n)` in place; scratch >= n/CH + n/CH^2 + 2*CH + 8 elements
+static void scan_mul_exclusive(fe* data, size_t n, fe* scratch, cudaStream_t st) {
+    if (n <= 1) {
+        // data[0] <- 1 handled by the local kernel as well
+    }
+    const size_t n1 = (n + CH - 1) / CH;
+    k_scan_mul_local<<<grid_for(n1, 128), 128, 0, st>>>(data, n, scratch);
+    if (n1 > 1) {
+        scan_mul_exclusive(scratch, n1, scratch + n1, st);
+        k_scan_mul_apply<<<grid_for(n, 256), 256, 0, st>>>(data, n, scratch);
+    }
+}
+
+// Horner suffix scan; S may be null (evaluation only).  The value p(z) ends up at out_total (device).
+// scratch >= 2 * (len/CH + len/CH^2 + 2*CH + 8) elements
+static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, fe* scratch, cudaStream_t st) {
+    const size_t n1 = (len + CH - 1) / CH;
+    fe* H = scratch;
+    fe* T = scratch + n1;
+    k_horner_local<<<grid_for(n1, 128), 128, 0, st>>>(p, len, z, S, H);
+    if (n1 == 1) {
+        cudaMemcpyAsync(out_total, H, sizeof(fe), cudaMemcpyDeviceToDevice, st);
+        return;
+    }
+    const fe zc = host_pow(z, CH);
+    horner_suffix(H, n1, zc, S ? T : nullptr, out_total, scratch + 2 * n1, st);
+    if (S) k_horner_apply<<<grid_for(n1, 128), 128, 0, st>>>(S, len, z, T, n1);
+}
+
+struct Workspace {
+    fe *wires_ev, *wpoly, *pi_poly, *zpoly, *num, *den, *tmp, *scan, *ext, *quot, *split, *lin, *sdiv, *hscr, *evals;
+    uint32_t* flag;
+    size_t S;  // stride of the (n + 3)-coefficient polynomials
+};
+static size_t workspace_elems(size_t n) {
+    const size_t S = n + 4, m = 8 * n;
+    return NW * n + NW * S + n + S + 3 * n + (n / CH + 4 * CH + 64) + 7 * m + m + NW * S + S + (S + 8) +
+           4 * (S / CH + 4 * CH + 64) + 32 + 8;
+}
+static Workspace carve(fe* base, size_t n) {
+    Workspace w;
+    const size_t S = n + 4, m = 8 * n;
+    w.S = S;
+    fe* p = base;
+    w.wires_ev = p; p += NW * n;
+    w.wpoly = p; p += NW * S;
+    w.pi_poly = p; p += n;
+    w.zpoly = p; p += S;
+    w.num = p; p += n;
+    w.den = p; p += n;
+    w.tmp = p; p += n;
+    w.scan = p; p += n / CH + 4 * CH + 64;
+    w.ext = p; p += 7 * m;
+    w.quot = p; p += m;
+    w.split = p; p += NW * S;
+    w.lin = p; p += S;
+    w.sdiv = p; p += S + 8;
+    w.hscr = p; p += 4 * (S / CH + 4 * CH + 64);
+    w.evals = p; p += 32;
+    w.flag = reinterpret_cast<uint32_t*>(p);
+    return w;
+}
+
+static int commit(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, g1_affine* out) {
+    int inf = 0;
+    int rc = msm_device(pk->srs, 0, d_coeffs, len, /*montgomery=*/1, &c->msm, c->stream, out, &inf);
+    if (rc != B200_OK) return rc;
+    if (inf) std::memset(out, 0, sizeof(*out));
+    return B200_OK;
+}
+
+static int alloc_fe(fe** p, size_t count) {
+    cudaError_t e = cudaMalloc(p, count * sizeof(fe));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(proving key)");
+    return B200_OK;
+}
+
+static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_inputs, const fe* h_selectors,
+                      const uint64_t* h_perm, const fe* h_k, ProvingKey** out) {
+    const size_t n = (size_t)1 << log_n, m = 8 * n;
+    if (log_n < 2 || log_n + 3 > 28) {
+        set_error("preprocess: log_n out of range");
+        return B200_ERR_INVALID;
+    }
+    if (srs->n < n + 3) {
+        set_error("preprocess: SRS shorter than n + 3 (MAX_SRS_DEGREE rule, srs.rs:44-47)");
+        return B200_ERR_INVALID;
+    }
+    if (num_inputs > n) return B200_ERR_INVALID;
+    cudaStream_t st = c->stream;
+    ProvingKey* pk = new ProvingKey();
+    pk->log_n = log_n;
+    pk->n = n;
+    pk->m = m;
+    pk->num_inputs = num_inputs;
+    pk->srs = srs;
+    for (int i = 0; i < NW; ++i) pk->k.v[i] = h_k[i];
+    int rc;
+    Domain *dn = nullptr, *dm = nullptr;
+    if ((rc = get_domain(c, log_n, &dn)) != B200_OK || (rc = get_domain(c, log_n + 3, &dm)) != B200_OK) {
+        delete pk;
+        return rc;
+    }
+    pk->group_gen = dn->group_gen;
+    uint64_t* d_perm = nullptr;
+    auto fail = [&](int code) {
+        if (d_perm) cudaFree(d_perm);
+        delete pk;
+        return code;
+    };
+    if ((rc = alloc_fe(&pk->sel_coeffs, NS * n)) || (rc = alloc_fe(&pk->sig_coeffs, NW * n)) ||
+        (rc = alloc_fe(&pk->sig_evals, NW * n)) || (rc = alloc_fe(&pk->ce_sel, NS * m)) ||
+        (rc = alloc_fe(&pk->ce_sig, NW * m)) || (rc = alloc_fe(&pk->dom, n)) || (rc = alloc_fe(&pk->coset_pts, m)) ||
+        (rc = alloc_fe(&pk->l1_inv, m)))
+        return fail(rc);
+    if (cudaMalloc(&d_perm, NW * n * 8) != cudaSuccess) return fail(B200_ERR_CUDA);
+    if ((rc = c->ntt_scratch.reserve((size_t)NS * m * sizeof(fe))) != B200_OK) return fail(rc);
+    fe* scratch = reinterpret_cast<fe*>(c->ntt_scratch.p);
+
+    const fe one = fe_one<Fr>();
+    const fe g = fe_from_u32<Fr>(5);
+    fill_powers(pk->dom, n, dn->group_gen, one, st);
+    fill_powers(pk->coset_pts, m, dm->group_gen, g, st);
+    for (int i = 0; i < 8; ++i) {
+        const fe x = FMUL(g, host_pow(dm->group_gen, (uint64_t)i));
+        pk->zh_inv[i] = fe_inv<Fr>(FSUB(host_pow(x, n), one));
+    }
+    k_l1_denominators<<<grid_for(m, 256), 256, 0, st>>>(pk->coset_pts, m, host_from_u64(n), pk->l1_inv);
+    k_batch_inverse<<<grid_for((m + 15) / 16, 128), 128, 0, st>>>(pk->l1_inv, pk->ce_sel /*scratch, overwritten below*/, m);
+
+    // selectors: evaluations -> coefficients -> commitments
+    cudaMemcpyAsync(pk->sel_coeffs, h_selectors, NS * n * sizeof(fe), cudaMemcpyHostToDevice, st);
+    if ((rc = ntt_device(dn, pk->sel_coeffs, scratch, 1, 0, NS, n, st)) != B200_OK) return fail(rc);
+    // sigmas: permutation -> evaluations (kept for the grand product) -> coefficients
+    cudaMemcpyAsync(d_perm, h_perm, NW * n * 8, cudaMemcpyHostToDevice, st);
+    k_sigma_evals<<<grid_for(NW * n, 256), 256, 0, st>>>(d_perm, pk->dom, n, pk->k, pk->sig_evals);
+    cudaMemcpyAsync(pk->sig_coeffs, pk->sig_evals, NW * n * sizeof(fe), cudaMemcpyDeviceToDevice, st);
+    if ((rc = ntt_device(dn, pk->sig_coeffs, scratch, 1, 0, NW, n, st)) != B200_OK) return fail(rc);
+    // resident coset evaluations over the 8n domain
+    cudaMemsetAsync(pk->ce_sel, 0, NS * m * sizeof(fe), st);
+    cudaMemsetAsync(pk->ce_sig, 0, NW * m * sizeof(fe), st);
+    cudaMemcpy2DAsync(pk->ce_sel, m * sizeof(fe), pk->sel_coeffs, n * sizeof(fe), n * sizeof(fe), NS,
+                      cudaMemcpyDeviceToDevice, st);
+    cudaMemcpy2DAsync(pk->ce_sig, m * sizeof(fe), pk->sig_coeffs, n * sizeof(fe), n * sizeof(fe), NW,
+                      cudaMemcpyDeviceToDevice, st);
+    if ((rc = ntt_device(dm, pk->ce_sel, scratch, 0, 1, NS, m, st)) != B200_OK) return fail(rc);
+    if ((rc = ntt_device(dm, pk->ce_sig, scratch, 0, 1, NW, m, st)) != B200_OK) return fail(rc);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "preprocess"));
+    cudaFree(d_perm);
+    d_perm = nullptr;
+    // the 18 commitments of the verifying key
+    for (int s = 0; s < NS; ++s)
+        if ((rc = commit(c, pk, pk->sel_coeffs + (size_t)s * n, n, &pk->sel_comms[s])) != B200_OK) return fail(rc);
+    for (int i = 0; i < NW; ++i)
+        if ((rc = commit(c, pk, pk->sig_coeffs + (size_t)i * n, n, &pk->sig_comms[i])) != B200_OK) return fail(rc);
+    *out = pk;
+    return B200_OK;
+}
+
+struct ProofOut {  // same field order and layout as b200_proof / PlonkProofDef
+    g1_affine wires_poly_comms[NW];
+    g1_affine prod_perm_poly_comm;
+    g1_affine split_quot_poly_comms[NW];
+    g1_affine opening_proof;
+    g1_affine shifted_opening_proof;
+    fe wires_evals[NW];
+    fe wire_sigma_evals[NW - 1];
+    fe perm_next_eval;
+};
+static_assert(sizeof(ProofOut) == sizeof(b200_proof), "proof layout");
+
+static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* h_pub_inputs, const fe* h_blinders,
+                 ProofOut* proof, fe* h_link_poly, fe* h_challenges) {
+    const size_t n = pk->n, m = pk->m;
+    const unsigned log_n = pk->log_n;
+    cudaStream_t st = c->stream;
+    int rc;
+    if ((rc = c->plonk_ws.reserve(workspace_elems(n) * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->ntt_scratch.reserve((size_t)7 * m * sizeof(fe))) != B200_OK) return rc;
+    Workspace w = carve(reinterpret_cast<fe*>(c->plonk_ws.p), n);
+    fe* nscr = reinterpret_cast<fe*>(c->ntt_scratch.p);
+    const size_t S = w.S;
+    Domain *dn = nullptr, *dm = nullptr;
+    if ((rc = get_domain(c, log_n, &dn)) != B200_OK || (rc = get_domain(c, log_n + 3, &dm)) != B200_OK) return rc;
+    const fe one = fe_one<Fr>();
+
+    SolidityTranscript tr;
+    tr.append_u32_be(254);  // field size in bits
+    tr.append_u64_be((uint64_t)n);
+    tr.append_u64_be((uint64_t)pk->num_inputs);
+    for (int i = 0; i < NW; ++i) tr.append_field_elem(pk->k.v[i]);
+    for (int s = 0; s < NS; ++s) tr.append_commitment(pk->sel_comms[s]);
+    for (int i = 0; i < NW; ++i) tr.append_commitment(pk->sig_comms[i]);
+    for (size_t i = 0; i < pk->num_inputs; ++i) tr.append_field_elem(h_pub_inputs[i]);
+
+    // ---- round 1 ------------------------------------------------------------------------------------
+    B200_CUDA(cudaMemcpyAsync(w.wires_ev, h_wires, NW * n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(w.wpoly, 0, NW * S * sizeof(fe), st));
+    B200_CUDA(cudaMemcpy2DAsync(w.wpoly, S * sizeof(fe), w.wires_ev, n * sizeof(fe), n * sizeof(fe), NW,
+                                cudaMemcpyDeviceToDevice, st));
+    if ((rc = ntt_device(dn, w.wpoly, nscr, 1, 0, NW, S, st)) != B200_OK) return rc;
+    for (int i = 0; i < NW; ++i) {
+        BlindArgs b;
+        b.count = 2;
+        b.b[0] = h_blinders[2 * i];
+        b.b[1] = h_blinders[2 * i + 1];
+        b.b[2] = fe_zero();
+        k_blind<<<1, 32, 0, st>>>(w.wpoly + (size_t)i * S, n, b);
+    }
+    B200_CUDA(cudaMemsetAsync(w.pi_poly, 0, n * sizeof(fe), st));
+    if (pk->num_inputs)
+        B200_CUDA(cudaMemcpyAsync(w.pi_poly, h_pub_inputs, pk->num_inputs * sizeof(fe), cudaMemcpyHostToDevice, st));
+    if ((rc = ntt_device(dn, w.pi_poly, nscr, 1, 0, 1, n, st)) != B200_OK) return rc;
+    for (int i = 0; i < NW; ++i)
+        if ((rc = commit(c, pk, w.wpoly + (size_t)i * S, n + 2, &proof->wires_poly_comms[i])) != B200_OK) return rc;
+    if (h_link_poly)
+        B200_CUDA(cudaMemcpyAsync(h_link_poly, w.wpoly, (n + 2) * sizeof(fe), cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < NW; ++i) tr.append_commitment(proof->wires_poly_comms[i]);
+
+    // ---- round 2 ------------------------------------------------------------------------------------
+    const fe beta = tr.get_and_append_challenge();
+    const fe gamma = tr.get_and_append_challenge();
+    k_perm_num_den<<<grid_for(n, 128), 128, 0, st>>>(w.wires_ev, pk->sig_evals, pk->dom, pk->k, beta, gamma, n, w.num, w.den);
+    k_ratio<<<grid_for((n + 15) / 16, 64), 64, 0, st>>>(w.num, w.den, w.tmp, n);
+    scan_mul_exclusive(w.den, n, w.scan, st);  // z(w^j) = prod_{i<j} ratio_i
+    B200_CUDA(cudaMemsetAsync(w.zpoly, 0, S * sizeof(fe), st));
+    B200_CUDA(cudaMemcpyAsync(w.zpoly, w.den, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    if ((rc = ntt_device(dn, w.zpoly, nscr, 1, 0, 1, S, st)) != B200_OK) return rc;
+    {
+        BlindArgs b;
+        b.count = 3;
+        for (int i = 0; i < 3; ++i) b.b[i] = h_blinders[10 + i];
+        k_blind<<<1, 32, 0, st>>>(w.zpoly, n, b);
+    }
+    if ((rc = commit(c, pk, w.zpoly, n + 3, &proof->prod_perm_poly_comm)) != B200_OK) return rc;
+    tr.append_commitment(proof->prod_perm_poly_comm);
+
+    // ---- round 3 ------------------------------------------------------------------------------------
+    const fe alpha = tr.get_and_append_challenge();
+    B200_CUDA(cudaMemsetAsync(w.ext, 0, 7 * m * sizeof(fe), st));
+    B200_CUDA(cudaMemcpy2DAsync(w.ext, m * sizeof(fe), w.wpoly, S * sizeof(fe), (n + 2) * sizeof(fe), NW,
+                                cudaMemcpyDeviceToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(w.ext + 5 * m, w.zpoly, (n + 3) * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(w.ext + 6 * m, w.pi_poly, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    if ((rc = ntt_device(dm, w.ext, nscr, 0, 1, 7, m, st)) != B200_OK) return rc;
+    {
+        QuotArgs q;
+        q.sel = pk->ce_sel;
+        q.sig = pk->ce_sig;
+        q.ext = w.ext;
+        q.pts = pk->coset_pts;
+        q.l1_inv = pk->l1_inv;
+        q.out = w.quot;
+        q.m = m;
+        q.k = pk->k;
+        q.beta = beta;
+        q.gamma = gamma;
+        q.alpha = alpha;
+        q.alpha2 = fe_sqr<Fr>(alpha);
+        for (int i = 0; i < 8; ++i) q.zh_inv[i] = pk->zh_inv[i];
+        k_quotient<<<grid_for(m, 128), 128, 0, st>>>(q);
+    }
+    if ((rc = ntt_device(dm, w.quot, nscr, 1, 1, 1, m, st)) != B200_OK) return rc;
+    const size_t deg = NW * (n + 1) + 2;
+    B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
+    k_check_degree<<<grid_for(m - deg, 256), 256, 0, st>>>(w.quot, deg, m, w.flag);
+    uint32_t h_flag = 0;
+    B200_CUDA(cudaMemcpyAsync(&h_flag, w.flag, 4, cudaMemcpyDeviceToHost, st));
+    {
+        SplitArgs sa;
+        for (int i = 0; i < 4; ++i) sa.b[i] = h_blinders[13 + i];
+        k_split_quotient<<<dim3(grid_for(n + 3, 256), NW), 256, 0, st>>>(w.quot, n, S, sa, w.split);
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (h_flag) {
+        set_error("WrongQuotientPolyDegree: the witness does not satisfy the circuit");
+        return B200_ERR_UNSATISFIED;
+    }
+    for (int i = 0; i < NW; ++i) {
+        const size_t len = i < NW - 1 ? n + 3 : n;
+        if ((rc = commit(c, pk, w.split + (size_t)i * S, len, &proof->split_quot_poly_comms[i])) != B200_OK) return rc;
+    }
+    for (int i = 0; i < NW; ++i) tr.append_commitment(proof->split_quot_poly_comms[i]);
+
+    // ---- round 4 ------------------------------------------------------------------------------------
+    const fe zeta = tr.get_and_append_challenge();
+    const fe zeta_w = FMUL(zeta, pk->group_gen);
+    for (int i = 0; i < NW; ++i) horner_suffix(w.wpoly + (size_t)i * S, n + 2, zeta, nullptr, w.evals + i, w.hscr, st);
+    for (int i = 0; i < NW - 1; ++i)
+        horner_suffix(pk->sig_coeffs + (size_t)i * n, n, zeta, nullptr, w.evals + NW + i, w.hscr, st);
+    horner_suffix(w.zpoly, n + 3, zeta_w, nullptr, w.evals + 2 * NW - 1, w.hscr, st);
+    fe h_evals[2 * NW];
+    B200_CUDA(cudaMemcpyAsync(h_evals, w.evals, sizeof(h_evals), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < NW; ++i) proof->wires_evals[i] = h_evals[i];
+    for (int i = 0; i < NW - 1; ++i) proof->wire_sigma_evals[i] = h_evals[NW + i];
+    proof->perm_next_eval = h_evals[2 * NW - 1];
+    for (int i = 0; i < NW; ++i) tr.append_field_elem(proof->wires_evals[i]);
+    for (int i = 0; i < NW - 1; ++i) tr.append_field_elem(proof->wire_sigma_evals[i]);
+    tr.append_field_elem(proof->perm_next_eval);
+
+    // ---- round 5 ------------------------------------------------------------------------------------
+    const fe v = tr.get_and_append_challenge();
+    {
+        const fe* we = proof->wires_evals;
+        const fe* se = proof->wire_sigma_evals;
+        LinArgs a;
+        int t = 0;
+        auto push = [&](const fe* p, size_t len, const fe& s) {
+            a.p[t] = p;
+            a.len[t] = (uint32_t)len;
+            a.s[t] = s;
+            ++t;
+        };
+        auto pow5 = [&](const fe& x) { return FMUL(fe_sqr<Fr>(fe_sqr<Fr>(x)), x); };
+        const fe* sel = pk->sel_coeffs;
+        for (int j = 0; j < 4; ++j) push(sel + (size_t)j * n, n, we[j]);
+        push(sel + 4 * n, n, FMUL(we[0], we[1]));
+        push(sel + 5 * n, n, FMUL(we[2], we[3]));
+        for (int j = 0; j < 4; ++j) push(sel + (size_t)(6 + j) * n, n, pow5(we[j]));
+        push(sel + 10 * n, n, fe_neg<Fr>(we[4]));
+        push(sel + 11 * n, n, one);
+        push(sel + 12 * n, n, FMUL(FMUL(FMUL(we[0], we[1]), FMUL(we[2], we[3])), we[4]));
+        // z(X): alpha prod(w_i + beta k_i zeta + gamma) + alpha^2 L1(zeta)
+        const fe vanish = FSUB(host_pow(zeta, n), one);
+        const fe l1 = FMUL(vanish, fe_inv<Fr>(FMUL(host_from_u64(n), FSUB(zeta, one))));
+        fe cz = alpha;
+        for (int j = 0; j < NW; ++j) cz = FMUL(cz, FADD(FADD(we[j], FMUL(FMUL(pk->k.v[j], zeta), beta)), gamma));
+        cz = FADD(cz, FMUL(fe_sqr<Fr>(alpha), l1));
+        push(w.zpoly, n + 3, cz);
+        // sigma_4(X): -alpha beta z(zeta w) prod_{i<4}(w_i + beta sigma_i + gamma)
+        fe cs = FMUL(FMUL(alpha, beta), proof->perm_next_eval);
+        for (int j = 0; j < NW - 1; ++j) cs = FMUL(cs, FADD(FADD(we[j], FMUL(beta, se[j])), gamma));
+        push(pk->sig_coeffs + (size_t)(NW - 1) * n, n, fe_neg<Fr>(cs));
+        // - Z_H(zeta) * sum zeta^((n+2) i) t_i(X)
+        const fe zn2 = FMUL(FMUL(FADD(vanish, one), zeta), zeta);
+        fe ct = fe_neg<Fr>(vanish);
+        for (int i = 0; i < NW; ++i) {
+            push(w.split + (size_t)i * S, i < NW - 1 ? n + 3 : n, ct);
+            ct = FMUL(ct, zn2);
+        }
+        // batched opening at zeta: lin + v w_0 + ... + v^5 w_4 + v^6 sigma_0 + ... + v^9 sigma_3
+        fe cv = one;
+        for (int i = 0; i < NW; ++i) {
+            cv = FMUL(cv, v);
+            push(w.wpoly + (size_t)i * S, n + 2, cv);
+        }
+        for (int i = 0; i < NW - 1; ++i) {
+            cv = FMUL(cv, v);
+            push(pk->sig_coeffs + (size_t)i * n, n, cv);
+        }
+        a.count = t;
+        k_lincomb<<<grid_for(n + 3, 128), 128, 0, st>>>(a, n + 3, w.lin);
+    }
+    // opening proofs: commit((batch - batch(zeta)) / (X - zeta)) and commit((z - z(zeta w)) / (X - zeta w))
+    horner_suffix(w.lin, n + 3, zeta, w.sdiv, w.evals + 16, w.hscr, st);
+    if ((rc = commit(c, pk, w.sdiv + 1, n + 2, &proof->opening_proof)) != B200_OK) return rc;
+    horner_suffix(w.zpoly, n + 3, zeta_w, w.sdiv, w.evals + 17, w.hscr, st);
+    if ((rc = commit(c, pk, w.sdiv + 1, n + 2, &proof->shifted_opening_proof)) != B200_OK) return rc;
+    if (h_challenges) {
+        tr.append_commitment(proof->opening_proof);
+        tr.append_commitment(proof->shifted_opening_proof);
+        const fe u = tr.get_and_append_challenge();
+        const fe all[6] = {beta, gamma, alpha, zeta, v, u};
+        std::memcpy(h_challenges, all, sizeof(all));
+    }
+    return B200_OK;
+}
+
+}  // namespace b200
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace b200;
+
+struct b200_pk {
+    ProvingKey* pk;
+};
+
+extern "C" {
+
+int b200_plonk_preprocess(b200_ctx* ctx, const b200_bases* srs, unsigned log_n, size_t num_inputs,
+                          const uint64_t* selectors_evals, const uint64_t* perm, const uint64_t* k, b200_pk** out) {
+    B200_TRY
+    if (!ctx || !srs || !selectors_evals || !perm || !k || !out) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    ProvingKey* pk = nullptr;
+    int rc = preprocess(&ctx->c, srs->b, log_n, num_inputs, reinterpret_cast<const fe*>(selectors_evals), perm,
+                        reinterpret_cast<const fe*>(k), &pk);
+    if (rc != B200_OK) return rc;
+    *out = new b200_pk{pk};
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t* sigma_comms) {
+    if (!pk || !selector_comms || !sigma_comms) return B200_ERR_INVALID;
+    std::memcpy(selector_comms, pk->pk->sel_comms, sizeof(pk->pk->sel_comms));
+    std::memcpy(sigma_comms, pk->pk->sig_comms, sizeof(pk->pk->sig_comms));
+    return B200_OK;
+}
+
+void b200_pk_free(b200_ctx* ctx, b200_pk* pk) {
+    if (!pk) return;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->c.mu);
+        cudaSetDevice(ctx->c.device);
+        cudaStreamSynchronize(ctx->c.stream);
+        delete pk->pk;
+    } else {
+        delete pk->pk;
+    }
+    delete pk;
+}
+
+int b200_plonk_prove(b200_ctx* ctx, const b200_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
+                     const uint64_t* blinders, b200_proof* proof, uint64_t* link_poly, uint64_t* challenges) {
+    B200_TRY
+    if (!ctx || !pk || !wires || !blinders || !proof || (pk->pk->num_inputs && !pub_inputs)) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    return prove(&ctx->c, pk->pk, reinterpret_cast<const fe*>(wires), reinterpret_cast<const fe*>(pub_inputs),
+                 reinterpret_cast<const fe*>(blinders), reinterpret_cast<ProofOut*>(proof),
+                 reinterpret_cast<fe*>(link_poly), reinterpret_cast<fe*>(challenges));
+    B200_CATCH
+}
+
+}  // extern "C"

@@ -105,3 +105,16 @@ def test_shard_range():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_keccak256_known_answers(oracle):
+    """Transcript hash of the product (C++) pinned by the Keccak-256 known answers, and equal to
+    the oracle's independent C implementation on random lengths (block boundaries 135/136/137)."""
+    from renegade_b200.backend import keccak256
+    assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    import random
+    rnd = random.Random(7)
+    for ln in (1, 55, 135, 136, 137, 271, 272, 273, 1000):
+        msg = bytes(rnd.randrange(256) for _ in range(ln))
+        assert keccak256(msg) == oracle.keccak256(msg), ln
