@@ -103,6 +103,13 @@ int b200_msm_device(b200_ctx* ctx, const b200_bases* bases, size_t base_off,
                     const void* d_scalars, size_t n, int scalars_montgomery, uint64_t out_xy[8],
                     int* out_is_identity);
 
+/* `batch` MSMs over the same bases in one pass: scalar vector i starts at d_scalars + i*stride
+ * (elements), each of n scalars; out_xy receives batch x 64 bytes.  Replaces jf-primitives
+ * `UnivariateKzgPCS::batch_commit` (the 5 wire / 5 quotient commitments of a proof). */
+int b200_msm_batch_device(b200_ctx* ctx, const b200_bases* bases, size_t base_off,
+                          const void* d_scalars, size_t n, size_t stride, unsigned batch,
+                          int scalars_montgomery, uint64_t* out_xy, int* out_is_identity);
+
 /* Device-side phase timing (CUDA events recorded on the context's stream).  enable != 0 turns
  * it on for subsequent MSM calls; out_ms (may be NULL) receives the last call's
  * {total, sort = count+scan+scatter, bucket accumulation, bucket reduction} in ms. */
@@ -153,7 +160,8 @@ int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t*
 void b200_pk_free(b200_ctx* ctx, b200_pk* pk);
 
 /* Replaces `PlonkKzgSnark::prove_with_link_hint::<_, _, SolidityTranscript>(&mut rng, &circuit,
- * &pk)` (traits.rs:996).  wires: 5 x n wire values (the witness table after synthesis);
+ * &pk)` (traits.rs:996).  wires: 5 x n wire values (the witness table after synthesis; host
+ * or device pointer);
  * pub_inputs: num_inputs values; blinders: the 17 Fr elements the reference draws from its RNG
  * (2 per wire polynomial, 3 for the permutation product, 4 for the quotient split), in draw
  * order, supplied by the caller so both sides can be made deterministic.
@@ -164,6 +172,10 @@ void b200_pk_free(b200_ctx* ctx, b200_pk* pk);
 int b200_plonk_prove(b200_ctx* ctx, const b200_pk* pk, const uint64_t* wires,
                      const uint64_t* pub_inputs, const uint64_t* blinders, b200_proof* proof,
                      uint64_t* link_poly, uint64_t* challenges);
+
+/* Wall-clock milliseconds of the last proof's phases on this context: round 1, round 2, round 3
+ * (coset NTTs + quotient + split), round 3 commitments, round 4, round 5, then two spare slots. */
+int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]);
 
 /* Keccak-256 of the transcript (host; exported so the hash can be pinned by known answers). */
 void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);

@@ -349,3 +349,20 @@ def keccak256(data: bytes) -> bytes:
     out = (C.c_uint8 * 32)()
     _lib.load().b200_keccak256(data, len(data), out)
     return bytes(out)
+
+
+def plonk_last_timings(ctx: Context) -> dict:
+    arr = (C.c_float * 8)()
+    _lib.check(ctx._lib.b200_plonk_last_timings(ctx._h, C.byref(arr)))
+    names = ("round1", "round2", "round3_quotient", "round3_commit", "round4", "round5")
+    return {k: arr[i] for i, k in enumerate(names)}
+
+
+def prove_raw(ctx: Context, pk: ProvingKey, wires_ptr: int, pub_inputs: np.ndarray, blinders: np.ndarray) -> B200Proof:
+    """prove with the wire table given by address (pinned host or device memory)."""
+    proof = B200Proof()
+    pi = np.ascontiguousarray(pub_inputs, dtype=np.uint64)
+    bl = np.ascontiguousarray(blinders, dtype=np.uint64)
+    _lib.check(ctx._lib.b200_plonk_prove(ctx._h, pk._h, C.c_void_p(wires_ptr), _ptr(pi) if pi.size else None, _ptr(bl),
+                                         C.byref(proof), None, None))
+    return proof

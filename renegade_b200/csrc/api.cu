@@ -344,6 +344,25 @@ int b200_g1_sum_affine(const uint64_t* points_xy, const int* is_identity, size_t
     B200_CATCH
 }
 
+int b200_msm_batch_device(b200_ctx* ctx, const b200_bases* bases, size_t base_off, const void* d_scalars, size_t n,
+                          size_t stride, unsigned batch, int scalars_montgomery, uint64_t* out_xy,
+                          int* out_is_identity) {
+    B200_TRY
+    if (!ctx || !bases || !out_xy || (n && !d_scalars) || batch == 0 || batch > 64 || stride < n) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    std::vector<g1_affine> r(batch);
+    std::vector<int> inf(batch, 0);
+    int rc = msm_device_batch(bases->b, base_off, reinterpret_cast<const fe*>(d_scalars), n, stride, batch,
+                              scalars_montgomery, &ctx->c.msm, ctx->c.stream, r.data(), inf.data());
+    if (rc != B200_OK) return rc;
+    std::memcpy(out_xy, r.data(), (size_t)batch * 64);
+    if (out_is_identity)
+        for (unsigned i = 0; i < batch; ++i) out_is_identity[i] = inf[i];
+    return B200_OK;
+    B200_CATCH
+}
+
 int b200_msm_timing(b200_ctx* ctx, int enable, float out_ms[4]) {
     B200_TRY
     if (!ctx) return B200_ERR_INVALID;

@@ -102,6 +102,9 @@ int bases_create_device(const g1_affine* d_points, size_t n, int c_override, cud
 // combined there (Horner + one inversion).
 int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, int montgomery,
                MsmScratch* s, cudaStream_t st, g1_affine* out, int* out_inf);
+int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
+                     unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st, g1_affine* out,
+                     int* out_inf);
 // synthetic known-discrete-log bases P_i = a_i * G, a_i = SplitMix64-derived
 int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
                                cudaStream_t st);
@@ -120,6 +123,7 @@ struct Context {
     float ntt_last_ms = 0.f;  // device time of the last b200_ntt_device call (CUDA events)
     MsmScratch msm;
     DevBuf plonk_ws;  // prover workspace (plonk.cu)
+    float plonk_ms[8] = {0};  // wall time of the last proof's phases
     ~Context();
 };
 

@@ -73,21 +73,26 @@ __device__ __forceinline__ void for_each_digit(const fe* scalars, size_t i, int 
     }
 }
 
-__global__ void msm_count_kernel(const fe* scalars, size_t n, int montgomery, MsmPlan pl,
-                                 uint32_t* counts) {
+// blockIdx.y = index of the MSM inside a batch (same bases, `stride` scalars apart); every MSM owns
+// its own range of `buckets_per_msm` buckets, so the later phases see one big bucket array.
+__global__ void msm_count_kernel(const fe* scalars, size_t n, size_t stride, int montgomery, MsmPlan pl,
+                                 uint32_t buckets_per_msm, uint32_t* counts) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for_each_digit(scalars, i, montgomery, pl, (uint32_t)i,
-                   [&](uint32_t bucket, uint32_t) { atomicAdd(counts + bucket, 1u); });
+    uint32_t* my = counts + (size_t)blockIdx.y * buckets_per_msm;
+    for_each_digit(scalars + (size_t)blockIdx.y * stride, i, montgomery, pl, (uint32_t)i,
+                   [&](uint32_t bucket, uint32_t) { atomicAdd(my + bucket, 1u); });
 }
 
-__global__ void msm_scatter_kernel(const fe* scalars, size_t n, int montgomery, MsmPlan pl,
-                                   uint32_t base_off, uint32_t* cursor, uint32_t* entries) {
+__global__ void msm_scatter_kernel(const fe* scalars, size_t n, size_t stride, int montgomery, MsmPlan pl,
+                                   uint32_t base_off, uint32_t buckets_per_msm, uint32_t* cursor,
+                                   uint32_t* entries) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for_each_digit(scalars, i, montgomery, pl, (uint32_t)i + base_off,
+    uint32_t* my = cursor + (size_t)blockIdx.y * buckets_per_msm;
+    for_each_digit(scalars + (size_t)blockIdx.y * stride, i, montgomery, pl, (uint32_t)i + base_off,
                    [&](uint32_t bucket, uint32_t code) {
-                       const uint32_t pos = atomicAdd(cursor + bucket, 1u);
+                       const uint32_t pos = atomicAdd(my + bucket, 1u);
                        entries[pos] = code;
                    });
 }
@@ -547,24 +552,33 @@ static int exclusive_scan_u32(In d_in, size_t n, uint32_t* d_out, DevBuf* chunk_
     return B200_OK;
 }
 
-int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, int montgomery,
-               MsmScratch* s, cudaStream_t st, g1_affine* out, int* out_inf) {
+// `batch` MSMs over the same bases (scalar vectors `stride` elements apart) in one pass: the
+// digit sort, the bucket folding and the reduction each run once over batch * buckets buckets,
+// which is what fills 148 SMs at the prover's 2^16-point sizes.
+int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
+                     unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st, g1_affine* out,
+                     int* out_inf) {
     if (base_off + n > b->n) {
         set_error("msm: base_off + n exceeds the loaded bases");
         return B200_ERR_INVALID;
     }
+    if (batch == 0) return B200_OK;
     if (n == 0) {
-        out->x = fe_zero();
-        out->y = fe_zero();
-        if (out_inf) *out_inf = 1;
+        for (unsigned i = 0; i < batch; ++i) {
+            out[i].x = fe_zero();
+            out[i].y = fe_zero();
+            if (out_inf) out_inf[i] = 1;
+        }
         return B200_OK;
     }
     const MsmPlan& pl = b->plan;
     const uint32_t half = 1u << (pl.c - 1);
-    const size_t n_buckets = (size_t)pl.n_phys * half;
-    const size_t max_entries = n * (size_t)pl.n_digits;
-    if (max_entries >= ((size_t)1 << 32)) {
-        set_error("msm: n * windows exceeds 2^32 entries");
+    const size_t buckets_per_msm = (size_t)pl.n_phys * half;
+    const size_t n_buckets = buckets_per_msm * batch;
+    const size_t n_windows = (size_t)pl.n_phys * batch;
+    const size_t max_entries = n * (size_t)pl.n_digits * batch;
+    if (max_entries >= ((size_t)1 << 32) || n_buckets >= ((size_t)1 << 31)) {
+        set_error("msm: batch * n * windows exceeds 2^32 entries");
         return B200_ERR_INVALID;
     }
     int rc;
@@ -582,8 +596,8 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     const uint32_t reduce_threads_needed = (half + kReduceChunk - 1) / kReduceChunk;
     const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
-    if ((rc = s->partials.reserve((size_t)pl.n_phys * reduce_blocks * sizeof(g1_xyzz))) != B200_OK) return rc;
-    if ((rc = s->window_sums.reserve((size_t)pl.n_phys * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->partials.reserve(n_windows * reduce_blocks * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
 
     uint32_t* counts = (uint32_t*)s->counts.p;
     uint32_t* offsets = (uint32_t*)s->offsets.p;
@@ -605,11 +619,12 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
     if (s->timing) cudaEventRecord(s->ev[0], st);
     B200_CUDA(cudaMemsetAsync(counts, 0, n_buckets * 4, st));
     const unsigned bs = 256;
-    const unsigned grid_n = (unsigned)((n + bs - 1) / bs);
-    msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, montgomery, pl, counts);
+    const dim3 grid_n((unsigned)((n + bs - 1) / bs), batch);
+    msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)buckets_per_msm, counts);
     if ((rc = exclusive_scan_u32(ScanCounts{counts}, n_buckets, offsets, &s->block_sums, st)) != B200_OK) return rc;
     B200_CUDA(cudaMemcpyAsync(cursor, offsets, n_buckets * 4, cudaMemcpyDeviceToDevice, st));
-    msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, montgomery, pl, (uint32_t)base_off, cursor, entries);
+    msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)base_off,
+                                              (uint32_t)buckets_per_msm, cursor, entries);
     if ((rc = exclusive_scan_u32(ScanSegCounts{offsets}, n_buckets, seg_offsets, &s->block_sums, st)) != B200_OK) return rc;
     msm_segfill_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(seg_offsets, (uint32_t)n_buckets, seg_bucket);
     B200_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
@@ -621,14 +636,13 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
     msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(
         seg_sums, seg_offsets, heavy_count, heavy_list, buckets);
     if (s->timing) cudaEventRecord(s->ev[2], st);
-    msm_reduce_kernel<<<dim3(reduce_blocks, pl.n_phys), kReduceThreads, 0, st>>>(buckets, half, pl.c, partials);
-    msm_reduce_final_kernel<<<pl.n_phys, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);
+    msm_reduce_kernel<<<dim3(reduce_blocks, (unsigned)n_windows), kReduceThreads, 0, st>>>(buckets, half, pl.c, partials);
+    msm_reduce_final_kernel<<<(unsigned)n_windows, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);
     B200_CUDA(cudaGetLastError());
 
-    std::vector<g1_xyzz> h_sums(pl.n_phys);
+    std::vector<g1_xyzz> h_sums(n_windows);
     if (s->timing) cudaEventRecord(s->ev[3], st);
-    B200_CUDA(cudaMemcpyAsync(h_sums.data(), window_sums, (size_t)pl.n_phys * sizeof(g1_xyzz),
-                              cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(h_sums.data(), window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     if (s->timing) cudaEventRecord(s->ev[4], st);
     B200_CUDA(cudaStreamSynchronize(st));
     if (s->timing) {
@@ -638,16 +652,24 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
         cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
     }
 
-    // host epilogue: Horner over the physical windows (none when fully precomputed) and the one
-    // field inversion of the affine normalisation — a few hundred bytes of work.
-    g1_xyzz total = h_sums[pl.n_phys - 1];
-    for (int p = pl.n_phys - 2; p >= 0; --p) {
-        for (int k = 0; k < pl.c; ++k) total = g1_dbl(total);
-        total = g1_add(total, h_sums[p]);
+    // host epilogue per MSM: Horner over the physical windows (none when fully precomputed) and
+    // the one field inversion of the affine normalisation — a few hundred bytes of work.
+    for (unsigned i = 0; i < batch; ++i) {
+        const g1_xyzz* hs = h_sums.data() + (size_t)i * pl.n_phys;
+        g1_xyzz total = hs[pl.n_phys - 1];
+        for (int p = pl.n_phys - 2; p >= 0; --p) {
+            for (int k = 0; k < pl.c; ++k) total = g1_dbl(total);
+            total = g1_add(total, hs[p]);
+        }
+        out[i] = g1_to_affine(total);
+        if (out_inf) out_inf[i] = g1_xyzz_is_inf(total) ? 1 : 0;
     }
-    *out = g1_to_affine(total);
-    if (out_inf) *out_inf = g1_xyzz_is_inf(total) ? 1 : 0;
     return B200_OK;
+}
+
+int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, int montgomery,
+               MsmScratch* s, cudaStream_t st, g1_affine* out, int* out_inf) {
+    return msm_device_batch(b, base_off, d_scalars, n, n, 1, montgomery, s, st, out, out_inf);
 }
 
 int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,

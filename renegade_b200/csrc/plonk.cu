@@ -14,6 +14,7 @@
 // keys) — so a proof runs 7 size-8n coset NTTs instead of the reference's 25.  Polynomials never
 // leave the device between rounds; the host sees 13 commitments and 10 evaluations and runs the
 // (serial, few-KB) Keccak transcript between rounds.
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -159,6 +160,26 @@ __global__ void k_horner_local(const fe* __restrict__ p, size_t len, fe z, fe* _
         if (S) fe_store(S + i, run);
     }
     fe_store(H + t, run);
+}
+// batched evaluation-only variant: blockIdx.y selects the polynomial
+constexpr int kMaxEval = 10;
+struct EvalArgs {
+    const fe* p[kMaxEval];
+    fe* H[kMaxEval];
+    fe z[kMaxEval];
+    uint32_t len[kMaxEval];
+};
+__global__ void k_horner_local_batch(EvalArgs a) {
+    const int q = blockIdx.y;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t beg = t * CH, len = a.len[q];
+    if (beg >= len) return;
+    const size_t end = beg + CH < len ? beg + CH : len;
+    const fe z = a.z[q];
+    const fe* p = a.p[q];
+    fe run = fe_zero();
+    for (size_t i = end; i-- > beg;) run = FADD(FMUL(run, z), fe_load_ro(p + i));
+    fe_store(a.H[q] + t, run);
 }
 // S[j] += z^(chunk_end - j) * T[chunk + 1]
 __global__ void k_horner_apply(fe* __restrict__ S, size_t len, fe z, const fe* __restrict__ T, size_t n_chunks) {
@@ -338,15 +359,56 @@ static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, f
     if (S) k_horner_apply<<<grid_for(n1, 128), 128, 0, st>>>(S, len, z, T, n1);
 }
 
+// p_q(z_q) for up to kMaxEval polynomials, written to out[q];
+// scratch: count * (max_len/CH + max_len/CH^2 + 2*CH + 16)
+static void eval_batch(const fe* const* polys, const size_t* lens, const fe* points, int count, fe* out, fe* scratch,
+                       cudaStream_t st) {
+    EvalArgs a;
+    size_t cur_len[kMaxEval], max_len = 0;
+    for (int q = 0; q < count; ++q) {
+        a.p[q] = polys[q];
+        a.z[q] = points[q];
+        cur_len[q] = lens[q];
+        max_len = lens[q] > max_len ? lens[q] : max_len;
+    }
+    // two disjoint regions per polynomial (levels alternate A, B, A, ...): a level reads one and
+    // writes the other
+    const size_t region_a = max_len / CH + 2, region_b = max_len / CH / CH + CH + 2;
+    const size_t per_poly = region_a + region_b;
+    int level = 0;
+    while (true) {
+        bool last = true;
+        size_t max_chunks = 0;
+        for (int q = 0; q < count; ++q) {
+            const size_t n1 = (cur_len[q] + CH - 1) / CH;
+            if (n1 > 1) last = false;
+            max_chunks = n1 > max_chunks ? n1 : max_chunks;
+        }
+        for (int q = 0; q < count; ++q) {
+            a.len[q] = (uint32_t)cur_len[q];
+            // levels alternate between the two halves of each polynomial's scratch slice
+            a.H[q] = last ? out + q : scratch + (size_t)q * per_poly + (level & 1 ? region_a : 0);
+        }
+        k_horner_local_batch<<<dim3(grid_for(max_chunks, 64), count), 64, 0, st>>>(a);
+        if (last) break;
+        for (int q = 0; q < count; ++q) {
+            a.p[q] = a.H[q];
+            a.z[q] = host_pow(a.z[q], CH);
+            cur_len[q] = (cur_len[q] + CH - 1) / CH;
+        }
+        ++level;
+    }
+}
+
 struct Workspace {
-    fe *wires_ev, *wpoly, *pi_poly, *zpoly, *num, *den, *tmp, *scan, *ext, *quot, *split, *lin, *sdiv, *hscr, *evals;
+    fe *wires_ev, *wpoly, *pi_poly, *zpoly, *num, *den, *tmp, *scan, *ext, *quot, *split, *lin, *sdiv, *hscr, *escr, *evals;
     uint32_t* flag;
     size_t S;  // stride of the (n + 3)-coefficient polynomials
 };
 static size_t workspace_elems(size_t n) {
     const size_t S = n + 4, m = 8 * n;
-    return NW * n + NW * S + n + S + 3 * n + (n / CH + 4 * CH + 64) + 7 * m + m + NW * S + S + (S + 8) +
-           4 * (S / CH + 4 * CH + 64) + 32 + 8;
+    return NW * n + NW * S + n + S + 3 * n + (n / CH + 4 * CH + 64) + 7 * m + m + NW * S + S + 2 * (S + 8) +
+           4 * (S / CH + 4 * CH + 64) + kMaxEval * (S / CH + S / CH / CH + 2 * CH + 16) + 32 + 8;
 }
 static Workspace carve(fe* base, size_t n) {
     Workspace w;
@@ -365,8 +427,9 @@ static Workspace carve(fe* base, size_t n) {
     w.quot = p; p += m;
     w.split = p; p += NW * S;
     w.lin = p; p += S;
-    w.sdiv = p; p += S + 8;
+    w.sdiv = p; p += 2 * (S + 8);
     w.hscr = p; p += 4 * (S / CH + 4 * CH + 64);
+    w.escr = p; p += kMaxEval * (S / CH + S / CH / CH + 2 * CH + 16);
     w.evals = p; p += 32;
     w.flag = reinterpret_cast<uint32_t*>(p);
     return w;
@@ -377,6 +440,18 @@ static int commit(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t l
     int rc = msm_device(pk->srs, 0, d_coeffs, len, /*montgomery=*/1, &c->msm, c->stream, out, &inf);
     if (rc != B200_OK) return rc;
     if (inf) std::memset(out, 0, sizeof(*out));
+    return B200_OK;
+}
+
+// `count` commitments to polynomials `stride` coefficients apart, in one batched MSM
+static int commit_batch(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, size_t stride,
+                        unsigned count, g1_affine* out) {
+    int inf[32];
+    if (count > 32) return B200_ERR_INVALID;
+    int rc = msm_device_batch(pk->srs, 0, d_coeffs, len, stride, count, /*montgomery=*/1, &c->msm, c->stream, out, inf);
+    if (rc != B200_OK) return rc;
+    for (unsigned i = 0; i < count; ++i)
+        if (inf[i]) std::memset(&out[i], 0, sizeof(out[i]));
     return B200_OK;
 }
 
@@ -460,10 +535,8 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
     cudaFree(d_perm);
     d_perm = nullptr;
     // the 18 commitments of the verifying key
-    for (int s = 0; s < NS; ++s)
-        if ((rc = commit(c, pk, pk->sel_coeffs + (size_t)s * n, n, &pk->sel_comms[s])) != B200_OK) return fail(rc);
-    for (int i = 0; i < NW; ++i)
-        if ((rc = commit(c, pk, pk->sig_coeffs + (size_t)i * n, n, &pk->sig_comms[i])) != B200_OK) return fail(rc);
+    if ((rc = commit_batch(c, pk, pk->sel_coeffs, n, n, NS, pk->sel_comms)) != B200_OK) return fail(rc);
+    if ((rc = commit_batch(c, pk, pk->sig_coeffs, n, n, NW, pk->sig_comms)) != B200_OK) return fail(rc);
     *out = pk;
     return B200_OK;
 }
@@ -495,6 +568,14 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     if ((rc = get_domain(c, log_n, &dn)) != B200_OK || (rc = get_domain(c, log_n + 3, &dm)) != B200_OK) return rc;
     const fe one = fe_one<Fr>();
 
+    using clk = std::chrono::steady_clock;
+    auto t_prev = clk::now();
+    int phase = 0;
+    auto mark = [&]() {  // wall time between sync points (every commit synchronises the stream)
+        const auto now = clk::now();
+        if (phase < 8) c->plonk_ms[phase++] = std::chrono::duration<float, std::milli>(now - t_prev).count();
+        t_prev = now;
+    };
     SolidityTranscript tr;
     tr.append_u32_be(254);  // field size in bits
     tr.append_u64_be((uint64_t)n);
@@ -505,7 +586,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     for (size_t i = 0; i < pk->num_inputs; ++i) tr.append_field_elem(h_pub_inputs[i]);
 
     // ---- round 1 ------------------------------------------------------------------------------------
-    B200_CUDA(cudaMemcpyAsync(w.wires_ev, h_wires, NW * n * sizeof(fe), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(w.wires_ev, h_wires, NW * n * sizeof(fe), cudaMemcpyDefault, st));  // host or device pointer (UVA)
     B200_CUDA(cudaMemsetAsync(w.wpoly, 0, NW * S * sizeof(fe), st));
     B200_CUDA(cudaMemcpy2DAsync(w.wpoly, S * sizeof(fe), w.wires_ev, n * sizeof(fe), n * sizeof(fe), NW,
                                 cudaMemcpyDeviceToDevice, st));
@@ -522,11 +603,11 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     if (pk->num_inputs)
         B200_CUDA(cudaMemcpyAsync(w.pi_poly, h_pub_inputs, pk->num_inputs * sizeof(fe), cudaMemcpyHostToDevice, st));
     if ((rc = ntt_device(dn, w.pi_poly, nscr, 1, 0, 1, n, st)) != B200_OK) return rc;
-    for (int i = 0; i < NW; ++i)
-        if ((rc = commit(c, pk, w.wpoly + (size_t)i * S, n + 2, &proof->wires_poly_comms[i])) != B200_OK) return rc;
+    if ((rc = commit_batch(c, pk, w.wpoly, n + 2, S, NW, proof->wires_poly_comms)) != B200_OK) return rc;
     if (h_link_poly)
         B200_CUDA(cudaMemcpyAsync(h_link_poly, w.wpoly, (n + 2) * sizeof(fe), cudaMemcpyDeviceToHost, st));
     for (int i = 0; i < NW; ++i) tr.append_commitment(proof->wires_poly_comms[i]);
+    mark();  // [0] round 1
 
     // ---- round 2 ------------------------------------------------------------------------------------
     const fe beta = tr.get_and_append_challenge();
@@ -545,6 +626,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     }
     if ((rc = commit(c, pk, w.zpoly, n + 3, &proof->prod_perm_poly_comm)) != B200_OK) return rc;
     tr.append_commitment(proof->prod_perm_poly_comm);
+    mark();  // [1] round 2
 
     // ---- round 3 ------------------------------------------------------------------------------------
     const fe alpha = tr.get_and_append_challenge();
@@ -583,23 +665,28 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         k_split_quotient<<<dim3(grid_for(n + 3, 256), NW), 256, 0, st>>>(w.quot, n, S, sa, w.split);
     }
     B200_CUDA(cudaStreamSynchronize(st));
+    mark();  // [2] round 3: coset NTTs + quotient + split
     if (h_flag) {
         set_error("WrongQuotientPolyDegree: the witness does not satisfy the circuit");
         return B200_ERR_UNSATISFIED;
     }
-    for (int i = 0; i < NW; ++i) {
-        const size_t len = i < NW - 1 ? n + 3 : n;
-        if ((rc = commit(c, pk, w.split + (size_t)i * S, len, &proof->split_quot_poly_comms[i])) != B200_OK) return rc;
-    }
+    // the last chunk has n coefficients; its tail up to n + 3 is zero, so one batch length serves
+    if ((rc = commit_batch(c, pk, w.split, n + 3, S, NW, proof->split_quot_poly_comms)) != B200_OK) return rc;
     for (int i = 0; i < NW; ++i) tr.append_commitment(proof->split_quot_poly_comms[i]);
+    mark();  // [3] round 3: the 5 quotient commitments
 
     // ---- round 4 ------------------------------------------------------------------------------------
     const fe zeta = tr.get_and_append_challenge();
     const fe zeta_w = FMUL(zeta, pk->group_gen);
-    for (int i = 0; i < NW; ++i) horner_suffix(w.wpoly + (size_t)i * S, n + 2, zeta, nullptr, w.evals + i, w.hscr, st);
-    for (int i = 0; i < NW - 1; ++i)
-        horner_suffix(pk->sig_coeffs + (size_t)i * n, n, zeta, nullptr, w.evals + NW + i, w.hscr, st);
-    horner_suffix(w.zpoly, n + 3, zeta_w, nullptr, w.evals + 2 * NW - 1, w.hscr, st);
+    {
+        const fe* polys[kMaxEval];
+        size_t lens[kMaxEval];
+        fe pts[kMaxEval];
+        for (int i = 0; i < NW; ++i) { polys[i] = w.wpoly + (size_t)i * S; lens[i] = n + 2; pts[i] = zeta; }
+        for (int i = 0; i < NW - 1; ++i) { polys[NW + i] = pk->sig_coeffs + (size_t)i * n; lens[NW + i] = n; pts[NW + i] = zeta; }
+        polys[2 * NW - 1] = w.zpoly; lens[2 * NW - 1] = n + 3; pts[2 * NW - 1] = zeta_w;
+        eval_batch(polys, lens, pts, 2 * NW, w.evals, w.escr, st);
+    }
     fe h_evals[2 * NW];
     B200_CUDA(cudaMemcpyAsync(h_evals, w.evals, sizeof(h_evals), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -609,6 +696,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     for (int i = 0; i < NW; ++i) tr.append_field_elem(proof->wires_evals[i]);
     for (int i = 0; i < NW - 1; ++i) tr.append_field_elem(proof->wire_sigma_evals[i]);
     tr.append_field_elem(proof->perm_next_eval);
+    mark();  // [4] round 4
 
     // ---- round 5 ------------------------------------------------------------------------------------
     const fe v = tr.get_and_append_challenge();
@@ -665,9 +753,14 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     }
     // opening proofs: commit((batch - batch(zeta)) / (X - zeta)) and commit((z - z(zeta w)) / (X - zeta w))
     horner_suffix(w.lin, n + 3, zeta, w.sdiv, w.evals + 16, w.hscr, st);
-    if ((rc = commit(c, pk, w.sdiv + 1, n + 2, &proof->opening_proof)) != B200_OK) return rc;
-    horner_suffix(w.zpoly, n + 3, zeta_w, w.sdiv, w.evals + 17, w.hscr, st);
-    if ((rc = commit(c, pk, w.sdiv + 1, n + 2, &proof->shifted_opening_proof)) != B200_OK) return rc;
+    horner_suffix(w.zpoly, n + 3, zeta_w, w.sdiv + (S + 8), w.evals + 17, w.hscr, st);
+    {
+        g1_affine open2[2];
+        if ((rc = commit_batch(c, pk, w.sdiv + 1, n + 2, S + 8, 2, open2)) != B200_OK) return rc;
+        proof->opening_proof = open2[0];
+        proof->shifted_opening_proof = open2[1];
+    }
+    mark();  // [5] round 5
     if (h_challenges) {
         tr.append_commitment(proof->opening_proof);
         tr.append_commitment(proof->shifted_opening_proof);
@@ -710,6 +803,12 @@ int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t*
     if (!pk || !selector_comms || !sigma_comms) return B200_ERR_INVALID;
     std::memcpy(selector_comms, pk->pk->sel_comms, sizeof(pk->pk->sel_comms));
     std::memcpy(sigma_comms, pk->pk->sig_comms, sizeof(pk->pk->sig_comms));
+    return B200_OK;
+}
+
+int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]) {
+    if (!ctx || !out_ms) return B200_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) out_ms[i] = ctx->c.plonk_ms[i];
     return B200_OK;
 }
 

@@ -170,3 +170,26 @@ def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle):
         recs[r, :8], recs[r, 8] = xy, int(pinf)
     out2, inf2 = combine_partials(ctx, recs)
     assert not inf2 and (out2 == exp).all()
+
+
+def test_msm_batch_via_prover_sizes(ctx, oracle):
+    """Batched MSM (several scalar vectors over the same bases in one pass) is exercised through
+    the prover; here directly: 5 vectors of 3000 scalars, a stride apart, vs 5 oracle MSMs."""
+    import ctypes as C
+    import torch
+    from renegade_b200 import _lib
+    n, batch, stride = 3000, 5, 3008
+    pts = oracle.known_dlog_bases(0xB200, n)
+    bases = ctx.load_bases(pts)
+    s = np.zeros((batch, stride, 4), dtype=np.uint64)
+    for b in range(batch):
+        s[b, :n] = oracle.splitmix_fr(0x100 + b, n, montgomery=True)
+    t = torch.from_numpy(s.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    out = np.zeros((batch, 8), dtype=np.uint64)
+    inf = (C.c_int * batch)()
+    _lib.check(ctx._lib.b200_msm_batch_device(ctx._h, bases._h, 0, C.c_void_p(t.data_ptr()), n, stride, batch, 1,
+                                              out.ctypes.data_as(C.c_void_p), inf))
+    for b in range(batch):
+        exp, _ = oracle.msm(pts, oracle.array_from_mont(oracle.FR, s[b, :n]))
+        assert (out[b] == exp).all(), b
