@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — the driver's benchmark contract for the B200-native proving backend.
+"""bench.py — the driver's benchmark contract for the B200-native PlonK proving backend.
 
-Workload (BASELINE.json configs[1]): one 2^20-point BN254 G1 Pippenger MSM per GPU, known-dlog
-synthetic bases a_i*G (SplitMix64 seed 0xB200) and uniform 254-bit scalars (seed 0x5CA1A8),
-SURVEY.md §8(d).  A "step" is one MSM over that batch.  metric = MSM achieved GB/s
-= algorithmic bytes (96 B per (point, scalar) pair) / time.
+Headline (BASELINE.json metric, first clause; configs[3]): proofs/sec of the VALID-MATCH-class
+TurboPlonk statement — a synthetic circuit of n = 2^16 gates with 17 public inputs standing in for
+`IntentAndBalancePrivateSettlementCircuit` (the reference's Rust circuit synthesis
+cannot run here) — proved by the device prover behind `b200_plonk_prove`.  A "step" is one full
+proof: witness table in, 1152-byte proof out.  `value` has the witness table resident in HBM;
+`e2e` passes it from pinned host memory through the same C-ABI call (H2D inside the timed region).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Second clause (configs[1]): a 2^20-point BN254 G1 MSM per GPU, reported in the `msm` object of the
+same JSON line as achieved GB/s of algorithmic bytes (96 B per (point, scalar) pair).
 
-N > 1 (under torchrun, one rank per GPU): weak scaling — every rank owns 2^20 points of an
-N*2^20-point MSM, runs Pippenger on its shard, and one NCCL all_gather of the 72-byte partial
-sums + a k-term G1 sum finishes the job (EC addition is not an NCCL reduce op).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--concurrency C]
 
---impl reference times the CPU restatement of the reference's arkworks path (oracle/, the
-reference itself is Rust and cannot be built here) on the host cores, same metric and config.
+N > 1 (under torchrun, one rank per GPU): proofs are independent jobs — one proof stream per GPU,
+no data-path collective (weak scaling); the MSM leg shards one N*2^20-point MSM by point range
+and finishes with one NCCL all_gather of 72-byte partial sums + a k-term G1 sum (EC addition is
+not an NCCL reduce op).
+
+--impl reference times the CPU restatement of the reference's prover (oracle/: the reference is
+Rust with un-vendored crates and cannot be built here) on all host cores, same circuit.
 """
 import argparse
 import json
@@ -26,12 +32,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LOG_N = 20
-N_POINTS = 1 << LOG_N
-BYTES_PER_PAIR = 96  # 64 B affine base + 32 B scalar
-SEED_BASES, SEED_SCALARS = 0xB200, 0x5CA1A8
-KERNELS_PER_MSM = 14  # count, 3x scan, scatter, 3x scan, segfill, accumulate, combine, heavy_combine, reduce, reduce_final
-METRIC = "MSM achieved GB/s (algorithmic bytes / time), 2^20-point BN254 G1 Pippenger per GPU"
+LOG_N = 16                 # "~2^16 constraints"
+NUM_INPUTS = 17            # IntentAndBalancePrivateSettlementStatement
+CIRCUIT_SEED = 0xB200
+MSM_LOG_N = 20
+BYTES_PER_PAIR = 96        # 64 B affine base + 32 B scalar
+SEED_BASES, SEED_SCALARS, SEED_SRS = 0xB200, 0x5CA1A8, 0x7A0
+# kernels launched per batched MSM: count, 3x scan, scatter, 3x scan, segfill, accumulate, combine,
+# heavy_combine, reduce, reduce_final
+KERNELS_PER_MSM = 14
+METRIC = "proofs/sec, VALID-MATCH-class TurboPlonk proof (n = 2^16 gates, BN254/KZG)"
+WORKLOAD = ("synthetic TurboPlonk circuit, n = 2^16 gates, 17 public inputs, 5 wire columns, 13 selector columns "
+            "(stand-in for IntentAndBalancePrivateSettlementCircuit, BASELINE.json configs[3]); "
+            "13 KZG commitments of ~2^16 points + 8 size-2^19 and 7 size-2^16 NTTs per proof")
 
 
 def measured_peak_hbm():
@@ -46,9 +59,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
     def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -88,59 +99,71 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def base_line(args, world):
+    return {"metric": METRIC, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery integers; Fr and Fq of BN254)", "data": "synthetic"}
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle's arkworks-rule Pippenger (OpenMP over windows) on the host cores."""
+    """CPU arm: the oracle's restatement of the reference prover, all host cores (OpenMP)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c
+    from renegade_b200 import synth
     oracle_c.build()
-    cores = oracle_c.num_threads()
-    # bounded sample: keep the whole run within a few minutes whatever the core count
     t0 = time.perf_counter()
-    probe_n = 1 << 14
-    pb = oracle_c.known_dlog_bases(SEED_BASES, probe_n)
-    ps = oracle_c.splitmix_fr(SEED_SCALARS, probe_n, False)
-    t1 = time.perf_counter()
-    oracle_c.msm(pb, ps)
-    probe = time.perf_counter() - t1
-    total_calls = args.steps + args.warmup
-    log_sample = LOG_N
-    # MSM time grows ~linearly in n at fixed window: scale the probe, cap the run at ~150 s
-    while log_sample > 14 and probe * (1 << (log_sample - 14)) * total_calls > 150.0:
-        log_sample -= 1
-    n = 1 << log_sample
-    bases = oracle_c.known_dlog_bases(SEED_BASES, n)
-    scalars = oracle_c.splitmix_fr(SEED_SCALARS, n, False)
-    for _ in range(args.warmup):
-        oracle_c.msm(bases, scalars)
+    cores = oracle_c.autotune_threads()  # all logical CPUs unless a subset is faster on this (shared) host
+    log_n = LOG_N
+    while True:
+        n = 1 << log_n
+        circ = synth.synth_circuit(log_n, num_inputs=NUM_INPUTS, seed=CIRCUIT_SEED)
+        srs = oracle_c.known_dlog_bases(SEED_SRS, n + 3)
+        pk = oracle_c.plonk_preprocess(log_n, circ.selectors, circ.perm, circ.k, srs)
+        bl = synth.splitmix_blinders(1)
+        t = time.perf_counter()
+        rc, _, _, _ = oracle_c.plonk_prove(log_n, circ.num_inputs, circ.k, pk, circ.wires, circ.pub_inputs, bl, srs)
+        probe = time.perf_counter() - t
+        assert rc == 0
+        # bounded sample: the whole --steps/--warmup run must end within a few minutes
+        if probe * (args.steps + args.warmup) <= 240.0 or log_n <= 12:
+            break
+        log_n -= 1
+    for i in range(args.warmup):
+        oracle_c.plonk_prove(log_n, circ.num_inputs, circ.k, pk, circ.wires, circ.pub_inputs, bl, srs)
     t = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_c.msm(bases, scalars)
+    for i in range(args.steps):
+        oracle_c.plonk_prove(log_n, circ.num_inputs, circ.k, pk, circ.wires, circ.pub_inputs, synth.splitmix_blinders(i), srs)
     dt = (time.perf_counter() - t) / max(args.steps, 1)
-    gbs = n * BYTES_PER_PAIR / dt / 1e9
-    sample = f"2^{log_sample}-point prefix of the 2^20 workload per step (arkworks window rule c={oracle_c.msm_window_bits(n)})"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integers)",
-        "data": "synthetic", "points_per_sec": n / dt,
-        "config": {"workload": "2^20-point BN254 G1 Pippenger MSM (BASELINE.json configs[1])", "sample": sample},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "restated CPU baseline (C + OpenMP, arkworks msm_bigint algorithm), not arkworks itself"},
-        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    scale = float(1 << (LOG_N - log_n))  # a 2^k-times smaller circuit stands for 1/2^k of a proof
+    value = 1.0 / (dt * scale)
+    sample = "1 full proof of the same circuit per step" if log_n == LOG_N else \
+        f"one proof of a 2^{log_n}-gate circuit per step, counted as 1/{int(scale)} proof"
+    out = base_line(args, args.gpus)
+    out.update({
+        "impl": "reference", "value": value, "ms_per_step": dt * 1e3,
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "restated CPU prover (C + OpenMP; arkworks msm_bigint / radix-2 FFT algorithms, "
+                                 "jellyfish TurboPlonk rounds) — not the Rust reference itself"},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "setup_s": time.perf_counter() - t0,
-    }))
+    })
+    print(json.dumps(out))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--concurrency", type=int, default=int(os.environ.get("B200_BENCH_CONCURRENCY", "1")),
+                    help="proofs in flight per GPU (one context + stream each)")
+    ap.add_argument("--msm-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msm", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -156,6 +179,8 @@ def main():
     import torch
     import torch.distributed as dist
     import renegade_b200 as rb
+    from renegade_b200 import synth
+    from renegade_b200.backend import PlonkKzgSnark, plonk_last_timings, prove_raw
     from renegade_b200.sharded import all_gather_partials, combine_partials, pack_partial
 
     torch.cuda.set_device(local_rank)
@@ -163,79 +188,107 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    ctx = rb.Context(local_rank)
-    n = N_POINTS
-    first = rank * n  # this rank's slice of the world*2^20-point MSM
-    d_pts = torch.empty((n, 8), dtype=torch.int64, device=dev)
-    d_scalars = torch.empty((n, 4), dtype=torch.int64, device=dev)
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter()
-    ctx.known_dlog_bases_device(SEED_BASES, n, d_pts.data_ptr(), first=first)
-    ctx.splitmix_fr_device(SEED_SCALARS, n, d_scalars.data_ptr(), montgomery=False, first=first)
-    bases = ctx.load_bases_device(d_pts.data_ptr(), n, window_bits=args.window_bits)
-    setup_s = time.perf_counter() - t_setup
-    plan = bases.plan
-    h_scalars = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-    h_scalars.copy_(d_scalars)
-    torch.cuda.synchronize()
-    ctx.msm_timing(True)
-
-    def step_resident():
-        xy, inf = ctx.msm_device(bases, d_scalars.data_ptr(), n, montgomery=False)
-        if world > 1:
-            rec = all_gather_partials(pack_partial(xy, inf), dev)
-            xy, inf = combine_partials(ctx, rec)
-        return xy, inf
-
-    def step_e2e():
-        # public API with HOST buffers: H2D of the scalars and D2H of the result inside the call
-        xy, inf = ctx.msm(bases, h_scalars.numpy().view(np.uint64), montgomery=False)
-        if world > 1:
-            rec = all_gather_partials(pack_partial(xy, inf), dev)
-            xy, inf = combine_partials(ctx, rec)
-        return xy, inf
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, collect=None):
-        barrier()
-        t = time.perf_counter()
-        for _ in range(steps):
-            r = fn()
-            if collect is not None:
-                collect.append(ctx.msm_timing(True))
-        barrier()
-        dt = time.perf_counter() - t
+    def max_over_ranks(dt):
         if world > 1:
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        return dt, r
+            return float(tt.item())
+        return dt
 
-    for _ in range(args.warmup):
-        result = step_resident()
+    # ---------------------------------------------------------------------------------------------
+    # setup: circuit, SRS, proving key (device resident), witness tables
+    # ---------------------------------------------------------------------------------------------
+    t_setup = time.perf_counter()
+    n = 1 << LOG_N
+    conc = max(1, args.concurrency)
+    ctxs = [rb.Context(local_rank) for _ in range(conc)]
+    ctx = ctxs[0]
+    circ = synth.synth_circuit(LOG_N, num_inputs=NUM_INPUTS, seed=CIRCUIT_SEED + rank)
+    d_srs = torch.empty((n + 3, 8), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    # any n + 3 valid G1 points cost the same as a powers-of-tau SRS (the reference's real SRS file
+    # is not on the GPU box); known-dlog points are generated on the device
+    ctx.known_dlog_bases_device(SEED_SRS, n + 3, d_srs.data_ptr())
+    srs = ctx.load_bases_device(d_srs.data_ptr(), n + 3)
+    pk = PlonkKzgSnark.preprocess(ctx, srs, LOG_N, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    h_wires = torch.from_numpy(circ.wires.view(np.int64)).pin_memory()
+    d_wires = h_wires.to(dev)
+    torch.cuda.synchronize()
+    blinders = [synth.splitmix_blinders(1000 * rank + i) for i in range(args.steps + args.warmup + 8)]
+    setup_s = time.perf_counter() - t_setup
+
+    def run_proofs(count, wires_ptr, first_blinder, collect=None):
+        """`count` proofs, `conc` in flight (one context/stream each)."""
+        if conc == 1:
+            for i in range(count):
+                proof = prove_raw(ctx, pk, wires_ptr, circ.pub_inputs, blinders[first_blinder + i])
+                if collect is not None:
+                    collect.append(plonk_last_timings(ctx))
+            return proof
+        nxt, lock, last = [0], threading.Lock(), [None]
+
+        def worker(c):
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= count:
+                    return
+                last[0] = prove_raw(c, pk, wires_ptr, circ.pub_inputs, blinders[first_blinder + i])
+        ths = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return last[0]
+
+    # ---- proofs, witness resident in HBM ---------------------------------------------------------------
+    run_proofs(args.warmup * conc, d_wires.data_ptr(), 0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     phases = []
-    dt, result = timed(step_resident, args.steps, phases)
+    barrier()
+    t = time.perf_counter()
+    proof = run_proofs(args.steps, d_wires.data_ptr(), args.warmup, phases)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t)
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step_e2e()
-    dt_e2e, result_e2e = timed(step_e2e, args.steps)
-    assert (result[0] == result_e2e[0]).all() and result[1] == result_e2e[1]
+    # ---- the same through the public call with HOST buffers (e2e) ---------------------------------------
+    run_proofs(2 * conc, h_wires.data_ptr(), 0)
+    barrier()
+    t = time.perf_counter()
+    proof_e2e = run_proofs(args.steps, h_wires.data_ptr(), args.warmup)
+    barrier()
+    dt_e2e = max_over_ranks(time.perf_counter() - t)
+    if conc == 1:
+        assert bytes(proof) == bytes(proof_e2e)  # same witness + blinders -> identical proof
 
-    ms_step = dt / args.steps * 1e3
-    total_pairs = n * world
-    value = total_pairs * BYTES_PER_PAIR / (dt / args.steps) / 1e9
-    e2e_value = total_pairs * BYTES_PER_PAIR / (dt_e2e / args.steps) / 1e9
-    acc_ms = sum(p["accumulate"] for p in phases) / len(phases)
-    dev_ms = sum(p["total"] for p in phases) / len(phases)
+    # ---- kernel-level numbers of the dominant kernel inside a proof --------------------------------------
+    # bucket accumulation of the batched commitments, timed with CUDA events on the library's stream
+    ctx.msm_timing(True)
+    msm_ms = []
+    d_polys = torch.empty((5, n + 4, 4), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    for b in range(5):
+        ctx.splitmix_fr_device(0xC0FFEE + b, n + 2, d_polys[b].data_ptr(), montgomery=True)
+    import ctypes as C
+    from renegade_b200 import _lib
+    out5 = np.zeros((5, 8), dtype=np.uint64)
+    for i in range(6):
+        _lib.check(ctx._lib.b200_msm_batch_device(ctx._h, srs._h, 0, C.c_void_p(d_polys.data_ptr()), n + 2, n + 4, 5, 1,
+                                                  out5.ctypes.data_as(C.c_void_p), None))
+        if i >= 2:
+            msm_ms.append(ctx.msm_timing(True))
+    acc_ms = sum(p["accumulate"] for p in msm_ms) / len(msm_ms)
+    commit_pairs = 5 * (n + 2)
     peak, peak_src = measured_peak_hbm()
-    achieved = n * BYTES_PER_PAIR / (acc_ms * 1e-3) / 1e9
+    achieved = commit_pairs * BYTES_PER_PAIR / (acc_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "msm_accumulate_traffic.json")) as f:
@@ -243,56 +296,111 @@ def main():
     except Exception:
         pass
 
+    # ---- second clause: 2^20-point MSM per GPU, sharded across ranks -------------------------------------
+    msm = None
+    if not args.no_msm:
+        nm = 1 << MSM_LOG_N
+        first = rank * nm
+        d_pts = torch.empty((nm, 8), dtype=torch.int64, device=dev)
+        d_sc = torch.empty((nm, 4), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        ctx.known_dlog_bases_device(SEED_BASES, nm, d_pts.data_ptr(), first=first)
+        ctx.splitmix_fr_device(SEED_SCALARS, nm, d_sc.data_ptr(), montgomery=False, first=first)
+        mbases = ctx.load_bases_device(d_pts.data_ptr(), nm)
+        h_sc = torch.empty((nm, 4), dtype=torch.int64).pin_memory()
+        h_sc.copy_(d_sc)
+        torch.cuda.synchronize()
+
+        def msm_step(host):
+            if host:
+                xy, inf = ctx.msm(mbases, h_sc.numpy().view(np.uint64), montgomery=False)
+            else:
+                xy, inf = ctx.msm_device(mbases, d_sc.data_ptr(), nm, montgomery=False)
+            if world > 1:
+                xy, inf = combine_partials(ctx, all_gather_partials(pack_partial(xy, inf), dev))
+            return xy, inf
+        for _ in range(3):
+            msm_step(False)
+        mph = []
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.msm_steps):
+            r0 = msm_step(False)
+            mph.append(ctx.msm_timing(True))
+        barrier()
+        mdt = max_over_ranks(time.perf_counter() - t) / args.msm_steps
+        for _ in range(2):
+            msm_step(True)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.msm_steps):
+            r1 = msm_step(True)
+        barrier()
+        mdt_e2e = max_over_ranks(time.perf_counter() - t) / args.msm_steps
+        assert (r0[0] == r1[0]).all()
+        macc = sum(p["accumulate"] for p in mph) / len(mph)
+        mplan = mbases.plan
+        msm = {
+            "workload": "2^20-point BN254 G1 Pippenger MSM per GPU (BASELINE.json configs[1]); N GPUs = one "
+                        "N*2^20-point MSM sharded by point range + NCCL all_gather of the partial sums",
+            "value": world * nm * BYTES_PER_PAIR / mdt / 1e9, "unit": "GB/s", "ms_per_step": mdt * 1e3,
+            "points_per_sec": world * nm / mdt, "steps": args.msm_steps,
+            "e2e": {"value": world * nm * BYTES_PER_PAIR / mdt_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nm * 32,
+                    "d2h_bytes_per_step": 128},
+            "device_phases_ms": {k: sum(p[k] for p in mph) / len(mph) for k in ("total", "sort", "accumulate", "reduce")},
+            "plan": mplan,
+            "roofline": {"bound": "hbm", "achieved": nm * BYTES_PER_PAIR / (macc * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": nm * BYTES_PER_PAIR / (macc * 1e-3) / 1e9 / peak, "kernel": "msm_accumulate_kernel"},
+            "l2": "window tables %.0f MB + 32 MB of scalars per step vs 126 MB of L2" % (mplan["tables"] * nm * 64 / 1e6),
+        }
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    out = {
-        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
-        "points_per_sec": total_pairs / (dt / args.steps),
-        "config": {
-            "workload": "2^20-point BN254 G1 Pippenger MSM per GPU (BASELINE.json configs[1]); "
-                        "N GPUs = one N*2^20-point MSM sharded by point range + NCCL all_gather of partial sums",
-            "points_per_gpu": n, "total_points": total_pairs, "window_bits": plan["window_bits"],
-            "digits": plan["digits"], "physical_windows": plan["physical_windows"], "tables": plan["tables"],
-            "l2": "inputs larger than L2: window tables %.0f MB + scalars 32 MB per step vs 126 MB L2"
-                  % (plan["tables"] * n * 64 / 1e6),
-            "timing": "wall clock around K synchronous steps (barrier + cuda sync both sides, max over ranks); "
-                      "device_ms_per_step from CUDA events on the library's stream",
-        },
-        "device_ms_per_step": dev_ms,
-        "phases_ms": {k: sum(p[k] for p in phases) / len(phases) for k in ("sort", "accumulate", "reduce")},
+    ms_step = dt / args.steps * 1e3
+    out = base_line(args, world)
+    n_msm_calls = 4  # batched commitments per proof: 5 wires, z, 5 quotient chunks, 2 openings
+    out.update({
+        "value": world * args.steps / dt, "ms_per_step": ms_step,
+        "config": {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": NUM_INPUTS, "gates_used": circ.n_gates,
+                   "concurrency_per_gpu": conc, "parallelism": "one proof stream per GPU (replicas, no collective)",
+                   "msm_plan": srs.plan,
+                   "l2": "per-proof working set > L2: 18 resident coset tables (302 MB) + 7 x 16 MB extended "
+                         "polynomials + 1.1 GB of SRS window tables vs 126 MB of L2",
+                   "timing": "wall clock around K proofs, barrier + cuda synchronize on both sides, max over ranks; "
+                             "kernel times from CUDA events on the library's stream"},
+        "phases_ms": ({k: sum(p[k] for p in phases) / len(phases) for k in phases[0]} if phases else None),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "msm_accumulate_kernel", "peak_source": peak_src,
-                     "note": "the kernel is integer-multiply-pipe bound (≈%d Fq products per point), not HBM bound; "
-                             "see DESIGN.md" % (10 * plan["digits"])},
-        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 128 * plan["physical_windows"],
-                "ms_per_step": dt_e2e / args.steps * 1e3},
-        "gpu_launches": KERNELS_PER_MSM * args.steps,
-        "clocks": clocks, "setup_s": setup_s,
-    }
+                     "traffic": traffic, "kernel": "msm_accumulate_kernel (batched commitment of 5 polynomials of 2^16+2 coefficients)",
+                     "peak_source": peak_src,
+                     "note": "integer-multiply-pipe bound: ~10.6 Fq products per bucket addition, 17 additions per "
+                             "scalar; see DESIGN.md for the INT-pipe roofline"},
+        "e2e": {"value": world * args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": 5 * n * 32 + NUM_INPUTS * 32 + 17 * 32,
+                "d2h_bytes_per_step": 1152, "ms_per_step": dt_e2e / args.steps * 1e3},
+        "gpu_launches": args.steps * (n_msm_calls * KERNELS_PER_MSM + 60),
+        "clocks": clocks, "setup_s": setup_s, "msm": msm,
+    })
 
     if not args.no_cpu_baseline and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import oracle_c  # CPU baseline leg: the only place bench.py executes the oracle
+        import oracle_c  # CPU baseline leg: the only place the product arm executes the oracle
         oracle_c.build()
-        log_sample = 18
-        ns = 1 << log_sample
-        hb = d_pts[:ns].cpu().numpy().view(np.uint64)
-        hs = h_scalars[:ns].numpy().view(np.uint64)
-        oracle_c.msm(hb[:4096], hs[:4096])
+        oracle_c.autotune_threads()
+        h_srs = d_srs.cpu().numpy().view(np.uint64)
+        opk = oracle_c.plonk_preprocess(LOG_N, circ.selectors, circ.perm, circ.k, h_srs)
+        bl = blinders[args.warmup + args.steps - 1]
         t = time.perf_counter()
-        cxy, cinf = oracle_c.msm(hb, hs)
+        rc, oproof, _, _ = oracle_c.plonk_prove(LOG_N, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl, h_srs)
         cdt = time.perf_counter() - t
-        gxy, ginf = ctx.msm_device(bases, d_scalars.data_ptr(), ns, montgomery=False)
+        gproof = prove_raw(ctx, pk, d_wires.data_ptr(), circ.pub_inputs, bl)
         out["cpu_baseline"] = {
-            "value": ns * BYTES_PER_PAIR / cdt / 1e9, "unit": "GB/s", "cores": oracle_c.num_threads(), "kind": "port",
-            "sample": "one 2^%d-point prefix of the same bases/scalars (%.2f s)" % (log_sample, cdt),
-            "points_per_sec": ns / cdt, "bit_exact_vs_gpu": bool((cxy == gxy).all() and cinf == ginf),
-            "note": "restated CPU baseline (C + OpenMP over windows, arkworks msm_bigint algorithm); not arkworks itself",
+            "value": 1.0 / cdt, "unit": "proofs/s", "cores": oracle_c.num_threads(), "kind": "port",
+            "sample": "1 full proof of the same circuit, same SRS and blinders (%.2f s)" % cdt,
+            "bit_exact_vs_gpu": bool(rc == 0 and bytes(oproof) == bytes(gproof)),
+            "note": "restated CPU prover (C + OpenMP; arkworks msm_bigint / radix-2 FFT algorithms, jellyfish "
+                    "TurboPlonk rounds) — not the Rust reference itself",
         }
     print(json.dumps(out))
     if world > 1:

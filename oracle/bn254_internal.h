@@ -121,11 +121,46 @@ ORC_UNUSED static void fp_pow(const fp_params* P, u64 out[4], const u64 a[4], co
     }
     memcpy(out, acc, 32);
 }
-/* Fermat inverse a^(p-2); inverse of 0 is 0 */
+/* Inverse by the binary extended Euclidean algorithm (what ark-ff's `inverse` uses: Guajardo-
+ * Kumar-Paar-Pelzl binary EEA on the Montgomery residue, then a fix-up by R^2); inverse of 0 is 0.
+ * Input/output in Montgomery form: a*R  ->  a^-1 * R. */
+ORC_UNUSED static inline void shr1_4(u64 a[4]) {
+    a[0] = (a[0] >> 1) | (a[1] << 63);
+    a[1] = (a[1] >> 1) | (a[2] << 63);
+    a[2] = (a[2] >> 1) | (a[3] << 63);
+    a[3] >>= 1;
+}
 ORC_UNUSED static void fp_inv(const fp_params* P, u64 out[4], const u64 a[4]) {
-    u64 e[4], two[4] = {2, 0, 0, 0};
-    sub4(e, P->p, two);
-    fp_pow(P, out, a, e);
+    if (is_zero4(a)) { memset(out, 0, 32); return; }
+    /* invariant: b * a = u (mod p), c * a = v (mod p); a is the Montgomery residue aR, so the
+     * result x satisfies x * aR = 1, i.e. x = a^-1 R^-1; multiplying by R^3 (Montgomery) gives a^-1 R */
+    u64 u[4], v[4], b[4] = {1, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+    const u64 one[4] = {1, 0, 0, 0};
+    memcpy(u, a, 32);
+    memcpy(v, P->p, 32);
+    while (!eq4(u, one) && !eq4(v, one)) {
+        while (!(u[0] & 1)) {
+            shr1_4(u);
+            if (b[0] & 1) { u64 carry = add4(b, b, P->p); shr1_4(b); b[3] |= carry << 63; }
+            else shr1_4(b);
+        }
+        while (!(v[0] & 1)) {
+            shr1_4(v);
+            if (c[0] & 1) { u64 carry = add4(c, c, P->p); shr1_4(c); c[3] |= carry << 63; }
+            else shr1_4(c);
+        }
+        if (ge4(u, v)) {
+            sub4(u, u, v);
+            if (sub4(b, b, c)) add4(b, b, P->p);
+        } else {
+            sub4(v, v, u);
+            if (sub4(c, c, b)) add4(c, c, P->p);
+        }
+    }
+    const u64* x = eq4(u, one) ? b : c;
+    u64 r3[4];
+    fp_mul(P, r3, P->r2, P->r2); /* R^3 */
+    fp_mul(P, out, x, r3);
 }
 ORC_UNUSED static inline void fp_to_mont(const fp_params* P, u64 out[4], const u64 a[4]) { fp_mul(P, out, a, P->r2); }
 ORC_UNUSED static inline void fp_from_mont(const fp_params* P, u64 out[4], const u64 a[4]) {

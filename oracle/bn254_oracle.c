@@ -254,9 +254,20 @@ void orc_ntt(u64* data, unsigned log_n, int inverse, int coset) {
     /* twiddle table w^k, k < n/2 */
     size_t half = n / 2 ? n / 2 : 1;
     u64* tw = (u64*)malloc(half * 32);
-    memcpy(tw, FR.r1, 32);
-    for (size_t k = 1; k < half; ++k) fp_mul(&FR, tw + 4 * k, tw + 4 * (k - 1), w);
-
+    {
+        const size_t chunk = 2048;
+#pragma omp parallel for schedule(static)
+        for (size_t c0 = 0; c0 < half; c0 += chunk) {
+            u64 e[4] = {c0, 0, 0, 0}, t[4];
+            fp_pow(&FR, t, w, e);
+            size_t end = c0 + chunk < half ? c0 + chunk : half;
+            for (size_t k = c0; k < end; ++k) {
+                memcpy(tw + 4 * k, t, 32);
+                fp_mul(&FR, t, t, w);
+            }
+        }
+    }
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; ++i) {
         size_t j = bitrev(i, log_n);
         if (i < j) {
@@ -293,6 +304,14 @@ void orc_ntt(u64* data, unsigned log_n, int inverse, int coset) {
             distribute_powers(data, n, gi);
         }
     }
+}
+
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int orc_num_threads(void) {

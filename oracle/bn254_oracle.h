@@ -67,6 +67,7 @@ void orc_ntt(uint64_t* data, unsigned log_n, int inverse, int coset);
 void orc_domain_generator(unsigned log_n, uint64_t out_mont[4]);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,8 @@ def lib():
     if _lib is None:
         if not os.path.exists(_SO):
             build()
+        # idle OpenMP workers must sleep, not spin: the GPU box's host CPUs are shared
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         _lib = C.CDLL(_SO)
         _lib.orc_msm_window_bits.restype = C.c_int
         _lib.orc_msm_window_bits.argtypes = [C.c_size_t]
@@ -157,6 +159,35 @@ def domain_generator(log_n: int) -> np.ndarray:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(C.c_int(n))
+
+
+def autotune_threads(candidates=None) -> int:
+    """Pick the OpenMP thread count that runs a small MSM + NTT fastest on this host (on a shared
+    box "all logical CPUs" can be far slower than a subset) and keep it.  Returns the choice."""
+    import time
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if candidates is None:
+        candidates = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
+    bases = known_dlog_bases(1, 1 << 13)
+    sc = splitmix_fr(2, 1 << 13, False)
+    x = splitmix_fr(3, 1 << 16, True)
+    best, best_t = candidates[-1], float("inf")
+    for c in candidates:
+        set_num_threads(c)
+        msm(bases, sc)
+        t = time.perf_counter()
+        for _ in range(3):
+            msm(bases, sc)
+            ntt(x)
+        dt = time.perf_counter() - t
+        if dt < best_t:
+            best, best_t = c, dt
+    set_num_threads(best)
+    return best
 
 
 # ---------------------------------------------------------------------------------------------
