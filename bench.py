@@ -38,9 +38,9 @@ CIRCUIT_SEED = 0xB200
 MSM_LOG_N = 20
 BYTES_PER_PAIR = 96        # 64 B affine base + 32 B scalar
 SEED_BASES, SEED_SCALARS, SEED_SRS = 0xB200, 0x5CA1A8, 0x7A0
-# kernels launched per batched MSM: count, 3x scan, scatter, 3x scan, segfill, accumulate, combine,
-# heavy_combine, reduce, reduce_final
-KERNELS_PER_MSM = 14
+# kernels launched per batched MSM: count, 3x scan, scatter, 3x scan, segfill, 3x segment ordering,
+# accumulate, combine, heavy_combine, reduce, reduce_final
+KERNELS_PER_MSM = 17
 METRIC = "proofs/sec, VALID-MATCH-class TurboPlonk proof (n = 2^16 gates, BN254/KZG)"
 WORKLOAD = ("synthetic TurboPlonk circuit, n = 2^16 gates, 17 public inputs, 5 wire columns, 13 selector columns "
             "(stand-in for IntentAndBalancePrivateSettlementCircuit, BASELINE.json configs[3]); "

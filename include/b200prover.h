@@ -173,6 +173,25 @@ int b200_plonk_prove(b200_ctx* ctx, const b200_pk* pk, const uint64_t* wires,
                      const uint64_t* pub_inputs, const uint64_t* blinders, b200_proof* proof,
                      uint64_t* link_poly, uint64_t* challenges);
 
+/* Flat link proof, field order of mpc-plonk `LinkingProof { quotient_commitment, opening_proof }`
+ * (crates/relayer-types/types-proofs/src/mocks.rs:28-30). */
+typedef struct {
+    uint64_t quotient_commitment[8];
+    uint64_t opening_proof[8];
+} b200_link_proof;
+
+/* Replaces `PlonkKzgSnark::link_proofs::<SolidityTranscript>(&hint_a, &hint_b, &group_layout,
+ * &pk.commit_key)` (circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47,
+ * intent_and_balance.rs:66-72).  a1 / a2: the two `LinkingHint.linking_wire_poly` coefficient
+ * vectors (Montgomery, host or device pointers; lengths may differ), comm1 / comm2 their
+ * `linking_wire_comm`; (alignment, offset, size) = mpc-relation `GroupLayout`: the group sits on
+ * the roots g^(offset + i), i < size, g the generator of the 2^alignment-th roots of unity.
+ * eta (may be NULL) receives the Fiat–Shamir challenge. */
+int b200_plonk_link(b200_ctx* ctx, const b200_bases* srs, const uint64_t* a1, size_t len1,
+                    const uint64_t* a2, size_t len2, const uint64_t* comm1, const uint64_t* comm2,
+                    unsigned alignment, size_t offset, size_t size, b200_link_proof* proof,
+                    uint64_t* eta);
+
 /* Wall-clock milliseconds of the last proof's phases on this context: round 1, round 2, round 3
  * (coset NTTs + quotient + split), round 3 commitments, round 4, round 5, then two spare slots. */
 int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]);

@@ -262,3 +262,32 @@ def plonk_verify_known_tau(log_n, num_inputs, k, pk, pub_inputs, proof: PlonkPro
         C.c_uint(log_n), C.c_size_t(num_inputs), _p(np.ascontiguousarray(k, dtype=np.uint64)),
         _p(pk["selector_comms"]), _p(pk["sigma_comms"]), _p(np.ascontiguousarray(pub_inputs, dtype=np.uint64)),
         C.byref(proof), _p(np.ascontiguousarray(tau_mont, dtype=np.uint64))))
+
+
+class LinkProof(C.Structure):
+    """orc_link_proof / mpc-plonk `LinkingProof { quotient_commitment, opening_proof }`."""
+    _fields_ = [("quotient_commitment", C.c_uint64 * 8), ("opening_proof", C.c_uint64 * 8)]
+
+    def to_array(self) -> np.ndarray:
+        return np.frombuffer(bytes(self), dtype=np.uint64).copy()
+
+
+def plonk_link(a1, a2, comm1, comm2, alignment, offset, size, srs):
+    a1 = np.ascontiguousarray(a1, dtype=np.uint64).reshape(-1, 4)
+    a2 = np.ascontiguousarray(a2, dtype=np.uint64).reshape(-1, 4)
+    proof = LinkProof()
+    eta = np.zeros(4, dtype=np.uint64)
+    lib().orc_plonk_link.restype = C.c_int
+    rc = lib().orc_plonk_link(_p(a1), C.c_size_t(a1.shape[0]), _p(a2), C.c_size_t(a2.shape[0]),
+                              _p(np.ascontiguousarray(comm1, dtype=np.uint64)), _p(np.ascontiguousarray(comm2, dtype=np.uint64)),
+                              C.c_uint(alignment), C.c_size_t(offset), C.c_size_t(size),
+                              _p(np.ascontiguousarray(srs, dtype=np.uint64)), C.byref(proof), _p(eta))
+    return rc, proof, eta
+
+
+def plonk_link_verify_known_tau(comm1, comm2, alignment, offset, size, proof: LinkProof, tau_mont) -> bool:
+    lib().orc_plonk_link_verify_known_tau.restype = C.c_int
+    return bool(lib().orc_plonk_link_verify_known_tau(
+        _p(np.ascontiguousarray(comm1, dtype=np.uint64)), _p(np.ascontiguousarray(comm2, dtype=np.uint64)),
+        C.c_uint(alignment), C.c_size_t(offset), C.c_size_t(size), C.byref(proof),
+        _p(np.ascontiguousarray(tau_mont, dtype=np.uint64))))

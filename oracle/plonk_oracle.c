@@ -625,3 +625,94 @@ int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const u64* k, 
     ok &= jac_equal(&lhs, &rhs);
     return ok;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * proof linking
+ * ---------------------------------------------------------------------------------------- */
+static void link_challenge(const u64* comm1, const u64* comm2, const u64* comm_q, u64 eta[4]) {
+    transcript tr;
+    tr_init(&tr);
+    tr_append_g1(&tr, comm1);
+    tr_append_g1(&tr, comm2);
+    tr_append_g1(&tr, comm_q);
+    tr_challenge(&tr, eta);
+    tr_free(&tr);
+}
+
+int orc_plonk_link(const u64* a1, size_t len1, const u64* a2, size_t len2, const u64* comm1, const u64* comm2,
+                   unsigned alignment, size_t offset, size_t size, const u64* srs, orc_link_proof* proof, u64* eta_out) {
+    const size_t len = len1 > len2 ? len1 : len2;
+    if (size == 0 || size >= len) return 1;
+    u64* diff = (u64*)calloc(len, 32);
+    for (size_t i = 0; i < len; ++i) {
+        u64 x[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0};
+        if (i < len1) fr_set(x, a1 + 4 * i);
+        if (i < len2) fr_set(y, a2 + 4 * i);
+        SUB(diff + 4 * i, x, y);
+    }
+    /* roots of the vanishing polynomial of the link group */
+    u64 g[4], root[4];
+    orc_domain_generator(alignment, g);
+    fr_pow_u64(root, g, (u64)offset);
+    /* q = diff / prod (X - root_i): successive synthetic divisions (remainders dropped, like
+     * DensePolynomial division) */
+    u64* cur = (u64*)malloc(len * 32);
+    u64* nxt = (u64*)calloc(len, 32);
+    memcpy(cur, diff, len * 32);
+    size_t cur_len = len;
+    u64 zd_eta_roots[4];
+    u64* roots = (u64*)malloc(size * 32);
+    for (size_t i = 0; i < size; ++i) {
+        fr_set(roots + 4 * i, root);
+        poly_div_linear(cur, cur_len, root, nxt);
+        --cur_len;
+        u64* t = cur; cur = nxt; nxt = t;
+        MUL(root, root, g);
+    }
+    commit(srs, cur, cur_len, proof->quotient_commitment);
+    u64 eta[4];
+    link_challenge(comm1, comm2, proof->quotient_commitment, eta);
+    if (eta_out) fr_set(eta_out, eta);
+    /* identity = diff - Z_D(eta) * q, opened at eta */
+    fr_one(zd_eta_roots);
+    for (size_t i = 0; i < size; ++i) {
+        u64 t[4];
+        SUB(t, eta, roots + 4 * i);
+        MUL(zd_eta_roots, zd_eta_roots, t);
+    }
+    u64 neg[4], zero[4];
+    fr_zero(zero);
+    SUB(neg, zero, zd_eta_roots);
+    poly_axpy(diff, cur, cur_len, neg);
+    memset(nxt, 0, len * 32);
+    poly_div_linear(diff, len, eta, nxt);
+    commit(srs, nxt, len - 1, proof->opening_proof);
+    free(roots); free(cur); free(nxt); free(diff);
+    return 0;
+}
+
+int orc_plonk_link_verify_known_tau(const u64* comm1, const u64* comm2, unsigned alignment, size_t offset, size_t size,
+                                    const orc_link_proof* proof, const u64* tau) {
+    u64 eta[4], g[4], root[4], zd[4], t[4], zero[4];
+    link_challenge(comm1, comm2, proof->quotient_commitment, eta);
+    orc_domain_generator(alignment, g);
+    fr_pow_u64(root, g, (u64)offset);
+    fr_one(zd);
+    for (size_t i = 0; i < size; ++i) {
+        SUB(t, eta, root);
+        MUL(zd, zd, t);
+        MUL(root, root, g);
+    }
+    fr_zero(zero);
+    jac lhs, rhs, tmp;
+    SUB(t, tau, eta);
+    g1_scale(&lhs, proof->opening_proof, t);
+    g1_load(&rhs, comm1);
+    u64 one[4], minus_one[4];
+    fr_one(one);
+    SUB(minus_one, zero, one);
+    g1_scale(&tmp, comm2, minus_one); jac_add(&rhs, &rhs, &tmp);
+    SUB(t, zero, zd);
+    g1_scale(&tmp, proof->quotient_commitment, t); jac_add(&rhs, &rhs, &tmp);
+    return jac_equal(&lhs, &rhs);
+}

@@ -73,6 +73,28 @@ int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const uint64_t
                                const uint64_t* pub_inputs, const orc_plonk_proof* proof,
                                const uint64_t* tau);
 
+/* ---- proof linking: restates mpc-plonk `PlonkKzgSnark::link_proofs::<SolidityTranscript>` as
+ * called at circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47:
+ * the two proofs' first wire polynomials a1, a2 agree on the link group's sub-domain
+ * D = { g^(offset+i) : i < size }, g = generator of the 2^alignment roots of unity
+ * (mpc-relation `GroupLayout { offset, size, alignment }`).
+ *   q = (a1 - a2) / Z_D, commit q; eta = transcript(comm1, comm2, comm_q);
+ *   opening = commit( (a1 - a2 - Z_D(eta) q) / (X - eta) ).
+ * field order mirrors `LinkingProof { quotient_commitment, opening_proof }`
+ * (types-proofs/src/mocks.rs:28-30). */
+typedef struct {
+    uint64_t quotient_commitment[8];
+    uint64_t opening_proof[8];
+} orc_link_proof;
+
+int orc_plonk_link(const uint64_t* a1, size_t len1, const uint64_t* a2, size_t len2,
+                   const uint64_t* comm1, const uint64_t* comm2, unsigned alignment, size_t offset,
+                   size_t size, const uint64_t* srs, orc_link_proof* proof, uint64_t* eta_out);
+/* verify_link_proof for an SRS with known tau: (tau - eta) * opening == comm1 - comm2 - Z_D(eta) * comm_q */
+int orc_plonk_link_verify_known_tau(const uint64_t* comm1, const uint64_t* comm2, unsigned alignment,
+                                    size_t offset, size_t size, const orc_link_proof* proof,
+                                    const uint64_t* tau);
+
 /* srs[i] = tau^i * G, i < n (test SRS with known tau) */
 void orc_srs_from_tau(const uint64_t* tau, size_t n, uint64_t* out_xy);
 

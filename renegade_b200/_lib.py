@@ -22,7 +22,7 @@ EXPORTS = [
     "b200_ntt", "b200_ntt_device", "b200_ntt_last_ms", "b200_domain_generator",
     "b200_splitmix_fr_device", "b200_known_dlog_bases_device",
     "b200_selftest_field", "b200_field_op",
-    "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_free", "b200_plonk_prove", "b200_plonk_last_timings", "b200_keccak256",
+    "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_free", "b200_plonk_prove", "b200_plonk_link", "b200_plonk_last_timings", "b200_keccak256",
 ]
 
 
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     lib.b200_pk_free.argtypes = [vp, vp]
     lib.b200_pk_free.restype = None
     lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200_plonk_link.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, u32, sz, sz, vp, vp]
     lib.b200_plonk_last_timings.argtypes = [vp, C.POINTER(C.c_float * 8)]
     lib.b200_keccak256.argtypes = [C.c_char_p, sz, vp]
     lib.b200_keccak256.restype = None

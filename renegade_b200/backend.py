@@ -366,3 +366,34 @@ def prove_raw(ctx: Context, pk: ProvingKey, wires_ptr: int, pub_inputs: np.ndarr
     _lib.check(ctx._lib.b200_plonk_prove(ctx._h, pk._h, C.c_void_p(wires_ptr), _ptr(pi) if pi.size else None, _ptr(bl),
                                          C.byref(proof), None, None))
     return proof
+
+
+class B200LinkProof(C.Structure):
+    """b200_link_proof: mpc-plonk `LinkingProof { quotient_commitment, opening_proof }`."""
+    _fields_ = [("quotient_commitment", C.c_uint64 * 8), ("opening_proof", C.c_uint64 * 8)]
+
+    def to_array(self) -> np.ndarray:
+        return np.frombuffer(bytes(self), dtype=np.uint64).copy()
+
+
+@dataclass
+class GroupLayout:
+    """mpc-relation `GroupLayout`: the link group occupies the roots g^(offset + i), i < size,
+    of the 2^alignment-th roots of unity."""
+    alignment: int
+    offset: int
+    size: int
+
+
+def link_proofs(ctx: Context, srs: Bases, hint_a: LinkingHint, hint_b: LinkingHint, layout: GroupLayout):
+    """`PlonkKzgSnark::link_proofs::<SolidityTranscript>` (proof_linking/intent_only.rs:42-47).
+    Returns (B200LinkProof, eta)."""
+    a1 = np.ascontiguousarray(hint_a.linking_wire_poly, dtype=np.uint64).reshape(-1, 4)
+    a2 = np.ascontiguousarray(hint_b.linking_wire_poly, dtype=np.uint64).reshape(-1, 4)
+    c1 = np.ascontiguousarray(hint_a.linking_wire_comm, dtype=np.uint64)
+    c2 = np.ascontiguousarray(hint_b.linking_wire_comm, dtype=np.uint64)
+    proof = B200LinkProof()
+    eta = np.zeros(4, dtype=np.uint64)
+    _lib.check(ctx._lib.b200_plonk_link(ctx._h, srs._h, _ptr(a1), a1.shape[0], _ptr(a2), a2.shape[0], _ptr(c1), _ptr(c2),
+                                        layout.alignment, layout.offset, layout.size, C.byref(proof), _ptr(eta)))
+    return proof, eta

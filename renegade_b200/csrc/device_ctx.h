@@ -81,7 +81,7 @@ struct Bases {
 
 struct MsmScratch {
     DevBuf counts, offsets, cursor, entries, buckets, block_sums, partials, window_sums, scalars;
-    DevBuf seg_offsets, seg_bucket, seg_sums, heavy;
+    DevBuf seg_offsets, seg_bucket, seg_sums, heavy, seg_order;
     // optional per-phase device timing (CUDA events on the launching stream)
     bool timing = false;
     bool ev_init = false;

@@ -419,7 +419,60 @@ FF_HD fe fe_mul(const fe& a, const fe& b) {
     for (int k = 0; k < 8; ++k) r.l[k] = borrow ? r.l[k] : t.l[k];
     return r;
 #else
-    return fe_mul_chain<C>(a, b);
+    // host path (transcript, affine normalisation, linearisation scalars): 4 x 64-bit CIOS
+    uint64_t x[4], y[4], p[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        x[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+        y[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+        p[i] = (uint64_t)C::mod(2 * i) | ((uint64_t)C::mod(2 * i + 1) << 32);
+    }
+    // -p^-1 mod 2^64 from the 32-bit constant by one Newton step
+    const uint64_t pinv32 = (uint64_t)(0u - C::inv);          // p^-1 mod 2^32
+    const uint64_t pinv64 = pinv32 * (2 - p[0] * pinv32);      // p^-1 mod 2^64
+    const uint64_t ninv = 0 - pinv64;
+    typedef unsigned __int128 u128;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; ++j) {
+            u128 v = (u128)x[j] * y[i] + t[j] + carry;
+            t[j] = (uint64_t)v;
+            carry = (uint64_t)(v >> 64);
+        }
+        u128 v = (u128)t[4] + carry;
+        t[4] = (uint64_t)v;
+        t[5] = (uint64_t)(v >> 64);
+        const uint64_t m = t[0] * ninv;
+        v = (u128)m * p[0] + t[0];
+        carry = (uint64_t)(v >> 64);
+        for (int j = 1; j < 4; ++j) {
+            v = (u128)m * p[j] + t[j] + carry;
+            t[j - 1] = (uint64_t)v;
+            carry = (uint64_t)(v >> 64);
+        }
+        v = (u128)t[4] + carry;
+        t[3] = (uint64_t)v;
+        t[4] = t[5] + (uint64_t)(v >> 64);
+    }
+    bool ge = t[4] != 0;
+    if (!ge) {
+        ge = true;
+        for (int i = 3; i >= 0; --i)
+            if (t[i] != p[i]) { ge = t[i] > p[i]; break; }
+    }
+    if (ge) {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 4; ++i) {
+            u128 d = (u128)t[i] - p[i] - borrow;
+            t[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
+        }
+    }
+    fe r;
+    for (int i = 0; i < 4; ++i) {
+        r.l[2 * i] = (uint32_t)t[i];
+        r.l[2 * i + 1] = (uint32_t)(t[i] >> 32);
+    }
+    return r;
 #endif
 }
 

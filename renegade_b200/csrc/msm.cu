@@ -209,15 +209,64 @@ __global__ void msm_segfill_kernel(const uint32_t* __restrict__ seg_offsets, uin
     for (uint32_t s = s0; s < s1; ++s) seg_bucket[s] = b;
 }
 
+// Segment lengths differ (Poisson bucket sizes); lanes of a warp that fold different numbers of
+// points idle in lockstep.  A counting sort of the segment ids by length (kSegLen+1 bins, longest
+// first) hands every warp segments of equal length.
+__device__ __forceinline__ uint32_t segment_length(const uint32_t* offsets, const uint32_t* seg_offsets, uint32_t b,
+                                                   uint32_t s) {
+    const uint32_t j = s - seg_offsets[b], k = seg_offsets[b + 1] - seg_offsets[b];
+    const uint32_t cnt = offsets[b + 1] - offsets[b];
+    return cnt / k + (j < cnt % k ? 1u : 0u);
+}
+__global__ void msm_seglen_hist_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ seg_offsets,
+                                       const uint32_t* __restrict__ seg_bucket, uint32_t n_buckets,
+                                       uint32_t* __restrict__ hist /* kSegLen + 1 bins */) {
+    __shared__ uint32_t sh[kSegLen + 1];
+    if (threadIdx.x <= kSegLen) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < seg_offsets[n_buckets]) atomicAdd(&sh[segment_length(offsets, seg_offsets, seg_bucket[s], s)], 1u);
+    __syncthreads();
+    if (threadIdx.x <= kSegLen && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+// hist -> start offsets, longest length first (single small block)
+__global__ void msm_seglen_starts_kernel(uint32_t* hist) {
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int l = kSegLen; l >= 0; --l) {
+            const uint32_t c = hist[l];
+            hist[l] = run;
+            run += c;
+        }
+    }
+}
+__global__ void msm_seglen_scatter_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ seg_offsets,
+                                          const uint32_t* __restrict__ seg_bucket, uint32_t n_buckets,
+                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= seg_offsets[n_buckets]) return;
+    const uint32_t len = segment_length(offsets, seg_offsets, seg_bucket[s], s);
+    // warp-aggregated: lanes with the same length take consecutive slots with one atomic
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, len);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[len], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = s;
+}
+
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ entries,
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint32_t* __restrict__ seg_offsets,
                                                              const uint32_t* __restrict__ seg_bucket,
+                                                             const uint32_t* __restrict__ order,
                                                              const g1_affine* __restrict__ tables,
                                                              size_t n_points, uint32_t n_buckets,
                                                              g1_xyzz* __restrict__ seg_sums) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= seg_offsets[n_buckets]) return;  // the grid is sized for the worst case
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= seg_offsets[n_buckets]) return;  // the grid is sized for the worst case
+    const uint32_t s = order[tid];
     const uint32_t b = seg_bucket[s];
     const uint32_t j = s - seg_offsets[b], k = seg_offsets[b + 1] - seg_offsets[b];
     const uint32_t first = offsets[b], cnt = offsets[b + 1] - first;
@@ -594,6 +643,7 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->seg_bucket.reserve(max_segs * 4)) != B200_OK) return rc;
     if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
+    if ((rc = s->seg_order.reserve((max_segs + kSegLen + 2) * 4)) != B200_OK) return rc;
     const uint32_t reduce_threads_needed = (half + kReduceChunk - 1) / kReduceChunk;
     const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
     if ((rc = s->partials.reserve(n_windows * reduce_blocks * sizeof(g1_xyzz))) != B200_OK) return rc;
@@ -611,6 +661,8 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     g1_xyzz* seg_sums = (g1_xyzz*)s->seg_sums.p;
     uint32_t* heavy_count = (uint32_t*)s->heavy.p;
     uint32_t* heavy_list = heavy_count + 1;
+    uint32_t* seg_hist = (uint32_t*)s->seg_order.p;  // kSegLen + 1 bins, then the ordering itself
+    uint32_t* seg_order = seg_hist + kSegLen + 2;
 
     if (s->timing && !s->ev_init) {
         for (auto& e : s->ev) B200_CUDA(cudaEventCreate(&e));
@@ -628,9 +680,14 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = exclusive_scan_u32(ScanSegCounts{offsets}, n_buckets, seg_offsets, &s->block_sums, st)) != B200_OK) return rc;
     msm_segfill_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(seg_offsets, (uint32_t)n_buckets, seg_bucket);
     B200_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
+    B200_CUDA(cudaMemsetAsync(seg_hist, 0, (kSegLen + 2) * 4, st));
+    const unsigned seg_grid = (unsigned)((max_segs + 255) / 256);
+    msm_seglen_hist_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist);
+    msm_seglen_starts_kernel<<<1, 32, 0, st>>>(seg_hist);
+    msm_seglen_scatter_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist, seg_order);
     if (s->timing) cudaEventRecord(s->ev[1], st);
     msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, st>>>(
-        entries, offsets, seg_offsets, seg_bucket, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
+        entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
     msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
         seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, heavy_count, heavy_list);
     msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(
@@ -652,8 +709,12 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
     }
 
-    // host epilogue per MSM: Horner over the physical windows (none when fully precomputed) and
-    // the one field inversion of the affine normalisation — a few hundred bytes of work.
+    // host epilogue: per MSM a Horner over the physical windows (none when fully precomputed), then
+    // ONE field inversion for the whole batch (Montgomery's trick over the ZZZ coordinates) — a few
+    // hundred bytes of work.
+    std::vector<g1_xyzz> totals(batch);
+    std::vector<fe> prefix(batch);
+    fe run = fe_one<FqCfg>();
     for (unsigned i = 0; i < batch; ++i) {
         const g1_xyzz* hs = h_sums.data() + (size_t)i * pl.n_phys;
         g1_xyzz total = hs[pl.n_phys - 1];
@@ -661,8 +722,25 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
             for (int k = 0; k < pl.c; ++k) total = g1_dbl(total);
             total = g1_add(total, hs[p]);
         }
-        out[i] = g1_to_affine(total);
-        if (out_inf) out_inf[i] = g1_xyzz_is_inf(total) ? 1 : 0;
+        totals[i] = total;
+        prefix[i] = run;
+        if (!g1_xyzz_is_inf(total)) run = fe_mul<FqCfg>(run, total.zzz);
+    }
+    fe inv = fe_inv<FqCfg>(run);
+    for (unsigned i = batch; i-- > 0;) {
+        const g1_xyzz& t = totals[i];
+        if (g1_xyzz_is_inf(t)) {
+            out[i].x = fe_zero();
+            out[i].y = fe_zero();
+            if (out_inf) out_inf[i] = 1;
+            continue;
+        }
+        const fe i3 = fe_mul<FqCfg>(inv, prefix[i]);  // 1 / ZZZ_i
+        inv = fe_mul<FqCfg>(inv, t.zzz);
+        const fe izz = fe_mul<FqCfg>(fe_sqr<FqCfg>(t.zz), fe_sqr<FqCfg>(i3));  // 1/ZZ = ZZ^2 / ZZZ^2
+        out[i].x = fe_mul<FqCfg>(t.x, izz);
+        out[i].y = fe_mul<FqCfg>(t.y, i3);
+        if (out_inf) out_inf[i] = 0;
     }
     return B200_OK;
 }

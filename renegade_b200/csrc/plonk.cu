@@ -181,18 +181,16 @@ __global__ void k_horner_local_batch(EvalArgs a) {
     for (size_t i = end; i-- > beg;) run = FADD(FMUL(run, z), fe_load_ro(p + i));
     fe_store(a.H[q] + t, run);
 }
-// S[j] += z^(chunk_end - j) * T[chunk + 1]
-__global__ void k_horner_apply(fe* __restrict__ S, size_t len, fe z, const fe* __restrict__ T, size_t n_chunks) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t + 1 >= n_chunks) return;  // the last chunk has no carry
-    const size_t beg = t * CH, end = beg + CH;
-    const fe carry = fe_load_ro(T + t + 1);
-    fe pw = z;
-    for (size_t i = end; i-- > beg;) {
-        fe_store(S + i, FADD(fe_load(S + i), FMUL(pw, carry)));
-        pw = FMUL(pw, z);
-    }
-    (void)len;
+// S[j] += z^(chunk_end - j) * T[chunk + 1], one thread per element; zpow[e] = z^e for e = 1..CH
+struct ZPow {
+    fe v[CH + 1];
+};
+__global__ void k_horner_apply(fe* __restrict__ S, size_t len, ZPow zp, const fe* __restrict__ T, size_t n_chunks) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t t = j / CH;
+    if (j >= len || t + 1 >= n_chunks) return;  // the last chunk has no carry
+    const size_t e = (t + 1) * CH - j;
+    fe_store(S + j, FADD(fe_load(S + j), FMUL(zp.v[e], fe_load_ro(T + t + 1))));
 }
 
 // ---- round 3: quotient over the coset g * H_8n ------------------------------------------------------
@@ -356,7 +354,12 @@ static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, f
     }
     const fe zc = host_pow(z, CH);
     horner_suffix(H, n1, zc, S ? T : nullptr, out_total, scratch + 2 * n1, st);
-    if (S) k_horner_apply<<<grid_for(n1, 128), 128, 0, st>>>(S, len, z, T, n1);
+    if (S) {
+        ZPow zp;
+        zp.v[0] = fe_one<Fr>();
+        for (int e = 1; e <= CH; ++e) zp.v[e] = FMUL(zp.v[e - 1], z);
+        k_horner_apply<<<grid_for(len, 256), 256, 0, st>>>(S, len, zp, T, n1);
+    }
 }
 
 // p_q(z_q) for up to kMaxEval polynomials, written to out[q];
@@ -771,6 +774,92 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// proof linking — replaces `PlonkKzgSnark::link_proofs::<SolidityTranscript>(hint_a, hint_b,
+// &group_layout, &commit_key)` (circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47,
+// intent_and_balance.rs:66-72): q = (a1 - a2) / Z_D with Z_D = prod_{i<size} (X - g^(offset+i)),
+// g the generator of the 2^alignment roots of unity (`GroupLayout`); eta from the transcript;
+// opening of a1 - a2 - Z_D(eta) q at eta.  Division by Z_D = `size` synthetic divisions, each the
+// Horner suffix scan run in place.
+// ---------------------------------------------------------------------------------------------
+struct LinkOut {
+    g1_affine quotient_commitment;
+    g1_affine opening_proof;
+};
+static_assert(sizeof(LinkOut) == sizeof(b200_link_proof), "link proof layout");
+
+static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const fe* h_a2, size_t len2,
+                const g1_affine& comm1, const g1_affine& comm2, unsigned alignment, size_t offset, size_t size,
+                LinkOut* out, fe* h_eta) {
+    const size_t len = len1 > len2 ? len1 : len2;
+    if (size == 0 || size >= len || alignment > 28 || len > srs->n) {
+        set_error("link: bad group layout or polynomial length");
+        return B200_ERR_INVALID;
+    }
+    cudaStream_t st = c->stream;
+    int rc;
+    const size_t L = len + 8;
+    const size_t scr = 4 * (L / CH + 4 * CH + 64);
+    if ((rc = c->plonk_ws.reserve((6 * L + scr + 16) * sizeof(fe))) != B200_OK) return rc;
+    fe* base = reinterpret_cast<fe*>(c->plonk_ws.p);
+    fe *d_a1 = base, *d_a2 = base + L, *d_diff = base + 2 * L, *d_ident = base + 3 * L;
+    fe* d_pp[2] = {base + 4 * L, base + 5 * L};  // ping-pong buffers of the successive divisions
+    fe* hscr = base + 6 * L;
+    fe* slot = hscr + scr;
+    B200_CUDA(cudaMemcpyAsync(d_a1, h_a1, len1 * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaMemcpyAsync(d_a2, h_a2, len2 * sizeof(fe), cudaMemcpyDefault, st));
+    const fe one = fe_one<Fr>();
+    {
+        LinArgs a;
+        a.count = 2;
+        a.p[0] = d_a1; a.len[0] = (uint32_t)len1; a.s[0] = one;
+        a.p[1] = d_a2; a.len[1] = (uint32_t)len2; a.s[1] = fe_neg<Fr>(one);
+        k_lincomb<<<grid_for(len, 128), 128, 0, st>>>(a, len, d_diff);
+    }
+    // roots of the link group's vanishing polynomial
+    const fe g = host_root_of_unity(alignment);
+    std::vector<fe> roots(size);
+    fe root = host_pow(g, (uint64_t)offset);
+    const fe* cur = d_diff;
+    size_t cur_len = len;
+    for (size_t i = 0; i < size; ++i) {
+        roots[i] = root;
+        fe* dst = d_pp[i & 1];
+        horner_suffix(cur, cur_len, root, dst, slot, hscr, st);
+        cur = dst + 1;  // drop the remainder S[0]
+        --cur_len;
+        root = FMUL(root, g);
+    }
+    {
+        ProvingKey tmp;  // commit() only needs the SRS
+        tmp.srs = srs;
+        if ((rc = commit(c, &tmp, cur, cur_len, &out->quotient_commitment)) != B200_OK) return rc;
+    }
+    SolidityTranscript tr;
+    tr.append_commitment(comm1);
+    tr.append_commitment(comm2);
+    tr.append_commitment(out->quotient_commitment);
+    const fe eta = tr.get_and_append_challenge();
+    if (h_eta) *h_eta = eta;
+    fe zd = one;
+    for (size_t i = 0; i < size; ++i) zd = FMUL(zd, FSUB(eta, roots[i]));
+    {
+        LinArgs a;
+        a.count = 2;
+        a.p[0] = d_diff; a.len[0] = (uint32_t)len; a.s[0] = one;
+        a.p[1] = cur; a.len[1] = (uint32_t)cur_len; a.s[1] = fe_neg<Fr>(zd);
+        k_lincomb<<<grid_for(len, 128), 128, 0, st>>>(a, len, d_ident);
+    }
+    fe* d_open = d_pp[size & 1];  // the buffer that does not hold the quotient
+    horner_suffix(d_ident, len, eta, d_open, slot, hscr, st);
+    {
+        ProvingKey tmp;
+        tmp.srs = srs;
+        if ((rc = commit(c, &tmp, d_open + 1, len - 1, &out->opening_proof)) != B200_OK) return rc;
+    }
+    return B200_OK;
+}
+
 }  // namespace b200
 
 // ---------------------------------------------------------------------------------------------
@@ -804,6 +893,21 @@ int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t*
     std::memcpy(selector_comms, pk->pk->sel_comms, sizeof(pk->pk->sel_comms));
     std::memcpy(sigma_comms, pk->pk->sig_comms, sizeof(pk->pk->sig_comms));
     return B200_OK;
+}
+
+int b200_plonk_link(b200_ctx* ctx, const b200_bases* srs, const uint64_t* a1, size_t len1, const uint64_t* a2,
+                    size_t len2, const uint64_t* comm1, const uint64_t* comm2, unsigned alignment, size_t offset,
+                    size_t size, b200_link_proof* proof, uint64_t* eta) {
+    B200_TRY
+    if (!ctx || !srs || !a1 || !a2 || !comm1 || !comm2 || !proof) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    g1_affine c1, c2;
+    std::memcpy(&c1, comm1, 64);
+    std::memcpy(&c2, comm2, 64);
+    return link(&ctx->c, srs->b, reinterpret_cast<const fe*>(a1), len1, reinterpret_cast<const fe*>(a2), len2, c1, c2,
+                alignment, offset, size, reinterpret_cast<LinkOut*>(proof), reinterpret_cast<fe*>(eta));
+    B200_CATCH
 }
 
 int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]) {

@@ -69,8 +69,19 @@ def gate_value(q, w, pi):
 
 
 def synth_circuit(log_n: int, num_inputs: int = 17, seed: int = 0xB200, fill: float = 0.93,
-                  check: bool = False) -> SynthCircuit:
+                  check: bool = False, link=None) -> SynthCircuit:
+    """link = (alignment, offset, values): a proof-linking group.  Value i is pinned to wire 0 of
+    row (offset + i) * n / 2^alignment — the row whose domain element is the (offset + i)-th
+    2^alignment-th root of unity — with all selectors zero, as mpc-relation places link gates
+    (SURVEY.md App. A, round 1); later gates may reuse the value through copy constraints."""
     n = 1 << log_n
+    link_rows = {}
+    if link is not None:
+        alignment, offset, link_vals = link
+        assert alignment <= log_n
+        for i, v in enumerate(link_vals):
+            link_rows[(offset + i) << (log_n - alignment)] = v % R
+        assert min(link_rows) >= num_inputs, "link group collides with the public-input rows"
     rnd = random.Random(seed)
     n_gates = max(num_inputs + 1, min(n - 1, int(n * fill)))
     values = [0]                       # variable 0 is the constant zero
@@ -95,6 +106,12 @@ def synth_circuit(log_n: int, num_inputs: int = 17, seed: int = 0xB200, fill: fl
 
     for row in range(n_gates):
         q = [0] * N_SELECTORS
+        if row in link_rows:           # link gate: wire 0 carries the shared value, no constraint
+            var = new_var(link_rows[row])
+            for wcol, vv in enumerate([var, 0, 0, 0, 0]):
+                wire_var[wcol][row] = vv
+                positions[vv].append((wcol, row))
+            continue
         if row < num_inputs:           # IO gate: w4 = public input
             pi = rnd.randrange(R)
             pub_inputs.append(pi)
@@ -136,8 +153,12 @@ def synth_circuit(log_n: int, num_inputs: int = 17, seed: int = 0xB200, fill: fl
             positions[var].append((wcol, row))
     # padding rows: all selectors zero, all wires the zero variable
     for row in range(n_gates, n):
+        cols = [0] * N_WIRES
+        if row in link_rows:
+            cols[0] = new_var(link_rows[row])
         for wcol in range(N_WIRES):
-            positions[0].append((wcol, row))
+            wire_var[wcol][row] = cols[wcol]
+            positions[cols[wcol]].append((wcol, row))
 
     # copy-constraint permutation: each variable's occurrences form one cycle
     perm = np.empty(N_WIRES * n, dtype=np.uint64)

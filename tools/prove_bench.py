@@ -8,12 +8,13 @@ from renegade_b200.backend import PlonkKzgSnark, plonk_last_timings, prove_raw
 
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+wbits = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 n = 1 << log_n
 ctx = rb.Context(0)
 t = time.time(); circ = synth.synth_circuit(log_n, num_inputs=17, seed=0xB200); t_synth = time.time() - t
 d_srs = torch.empty((n + 3, 8), dtype=torch.int64, device="cuda"); torch.cuda.synchronize()
 ctx.known_dlog_bases_device(0x7A0, n + 3, d_srs.data_ptr())     # any valid G1 points serve as a timing SRS
-t = time.time(); bases = ctx.load_bases_device(d_srs.data_ptr(), n + 3); t_srs = time.time() - t
+t = time.time(); bases = ctx.load_bases_device(d_srs.data_ptr(), n + 3, window_bits=wbits); t_srs = time.time() - t
 t = time.time(); pk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k); t_pre = time.time() - t
 bl = synth.splitmix_blinders(1)
 hw = torch.from_numpy(circ.wires.view(np.int64)).pin_memory()
