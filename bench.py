@@ -159,8 +159,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--concurrency", type=int, default=int(os.environ.get("B200_BENCH_CONCURRENCY", "1")),
-                    help="proofs in flight per GPU (one context + stream each)")
+    ap.add_argument("--concurrency", type=int, default=int(os.environ.get("B200_BENCH_CONCURRENCY", "4")),
+                    help="proofs in flight per GPU (one context + stream each), like the reference's rayon pool "
+                         "of concurrent proof jobs (native_proof_manager.rs:187-192)")
     ap.add_argument("--msm-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm", action="store_true")
@@ -296,6 +297,39 @@ def main():
     except Exception:
         pass
 
+    # ---- single-proof latency (one proof in flight) and its phases -----------------------------------------
+    lat_phases = []
+    for i in range(8):
+        prove_raw(ctx, pk, d_wires.data_ptr(), circ.pub_inputs, blinders[i])
+        if i >= 2:
+            lat_phases.append(plonk_last_timings(ctx))
+    single = {k: sum(p[k] for p in lat_phases) / len(lat_phases) for k in lat_phases[0]}
+    single_ms = sum(single.values())
+
+    # ---- configs[2]: 2^20 NTT + iNTT round trip (device resident, CUDA events in the library) ------------
+    ntt = None
+    if not args.no_msm:
+        nn = 1 << 20
+        d_x = torch.empty((nn, 4), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        ctx.splitmix_fr_device(0x1177, nn, d_x.data_ptr(), montgomery=True)
+        ref = d_x.clone()
+        f_ms, i_ms = [], []
+        for i in range(8):
+            ctx.ntt_device(d_x.data_ptr(), 20, inverse=False)
+            f = ctx.ntt_last_ms()
+            ctx.ntt_device(d_x.data_ptr(), 20, inverse=True)
+            if i >= 3:
+                f_ms.append(f)
+                i_ms.append(ctx.ntt_last_ms())
+        rt_ms = min(f_ms) + min(i_ms)
+        ntt = {"workload": "2^20-element BN254-Fr NTT + iNTT round trip (BASELINE.json configs[2])",
+               "round_trip_ms": rt_ms, "fwd_ms": min(f_ms), "inv_ms": min(i_ms), "round_trip_ok": bool(torch.equal(d_x, ref)),
+               "roofline": {"bound": "hbm", "achieved": nn * 128 / (rt_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": nn * 128 / (rt_ms * 1e-3) / 1e9 / peak, "kernel": "ntt_pass_kernel",
+                            "note": "64 B per element per transform (SURVEY 8(d)); the kernel is bound by the integer "
+                                    "pipe: 10 Fr products per element per transform"}}
+
     # ---- second clause: 2^20-point MSM per GPU, sharded across ranks -------------------------------------
     msm = None
     if not args.no_msm:
@@ -371,7 +405,6 @@ def main():
                          "polynomials + 1.1 GB of SRS window tables vs 126 MB of L2",
                    "timing": "wall clock around K proofs, barrier + cuda synchronize on both sides, max over ranks; "
                              "kernel times from CUDA events on the library's stream"},
-        "phases_ms": ({k: sum(p[k] for p in phases) / len(phases) for k in phases[0]} if phases else None),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "msm_accumulate_kernel (batched commitment of 5 polynomials of 2^16+2 coefficients)",
                      "peak_source": peak_src,
@@ -380,7 +413,8 @@ def main():
         "e2e": {"value": world * args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": 5 * n * 32 + NUM_INPUTS * 32 + 17 * 32,
                 "d2h_bytes_per_step": 1152, "ms_per_step": dt_e2e / args.steps * 1e3},
         "gpu_launches": args.steps * (n_msm_calls * KERNELS_PER_MSM + 60),
-        "clocks": clocks, "setup_s": setup_s, "msm": msm,
+        "latency_ms_one_proof_in_flight": single_ms, "latency_phases_ms": single,
+        "clocks": clocks, "setup_s": setup_s, "msm": msm, "ntt": ntt,
     })
 
     if not args.no_cpu_baseline and world == 1:

@@ -34,7 +34,7 @@ constexpr uint32_t kIdxBits = 26;  // entry = sign(1) | table(5) | point index(2
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
 constexpr int kSegLen = 32;        // a bucket is folded in segments of at most this many points
 constexpr int kCombineSeq = 64;    // buckets with more segments than this take the block-tree path
-constexpr int kReduceChunk = 16;   // buckets per thread in the running-sum reduction
+constexpr int kReduceChunk = 4;    // buckets per thread in the running-sum reduction (short serial chains: the kernel is latency-bound)
 constexpr int kReduceThreads = 128;
 
 // ---- scalar digits ---------------------------------------------------------------------------
