@@ -27,6 +27,9 @@ Context::~Context() {
         cudaEventDestroy(ntt_ev[0]);
         cudaEventDestroy(ntt_ev[1]);
     }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
 }
 

@@ -124,6 +124,9 @@ struct Context {
     MsmScratch msm;
     DevBuf plonk_ws;  // prover workspace (plonk.cu)
     float plonk_ms[8] = {0};  // wall time of the last proof's phases
+    cudaStream_t stream2 = nullptr;  // side stream of the prover (challenge-independent coset NTTs)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DevBuf ntt_scratch2;
     ~Context();
 };
 

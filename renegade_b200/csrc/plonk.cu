@@ -197,7 +197,7 @@ __global__ void k_horner_apply(fe* __restrict__ S, size_t len, ZPow zp, const fe
 struct QuotArgs {
     const fe* sel;   // 13 x m resident coset evaluations
     const fe* sig;   // 5 x m
-    const fe* ext;   // 7 x m: wires 0..4, z, public-input polynomial
+    const fe* ext;   // 7 x m: wires 0..4, public-input polynomial, z
     const fe* pts;   // m evaluation points g * w_m^i
     const fe* l1_inv;  // 1 / (n (x_i - 1))
     fe* out;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
 #pragma unroll
     for (int j = 0; j < NW; ++j) w[j] = fe_load_ro(a.ext + j * m + i);
     // gate: q_c + pi + sum q_lc w + q_mul0 w0 w1 + q_mul1 w2 w3 + q_ecc w0..w4 + sum q_hash w^5 - q_o w4
-    fe acc = FADD(fe_load_ro(a.sel + 11 * m + i), fe_load_ro(a.ext + 6 * m + i));
+    fe acc = FADD(fe_load_ro(a.sel + 11 * m + i), fe_load_ro(a.ext + 5 * m + i));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         acc = FADD(acc, FMUL(fe_load_ro(a.sel + j * m + i), w[j]));
@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     acc = FADD(acc, FMUL(fe_load_ro(a.sel + 12 * m + i), FMUL(FMUL(w01, w23), w[4])));
     acc = FSUB(acc, FMUL(fe_load_ro(a.sel + 10 * m + i), w[4]));
     // permutation: alpha * ( z prod(w + beta k x + gamma) - z(wx) prod(w + beta sigma + gamma) )
-    const fe zx = fe_load_ro(a.ext + 5 * m + i);
-    const fe zxw = fe_load_ro(a.ext + 5 * m + ((i + 8) & (m - 1)));
+    const fe zx = fe_load_ro(a.ext + 6 * m + i);
+    const fe zxw = fe_load_ro(a.ext + 6 * m + ((i + 8) & (m - 1)));
     const fe bx = FMUL(a.beta, fe_load_ro(a.pts + i));
     fe p1 = zx, p2 = zxw;
 #pragma unroll
@@ -564,6 +564,12 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     int rc;
     if ((rc = c->plonk_ws.reserve(workspace_elems(n) * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch.reserve((size_t)7 * m * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->ntt_scratch2.reserve((size_t)6 * m * sizeof(fe))) != B200_OK) return rc;
+    if (!c->stream2) {
+        B200_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        B200_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     Workspace w = carve(reinterpret_cast<fe*>(c->plonk_ws.p), n);
     fe* nscr = reinterpret_cast<fe*>(c->ntt_scratch.p);
     const size_t S = w.S;
@@ -606,6 +612,28 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     if (pk->num_inputs)
         B200_CUDA(cudaMemcpyAsync(w.pi_poly, h_pub_inputs, pk->num_inputs * sizeof(fe), cudaMemcpyHostToDevice, st));
     if ((rc = ntt_device(dn, w.pi_poly, nscr, 1, 0, 1, n, st)) != B200_OK) return rc;
+    // Fork: the coset evaluations of the 5 wire polynomials and of the public-input polynomial do not
+    // depend on any challenge, so they run on a second stream underneath the round-1/2 commitments
+    // (whose bucket reduction and host round trip leave most SMs idle).
+    struct Side {
+        Context* c;
+        bool pending = false;
+        ~Side() {
+            if (pending) cudaStreamSynchronize(c->stream2);  // error paths: never leave the side stream running
+        }
+    } side{c};
+    {
+        cudaStream_t s2 = c->stream2;
+        B200_CUDA(cudaEventRecord(c->ev_fork, st));
+        B200_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+        side.pending = true;
+        B200_CUDA(cudaMemsetAsync(w.ext, 0, 6 * m * sizeof(fe), s2));
+        B200_CUDA(cudaMemcpy2DAsync(w.ext, m * sizeof(fe), w.wpoly, S * sizeof(fe), (n + 2) * sizeof(fe), NW,
+                                    cudaMemcpyDeviceToDevice, s2));
+        B200_CUDA(cudaMemcpyAsync(w.ext + 5 * m, w.pi_poly, n * sizeof(fe), cudaMemcpyDeviceToDevice, s2));
+        if ((rc = ntt_device(dm, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), 0, 1, 6, m, s2)) != B200_OK) return rc;
+        B200_CUDA(cudaEventRecord(c->ev_join, s2));
+    }
     if ((rc = commit_batch(c, pk, w.wpoly, n + 2, S, NW, proof->wires_poly_comms)) != B200_OK) return rc;
     if (h_link_poly)
         B200_CUDA(cudaMemcpyAsync(h_link_poly, w.wpoly, (n + 2) * sizeof(fe), cudaMemcpyDeviceToHost, st));
@@ -633,12 +661,11 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 
     // ---- round 3 ------------------------------------------------------------------------------------
     const fe alpha = tr.get_and_append_challenge();
-    B200_CUDA(cudaMemsetAsync(w.ext, 0, 7 * m * sizeof(fe), st));
-    B200_CUDA(cudaMemcpy2DAsync(w.ext, m * sizeof(fe), w.wpoly, S * sizeof(fe), (n + 2) * sizeof(fe), NW,
-                                cudaMemcpyDeviceToDevice, st));
-    B200_CUDA(cudaMemcpyAsync(w.ext + 5 * m, w.zpoly, (n + 3) * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    B200_CUDA(cudaMemcpyAsync(w.ext + 6 * m, w.pi_poly, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    if ((rc = ntt_device(dm, w.ext, nscr, 0, 1, 7, m, st)) != B200_OK) return rc;
+    B200_CUDA(cudaMemsetAsync(w.ext + 6 * m, 0, m * sizeof(fe), st));
+    B200_CUDA(cudaMemcpyAsync(w.ext + 6 * m, w.zpoly, (n + 3) * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    if ((rc = ntt_device(dm, w.ext + 6 * m, nscr, 0, 1, 1, m, st)) != B200_OK) return rc;
+    B200_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));  // join: wire / PI coset evaluations are ready
+    side.pending = false;
     {
         QuotArgs q;
         q.sel = pk->ce_sel;
