@@ -475,10 +475,10 @@ MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
         // a 254-bit scalar falls short of a full window: a short top digit piles n / 2^t points
         // into 2^t buckets (hot atomics in the sort, more segments to combine).
         const int t = 254 - c * (W - 1);
-        const int shrt = t >= c - 1 ? 0 : (c - 1 - t);
+        const int shrt = t >= c - 3 ? 0 : (c - 3 - t);  // up to 2 bits short showed no penalty
         const double nw = (double)n * W;
         const double cost = nw * (1.0 + 0.02 * shrt) / 5.8e6 + nw * (1.0 + 0.1 * shrt) / 45e6 + 0.42 +
-                            (double)((size_t)1 << (c - 1)) / 1.0e6;
+                            (double)((size_t)1 << (c - 1)) / 2.0e6;
         if (cost < best_cost) {
             best_cost = cost;
             best.c = c;

@@ -70,33 +70,60 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     }
     __syncthreads();
 
-    // ---- butterflies: (x0, x1) -> (x0 + x1, (x0 - x1) * w^(j * n / 2^(s+1))) ----------------
-    for (int sp = t_log - 1; sp >= 0; --sp) {
+    // ---- butterflies, two stages per shared-memory round trip (radix 4 in registers) ----------
+    // stage s pairs indices 2^s apart: (x0, x1) -> (x0 + x1, (x0 - x1) * w^(j * n / 2^(s+1))), j = idx mod 2^s.
+    auto lds = [&](uint32_t pos) {
+        const uint4 u = plane_lo[pos], v = plane_hi[pos];
+        fe x;
+        x.l[0] = u.x; x.l[1] = u.y; x.l[2] = u.z; x.l[3] = u.w;
+        x.l[4] = v.x; x.l[5] = v.y; x.l[6] = v.z; x.l[7] = v.w;
+        return x;
+    };
+    auto sts = [&](uint32_t pos, const fe& y) {
+        plane_lo[pos] = make_uint4(y.l[0], y.l[1], y.l[2], y.l[3]);
+        plane_hi[pos] = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
+    };
+    int sp = t_log - 1;
+    for (; sp >= 1; sp -= 2) {
         const int s = a.lo + sp;
-        const uint32_t sp_mask = (1u << sp) - 1u;
+        const uint32_t low_mask = (1u << (sp - 1)) - 1u;
+        for (uint32_t t = threadIdx.x; t < (uint32_t)(E >> 2); t += blockDim.x) {
+            const uint32_t qq = t & Q_mask;
+            const uint32_t r = t >> q_log;
+            const uint32_t low = r & low_mask;
+            const uint32_t base = ((r >> (sp - 1)) << (sp + 1)) | low;
+            const uint32_t lw = (q_base + qq) & lo_mask;
+            const uint32_t p00 = (base << q_log) | qq;
+            const uint32_t p01 = ((base | (1u << (sp - 1))) << q_log) | qq;
+            const uint32_t p10 = ((base | (1u << sp)) << q_log) | qq;
+            const uint32_t p11 = ((base | (3u << (sp - 1))) << q_log) | qq;
+            const size_t j0 = ((size_t)low << a.lo) | lw;
+            const size_t j1 = ((size_t)(low | (1u << (sp - 1))) << a.lo) | lw;
+            const fe w0 = fe_load_ro(a.tw + (j0 << (a.log_n - s - 1)));
+            const fe w1 = fe_load_ro(a.tw + (j1 << (a.log_n - s - 1)));
+            const fe wp = fe_load_ro(a.tw + (j0 << (a.log_n - s)));
+            const fe x00 = lds(p00), x01 = lds(p01), x10 = lds(p10), x11 = lds(p11);
+            const fe y00 = fe_add<FrCfg>(x00, x10);
+            const fe y10 = fe_mul<FrCfg>(fe_sub<FrCfg>(x00, x10), w0);
+            const fe y01 = fe_add<FrCfg>(x01, x11);
+            const fe y11 = fe_mul<FrCfg>(fe_sub<FrCfg>(x01, x11), w1);
+            sts(p00, fe_add<FrCfg>(y00, y01));
+            sts(p01, fe_mul<FrCfg>(fe_sub<FrCfg>(y00, y01), wp));
+            sts(p10, fe_add<FrCfg>(y10, y11));
+            sts(p11, fe_mul<FrCfg>(fe_sub<FrCfg>(y10, y11), wp));
+        }
+        __syncthreads();
+    }
+    if (sp == 0) {  // odd number of stages in this pass: one radix-2 stage on neighbouring elements
         for (uint32_t t = threadIdx.x; t < (uint32_t)(E >> 1); t += blockDim.x) {
             const uint32_t qq = t & Q_mask;
             const uint32_t r = t >> q_log;
-            const uint32_t m0 = ((r >> sp) << (sp + 1)) | (r & sp_mask);
-            const uint32_t m1 = m0 + (1u << sp);
-            const uint32_t p0 = (m0 << q_log) | qq, p1 = (m1 << q_log) | qq;
-            const uint32_t lw = (q_base + qq) & lo_mask;
-            const size_t j = ((size_t)(m0 & sp_mask) << a.lo) | lw;
-            const size_t k = j << (a.log_n - s - 1);
-            const fe w = fe_load_ro(a.tw + k);
-            fe x0, x1;
-            uint4 u = plane_lo[p0], v = plane_hi[p0];
-            x0.l[0] = u.x; x0.l[1] = u.y; x0.l[2] = u.z; x0.l[3] = u.w;
-            x0.l[4] = v.x; x0.l[5] = v.y; x0.l[6] = v.z; x0.l[7] = v.w;
-            u = plane_lo[p1]; v = plane_hi[p1];
-            x1.l[0] = u.x; x1.l[1] = u.y; x1.l[2] = u.z; x1.l[3] = u.w;
-            x1.l[4] = v.x; x1.l[5] = v.y; x1.l[6] = v.z; x1.l[7] = v.w;
-            const fe y0 = fe_add<FrCfg>(x0, x1);
-            const fe y1 = fe_mul<FrCfg>(fe_sub<FrCfg>(x0, x1), w);
-            plane_lo[p0] = make_uint4(y0.l[0], y0.l[1], y0.l[2], y0.l[3]);
-            plane_hi[p0] = make_uint4(y0.l[4], y0.l[5], y0.l[6], y0.l[7]);
-            plane_lo[p1] = make_uint4(y1.l[0], y1.l[1], y1.l[2], y1.l[3]);
-            plane_hi[p1] = make_uint4(y1.l[4], y1.l[5], y1.l[6], y1.l[7]);
+            const uint32_t p0 = ((r << 1) << q_log) | qq, p1 = (((r << 1) | 1u) << q_log) | qq;
+            const size_t lw = (q_base + qq) & lo_mask;
+            const fe w = fe_load_ro(a.tw + (lw << (a.log_n - a.lo - 1)));
+            const fe x0 = lds(p0), x1 = lds(p1);
+            sts(p0, fe_add<FrCfg>(x0, x1));
+            sts(p1, fe_mul<FrCfg>(fe_sub<FrCfg>(x0, x1), w));
         }
         __syncthreads();
     }
