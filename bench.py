@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--concurrency", type=int, default=int(os.environ.get("B200_BENCH_CONCURRENCY", "4")),
+    ap.add_argument("--concurrency", type=int, default=int(os.environ.get("B200_BENCH_CONCURRENCY", "6")),
                     help="proofs in flight per GPU (one context + stream each), like the reference's rayon pool "
                          "of concurrent proof jobs (native_proof_manager.rs:187-192)")
     ap.add_argument("--msm-steps", type=int, default=10)
