@@ -196,6 +196,18 @@ int b200_plonk_link(b200_ctx* ctx, const b200_bases* srs, const uint64_t* a1, si
  * (coset NTTs + quotient + split), round 3 commitments, round 4, round 5, then two spare slots. */
 int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]);
 
+/* ---- witness-side batch hashing ------------------------------------- */
+/* `batch` independent Poseidon2 sponge hashes of `len` scalars each (inputs: batch x len x 4
+ * limbs, Montgomery; out: batch x 4 limbs; host or device pointers).  Each equals the reference's
+ * `compute_poseidon_hash(&values)` / `Poseidon2Sponge::new().hash(&values)`
+ * (crates/crypto/src/hash/mod.rs:12-18, poseidon2.rs:38-44): t = 3, rate 2, R_F = 8, R_P = 56,
+ * alpha = 5, constants of crates/crypto/src/hash/constants.rs. */
+int b200_poseidon2_hash_batch(b200_ctx* ctx, const uint64_t* inputs, size_t batch, size_t len,
+                              uint64_t* out);
+/* `batch` bare permutations of 3-element states, in place (`Poseidon2Sponge::permute`,
+ * poseidon2.rs:90-110). */
+int b200_poseidon2_permute_batch(b200_ctx* ctx, uint64_t* states, size_t batch);
+
 /* Keccak-256 of the transcript (host; exported so the hash can be pinned by known answers). */
 void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
 

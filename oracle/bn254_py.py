@@ -388,3 +388,50 @@ def splitmix_fr(seed: int, n: int):
             v |= next(g) << (64 * k)
         out.append(v % R)
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# Poseidon2 (restates crates/crypto/src/hash/poseidon2.rs:25-209; t = 3, rate 2, capacity 1,
+# R_F = 8, R_P = 56, alpha = 5 — constants.rs:15-36).  Round constants are read from the fixture
+# tests/golden/poseidon2.json, extracted from the reference's constants.rs; the permutation is
+# pinned by the published HorizenLabs known answer for the input (0, 1, 2).
+# ---------------------------------------------------------------------------------------
+def poseidon2_load_constants(path):
+    import json
+    with open(path) as f:
+        d = json.load(f)
+    return [int(v, 16) for v in d["full_round_constants"]], [int(v, 16) for v in d["partial_round_constants"]]
+
+
+def poseidon2_permute(state, full, partial):
+    """Poseidon2Sponge::permute (poseidon2.rs:90-110)."""
+    def ext_mds(s):  # poseidon2.rs:146-152
+        t = sum(s) % R
+        return [(x + t) % R for x in s]
+
+    def int_mds(s):  # poseidon2.rs:187-195
+        t = sum(s) % R
+        s = [s[0], s[1], 2 * s[2] % R]
+        return [(x + t) % R for x in s]
+    st = ext_mds(list(state))
+    for r in range(4):
+        st = ext_mds([pow((x + full[3 * r + i]) % R, 5, R) for i, x in enumerate(st)])
+    for r in range(56):
+        st = int_mds([pow((st[0] + partial[r]) % R, 5, R), st[1], st[2]])
+    for r in range(4, 8):
+        st = ext_mds([pow((x + full[3 * r + i]) % R, 5, R) for i, x in enumerate(st)])
+    return st
+
+
+def poseidon2_hash(values, full, partial):
+    """Poseidon2Sponge::new().hash(values) = compute_poseidon_hash (mod.rs:12-18): absorb at rate 2
+    into state[1..3] (poseidon2.rs:47-59), one squeeze (poseidon2.rs:67-79)."""
+    st, nxt = [0, 0, 0], 0
+    for x in values:
+        if nxt == 2:
+            st = poseidon2_permute(st, full, partial)
+            nxt = 0
+        st[nxt + 1] = (st[nxt + 1] + x) % R
+        nxt += 1
+    st = poseidon2_permute(st, full, partial)
+    return st[1]

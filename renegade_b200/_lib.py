@@ -23,6 +23,7 @@ EXPORTS = [
     "b200_splitmix_fr_device", "b200_known_dlog_bases_device",
     "b200_selftest_field", "b200_field_op",
     "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_free", "b200_plonk_prove", "b200_plonk_link", "b200_plonk_last_timings", "b200_keccak256",
+    "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch",
 ]
 
 
@@ -79,6 +80,8 @@ def load() -> C.CDLL:
     lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.b200_plonk_link.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, u32, sz, sz, vp, vp]
     lib.b200_plonk_last_timings.argtypes = [vp, C.POINTER(C.c_float * 8)]
+    lib.b200_poseidon2_hash_batch.argtypes = [vp, vp, sz, sz, vp]
+    lib.b200_poseidon2_permute_batch.argtypes = [vp, vp, sz]
     lib.b200_keccak256.argtypes = [C.c_char_p, sz, vp]
     lib.b200_keccak256.restype = None
     for name in EXPORTS:

@@ -397,3 +397,20 @@ def link_proofs(ctx: Context, srs: Bases, hint_a: LinkingHint, hint_b: LinkingHi
     _lib.check(ctx._lib.b200_plonk_link(ctx._h, srs._h, _ptr(a1), a1.shape[0], _ptr(a2), a2.shape[0], _ptr(c1), _ptr(c2),
                                         layout.alignment, layout.offset, layout.size, C.byref(proof), _ptr(eta)))
     return proof, eta
+
+
+def compute_poseidon_hash_batch(ctx: Context, values: np.ndarray) -> np.ndarray:
+    """`batch` x `crypto::hash::compute_poseidon_hash(&values[i])` (crates/crypto/src/hash/mod.rs:12-18):
+    values has shape (batch, len, 4) Montgomery; returns (batch, 4)."""
+    v = np.ascontiguousarray(values, dtype=np.uint64)
+    batch, ln = v.shape[0], v.shape[1]
+    out = np.zeros((batch, 4), dtype=np.uint64)
+    _lib.check(ctx._lib.b200_poseidon2_hash_batch(ctx._h, _ptr(v) if v.size else None, batch, ln, _ptr(out)))
+    return out
+
+
+def poseidon2_permute_batch(ctx: Context, states: np.ndarray) -> np.ndarray:
+    """`Poseidon2Sponge::permute` (poseidon2.rs:90-110) on (batch, 3, 4) states; returns the permuted copy."""
+    s = np.array(states, dtype=np.uint64, copy=True, order="C")
+    _lib.check(ctx._lib.b200_poseidon2_permute_batch(ctx._h, _ptr(s), s.shape[0]))
+    return s

@@ -1,0 +1,161 @@
+// Batch Poseidon2 hashing over the BN254 scalar field (the witness-side hashing
+// that dominates once MSM/NTT are on the device).
+//
+// Replaces, for batches of independent hashes, the reference's native
+//   crypto::hash::Poseidon2Sponge::{hash, absorb, squeeze, permute}
+//     /root/reference/crates/crypto/src/hash/poseidon2.rs:25-209
+//   crypto::hash::compute_poseidon_hash        /root/reference/crates/crypto/src/hash/mod.rs:12-18
+// with t = 3 (RATE 2, CAPACITY 1), R_F = 8, R_P = 56, alpha = 5 (constants.rs:15-36).  One thread
+// per hash: a permutation is 80 S-boxes = 240 Fr products plus additions, integer-pipe bound like
+// everything else here; constants live in __constant__ memory.
+#include <cstring>
+
+#include "b200prover.h"
+#include "device_ctx.h"
+#include "poseidon2_constants.h"
+
+namespace b200 {
+
+namespace {
+
+__constant__ uint32_t c_full_rc[24][8];
+__constant__ uint32_t c_partial_rc[56][8];
+
+using Fr = FrCfg;
+
+__device__ __forceinline__ fe rc_full(int i) {
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = c_full_rc[i][k];
+    return r;
+}
+__device__ __forceinline__ fe rc_partial(int i) {
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = c_partial_rc[i][k];
+    return r;
+}
+__device__ __forceinline__ fe sbox(const fe& x) {  // x^5 (poseidon2.rs:201-208)
+    const fe x2 = fe_sqr<Fr>(x);
+    return fe_mul<Fr>(fe_sqr<Fr>(x2), x);
+}
+// M_E = circ(2,1,1): add the sum of the state to every element (poseidon2.rs:146-152)
+__device__ __forceinline__ void external_mds(fe s[3]) {
+    const fe sum = fe_add<Fr>(fe_add<Fr>(s[0], s[1]), s[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s[i] = fe_add<Fr>(s[i], sum);
+}
+// M_I = [[2,1,1],[1,2,1],[1,1,3]] (poseidon2.rs:187-195)
+__device__ __forceinline__ void internal_mds(fe s[3]) {
+    const fe sum = fe_add<Fr>(fe_add<Fr>(s[0], s[1]), s[2]);
+    s[2] = fe_dbl<Fr>(s[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s[i] = fe_add<Fr>(s[i], sum);
+}
+// poseidon2.rs:90-110
+__device__ void permute(fe s[3]) {
+    external_mds(s);
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s[i] = sbox(fe_add<Fr>(s[i], rc_full(3 * r + i)));
+        external_mds(s);
+    }
+    for (int r = 0; r < 56; ++r) {
+        s[0] = sbox(fe_add<Fr>(s[0], rc_partial(r)));
+        internal_mds(s);
+    }
+    for (int r = 4; r < 8; ++r) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s[i] = sbox(fe_add<Fr>(s[i], rc_full(3 * r + i)));
+        external_mds(s);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_poseidon2_permute(fe* states, size_t batch) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch) return;
+    fe s[3];
+    for (int i = 0; i < 3; ++i) s[i] = fe_load(states + 3 * t + i);
+    permute(s);
+    for (int i = 0; i < 3; ++i) fe_store(states + 3 * t + i, s[i]);
+}
+
+// Poseidon2Sponge::hash: absorb `len` scalars at rate 2 (permuting when the rate is full), then one
+// squeeze = permute and return state[CAPACITY] (poseidon2.rs:38-84)
+__global__ void __launch_bounds__(128) k_poseidon2_hash(const fe* __restrict__ in, size_t batch, size_t len,
+                                                        fe* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch) return;
+    fe s[3] = {fe_zero(), fe_zero(), fe_zero()};
+    int next = 0;
+    const fe* x = in + t * len;
+    for (size_t i = 0; i < len; ++i) {
+        if (next == 2) {
+            permute(s);
+            next = 0;
+        }
+        s[next + 1] = fe_add<Fr>(s[next + 1], fe_load_ro(x + i));
+        ++next;
+    }
+    permute(s);
+    fe_store(out + t, s[1]);
+}
+
+bool g_constants_loaded[64] = {false};
+
+}  // namespace
+
+static int load_constants(int device) {
+    if (device >= 0 && device < 64 && g_constants_loaded[device]) return B200_OK;
+    B200_CUDA(cudaMemcpyToSymbol(c_full_rc, kPoseidon2FullRc, sizeof(kPoseidon2FullRc)));
+    B200_CUDA(cudaMemcpyToSymbol(c_partial_rc, kPoseidon2PartialRc, sizeof(kPoseidon2PartialRc)));
+    if (device >= 0 && device < 64) g_constants_loaded[device] = true;
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_poseidon2_permute_batch(b200_ctx* ctx, uint64_t* states, size_t batch) {
+    B200_TRY
+    if (!ctx || (batch && !states)) return B200_ERR_INVALID;
+    if (batch == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = load_constants(ctx->c.device);
+    if (rc != B200_OK) return rc;
+    cudaStream_t st = ctx->c.stream;
+    if ((rc = ctx->c.plonk_ws.reserve(batch * 3 * sizeof(fe))) != B200_OK) return rc;
+    fe* d = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
+    B200_CUDA(cudaMemcpyAsync(d, states, batch * 3 * sizeof(fe), cudaMemcpyDefault, st));
+    k_poseidon2_permute<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(d, batch);
+    B200_CUDA(cudaMemcpyAsync(states, d, batch * 3 * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_poseidon2_hash_batch(b200_ctx* ctx, const uint64_t* inputs, size_t batch, size_t len, uint64_t* out) {
+    B200_TRY
+    if (!ctx || !out || (batch && len && !inputs)) return B200_ERR_INVALID;
+    if (batch == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = load_constants(ctx->c.device);
+    if (rc != B200_OK) return rc;
+    cudaStream_t st = ctx->c.stream;
+    if ((rc = ctx->c.plonk_ws.reserve((batch * len + batch + 1) * sizeof(fe))) != B200_OK) return rc;
+    fe* d_in = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
+    fe* d_out = d_in + batch * len;
+    if (len) B200_CUDA(cudaMemcpyAsync(d_in, inputs, batch * len * sizeof(fe), cudaMemcpyDefault, st));
+    k_poseidon2_hash<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(d_in, batch, len, d_out);
+    B200_CUDA(cudaMemcpyAsync(out, d_out, batch * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+    B200_CATCH
+}
+
+}  // extern "C"

@@ -10,6 +10,11 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built library (it is git-ignored): build it once, in-tree
+    lib = os.path.join(ROOT, "renegade_b200", "libb200prover.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "renegade_b200", "csrc"), "-j4", "-s"])
 
 
 @pytest.fixture(scope="session")
