@@ -90,6 +90,10 @@ __global__ void selftest_field_kernel(uint64_t seed, size_t iters, unsigned long
             b.l[0] -= 1;
         }
         if (!fe_eq(fe_mul<FqCfg>(a, b), fe_mul_chain<FqCfg>(a, b))) ++bad;
+        // fused a*b + c*d / a*b - c*d vs two separate products
+        const fe c = st_random_fe<FqCfg>(seed ^ 0x7777, 2 * i), d = i == 0 ? a : st_random_fe<FqCfg>(seed ^ 0x7777, 2 * i + 1);
+        if (!fe_eq(fe_mul_add2<FqCfg>(a, b, c, d), fe_add<FqCfg>(fe_mul_chain<FqCfg>(a, b), fe_mul_chain<FqCfg>(c, d)))) ++bad;
+        if (!fe_eq(fe_mul_sub2<FqCfg>(a, b, c, d), fe_sub<FqCfg>(fe_mul_chain<FqCfg>(a, b), fe_mul_chain<FqCfg>(c, d)))) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -63,7 +63,7 @@ FF_HD g1_xyzz g1_dbl_affine(const g1_affine& p) {
     fe xx = fe_sqr<Fq>(p.x);
     fe m = fe_add<Fq>(fe_dbl<Fq>(xx), xx);
     r.x = fe_sub<Fq>(fe_sqr<Fq>(m), fe_dbl<Fq>(s));
-    r.y = fe_sub<Fq>(fe_mul<Fq>(m, fe_sub<Fq>(s, r.x)), fe_mul<Fq>(w, p.y));
+    r.y = fe_mul_sub2<Fq>(m, fe_sub<Fq>(s, r.x), w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -80,7 +80,7 @@ FF_HD g1_xyzz g1_dbl(const g1_xyzz& p) {
     fe xx = fe_sqr<Fq>(p.x);
     fe m = fe_add<Fq>(fe_dbl<Fq>(xx), xx);
     r.x = fe_sub<Fq>(fe_sqr<Fq>(m), fe_dbl<Fq>(s));
-    r.y = fe_sub<Fq>(fe_mul<Fq>(m, fe_sub<Fq>(s, r.x)), fe_mul<Fq>(w, p.y));
+    r.y = fe_mul_sub2<Fq>(m, fe_sub<Fq>(s, r.x), w, p.y);
     r.zz = fe_mul<Fq>(v, p.zz);
     r.zzz = fe_mul<Fq>(w, p.zzz);
     return r;
@@ -104,7 +104,7 @@ FF_HD g1_xyzz g1_add_mixed(const g1_xyzz& a, const g1_affine& p) {
     fe ppp = fe_mul<Fq>(pp_, pp);
     fe q = fe_mul<Fq>(a.x, pp);
     r.x = fe_sub<Fq>(fe_sub<Fq>(fe_sqr<Fq>(rr), ppp), fe_dbl<Fq>(q));
-    r.y = fe_sub<Fq>(fe_mul<Fq>(rr, fe_sub<Fq>(q, r.x)), fe_mul<Fq>(a.y, ppp));
+    r.y = fe_mul_sub2<Fq>(rr, fe_sub<Fq>(q, r.x), a.y, ppp);
     r.zz = fe_mul<Fq>(a.zz, pp);
     r.zzz = fe_mul<Fq>(a.zzz, ppp);
     return r;
@@ -129,7 +129,7 @@ FF_HD g1_xyzz g1_add(const g1_xyzz& a, const g1_xyzz& b) {
     fe ppp = fe_mul<Fq>(pp_, pp);
     fe q = fe_mul<Fq>(u1, pp);
     r.x = fe_sub<Fq>(fe_sub<Fq>(fe_sqr<Fq>(rr), ppp), fe_dbl<Fq>(q));
-    r.y = fe_sub<Fq>(fe_mul<Fq>(rr, fe_sub<Fq>(q, r.x)), fe_mul<Fq>(s1, ppp));
+    r.y = fe_mul_sub2<Fq>(rr, fe_sub<Fq>(q, r.x), s1, ppp);
     r.zz = fe_mul<Fq>(fe_mul<Fq>(a.zz, b.zz), pp);
     r.zzz = fe_mul<Fq>(fe_mul<Fq>(a.zzz, b.zzz), ppp);
     return r;

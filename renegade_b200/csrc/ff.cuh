@@ -476,6 +476,117 @@ FF_HD fe fe_mul(const fe& a, const fe& b) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// a*b + c*d (Montgomery) with ONE reduction: each round accumulates both partial products before
+// the single m*p step, so the pair costs 192 instead of 256 wide multiply-adds.  Bounds: the
+// running value stays below a + c + p < 3p < 2^256, inside a round below 2^288 (E needs 9 limbs,
+// O never carries out of 8) — checked with exact carry semantics in Python before the PTX was
+// written; the device result is cross-checked against two separate products in
+// b200_selftest_field.  Used for Y3 = R (Q - X3) - Y1 PPP of the curve additions.
+// ---------------------------------------------------------------------------------------------
+template <class C>
+FF_HD fe fe_mul_add2(const fe& a, const fe& b, const fe& c, const fe& d) {
+#if defined(__CUDA_ARCH__)
+    uint32_t E[9], O[8];
+    {
+        const uint32_t s = b.l[0], t = d.l[0];
+        ptx::wmul(O[0], O[1], a.l[1], s);
+        ptx::wmul(O[2], O[3], a.l[3], s);
+        ptx::wmul(O[4], O[5], a.l[5], s);
+        ptx::wmul(O[6], O[7], a.l[7], s);
+        ptx::wmul(E[0], E[1], a.l[0], s);
+        ptx::wmul(E[2], E[3], a.l[2], s);
+        ptx::wmul(E[4], E[5], a.l[4], s);
+        ptx::wmul(E[6], E[7], a.l[6], s);
+        ptx::wmad_cc(O[0], O[1], c.l[1], t);
+        ptx::wmadc_cc(O[2], O[3], c.l[3], t);
+        ptx::wmadc_cc(O[4], O[5], c.l[5], t);
+        ptx::wmadc_cc(O[6], O[7], c.l[7], t);
+        ptx::wmad_cc(E[0], E[1], c.l[0], t);
+        ptx::wmadc_cc(E[2], E[3], c.l[2], t);
+        ptx::wmadc_cc(E[4], E[5], c.l[4], t);
+        ptx::wmadc_cc(E[6], E[7], c.l[6], t);
+        E[8] = ptx::addc(0u, 0u);
+        const uint32_t m = E[0] * C::inv;
+        ptx::wmad_cc(O[0], O[1], C::mod(1), m);
+        ptx::wmadc_cc(O[2], O[3], C::mod(3), m);
+        ptx::wmadc_cc(O[4], O[5], C::mod(5), m);
+        ptx::wmadc_cc(O[6], O[7], C::mod(7), m);
+        ptx::wmad_cc(E[0], E[1], C::mod(0), m);
+        ptx::wmadc_cc(E[2], E[3], C::mod(2), m);
+        ptx::wmadc_cc(E[4], E[5], C::mod(4), m);
+        ptx::wmadc_cc(E[6], E[7], C::mod(6), m);
+        E[8] = ptx::addc(E[8], 0u);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        uint32_t nE[9], nO[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nE[k] = O[k];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) nO[k] = E[k + 2];
+        nO[7] = 0;
+        const uint32_t s = b.l[i], t = d.l[i];
+        nE[0] = ptx::add_cc(nE[0], E[1]);  // carry has weight 2^32 -> first odd chain
+        ptx::wmadc_cc(nO[0], nO[1], a.l[1], s);
+        ptx::wmadc_cc(nO[2], nO[3], a.l[3], s);
+        ptx::wmadc_cc(nO[4], nO[5], a.l[5], s);
+        ptx::wmadc_cc(nO[6], nO[7], a.l[7], s);
+        ptx::wmad_cc(nE[0], nE[1], a.l[0], s);
+        ptx::wmadc_cc(nE[2], nE[3], a.l[2], s);
+        ptx::wmadc_cc(nE[4], nE[5], a.l[4], s);
+        ptx::wmadc_cc(nE[6], nE[7], a.l[6], s);
+        nE[8] = ptx::addc(0u, 0u);
+        ptx::wmad_cc(nO[0], nO[1], c.l[1], t);
+        ptx::wmadc_cc(nO[2], nO[3], c.l[3], t);
+        ptx::wmadc_cc(nO[4], nO[5], c.l[5], t);
+        ptx::wmadc_cc(nO[6], nO[7], c.l[7], t);
+        ptx::wmad_cc(nE[0], nE[1], c.l[0], t);
+        ptx::wmadc_cc(nE[2], nE[3], c.l[2], t);
+        ptx::wmadc_cc(nE[4], nE[5], c.l[4], t);
+        ptx::wmadc_cc(nE[6], nE[7], c.l[6], t);
+        nE[8] = ptx::addc(nE[8], 0u);
+        const uint32_t m = nE[0] * C::inv;
+        ptx::wmad_cc(nO[0], nO[1], C::mod(1), m);
+        ptx::wmadc_cc(nO[2], nO[3], C::mod(3), m);
+        ptx::wmadc_cc(nO[4], nO[5], C::mod(5), m);
+        ptx::wmadc_cc(nO[6], nO[7], C::mod(7), m);
+        ptx::wmad_cc(nE[0], nE[1], C::mod(0), m);
+        ptx::wmadc_cc(nE[2], nE[3], C::mod(2), m);
+        ptx::wmadc_cc(nE[4], nE[5], C::mod(4), m);
+        ptx::wmadc_cc(nE[6], nE[7], C::mod(6), m);
+        nE[8] = ptx::addc(nE[8], 0u);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = nE[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) O[k] = nO[k];
+    }
+    fe r, t;
+    r.l[0] = ptx::add_cc(O[0], E[1]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) r.l[k] = ptx::addc_cc(O[k], E[k + 1]);
+    r.l[7] = ptx::addc(O[7], E[8]);
+    // result < 3p: two conditional subtractions
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        t.l[0] = ptx::sub_cc(r.l[0], C::mod(0));
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t.l[k] = ptx::subc_cc(r.l[k], C::mod(k));
+        const uint32_t borrow = ptx::subc(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.l[k] = borrow ? r.l[k] : t.l[k];
+    }
+    return r;
+#else
+    return fe_add<C>(fe_mul<C>(a, b), fe_mul<C>(c, d));
+#endif
+}
+// a*b - c*d
+template <class C>
+FF_HD fe fe_mul_sub2(const fe& a, const fe& b, const fe& c, const fe& d) {
+    return fe_mul_add2<C>(a, b, c, fe_sub<C>(fe_zero(), d));
+}
+
 template <class C>
 FF_HD fe fe_sqr(const fe& a) {
     return fe_mul<C>(a, a);

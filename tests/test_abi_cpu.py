@@ -118,3 +118,23 @@ def test_keccak256_known_answers(oracle):
     for ln in (1, 55, 135, 136, 137, 271, 272, 273, 1000):
         msg = bytes(rnd.randrange(256) for _ in range(ln))
         assert keccak256(msg) == oracle.keccak256(msg), ln
+
+
+def test_bad_arguments_return_error_codes():
+    """The boundary never aborts or throws: NULL handles / pointers come back as B200_ERR_INVALID
+    (a prover failure must surface as an error value)."""
+    from renegade_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_uint64 * 8)()
+    inf = C.c_int(0)
+    assert lib.b200_msm(None, None, 0, None, 0, 0, out, C.byref(inf)) == -1
+    assert lib.b200_ntt(None, None, 10, 0, 0) == -1
+    assert lib.b200_plonk_prove(None, None, None, None, None, None, None, None) == -1
+    assert lib.b200_plonk_link(None, None, None, 0, None, 0, None, None, 8, 0, 4, None, None) == -1
+    assert lib.b200_poseidon2_hash_batch(None, None, 1, 2, None) == -1
+    assert lib.b200_init(0, None) == -1
+    h = C.c_void_p()
+    assert lib.b200_init(-3, C.byref(h)) in (-1, -6)   # bad ordinal (or no device at all on the CPU box)
+    lib.b200_shutdown(None)           # tolerated
+    lib.b200_bases_free(None, None)   # tolerated
+    lib.b200_pk_free(None, None)
