@@ -293,6 +293,12 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
     g1_xyzz_store(seg_sums + s, acc);
 }
 
+// The reduction-side kernels run one warp per SM sub-partition on long dependent chains; with
+// g1_add inlined a dozen times their code no longer fits the instruction cache (ncu: 0.67
+// "no instruction" stalls per issue).  Out-of-line copies keep those kernels small.
+__device__ __noinline__ g1_xyzz xyzz_add(const g1_xyzz& a, const g1_xyzz& b) { return g1_add(a, b); }
+__device__ __noinline__ g1_xyzz xyzz_dbl(const g1_xyzz& a) { return g1_dbl(a); }
+
 // bucket = sum of its segment sums: sequential for ordinary buckets, deferred to a block tree
 // (msm_heavy_combine_kernel) for buckets cut into more than kCombineSeq segments.
 __global__ void __launch_bounds__(128) msm_bucket_combine_kernel(const g1_xyzz* __restrict__ seg_sums,
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(128) msm_bucket_combine_kernel(const g1_xyzz* 
     g1_xyzz acc = g1_xyzz_inf();
     if (s0 < s1) {
         acc = g1_xyzz_load(seg_sums + s0);
-        for (uint32_t s = s0 + 1; s < s1; ++s) acc = g1_add(acc, g1_xyzz_load(seg_sums + s));
+        for (uint32_t s = s0 + 1; s < s1; ++s) acc = xyzz_add(acc, g1_xyzz_load(seg_sums + s));
     }
     g1_xyzz_store(buckets + b, acc);
 }
@@ -326,11 +332,11 @@ __global__ void __launch_bounds__(kReduceThreads) msm_heavy_combine_kernel(const
         const uint32_t b = heavy_list[h];
         const uint32_t s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
         g1_xyzz acc = g1_xyzz_inf();
-        for (uint32_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) acc = g1_add(acc, g1_xyzz_load(seg_sums + s));
+        for (uint32_t s = s0 + threadIdx.x; s < s1; s += blockDim.x) acc = xyzz_add(acc, g1_xyzz_load(seg_sums + s));
         sh[threadIdx.x] = acc;
         __syncthreads();
         for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
-            if ((int)threadIdx.x < stride) sh[threadIdx.x] = g1_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+            if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
             __syncthreads();
         }
         if (threadIdx.x == 0) g1_xyzz_store(buckets + b, sh[0]);
@@ -355,21 +361,21 @@ __global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyz
         const uint32_t cnt = min((uint32_t)kReduceChunk, buckets_per_window - first);
         g1_xyzz run = g1_xyzz_inf(), acc = g1_xyzz_inf();
         for (int i = (int)cnt - 1; i >= 0; --i) {
-            run = g1_add(run, g1_xyzz_load(B + i));
-            acc = g1_add(acc, run);
+            run = xyzz_add(run, g1_xyzz_load(B + i));
+            acc = xyzz_add(acc, run);
         }
         // (first) * run by double-and-add; first < 2^(c-1)
         g1_xyzz scaled = g1_xyzz_inf();
         for (int bit = c - 2; bit >= 0; --bit) {
-            scaled = g1_dbl(scaled);
-            if ((first >> bit) & 1u) scaled = g1_add(scaled, run);
+            scaled = xyzz_dbl(scaled);
+            if ((first >> bit) & 1u) scaled = xyzz_add(scaled, run);
         }
-        contrib = g1_add(acc, scaled);
+        contrib = xyzz_add(acc, scaled);
     }
     sh[threadIdx.x] = contrib;
     __syncthreads();
     for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
-        if ((int)threadIdx.x < stride) sh[threadIdx.x] = g1_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+        if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
         __syncthreads();
     }
     if (threadIdx.x == 0) g1_xyzz_store(partials + (size_t)window * gridDim.x + blockIdx.x, sh[0]);
@@ -382,11 +388,11 @@ __global__ void __launch_bounds__(kReduceThreads) msm_reduce_final_kernel(const 
     const uint32_t window = blockIdx.x;
     g1_xyzz acc = g1_xyzz_inf();
     for (uint32_t i = threadIdx.x; i < n_partials; i += blockDim.x)
-        acc = g1_add(acc, g1_xyzz_load(partials + (size_t)window * n_partials + i));
+        acc = xyzz_add(acc, g1_xyzz_load(partials + (size_t)window * n_partials + i));
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
-        if ((int)threadIdx.x < stride) sh[threadIdx.x] = g1_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+        if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
         __syncthreads();
     }
     if (threadIdx.x == 0) g1_xyzz_store(window_sums + window, sh[0]);
