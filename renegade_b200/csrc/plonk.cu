@@ -206,6 +206,9 @@ struct QuotArgs {
     fe beta, gamma, alpha, alpha2;
     fe zh_inv[8];
 };
+// k_quotient chains ~60 field products; fully unrolled it is ~180 KB of code and starves on the
+// instruction cache (ncu: 1.9 "no instruction" stalls per issue; an out-of-line multiplier was
+// slower still: 0.85 -> 0.98 ms, stack traffic).  The per-wire loops are therefore kept rolled.
 __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.m) return;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     for (int j = 0; j < NW; ++j) w[j] = fe_load_ro(a.ext + j * m + i);
     // gate: q_c + pi + sum q_lc w + q_mul0 w0 w1 + q_mul1 w2 w3 + q_ecc w0..w4 + sum q_hash w^5 - q_o w4
     fe acc = FADD(fe_load_ro(a.sel + 11 * m + i), fe_load_ro(a.ext + 5 * m + i));
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 4; ++j) {
         acc = FADD(acc, FMUL(fe_load_ro(a.sel + j * m + i), w[j]));
         const fe w2 = fe_sqr<Fr>(w[j]);
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     const fe zxw = fe_load_ro(a.ext + 6 * m + ((i + 8) & (m - 1)));
     const fe bx = FMUL(a.beta, fe_load_ro(a.pts + i));
     fe p1 = zx, p2 = zxw;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NW; ++j) {
         const fe t = FADD(w[j], a.gamma);
         p1 = FMUL(p1, FADD(t, FMUL(a.k.v[j], bx)));
