@@ -83,3 +83,38 @@ def test_prove_2_16_verifies(ctx, oracle, pyoracle):
     assert oracle.plonk_verify_known_tau(log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, op, tau)
     rc, oproof, _, _ = oracle.plonk_prove(log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, blinders, srs)
     assert rc == 0 and (proof.to_array() == oproof.to_array()).all()
+
+
+def test_prove_2_17_max_domain(ctx, oracle, pyoracle):
+    """The largest domain the reference supports: MAX_SRS_DEGREE = 2^17 + 2 (srs.rs:44-47), i.e. an
+    SRS of exactly 2^17 + 3 powers and blinded polynomials of n + 3 coefficients."""
+    log_n = 17
+    circ, tau, srs = setup(ctx, oracle, pyoracle, log_n, seed=0x17, num_inputs=13)
+    assert srs.shape[0] == (1 << 17) + 3
+    bases = ctx.load_bases(srs)
+    pk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    blinders = synth.splitmix_blinders(0x1717)
+    proof, hint = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, blinders)
+    opk = {"selector_comms": pk.selector_comms, "sigma_comms": pk.sigma_comms}
+    op = oracle.PlonkProof.from_buffer_copy(bytes(proof))
+    assert oracle.plonk_verify_known_tau(log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, op, tau)
+    # one more power than the SRS holds must be refused up front (MAX_SRS_DEGREE rule), not crash
+    from renegade_b200._lib import B200Error
+    short = ctx.load_bases(srs[: (1 << 17) + 2])
+    with pytest.raises(B200Error):
+        PlonkKzgSnark.preprocess(ctx, short, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+
+
+def test_zero_public_inputs_and_tiny_domain(ctx, oracle, pyoracle):
+    """Edge cases: a circuit without public inputs, and the smallest domain the prover accepts (n = 4)."""
+    from renegade_b200._lib import B200Error
+    for log_n, num_inputs in ((6, 0), (2, 1)):
+        circ, tau, srs = setup(ctx, oracle, pyoracle, log_n, seed=40 + log_n, num_inputs=num_inputs)
+        bases = ctx.load_bases(srs)
+        pk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+        bl = synth.splitmix_blinders(3)
+        proof, _ = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+        opk = oracle.plonk_preprocess(log_n, circ.selectors, circ.perm, circ.k, srs)
+        rc, oproof, _, _ = oracle.plonk_prove(log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl, srs)
+        assert rc == 0 and (proof.to_array() == oproof.to_array()).all(), (log_n, num_inputs)
+        assert oracle.plonk_verify_known_tau(log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, oproof, tau)
