@@ -332,6 +332,12 @@ def main():
 
     # ---- second clause: 2^20-point MSM per GPU, sharded across ranks -------------------------------------
     msm = None
+    msm_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "msm_accumulate_traffic_2_20.json")) as f:
+            msm_traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     if not args.no_msm:
         nm = 1 << MSM_LOG_N
         first = rank * nm
@@ -384,7 +390,15 @@ def main():
             "device_phases_ms": {k: sum(p[k] for p in mph) / len(mph) for k in ("total", "sort", "accumulate", "reduce")},
             "plan": mplan,
             "roofline": {"bound": "hbm", "achieved": nm * BYTES_PER_PAIR / (macc * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": nm * BYTES_PER_PAIR / (macc * 1e-3) / 1e9 / peak, "kernel": "msm_accumulate_kernel"},
+                         "frac": nm * BYTES_PER_PAIR / (macc * 1e-3) / 1e9 / peak, "kernel": "msm_accumulate_kernel",
+                         "traffic": msm_traffic,
+                         # what actually bounds the kernel: Fq products on the IMAD.WIDE pipe.  A mixed addition is
+                         # 8M + 2S with one fused pair = 9.5 product-equivalents of 128 IMAD.WIDE each; the pipe issues
+                         # one warp-wide IMAD.WIDE per ~4 clk per SM sub-partition (tools/microbench.cu).
+                         "int_pipe": {"achieved_gmul_per_s": nm * mplan["digits"] * 9.5 / (macc * 1e-3) / 1e9,
+                                      "peak_gmul_per_s": 148 * 4 * 32 / (128 * 4.0) * 1.965,
+                                      "frac": nm * mplan["digits"] * 9.5 / (macc * 1e-3) / 1e9 / (148 * 4 * 32 / (128 * 4.0) * 1.965),
+                                      "measured_multiplier_gmul_per_s": 66.6}},
             "l2": "window tables %.0f MB + 32 MB of scalars per step vs 126 MB of L2" % (mplan["tables"] * nm * 64 / 1e6),
         }
 
