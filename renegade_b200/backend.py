@@ -187,15 +187,16 @@ class UnivariateUniversalParams:
 
 
 def parse_ptau_file(ctx: Context, data: bytes, window_bits: int = 0,
-                    check_on_curve: bool = True) -> UnivariateUniversalParams:
+                    check_on_curve: bool = True, count: int | None = None) -> UnivariateUniversalParams:
     """srs.rs:63-71: header/section checks, MAX_SRS_DEGREE+1 G1 powers, on-curve assertion
-    (srs.rs:178-179, run on the device)."""
+    (srs.rs:178-179, run on the device).  `count` overrides the number of powers kept (the
+    reference always keeps MAX_SRS_DEGREE + 1; smaller values serve truncated test files)."""
     lib = _lib.load()
     buf = (C.c_char * len(data)).from_buffer_copy(data)
     rec = C.c_void_p()
     n = C.c_size_t()
     _lib.check(lib.b200_srs_parse_ptau(C.cast(buf, C.c_void_p), len(data), C.byref(rec), C.byref(n)))
-    need = MAX_SRS_DEGREE + 1
+    need = MAX_SRS_DEGREE + 1 if count is None else count
     if n.value < need:
         raise _lib.B200Error(-4, f"ptau: only {n.value} G1 records available, need {need}")
     off = rec.value - C.addressof(buf)

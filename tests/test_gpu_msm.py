@@ -193,3 +193,24 @@ def test_msm_batch_via_prover_sizes(ctx, oracle):
     for b in range(batch):
         exp, _ = oracle.msm(pts, oracle.array_from_mont(oracle.FR, s[b, :n]))
         assert (out[b] == exp).all(), b
+
+
+def test_parse_ptau_file_on_reference_bytes(ctx, oracle, srs_head):
+    """The SRS loader end to end on the reference's own file bytes (first 512 powers of
+    srs/srs00): header checks on the host, upload, on-curve assertion on the device, commit."""
+    from renegade_b200._lib import B200Error
+    params = rb.parse_ptau_file(ctx, srs_head, count=512)
+    assert len(params.powers_of_g) == 512 and params.powers_of_g_host.shape == (512, 8)
+    coeffs = oracle.splitmix_fr(0xABC, 300, montgomery=True)
+    out, inf = rb.UnivariateKzgPCS.commit(ctx, params.powers_of_g, coeffs)
+    exp, _ = oracle.msm(params.powers_of_g_host[:300], oracle.array_from_mont(oracle.FR, coeffs))
+    assert not inf and (out == exp).all()
+    # the full-size request (MAX_SRS_DEGREE + 1 powers) must be refused on a truncated file
+    with pytest.raises(B200Error):
+        rb.parse_ptau_file(ctx, srs_head)
+    # a corrupted record is caught by the device-side on-curve check (srs.rs:179 "point not on curve")
+    bad = bytearray(srs_head)
+    bad[80 + 64 * 100] ^= 1
+    with pytest.raises(B200Error) as ei:
+        rb.parse_ptau_file(ctx, bytes(bad), count=512)
+    assert ei.value.code == -5
