@@ -81,6 +81,8 @@ __global__ void selftest_field_kernel(uint64_t seed, size_t iters, unsigned long
             b.l[0] -= 1;
         }
         if (!fe_eq(fe_mul<FrCfg>(a, b), fe_mul_chain<FrCfg>(a, b))) ++bad;
+        if (!fe_eq(fe_sqr<FrCfg>(a), fe_mul_chain<FrCfg>(a, a))) ++bad;  // dedicated squarer
+        if (!fe_eq(fe_sqr<FrCfg>(b), fe_mul_chain<FrCfg>(b, b))) ++bad;
     }
     {
         fe a = st_random_fe<FqCfg>(seed ^ 0x5151, 2 * i), b = st_random_fe<FqCfg>(seed ^ 0x5151, 2 * i + 1);
@@ -90,6 +92,8 @@ __global__ void selftest_field_kernel(uint64_t seed, size_t iters, unsigned long
             b.l[0] -= 1;
         }
         if (!fe_eq(fe_mul<FqCfg>(a, b), fe_mul_chain<FqCfg>(a, b))) ++bad;
+        if (!fe_eq(fe_sqr<FqCfg>(a), fe_mul_chain<FqCfg>(a, a))) ++bad;
+        if (!fe_eq(fe_sqr<FqCfg>(b), fe_mul_chain<FqCfg>(b, b))) ++bad;
         // fused a*b + c*d / a*b - c*d vs two separate products
         const fe c = st_random_fe<FqCfg>(seed ^ 0x7777, 2 * i), d = i == 0 ? a : st_random_fe<FqCfg>(seed ^ 0x7777, 2 * i + 1);
         if (!fe_eq(fe_mul_add2<FqCfg>(a, b, c, d), fe_add<FqCfg>(fe_mul_chain<FqCfg>(a, b), fe_mul_chain<FqCfg>(c, d)))) ++bad;

@@ -587,9 +587,109 @@ FF_HD fe fe_mul_sub2(const fe& a, const fe& b, const fe& c, const fe& d) {
     return fe_mul_add2<C>(a, b, c, fe_sub<C>(fe_zero(), d));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Montgomery square.  Same even/odd word-serial scheme as fe_mul, but round i only multiplies
+// a_i by the limbs it has not met yet: a^2 = sum_i a_i * (a_i X^i + 2 * sum_{j>i} a_j X^j), and
+// 2 * (a >> 32(i+1)) is read off d = 2a (fits 8 limbs: a < 2^254) with the bit that crossed the
+// limb boundary masked.  36 + 64 = 100 wide multiply-adds instead of 128.  The running value stays
+// below 2a + p < 3p < 2^256 and the result below 2p (validated in Python with exact carries;
+// cross-checked against fe_mul(a, a) on the device by b200_selftest_field).
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+template <class C, int I>
+FF_D void fe_sqr_round(uint32_t (&E)[9], uint32_t (&O)[8], const fe& a, const fe& d) {
+    // operand limbs of this round: v_I = a_I, v_{I+1} = d_{I+1} & ~1, v_j = d_j (j >= I+2)
+    auto v = [&](int j) -> uint32_t {
+        return j == I ? a.l[j] : (j == I + 1 ? (d.l[j] & 0xfffffffeu) : d.l[j]);
+    };
+    const uint32_t s = a.l[I];
+    uint32_t nE[9], nO[8];
+    if constexpr (I == 0) {
+        ptx::wmul(nO[0], nO[1], v(1), s);
+        ptx::wmul(nO[2], nO[3], v(3), s);
+        ptx::wmul(nO[4], nO[5], v(5), s);
+        ptx::wmul(nO[6], nO[7], v(7), s);
+        ptx::wmul(nE[0], nE[1], v(0), s);
+        ptx::wmul(nE[2], nE[3], v(2), s);
+        ptx::wmul(nE[4], nE[5], v(4), s);
+        ptx::wmul(nE[6], nE[7], v(6), s);
+        nE[8] = 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nE[k] = O[k];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) nO[k] = E[k + 2];
+        nO[7] = 0;
+        nE[8] = 0;
+        constexpr int j0 = (I & 1) ? I : I + 1;   // first odd limb index >= I
+        constexpr int j0e = (I & 1) ? I + 1 : I;  // first even limb index >= I
+        nE[0] = ptx::add_cc(nE[0], E[1]);  // carry (weight 2^32) runs up the odd array
+#pragma unroll
+        for (int k = 0; k < j0 - 1; ++k) nO[k] = ptx::addc_cc(nO[k], 0u);
+        if constexpr (j0 <= 1) ptx::wmadc_cc(nO[0], nO[1], v(1), s);
+        if constexpr (j0 <= 3) ptx::wmadc_cc(nO[2], nO[3], v(3), s);
+        if constexpr (j0 <= 5) ptx::wmadc_cc(nO[4], nO[5], v(5), s);
+        ptx::wmadc_cc(nO[6], nO[7], v(7), s);
+        if constexpr (j0e <= 6) {
+            // the first product of the even chain starts a fresh carry chain
+            if constexpr (j0e == 0) ptx::wmad_cc(nE[0], nE[1], v(0), s);
+            if constexpr (j0e == 2) ptx::wmad_cc(nE[2], nE[3], v(2), s);
+            if constexpr (j0e < 2) ptx::wmadc_cc(nE[2], nE[3], v(2), s);
+            if constexpr (j0e == 4) ptx::wmad_cc(nE[4], nE[5], v(4), s);
+            if constexpr (j0e < 4) ptx::wmadc_cc(nE[4], nE[5], v(4), s);
+            if constexpr (j0e == 6) ptx::wmad_cc(nE[6], nE[7], v(6), s);
+            if constexpr (j0e < 6) ptx::wmadc_cc(nE[6], nE[7], v(6), s);
+            nE[8] = ptx::addc(0u, 0u);
+        }
+    }
+    const uint32_t m = nE[0] * C::inv;
+    ptx::wmad_cc(nO[0], nO[1], C::mod(1), m);
+    ptx::wmadc_cc(nO[2], nO[3], C::mod(3), m);
+    ptx::wmadc_cc(nO[4], nO[5], C::mod(5), m);
+    ptx::wmadc_cc(nO[6], nO[7], C::mod(7), m);
+    ptx::wmad_cc(nE[0], nE[1], C::mod(0), m);
+    ptx::wmadc_cc(nE[2], nE[3], C::mod(2), m);
+    ptx::wmadc_cc(nE[4], nE[5], C::mod(4), m);
+    ptx::wmadc_cc(nE[6], nE[7], C::mod(6), m);
+    nE[8] = ptx::addc(nE[8], 0u);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E[k] = nE[k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) O[k] = nO[k];
+}
+#endif
+
 template <class C>
 FF_HD fe fe_sqr(const fe& a) {
+#if defined(__CUDA_ARCH__)
+    fe d;  // 2a as a plain 256-bit integer (no reduction: a < 2^254)
+#pragma unroll
+    for (int k = 7; k >= 1; --k) d.l[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
+    d.l[0] = a.l[0] << 1;
+    uint32_t E[9], O[8];
+    fe_sqr_round<C, 0>(E, O, a, d);
+    fe_sqr_round<C, 1>(E, O, a, d);
+    fe_sqr_round<C, 2>(E, O, a, d);
+    fe_sqr_round<C, 3>(E, O, a, d);
+    fe_sqr_round<C, 4>(E, O, a, d);
+    fe_sqr_round<C, 5>(E, O, a, d);
+    fe_sqr_round<C, 6>(E, O, a, d);
+    fe_sqr_round<C, 7>(E, O, a, d);
+    fe r, t;
+    r.l[0] = ptx::add_cc(O[0], E[1]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) r.l[k] = ptx::addc_cc(O[k], E[k + 1]);
+    r.l[7] = ptx::addc(O[7], E[8]);
+    t.l[0] = ptx::sub_cc(r.l[0], C::mod(0));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t.l[k] = ptx::subc_cc(r.l[k], C::mod(k));
+    const uint32_t borrow = ptx::subc(0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = borrow ? r.l[k] : t.l[k];
+    return r;
+#else
     return fe_mul<C>(a, a);
+#endif
 }
 
 template <class C>
