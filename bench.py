@@ -38,9 +38,6 @@ CIRCUIT_SEED = 0xB200
 MSM_LOG_N = 20
 BYTES_PER_PAIR = 96        # 64 B affine base + 32 B scalar
 SEED_BASES, SEED_SCALARS, SEED_SRS = 0xB200, 0x5CA1A8, 0x7A0
-# kernels launched per batched MSM: count, 3x scan, scatter, 3x scan, segfill, 3x segment ordering,
-# accumulate, combine, heavy_combine, reduce, reduce_final
-KERNELS_PER_MSM = 17
 METRIC = "proofs/sec, VALID-MATCH-class TurboPlonk proof (n = 2^16 gates, BN254/KZG)"
 WORKLOAD = ("synthetic TurboPlonk circuit, n = 2^16 gates, 17 public inputs, 5 wire columns, 13 selector columns "
             "(stand-in for IntentAndBalancePrivateSettlementCircuit, BASELINE.json configs[3]); "
@@ -409,7 +406,6 @@ def main():
 
     ms_step = dt / args.steps * 1e3
     out = base_line(args, world)
-    n_msm_calls = 4  # batched commitments per proof: 5 wires, z, 5 quotient chunks, 2 openings
     out.update({
         "value": world * args.steps / dt, "ms_per_step": ms_step,
         "config": {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": NUM_INPUTS, "gates_used": circ.n_gates,

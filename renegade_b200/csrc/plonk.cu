@@ -809,8 +809,8 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 // &group_layout, &commit_key)` (circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47,
 // intent_and_balance.rs:66-72): q = (a1 - a2) / Z_D with Z_D = prod_{i<size} (X - g^(offset+i)),
 // g the generator of the 2^alignment roots of unity (`GroupLayout`); eta from the transcript;
-// opening of a1 - a2 - Z_D(eta) q at eta.  Division by Z_D = `size` synthetic divisions, each the
-// Horner suffix scan run in place.
+// opening of a1 - a2 - Z_D(eta) q at eta.  Division by Z_D = `size` synthetic divisions (Horner suffix
+// scans ping-ponging between two buffers).
 // ---------------------------------------------------------------------------------------------
 struct LinkOut {
     g1_affine quotient_commitment;
