@@ -291,3 +291,25 @@ def plonk_link_verify_known_tau(comm1, comm2, alignment, offset, size, proof: Li
         _p(np.ascontiguousarray(comm1, dtype=np.uint64)), _p(np.ascontiguousarray(comm2, dtype=np.uint64)),
         C.c_uint(alignment), C.c_size_t(offset), C.c_size_t(size), C.byref(proof),
         _p(np.ascontiguousarray(tau_mont, dtype=np.uint64))))
+
+
+def plonk_verify_operands(log_n, num_inputs, k, pk, pub_inputs, proof: PlonkProof):
+    """G1 operands (A, B) of the pairing check e(A, [tau]_2) == e(B, [1]_2); each is an (x||y Montgomery, is_identity) pair."""
+    a, b = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+    ai, bi = C.c_int(0), C.c_int(0)
+    lib().orc_plonk_verify_operands(
+        C.c_uint(log_n), C.c_size_t(num_inputs), _p(np.ascontiguousarray(k, dtype=np.uint64)),
+        _p(pk["selector_comms"]), _p(pk["sigma_comms"]), _p(np.ascontiguousarray(pub_inputs, dtype=np.uint64)),
+        C.byref(proof), _p(a), C.byref(ai), _p(b), C.byref(bi))
+    return (a, bool(ai.value)), (b, bool(bi.value))
+
+
+def plonk_verify_pairing(log_n, num_inputs, k, pk, pub_inputs, proof: PlonkProof, g2_h, g2_tau_h) -> bool:
+    """`PlonkKzgSnark::verify` for an SRS with unknown tau: e(A, tau H) * e(-B, H) == 1, with the pairing of
+    oracle/bn254_pairing_py.py (g2_h, g2_tau_h as decoded by bn254_pairing_py.decode_g2_mont)."""
+    import bn254_pairing_py as pr
+    import bn254_py as py
+    (a, a_inf), (b, b_inf) = plonk_verify_operands(log_n, num_inputs, k, pk, pub_inputs, proof)
+    pa = None if a_inf else py.decode_g1_mont(a.tobytes(), 0)
+    pb = None if b_inf else py.g1_neg(py.decode_g1_mont(b.tobytes(), 0))
+    return pr.pairing_product_is_one([(pa, g2_tau_h), (pb, g2_h)])

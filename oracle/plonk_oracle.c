@@ -533,9 +533,15 @@ static int jac_equal(const jac* a, const jac* b) {
     return eq4(A.x, B.x) && eq4(A.y, B.y);
 }
 
-int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const u64* k, const u64* selector_comms,
-                               const u64* sigma_comms, const u64* pub_inputs, const orc_plonk_proof* proof,
-                               const u64* tau) {
+/* Shared verifier core.  With tau != NULL the two KZG equations are checked in G1 (known-tau SRS).
+ * With out_a / out_b != NULL it instead outputs the operands of the batched pairing check
+ *     e(A, [tau]_2) == e(B, [1]_2),
+ *     A = W_zeta + u W_zeta_omega,
+ *     B = zeta W_zeta + u zeta omega W_zeta_omega + (F - E G) + u ([z] - z_omega G),
+ * which is the equation jellyfish's verifier hands to the pairing (u drawn after the openings). */
+static int verify_impl(unsigned log_n, size_t num_inputs, const u64* k, const u64* selector_comms,
+                       const u64* sigma_comms, const u64* pub_inputs, const orc_plonk_proof* proof,
+                       const u64* tau, u64* out_a, int* a_inf, u64* out_b, int* b_inf) {
     const size_t n = (size_t)1 << log_n;
     orc_plonk_challenges ch;
     transcript tr;
@@ -552,6 +558,9 @@ int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const u64* k, 
     for (int i = 0; i < NW - 1; ++i) tr_append_fr(&tr, proof->wire_sigma_evals[i]);
     tr_append_fr(&tr, proof->perm_next_eval);
     tr_challenge(&tr, ch.v);
+    tr_append_g1(&tr, proof->opening_proof);
+    tr_append_g1(&tr, proof->shifted_opening_proof);
+    tr_challenge(&tr, ch.u);
     tr_free(&tr);
 
     u64 one[4], w[4], vanish[4], l1[4], nfr[4], alpha2[4], t[4], u[4];
@@ -613,6 +622,24 @@ int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const u64* k, 
     u64 two[4] = {2, 0, 0, 0};
     fp_to_mont(&FQ, G + 4, two);
     jac lhs, rhs = F, tmp;
+    if (!tau) {
+        /* pairing operands */
+        u64 zw2[4], coef[4];
+        MUL(zw2, ch.zeta, w);
+        jac A, B = F;
+        g1_load(&A, proof->opening_proof);
+        g1_acc(&A, proof->shifted_opening_proof, ch.u);
+        fr_zero(u); SUB(t, u, E); g1_acc(&B, G, t);                       /* F - E G */
+        g1_acc(&B, proof->opening_proof, ch.zeta);                        /* + zeta W */
+        MUL(coef, ch.u, zw2); g1_acc(&B, proof->shifted_opening_proof, coef); /* + u zeta omega W' */
+        g1_acc(&B, proof->prod_perm_poly_comm, ch.u);                     /* + u [z] */
+        MUL(coef, ch.u, proof->perm_next_eval); fr_zero(u); SUB(coef, u, coef);
+        g1_acc(&B, G, coef);                                              /* - u z_omega G */
+        aff Aa, Ba;
+        jac_to_affine(&Aa, &A); jac_to_affine(&Ba, &B);
+        aff_store(&Aa, out_a, a_inf); aff_store(&Ba, out_b, b_inf);
+        return 1;
+    }
     SUB(t, tau, ch.zeta); g1_scale(&lhs, proof->opening_proof, t);
     fr_zero(u); SUB(t, u, E); g1_scale(&tmp, G, t); jac_add(&rhs, &rhs, &tmp);
     int ok = jac_equal(&lhs, &rhs);
@@ -624,6 +651,18 @@ int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const u64* k, 
     fr_zero(u); SUB(t, u, proof->perm_next_eval); g1_scale(&tmp, G, t); jac_add(&rhs, &rhs, &tmp);
     ok &= jac_equal(&lhs, &rhs);
     return ok;
+}
+
+int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const u64* k, const u64* selector_comms,
+                               const u64* sigma_comms, const u64* pub_inputs, const orc_plonk_proof* proof,
+                               const u64* tau) {
+    return verify_impl(log_n, num_inputs, k, selector_comms, sigma_comms, pub_inputs, proof, tau, NULL, NULL, NULL, NULL);
+}
+
+int orc_plonk_verify_operands(unsigned log_n, size_t num_inputs, const u64* k, const u64* selector_comms,
+                              const u64* sigma_comms, const u64* pub_inputs, const orc_plonk_proof* proof,
+                              u64* out_a, int* a_inf, u64* out_b, int* b_inf) {
+    return verify_impl(log_n, num_inputs, k, selector_comms, sigma_comms, pub_inputs, proof, NULL, out_a, a_inf, out_b, b_inf);
 }
 
 /* ------------------------------------------------------------------------------------------

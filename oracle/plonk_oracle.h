@@ -73,6 +73,14 @@ int orc_plonk_verify_known_tau(unsigned log_n, size_t num_inputs, const uint64_t
                                const uint64_t* pub_inputs, const orc_plonk_proof* proof,
                                const uint64_t* tau);
 
+/* The same verifier for an SRS with UNKNOWN tau (the reference's real SRS): outputs the two G1
+ * operands of the pairing check e(A, [tau]_2) == e(B, [1]_2) that `PlonkKzgSnark::verify` performs
+ * (traits.rs:1012-1018); the pairing itself is evaluated by oracle/bn254_pairing_py.py. */
+int orc_plonk_verify_operands(unsigned log_n, size_t num_inputs, const uint64_t* k,
+                              const uint64_t* selector_comms, const uint64_t* sigma_comms,
+                              const uint64_t* pub_inputs, const orc_plonk_proof* proof,
+                              uint64_t* out_a, int* a_inf, uint64_t* out_b, int* b_inf);
+
 /* ---- proof linking: restates mpc-plonk `PlonkKzgSnark::link_proofs::<SolidityTranscript>` as
  * called at circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47:
  * the two proofs' first wire polynomials a1, a2 agree on the link group's sub-domain

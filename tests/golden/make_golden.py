@@ -83,6 +83,16 @@ def main():
                            "fft": [hx(v) for v in o.dft_naive(x)],
                            "ifft": [hx(v) for v in o.dft_naive(x, inverse=True)],
                            "coset_fft": [hx(v) for v in o.dft_naive([v * pow(5, i, o.R) % o.R for i, v in enumerate(x)])]})
+    # the two G2 points the reference reads (srs.rs:147-157): H and tau*H, first two 128-byte records of
+    # ptau section 3 (after the 12-byte section header)
+    sec3 = 80 + 64 * ((1 << 18) - 1)  # section 2 holds 2^18 - 1 G1 records
+    with open("/root/reference/srs/srs00", "rb") as f:
+        f.seek(sec3)
+        hdr = f.read(12)
+        assert int.from_bytes(hdr[:4], "little") == 3
+        g2 = f.read(256)
+    with open(os.path.join(HERE, "srs_g2.bin"), "wb") as f:
+        f.write(g2)
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1)
     print("wrote srs_head.bin (%d bytes) and kat.json" % (80 + 64 * N_SRS))
