@@ -115,6 +115,11 @@ int b200_msm_batch_device(b200_ctx* ctx, const b200_bases* bases, size_t base_of
  * {total, sort = count+scan+scatter, bucket accumulation, bucket reduction} in ms. */
 int b200_msm_timing(b200_ctx* ctx, int enable, float out_ms[4]);
 
+/* Running totals of the bucket-accumulation kernel since the last reset while timing is enabled:
+ * out = {milliseconds, (point, scalar) pairs, launches}, every MSM call on this context included
+ * (the prover's batched commitments too). */
+int b200_msm_timing_totals(b200_ctx* ctx, int reset, double out[3]);
+
 /* Sum of k affine points on the host (combining per-GPU partial MSM results after the NCCL
  * gather; ark-ec `Projective += Affine`). */
 int b200_g1_sum_affine(const uint64_t* points_xy, const int* is_identity, size_t k,

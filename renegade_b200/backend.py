@@ -90,6 +90,12 @@ class Context:
         _lib.check(self._lib.b200_msm_timing(self._h, int(enable), C.byref(arr)))
         return {"total": arr[0], "sort": arr[1], "accumulate": arr[2], "reduce": arr[3]}
 
+    def msm_timing_totals(self, reset: bool = False) -> dict:
+        """Bucket-accumulation totals since the last reset (timing must be enabled): ms, pairs, launches."""
+        arr = (C.c_double * 3)()
+        _lib.check(self._lib.b200_msm_timing_totals(self._h, int(reset), C.byref(arr)))
+        return {"accumulate_ms": arr[0], "pairs": arr[1], "launches": arr[2]}
+
     def ntt_last_ms(self) -> float:
         v = C.c_float(0)
         _lib.check(self._lib.b200_ntt_last_ms(self._h, C.byref(v)))

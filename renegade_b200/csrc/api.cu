@@ -374,6 +374,20 @@ int b200_msm_batch_device(b200_ctx* ctx, const b200_bases* bases, size_t base_of
     B200_CATCH
 }
 
+int b200_msm_timing_totals(b200_ctx* ctx, int reset, double out[3]) {
+    B200_TRY
+    if (!ctx) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    if (out) {
+        out[0] = ctx->c.msm.tot_acc_ms;
+        out[1] = ctx->c.msm.tot_pairs;
+        out[2] = ctx->c.msm.tot_launches;
+    }
+    if (reset) ctx->c.msm.tot_acc_ms = ctx->c.msm.tot_pairs = ctx->c.msm.tot_launches = 0;
+    return B200_OK;
+    B200_CATCH
+}
+
 int b200_msm_timing(b200_ctx* ctx, int enable, float out_ms[4]) {
     B200_TRY
     if (!ctx) return B200_ERR_INVALID;

@@ -87,6 +87,8 @@ struct MsmScratch {
     bool ev_init = false;
     cudaEvent_t ev[5] = {};
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
+    // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
+    double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
     ~MsmScratch() {
         if (ev_init)
             for (auto& e : ev) cudaEventDestroy(e);

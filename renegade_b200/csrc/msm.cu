@@ -713,6 +713,9 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         cudaEventElapsedTime(&s->ms[1], s->ev[0], s->ev[1]);
         cudaEventElapsedTime(&s->ms[2], s->ev[1], s->ev[2]);
         cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
+        s->tot_acc_ms += s->ms[2];
+        s->tot_pairs += (double)n * batch;
+        s->tot_launches += 1;
     }
 
     // host epilogue: per MSM a Horner over the physical windows (none when fully precomputed), then
