@@ -345,51 +345,115 @@ __global__ void __launch_bounds__(kReduceThreads) msm_heavy_combine_kernel(const
 }
 
 // ---- bucket reduction: sum_k (k+1) * B[k] per physical window -----------------------------------
-// thread t owns buckets [t*K, (t+1)*K): running sum gives A = sum (i+1) B[tK+i] and S = sum B;
-// its contribution is A + (tK) * S.  Contributions are tree-added in shared memory per block.
+// These kernels are latency-bound (one warp per SM sub-partition walking a chain of dependent XYZZ
+// operations), so the formulation minimises the LENGTH of that chain, not the operation count:
+//   thread t = bx*T + tid owns buckets [tK, (t+1)K): running sums give S_t = sum B and
+//   A_t = sum (i+1) B[tK+i]; the window total is sum_t A_t + K * sum_t t * S_t.
+//   sum_t t*S_t = T * sum_bx bx * (sum_tid S) + sum_bx sum_tid tid * S, and a weighted sum
+//   sum_i i*X_i equals the sum of the inclusive suffix sums R_1 + R_2 + ... — a log-depth block scan
+//   instead of a per-thread double-and-add by the chunk index (2(c-1) dependent operations).
+// Chain per window: 2K (chunk) + log T (scan) + log K + 1 + log T (tree), then the same scan + tree
+// once more over the per-block totals in msm_reduce_final_kernel.
+constexpr int ilog2_c(unsigned v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+constexpr int kReduceChunkLog = ilog2_c(kReduceChunk);
+constexpr int kReduceThreadsLog = ilog2_c(kReduceThreads);
+static_assert((1 << kReduceChunkLog) == kReduceChunk && (1 << kReduceThreadsLog) == kReduceThreads,
+              "reduction chunk and block size are powers of two");
+
+// v_tid <- sum_{j >= tid} v_j over the block (Hillis–Steele); entries at index >= valid are the identity
+__device__ __forceinline__ g1_xyzz block_suffix_scan(g1_xyzz v, g1_xyzz* sh, uint32_t valid) {
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < (uint32_t)kReduceThreads && d < valid; d <<= 1) {
+        const bool has = threadIdx.x + d < (uint32_t)kReduceThreads;
+        g1_xyzz o = g1_xyzz_inf();
+        if (has) o = sh[threadIdx.x + d];
+        __syncthreads();
+        v = xyzz_add(v, o);
+        sh[threadIdx.x] = v;
+        __syncthreads();
+    }
+    return v;
+}
+
+// partials[(window * gridDim.x + bx) * 2 + {0, 1}] = { V_bx, (K*T) * sum_tid S }  with
+// V_bx = sum_tid (A_tid + K * R_tid [tid >= 1])
 __global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyzz* __restrict__ buckets,
                                                                     uint32_t buckets_per_window,
-                                                                    int c,
                                                                     g1_xyzz* __restrict__ partials) {
     __shared__ g1_xyzz sh[kReduceThreads];
     const uint32_t window = blockIdx.y;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t first = t * kReduceChunk;
-    g1_xyzz contrib = g1_xyzz_inf();
+    const uint32_t threads_needed = (buckets_per_window + kReduceChunk - 1) / kReduceChunk;
+    const uint32_t valid = min((uint32_t)kReduceThreads, threads_needed - blockIdx.x * blockDim.x);
+    g1_xyzz run = g1_xyzz_inf(), acc = g1_xyzz_inf();
     if (first < buckets_per_window) {
         const g1_xyzz* B = buckets + (size_t)window * buckets_per_window + first;
         const uint32_t cnt = min((uint32_t)kReduceChunk, buckets_per_window - first);
-        g1_xyzz run = g1_xyzz_inf(), acc = g1_xyzz_inf();
         for (int i = (int)cnt - 1; i >= 0; --i) {
             run = xyzz_add(run, g1_xyzz_load(B + i));
             acc = xyzz_add(acc, run);
         }
-        // (first) * run by double-and-add; first < 2^(c-1)
-        g1_xyzz scaled = g1_xyzz_inf();
-        for (int bit = c - 2; bit >= 0; --bit) {
-            scaled = xyzz_dbl(scaled);
-            if ((first >> bit) & 1u) scaled = xyzz_add(scaled, run);
-        }
-        contrib = xyzz_add(acc, scaled);
     }
-    sh[threadIdx.x] = contrib;
+    const g1_xyzz R = block_suffix_scan(run, sh, valid);
+    g1_xyzz V = acc;
+    if (threadIdx.x >= 1 && threadIdx.x < valid) {
+        g1_xyzz kr = R;
+#pragma unroll 1
+        for (int i = 0; i < kReduceChunkLog; ++i) kr = xyzz_dbl(kr);
+        V = xyzz_add(V, kr);
+    }
+    // the block total, scaled by K*T, is produced by the last thread (its warp has no part in the tree
+    // below) while the first warps fold V: its doublings are spread over the tree levels
+    g1_xyzz Tp = g1_xyzz_inf();
+    if (threadIdx.x == kReduceThreads - 1) Tp = sh[0];
     __syncthreads();
-    for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
+    sh[threadIdx.x] = V;
+    __syncthreads();
+    int dleft = kReduceChunkLog + kReduceThreadsLog, levels_left = kReduceThreadsLog;
+    for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1, --levels_left) {
         if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+        if (threadIdx.x == kReduceThreads - 1) {
+            const int per = (dleft + levels_left - 1) / levels_left;
+            for (int i = 0; i < per; ++i) Tp = xyzz_dbl(Tp);
+            dleft -= per;
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) g1_xyzz_store(partials + (size_t)window * gridDim.x + blockIdx.x, sh[0]);
+    g1_xyzz* out = partials + ((size_t)window * gridDim.x + blockIdx.x) * 2;
+    if (threadIdx.x == 0) g1_xyzz_store(out, sh[0]);
+    if (threadIdx.x == kReduceThreads - 1) g1_xyzz_store(out + 1, Tp);
 }
 
+// window sum = sum_b V_b + sum_b b * T'_b.  Thread tid owns blocks tid, tid + T, ...: with
+// p = sum_m X_m and q = sum_m m * X_m (running sums), sum_b b * X_b = sum_{tid >= 1} R_tid + T * sum_tid q_tid.
 __global__ void __launch_bounds__(kReduceThreads) msm_reduce_final_kernel(const g1_xyzz* __restrict__ partials,
-                                                                          uint32_t n_partials,
+                                                                          uint32_t n_blocks,
                                                                           g1_xyzz* __restrict__ window_sums) {
     __shared__ g1_xyzz sh[kReduceThreads];
     const uint32_t window = blockIdx.x;
-    g1_xyzz acc = g1_xyzz_inf();
-    for (uint32_t i = threadIdx.x; i < n_partials; i += blockDim.x)
-        acc = xyzz_add(acc, g1_xyzz_load(partials + (size_t)window * n_partials + i));
-    sh[threadIdx.x] = acc;
+    const g1_xyzz* P = partials + (size_t)window * n_blocks * 2;
+    const int rounds = (int)((n_blocks + kReduceThreads - 1) / kReduceThreads);
+    g1_xyzz vsum = g1_xyzz_inf(), p = g1_xyzz_inf(), q = g1_xyzz_inf();
+    for (int m = rounds - 1; m >= 0; --m) {
+        const uint32_t j = threadIdx.x + (uint32_t)m * kReduceThreads;
+        if (j < n_blocks) {
+            vsum = xyzz_add(vsum, g1_xyzz_load(P + 2 * (size_t)j));
+            p = xyzz_add(p, g1_xyzz_load(P + 2 * (size_t)j + 1));
+        }
+        if (m > 0) q = xyzz_add(q, p);
+    }
+    const uint32_t valid = min((uint32_t)kReduceThreads, n_blocks);
+    const g1_xyzz R = block_suffix_scan(p, sh, valid);
+    g1_xyzz W = vsum;
+    if (threadIdx.x >= 1 && threadIdx.x < valid) W = xyzz_add(W, R);
+    if (rounds > 1) {
+#pragma unroll 1
+        for (int i = 0; i < kReduceThreadsLog; ++i) q = xyzz_dbl(q);
+        W = xyzz_add(W, q);
+    }
+    sh[threadIdx.x] = W;
     __syncthreads();
     for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
         if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
@@ -652,7 +716,7 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->seg_order.reserve((max_segs + kSegLen + 2) * 4)) != B200_OK) return rc;
     const uint32_t reduce_threads_needed = (half + kReduceChunk - 1) / kReduceChunk;
     const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
-    if ((rc = s->partials.reserve(n_windows * reduce_blocks * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->partials.reserve(n_windows * reduce_blocks * 2 * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
 
     uint32_t* counts = (uint32_t*)s->counts.p;
@@ -699,7 +763,7 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(
         seg_sums, seg_offsets, heavy_count, heavy_list, buckets);
     if (s->timing) cudaEventRecord(s->ev[2], st);
-    msm_reduce_kernel<<<dim3(reduce_blocks, (unsigned)n_windows), kReduceThreads, 0, st>>>(buckets, half, pl.c, partials);
+    msm_reduce_kernel<<<dim3(reduce_blocks, (unsigned)n_windows), kReduceThreads, 0, st>>>(buckets, half, partials);
     msm_reduce_final_kernel<<<(unsigned)n_windows, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);
     B200_CUDA(cudaGetLastError());
 
