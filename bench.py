@@ -178,7 +178,7 @@ def main():
     import torch.distributed as dist
     import renegade_b200 as rb
     from renegade_b200 import synth
-    from renegade_b200.backend import PlonkKzgSnark, plonk_last_timings, prove_raw
+    from renegade_b200.backend import PlonkKzgSnark, ProverPool, plonk_last_timings, prove_raw
     from renegade_b200.sharded import all_gather_partials, combine_partials, pack_partial
 
     torch.cuda.set_device(local_rank)
@@ -204,7 +204,10 @@ def main():
     t_setup = time.perf_counter()
     n = 1 << LOG_N
     conc = max(1, args.concurrency)
-    ctxs = [rb.Context(local_rank) for _ in range(conc)]
+    # conc > 1: the library's own prover pool (b200_pool: FIFO queue + `conc` worker threads, one context
+    # each, keys shared) — the same C-ABI object a relayer's proof manager would hold
+    pool = ProverPool(local_rank, workers=conc) if conc > 1 else None
+    ctxs = [pool.context(i) for i in range(conc)] if pool else [rb.Context(local_rank)]
     ctx = ctxs[0]
     circ = synth.synth_circuit(LOG_N, num_inputs=NUM_INPUTS, seed=CIRCUIT_SEED + rank)
     d_srs = torch.empty((n + 3, 8), dtype=torch.int64, device=dev)
@@ -221,29 +224,18 @@ def main():
     setup_s = time.perf_counter() - t_setup
 
     def run_proofs(count, wires_ptr, first_blinder, collect=None):
-        """`count` proofs, `conc` in flight (one context/stream each)."""
+        """`count` proofs, `conc` in flight (pool workers, one context/stream each)."""
         if conc == 1:
             for i in range(count):
                 proof = prove_raw(ctx, pk, wires_ptr, circ.pub_inputs, blinders[first_blinder + i])
                 if collect is not None:
                     collect.append(plonk_last_timings(ctx))
             return proof
-        nxt, lock, last = [0], threading.Lock(), [None]
-
-        def worker(c):
-            while True:
-                with lock:
-                    i = nxt[0]
-                    nxt[0] += 1
-                if i >= count:
-                    return
-                last[0] = prove_raw(c, pk, wires_ptr, circ.pub_inputs, blinders[first_blinder + i])
-        ths = [threading.Thread(target=worker, args=(c,)) for c in ctxs]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
-        return last[0]
+        tickets = [pool.submit_prove(pk, wires_ptr, circ.pub_inputs, blinders[first_blinder + i]) for i in range(count)]
+        proof = None
+        for tk in tickets:
+            proof = pool.wait(tk)
+        return proof
 
     # ---- proofs, witness resident in HBM ---------------------------------------------------------------
     run_proofs(args.warmup * conc, d_wires.data_ptr(), 0)

@@ -79,6 +79,23 @@ int main(int argc, char** argv) {
         return 4;
     }
 
+    /* the same proof through the prover pool (the NativeProofManager-shaped entry point): four jobs on
+     * two workers share the key; every result must equal the single-context proof byte for byte */
+    wires[4 * (4 * n + num_inputs + 1)] ^= 1u; /* restore the good witness */
+    b200_pool* pool = NULL;
+    CHECK(b200_pool_create(0, 2, &pool));
+    b200_proof pooled[4];
+    uint64_t tickets[4];
+    for (int i = 0; i < 4; ++i)
+        CHECK(b200_pool_submit_prove(pool, pk, wires, pub_inputs, num_inputs, blinders, &pooled[i], NULL, &tickets[i]));
+    for (int i = 3; i >= 0; --i) CHECK(b200_pool_wait(pool, tickets[i]));
+    for (int i = 0; i < 4; ++i)
+        if (memcmp(&pooled[i], &proof, sizeof(proof)) != 0) {
+            fprintf(stderr, "pool proof %d differs from the direct proof\n", i);
+            return 5;
+        }
+    b200_pool_destroy(pool);
+
     FILE* o = fopen(argv[2], "wb");
     if (!o) { perror("out"); return 1; }
     fwrite(&proof, sizeof(proof), 1, o);

@@ -24,6 +24,8 @@ EXPORTS = [
     "b200_selftest_field", "b200_field_op",
     "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_free", "b200_plonk_prove", "b200_plonk_link", "b200_plonk_last_timings", "b200_keccak256",
     "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch",
+    "b200_pool_create", "b200_pool_destroy", "b200_pool_workers", "b200_pool_ctx", "b200_pool_submit_prove",
+    "b200_pool_submit_link", "b200_pool_wait", "b200_pool_wait_all", "b200_pool_stats",
 ]
 
 
@@ -83,6 +85,18 @@ def load() -> C.CDLL:
     lib.b200_plonk_last_timings.argtypes = [vp, C.POINTER(C.c_float * 8)]
     lib.b200_poseidon2_hash_batch.argtypes = [vp, vp, sz, sz, vp]
     lib.b200_poseidon2_permute_batch.argtypes = [vp, vp, sz]
+    lib.b200_pool_create.argtypes = [i32, u32, C.POINTER(vp)]
+    lib.b200_pool_destroy.argtypes = [vp]
+    lib.b200_pool_destroy.restype = None
+    lib.b200_pool_workers.argtypes = [vp]
+    lib.b200_pool_workers.restype = u32
+    lib.b200_pool_ctx.argtypes = [vp, u32]
+    lib.b200_pool_ctx.restype = vp
+    lib.b200_pool_submit_prove.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
+    lib.b200_pool_submit_link.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, u32, sz, sz, vp, C.POINTER(u64)]
+    lib.b200_pool_wait.argtypes = [vp, u64]
+    lib.b200_pool_wait_all.argtypes = [vp]
+    lib.b200_pool_stats.argtypes = [vp, C.POINTER(u64 * 4)]
     lib.b200_keccak256.argtypes = [C.c_char_p, sz, vp]
     lib.b200_keccak256.restype = None
     for name in EXPORTS:

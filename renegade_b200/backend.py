@@ -170,7 +170,7 @@ class Bases:
         return {"window_bits": arr[0], "digits": arr[1], "physical_windows": arr[2], "tables": arr[3]}
 
     def free(self):
-        if self._h and self._ctx._h:
+        if self._h:  # a context that is already gone is passed as NULL (the library allows it)
             self._ctx._lib.b200_bases_free(self._ctx._h, self._h)
         self._h = None
 
@@ -307,7 +307,7 @@ class ProvingKey:
         return 1 << self.log_n
 
     def free(self):
-        if self._h and self._ctx._h:
+        if self._h:
             self._ctx._lib.b200_pk_free(self._ctx._h, self._h)
         self._h = None
 
@@ -421,3 +421,97 @@ def poseidon2_permute_batch(ctx: Context, states: np.ndarray) -> np.ndarray:
     s = np.array(states, dtype=np.uint64, copy=True, order="C")
     _lib.check(ctx._lib.b200_poseidon2_permute_batch(ctx._h, _ptr(s), s.shape[0]))
     return s
+
+
+class ProverPool:
+    """b200_pool: the device-side counterpart of the reference's `NativeProofManager` thread pool
+    (crates/workers/proof-manager/src/implementations/native_proof_manager.rs:138-201, `spawn_fifo`
+    per job).  `workers` proofs are in flight on one GPU; keys and SRS tables are shared.
+
+    Buffers passed to `submit_*` are kept alive by the pool object until the ticket is waited for."""
+
+    def __init__(self, device: int = 0, workers: int = 6):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_pool_create(device, workers, C.byref(h)))
+        self._h = h
+        self.device = device
+        self._keep = {}  # ticket -> objects the job reads or writes
+        self._borrowed = []
+
+    @property
+    def workers(self) -> int:
+        return int(self._lib.b200_pool_workers(self._h))
+
+    def context(self, worker: int = 0) -> Context:
+        """Worker `worker`'s context (borrowed: the pool frees it), for set-up calls."""
+        raw = self._lib.b200_pool_ctx(self._h, worker)
+        if not raw:
+            raise IndexError("worker index out of range")
+        ctx = Context.__new__(Context)
+        ctx._lib, ctx._h, ctx.device, ctx._borrowed = self._lib, C.c_void_p(raw), self.device, True
+        ctx.close = lambda: None  # the pool owns it
+        self._borrowed.append(ctx)
+        return ctx
+
+    def submit_prove(self, pk: "ProvingKey", wires_ptr: int, pub_inputs: np.ndarray, blinders: np.ndarray,
+                     with_link_poly: bool = False, keep=None) -> int:
+        """Queue one proof; returns the ticket.  `wires_ptr`: address of the 5 x n wire table (pinned host
+        or device memory), which the caller keeps valid until `wait(ticket)` returns (pass the owning
+        object as `keep` to let the pool hold a reference)."""
+        proof = B200Proof()
+        pi = np.ascontiguousarray(pub_inputs, dtype=np.uint64)
+        bl = np.ascontiguousarray(blinders, dtype=np.uint64)
+        link = np.zeros((pk.domain_size + 2, 4), dtype=np.uint64) if with_link_poly else None
+        ticket = C.c_uint64()
+        _lib.check(self._lib.b200_pool_submit_prove(self._h, pk._h, C.c_void_p(wires_ptr), _ptr(pi) if pi.size else None,
+                                                    pi.size // 4, _ptr(bl), C.byref(proof),
+                                                    _ptr(link) if link is not None else None, C.byref(ticket)))
+        self._keep[ticket.value] = (proof, link, keep, pk)
+        return ticket.value
+
+    def submit_link(self, srs: "Bases", hint_a: "LinkingHint", hint_b: "LinkingHint", layout: "GroupLayout") -> int:
+        a1 = np.ascontiguousarray(hint_a.linking_wire_poly, dtype=np.uint64).reshape(-1, 4)
+        a2 = np.ascontiguousarray(hint_b.linking_wire_poly, dtype=np.uint64).reshape(-1, 4)
+        c1 = np.ascontiguousarray(hint_a.linking_wire_comm, dtype=np.uint64)
+        c2 = np.ascontiguousarray(hint_b.linking_wire_comm, dtype=np.uint64)
+        proof = B200LinkProof()
+        ticket = C.c_uint64()
+        _lib.check(self._lib.b200_pool_submit_link(self._h, srs._h, _ptr(a1), a1.shape[0], _ptr(a2), a2.shape[0],
+                                                   _ptr(c1), _ptr(c2), layout.alignment, layout.offset, layout.size,
+                                                   C.byref(proof), C.byref(ticket)))
+        self._keep[ticket.value] = (proof, None, (a1, a2, c1, c2), srs)
+        return ticket.value
+
+    def wait(self, ticket: int):
+        """Blocks until the job is done; returns its B200Proof (or (B200Proof, link_poly) when the job was
+        submitted with `with_link_poly`, or the B200LinkProof of a link job); raises B200Error with the
+        job's own status and message if it failed."""
+        rc = self._lib.b200_pool_wait(self._h, ticket)
+        proof, link, _, _ = self._keep.pop(ticket, (None, None, None, None))
+        _lib.check(rc)
+        return (proof, link) if link is not None else proof
+
+    def wait_all(self) -> None:
+        rc = self._lib.b200_pool_wait_all(self._h)
+        self._keep.clear()
+        _lib.check(rc)
+
+    def stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        _lib.check(self._lib.b200_pool_stats(self._h, C.byref(out)))
+        return dict(zip(("submitted", "completed", "failed", "queued"), (int(v) for v in out)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200_pool_destroy(self._h)
+            self._h = None
+            self._keep.clear()
+            for ctx in self._borrowed:  # their handles died with the pool
+                ctx._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

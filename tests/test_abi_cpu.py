@@ -138,3 +138,26 @@ def test_bad_arguments_return_error_codes():
     lib.b200_shutdown(None)           # tolerated
     lib.b200_bases_free(None, None)   # tolerated
     lib.b200_pk_free(None, None)
+
+
+def test_pool_boundary_without_a_device():
+    """The prover pool follows the same conventions: error values for NULL handles, NO_DEVICE (never a host
+    fallback) when its contexts cannot be created."""
+    import torch
+    from renegade_b200 import _lib
+    lib = _lib.load()
+    t = C.c_uint64(0)
+    assert lib.b200_pool_create(0, 0, C.byref(C.c_void_p())) == -1       # zero workers
+    assert lib.b200_pool_create(0, 4, None) == -1
+    assert lib.b200_pool_submit_prove(None, None, None, None, 0, None, None, None, C.byref(t)) == -1
+    assert lib.b200_pool_submit_link(None, None, None, 0, None, 0, None, None, 8, 0, 4, None, C.byref(t)) == -1
+    assert lib.b200_pool_wait(None, 1) == -1
+    assert lib.b200_pool_wait_all(None) == -1
+    assert lib.b200_pool_stats(None, None) == -1
+    assert lib.b200_pool_workers(None) == 0
+    assert not lib.b200_pool_ctx(None, 0)
+    lib.b200_pool_destroy(None)  # tolerated
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.b200_pool_create(0, 2, C.byref(h)) == -6 and not h.value
+        assert b"no CPU fallback" in lib.b200_last_error()
