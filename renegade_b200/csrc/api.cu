@@ -30,6 +30,9 @@ Context::~Context() {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (stream2) cudaStreamDestroy(stream2);
+    if (heavy) cudaStreamDestroy(heavy);
+    if (hv_fork) cudaEventDestroy(hv_fork);
+    if (hv_join) cudaEventDestroy(hv_join);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -146,11 +149,29 @@ int b200_init(int device, b200_ctx** out) {
     B200_CUDA(cudaSetDevice(device));
     b200_ctx* ctx = new b200_ctx();
     ctx->c.device = device;
-    e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking);
+    // The context's own stream runs at the highest priority and carries the short, latency-bound kernels
+    // (sorts, scans, bucket reduction, transcript-driven glue); the long throughput-bound kernels (bucket
+    // accumulation, the side-stream coset NTTs) go to a lowest-priority companion stream.  With several
+    // contexts proving on one GPU the block scheduler then slots a proof's short kernels in as soon as
+    // SM resources free up instead of queueing them behind another proof's big grid.
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    const char* pe = std::getenv("B200_STREAM_PRIORITIES");
+    const bool prio = !(pe && pe[0] == '0');
+    e = cudaStreamCreateWithPriority(&ctx->c.stream, cudaStreamNonBlocking, prio ? prio_greatest : 0);
+    if (e == cudaSuccess && prio) {
+        e = cudaStreamCreateWithPriority(&ctx->c.heavy, cudaStreamNonBlocking, prio_least);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->c.hv_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->c.hv_join, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         delete ctx;
         return cuda_fail(e, "cudaStreamCreate");
     }
+    ctx->c.msm.hv_stream = ctx->c.heavy;
+    ctx->c.heavy_plonk = prio && !(pe && pe[0] == '1');  // B200_STREAM_PRIORITIES=1: accumulation only
+    ctx->c.msm.hv_fork = ctx->c.hv_fork;
+    ctx->c.msm.hv_join = ctx->c.hv_join;
     *out = ctx;
     return B200_OK;
     B200_CATCH

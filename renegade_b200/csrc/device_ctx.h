@@ -60,7 +60,7 @@ int domain_create(unsigned log_n, cudaStream_t st, Domain** out);
 void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st);
 fe host_root_of_unity(unsigned log_n);
 int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, unsigned batch,
-               size_t stride, cudaStream_t st);
+               size_t stride, cudaStream_t st, size_t nonzero_len = 0);
 
 // ---- MSM ------------------------------------------------------------------------------------
 struct MsmPlan {
@@ -89,6 +89,9 @@ struct MsmScratch {
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
     // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
     double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
+    // borrowed from the context: low-priority stream for the accumulation kernel (null: same stream)
+    cudaStream_t hv_stream = nullptr;
+    cudaEvent_t hv_fork = nullptr, hv_join = nullptr;
     ~MsmScratch() {
         if (ev_init)
             for (auto& e : ev) cudaEventDestroy(e);
@@ -127,6 +130,10 @@ struct Context {
     DevBuf plonk_ws;  // prover workspace (plonk.cu)
     float plonk_ms[8] = {0};  // wall time of the last proof's phases
     cudaStream_t stream2 = nullptr;  // side stream of the prover (challenge-independent coset NTTs)
+    // lowest-priority companion of `stream` for the long throughput-bound kernels (null: priorities off)
+    cudaStream_t heavy = nullptr;
+    cudaEvent_t hv_fork = nullptr, hv_join = nullptr;
+    bool heavy_plonk = false;  // also route the prover's NTT passes and quotient kernel there
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf ntt_scratch2;
     ~Context();

@@ -756,8 +756,18 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     msm_seglen_starts_kernel<<<1, 32, 0, st>>>(seg_hist);
     msm_seglen_scatter_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist, seg_order);
     if (s->timing) cudaEventRecord(s->ev[1], st);
-    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, st>>>(
+    // the one long kernel of the MSM goes to the low-priority companion stream (see b200_init)
+    cudaStream_t hv = s->hv_stream ? s->hv_stream : st;
+    if (s->hv_stream) {
+        B200_CUDA(cudaEventRecord(s->hv_fork, st));
+        B200_CUDA(cudaStreamWaitEvent(hv, s->hv_fork, 0));
+    }
+    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
         entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
+    if (s->hv_stream) {
+        B200_CUDA(cudaEventRecord(s->hv_join, hv));
+        B200_CUDA(cudaStreamWaitEvent(st, s->hv_join, 0));
+    }
     msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
         seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, heavy_count, heavy_list);
     msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(

@@ -331,6 +331,26 @@ static fe host_from_u64(uint64_t v) {
     return fe_to_mont<Fr>(x);
 }
 
+// Runs the enclosed launches on the context's low-priority stream (b200_init), ordered after what is
+// already queued on `st` and before what `st` gets next: for the long throughput-bound kernels, so that
+// other contexts' short kernels are scheduled ahead of them.
+struct HeavyScope {
+    Context* c;
+    cudaStream_t st, run;
+    HeavyScope(Context* c_, cudaStream_t st_) : c(c_), st(st_), run(c_->heavy_plonk ? c_->heavy : st_) {
+        if (c->heavy_plonk) {
+            cudaEventRecord(c->hv_fork, st);
+            cudaStreamWaitEvent(run, c->hv_fork, 0);
+        }
+    }
+    ~HeavyScope() {
+        if (c->heavy_plonk) {
+            cudaEventRecord(c->hv_join, run);
+            cudaStreamWaitEvent(st, c->hv_join, 0);
+        }
+    }
+};
+
 // exclusive product scan of `data[0..n)` in place; scratch >= n/CH + n/CH^2 + 2*CH + 8 elements
 static void scan_mul_exclusive(fe* data, size_t n, fe* scratch, cudaStream_t st) {
     if (n <= 1) {
@@ -569,7 +589,9 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     if ((rc = c->ntt_scratch.reserve((size_t)7 * m * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch2.reserve((size_t)6 * m * sizeof(fe))) != B200_OK) return rc;
     if (!c->stream2) {
-        B200_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        B200_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, c->heavy ? prio_least : 0));
         B200_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         B200_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     }
@@ -602,7 +624,10 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     B200_CUDA(cudaMemsetAsync(w.wpoly, 0, NW * S * sizeof(fe), st));
     B200_CUDA(cudaMemcpy2DAsync(w.wpoly, S * sizeof(fe), w.wires_ev, n * sizeof(fe), n * sizeof(fe), NW,
                                 cudaMemcpyDeviceToDevice, st));
-    if ((rc = ntt_device(dn, w.wpoly, nscr, 1, 0, NW, S, st)) != B200_OK) return rc;
+    {
+        HeavyScope hv(c, st);
+        if ((rc = ntt_device(dn, w.wpoly, nscr, 1, 0, NW, S, hv.run)) != B200_OK) return rc;
+    }
     for (int i = 0; i < NW; ++i) {
         BlindArgs b;
         b.count = 2;
@@ -630,11 +655,13 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         B200_CUDA(cudaEventRecord(c->ev_fork, st));
         B200_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
         side.pending = true;
-        B200_CUDA(cudaMemsetAsync(w.ext, 0, 6 * m * sizeof(fe), s2));
+        // degree < n + 2 polynomials over the 8n coset: only the first n + 2 inputs of each transform are read
         B200_CUDA(cudaMemcpy2DAsync(w.ext, m * sizeof(fe), w.wpoly, S * sizeof(fe), (n + 2) * sizeof(fe), NW,
                                     cudaMemcpyDeviceToDevice, s2));
+        B200_CUDA(cudaMemsetAsync(w.ext + 5 * m + n, 0, 2 * sizeof(fe), s2));
         B200_CUDA(cudaMemcpyAsync(w.ext + 5 * m, w.pi_poly, n * sizeof(fe), cudaMemcpyDeviceToDevice, s2));
-        if ((rc = ntt_device(dm, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), 0, 1, 6, m, s2)) != B200_OK) return rc;
+        if ((rc = ntt_device(dm, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), 0, 1, 6, m, s2, n + 2)) != B200_OK)
+            return rc;
         B200_CUDA(cudaEventRecord(c->ev_join, s2));
     }
     if ((rc = commit_batch(c, pk, w.wpoly, n + 2, S, NW, proof->wires_poly_comms)) != B200_OK) return rc;
@@ -664,9 +691,11 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 
     // ---- round 3 ------------------------------------------------------------------------------------
     const fe alpha = tr.get_and_append_challenge();
-    B200_CUDA(cudaMemsetAsync(w.ext + 6 * m, 0, m * sizeof(fe), st));
     B200_CUDA(cudaMemcpyAsync(w.ext + 6 * m, w.zpoly, (n + 3) * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    if ((rc = ntt_device(dm, w.ext + 6 * m, nscr, 0, 1, 1, m, st)) != B200_OK) return rc;
+    {
+        HeavyScope hv(c, st);
+        if ((rc = ntt_device(dm, w.ext + 6 * m, nscr, 0, 1, 1, m, hv.run, n + 3)) != B200_OK) return rc;
+    }
     B200_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));  // join: wire / PI coset evaluations are ready
     side.pending = false;
     {
@@ -684,9 +713,10 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         q.alpha = alpha;
         q.alpha2 = fe_sqr<Fr>(alpha);
         for (int i = 0; i < 8; ++i) q.zh_inv[i] = pk->zh_inv[i];
-        k_quotient<<<grid_for(m, 128), 128, 0, st>>>(q);
+        HeavyScope hv(c, st);
+        k_quotient<<<grid_for(m, 128), 128, 0, hv.run>>>(q);
+        if ((rc = ntt_device(dm, w.quot, nscr, 1, 1, 1, m, hv.run)) != B200_OK) return rc;
     }
-    if ((rc = ntt_device(dm, w.quot, nscr, 1, 1, 1, m, st)) != B200_OK) return rc;
     const size_t deg = NW * (n + 1) + 2;
     B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
     k_check_degree<<<grid_for(m - deg, 256), 256, 0, st>>>(w.quot, deg, m, w.flag);
