@@ -14,6 +14,7 @@
 // keys) — so a proof runs 7 size-8n coset NTTs instead of the reference's 25.  Polynomials never
 // leave the device between rounds; the host sees 13 commitments and 10 evaluations and runs the
 // (serial, few-KB) Keccak transcript between rounds.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <vector>
@@ -193,18 +194,65 @@ __global__ void k_horner_apply(fe* __restrict__ S, size_t len, ZPow zp, const fe
     fe_store(S + j, FADD(fe_load(S + j), FMUL(zp.v[e], fe_load_ro(T + t + 1))));
 }
 
-// ---- round 3: quotient over the coset g * H_8n ------------------------------------------------------
+// ---- round 3: quotient over nc cosets s_j * H_n of the 8n-th roots' coset g * H_8n ---------------------
+// The reference evaluates the quotient on all of g * H_8n (8n points, the next power of two above its
+// degree 5n + 7) and interpolates with one size-8n inverse FFT.  g * H_8n is the union of the 8 cosets
+// s_j * H_n, s_j = g * w_8n^j, and t(X) = sum_k X^(kn) t_k(X) (deg t_k < n) restricted to coset j is
+// u_j = sum_k c_j^k t_k with c_j = s_j^n: nc = 6 cosets (6n > 5n + 7 points) determine t.  So every
+// polynomial is evaluated on 6 cosets with size-n transforms (after folding X^n -> c_j), the quotient
+// kernel runs on 6n points, and t comes back from 6 size-n inverse transforms and one 6 x 6
+// inverse-Vandermonde combination per coefficient index — the same coefficients, 25 % fewer points and
+// 16 instead of 19 butterfly levels.  Layout of every table: [coset j][h], point s_j * w_n^h.
+struct CosetConsts {
+    fe cn[8];  // c_j = s_j^n
+};
+// dst[(p * nc + j) * n + i] = (a_p[i] + c_j * a_p[n + i]) * s_j^i : input of the size-n transform that
+// evaluates polynomial p (len <= 2n coefficients, `src_stride` apart) on coset j
+__global__ void k_coset_fold(const fe* __restrict__ src, size_t src_stride, size_t len, size_t n, int nc,
+                             CosetConsts cc, const fe* __restrict__ cscale, fe* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = blockIdx.y;
+    const fe* a = src + (size_t)blockIdx.z * src_stride;
+    fe v = fe_load_ro(a + i);
+    if (n + i < len) v = FADD(v, FMUL(cc.cn[j], fe_load_ro(a + n + i)));
+    v = FMUL(v, fe_load_ro(cscale + (size_t)j * n + i));
+    fe_store(dst + ((size_t)blockIdx.z * nc + j) * n + i, v);
+}
+
+constexpr int kMaxCosets = 8;
+struct CombineArgs {
+    fe minv[kMaxCosets * kMaxCosets];  // inverse of the Vandermonde matrix V[j][k] = c_j^k, row-major [k][j]
+};
+// in place: q[j * n + i] holds (n^-1-scaled) coefficient i of u_j(s_j X); afterwards q[k * n + i] = t_k[i]
+template <int NC>
+__global__ void k_coset_combine(fe* __restrict__ q, size_t n, const fe* __restrict__ cscale_inv, CombineArgs a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe u[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) u[j] = FMUL(fe_load(q + (size_t)j * n + i), fe_load_ro(cscale_inv + (size_t)j * n + i));
+#pragma unroll 1
+    for (int k = 0; k < NC; ++k) {
+        fe acc = FMUL(a.minv[k * NC], u[0]);
+#pragma unroll
+        for (int j = 1; j < NC; ++j) acc = FADD(acc, FMUL(a.minv[k * NC + j], u[j]));
+        fe_store(q + (size_t)k * n + i, acc);
+    }
+}
+
 struct QuotArgs {
     const fe* sel;   // 13 x m resident coset evaluations
     const fe* sig;   // 5 x m
     const fe* ext;   // 7 x m: wires 0..4, public-input polynomial, z
-    const fe* pts;   // m evaluation points g * w_m^i
+    const fe* pts;   // m evaluation points s_j * w_n^h
     const fe* l1_inv;  // 1 / (n (x_i - 1))
     fe* out;
-    size_t m;
+    size_t m;        // nc * n
+    unsigned log_n;
     KArr k;
     fe beta, gamma, alpha, alpha2;
-    fe zh_inv[8];
+    fe zh_inv[8];    // 1 / (c_j - 1)
 };
 // k_quotient chains ~60 field products; fully unrolled it is ~180 KB of code and starves on the
 // instruction cache (ncu: 1.9 "no instruction" stalls per issue; an out-of-line multiplier was
@@ -231,7 +279,8 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     acc = FSUB(acc, FMUL(fe_load_ro(a.sel + 10 * m + i), w[4]));
     // permutation: alpha * ( z prod(w + beta k x + gamma) - z(wx) prod(w + beta sigma + gamma) )
     const fe zx = fe_load_ro(a.ext + 6 * m + i);
-    const fe zxw = fe_load_ro(a.ext + 6 * m + ((i + 8) & (m - 1)));
+    const size_t nmask = ((size_t)1 << a.log_n) - 1;
+    const fe zxw = fe_load_ro(a.ext + 6 * m + ((i & ~nmask) | ((i + 1) & nmask)));  // z(w x): next point of the same coset
     const fe bx = FMUL(a.beta, fe_load_ro(a.pts + i));
     fe p1 = zx, p2 = zxw;
 #pragma unroll 1
@@ -241,7 +290,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
         p2 = FMUL(p2, FADD(t, FMUL(a.beta, fe_load_ro(a.sig + j * m + i))));
     }
     acc = FADD(acc, FMUL(a.alpha, FSUB(p1, p2)));
-    acc = FMUL(acc, a.zh_inv[i & 7]);
+    acc = FMUL(acc, a.zh_inv[i >> a.log_n]);
     // alpha^2 (z - 1) L1(x) / Z_H(x)
     acc = FADD(acc, FMUL(FMUL(a.alpha2, FSUB(zx, fe_one<Fr>())), fe_load_ro(a.l1_inv + i)));
     fe_store(a.out + i, acc);
@@ -306,14 +355,49 @@ struct ProvingKey {
     fe *sel_coeffs = nullptr, *sig_coeffs = nullptr, *sig_evals = nullptr;
     fe *ce_sel = nullptr, *ce_sig = nullptr;
     fe *dom = nullptr, *coset_pts = nullptr, *l1_inv = nullptr;
+    // quotient domain: nc cosets s_j * H_n, m = nc * n points (see "round 3" above)
+    int nc = 0;
+    fe *cscale = nullptr, *cscale_inv = nullptr;  // s_j^i and s_j^-i, [j][i]
+    CosetConsts cc;
+    CombineArgs comb;
     fe zh_inv[8];
     fe group_gen;
     g1_affine sel_comms[NS], sig_comms[NW];
     ~ProvingKey() {
-        for (fe* p : {sel_coeffs, sig_coeffs, sig_evals, ce_sel, ce_sig, dom, coset_pts, l1_inv})
+        for (fe* p : {sel_coeffs, sig_coeffs, sig_evals, ce_sel, ce_sig, dom, coset_pts, l1_inv, cscale, cscale_inv})
             if (p) cudaFree(p);
     }
 };
+
+// inverse of the nc x nc matrix a (row-major) over Fr by Gauss–Jordan elimination (host, set-up time)
+static bool host_mat_inverse(const fe* a, int nc, fe* out) {
+    const fe one = fe_one<Fr>(), zero = fe_zero();
+    std::vector<fe> m((size_t)nc * 2 * nc);
+    for (int r = 0; r < nc; ++r)
+        for (int c = 0; c < nc; ++c) {
+            m[(size_t)r * 2 * nc + c] = a[r * nc + c];
+            m[(size_t)r * 2 * nc + nc + c] = r == c ? one : zero;
+        }
+    for (int col = 0; col < nc; ++col) {
+        int piv = -1;
+        for (int r = col; r < nc && piv < 0; ++r)
+            if (!fe_is_zero(m[(size_t)r * 2 * nc + col])) piv = r;
+        if (piv < 0) return false;
+        for (int c = 0; c < 2 * nc; ++c) std::swap(m[(size_t)col * 2 * nc + c], m[(size_t)piv * 2 * nc + c]);
+        const fe iv = fe_inv<Fr>(m[(size_t)col * 2 * nc + col]);
+        for (int c = 0; c < 2 * nc; ++c) m[(size_t)col * 2 * nc + c] = FMUL(m[(size_t)col * 2 * nc + c], iv);
+        for (int r = 0; r < nc; ++r) {
+            if (r == col) continue;
+            const fe f = m[(size_t)r * 2 * nc + col];
+            if (fe_is_zero(f)) continue;
+            for (int c = 0; c < 2 * nc; ++c)
+                m[(size_t)r * 2 * nc + c] = FSUB(m[(size_t)r * 2 * nc + c], FMUL(f, m[(size_t)col * 2 * nc + c]));
+        }
+    }
+    for (int r = 0; r < nc; ++r)
+        for (int c = 0; c < nc; ++c) out[r * nc + c] = m[(size_t)r * 2 * nc + nc + c];
+    return true;
+}
 
 static fe host_pow(fe a, uint64_t e) {
     fe r = fe_one<Fr>();
@@ -433,7 +517,7 @@ struct Workspace {
 };
 static size_t workspace_elems(size_t n) {
     const size_t S = n + 4, m = 8 * n;
-    return NW * n + NW * S + n + S + 3 * n + (n / CH + 4 * CH + 64) + 7 * m + m + NW * S + S + 2 * (S + 8) +
+    return NW * n + NW * S + S + S + 3 * n + (n / CH + 4 * CH + 64) + 7 * m + m + NW * S + S + 2 * (S + 8) +
            4 * (S / CH + 4 * CH + 64) + kMaxEval * (S / CH + S / CH / CH + 2 * CH + 16) + 32 + 8;
 }
 static Workspace carve(fe* base, size_t n) {
@@ -443,7 +527,7 @@ static Workspace carve(fe* base, size_t n) {
     fe* p = base;
     w.wires_ev = p; p += NW * n;
     w.wpoly = p; p += NW * S;
-    w.pi_poly = p; p += n;
+    w.pi_poly = p; p += S;  // directly behind the wire polynomials: one batch of 6 for the coset evaluations
     w.zpoly = p; p += S;
     w.num = p; p += n;
     w.den = p; p += n;
@@ -487,9 +571,27 @@ static int alloc_fe(fe** p, size_t count) {
     return B200_OK;
 }
 
+// Evaluations of `count` polynomials (`len` <= 2n coefficients each, `src_stride` apart) on the nc cosets
+// of the quotient domain: dst[(p * nc + j) * n + h] = poly_p(s_j * w_n^h).  scratch: count * nc * n elements.
+static int coset_evals(const ProvingKey* pk, const Domain* dn, const fe* src, size_t src_stride, size_t len,
+                       unsigned count, fe* dst, fe* scratch, cudaStream_t st) {
+    const size_t n = pk->n;
+    if (len > 2 * n) {
+        set_error("coset_evals: polynomial longer than 2n");
+        return B200_ERR_INVALID;
+    }
+    k_coset_fold<<<dim3(grid_for(n, 256), (unsigned)pk->nc, count), 256, 0, st>>>(src, src_stride, len, n, pk->nc, pk->cc,
+                                                                                 pk->cscale, dst);
+    return ntt_device(dn, dst, scratch, /*inverse=*/0, /*coset=*/0, count * (unsigned)pk->nc, n, st);
+}
+
 static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_inputs, const fe* h_selectors,
                       const uint64_t* h_perm, const fe* h_k, ProvingKey** out) {
-    const size_t n = (size_t)1 << log_n, m = 8 * n;
+    const size_t n = (size_t)1 << log_n;
+    // 6 cosets (6n > 5n + 7 points) from n = 16 on; all 8 for the tiny domains, where 6n would not exceed
+    // the quotient's degree by enough to keep the degree check meaningful
+    const int nc = log_n >= 4 ? 6 : 8;
+    const size_t m = (size_t)nc * n;
     if (log_n < 2 || log_n + 3 > 28) {
         set_error("preprocess: log_n out of range");
         return B200_ERR_INVALID;
@@ -504,12 +606,13 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
     pk->log_n = log_n;
     pk->n = n;
     pk->m = m;
+    pk->nc = nc;
     pk->num_inputs = num_inputs;
     pk->srs = srs;
     for (int i = 0; i < NW; ++i) pk->k.v[i] = h_k[i];
     int rc;
-    Domain *dn = nullptr, *dm = nullptr;
-    if ((rc = get_domain(c, log_n, &dn)) != B200_OK || (rc = get_domain(c, log_n + 3, &dm)) != B200_OK) {
+    Domain* dn = nullptr;
+    if ((rc = get_domain(c, log_n, &dn)) != B200_OK) {
         delete pk;
         return rc;
     }
@@ -523,7 +626,7 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
     if ((rc = alloc_fe(&pk->sel_coeffs, NS * n)) || (rc = alloc_fe(&pk->sig_coeffs, NW * n)) ||
         (rc = alloc_fe(&pk->sig_evals, NW * n)) || (rc = alloc_fe(&pk->ce_sel, NS * m)) ||
         (rc = alloc_fe(&pk->ce_sig, NW * m)) || (rc = alloc_fe(&pk->dom, n)) || (rc = alloc_fe(&pk->coset_pts, m)) ||
-        (rc = alloc_fe(&pk->l1_inv, m)))
+        (rc = alloc_fe(&pk->l1_inv, m)) || (rc = alloc_fe(&pk->cscale, m)) || (rc = alloc_fe(&pk->cscale_inv, m)))
         return fail(rc);
     if (cudaMalloc(&d_perm, NW * n * 8) != cudaSuccess) return fail(B200_ERR_CUDA);
     if ((rc = c->ntt_scratch.reserve((size_t)NS * m * sizeof(fe))) != B200_OK) return fail(rc);
@@ -532,10 +635,31 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
     const fe one = fe_one<Fr>();
     const fe g = fe_from_u32<Fr>(5);
     fill_powers(pk->dom, n, dn->group_gen, one, st);
-    fill_powers(pk->coset_pts, m, dm->group_gen, g, st);
-    for (int i = 0; i < 8; ++i) {
-        const fe x = FMUL(g, host_pow(dm->group_gen, (uint64_t)i));
-        pk->zh_inv[i] = fe_inv<Fr>(FSUB(host_pow(x, n), one));
+    {
+        const fe w8n = host_root_of_unity(log_n + 3);
+        fe vand[kMaxCosets * kMaxCosets];
+        for (int j = 0; j < nc; ++j) {
+            const fe sj = FMUL(g, host_pow(w8n, (uint64_t)j));  // s_j = g * w_8n^j
+            const fe cj = host_pow(sj, n);                       // x^n on the whole coset
+            pk->cc.cn[j] = cj;
+            pk->zh_inv[j] = fe_inv<Fr>(FSUB(cj, one));
+            fe pw = one;
+            for (int k = 0; k < nc; ++k) {
+                vand[j * nc + k] = pw;
+                pw = FMUL(pw, cj);
+            }
+            fill_powers(pk->coset_pts + (size_t)j * n, n, dn->group_gen, sj, st);  // s_j * w_n^h
+            fill_powers(pk->cscale + (size_t)j * n, n, sj, one, st);               // s_j^i
+            fill_powers(pk->cscale_inv + (size_t)j * n, n, fe_inv<Fr>(sj), one, st);
+        }
+        for (int j = nc; j < 8; ++j) {
+            pk->cc.cn[j] = fe_zero();
+            pk->zh_inv[j] = fe_zero();
+        }
+        if (!host_mat_inverse(vand, nc, pk->comb.minv)) {
+            set_error("preprocess: singular coset Vandermonde matrix");
+            return fail(B200_ERR_INVALID);
+        }
     }
     k_l1_denominators<<<grid_for(m, 256), 256, 0, st>>>(pk->coset_pts, m, host_from_u64(n), pk->l1_inv);
     k_batch_inverse<<<grid_for((m + 15) / 16, 128), 128, 0, st>>>(pk->l1_inv, pk->ce_sel /*scratch, overwritten below*/, m);
@@ -548,15 +672,9 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
     k_sigma_evals<<<grid_for(NW * n, 256), 256, 0, st>>>(d_perm, pk->dom, n, pk->k, pk->sig_evals);
     cudaMemcpyAsync(pk->sig_coeffs, pk->sig_evals, NW * n * sizeof(fe), cudaMemcpyDeviceToDevice, st);
     if ((rc = ntt_device(dn, pk->sig_coeffs, scratch, 1, 0, NW, n, st)) != B200_OK) return fail(rc);
-    // resident coset evaluations over the 8n domain
-    cudaMemsetAsync(pk->ce_sel, 0, NS * m * sizeof(fe), st);
-    cudaMemsetAsync(pk->ce_sig, 0, NW * m * sizeof(fe), st);
-    cudaMemcpy2DAsync(pk->ce_sel, m * sizeof(fe), pk->sel_coeffs, n * sizeof(fe), n * sizeof(fe), NS,
-                      cudaMemcpyDeviceToDevice, st);
-    cudaMemcpy2DAsync(pk->ce_sig, m * sizeof(fe), pk->sig_coeffs, n * sizeof(fe), n * sizeof(fe), NW,
-                      cudaMemcpyDeviceToDevice, st);
-    if ((rc = ntt_device(dm, pk->ce_sel, scratch, 0, 1, NS, m, st)) != B200_OK) return fail(rc);
-    if ((rc = ntt_device(dm, pk->ce_sig, scratch, 0, 1, NW, m, st)) != B200_OK) return fail(rc);
+    // resident evaluations of the 18 fixed polynomials on the quotient domain
+    if ((rc = coset_evals(pk, dn, pk->sel_coeffs, n, n, NS, pk->ce_sel, scratch, st)) != B200_OK) return fail(rc);
+    if ((rc = coset_evals(pk, dn, pk->sig_coeffs, n, n, NW, pk->ce_sig, scratch, st)) != B200_OK) return fail(rc);
     if (cudaStreamSynchronize(st) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "preprocess"));
     cudaFree(d_perm);
     d_perm = nullptr;
@@ -598,8 +716,8 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     Workspace w = carve(reinterpret_cast<fe*>(c->plonk_ws.p), n);
     fe* nscr = reinterpret_cast<fe*>(c->ntt_scratch.p);
     const size_t S = w.S;
-    Domain *dn = nullptr, *dm = nullptr;
-    if ((rc = get_domain(c, log_n, &dn)) != B200_OK || (rc = get_domain(c, log_n + 3, &dm)) != B200_OK) return rc;
+    Domain* dn = nullptr;
+    if ((rc = get_domain(c, log_n, &dn)) != B200_OK) return rc;
     const fe one = fe_one<Fr>();
 
     using clk = std::chrono::steady_clock;
@@ -636,7 +754,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         b.b[2] = fe_zero();
         k_blind<<<1, 32, 0, st>>>(w.wpoly + (size_t)i * S, n, b);
     }
-    B200_CUDA(cudaMemsetAsync(w.pi_poly, 0, n * sizeof(fe), st));
+    B200_CUDA(cudaMemsetAsync(w.pi_poly, 0, S * sizeof(fe), st));
     if (pk->num_inputs)
         B200_CUDA(cudaMemcpyAsync(w.pi_poly, h_pub_inputs, pk->num_inputs * sizeof(fe), cudaMemcpyHostToDevice, st));
     if ((rc = ntt_device(dn, w.pi_poly, nscr, 1, 0, 1, n, st)) != B200_OK) return rc;
@@ -655,12 +773,9 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         B200_CUDA(cudaEventRecord(c->ev_fork, st));
         B200_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
         side.pending = true;
-        // degree < n + 2 polynomials over the 8n coset: only the first n + 2 inputs of each transform are read
-        B200_CUDA(cudaMemcpy2DAsync(w.ext, m * sizeof(fe), w.wpoly, S * sizeof(fe), (n + 2) * sizeof(fe), NW,
-                                    cudaMemcpyDeviceToDevice, s2));
-        B200_CUDA(cudaMemsetAsync(w.ext + 5 * m + n, 0, 2 * sizeof(fe), s2));
-        B200_CUDA(cudaMemcpyAsync(w.ext + 5 * m, w.pi_poly, n * sizeof(fe), cudaMemcpyDeviceToDevice, s2));
-        if ((rc = ntt_device(dm, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), 0, 1, 6, m, s2, n + 2)) != B200_OK)
+        // 5 wire polynomials (n + 2 coefficients) and the public-input polynomial (n, zero tail) in one batch
+        if ((rc = coset_evals(pk, dn, w.wpoly, S, n + 2, NW + 1, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), s2)) !=
+            B200_OK)
             return rc;
         B200_CUDA(cudaEventRecord(c->ev_join, s2));
     }
@@ -691,10 +806,9 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 
     // ---- round 3 ------------------------------------------------------------------------------------
     const fe alpha = tr.get_and_append_challenge();
-    B200_CUDA(cudaMemcpyAsync(w.ext + 6 * m, w.zpoly, (n + 3) * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     {
         HeavyScope hv(c, st);
-        if ((rc = ntt_device(dm, w.ext + 6 * m, nscr, 0, 1, 1, m, hv.run, n + 3)) != B200_OK) return rc;
+        if ((rc = coset_evals(pk, dn, w.zpoly, S, n + 3, 1, w.ext + 6 * m, nscr, hv.run)) != B200_OK) return rc;
     }
     B200_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));  // join: wire / PI coset evaluations are ready
     side.pending = false;
@@ -707,6 +821,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         q.l1_inv = pk->l1_inv;
         q.out = w.quot;
         q.m = m;
+        q.log_n = log_n;
         q.k = pk->k;
         q.beta = beta;
         q.gamma = gamma;
@@ -715,7 +830,10 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         for (int i = 0; i < 8; ++i) q.zh_inv[i] = pk->zh_inv[i];
         HeavyScope hv(c, st);
         k_quotient<<<grid_for(m, 128), 128, 0, hv.run>>>(q);
-        if ((rc = ntt_device(dm, w.quot, nscr, 1, 1, 1, m, hv.run)) != B200_OK) return rc;
+        // back to coefficients: nc size-n inverse transforms, then un-scale and un-mix the cosets
+        if ((rc = ntt_device(dn, w.quot, nscr, 1, 0, (unsigned)pk->nc, n, hv.run)) != B200_OK) return rc;
+        if (pk->nc == 6) k_coset_combine<6><<<grid_for(n, 128), 128, 0, hv.run>>>(w.quot, n, pk->cscale_inv, pk->comb);
+        else k_coset_combine<8><<<grid_for(n, 128), 128, 0, hv.run>>>(w.quot, n, pk->cscale_inv, pk->comb);
     }
     const size_t deg = NW * (n + 1) + 2;
     B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
