@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200prover.so")
+# B200_LIB_PATH: developer knob to load an alternative build of the same library (tuning experiments)
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200prover.so")
 
 # every symbol include/b200prover.h declares (tests/test_abi.py checks this list against the
 # header and against the built library)

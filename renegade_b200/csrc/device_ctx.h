@@ -79,6 +79,9 @@ struct Bases {
     }
 };
 
+// log2 of the buckets per thread in the bucket reduction: latency-tuned (a lone MSM) / throughput-tuned (prover)
+constexpr int kMsmReduceChunkLogLatency = 2, kMsmReduceChunkLogThroughput = 4;
+
 struct MsmScratch {
     DevBuf counts, offsets, cursor, entries, buckets, block_sums, partials, window_sums, scalars;
     DevBuf seg_offsets, seg_bucket, seg_sums, heavy, seg_order;
@@ -89,6 +92,7 @@ struct MsmScratch {
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
     // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
     double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
+    int reduce_chunk_log = 0;  // 0: latency-tuned default (a lone MSM); the prover sets the throughput value
     // borrowed from the context: low-priority stream for the accumulation kernel (null: same stream)
     cudaStream_t hv_stream = nullptr;
     cudaEvent_t hv_fork = nullptr, hv_join = nullptr;

@@ -32,9 +32,17 @@ namespace {
 
 constexpr uint32_t kIdxBits = 26;  // entry = sign(1) | table(5) | point index(26)
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
-constexpr int kSegLen = 32;        // a bucket is folded in segments of at most this many points
+#ifndef B200_SEG_LEN
+#define B200_SEG_LEN 32
+#endif
+constexpr int kSegLen = B200_SEG_LEN;  // a bucket is folded in segments of at most this many points
 constexpr int kCombineSeq = 64;    // buckets with more segments than this take the block-tree path
-constexpr int kReduceChunk = 4;    // buckets per thread in the running-sum reduction (short serial chains: the kernel is latency-bound)
+// Buckets per thread (2^chunk_log) in the running-sum reduction.  A lone MSM is latency-bound there and wants
+// short serial chains (4 buckets); inside the prover, where several proofs share the GPU, the reduction's
+// OPERATION COUNT is what matters (it competes for issue slots with other proofs' accumulation) and 16
+// buckets per thread is faster overall: 247 -> 265 proofs/s, while the 2^20 MSM alone goes 3.15 -> 3.28 ms
+// (profiles/r1p_reduce_chunk_seglen_variants.log).
+constexpr int kReduceChunkLogLatency = kMsmReduceChunkLogLatency;
 constexpr int kReduceThreads = 128;
 
 // ---- scalar digits ---------------------------------------------------------------------------
@@ -355,10 +363,8 @@ __global__ void __launch_bounds__(kReduceThreads) msm_heavy_combine_kernel(const
 // Chain per window: 2K (chunk) + log T (scan) + log K + 1 + log T (tree), then the same scan + tree
 // once more over the per-block totals in msm_reduce_final_kernel.
 constexpr int ilog2_c(unsigned v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
-constexpr int kReduceChunkLog = ilog2_c(kReduceChunk);
 constexpr int kReduceThreadsLog = ilog2_c(kReduceThreads);
-static_assert((1 << kReduceChunkLog) == kReduceChunk && (1 << kReduceThreadsLog) == kReduceThreads,
-              "reduction chunk and block size are powers of two");
+static_assert((1 << kReduceThreadsLog) == kReduceThreads, "reduction block size is a power of two");
 
 // v_tid <- sum_{j >= tid} v_j over the block (Hillis–Steele); entries at index >= valid are the identity
 __device__ __forceinline__ g1_xyzz block_suffix_scan(g1_xyzz v, g1_xyzz* sh, uint32_t valid) {
@@ -379,18 +385,19 @@ __device__ __forceinline__ g1_xyzz block_suffix_scan(g1_xyzz v, g1_xyzz* sh, uin
 // partials[(window * gridDim.x + bx) * 2 + {0, 1}] = { V_bx, (K*T) * sum_tid S }  with
 // V_bx = sum_tid (A_tid + K * R_tid [tid >= 1])
 __global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyzz* __restrict__ buckets,
-                                                                    uint32_t buckets_per_window,
+                                                                    uint32_t buckets_per_window, int chunk_log,
                                                                     g1_xyzz* __restrict__ partials) {
     __shared__ g1_xyzz sh[kReduceThreads];
     const uint32_t window = blockIdx.y;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t first = t * kReduceChunk;
-    const uint32_t threads_needed = (buckets_per_window + kReduceChunk - 1) / kReduceChunk;
+    const uint32_t chunk = 1u << chunk_log;
+    const uint32_t first = t << chunk_log;
+    const uint32_t threads_needed = (buckets_per_window + chunk - 1) >> chunk_log;
     const uint32_t valid = min((uint32_t)kReduceThreads, threads_needed - blockIdx.x * blockDim.x);
     g1_xyzz run = g1_xyzz_inf(), acc = g1_xyzz_inf();
     if (first < buckets_per_window) {
         const g1_xyzz* B = buckets + (size_t)window * buckets_per_window + first;
-        const uint32_t cnt = min((uint32_t)kReduceChunk, buckets_per_window - first);
+        const uint32_t cnt = min(chunk, buckets_per_window - first);
         for (int i = (int)cnt - 1; i >= 0; --i) {
             run = xyzz_add(run, g1_xyzz_load(B + i));
             acc = xyzz_add(acc, run);
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyz
     if (threadIdx.x >= 1 && threadIdx.x < valid) {
         g1_xyzz kr = R;
 #pragma unroll 1
-        for (int i = 0; i < kReduceChunkLog; ++i) kr = xyzz_dbl(kr);
+        for (int i = 0; i < chunk_log; ++i) kr = xyzz_dbl(kr);
         V = xyzz_add(V, kr);
     }
     // the block total, scaled by K*T, is produced by the last thread (its warp has no part in the tree
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyz
     __syncthreads();
     sh[threadIdx.x] = V;
     __syncthreads();
-    int dleft = kReduceChunkLog + kReduceThreadsLog, levels_left = kReduceThreadsLog;
+    int dleft = chunk_log + kReduceThreadsLog, levels_left = kReduceThreadsLog;
     for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1, --levels_left) {
         if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
         if (threadIdx.x == kReduceThreads - 1) {
@@ -714,7 +721,9 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     if ((rc = s->seg_order.reserve((max_segs + kSegLen + 2) * 4)) != B200_OK) return rc;
-    const uint32_t reduce_threads_needed = (half + kReduceChunk - 1) / kReduceChunk;
+    int chunk_log = s->reduce_chunk_log > 0 ? s->reduce_chunk_log : kReduceChunkLogLatency;
+    while (chunk_log > 0 && (half >> chunk_log) < 32) --chunk_log;  // tiny windows: keep a warp's worth of threads
+    const uint32_t reduce_threads_needed = (half + (1u << chunk_log) - 1) >> chunk_log;
     const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
     if ((rc = s->partials.reserve(n_windows * reduce_blocks * 2 * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
@@ -773,7 +782,7 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(
         seg_sums, seg_offsets, heavy_count, heavy_list, buckets);
     if (s->timing) cudaEventRecord(s->ev[2], st);
-    msm_reduce_kernel<<<dim3(reduce_blocks, (unsigned)n_windows), kReduceThreads, 0, st>>>(buckets, half, partials);
+    msm_reduce_kernel<<<dim3(reduce_blocks, (unsigned)n_windows), kReduceThreads, 0, st>>>(buckets, half, chunk_log, partials);
     msm_reduce_final_kernel<<<(unsigned)n_windows, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);
     B200_CUDA(cudaGetLastError());
 

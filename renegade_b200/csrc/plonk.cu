@@ -545,8 +545,25 @@ static Workspace carve(fe* base, size_t n) {
     return w;
 }
 
+// The prover's commitments use the throughput-tuned bucket reduction (device_ctx.h: 16 buckets per thread):
+// proofs are made several at a time per GPU, where operation count beats chain length.
+struct ProverMsmTuning {
+    MsmScratch* s;
+    int saved;
+    explicit ProverMsmTuning(MsmScratch* s_) : s(s_), saved(s_->reduce_chunk_log) {
+        static const int log = [] {
+            const char* e = std::getenv("B200_PROVER_REDUCE_CHUNK_LOG");  // tuning knob
+            const int v = e ? std::atoi(e) : 0;
+            return v >= 1 && v <= 8 ? v : kMsmReduceChunkLogThroughput;
+        }();
+        s->reduce_chunk_log = log;
+    }
+    ~ProverMsmTuning() { s->reduce_chunk_log = saved; }
+};
+
 static int commit(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, g1_affine* out) {
     int inf = 0;
+    ProverMsmTuning tune(&c->msm);
     int rc = msm_device(pk->srs, 0, d_coeffs, len, /*montgomery=*/1, &c->msm, c->stream, out, &inf);
     if (rc != B200_OK) return rc;
     if (inf) std::memset(out, 0, sizeof(*out));
@@ -558,6 +575,7 @@ static int commit_batch(Context* c, const ProvingKey* pk, const fe* d_coeffs, si
                         unsigned count, g1_affine* out) {
     int inf[32];
     if (count > 32) return B200_ERR_INVALID;
+    ProverMsmTuning tune(&c->msm);
     int rc = msm_device_batch(pk->srs, 0, d_coeffs, len, stride, count, /*montgomery=*/1, &c->msm, c->stream, out, inf);
     if (rc != B200_OK) return rc;
     for (unsigned i = 0; i < count; ++i)
