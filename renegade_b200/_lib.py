@@ -19,7 +19,7 @@ EXPORTS = [
     "b200_init", "b200_shutdown", "b200_last_error", "b200_version",
     "b200_srs_parse_ptau", "b200_bases_load", "b200_bases_load_device", "b200_bases_free",
     "b200_bases_len", "b200_bases_plan",
-    "b200_msm", "b200_msm_device", "b200_msm_batch_device", "b200_msm_timing", "b200_msm_timing_totals", "b200_g1_sum_affine",
+    "b200_msm", "b200_msm_device", "b200_msm_batch_device", "b200_msm_timing", "b200_msm_timing_totals", "b200_msm_tuning", "b200_g1_sum_affine",
     "b200_ntt", "b200_ntt_device", "b200_ntt_last_ms", "b200_domain_generator",
     "b200_splitmix_fr_device", "b200_known_dlog_bases_device",
     "b200_selftest_field", "b200_field_op",
@@ -68,6 +68,7 @@ def load() -> C.CDLL:
     lib.b200_msm_batch_device.argtypes = [vp, vp, sz, vp, sz, sz, u32, i32, vp, vp]
     lib.b200_msm_timing_totals.argtypes = [vp, i32, C.POINTER(C.c_double * 3)]
     lib.b200_msm_timing.argtypes = [vp, i32, C.POINTER(C.c_float * 4)]
+    lib.b200_msm_tuning.argtypes = [vp, i32]
     lib.b200_ntt_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.b200_g1_sum_affine.argtypes = [vp, vp, sz, vp, C.POINTER(i32)]
     lib.b200_ntt.argtypes = [vp, vp, u32, i32, i32]

@@ -90,6 +90,11 @@ class Context:
         _lib.check(self._lib.b200_msm_timing(self._h, int(enable), C.byref(arr)))
         return {"total": arr[0], "sort": arr[1], "accumulate": arr[2], "reduce": arr[3]}
 
+    def msm_tuning(self, throughput_mode: bool) -> None:
+        """False (default): latency-tuned MSM; True: throughput-tuned (batched-affine pairing rounds, longer
+        reduction chains) — same results, for when several MSMs are in flight on the GPU."""
+        _lib.check(self._lib.b200_msm_tuning(self._h, int(throughput_mode)))
+
     def msm_timing_totals(self, reset: bool = False) -> dict:
         """Bucket-accumulation totals since the last reset (timing must be enabled): ms, pairs, launches."""
         arr = (C.c_double * 3)()

@@ -9,6 +9,15 @@ import renegade_b200 as rb
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[False, True], ids=["latency", "throughput"])
+def mode(request, ctx):
+    """Both MSM tunings (b200_msm_tuning): XYZZ-only folding, and the prover's throughput mode with
+    batched-affine pairing rounds and long reduction chains.  Results must be identical."""
+    ctx.msm_tuning(request.param)
+    yield request.param
+    ctx.msm_tuning(False)
+
+
 def H(s):
     return int(s, 16)
 
@@ -26,7 +35,7 @@ def test_known_dlog_golden(ctx, oracle, pyoracle, kat):
 
 @pytest.mark.parametrize("n,c", [(1, 0), (31, 0), (32, 8), (1000, 0), (1000, 9), (4099, 0), (4099, 13),
                                  (1 << 14, 0), ((1 << 16) + 3, 0)])
-def test_msm_matches_oracle(ctx, oracle, n, c):
+def test_msm_matches_oracle(ctx, oracle, n, c, mode):
     pts = oracle.known_dlog_bases(0xB200, n)
     bases = ctx.load_bases(pts, window_bits=c)
     s = oracle.splitmix_fr(0x5CA1A8, n, montgomery=False)
@@ -59,7 +68,7 @@ def test_msm_partial_precompute(ctx, oracle, monkeypatch):
         assert (out == exp).all()
 
 
-def test_msm_on_reference_srs_points(ctx, oracle, pyoracle, kat, srs_head):
+def test_msm_on_reference_srs_points(ctx, oracle, pyoracle, kat, srs_head, mode):
     py = pyoracle
     params_pts = np.frombuffer(srs_head[80:], dtype=np.uint64).reshape(-1, 8)
     bases = ctx.load_bases(params_pts, check_on_curve=True)  # srs.rs:178-179 on the device
@@ -82,7 +91,7 @@ def test_on_curve_check_rejects(ctx, srs_head):
     assert ei.value.code == -5 and "not on curve" in str(ei.value)
 
 
-def test_msm_edge_cases(ctx, oracle, pyoracle):
+def test_msm_edge_cases(ctx, oracle, pyoracle, mode):
     py = pyoracle
     n = 300
     pts = oracle.known_dlog_bases(0xB200, n)
@@ -121,7 +130,7 @@ def test_msm_edge_cases(ctx, oracle, pyoracle):
     assert (out == exp).all()
 
 
-def test_msm_skewed_scalars(ctx, oracle, pyoracle):
+def test_msm_skewed_scalars(ctx, oracle, pyoracle, mode):
     """Digit distributions that pile points into few buckets: identical scalars (one bucket per
     window holds every point -> block-tree combine path), small scalars (only the low windows),
     and a 0/1/small mix like witness values."""
@@ -138,7 +147,7 @@ def test_msm_skewed_scalars(ctx, oracle, pyoracle):
         assert inf == einf and (out == exp).all()
 
 
-def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle):
+def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle, mode):
     """BASELINE.json config 2 at full size.  Bases a_i*G are generated on the device, so
     sum s_i*P_i must equal (sum a_i*s_i mod r)*G — one scalar multiplication checks 2^20
     terms; the same inputs split in two 'ranks' and recombined give the identical point."""
@@ -172,7 +181,7 @@ def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle):
     assert not inf2 and (out2 == exp).all()
 
 
-def test_msm_batch_via_prover_sizes(ctx, oracle):
+def test_msm_batch_via_prover_sizes(ctx, oracle, mode):
     """Batched MSM (several scalar vectors over the same bases in one pass) is exercised through
     the prover; here directly: 5 vectors of 3000 scalars, a stride apart, vs 5 oracle MSMs."""
     import ctypes as C
