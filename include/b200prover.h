@@ -111,11 +111,10 @@ int b200_msm_batch_device(b200_ctx* ctx, const b200_bases* bases, size_t base_of
                           int scalars_montgomery, uint64_t* out_xy, int* out_is_identity);
 
 /* Selects how the MSM entry points of this context trade latency for throughput.  0 (default): one MSM
- * at a time should finish as early as possible (XYZZ bucket folding only, short reduction chains).
- * 1: several MSMs are in flight on the GPU (other contexts) and the operation count matters: bucket lists
- * are first halved twice by batched-affine pairing rounds (one shared inversion per block) and the bucket
- * reduction uses longer per-thread chains.  Results are identical.  The prover always uses mode 1 for its
- * own commitments. */
+ * at a time should finish as early as possible (short dependent chains in the bucket reduction: 4 buckets
+ * per thread).  1: several MSMs are in flight on the GPU (other contexts) and the operation count matters
+ * (16 buckets per thread: fewer scan operations competing with other launches' bucket accumulation).
+ * Results are identical.  The prover always uses mode 1 for its own commitments. */
 int b200_msm_tuning(b200_ctx* ctx, int throughput_mode);
 /* Device-side phase timing (CUDA events recorded on the context's stream).  enable != 0 turns
  * it on for subsequent MSM calls; out_ms (may be NULL) receives the last call's

@@ -91,8 +91,8 @@ class Context:
         return {"total": arr[0], "sort": arr[1], "accumulate": arr[2], "reduce": arr[3]}
 
     def msm_tuning(self, throughput_mode: bool) -> None:
-        """False (default): latency-tuned MSM; True: throughput-tuned (batched-affine pairing rounds, longer
-        reduction chains) — same results, for when several MSMs are in flight on the GPU."""
+        """False (default): latency-tuned MSM; True: throughput-tuned (longer per-thread chains in the bucket
+        reduction, fewer operations) — same results, for when several MSMs are in flight on the GPU."""
         _lib.check(self._lib.b200_msm_tuning(self._h, int(throughput_mode)))
 
     def msm_timing_totals(self, reset: bool = False) -> dict:

@@ -413,9 +413,7 @@ int b200_msm_tuning(b200_ctx* ctx, int throughput_mode) {
     B200_TRY
     if (!ctx) return B200_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->c.mu);
-    ctx->c.msm.affine_rounds = throughput_mode ? kMsmAffineRoundsThroughput : 0;
     ctx->c.msm.reduce_chunk_log = throughput_mode ? kMsmReduceChunkLogThroughput : 0;
-    ctx->c.msm.pair_per_thread = 0;
     return B200_OK;
     B200_CATCH
 }

@@ -60,7 +60,7 @@ int domain_create(unsigned log_n, cudaStream_t st, Domain** out);
 void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st);
 fe host_root_of_unity(unsigned log_n);
 int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, unsigned batch,
-               size_t stride, cudaStream_t st, size_t nonzero_len = 0);
+               size_t stride, cudaStream_t st);
 
 // ---- MSM ------------------------------------------------------------------------------------
 struct MsmPlan {
@@ -81,8 +81,6 @@ struct Bases {
 
 // log2 of the buckets per thread in the bucket reduction: latency-tuned (a lone MSM) / throughput-tuned (prover)
 constexpr int kMsmReduceChunkLogLatency = 2, kMsmReduceChunkLogThroughput = 4;
-// batched-affine pairing rounds before the XYZZ fold in throughput mode (msm.cu)
-constexpr int kMsmAffineRoundsThroughput = 2;
 
 struct MsmScratch {
     DevBuf counts, offsets, cursor, entries, buckets, block_sums, partials, window_sums, scalars;
@@ -94,9 +92,6 @@ struct MsmScratch {
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
     // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
     double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
-    // throughput mode (prover): batched-affine pairing rounds before the XYZZ fold (0: off), slots per thread
-    int affine_rounds = 0, pair_per_thread = 0;
-    DevBuf pair_pts[2], pair_off[2], pair_prefix;
     int reduce_chunk_log = 0;  // 0: latency-tuned default (a lone MSM); the prover sets the throughput value
     // borrowed from the context: low-priority stream for the accumulation kernel (null: same stream)
     cudaStream_t hv_stream = nullptr;

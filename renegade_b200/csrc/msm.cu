@@ -143,10 +143,6 @@ struct ScanCounts {
     const uint32_t* p;
     __device__ __forceinline__ uint32_t operator()(size_t i) const { return p[i]; }
 };
-struct ScanHalfCounts {  // ceil(bucket size / 2): a bucket's size after one pairing round
-    const uint32_t* offsets;
-    __device__ __forceinline__ uint32_t operator()(size_t i) const { return (offsets[i + 1] - offsets[i] + 1u) >> 1; }
-};
 struct ScanSegCounts {  // ceil(bucket size / kSegLen)
     const uint32_t* offsets;
     __device__ __forceinline__ uint32_t operator()(size_t i) const {
@@ -301,188 +297,6 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
             acc = g1_add_mixed(acc, cur);
             if (e >= end) break;
         }
-    }
-    g1_xyzz_store(seg_sums + s, acc);
-}
-
-// ---- batched-affine pairing rounds (throughput mode) -------------------------------------------------
-// One round replaces every bucket's sorted list p0, p1, p2, ... by p0+p1, p2+p3, ... (an odd tail passes
-// through), in AFFINE coordinates: lambda = (y2 - y1) / (x2 - x1) with all the denominators of a block
-// inverted together (Montgomery's trick: per-thread prefix products, a product scan over the block, one
-// Fermat inversion per block).  An addition then costs 5 products + 1 square plus its share of the scans
-// and of the inversion (~6.7 product-equivalents at 64 pairs per thread) instead of the 9.8 of an XYZZ
-// mixed addition.  Two rounds do 3/4 of all bucket additions this way; the rest stays on the XYZZ
-// segment kernel, which then reads the compacted affine points.  The price is latency (a serial
-// inversion per block and round), so a lone MSM keeps the XYZZ-only path.
-// Exceptional pairs (equal x: doubling or P + (-P); the identity, stored as (0, 0) — no curve point has
-// x = 0 since 3 is a non-residue) take a slow per-pair path and put 1 into the shared product.
-constexpr int kPairThreads = 256;
-struct PairArgs {
-    const uint32_t* entries;   // first round: sorted entry codes ...
-    const g1_affine* tables;   // ... into the window tables
-    size_t n_points;
-    const g1_affine* src;      // later rounds: the previous round's points
-    const uint32_t* off_in;    // bucket offsets of the input (n_buckets + 1)
-    const uint32_t* off_out;   // bucket offsets of the output: exclusive scan of ceil(size / 2)
-    uint32_t n_buckets;
-    uint32_t per_thread;       // output slots per thread
-    g1_affine* dst;
-    fe* prefix;                // per_thread * (threads of the grid) elements
-};
-
-template <bool FIRST>
-__device__ __forceinline__ fe pair_load_x(const PairArgs& a, uint32_t e) {
-    if (FIRST) {
-        const uint32_t code = a.entries[e];
-        const size_t idx = code & kIdxMask, table = (code >> kIdxBits) & 31u;
-        return fe_load_ro(&a.tables[table * a.n_points + idx].x);
-    }
-    return fe_load_ro(&a.src[e].x);
-}
-template <bool FIRST>
-__device__ __forceinline__ g1_affine pair_load(const PairArgs& a, uint32_t e) {
-    if (FIRST) {
-        const uint32_t code = a.entries[e];
-        g1_affine p = load_entry_point(a.tables, a.n_points, code);
-        if (code >> 31) p.y = fe_neg<FqCfg>(p.y);
-        return p;
-    }
-    return g1_affine_load_ro(a.src + e);
-}
-
-template <bool FIRST>
-__global__ void __launch_bounds__(kPairThreads) msm_pair_round_kernel(PairArgs a) {
-    __shared__ fe sh_p[kPairThreads];
-    __shared__ fe sh_s[kPairThreads];
-    __shared__ fe sh_inv;
-    const uint32_t total = a.off_out[a.n_buckets];
-    if ((uint64_t)blockIdx.x * kPairThreads * a.per_thread >= total) return;  // whole block past the end
-    const uint32_t gt = blockIdx.x * kPairThreads + threadIdx.x;
-    const size_t nt = (size_t)gridDim.x * kPairThreads;
-    const uint64_t s0_64 = (uint64_t)gt * a.per_thread;
-    const uint32_t s0 = s0_64 < total ? (uint32_t)s0_64 : total;
-    const uint32_t s1 = (uint32_t)min((uint64_t)total, s0_64 + a.per_thread);
-    const fe one = fe_one<FqCfg>();
-
-    // bucket of the first slot: the largest b with off_out[b] <= s0
-    uint32_t bb = 0;
-    {
-        uint32_t lo = 0, hi = a.n_buckets;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (a.off_out[mid] <= s0) lo = mid;
-            else hi = mid - 1;
-        }
-        bb = lo < a.n_buckets ? lo : a.n_buckets - 1;
-    }
-    uint32_t o_lo = a.off_out[bb], o_hi = a.off_out[bb + 1], i_lo = a.off_in[bb], i_hi = a.off_in[bb + 1];
-
-    // ---- forward: prefix products of the denominators ----------------------------------------------
-    fe run = one;
-    for (uint32_t slot = s0; slot < s1; ++slot) {
-        while (slot >= o_hi) {
-            ++bb;
-            o_lo = o_hi;
-            o_hi = a.off_out[bb + 1];
-            i_lo = i_hi;
-            i_hi = a.off_in[bb + 1];
-        }
-        const uint32_t e0 = i_lo + 2u * (slot - o_lo);
-        if (e0 + 1 < i_hi) {
-            const fe x1 = pair_load_x<FIRST>(a, e0), x2 = pair_load_x<FIRST>(a, e0 + 1);
-            const fe d = fe_sub<FqCfg>(x2, x1);
-            fe_store(a.prefix + (size_t)(slot - s0) * nt + gt, run);
-            if (!fe_is_zero(d) && !fe_is_zero(x1) && !fe_is_zero(x2)) run = fe_mul<FqCfg>(run, d);
-        }
-    }
-
-    // ---- block: inverse of every thread's product from ONE inversion ---------------------------------
-    sh_p[threadIdx.x] = run;
-    sh_s[threadIdx.x] = run;
-    __syncthreads();
-    {
-        fe pre = run, suf = run;  // inclusive prefix / suffix products over the block (Hillis–Steele)
-        for (uint32_t d = 1; d < (uint32_t)kPairThreads; d <<= 1) {
-            const bool hp = threadIdx.x >= d, hs = threadIdx.x + d < (uint32_t)kPairThreads;
-            fe pl = one, sr = one;
-            if (hp) pl = sh_p[threadIdx.x - d];
-            if (hs) sr = sh_s[threadIdx.x + d];
-            __syncthreads();
-            if (hp) pre = fe_mul<FqCfg>(pre, pl);
-            if (hs) suf = fe_mul<FqCfg>(suf, sr);
-            sh_p[threadIdx.x] = pre;
-            sh_s[threadIdx.x] = suf;
-            __syncthreads();
-        }
-    }
-    if (threadIdx.x == 0) sh_inv = fe_inv<FqCfg>(sh_s[0]);
-    __syncthreads();
-    fe inv_run = sh_inv;  // -> 1 / (this thread's product) = 1/total * (product of all the other threads')
-    if (threadIdx.x > 0) inv_run = fe_mul<FqCfg>(inv_run, sh_p[threadIdx.x - 1]);
-    if (threadIdx.x + 1 < (uint32_t)kPairThreads) inv_run = fe_mul<FqCfg>(inv_run, sh_s[threadIdx.x + 1]);
-
-    // ---- backward: peel the inverses off, add ----------------------------------------------------------
-    for (uint32_t slot = s1; slot-- > s0;) {
-        while (slot < o_lo) {
-            --bb;
-            o_hi = o_lo;
-            o_lo = a.off_out[bb];
-            i_hi = i_lo;
-            i_lo = a.off_in[bb];
-        }
-        const uint32_t e0 = i_lo + 2u * (slot - o_lo);
-        g1_affine r = pair_load<FIRST>(a, e0);
-        if (e0 + 1 < i_hi) {
-            const g1_affine q = pair_load<FIRST>(a, e0 + 1);
-            const fe d = fe_sub<FqCfg>(q.x, r.x);
-            const bool inf1 = fe_is_zero(r.x), inf2 = fe_is_zero(q.x);
-            if (!fe_is_zero(d) && !inf1 && !inf2) {
-                const fe inv_d = fe_mul<FqCfg>(inv_run, fe_load(a.prefix + (size_t)(slot - s0) * nt + gt));
-                inv_run = fe_mul<FqCfg>(inv_run, d);
-                const fe lam = fe_mul<FqCfg>(fe_sub<FqCfg>(q.y, r.y), inv_d);
-                const fe x3 = fe_sub<FqCfg>(fe_sub<FqCfg>(fe_sqr<FqCfg>(lam), r.x), q.x);
-                r.y = fe_sub<FqCfg>(fe_mul<FqCfg>(lam, fe_sub<FqCfg>(r.x, x3)), r.y);
-                r.x = x3;
-            } else if (inf1) {
-                r = q;
-            } else if (!inf2) {  // same x: doubling, or P + (-P)
-                if (fe_eq(q.y, r.y)) {
-                    const fe xx = fe_sqr<FqCfg>(r.x);
-                    const fe lam = fe_mul<FqCfg>(fe_add<FqCfg>(fe_dbl<FqCfg>(xx), xx), fe_inv<FqCfg>(fe_dbl<FqCfg>(r.y)));
-                    const fe x3 = fe_sub<FqCfg>(fe_sqr<FqCfg>(lam), fe_dbl<FqCfg>(r.x));
-                    r.y = fe_sub<FqCfg>(fe_mul<FqCfg>(lam, fe_sub<FqCfg>(r.x, x3)), r.y);
-                    r.x = x3;
-                } else {
-                    r.x = fe_zero();
-                    r.y = fe_zero();
-                }
-            }
-        }
-        g1_affine_store(a.dst + slot, r);
-    }
-}
-
-// msm_accumulate_kernel over the compacted affine points the pairing rounds leave (no tables, no signs;
-// the identity marker is skipped)
-__global__ void __launch_bounds__(128) msm_accumulate_affine_kernel(const g1_affine* __restrict__ pts,
-                                                                    const uint32_t* __restrict__ offsets,
-                                                                    const uint32_t* __restrict__ seg_offsets,
-                                                                    const uint32_t* __restrict__ seg_bucket,
-                                                                    const uint32_t* __restrict__ order,
-                                                                    uint32_t n_buckets, g1_xyzz* __restrict__ seg_sums) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= seg_offsets[n_buckets]) return;
-    const uint32_t s = order[tid];
-    const uint32_t b = seg_bucket[s];
-    const uint32_t j = s - seg_offsets[b], k = seg_offsets[b + 1] - seg_offsets[b];
-    const uint32_t first = offsets[b], cnt = offsets[b + 1] - first;
-    const uint32_t base = cnt / k, rem = cnt % k;
-    uint32_t e = first + j * base + min(j, rem);
-    const uint32_t end = e + base + (j < rem ? 1u : 0u);
-    g1_xyzz acc = g1_xyzz_inf();
-    for (; e < end; ++e) {
-        const g1_affine p = g1_affine_load_ro(pts + e);
-        if (!fe_is_zero(p.x)) acc = g1_add_mixed(acc, p);
     }
     g1_xyzz_store(seg_sums + s, acc);
 }
@@ -907,21 +721,6 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     if ((rc = s->seg_order.reserve((max_segs + kSegLen + 2) * 4)) != B200_OK) return rc;
-    // pairing rounds (throughput mode only; a round needs >= 2 entries per bucket on average to pay)
-    int rounds = s->affine_rounds;
-    if (rounds > 2) rounds = 2;  // two ping-pong buffers / offset arrays are reserved below
-    if (max_entries < 4 * n_buckets) rounds = 0;
-    const uint32_t pair_per_thread = s->pair_per_thread > 0 ? (uint32_t)s->pair_per_thread : 64u;
-    if (rounds > 0) {
-        const size_t slots0 = (max_entries + 1) / 2 + n_buckets, slots1 = (slots0 + 1) / 2 + n_buckets;
-        if ((rc = s->pair_pts[0].reserve(slots0 * sizeof(g1_affine))) != B200_OK) return rc;
-        if (rounds > 1 && (rc = s->pair_pts[1].reserve(slots1 * sizeof(g1_affine))) != B200_OK) return rc;
-        for (int r = 0; r < rounds; ++r)
-            if ((rc = s->pair_off[r].reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
-        // prefix products: per_thread x (threads of the largest grid)
-        const size_t threads0 = ((slots0 + (size_t)kPairThreads * pair_per_thread - 1) / ((size_t)kPairThreads * pair_per_thread)) * kPairThreads;
-        if ((rc = s->pair_prefix.reserve(threads0 * pair_per_thread * sizeof(fe))) != B200_OK) return rc;
-    }
     int chunk_log = s->reduce_chunk_log > 0 ? s->reduce_chunk_log : kReduceChunkLogLatency;
     while (chunk_log > 0 && (half >> chunk_log) < 32) --chunk_log;  // tiny windows: keep a warp's worth of threads
     const uint32_t reduce_threads_needed = (half + (1u << chunk_log) - 1) >> chunk_log;
@@ -971,55 +770,18 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
             cudaStreamWaitEvent(st, s->hv_join, 0);
         }
     };
-    // throughput mode: batched-affine pairing rounds halve the bucket lists before the XYZZ fold
-    const uint32_t* cur_off = offsets;      // bucket offsets of what the fold reads
-    const g1_affine* cur_pts = nullptr;     // null: the fold reads entry codes + tables
-    if (rounds > 0) {
-        if (s->timing) cudaEventRecord(s->ev[1], st);
-        fork();
-        size_t max_in = max_entries;
-        for (int r = 0; r < rounds; ++r) {
-            const size_t max_slots = (max_in + 1) / 2 + n_buckets;
-            uint32_t* off_out = (uint32_t*)s->pair_off[r].p;
-            g1_affine* dst = (g1_affine*)s->pair_pts[r & 1].p;
-            if ((rc = exclusive_scan_u32(ScanHalfCounts{cur_off}, n_buckets, off_out, &s->block_sums, hv)) != B200_OK) return rc;
-            PairArgs pa;
-            pa.entries = entries;
-            pa.tables = b->tables;
-            pa.n_points = b->n;
-            pa.src = cur_pts;
-            pa.off_in = cur_off;
-            pa.off_out = off_out;
-            pa.n_buckets = (uint32_t)n_buckets;
-            pa.per_thread = pair_per_thread;
-            pa.dst = dst;
-            pa.prefix = (fe*)s->pair_prefix.p;
-            const unsigned grid = (unsigned)((max_slots + (size_t)kPairThreads * pair_per_thread - 1) /
-                                             ((size_t)kPairThreads * pair_per_thread));
-            if (r == 0) msm_pair_round_kernel<true><<<grid, kPairThreads, 0, hv>>>(pa);
-            else msm_pair_round_kernel<false><<<grid, kPairThreads, 0, hv>>>(pa);
-            cur_off = off_out;
-            cur_pts = dst;
-            max_in = max_slots;
-        }
-        join();
-    }
-    if ((rc = exclusive_scan_u32(ScanSegCounts{cur_off}, n_buckets, seg_offsets, &s->block_sums, st)) != B200_OK) return rc;
+    if ((rc = exclusive_scan_u32(ScanSegCounts{offsets}, n_buckets, seg_offsets, &s->block_sums, st)) != B200_OK) return rc;
     msm_segfill_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(seg_offsets, (uint32_t)n_buckets, seg_bucket);
     B200_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
     B200_CUDA(cudaMemsetAsync(seg_hist, 0, (kSegLen + 2) * 4, st));
     const unsigned seg_grid = (unsigned)((max_segs + 255) / 256);
-    msm_seglen_hist_kernel<<<seg_grid, 256, 0, st>>>(cur_off, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist);
+    msm_seglen_hist_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist);
     msm_seglen_starts_kernel<<<1, 32, 0, st>>>(seg_hist);
-    msm_seglen_scatter_kernel<<<seg_grid, 256, 0, st>>>(cur_off, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist, seg_order);
-    if (s->timing && rounds == 0) cudaEventRecord(s->ev[1], st);
+    msm_seglen_scatter_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist, seg_order);
+    if (s->timing) cudaEventRecord(s->ev[1], st);
     fork();
-    if (cur_pts)
-        msm_accumulate_affine_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
-            cur_pts, cur_off, seg_offsets, seg_bucket, seg_order, (uint32_t)n_buckets, seg_sums);
-    else
-        msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
-            entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
+    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
+        entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
     join();
     msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
         seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, heavy_count, heavy_list);

@@ -37,7 +37,6 @@ struct PassArgs {
     int log_n, lo, hi;  // this pass runs butterfly stages hi-1 .. lo
     int e_log;          // tile = 2^e_log elements
     size_t batch_stride;  // elements between consecutive transforms of a batch
-    size_t in_len;        // first pass: inputs at index >= in_len are zero and are neither read nor scaled
 };
 
 // 80 registers -> 3 resident blocks per SM.  Forcing 4 (64 registers, 84 B of spills) was measured slower:
@@ -65,11 +64,8 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
         else           { m = e >> q_log; qq = e & Q_mask; }   // adjacent sub-transforms adjacent
         const uint32_t q = q_base + qq;
         const size_t idx = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & lo_mask);
-        fe v = fe_zero();
-        if (idx < a.in_len) {
-            v = fe_load(in + idx);
-            if (a.pre) v = fe_mul<FrCfg>(v, fe_load_ro(a.pre + idx));
-        }
+        fe v = fe_load(in + idx);
+        if (a.pre) v = fe_mul<FrCfg>(v, fe_load_ro(a.pre + idx));
         const uint32_t pos = (m << q_log) | qq;
         plane_lo[pos] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
         plane_hi[pos] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
@@ -244,11 +240,8 @@ int domain_create(unsigned log_n, cudaStream_t st, Domain** out) {
 
 // data: batch transforms of n elements, `stride` elements apart, transformed in place.
 // scratch: at least (batch-1)*stride + n elements when log_n > kTileLog.
-// nonzero_len (0 = n): every transform's inputs at index >= nonzero_len are known to be zero (a low-degree
-// polynomial evaluated over a larger domain); the first pass then skips their loads and coset scaling, and
-// the caller need not clear that part of the buffer.
 int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, unsigned batch,
-               size_t stride, cudaStream_t st, size_t nonzero_len) {
+               size_t stride, cudaStream_t st) {
     const int L = (int)d->log_n;
     if (L == 0 || batch == 0) return B200_OK;  // size-1 transform is the identity (n^-1 = 1)
     const int P = (L + kTileLog - 1) / kTileLog;
@@ -274,7 +267,6 @@ int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, u
         a.has_post_scalar = 0;
         a.post_scalar = d->n_inv;
         a.batch_stride = stride;
-        a.in_len = (p == 0 && nonzero_len) ? nonzero_len : ((size_t)1 << L);
         const bool final_pass = (p == P - 1);
         // inner passes run in place; the pass before the last writes to scratch so that the last
         // (bit-reversing, hence out-of-place) pass lands back in `data`.  A single-pass transform

@@ -549,27 +549,16 @@ static Workspace carve(fe* base, size_t n) {
 // proofs are made several at a time per GPU, where operation count beats chain length.
 struct ProverMsmTuning {
     MsmScratch* s;
-    int saved_log, saved_rounds, saved_per_thread;
-    static int env_int(const char* name, int lo, int hi, int dflt) {  // tuning knobs
-        const char* e = std::getenv(name);
-        if (!e) return dflt;
-        const int v = std::atoi(e);
-        return v >= lo && v <= hi ? v : dflt;
-    }
-    explicit ProverMsmTuning(MsmScratch* s_)
-        : s(s_), saved_log(s_->reduce_chunk_log), saved_rounds(s_->affine_rounds), saved_per_thread(s_->pair_per_thread) {
-        static const int log = env_int("B200_PROVER_REDUCE_CHUNK_LOG", 1, 8, kMsmReduceChunkLogThroughput);
-        static const int rounds = env_int("B200_PROVER_AFFINE_ROUNDS", 0, 2, kMsmAffineRoundsThroughput);
-        static const int per_thread = env_int("B200_PROVER_PAIR_PER_THREAD", 1, 1024, 0);
+    int saved;
+    explicit ProverMsmTuning(MsmScratch* s_) : s(s_), saved(s_->reduce_chunk_log) {
+        static const int log = [] {
+            const char* e = std::getenv("B200_PROVER_REDUCE_CHUNK_LOG");  // tuning knob
+            const int v = e ? std::atoi(e) : 0;
+            return v >= 1 && v <= 8 ? v : kMsmReduceChunkLogThroughput;
+        }();
         s->reduce_chunk_log = log;
-        s->affine_rounds = rounds;
-        s->pair_per_thread = per_thread;
     }
-    ~ProverMsmTuning() {
-        s->reduce_chunk_log = saved_log;
-        s->affine_rounds = saved_rounds;
-        s->pair_per_thread = saved_per_thread;
-    }
+    ~ProverMsmTuning() { s->reduce_chunk_log = saved; }
 };
 
 static int commit(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, g1_affine* out) {

@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=[False, True], ids=["latency", "throughput"])
 def mode(request, ctx):
-    """Both MSM tunings (b200_msm_tuning): XYZZ-only folding, and the prover's throughput mode with
-    batched-affine pairing rounds and long reduction chains.  Results must be identical."""
+    """Both MSM tunings (b200_msm_tuning): latency (4 buckets per reduction thread) and the prover's
+    throughput mode (16).  Results must be identical."""
     ctx.msm_tuning(request.param)
     yield request.param
     ctx.msm_tuning(False)
