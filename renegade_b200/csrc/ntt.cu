@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
         plane_hi[pos] = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
     };
     int sp = t_log - 1;
-    for (; sp >= 1; sp -= 2) {
+    // the last pass ends on stages 1 and 0, whose twiddles are 1, 1, w^(n/4), 1: peeled below without the
+    // three trivial products
+    for (; sp >= 2 || (!FINAL && sp == 1); sp -= 2) {
         const int s = a.lo + sp;
         const uint32_t low_mask = (1u << (sp - 1)) - 1u;
         for (uint32_t t = threadIdx.x; t < (uint32_t)(E >> 2); t += blockDim.x) {
@@ -116,16 +118,39 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
         }
         __syncthreads();
     }
+    if (FINAL && sp == 1) {
+        const fe wi = fe_load_ro(a.tw + ((size_t)1 << (a.log_n - 2)));  // primitive 4th root (or its inverse)
+        for (uint32_t t = threadIdx.x; t < (uint32_t)(E >> 2); t += blockDim.x) {
+            const uint32_t qq = t & Q_mask;
+            const uint32_t base = (t >> q_log) << 2;
+            const uint32_t p00 = (base << q_log) | qq, p01 = ((base | 1u) << q_log) | qq;
+            const uint32_t p10 = ((base | 2u) << q_log) | qq, p11 = ((base | 3u) << q_log) | qq;
+            const fe x00 = lds(p00), x01 = lds(p01), x10 = lds(p10), x11 = lds(p11);
+            const fe y00 = fe_add<FrCfg>(x00, x10), y10 = fe_sub<FrCfg>(x00, x10);
+            const fe y01 = fe_add<FrCfg>(x01, x11);
+            const fe y11 = fe_mul<FrCfg>(fe_sub<FrCfg>(x01, x11), wi);
+            sts(p00, fe_add<FrCfg>(y00, y01));
+            sts(p01, fe_sub<FrCfg>(y00, y01));
+            sts(p10, fe_add<FrCfg>(y10, y11));
+            sts(p11, fe_sub<FrCfg>(y10, y11));
+        }
+        __syncthreads();
+        sp = -1;
+    }
     if (sp == 0) {  // odd number of stages in this pass: one radix-2 stage on neighbouring elements
         for (uint32_t t = threadIdx.x; t < (uint32_t)(E >> 1); t += blockDim.x) {
             const uint32_t qq = t & Q_mask;
             const uint32_t r = t >> q_log;
             const uint32_t p0 = ((r << 1) << q_log) | qq, p1 = (((r << 1) | 1u) << q_log) | qq;
             const size_t lw = (q_base + qq) & lo_mask;
-            const fe w = fe_load_ro(a.tw + (lw << (a.log_n - a.lo - 1)));
             const fe x0 = lds(p0), x1 = lds(p1);
             sts(p0, fe_add<FrCfg>(x0, x1));
-            sts(p1, fe_mul<FrCfg>(fe_sub<FrCfg>(x0, x1), w));
+            if (FINAL) {  // stage 0 of the whole transform: twiddle w^0 = 1
+                sts(p1, fe_sub<FrCfg>(x0, x1));
+            } else {
+                const fe w = fe_load_ro(a.tw + (lw << (a.log_n - a.lo - 1)));
+                sts(p1, fe_mul<FrCfg>(fe_sub<FrCfg>(x0, x1), w));
+            }
         }
         __syncthreads();
     }
