@@ -426,9 +426,10 @@ def main():
                              "`achieved_kernel_alone` the same kernel timed alone; see DESIGN.md for the INT-pipe roofline"},
         "e2e": {"value": world * args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": 5 * n * 32 + NUM_INPUTS * 32 + 17 * 32,
                 "d2h_bytes_per_step": 1152, "ms_per_step": dt_e2e / args.steps * 1e3},
-        # 110 kernel launches per proof (ncu launch list, profiles/r1k_proof_kernel_shares_final.txt):
-        # 4 batched commitments x 17 kernels + NTT passes, quotient, scans, evaluations, divisions
-        "gpu_launches": args.steps * 110,
+        # 113 kernel launches per proof (ncu launch list -> tools/kernel_shares.py,
+        # profiles/r1r_proof_kernel_shares.txt): 4 batched commitments x 17 kernels + NTT passes, coset
+        # fold / combine, quotient, scans, evaluations, divisions
+        "gpu_launches": args.steps * 113,
         "latency_ms_one_proof_in_flight": single_ms, "latency_phases_ms": single,
         "clocks": clocks, "setup_s": setup_s, "msm": msm, "ntt": ntt,
     })
