@@ -24,7 +24,10 @@ namespace b200 {
 
 namespace {
 
-constexpr int kTileLog = 10;  // 1024 elements = 32 KB of shared memory per block
+#ifndef B200_NTT_TILE_LOG
+#define B200_NTT_TILE_LOG 10
+#endif
+constexpr int kTileLog = B200_NTT_TILE_LOG;  // 1024 elements = 32 KB of shared memory per block
 
 struct PassArgs {
     const fe* in;
@@ -274,8 +277,8 @@ int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, u
     const int base = L / P, extra = L % P;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10);
-        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << 10);
+        cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog);
+        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog);
         attr_set = true;
     }
     int hi = L;

@@ -106,9 +106,10 @@ def test_prove_2_17_max_domain(ctx, oracle, pyoracle):
 
 
 def test_zero_public_inputs_and_tiny_domain(ctx, oracle, pyoracle):
-    """Edge cases: a circuit without public inputs, and the smallest domain the prover accepts (n = 4)."""
-    from renegade_b200._lib import B200Error
-    for log_n, num_inputs in ((6, 0), (2, 1)):
+    """Edge cases: a circuit without public inputs, the smallest domain the prover accepts (n = 4), and the
+    domains either side of the switch from 8 to 6 quotient cosets (n = 8 -> 8 cosets, n = 16 -> 6: 6n exceeds the
+    quotient's 5n + 8 coefficients by only 8 there)."""
+    for log_n, num_inputs in ((6, 0), (2, 1), (3, 2), (4, 3)):
         circ, tau, srs = setup(ctx, oracle, pyoracle, log_n, seed=40 + log_n, num_inputs=num_inputs)
         bases = ctx.load_bases(srs)
         pk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)

@@ -97,6 +97,27 @@ def test_pool_failed_job_reports_its_error_and_pool_survives(ctx, oracle, pyorac
         pool.close()
 
 
+def test_pool_destroy_drains_the_queue(ctx, oracle, pyoracle):
+    """`b200_pool_destroy` finishes what is queued (the reference's proof manager answers every job it took off
+    the queue): results land in the caller's buffers although nobody waited."""
+    log_n = 9
+    circ, tau, srs = make(ctx, oracle, pyoracle, log_n, seed=23)
+    bases = ctx.load_bases(srs)  # keys made on another context of the device are usable by the workers
+    pk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    wires = np.ascontiguousarray(circ.wires, dtype=np.uint64)
+    bl = synth.splitmix_blinders(77)
+    ref, _ = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+    pool = ProverPool(0, workers=2)
+    tickets = [pool.submit_prove(pk, wires.ctypes.data, circ.pub_inputs, bl, keep=wires) for _ in range(8)]
+    proofs = [pool._keep[t][0] for t in tickets]  # the output structs the jobs write into
+    held = dict(pool._keep)  # keep the buffers alive across close()
+    pool.close()
+    for p in proofs:
+        assert bytes(p) == bytes(ref)
+    del held
+    pk.free()
+
+
 def test_pool_submit_from_many_threads_and_link_jobs(ctx, oracle, pyoracle):
     """Any thread may submit and wait (the reference's workers answer on per-job oneshot channels);
     the settlement bundle's link proofs are queued like the reference forks them
