@@ -41,7 +41,8 @@ SEED_BASES, SEED_SCALARS, SEED_SRS = 0xB200, 0x5CA1A8, 0x7A0
 METRIC = "proofs/sec, VALID-MATCH-class TurboPlonk proof (n = 2^16 gates, BN254/KZG)"
 WORKLOAD = ("synthetic TurboPlonk circuit, n = 2^16 gates, 17 public inputs, 5 wire columns, 13 selector columns "
             "(stand-in for IntentAndBalancePrivateSettlementCircuit, BASELINE.json configs[3]); "
-            "13 KZG commitments of ~2^16 points + 8 size-2^19 and 7 size-2^16 NTTs per proof")
+            "13 KZG commitments of ~2^16 points and a degree-(5n+7) quotient per proof (the reference: 8n-point coset FFTs; "
+            "this library: 6 cosets of n points, same coefficients)")
 
 
 def measured_peak_hbm():
@@ -412,8 +413,8 @@ def main():
         "config": {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": NUM_INPUTS, "gates_used": circ.n_gates,
                    "concurrency_per_gpu": conc, "parallelism": "one proof stream per GPU (replicas, no collective)",
                    "msm_plan": srs.plan,
-                   "l2": "per-proof working set > L2: 18 resident coset tables (302 MB) + 7 x 16 MB extended "
-                         "polynomials + 1.1 GB of SRS window tables vs 126 MB of L2",
+                   "l2": "working set > L2: shared key tables 227 MB + SRS window tables 67 MB, plus per proof in flight "
+                         "7 x 12.6 MB extended polynomials and ~100 MB of MSM scratch, vs 126 MB of L2",
                    "timing": "wall clock around K proofs, barrier + cuda synchronize on both sides, max over ranks; "
                              "kernel times from CUDA events on the library's stream"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
