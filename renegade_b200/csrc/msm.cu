@@ -721,7 +721,10 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     if ((rc = s->seg_order.reserve((max_segs + kSegLen + 2) * 4)) != B200_OK) return rc;
-    int chunk_log = s->reduce_chunk_log > 0 ? s->reduce_chunk_log : kReduceChunkLogLatency;
+    // lone MSM: short chains while the reduction is latency-bound (<= 2^16 buckets -> <= 128 blocks); with more
+    // buckets the blocks outnumber the SMs and the operation count takes over, as inside the prover
+    int chunk_log = s->reduce_chunk_log > 0 ? s->reduce_chunk_log
+                                            : std::min(kMsmReduceChunkLogThroughput, std::max(kReduceChunkLogLatency, pl.c - 15));
     while (chunk_log > 0 && (half >> chunk_log) < 32) --chunk_log;  // tiny windows: keep a warp's worth of threads
     const uint32_t reduce_threads_needed = (half + (1u << chunk_log) - 1) >> chunk_log;
     const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;

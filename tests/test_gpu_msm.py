@@ -34,7 +34,7 @@ def test_known_dlog_golden(ctx, oracle, pyoracle, kat):
 
 
 @pytest.mark.parametrize("n,c", [(1, 0), (31, 0), (32, 8), (1000, 0), (1000, 9), (4099, 0), (4099, 13),
-                                 (1 << 14, 0), ((1 << 16) + 3, 0)])
+                                 (1 << 14, 0), ((1 << 16) + 3, 0), (3000, 18), (3000, 20)])
 def test_msm_matches_oracle(ctx, oracle, n, c, mode):
     pts = oracle.known_dlog_bases(0xB200, n)
     bases = ctx.load_bases(pts, window_bits=c)
