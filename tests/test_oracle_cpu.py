@@ -156,3 +156,47 @@ def test_splitmix_and_bases_match_python(oracle, pyoracle):
     a = py.splitmix_fr(0xB200, 6)
     for i in range(6):
         assert py.decode_g1_mont(B.tobytes(), i) == py.g1_mul(py.G1_GEN, a[i])
+
+
+def test_quotient_domain_of_six_cosets_matches_the_8n_coset(pyoracle):
+    """The algebra behind the device prover's quotient domain, pinned with the Python oracle's own
+    transforms: a polynomial t of degree <= 5n + 7 is recovered from its values on 6 of the 8 cosets s_j * H_n of
+    g * H_8n (the reference's quotient domain) by 6 size-n inverse transforms, the scaling s_j^-i and one 6 x 6
+    inverse-Vandermonde combination in c_j = s_j^n — and a polynomial with n + 3 coefficients is evaluated on coset j
+    by folding X^n -> c_j, scaling by s_j^i and ONE size-n transform."""
+    import random
+    py = pyoracle
+    rnd = random.Random(0xC05E7)
+    log_n, nc = 4, 6
+    n, g = 1 << log_n, py.FR_GENERATOR
+    w8n = py.domain_generator(log_n + 3)
+    s = [g * pow(w8n, j, py.R) % py.R for j in range(nc)]
+    c = [pow(sj, n, py.R) for sj in s]
+    t = [rnd.randrange(py.R) for _ in range(5 * n + 8)] + [0] * (8 * n - (5 * n + 8))
+    on_8n = py.coset_ntt(t)  # what the reference computes: t on g * w_8n^i, natural order
+    # coset j of the 8n domain is every 8th point starting at j
+    vals = [[on_8n[8 * h + j] for h in range(n)] for j in range(nc)]
+    u = []
+    for j in range(nc):
+        v = py.ntt(vals[j], inverse=True)  # coefficients of u_j(s_j X)
+        u.append([v[i] * pow(s[j], -i, py.R) % py.R for i in range(n)])
+    # invert the Vandermonde matrix V[j][k] = c_j^k by Gauss-Jordan
+    m = [[pow(c[j], k, py.R) for k in range(nc)] + [int(i == j) for i in range(nc)] for j in range(nc)]
+    for col in range(nc):
+        piv = next(r for r in range(col, nc) if m[r][col])
+        m[col], m[piv] = m[piv], m[col]
+        inv = pow(m[col][col], -1, py.R)
+        m[col] = [x * inv % py.R for x in m[col]]
+        for r in range(nc):
+            if r != col and m[r][col]:
+                f = m[r][col]
+                m[r] = [(x - f * y) % py.R for x, y in zip(m[r], m[col])]
+    minv = [row[nc:] for row in m]
+    rec = [sum(minv[k][j] * u[j][i] for j in range(nc)) % py.R for k in range(nc) for i in range(n)]
+    assert rec == t[:nc * n]
+    # forward direction: fold + scale + size-n transform == the 8n-coset values on that coset
+    a = [rnd.randrange(py.R) for _ in range(n + 3)]
+    a_on_8n = py.coset_ntt(a + [0] * (8 * n - len(a)))
+    for j in range(nc):
+        folded = [(a[i] + (c[j] * a[n + i] if n + i < len(a) else 0)) * pow(s[j], i, py.R) % py.R for i in range(n)]
+        assert py.ntt(folded) == [a_on_8n[8 * h + j] for h in range(n)], j
