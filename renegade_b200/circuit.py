@@ -1,0 +1,521 @@
+"""Host-side constraint system: the caller side of the proving boundary.
+
+The reference synthesises its circuits in Rust (`SingleProverCircuit::prove`, circuit-types/src/traits.rs:976-991:
+create the witness variables, `apply_constraints`, `finalize_for_arithmetization`) on mpc-relation's
+`PlonkCircuit<ScalarField>` and hands the finished tables to the prover.  That code cannot run here (no cargo), so this
+module restates the part of that interface the proving path consumes — variables, the TurboPlonk gate set with its 13
+selector columns, copy constraints, public-input gates first, zero padding to the domain — and the reference's own
+Poseidon2 and Merkle gadgets on top of it, so that tests and benches can prove circuits with the reference's gate
+structure instead of random tables:
+
+  * `PlonkCircuit`               mpc-relation `PlonkCircuit` (as used through `mpc_relation::traits::Circuit`)
+  * `FusedExternalSboxMDSGate`,
+    `FusedInternalSboxMDSGate`   circuits-core/src/zk_gadgets/primitives/poseidon/gates.rs:27-100, 117-179
+  * `PoseidonHashGadget`         .../poseidon/hash.rs:56-423 (195 gates per permutation)
+  * `PoseidonMerkleHashGadget`   .../primitives/merkle.rs:13-126
+  * `Poseidon2Sponge`,
+    `compute_poseidon_hash`      crates/crypto/src/hash/poseidon2.rs:25-209, hash/mod.rs:12-18 (native, for witnesses)
+
+Everything here is host-side input generation on Python integers; the tables `finalize_for_arithmetization` returns are
+exactly what `b200_plonk_preprocess` / `b200_plonk_prove` take (same layout as renegade_b200/synth.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+
+from .poseidon2_constants import CAPACITY, FULL_ROUND_CONSTANTS, PARTIAL_ROUND_CONSTANTS, R_F, R_P, RATE
+from .synth import N_SELECTORS, N_WIRES, Q_C, Q_ECC, Q_HASH, Q_LC, Q_MUL, Q_O, R, SynthCircuit, gate_value, to_mont_array
+
+GATE_WIDTH = 4
+Variable = int
+
+
+class CircuitError(Exception):
+    """mpc-relation `CircuitError` (surfaces as `ProverError::Circuit`, circuit-types/src/errors.rs:33-58)."""
+
+
+# ---------------------------------------------------------------------------------------------
+# Gates: one row of the 13 selector columns
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Gate:
+    """mpc-relation `Gate`: q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc (all zero by default).
+    Equation: q_c + PI + sum q_lc w + q_mul0 w0 w1 + q_mul1 w2 w3 + sum q_hash w^5 + q_ecc w0 w1 w2 w3 w4 = q_o w4."""
+    name: str = "Gate"
+    q_lc: Sequence[int] = (0, 0, 0, 0)
+    q_mul: Sequence[int] = (0, 0)
+    q_hash: Sequence[int] = (0, 0, 0, 0)
+    q_o: int = 0
+    q_c: int = 0
+    q_ecc: int = 0
+
+    def selectors(self) -> List[int]:
+        q = [0] * N_SELECTORS
+        for j in range(4):
+            q[Q_LC + j] = self.q_lc[j] % R
+            q[Q_HASH + j] = self.q_hash[j] % R
+        q[Q_MUL], q[Q_MUL + 1] = self.q_mul[0] % R, self.q_mul[1] % R
+        q[Q_O], q[Q_C], q[Q_ECC] = self.q_o % R, self.q_c % R, self.q_ecc % R
+        return q
+
+
+def PaddingGate() -> Gate:
+    return Gate("PaddingGate")
+
+
+def IoGate() -> Gate:
+    """w4 = public input (the public-input polynomial supplies the value)."""
+    return Gate("IoGate", q_o=1)
+
+
+def ConstantGate(c: int) -> Gate:
+    return Gate("ConstantGate", q_c=c, q_o=1)
+
+
+def AdditionGate() -> Gate:
+    return Gate("AdditionGate", q_lc=(1, 1, 0, 0), q_o=1)
+
+
+def SubtractionGate() -> Gate:
+    return Gate("SubtractionGate", q_lc=(1, -1, 0, 0), q_o=1)
+
+
+def MultiplicationGate() -> Gate:
+    return Gate("MultiplicationGate", q_mul=(1, 0), q_o=1)
+
+
+def LinCombGate(coeffs: Sequence[int]) -> Gate:
+    return Gate("LinCombGate", q_lc=tuple(coeffs), q_o=1)
+
+
+def EqualityGate() -> Gate:
+    return Gate("EqualityGate", q_lc=(1, -1, 0, 0))
+
+
+def BoolGate() -> Gate:
+    """wires (a, a, 0, 0, a): a * a = a."""
+    return Gate("BoolGate", q_mul=(1, 0), q_o=1)
+
+
+def MuxGate() -> Gate:
+    """wires (sel, a, sel, b, out): out = sel * a - sel * b + b = if sel { a } else { b }."""
+    return Gate("MuxGate", q_lc=(0, 0, 0, 1), q_mul=(1, -1), q_o=1)
+
+
+def pow5(x: int) -> int:
+    return pow(x, 5, R)
+
+
+class FusedExternalSboxMDSGate(Gate):
+    """poseidon/gates.rs:27-100: wires (state_curr, s0, s1, s2, out); out = rc + sum f(w), f = x^5 if `apply_sbox`
+    else x — the external MDS circ(2, 1, 1) row of element `state_curr` (each element plus the sum of all three)
+    fused with the next round's constant."""
+
+    def __init__(self, apply_sbox: bool, round_constant: int):
+        ones, zeros = (1, 1, 1, 1), (0, 0, 0, 0)
+        super().__init__("FusedExternalSboxMDSGate", q_lc=zeros if apply_sbox else ones,
+                         q_hash=ones if apply_sbox else zeros, q_o=1, q_c=round_constant)
+        self.apply_sbox = apply_sbox
+
+    def compute_output(self, state_curr: int, s0: int, s1: int, s2: int) -> int:
+        el = [state_curr, s0, s1, s2]
+        if self.apply_sbox:
+            el = [pow5(x) for x in el]
+        return (self.q_c + sum(el)) % R
+
+
+class FusedInternalSboxMDSGate(Gate):
+    """poseidon/gates.rs:117-179: out = rc + coeff * g(state_curr) + s0^5 + s1 + s2, g = x^5 if `apply_sbox` else x —
+    a row of the internal matrix [[2,1,1],[1,2,1],[1,1,3]] applied to (s0^5, s1, s2), fused with the next constant."""
+
+    def __init__(self, apply_sbox: bool, next_round_constant: int, state_elem_coeff: int):
+        c = state_elem_coeff
+        super().__init__("FusedInternalSboxMDSGate",
+                         q_hash=(c, 1, 0, 0) if apply_sbox else (0, 1, 0, 0),
+                         q_lc=(0, 0, 1, 1) if apply_sbox else (c, 0, 1, 1), q_o=1, q_c=next_round_constant)
+        self.apply_sbox, self.coeff = apply_sbox, c
+
+    def compute_output(self, state_curr: int, s0: int, s1: int, s2: int) -> int:
+        elem = pow5(state_curr) if self.apply_sbox else state_curr
+        return (self.q_c + self.coeff * elem + pow5(s0) + s1 + s2) % R
+
+
+# ---------------------------------------------------------------------------------------------
+# The constraint system
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class _Row:
+    wires: List[Variable]
+    gate: Gate
+
+
+class PlonkCircuit:
+    """mpc-relation `PlonkCircuit<ScalarField>`: variable 0 is the constant zero, variable 1 the constant one
+    (each pinned by a constant gate, as upstream's `new()` does)."""
+
+    def __init__(self):
+        self.witness_values: List[int] = []
+        self.rows: List[_Row] = []
+        self.pub_input_vars: List[Variable] = []
+        self._finalized = False
+        self._zero = self.create_variable(0)
+        self._one = self.create_variable(1)
+        self.enforce_constant(self._zero, 0)
+        self.enforce_constant(self._one, 1)
+
+    # ---- variables -----------------------------------------------------------------------
+    def zero(self) -> Variable:
+        return self._zero
+
+    def one(self) -> Variable:
+        return self._one
+
+    def create_variable(self, val: int) -> Variable:
+        self._check_open()
+        self.witness_values.append(val % R)
+        return len(self.witness_values) - 1
+
+    def create_public_variable(self, val: int) -> Variable:
+        var = self.create_variable(val)
+        self.pub_input_vars.append(var)
+        self.rows.append(_Row([self._zero] * GATE_WIDTH + [var], IoGate()))
+        return var
+
+    def create_constant_variable(self, val: int) -> Variable:
+        var = self.create_variable(val)
+        self.enforce_constant(var, val)
+        return var
+
+    def create_boolean_variable(self, val: bool) -> Variable:
+        var = self.create_variable(int(bool(val)))
+        self.enforce_bool(var)
+        return var
+
+    def witness(self, var: Variable) -> int:
+        if not 0 <= var < len(self.witness_values):
+            raise CircuitError(f"variable {var} out of bound")
+        return self.witness_values[var]
+
+    @property
+    def num_vars(self) -> int:
+        return len(self.witness_values)
+
+    @property
+    def num_gates(self) -> int:
+        return len(self.rows)
+
+    @property
+    def num_inputs(self) -> int:
+        return len(self.pub_input_vars)
+
+    # ---- gates ---------------------------------------------------------------------------
+    def insert_gate(self, wire_vars: Sequence[Variable], gate: Gate) -> None:
+        self._check_open()
+        if len(wire_vars) != GATE_WIDTH + 1:
+            raise CircuitError("a gate takes GATE_WIDTH + 1 wires")
+        for v in wire_vars:
+            self.witness(v)
+        self.rows.append(_Row(list(wire_vars), gate))
+
+    def _out(self, wires4: Sequence[Variable], gate: Gate, value: int) -> Variable:
+        out = self.create_variable(value)
+        self.insert_gate(list(wires4) + [out], gate)
+        return out
+
+    def add(self, a: Variable, b: Variable) -> Variable:
+        return self._out([a, b, self._zero, self._zero], AdditionGate(), self.witness(a) + self.witness(b))
+
+    def sub(self, a: Variable, b: Variable) -> Variable:
+        return self._out([a, b, self._zero, self._zero], SubtractionGate(), self.witness(a) - self.witness(b))
+
+    def mul(self, a: Variable, b: Variable) -> Variable:
+        return self._out([a, b, self._zero, self._zero], MultiplicationGate(), self.witness(a) * self.witness(b))
+
+    def lc(self, wires: Sequence[Variable], coeffs: Sequence[int]) -> Variable:
+        if len(wires) != GATE_WIDTH or len(coeffs) != GATE_WIDTH:
+            raise CircuitError("lc takes GATE_WIDTH wires and coefficients")
+        return self._out(wires, LinCombGate(coeffs), sum(c * self.witness(w) for c, w in zip(coeffs, wires)))
+
+    def mux(self, sel: Variable, a: Variable, b: Variable) -> Variable:
+        """if sel { a } else { b } (sel must be boolean-constrained by the caller, as `BoolVar` guarantees upstream)."""
+        s, va, vb = self.witness(sel), self.witness(a), self.witness(b)
+        return self._out([sel, a, sel, b], MuxGate(), s * va + (1 - s) * vb)
+
+    def enforce_equal(self, a: Variable, b: Variable) -> None:
+        self.insert_gate([a, b, self._zero, self._zero, self._zero], EqualityGate())
+
+    def enforce_constant(self, var: Variable, c: int) -> None:
+        self.insert_gate([self._zero] * GATE_WIDTH + [var], ConstantGate(c))
+
+    def enforce_bool(self, a: Variable) -> None:
+        self.insert_gate([a, a, self._zero, self._zero, a], BoolGate())
+
+    # ---- checks and arithmetization ----------------------------------------------------------
+    def _check_open(self) -> None:
+        if getattr(self, "_finalized", False):
+            raise CircuitError("circuit already finalized for arithmetization")
+
+    def check_circuit_satisfiability(self, pub_inputs: Sequence[int]) -> None:
+        """mpc-relation `check_circuit_satisfiability`: every gate equation holds for the current witness, with
+        the given public inputs (in `create_public_variable` order) feeding the IO gates."""
+        if len(pub_inputs) != self.num_inputs:
+            raise CircuitError("wrong number of public inputs")
+        pi_of = {id(row): v % R for row, v in zip([r for r in self.rows if r.gate.name == "IoGate"], pub_inputs)}
+        for i, row in enumerate(self.rows):
+            w = [self.witness_values[v] for v in row.wires]
+            if gate_value(row.gate.selectors(), w, pi_of.get(id(row), 0)) != 0:
+                raise CircuitError(f"gate {i} ({row.gate.name}) is not satisfied")
+
+    def public_input(self) -> List[int]:
+        return [self.witness_values[v] for v in self.pub_input_vars]
+
+    def finalize_for_arithmetization(self, min_log_n: int = 2) -> SynthCircuit:
+        """Public-input gates first, zero padding to the next power of two, one copy-constraint cycle per variable
+        (upstream: `finalize_for_arithmetization`, traits.rs:847,991).  Returns the flat tables the C ABI takes."""
+        self._check_open()
+        io = [r for r in self.rows if r.gate.name == "IoGate"]
+        rest = [r for r in self.rows if r.gate.name != "IoGate"]
+        rows = io + rest
+        n_gates = len(rows)
+        log_n = max(min_log_n, (n_gates - 1).bit_length())
+        n = 1 << log_n
+        rows = rows + [_Row([self._zero] * (GATE_WIDTH + 1), PaddingGate()) for _ in range(n - n_gates)]
+        sel = [[0] * n for _ in range(N_SELECTORS)]
+        wire_var = [[0] * n for _ in range(N_WIRES)]
+        positions: List[List] = [[] for _ in self.witness_values]
+        for r, row in enumerate(rows):
+            q = row.gate.selectors()
+            for s in range(N_SELECTORS):
+                sel[s][r] = q[s]
+            for wcol, var in enumerate(row.wires):
+                wire_var[wcol][r] = var
+                positions[var].append((wcol, r))
+        perm = np.empty(N_WIRES * n, dtype=np.uint64)
+        for occ in positions:
+            for a, b in zip(occ, occ[1:] + occ[:1]):
+                perm[a[0] * n + a[1]] = b[0] * n + b[1]
+        wires_int = [[self.witness_values[wire_var[w][r]] for r in range(n)] for w in range(N_WIRES)]
+        pub = self.public_input()
+        k_int = [pow(5, i, R) for i in range(N_WIRES)]
+        self._finalized = True
+        return SynthCircuit(log_n=log_n, num_inputs=len(pub), k=to_mont_array(k_int),
+                            selectors=np.stack([to_mont_array(col) for col in sel]), perm=perm,
+                            wires=np.stack([to_mont_array(col) for col in wires_int]),
+                            pub_inputs=to_mont_array(pub) if pub else np.zeros((0, 4), dtype=np.uint64),
+                            n_gates=n_gates, selectors_int=sel, wires_int=wires_int, pub_inputs_int=pub)
+
+
+# ---------------------------------------------------------------------------------------------
+# Native Poseidon2 (witness side)
+# ---------------------------------------------------------------------------------------------
+def _external_mds(s: List[int]) -> List[int]:
+    t = sum(s) % R
+    return [(x + t) % R for x in s]
+
+
+def _internal_mds(s: List[int]) -> List[int]:
+    t = sum(s) % R
+    return [(s[0] + t) % R, (s[1] + t) % R, (2 * s[2] + t) % R]
+
+
+class Poseidon2Sponge:
+    """crates/crypto/src/hash/poseidon2.rs:25-209: width 3, rate 2, capacity 1, R_F = 8, R_P = 56, alpha = 5."""
+
+    def __init__(self):
+        self.state = [0] * (CAPACITY + RATE)
+        self.next_index = 0
+        self.squeezing = False
+
+    def permute(self) -> None:
+        st = _external_mds(self.state)
+        half = R_F // 2
+        for r in range(half):
+            st = _external_mds([pow5((x + FULL_ROUND_CONSTANTS[r][i]) % R) for i, x in enumerate(st)])
+        for r in range(R_P):
+            st = _internal_mds([pow5((st[0] + PARTIAL_ROUND_CONSTANTS[r]) % R), st[1], st[2]])
+        for r in range(half, R_F):
+            st = _external_mds([pow5((x + FULL_ROUND_CONSTANTS[r][i]) % R) for i, x in enumerate(st)])
+        self.state = st
+
+    def absorb(self, x: int) -> None:
+        if self.squeezing:
+            raise ValueError("cannot absorb while squeezing")
+        if self.next_index == RATE:
+            self.permute()
+            self.next_index = 0
+        self.state[self.next_index + CAPACITY] = (self.state[self.next_index + CAPACITY] + x) % R
+        self.next_index += 1
+
+    def absorb_batch(self, xs: Sequence[int]) -> None:
+        for x in xs:
+            self.absorb(x)
+
+    def squeeze(self) -> int:
+        if not self.squeezing or self.next_index == RATE:
+            self.permute()
+            self.next_index = 0
+            self.squeezing = True
+        out = self.state[self.next_index + CAPACITY]
+        self.next_index += 1
+        return out
+
+    def hash(self, xs: Sequence[int]) -> int:
+        self.absorb_batch(xs)
+        return self.squeeze()
+
+
+def compute_poseidon_hash(values: Sequence[int]) -> int:
+    """crates/crypto/src/hash/mod.rs:12-18."""
+    return Poseidon2Sponge().hash(values)
+
+
+# ---------------------------------------------------------------------------------------------
+# Gadgets
+# ---------------------------------------------------------------------------------------------
+class PoseidonHashGadget:
+    """poseidon/hash.rs:56-423: the sponge over circuit variables; a permutation is 195 gates (one external MDS,
+    8 fused external rounds, 56 fused internal rounds, 3 gates each), every gate carrying the NEXT round's constant."""
+
+    def __init__(self, zero_var: Variable):
+        self.state = [zero_var] * (CAPACITY + RATE)
+        self.next_index = 0
+        self.in_squeeze_state = False
+
+    def reset_state(self, cs: PlonkCircuit) -> None:
+        self.state = [cs.zero()] * (CAPACITY + RATE)
+        self.next_index = 0
+        self.in_squeeze_state = False
+
+    def hash(self, hash_input: Sequence[Variable], cs: PlonkCircuit) -> Variable:
+        self.batch_absorb(hash_input, cs)
+        return self.squeeze(cs)
+
+    def hash_constrained(self, hash_input: Sequence[Variable], expected_output: Variable, cs: PlonkCircuit) -> None:
+        self.batch_absorb(hash_input, cs)
+        self.constrained_squeeze(expected_output, cs)
+
+    def absorb(self, a: Variable, cs: PlonkCircuit) -> None:
+        if self.in_squeeze_state:
+            raise CircuitError("Cannot absorb from a sponge that has already been squeezed")
+        if self.next_index == RATE:
+            self.permute(cs)
+            self.next_index = 0
+        idx = self.next_index + CAPACITY
+        self.state[idx] = cs.add(a, self.state[idx])
+        self.next_index += 1
+
+    def batch_absorb(self, xs: Sequence[Variable], cs: PlonkCircuit) -> None:
+        for x in xs:
+            self.absorb(x, cs)
+
+    def squeeze(self, cs: PlonkCircuit) -> Variable:
+        if not self.in_squeeze_state or self.next_index == RATE:
+            self.permute(cs)
+            self.next_index = 0
+            self.in_squeeze_state = True
+        res = self.state[CAPACITY + self.next_index]
+        self.next_index += 1
+        return res
+
+    def batch_squeeze(self, num_elements: int, cs: PlonkCircuit) -> List[Variable]:
+        return [self.squeeze(cs) for _ in range(num_elements)]
+
+    def constrained_squeeze(self, expected: Variable, cs: PlonkCircuit) -> None:
+        cs.enforce_equal(expected, self.squeeze(cs))
+
+    # ---- permutation (hash.rs:205-262) ------------------------------------------------------
+    def permute(self, cs: PlonkCircuit) -> None:
+        half = R_F // 2
+        self._fused_external(False, FULL_ROUND_CONSTANTS[0], cs)
+        for rnd in range(half - 1):
+            self._fused_external(True, FULL_ROUND_CONSTANTS[rnd + 1], cs)
+        rc = [PARTIAL_ROUND_CONSTANTS[0], 0, 0]
+        self._fused_external(True, rc, cs)
+        for rnd in range(R_P - 1):
+            rc[0] = PARTIAL_ROUND_CONSTANTS[rnd + 1]
+            self._fused_internal(rc, cs)
+        self._fused_internal(FULL_ROUND_CONSTANTS[half], cs)
+        for rnd in range(half, R_F - 1):
+            self._fused_external(True, FULL_ROUND_CONSTANTS[rnd + 1], cs)
+        self._fused_external(True, [0, 0, 0], cs)
+
+    def _fused_external(self, apply_sbox: bool, next_round_const: Sequence[int], cs: PlonkCircuit) -> None:
+        in_wires = list(self.state)
+        vals = [cs.witness(v) for v in in_wires]
+        for i in range(3):
+            gate = FusedExternalSboxMDSGate(apply_sbox, next_round_const[i])
+            out = cs.create_variable(gate.compute_output(vals[i], *vals))
+            cs.insert_gate([in_wires[i]] + in_wires + [out], gate)
+            self.state[i] = out
+
+    def _fused_internal(self, next_round_constants: Sequence[int], cs: PlonkCircuit) -> None:
+        in_wires = list(self.state)
+        vals = [cs.witness(v) for v in in_wires]
+        for i, (sbox, coeff) in enumerate(((True, 1), (False, 1), (False, 2))):
+            gate = FusedInternalSboxMDSGate(sbox, next_round_constants[i], coeff)
+            out = cs.create_variable(gate.compute_output(vals[i], *vals))
+            cs.insert_gate([in_wires[i]] + in_wires + [out], gate)
+            self.state[i] = out
+
+
+@dataclass
+class MerkleOpening:
+    """circuit-types `MerkleOpening<HEIGHT>`: sister nodes bottom-up and, per level, whether the running hash is the
+    RIGHT child of its parent."""
+    elems: List[int]
+    indices: List[bool]
+
+
+@dataclass
+class MerkleOpeningVar:
+    elems: List[Variable] = field(default_factory=list)
+    indices: List[Variable] = field(default_factory=list)
+
+
+class PoseidonMerkleHashGadget:
+    """primitives/merkle.rs:13-126."""
+
+    @staticmethod
+    def compute_root(leaf_node: Sequence[Variable], opening: MerkleOpeningVar, cs: PlonkCircuit) -> Variable:
+        leaf_hash = PoseidonHashGadget(cs.zero()).hash(leaf_node, cs)
+        return PoseidonMerkleHashGadget.compute_root_prehashed(leaf_hash, opening, cs)
+
+    @staticmethod
+    def compute_root_prehashed(leaf_node: Variable, opening: MerkleOpeningVar, cs: PlonkCircuit) -> Variable:
+        current = leaf_node
+        for path_elem, lr_select in zip(opening.elems, opening.indices):
+            # lr_select is true when the running hash is the right child (merkle.rs:80-91)
+            left = cs.mux(lr_select, path_elem, current)
+            right = cs.lc([current, path_elem, left, cs.zero()], [1, 1, -1, 1])
+            current = PoseidonHashGadget(cs.zero()).hash([left, right], cs)
+        return current
+
+    @staticmethod
+    def compute_and_constrain_root(leaf_node: Sequence[Variable], opening: MerkleOpeningVar, expected_root: Variable,
+                                   cs: PlonkCircuit) -> None:
+        cs.enforce_equal(expected_root, PoseidonMerkleHashGadget.compute_root(leaf_node, opening, cs))
+
+
+def native_merkle_root(leaf: Sequence[int], opening: MerkleOpening) -> int:
+    """The root `PoseidonMerkleHashGadget::compute_root` constrains, computed natively (merkle.rs tests: leaf hash =
+    sponge over the leaf buffer, internal nodes = two-to-one sponge hashes)."""
+    cur = compute_poseidon_hash(leaf)
+    for sister, is_right in zip(opening.elems, opening.indices):
+        cur = compute_poseidon_hash([sister, cur] if is_right else [cur, sister])
+    return cur
+
+
+def merkle_membership_circuit(leaf: Sequence[int], opening: MerkleOpening):
+    """A statement of the reference's shape in miniature: the Merkle root is public (like `merkle_root` in the
+    VALID-* statements), the leaf buffer and its opening are the witness.  Returns (PlonkCircuit, root)."""
+    cs = PlonkCircuit()
+    root_val = native_merkle_root(leaf, opening)
+    root = cs.create_public_variable(root_val)
+    leaf_vars = [cs.create_variable(v) for v in leaf]
+    op = MerkleOpeningVar([cs.create_variable(v) for v in opening.elems],
+                          [cs.create_boolean_variable(b) for b in opening.indices])
+    PoseidonMerkleHashGadget.compute_and_constrain_root(leaf_vars, op, root, cs)
+    return cs, root_val

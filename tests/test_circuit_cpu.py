@@ -1,0 +1,134 @@
+"""CPU: the host-side constraint system and the reference's Poseidon2 / Merkle gadgets restated on it
+(renegade_b200/circuit.py).  The native hash is checked against the oracle's Poseidon2 (itself pinned by the published
+HorizenLabs known answer with the reference's constants, tests/test_poseidon2.py); the gadget against the native hash
+and against the gate counts the reference documents; the arithmetization against the oracle prover and verifier:
+a circuit built here proves and verifies on the CPU restatement of the reference algorithm, which is what the device
+prover is bit-exact with."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from renegade_b200 import circuit as C
+from renegade_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAU = 0x19d2c3b4a5968778695a4b3c2d1e0f00112233445566778899aabbccddeeff01
+
+
+@pytest.fixture(scope="module")
+def p2(pyoracle):
+    return pyoracle.poseidon2_load_constants(os.path.join(ROOT, "tests", "golden", "poseidon2.json"))
+
+
+def test_native_sponge_matches_oracle(pyoracle, p2):
+    full, partial = p2
+    assert [c for row in C.FULL_ROUND_CONSTANTS for c in row] == full and C.PARTIAL_ROUND_CONSTANTS == partial
+    rnd = random.Random(5)
+    for ln in range(0, 7):
+        xs = [rnd.randrange(C.R) for _ in range(ln)]
+        assert C.compute_poseidon_hash(xs) == pyoracle.poseidon2_hash(xs, full, partial), ln
+    sp = C.Poseidon2Sponge()
+    sp.state = [0, 1, 2]
+    sp.permute()
+    assert sp.state == pyoracle.poseidon2_permute([0, 1, 2], full, partial)
+    # squeezing more than the rate permutes again (poseidon2.rs:67-79)
+    sp = C.Poseidon2Sponge()
+    sp.absorb_batch([7, 8, 9])
+    a, b, c3 = sp.squeeze(), sp.squeeze(), sp.squeeze()
+    st = pyoracle.poseidon2_permute(pyoracle.poseidon2_permute([0, 7, 8], full, partial)[:1] +
+                                    [(pyoracle.poseidon2_permute([0, 7, 8], full, partial)[1] + 9) % C.R,
+                                     pyoracle.poseidon2_permute([0, 7, 8], full, partial)[2]], full, partial)
+    assert (a, b) == (st[1], st[2]) and c3 == pyoracle.poseidon2_permute(st, full, partial)[1]
+
+
+def test_hash_gadget_matches_native_and_gate_count():
+    rnd = random.Random(6)
+    for ln in (1, 2, 3, 5):
+        cs = C.PlonkCircuit()
+        base = cs.num_gates                      # the two constant gates pinning zero and one
+        xs = [rnd.randrange(C.R) for _ in range(ln)]
+        vars_ = [cs.create_variable(x) for x in xs]
+        out = C.PoseidonHashGadget(cs.zero()).hash(vars_, cs)
+        assert cs.witness(out) == C.compute_poseidon_hash(xs)
+        perms = (ln + 1) // 2                    # one permutation per full rate block, the last one at the squeeze
+        assert cs.num_gates - base == ln + 195 * perms   # one addition gate per absorbed element; hash.rs:205 -> 195
+        cs.check_circuit_satisfiability([])
+        # expected output as a public input, constrained squeeze
+        cs2 = C.PlonkCircuit()
+        exp = cs2.create_public_variable(C.compute_poseidon_hash(xs))
+        C.PoseidonHashGadget(cs2.zero()).hash_constrained([cs2.create_variable(x) for x in xs], exp, cs2)
+        cs2.check_circuit_satisfiability(cs2.public_input())
+        with pytest.raises(C.CircuitError):
+            cs2.check_circuit_satisfiability([(cs2.public_input()[0] + 1) % C.R])
+
+
+def test_basic_gates_and_errors():
+    cs = C.PlonkCircuit()
+    a, b = cs.create_variable(11), cs.create_variable(C.R - 4)
+    assert cs.witness(cs.add(a, b)) == 7 and cs.witness(cs.sub(a, b)) == 15 and cs.witness(cs.mul(a, b)) == C.R - 44
+    assert cs.witness(cs.lc([a, b, cs.one(), cs.zero()], [2, 3, 5, 9])) == (22 - 12 + 5) % C.R
+    t, f = cs.create_boolean_variable(True), cs.create_boolean_variable(False)
+    assert cs.witness(cs.mux(t, a, b)) == 11 and cs.witness(cs.mux(f, a, b)) == C.R - 4
+    k = cs.create_constant_variable(99)
+    cs.enforce_equal(k, cs.add(cs.create_variable(90), cs.create_variable(9)))
+    cs.check_circuit_satisfiability([])
+    cs.witness_values[k] = 98                    # breaks its constant gate and the equality
+    with pytest.raises(C.CircuitError):
+        cs.check_circuit_satisfiability([])
+    with pytest.raises(C.CircuitError):
+        cs.insert_gate([0, 0, 0], C.AdditionGate())
+    with pytest.raises(C.CircuitError):
+        cs.witness(10 ** 9)
+    bad = C.PlonkCircuit()
+    nb = bad.create_variable(2)
+    bad.enforce_bool(nb)
+    with pytest.raises(C.CircuitError):
+        bad.check_circuit_satisfiability([])
+
+
+def merkle_case(height, leaf_len, seed):
+    rnd = random.Random(seed)
+    leaf = [rnd.randrange(C.R) for _ in range(leaf_len)]
+    opening = C.MerkleOpening([rnd.randrange(C.R) for _ in range(height)], [rnd.random() < 0.5 for _ in range(height)])
+    return leaf, opening
+
+
+def test_merkle_gadget_and_arithmetization(oracle, pyoracle):
+    py = pyoracle
+    leaf, opening = merkle_case(3, 3, seed=9)
+    cs, root = C.merkle_membership_circuit(leaf, opening)
+    assert root == C.native_merkle_root(leaf, opening)
+    cs.check_circuit_satisfiability([root])
+    with pytest.raises(C.CircuitError):
+        cs.check_circuit_satisfiability([(root + 1) % C.R])
+    circ = cs.finalize_for_arithmetization()
+    with pytest.raises(C.CircuitError):
+        cs.create_variable(1)                    # closed after finalisation, like upstream
+    n = circ.n
+    assert circ.num_inputs == 1 and circ.n_gates <= n < 2 * circ.n_gates
+    # IO gate first, every row satisfies the gate equation, the permutation is a bijection that preserves values
+    assert circ.selectors_int[synth.Q_O][0] == 1 and circ.wires_int[4][0] == root
+    for row in range(n):
+        pi = circ.pub_inputs_int[row] if row < circ.num_inputs else 0
+        assert synth.gate_value([circ.selectors_int[s][row] for s in range(13)],
+                                [circ.wires_int[w][row] for w in range(5)], pi) == 0, row
+    assert sorted(circ.perm.tolist()) == list(range(5 * n))
+    flat = [v for w in circ.wires_int for v in w]
+    assert all(flat[i] == flat[int(circ.perm[i])] for i in range(5 * n))
+    # the oracle prover proves it and the oracle verifier accepts; a wrong root is rejected
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, n + 3)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    bl = synth.splitmix_blinders(0xC1C)
+    rc, proof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl, srs)
+    assert rc == 0
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
+    wrong = synth.to_mont_array([(root + 1) % C.R])
+    assert not oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, wrong, proof, tau)
+    # a witness that breaks one gate is refused by the prover (WrongQuotientPolyDegree)
+    bad = circ.wires.copy()
+    bad[4, circ.n_gates - 2] = bad[4, circ.n_gates - 3]
+    rc, _, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, bad, circ.pub_inputs, bl, srs)
+    assert rc != 0

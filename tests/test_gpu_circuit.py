@@ -1,0 +1,42 @@
+"""GPU: a circuit with the reference's own gate structure — a height-10 Poseidon2 Merkle opening
+(`MERKLE_HEIGHT`, crates/constants/src/lib.rs:50; gadgets of circuits-core restated in renegade_b200/circuit.py, public
+root like the VALID-* statements) — proved on the device: proof bytes identical to the oracle prover's, accepted by the
+restated verifier, wrong root rejected."""
+import random
+
+import pytest
+
+from renegade_b200 import circuit as C
+from renegade_b200 import synth
+from renegade_b200.backend import PlonkKzgSnark
+
+pytestmark = pytest.mark.gpu
+
+TAU = 0x0f1e2d3c4b5a69788796a5b4c3d2e1f00123456789abcdef0fedcba987654321
+
+
+def test_merkle_opening_circuit_proves_on_device(ctx, oracle, pyoracle):
+    py = pyoracle
+    rnd = random.Random(0x3E7)
+    height = 10
+    leaf = [rnd.randrange(C.R) for _ in range(4)]
+    opening = C.MerkleOpening([rnd.randrange(C.R) for _ in range(height)], [rnd.random() < 0.5 for _ in range(height)])
+    cs, root = C.merkle_membership_circuit(leaf, opening)
+    cs.check_circuit_satisfiability([root])
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == 12 and circ.num_inputs == 1     # 11 hashes x (195 + a few) gates
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    bases = ctx.load_bases(srs)
+    pk = PlonkKzgSnark.preprocess(ctx, bases, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    assert (pk.selector_comms == opk["selector_comms"]).all() and (pk.sigma_comms == opk["sigma_comms"]).all()
+    bl = synth.splitmix_blinders(0x10)
+    proof, _ = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+    rc, oproof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl, srs)
+    assert rc == 0 and (proof.to_array() == oproof.to_array()).all()
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs,
+                                         oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
+    wrong = synth.to_mont_array([(root + 1) % C.R])
+    assert not oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, wrong,
+                                             oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
