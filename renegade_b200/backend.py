@@ -428,6 +428,13 @@ def poseidon2_permute_batch(ctx: Context, states: np.ndarray) -> np.ndarray:
     return s
 
 
+# ---- names the reference gives these objects (circuit-types/src/lib.rs:72-101) ------------
+PlonkProof = B200Proof                 # `pub type PlonkProof = Proof<SystemCurve>`
+PlonkLinkProof = B200LinkProof         # `pub type PlonkLinkProof = LinkingProof<SystemCurve>`
+ProofLinkingHint = LinkingHint         # `pub type ProofLinkingHint = LinkingHint<SystemCurve>`
+ProverError = _lib.B200Error           # circuit-types/src/errors.rs:33-58: a failing prove surfaces as an error value
+
+
 class ProverPool:
     """b200_pool: the device-side counterpart of the reference's `NativeProofManager` thread pool
     (crates/workers/proof-manager/src/implementations/native_proof_manager.rs:138-201, `spawn_fifo`

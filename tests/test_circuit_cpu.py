@@ -132,3 +132,29 @@ def test_merkle_gadget_and_arithmetization(oracle, pyoracle):
     bad[4, circ.n_gates - 2] = bad[4, circ.n_gates - 3]
     rc, _, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, bad, circ.pub_inputs, bl, srs)
     assert rc != 0
+
+
+def test_field_helpers(pyoracle, oracle):
+    """crypto::fields (fields.rs:21-163) restated: moduli, big-endian truncations, signed conversion, and the ABI's
+    Montgomery limbs against the oracle's own conversion."""
+    from renegade_b200 import fields as F
+    py = pyoracle
+    assert F.get_scalar_field_modulus() == py.R and F.get_base_field_modulus() == py.Q
+    v = 0x1234_5678_9ABC_DEF0_0FED_CBA9_8765_4321_1122_3344_5566_7788_99AA_BBCC_DDEE_FF00 % py.R
+    be = F.scalar_to_bytes_be(v)
+    assert len(be) == 32 and int.from_bytes(be, "big") == v
+    assert F.scalar_to_u64(v) == v & ((1 << 64) - 1) and F.scalar_to_u128(v) == v & ((1 << 128) - 1)
+    assert F.scalar_to_address(v) == be[12:] and F.address_to_scalar(be[12:]) == v & ((1 << 160) - 1)
+    assert F.scalar_to_u256(v) == v and F.u256_to_scalar((1 << 256) - 1) == ((1 << 256) - 1) % py.R
+    assert F.bigint_to_scalar(-5) == py.R - 5 and F.bigint_to_scalar(5) == 5 and F.bigint_to_scalar(-py.R) == 0
+    assert F.biguint_to_scalar(py.R + 3) == 3
+    with pytest.raises(ValueError):
+        F.biguint_to_scalar(-1)
+    assert F.bigint_to_scalar_bits(0b1011, 6) == [1, 1, 0, 1, 0, 0]
+    vals = [0, 1, py.R - 1, v]
+    limbs = F.scalars_to_limbs(vals)
+    assert (limbs == oracle.ints_to_array([py.to_mont(x, py.R) for x in vals])).all()
+    assert F.limbs_to_scalars(limbs) == vals
+    assert (F.scalars_to_limbs(vals) == synth.to_mont_array(vals)).all()
+    q = [2, py.Q - 1]
+    assert F.limbs_to_scalars(F.scalars_to_limbs(q, py.Q), py.Q) == q
