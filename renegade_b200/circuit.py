@@ -152,6 +152,15 @@ class _Row:
     gate: Gate
 
 
+@dataclass
+class GroupLayout:
+    """mpc-relation `GroupLayout` (what `get_circuit_layout`, traits.rs:914-946, reports per link group): element i of
+    the group sits on wire 0 of the row whose domain point is the (offset + i)-th 2^alignment-th root of unity."""
+    alignment: int
+    offset: int
+    size: int = 0
+
+
 class PlonkCircuit:
     """mpc-relation `PlonkCircuit<ScalarField>`: variable 0 is the constant zero, variable 1 the constant one
     (each pinned by a constant gate, as upstream's `new()` does)."""
@@ -160,6 +169,7 @@ class PlonkCircuit:
         self.witness_values: List[int] = []
         self.rows: List[_Row] = []
         self.pub_input_vars: List[Variable] = []
+        self.link_groups = {}      # id -> (GroupLayout, [variables])
         self._finalized = False
         self._zero = self.create_variable(0)
         self._one = self.create_variable(1)
@@ -183,6 +193,30 @@ class PlonkCircuit:
         self.pub_input_vars.append(var)
         self.rows.append(_Row([self._zero] * GATE_WIDTH + [var], IoGate()))
         return var
+
+    def create_link_group(self, group_id: str, layout: GroupLayout) -> str:
+        """mpc-relation `create_link_group(id, Some(layout))`: variables added to the group occupy wire 0 of the rows
+        the layout names, so that two circuits placing the same values there can be proof-linked
+        (`PlonkKzgSnark::link_proofs`, proof_linking/intent_only.rs:42-47)."""
+        self._check_open()
+        if group_id in self.link_groups:
+            raise CircuitError(f"link group {group_id} already exists")
+        self.link_groups[group_id] = (GroupLayout(layout.alignment, layout.offset, 0), [])
+        return group_id
+
+    def create_variable_with_link_groups(self, val: int, groups: Sequence[str]) -> Variable:
+        var = self.create_variable(val)
+        for g in groups:
+            if g not in self.link_groups:
+                raise CircuitError(f"unknown link group {g}")
+            layout, members = self.link_groups[g]
+            members.append(var)
+            layout.size = len(members)
+        return var
+
+    def get_circuit_layout(self) -> dict:
+        """`get_circuit_layout` (traits.rs:914-946): the placement of every link group."""
+        return {g: GroupLayout(l.alignment, l.offset, l.size) for g, (l, _) in self.link_groups.items()}
 
     def create_constant_variable(self, val: int) -> Variable:
         var = self.create_variable(val)
@@ -278,11 +312,28 @@ class PlonkCircuit:
         self._check_open()
         io = [r for r in self.rows if r.gate.name == "IoGate"]
         rest = [r for r in self.rows if r.gate.name != "IoGate"]
-        rows = io + rest
-        n_gates = len(rows)
-        log_n = max(min_log_n, (n_gates - 1).bit_length())
-        n = 1 << log_n
-        rows = rows + [_Row([self._zero] * (GATE_WIDTH + 1), PaddingGate()) for _ in range(n - n_gates)]
+        n_link = sum(len(m) for _, m in self.link_groups.values())
+        n_gates = len(io) + len(rest) + n_link
+        log_n = max([min_log_n, (n_gates - 1).bit_length()] + [l.alignment for l, _ in self.link_groups.values()])
+        while True:  # link rows are pinned to domain positions; everything else flows around them
+            n = 1 << log_n
+            pinned = {}
+            for gid, (l, members) in self.link_groups.items():
+                for i, var in enumerate(members):
+                    row = (l.offset + i) << (log_n - l.alignment)
+                    if row >= n or row < len(io) or row in pinned:
+                        raise CircuitError(f"link group {gid}: row {row} is outside the domain or already taken")
+                    pinned[row] = var
+            if n - len(pinned) >= len(io) + len(rest):
+                break
+            log_n += 1
+        rows: List[_Row] = []
+        pending = iter(io + rest)
+        for r in range(n):
+            if r in pinned:  # link gate: the value on wire 0, no constraint of its own
+                rows.append(_Row([pinned[r]] + [self._zero] * GATE_WIDTH, Gate("LinkGate")))
+            else:
+                rows.append(next(pending, None) or _Row([self._zero] * (GATE_WIDTH + 1), PaddingGate()))
         sel = [[0] * n for _ in range(N_SELECTORS)]
         wire_var = [[0] * n for _ in range(N_WIRES)]
         positions: List[List] = [[] for _ in self.witness_values]

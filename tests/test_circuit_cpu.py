@@ -158,3 +158,57 @@ def test_field_helpers(pyoracle, oracle):
     assert (F.scalars_to_limbs(vals) == synth.to_mont_array(vals)).all()
     q = [2, py.Q - 1]
     assert F.limbs_to_scalars(F.scalars_to_limbs(q, py.Q), py.Q) == q
+
+
+def test_link_groups_place_shared_values_and_link_on_the_oracle(oracle, pyoracle):
+    """Two circuits of different sizes put the same witness values into a link group with the same layout
+    (`create_link_group` / `create_variable_with_link_groups`, the way the reference's validity and settlement
+    circuits share a balance or an intent); `get_circuit_layout` reports it; the oracle proves both, links the two
+    hints (`PlonkKzgSnark::link_proofs`) and its link verifier accepts — and rejects when one circuit holds a
+    different value."""
+    py = pyoracle
+    layout = C.GroupLayout(alignment=6, offset=10)
+    shared = [(i * 0x9E3779B97F4A7C15 + 7) % C.R for i in range(5)]
+
+    def build(n_hashes, values):
+        cs = C.PlonkCircuit()
+        cs.create_link_group("shared_state", layout)
+        vars_ = [cs.create_variable_with_link_groups(v, ["shared_state"]) for v in values]
+        out = cs.create_public_variable(0)      # placeholder value, fixed below
+        acc = vars_
+        for _ in range(n_hashes):               # some constraints that consume the shared values
+            acc = [C.PoseidonHashGadget(cs.zero()).hash(acc, cs)] + vars_[1:]
+        cs.witness_values[out] = cs.witness(acc[0])
+        cs.enforce_equal(out, acc[0])
+        cs.check_circuit_satisfiability(cs.public_input())
+        lay = cs.get_circuit_layout()["shared_state"]
+        assert (lay.alignment, lay.offset, lay.size) == (6, 10, 5)
+        return cs.finalize_for_arithmetization()
+
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    circs = [build(1, shared), build(3, shared), build(1, shared[:4] + [shared[4] + 1])]
+    assert circs[0].log_n != circs[1].log_n
+    srs = oracle.srs_from_tau(tau, max(c.n for c in circs) + 3)
+    hints = []
+    for i, circ in enumerate(circs):
+        for j, v in enumerate(shared if i < 2 else shared[:4] + [(shared[4] + 1) % C.R]):
+            assert circ.wires_int[0][(layout.offset + j) << (circ.log_n - layout.alignment)] == v
+        opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs[:circ.n + 3])
+        rc, proof, _, link = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                                synth.splitmix_blinders(60 + i), srs[:circ.n + 3], True)
+        assert rc == 0
+        assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
+        hints.append((link, proof.to_array()[:8].copy()))
+    for other, ok in ((1, True), (2, False)):
+        rc, lp, _ = oracle.plonk_link(hints[0][0], hints[other][0], hints[0][1], hints[other][1], layout.alignment,
+                                      layout.offset, len(shared), srs)
+        assert rc == 0
+        assert oracle.plonk_link_verify_known_tau(hints[0][1], hints[other][1], layout.alignment, layout.offset,
+                                                  len(shared), lp, tau) == ok
+    # a layout that collides with the public-input rows is refused
+    bad = C.PlonkCircuit()
+    bad.create_link_group("g", C.GroupLayout(alignment=3, offset=0))
+    bad.create_variable_with_link_groups(5, ["g"])
+    bad.create_public_variable(1)
+    with pytest.raises(C.CircuitError):
+        bad.finalize_for_arithmetization()
