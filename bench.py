@@ -97,6 +97,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def make_circuit(kind, log_n, seed):
+    """The proved circuit.  "synthetic" (default): renegade_b200/synth.py, random gates of the reference's mix.
+    "merkle": as many height-10 Poseidon2 Merkle openings (the reference's gadgets restated in
+    renegade_b200/circuit.py, public roots) as fit the domain — 27 at n = 2^16; same prover work, real constraints."""
+    from renegade_b200 import synth
+    if kind == "synthetic":
+        return synth.synth_circuit(log_n, num_inputs=NUM_INPUTS, seed=seed)
+    import random
+    from renegade_b200 import circuit as cb
+    rnd = random.Random(seed)
+    cs = cb.PlonkCircuit()
+    per_opening = 2400  # 11 sponge hashes of 195-gate permutations plus selects and additions
+    while cs.num_gates + per_opening + 1 <= (1 << log_n):
+        leaf = [rnd.randrange(cb.R) for _ in range(4)]
+        opening = cb.MerkleOpening([rnd.randrange(cb.R) for _ in range(10)], [rnd.random() < 0.5 for _ in range(10)])
+        root = cs.create_public_variable(cb.native_merkle_root(leaf, opening))
+        op = cb.MerkleOpeningVar([cs.create_variable(v) for v in opening.elems],
+                                 [cs.create_boolean_variable(b) for b in opening.indices])
+        cb.PoseidonMerkleHashGadget.compute_and_constrain_root([cs.create_variable(v) for v in leaf], op, root, cs)
+    return cs.finalize_for_arithmetization(min_log_n=log_n)
+
+
 def base_line(args, world):
     return {"metric": METRIC, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -116,7 +138,7 @@ def run_reference(args, rank, world):
     log_n = LOG_N
     while True:
         n = 1 << log_n
-        circ = synth.synth_circuit(log_n, num_inputs=NUM_INPUTS, seed=CIRCUIT_SEED)
+        circ = make_circuit(args.circuit, log_n, CIRCUIT_SEED)
         srs = oracle_c.known_dlog_bases(SEED_SRS, n + 3)
         pk = oracle_c.plonk_preprocess(log_n, circ.selectors, circ.perm, circ.k, srs)
         bl = synth.splitmix_blinders(1)
@@ -163,6 +185,9 @@ def main():
     ap.add_argument("--msm-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm", action="store_true")
+    ap.add_argument("--circuit", choices=("synthetic", "merkle"), default="synthetic",
+                    help="synthetic: random gates of the reference's mix (default); merkle: height-10 Poseidon2 Merkle "
+                         "openings built with the reference's gadgets (renegade_b200/circuit.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -210,7 +235,7 @@ def main():
     pool = ProverPool(local_rank, workers=conc) if conc > 1 else None
     ctxs = [pool.context(i) for i in range(conc)] if pool else [rb.Context(local_rank)]
     ctx = ctxs[0]
-    circ = synth.synth_circuit(LOG_N, num_inputs=NUM_INPUTS, seed=CIRCUIT_SEED + rank)
+    circ = make_circuit(args.circuit, LOG_N, CIRCUIT_SEED + rank)
     d_srs = torch.empty((n + 3, 8), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
     # any n + 3 valid G1 points cost the same as a powers-of-tau SRS (the reference's real SRS file
@@ -410,7 +435,7 @@ def main():
     out = base_line(args, world)
     out.update({
         "value": world * args.steps / dt, "ms_per_step": ms_step,
-        "config": {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": NUM_INPUTS, "gates_used": circ.n_gates,
+        "config": {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": circ.num_inputs, "gates_used": circ.n_gates, "circuit": args.circuit,
                    "concurrency_per_gpu": conc, "parallelism": "one proof stream per GPU (replicas, no collective)",
                    "msm_plan": srs.plan,
                    "l2": "working set > L2: shared key tables 227 MB + SRS window tables 67 MB, plus per proof in flight "
@@ -425,7 +450,7 @@ def main():
                      "note": "integer-multiply-pipe bound: ~9.5 Fq product-equivalents per bucket addition, one addition per "
                              "window digit (16 per scalar); `achieved` is in situ (several proofs share the SMs), "
                              "`achieved_kernel_alone` the same kernel timed alone; see DESIGN.md for the INT-pipe roofline"},
-        "e2e": {"value": world * args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": 5 * n * 32 + NUM_INPUTS * 32 + 17 * 32,
+        "e2e": {"value": world * args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": 5 * n * 32 + circ.num_inputs * 32 + 17 * 32,
                 "d2h_bytes_per_step": 1152, "ms_per_step": dt_e2e / args.steps * 1e3},
         # 113 kernel launches per proof (ncu launch list -> tools/kernel_shares.py,
         # profiles/r1r_proof_kernel_shares.txt): 4 batched commitments x 17 kernels + NTT passes, coset

@@ -7,7 +7,6 @@ prover is bit-exact with."""
 import os
 import random
 
-import numpy as np
 import pytest
 
 from renegade_b200 import circuit as C
