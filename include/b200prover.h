@@ -214,7 +214,7 @@ int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]);
  * queue drained by `n_workers` host threads, each owning one context on `device`.  Proving keys
  * and SRS tables are shared read-only, so `n_workers` proofs are in flight on one GPU and the
  * latency-bound parts of one overlap the throughput-bound kernels of the others (1 -> 6 workers:
- * 138 -> 214 proofs/s at n = 2^16 on one B200).
+ * 149 -> 269 proofs/s at n = 2^16 on one B200).
  * Ownership: `pub_inputs` and `blinders` are copied at submit; `wires`, the link polynomials and
  * every output buffer stay owned by the caller and must remain valid until the job's ticket has
  * been waited for.  Any thread may submit or wait. */
