@@ -13,6 +13,8 @@ structure instead of random tables:
     `FusedInternalSboxMDSGate`   circuits-core/src/zk_gadgets/primitives/poseidon/gates.rs:27-100, 117-179
   * `PoseidonHashGadget`         .../poseidon/hash.rs:56-423 (195 gates per permutation)
   * `PoseidonMerkleHashGadget`   .../primitives/merkle.rs:13-126
+  * `ToBitsGadget`, `BitRangeGadget`                       .../primitives/bits.rs:22-110
+  * `EqZeroGadget`, `GreaterThanEq(Zero)Gadget`            .../primitives/comparators.rs:17-260
   * `Poseidon2Sponge`,
     `compute_poseidon_hash`      crates/crypto/src/hash/poseidon2.rs:25-209, hash/mod.rs:12-18 (native, for witnesses)
 
@@ -98,6 +100,15 @@ def EqualityGate() -> Gate:
 def BoolGate() -> Gate:
     """wires (a, a, 0, 0, a): a * a = a."""
     return Gate("BoolGate", q_mul=(1, 0), q_o=1)
+
+
+def MulAddGate(q_mul: Sequence[int]) -> Gate:
+    """wires (a, b, c, d, out): q0 * a * b + q1 * c * d = out."""
+    return Gate("MulAddGate", q_mul=tuple(q_mul), q_o=1)
+
+
+def ConstantAdditionGate(c: int) -> Gate:
+    return Gate("ConstantAdditionGate", q_lc=(1, 0, 0, 0), q_c=c, q_o=1)
 
 
 def MuxGate() -> Gate:
@@ -277,6 +288,40 @@ class PlonkCircuit:
         """if sel { a } else { b } (sel must be boolean-constrained by the caller, as `BoolVar` guarantees upstream)."""
         s, va, vb = self.witness(sel), self.witness(a), self.witness(b)
         return self._out([sel, a, sel, b], MuxGate(), s * va + (1 - s) * vb)
+
+    def add_constant(self, a: Variable, c: int) -> Variable:
+        return self._out([a, self._zero, self._zero, self._zero], ConstantAdditionGate(c), self.witness(a) + c)
+
+    def lc_sum(self, vars_: Sequence[Variable], coeffs: Sequence[int]) -> Variable:
+        """sum_i coeffs[i] * vars[i] with GATE_WIDTH-input linear-combination gates: the first gate takes four terms,
+        every further gate the running sum and three more (upstream `lc_sum`)."""
+        if len(vars_) != len(coeffs):
+            raise CircuitError("lc_sum takes as many coefficients as variables")
+        if not vars_:
+            return self._zero
+        pad = lambda v, c: (list(v) + [self._zero] * (GATE_WIDTH - len(v)), list(c) + [0] * (GATE_WIDTH - len(c)))
+        w, c = pad(vars_[:GATE_WIDTH], coeffs[:GATE_WIDTH])
+        acc = self.lc(w, c)
+        i = GATE_WIDTH
+        while i < len(vars_):
+            w, c = pad([acc] + list(vars_[i:i + GATE_WIDTH - 1]), [1] + list(coeffs[i:i + GATE_WIDTH - 1]))
+            acc = self.lc(w, c)
+            i += GATE_WIDTH - 1
+        return acc
+
+    def sum(self, vars_: Sequence[Variable]) -> Variable:
+        return self.lc_sum(vars_, [1] * len(vars_))
+
+    def mul_gate(self, a: Variable, b: Variable, c: Variable) -> None:
+        """enforce a * b = c."""
+        self.insert_gate([a, b, self._zero, self._zero, c], MultiplicationGate())
+
+    def mul_add_gate(self, wires: Sequence[Variable], q_mul: Sequence[int]) -> None:
+        """enforce q0 * w0 * w1 + q1 * w2 * w3 = w4."""
+        self.insert_gate(wires, MulAddGate(q_mul))
+
+    def enforce_true(self, b: Variable) -> None:
+        self.enforce_constant(b, 1)
 
     def enforce_equal(self, a: Variable, b: Variable) -> None:
         self.insert_gate([a, b, self._zero, self._zero, self._zero], EqualityGate())
@@ -510,6 +555,71 @@ class PoseidonHashGadget:
             out = cs.create_variable(gate.compute_output(vals[i], *vals))
             cs.insert_gate([in_wires[i]] + in_wires + [out], gate)
             self.state[i] = out
+
+
+def scalar_to_bits_le(a: int, n: int) -> List[int]:
+    """bits.rs:12-21: the low n bits, little-endian (zero-extended)."""
+    return [(a >> i) & 1 for i in range(n)]
+
+
+class ToBitsGadget:
+    """bits.rs:22-78."""
+
+    @staticmethod
+    def to_bits(a: Variable, num_bits: int, cs: PlonkCircuit) -> List[Variable]:
+        bits = [cs.create_boolean_variable(b) for b in scalar_to_bits_le(cs.witness(a), num_bits)]
+        cs.enforce_equal(ToBitsGadget.bit_reconstruct(bits, cs), a)
+        return bits
+
+    @staticmethod
+    def bit_reconstruct(bits: Sequence[Variable], cs: PlonkCircuit) -> Variable:
+        return cs.lc_sum(bits, [1 << i for i in range(len(bits))])
+
+
+class BitRangeGadget:
+    """bits.rs:80-95: a in [0, 2^num_bits)."""
+
+    @staticmethod
+    def constrain_bit_range(a: Variable, num_bits: int, cs: PlonkCircuit) -> None:
+        ToBitsGadget.to_bits(a, num_bits, cs)
+
+
+class EqZeroGadget:
+    """comparators.rs:17-60: is_zero = 1 - val * inv and is_zero * val = 0."""
+
+    @staticmethod
+    def eq_zero_var(val: Variable, cs: PlonkCircuit) -> Variable:
+        v = cs.witness(val)
+        is_zero = cs.create_variable(1 if v == 0 else 0)
+        inv = cs.create_variable(0 if v == 0 else pow(v, -1, R))
+        cs.mul_add_gate([val, inv, cs.one(), cs.one(), is_zero], [-1, 1])
+        cs.mul_gate(is_zero, val, cs.zero())
+        return is_zero
+
+
+class GreaterThanEqZeroGadget:
+    """comparators.rs:183-234: for x in [-2^D, 2^D), x >= 0 iff bit D of x + 2^D is set."""
+
+    @staticmethod
+    def greater_than_eq_zero(x: Variable, num_bits: int, cs: PlonkCircuit) -> Variable:
+        shifted = cs.add_constant(x, 1 << num_bits)
+        return ToBitsGadget.to_bits(shifted, num_bits + 1, cs)[num_bits]
+
+    @staticmethod
+    def constrain_greater_than_eq_zero(x: Variable, num_bits: int, cs: PlonkCircuit) -> None:
+        ToBitsGadget.to_bits(x, num_bits, cs)
+
+
+class GreaterThanEqGadget:
+    """comparators.rs:236-262: a >= b for values of at most num_bits bits."""
+
+    @staticmethod
+    def greater_than_eq(a: Variable, b: Variable, num_bits: int, cs: PlonkCircuit) -> Variable:
+        return GreaterThanEqZeroGadget.greater_than_eq_zero(cs.sub(a, b), num_bits, cs)
+
+    @staticmethod
+    def constrain_greater_than_eq(a: Variable, b: Variable, num_bits: int, cs: PlonkCircuit) -> None:
+        GreaterThanEqZeroGadget.constrain_greater_than_eq_zero(cs.sub(a, b), num_bits, cs)
 
 
 @dataclass
