@@ -15,6 +15,10 @@ structure instead of random tables:
   * `PoseidonMerkleHashGadget`   .../primitives/merkle.rs:13-126
   * `ToBitsGadget`, `BitRangeGadget`                       .../primitives/bits.rs:22-110
   * `EqZeroGadget`, `GreaterThanEq(Zero)Gadget`            .../primitives/comparators.rs:17-260
+  * `CSPRNGGadget`, `StreamCipherGadget`, `RecoveryIdGadget`,
+    `CommitmentGadget`, `AmountGadget`                     .../state_primitives/{csprng,stream_cipher,recovery_id,
+                                                           commitment}.rs, primitives/bitlength.rs
+  * `PoseidonCSPRNG`, `StateWrapper`                       darkpool-types/src/{csprng,state_wrapper}.rs (native side)
   * `Poseidon2Sponge`,
     `compute_poseidon_hash`      crates/crypto/src/hash/poseidon2.rs:25-209, hash/mod.rs:12-18 (native, for witnesses)
 
@@ -620,6 +624,132 @@ class GreaterThanEqGadget:
     @staticmethod
     def constrain_greater_than_eq(a: Variable, b: Variable, num_bits: int, cs: PlonkCircuit) -> None:
         GreaterThanEqZeroGadget.constrain_greater_than_eq_zero(cs.sub(a, b), num_bits, cs)
+
+
+# ---- state primitives: CSPRNG streams, stream cipher, recovery ids, commitments ---------------------------
+AMOUNT_BITS = 100  # circuit-types/src/lib.rs:59
+
+
+@dataclass
+class PoseidonCSPRNG:
+    """darkpool-types/src/csprng.rs:30-75: value i of the stream is H(seed, i)."""
+    seed: int
+    index: int = 0
+
+    def next(self) -> int:
+        out = compute_poseidon_hash([self.seed, self.index])
+        self.index += 1
+        return out
+
+    def get_ith(self, i: int) -> int:
+        return compute_poseidon_hash([self.seed, i])
+
+    def to_scalars(self) -> List[int]:
+        return [self.seed, self.index]
+
+    def stream_cipher_encrypt(self, values: Sequence[int]) -> List[int]:
+        """csprng.rs:62-74: ciphertext = value - pad, one fresh pad per value."""
+        return [(v - self.next()) % R for v in values]
+
+
+@dataclass
+class StateWrapper:
+    """darkpool-types/src/state_wrapper.rs:60-190 for an element given as its scalar serialisation."""
+    recovery_stream: PoseidonCSPRNG
+    share_stream: PoseidonCSPRNG
+    inner: List[int]
+    public_share: List[int]
+
+    @staticmethod
+    def new(inner: Sequence[int], share_stream_seed: int, recovery_stream_seed: int) -> "StateWrapper":
+        share = PoseidonCSPRNG(share_stream_seed)
+        public = share.stream_cipher_encrypt(inner)
+        return StateWrapper(PoseidonCSPRNG(recovery_stream_seed), share, list(inner), public)
+
+    def private_shares(self) -> List[int]:
+        return [(v - p) % R for v, p in zip(self.inner, self.public_share)]
+
+    def compute_recovery_id(self) -> int:
+        return self.recovery_stream.next()
+
+    def compute_private_commitment(self) -> int:
+        return compute_poseidon_hash(self.private_shares() + self.recovery_stream.to_scalars() + self.share_stream.to_scalars())
+
+    def compute_commitment(self) -> int:
+        comm = self.public_share[0]
+        for share in self.public_share[1:]:
+            comm = compute_poseidon_hash([comm, share])
+        return compute_poseidon_hash([self.compute_private_commitment(), comm])
+
+
+@dataclass
+class PoseidonCSPRNGVar:
+    seed: Variable
+    index: Variable
+
+    def to_vars(self) -> List[Variable]:
+        return [self.seed, self.index]
+
+
+class CSPRNGGadget:
+    """state_primitives/csprng.rs:9-47."""
+
+    @staticmethod
+    def next(state: PoseidonCSPRNGVar, cs: PlonkCircuit) -> Variable:
+        value = PoseidonHashGadget(cs.zero()).hash([state.seed, state.index], cs)
+        state.index = cs.add(state.index, cs.one())
+        return value
+
+    @staticmethod
+    def next_k(state: PoseidonCSPRNGVar, k: int, cs: PlonkCircuit) -> List[Variable]:
+        return [CSPRNGGadget.next(state, cs) for _ in range(k)]
+
+
+class StreamCipherGadget:
+    """state_primitives/stream_cipher.rs:13-33: returns (private share = the pads, public share = value - pad)."""
+
+    @staticmethod
+    def encrypt(value_vars: Sequence[Variable], state: PoseidonCSPRNGVar, cs: PlonkCircuit):
+        pads = CSPRNGGadget.next_k(state, len(value_vars), cs)
+        return pads, [cs.sub(v, p) for v, p in zip(value_vars, pads)]
+
+
+class RecoveryIdGadget:
+    """state_primitives/recovery_id.rs:9-20."""
+
+    @staticmethod
+    def compute_recovery_id(recovery_stream: PoseidonCSPRNGVar, cs: PlonkCircuit) -> Variable:
+        return CSPRNGGadget.next(recovery_stream, cs)
+
+
+class CommitmentGadget:
+    """state_primitives/commitment.rs:33-95, 433-446."""
+
+    @staticmethod
+    def compute_commitment(private_share: Sequence[Variable], recovery_stream: PoseidonCSPRNGVar,
+                           share_stream: PoseidonCSPRNGVar, public_share: Sequence[Variable], cs: PlonkCircuit) -> Variable:
+        hasher = PoseidonHashGadget(cs.zero())
+        hasher.batch_absorb(list(private_share) + recovery_stream.to_vars() + share_stream.to_vars(), cs)
+        private_commitment = hasher.squeeze(cs)
+        public_commitment = CommitmentGadget.compute_resumable_commitment(public_share, cs)
+        return PoseidonHashGadget(cs.zero()).hash([private_commitment, public_commitment], cs)
+
+    @staticmethod
+    def compute_resumable_commitment(values: Sequence[Variable], cs: PlonkCircuit) -> Variable:
+        if not values:
+            raise CircuitError("Cannot compute a resumable commitment with no values")
+        comm = values[0]
+        for value in values[1:]:
+            comm = PoseidonHashGadget(cs.zero()).hash([comm, value], cs)
+        return comm
+
+
+class AmountGadget:
+    """primitives/bitlength.rs:9-17."""
+
+    @staticmethod
+    def constrain_valid_amount(amount: Variable, cs: PlonkCircuit) -> None:
+        BitRangeGadget.constrain_bit_range(amount, AMOUNT_BITS, cs)
 
 
 @dataclass

@@ -250,3 +250,37 @@ def test_bits_and_comparator_gadgets():
         assert cs.witness(ge) == int(a >= b)
         cs.check_circuit_satisfiability([])
         assert sat(lambda c: C.GreaterThanEqGadget.constrain_greater_than_eq(c.create_variable(a), c.create_variable(b), 64, c)) == (a >= b)
+
+
+def test_valid_balance_create_circuit(oracle, pyoracle):
+    """BASELINE.json configs[0]: VALID BALANCE CREATE restated (renegade_b200/valid_balance_create.py).  The native
+    witness / statement satisfy the circuit; every statement field is binding; the domain is 2^13; the oracle
+    prover proves it and the oracle verifier accepts."""
+    from renegade_b200 import valid_balance_create as vbc
+    py = pyoracle
+    witness, statement = vbc.create_witness_statement(seed=7)
+    assert statement.recovery_id == witness.initial_recovery_stream.get_ith(witness.initial_recovery_stream.index)
+    assert witness.initial_share_stream.index == 8 and len(statement.to_scalars()) == 13
+    cs = vbc.ValidBalanceCreate.build(witness, statement)
+    pub = statement.to_scalars()
+    assert cs.public_input() == pub
+    cs.check_circuit_satisfiability(pub)
+    for i in range(len(pub)):                     # no statement field is free
+        bad = list(pub)
+        bad[i] = (bad[i] + 1) % C.R
+        with pytest.raises(C.CircuitError):
+            cs.check_circuit_satisfiability(bad)
+    # a witness whose fee balance is not zero does not satisfy the circuit even with a consistent statement
+    w2, s2 = vbc.create_witness_statement(seed=8)
+    w2.balance.relayer_fee_balance = 5
+    with pytest.raises(C.CircuitError):
+        vbc.ValidBalanceCreate.build(w2, s2).check_circuit_satisfiability(s2.to_scalars())
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == 13 and circ.num_inputs == 13 and 4500 < circ.n_gates < 5200
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    rc, proof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                         synth.splitmix_blinders(0xBA1), srs)
+    assert rc == 0
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)

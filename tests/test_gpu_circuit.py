@@ -40,3 +40,27 @@ def test_merkle_opening_circuit_proves_on_device(ctx, oracle, pyoracle):
     wrong = synth.to_mont_array([(root + 1) % C.R])
     assert not oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, wrong,
                                              oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
+
+
+def test_valid_balance_create_proves_on_device(ctx, oracle, pyoracle):
+    """BASELINE.json configs[0]: the VALID BALANCE CREATE circuit (restated in renegade_b200/valid_balance_create.py,
+    n = 2^13, 13 public inputs) — device proof bytes = oracle proof bytes, verifier accepts."""
+    from renegade_b200 import valid_balance_create as vbc
+    py = pyoracle
+    witness, statement = vbc.create_witness_statement(seed=0xB200)
+    cs = vbc.ValidBalanceCreate.build(witness, statement)
+    cs.check_circuit_satisfiability(statement.to_scalars())
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == 13 and circ.num_inputs == 13
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    bases = ctx.load_bases(srs)
+    pk = PlonkKzgSnark.preprocess(ctx, bases, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    assert (pk.selector_comms == opk["selector_comms"]).all() and (pk.sigma_comms == opk["sigma_comms"]).all()
+    bl = synth.splitmix_blinders(0x11)
+    proof, _ = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+    rc, oproof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl, srs)
+    assert rc == 0 and (proof.to_array() == oproof.to_array()).all()
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs,
+                                         oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
