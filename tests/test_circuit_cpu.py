@@ -284,3 +284,90 @@ def test_valid_balance_create_circuit(oracle, pyoracle):
                                          synth.splitmix_blinders(0xBA1), srs)
     assert rc == 0
     assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
+
+
+def test_private_settlement_circuit(oracle, pyoracle):
+    """BASELINE.json configs[3]'s statement, INTENT AND BALANCE PRIVATE SETTLEMENT, restated
+    (renegade_b200/private_settlement.py): a consistent two-party match satisfies it, each rule it encodes is binding,
+    it has 17 public inputs and four link groups, and it is a 2^12-gate circuit; the oracle proves and verifies it."""
+    from renegade_b200 import private_settlement as ps
+    py = pyoracle
+    parties, statement = ps.create_witness_statement(seed=11)
+    build = ps.IntentAndBalancePrivateSettlementCircuit.build
+    cs = build(parties, statement)
+    pub = statement.to_scalars()
+    assert len(pub) == 17 and cs.public_input() == pub
+    cs.check_circuit_satisfiability(pub)
+    assert {g: l.size for g, l in cs.get_circuit_layout().items()} == {
+        ps.PARTY_LINKS[0]: 17, ps.PARTY_LINKS[1]: 17, ps.OUTPUT_LINKS[0]: 11, ps.OUTPUT_LINKS[1]: 11}
+    for i in range(14):                                  # share updates are pinned by the statement
+        bad = list(pub)
+        bad[i] = (bad[i] + 1) % C.R
+        with pytest.raises(C.CircuitError):
+            cs.check_circuit_satisfiability(bad)
+
+    def broken(mutate):
+        p, s = ps.create_witness_statement(seed=11)
+        mutate(p, s)
+        try:
+            build(p, s).check_circuit_satisfiability(s.to_scalars())
+            return False
+        except C.CircuitError:
+            return True
+    assert broken(lambda p, s: setattr(p[0].settlement_obligation, "amount_out", p[0].settlement_obligation.amount_out + 1))
+    assert broken(lambda p, s: setattr(p[1].intent, "amount_in", p[1].settlement_obligation.amount_in - 1))   # overfill
+    assert broken(lambda p, s: setattr(p[0].intent, "min_price", p[0].intent.min_price * 4))                  # bad price
+    assert broken(lambda p, s: setattr(p[0].input_balance, "amount", p[0].settlement_obligation.amount_in - 1))
+    assert broken(lambda p, s: setattr(p[1].output_balance, "owner", p[1].output_balance.owner ^ 1))
+    assert broken(lambda p, s: setattr(p[0].output_balance, "amount", (1 << 100) - 1))                        # overflow
+    assert broken(lambda p, s: setattr(s, "protocol_fee", s.protocol_fee + (1 << 40)))                       # fee take changes
+
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == 12 and circ.num_inputs == 17 and 2600 < circ.n_gates < 3000
+    for gid, lay in cs.get_circuit_layout().items():     # the link values sit where the layout says
+        vals = {ps.PARTY_LINKS[0]: parties[0], ps.PARTY_LINKS[1]: parties[1]}.get(gid)
+        if vals is not None:
+            first = vals.intent.in_token
+            assert circ.wires_int[0][lay.offset << (circ.log_n - lay.alignment)] == first
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    rc, proof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                         synth.splitmix_blinders(0x5E7), srs)
+    assert rc == 0
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
+
+
+def test_private_settlement_links_to_a_validity_side_circuit(oracle, pyoracle):
+    """The settlement proof is linked to each party's validity proof through the values both circuits place in
+    `intent_and_balance_settlement_party0` (native_proof_manager.rs:726-782).  Here the validity side is a stub circuit
+    that holds the same 17 values under the same layout; the oracle links the two proofs and its verifier accepts."""
+    from renegade_b200 import private_settlement as ps
+    py = pyoracle
+    parties, statement = ps.create_witness_statement(seed=12)
+    cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
+    layout = cs.get_circuit_layout()[ps.PARTY_LINKS[0]]
+    p0 = parties[0]
+    shared = (p0.intent.to_scalars() + [p0.pre_settlement_amount_public_share] + p0.input_balance.to_scalars() +
+              p0.pre_settlement_in_balance_shares)
+    assert len(shared) == layout.size == 17
+    stub = C.PlonkCircuit()
+    stub.create_link_group(ps.PARTY_LINKS[0], C.GroupLayout(layout.alignment, layout.offset))
+    vars_ = [stub.create_variable_with_link_groups(v, [ps.PARTY_LINKS[0]]) for v in shared]
+    digest = stub.create_public_variable(C.compute_poseidon_hash(shared[:2]))
+    C.PoseidonHashGadget(stub.zero()).hash_constrained(vars_[:2], digest, stub)
+    stub.check_circuit_satisfiability(stub.public_input())
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    hints = []
+    circs = [cs.finalize_for_arithmetization(), stub.finalize_for_arithmetization()]
+    srs = oracle.srs_from_tau(tau, max(c.n for c in circs) + 3)
+    for i, circ in enumerate(circs):
+        opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs[:circ.n + 3])
+        rc, proof, _, link = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                                synth.splitmix_blinders(70 + i), srs[:circ.n + 3], True)
+        assert rc == 0
+        hints.append((link, proof.to_array()[:8].copy()))
+    rc, lp, _ = oracle.plonk_link(hints[0][0], hints[1][0], hints[0][1], hints[1][1], layout.alignment, layout.offset,
+                                  layout.size, srs)
+    assert rc == 0
+    assert oracle.plonk_link_verify_known_tau(hints[0][1], hints[1][1], layout.alignment, layout.offset, layout.size, lp, tau)

@@ -64,3 +64,29 @@ def test_valid_balance_create_proves_on_device(ctx, oracle, pyoracle):
     assert rc == 0 and (proof.to_array() == oproof.to_array()).all()
     assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs,
                                          oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
+
+
+def test_private_settlement_proves_on_device(ctx, oracle, pyoracle):
+    """BASELINE.json configs[3]'s statement at its own size: INTENT AND BALANCE PRIVATE SETTLEMENT restated
+    (renegade_b200/private_settlement.py; 17 public inputs, four link groups, n = 2^12) — device proof bytes and
+    linking hint = the oracle's, verifier accepts."""
+    from renegade_b200 import private_settlement as ps
+    py = pyoracle
+    parties, statement = ps.create_witness_statement(seed=0xB200)
+    cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
+    cs.check_circuit_satisfiability(statement.to_scalars())
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == 12 and circ.num_inputs == 17
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    bases = ctx.load_bases(srs)
+    pk = PlonkKzgSnark.preprocess(ctx, bases, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    assert (pk.selector_comms == opk["selector_comms"]).all() and (pk.sigma_comms == opk["sigma_comms"]).all()
+    bl = synth.splitmix_blinders(0x12)
+    proof, hint = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+    rc, oproof, _, olink = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl, srs, True)
+    assert rc == 0 and (proof.to_array() == oproof.to_array()).all()
+    assert (hint.linking_wire_poly == olink).all()
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs,
+                                         oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
