@@ -119,6 +119,51 @@ def make_circuit(kind, log_n, seed):
     return cs.finalize_for_arithmetization(min_log_n=log_n)
 
 
+def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps):
+    """The reference's own statements at their own sizes (restated in renegade_b200/valid_balance_create.py and
+    private_settlement.py: n = 2^13 and 2^12, not the 2^16 BASELINE.json quotes): one proof alone, and proofs/s end
+    to end from pinned host memory through the pool.  Reported beside the headline, never instead of it."""
+    import numpy as np
+    import torch
+    from renegade_b200 import private_settlement as ps
+    from renegade_b200 import synth
+    from renegade_b200 import valid_balance_create as vbc
+    from renegade_b200.backend import PlonkKzgSnark, prove_raw
+    w, st = vbc.create_witness_statement(1)
+    parties, st2 = ps.create_witness_statement(1)
+    circuits = [("valid_balance_create (BASELINE.json configs[0])", vbc.ValidBalanceCreate.build(w, st)),
+                ("intent_and_balance_private_settlement (the statement of configs[3])",
+                 ps.IntentAndBalancePrivateSettlementCircuit.build(parties, st2))]
+    res = {}
+    for name, cs in circuits:
+        circ = cs.finalize_for_arithmetization()
+        bases = ctx.load_bases_device(d_srs_ptr, circ.n + 3)
+        pk = PlonkKzgSnark.preprocess(ctx, bases, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+        h_w = torch.from_numpy(circ.wires.view(np.int64)).pin_memory()
+        bl = [synth.splitmix_blinders(5000 + i) for i in range(8)]
+        for i in range(3):
+            prove_raw(ctx, pk, h_w.data_ptr(), circ.pub_inputs, bl[i])
+        t = time.perf_counter()
+        for i in range(5):
+            prove_raw(ctx, pk, h_w.data_ptr(), circ.pub_inputs, bl[i])
+        single_ms = (time.perf_counter() - t) / 5 * 1e3
+        rate = None
+        if pool is not None:
+            def run(count):
+                tickets = [pool.submit_prove(pk, h_w.data_ptr(), circ.pub_inputs, bl[i % 8]) for i in range(count)]
+                for tk in tickets:
+                    pool.wait(tk)
+            run(2 * conc)
+            t = time.perf_counter()
+            run(steps)
+            rate = steps / (time.perf_counter() - t)
+        res[name] = {"log_n": circ.log_n, "gates": circ.n_gates, "num_inputs": circ.num_inputs,
+                     "ms_one_proof_in_flight": single_ms, "proofs_per_s_e2e": rate, "in_flight": conc, "steps": steps}
+        pk.free()
+        bases.free()
+    return res
+
+
 def base_line(args, world):
     return {"metric": METRIC, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -185,6 +230,8 @@ def main():
     ap.add_argument("--msm-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm", action="store_true")
+    ap.add_argument("--no-real-statements", action="store_true",
+                    help="skip the extra leg that proves the restated VALID BALANCE CREATE and PRIVATE SETTLEMENT circuits")
     ap.add_argument("--circuit", choices=("synthetic", "merkle"), default="synthetic",
                     help="synthetic: random gates of the reference's mix (default); merkle: height-10 Poseidon2 Merkle "
                          "openings built with the reference's gadgets (renegade_b200/circuit.py)")
@@ -479,6 +526,11 @@ def main():
             "note": "restated CPU prover (C + OpenMP; arkworks msm_bigint / radix-2 FFT algorithms, jellyfish "
                     "TurboPlonk rounds) — not the Rust reference itself",
         }
+    if world == 1 and not args.no_real_statements:
+        try:  # an extra: nothing in it may cost the headline line
+            out["real_statements"] = real_statement_leg(pool, ctx, d_srs.data_ptr(), conc, 300)
+        except Exception as e:
+            out["real_statements"] = {"error": repr(e)[:300]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
