@@ -484,6 +484,11 @@ class PoseidonHashGadget:
         self.next_index = 0
         self.in_squeeze_state = False
 
+    def clone(self) -> "PoseidonHashGadget":
+        other = PoseidonHashGadget(self.state[0])
+        other.state, other.next_index, other.in_squeeze_state = list(self.state), self.next_index, self.in_squeeze_state
+        return other
+
     def reset_state(self, cs: PlonkCircuit) -> None:
         self.state = [cs.zero()] * (CAPACITY + RATE)
         self.next_index = 0
@@ -676,10 +681,26 @@ class StateWrapper:
         return compute_poseidon_hash(self.private_shares() + self.recovery_stream.to_scalars() + self.share_stream.to_scalars())
 
     def compute_commitment(self) -> int:
+        return compute_poseidon_hash([self.compute_private_commitment(), self.compute_partial_public_commitment(len(self.public_share))])
+
+    def compute_partial_public_commitment(self, num_shares: int) -> int:
+        """state_wrapper.rs:133-142: the resumable chain over the first `num_shares` public shares."""
         comm = self.public_share[0]
-        for share in self.public_share[1:]:
+        for share in self.public_share[1:num_shares]:
             comm = compute_poseidon_hash([comm, share])
-        return compute_poseidon_hash([self.compute_private_commitment(), comm])
+        return comm
+
+    def compute_partial_commitment(self, num_shares: int):
+        """state_wrapper.rs:104-108: (private commitment, partial public commitment)."""
+        return self.compute_private_commitment(), self.compute_partial_public_commitment(num_shares)
+
+    def compute_nullifier(self) -> int:
+        """state_wrapper.rs:146-154: H(last recovery id, recovery stream seed)."""
+        return compute_poseidon_hash([self.recovery_stream.get_ith(self.recovery_stream.index - 1), self.recovery_stream.seed])
+
+    def clone(self) -> "StateWrapper":
+        return StateWrapper(PoseidonCSPRNG(self.recovery_stream.seed, self.recovery_stream.index),
+                            PoseidonCSPRNG(self.share_stream.seed, self.share_stream.index), list(self.inner), list(self.public_share))
 
 
 @dataclass
@@ -690,9 +711,34 @@ class PoseidonCSPRNGVar:
     def to_vars(self) -> List[Variable]:
         return [self.seed, self.index]
 
+    def clone(self) -> "PoseidonCSPRNGVar":
+        return PoseidonCSPRNGVar(self.seed, self.index)
+
+
+@dataclass
+class StateWrapperVar:
+    """darkpool-types `StateWrapperVar<T>`: the element's variables with its two stream states and public shares."""
+    recovery_stream: PoseidonCSPRNGVar
+    share_stream: PoseidonCSPRNGVar
+    inner: List[Variable]
+    public_share: List[Variable]
+
+    def clone(self) -> "StateWrapperVar":
+        return StateWrapperVar(self.recovery_stream.clone(), self.share_stream.clone(), list(self.inner), list(self.public_share))
+
+    @staticmethod
+    def create_witness(w: "StateWrapper", cs: PlonkCircuit) -> "StateWrapperVar":
+        mk = lambda st: PoseidonCSPRNGVar(cs.create_variable(st.seed), cs.create_variable(st.index))
+        return StateWrapperVar(mk(w.recovery_stream), mk(w.share_stream), [cs.create_variable(v) for v in w.inner],
+                               [cs.create_variable(v) for v in w.public_share])
+
 
 class CSPRNGGadget:
     """state_primitives/csprng.rs:9-47."""
+
+    @staticmethod
+    def get_ith(state: PoseidonCSPRNGVar, i: Variable, cs: PlonkCircuit) -> Variable:
+        return PoseidonHashGadget(cs.zero()).hash([state.seed, i], cs)
 
     @staticmethod
     def next(state: PoseidonCSPRNGVar, cs: PlonkCircuit) -> Variable:
@@ -744,6 +790,99 @@ class CommitmentGadget:
         return comm
 
 
+def _shared_prefix_length(a: Sequence[Variable], b: Sequence[Variable]) -> int:
+    """commitment.rs:14-29: how many leading VARIABLES two share vectors have in common."""
+    n = 0
+    while n < len(a) and a[n] == b[n]:
+        n += 1
+    return n
+
+
+class SharedPrefixCommitmentGadget:
+    """commitment.rs:128-330: commitments to two versions of an element that share a prefix of their shares hash that
+    prefix once (the new version of a rotated element differs from the old one in a few trailing fields only)."""
+
+    @staticmethod
+    def compute_private_commitments(priv1, priv2, elt1: "StateWrapperVar", elt2: "StateWrapperVar", cs: PlonkCircuit):
+        k = _shared_prefix_length(priv1, priv2)
+        hasher = PoseidonHashGadget(cs.zero())
+        hasher.batch_absorb(list(priv1[:k]), cs)
+        out = []
+        for priv, elt in ((priv1, elt1), (priv2, elt2)):
+            h = hasher.clone()
+            h.batch_absorb(list(priv[k:]) + elt.recovery_stream.to_vars() + elt.share_stream.to_vars(), cs)
+            out.append(h.squeeze(cs))
+        return out[0], out[1]
+
+    @staticmethod
+    def compute_public_partial_commitments(num_shares: int, pub1, pub2, cs: PlonkCircuit):
+        k = min(_shared_prefix_length(pub1, pub2), num_shares)
+        v1, v2 = [], []
+        if k > 0:
+            partial = CommitmentGadget.compute_resumable_commitment(list(pub1[:k]), cs)
+            v1, v2 = [partial], [partial]
+        v1 += list(pub1[k:])
+        v2 += list(pub2[k:num_shares])
+        return CommitmentGadget.compute_resumable_commitment(v1, cs), CommitmentGadget.compute_resumable_commitment(v2, cs)
+
+    @staticmethod
+    def compute_partial_commitments(num_shares: int, priv1, elt1, priv2, elt2, cs: PlonkCircuit):
+        """-> (full commitment of element 1, (private commitment, partial public commitment) of element 2)."""
+        pc1, pc2 = SharedPrefixCommitmentGadget.compute_private_commitments(priv1, priv2, elt1, elt2, cs)
+        pub1, pub2 = SharedPrefixCommitmentGadget.compute_public_partial_commitments(num_shares, elt1.public_share,
+                                                                                      elt2.public_share, cs)
+        return PoseidonHashGadget(cs.zero()).hash([pc1, pub1], cs), (pc2, pub2)
+
+
+class NotEqualGadget:
+    """comparators.rs:143-170: a != b as 1 - (a - b == 0), constrained true."""
+
+    @staticmethod
+    def constrain_not_equal(a: Variable, b: Variable, cs: PlonkCircuit) -> None:
+        eq = EqZeroGadget.eq_zero_var(cs.sub(a, b), cs)
+        neq = cs.lc([cs.one(), eq, cs.zero(), cs.zero()], [1, -1, 0, 0])
+        cs.enforce_true(neq)
+
+
+class NullifierGadget:
+    """state_primitives/nullifier.rs:10-33: H(recovery id of the last update, recovery stream seed)."""
+
+    @staticmethod
+    def compute_nullifier(element: "StateWrapperVar", cs: PlonkCircuit) -> Variable:
+        NotEqualGadget.constrain_not_equal(element.recovery_stream.index, cs.zero(), cs)
+        last_idx = cs.sub(element.recovery_stream.index, cs.one())
+        recovery_id = CSPRNGGadget.get_ith(element.recovery_stream, last_idx, cs)
+        return PoseidonHashGadget(cs.zero()).hash([recovery_id, element.recovery_stream.seed], cs)
+
+
+class ShareGadget:
+    """state_primitives/shares.rs:17-60."""
+
+    @staticmethod
+    def compute_complementary_shares(shares: Sequence[Variable], base: Sequence[Variable], cs: PlonkCircuit) -> List[Variable]:
+        return [cs.sub(b, s) for b, s in zip(base, shares)]
+
+
+class StateElementRotationGadget:
+    """state_primitives/state_rotation.rs:97-140 (`rotate_version_with_partial_commitment`): the new version's
+    recovery id, the old version's full and the new version's partial commitment (shared prefix), the Merkle opening
+    of the old commitment, the old version's nullifier."""
+
+    @staticmethod
+    def rotate_version_with_partial_commitment(num_shares: int, old_version: "StateWrapperVar", old_private_share,
+                                               old_opening: "MerkleOpeningVar", merkle_root: Variable, nullifier: Variable,
+                                               new_version: "StateWrapperVar", new_private_share,
+                                               new_partial_commitment, recovery_id: Variable, cs: PlonkCircuit) -> None:
+        cs.enforce_equal(RecoveryIdGadget.compute_recovery_id(new_version.recovery_stream, cs), recovery_id)
+        old_commitment, (priv_c, pub_c) = SharedPrefixCommitmentGadget.compute_partial_commitments(
+            num_shares, old_private_share, old_version, new_private_share, new_version, cs)
+        cs.enforce_equal(priv_c, new_partial_commitment[0])
+        cs.enforce_equal(pub_c, new_partial_commitment[1])
+        root = PoseidonMerkleHashGadget.compute_root_prehashed(old_commitment, old_opening, cs)
+        cs.enforce_equal(merkle_root, root)
+        cs.enforce_equal(NullifierGadget.compute_nullifier(old_version, cs), nullifier)
+
+
 class AmountGadget:
     """primitives/bitlength.rs:9-17."""
 
@@ -788,6 +927,13 @@ class PoseidonMerkleHashGadget:
     def compute_and_constrain_root(leaf_node: Sequence[Variable], opening: MerkleOpeningVar, expected_root: Variable,
                                    cs: PlonkCircuit) -> None:
         cs.enforce_equal(expected_root, PoseidonMerkleHashGadget.compute_root(leaf_node, opening, cs))
+
+
+def native_merkle_root_prehashed(leaf_hash: int, opening: MerkleOpening) -> int:
+    cur = leaf_hash
+    for sister, is_right in zip(opening.elems, opening.indices):
+        cur = compute_poseidon_hash([sister, cur] if is_right else [cur, sister])
+    return cur
 
 
 def native_merkle_root(leaf: Sequence[int], opening: MerkleOpening) -> int:

@@ -94,9 +94,11 @@ def fp_floor_mul(fp_repr: int, integer: int) -> int:
     return (fp_repr * integer) >> DEFAULT_FP_PRECISION
 
 
-def create_witness_statement(seed: int = 0):
+def create_witness_statement(seed: int = 0, linked=None):
     """A consistent two-party match: party 0 sells token A for B, party 1 the reverse, at a price both intents accept,
-    with balances that cover it; fee takes and share updates as the circuit (and the contracts) compute them."""
+    with balances that cover it; fee takes and share updates as the circuit (and the contracts) compute them.
+    `linked`: per party, None or the (amount public share, [3 post-match balance shares]) its validity proof produced —
+    the values the two proofs must agree on for the link to verify."""
     rnd = random.Random(seed)
     addr = lambda: rnd.randrange(1 << 160)
     tok_a, tok_b = addr(), addr()
@@ -115,6 +117,8 @@ def create_witness_statement(seed: int = 0):
                                   rnd.randrange(1 << 40), rnd.randrange(1 << 60))
         pre_amount_share = rnd.randrange(R)
         pre_in, pre_out = [rnd.randrange(R) for _ in range(3)], [rnd.randrange(R) for _ in range(3)]
+        if linked is not None and linked[len(parties)] is not None:
+            pre_amount_share, pre_in = linked[len(parties)][0], list(linked[len(parties)][1])
         relayer_take, protocol_take = fp_floor_mul(rfee, aout), fp_floor_mul(protocol_fee, aout)
         net = aout - relayer_take - protocol_take
         parties.append(PartyWitness(obligation, intent, pre_amount_share, in_bal, pre_in, out_bal, pre_out))

@@ -371,3 +371,63 @@ def test_private_settlement_links_to_a_validity_side_circuit(oracle, pyoracle):
                                   layout.size, srs)
     assert rc == 0
     assert oracle.plonk_link_verify_known_tau(hints[0][1], hints[1][1], layout.alignment, layout.offset, layout.size, lp, tau)
+
+
+def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle):
+    """INTENT AND BALANCE VALIDITY restated (renegade_b200/intent_and_balance_validity.py): 62 Poseidon2 permutations,
+    n = 2^14, 10 public inputs, every statement field binding.  Then the bundle the reference proves for a private
+    match (native_proof_manager.rs:526-584, 726-782): each party's validity proof, the settlement proof over the same
+    intents / balances / shares, and the link proofs between them on the party groups — proved, linked and verified on
+    the oracle."""
+    from renegade_b200 import intent_and_balance_validity as val
+    from renegade_b200 import private_settlement as ps
+    py = pyoracle
+    # the match first (who trades what), then each party's validity proof over ITS intent and input balance
+    parties, _ = ps.create_witness_statement(seed=21)
+    validity = [val.create_witness_statement(seed=30 + i, intent=parties[i].intent, balance=parties[i].input_balance)
+                for i in (0, 1)]
+    parties, statement = ps.create_witness_statement(
+        seed=21, linked=[(w.new_amount_public_share, w.post_match_balance_shares) for w, _ in validity])
+    settlement_cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
+    settlement_cs.check_circuit_satisfiability(statement.to_scalars())
+    layouts = settlement_cs.get_circuit_layout()
+
+    w0, s0 = validity[0]
+    cs0 = val.IntentAndBalanceValidityCircuit.build(w0, s0, layouts)
+    pub0 = s0.to_scalars()
+    assert len(pub0) == 10
+    cs0.check_circuit_satisfiability(pub0)
+    for i in range(len(pub0)):
+        bad = list(pub0)
+        bad[i] = (bad[i] + 1) % C.R
+        with pytest.raises(C.CircuitError):
+            cs0.check_circuit_satisfiability(bad)
+    from collections import Counter
+    names = Counter(r.gate.name for r in cs0.rows)
+    assert (names["FusedInternalSboxMDSGate"] + names["FusedExternalSboxMDSGate"]) == 62 * 195
+    cs1 = val.IntentAndBalanceValidityCircuit.build(*validity[1], layouts)
+    cs1.check_circuit_satisfiability(validity[1][1].to_scalars())
+
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    circs = [settlement_cs.finalize_for_arithmetization(), cs0.finalize_for_arithmetization(), cs1.finalize_for_arithmetization()]
+    assert [c.log_n for c in circs] == [12, 14, 14]
+    srs = oracle.srs_from_tau(tau, (1 << 14) + 3)
+    hints = []
+    for i, circ in enumerate(circs):
+        opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs[:circ.n + 3])
+        rc, proof, _, link = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                                synth.splitmix_blinders(90 + i), srs[:circ.n + 3], True)
+        assert rc == 0
+        assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
+        hints.append((link, proof.to_array()[:8].copy()))
+    for party in (0, 1):                         # validity proof of party i <-> settlement proof, on party i's group
+        lay = layouts[ps.PARTY_LINKS[party]]
+        v = hints[1 + party]
+        rc, lp, _ = oracle.plonk_link(v[0], hints[0][0], v[1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
+        assert rc == 0
+        assert oracle.plonk_link_verify_known_tau(v[1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)
+    # party 1's validity proof does not link on party 0's group: the settlement holds party 0's values there
+    lay = layouts[ps.PARTY_LINKS[0]]
+    rc, lp, _ = oracle.plonk_link(hints[2][0], hints[0][0], hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
+    assert rc == 0
+    assert not oracle.plonk_link_verify_known_tau(hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)

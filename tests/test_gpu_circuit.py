@@ -90,3 +90,49 @@ def test_private_settlement_proves_on_device(ctx, oracle, pyoracle):
     assert (hint.linking_wire_poly == olink).all()
     assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs,
                                          oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
+
+
+def test_private_match_bundle_on_device(ctx, oracle, pyoracle):
+    """The bundle the reference proves for a private match (native_proof_manager.rs:526-584, 726-782; SURVEY.md §8(d)
+    config 4), with the restated circuits: both parties' INTENT AND BALANCE VALIDITY proofs (n = 2^14), the PRIVATE
+    SETTLEMENT proof (n = 2^12) and the two party link proofs — all on the device, each byte-identical to the oracle's,
+    every proof and link accepted by the restated verifiers."""
+    from renegade_b200 import intent_and_balance_validity as val
+    from renegade_b200 import private_settlement as ps
+    from renegade_b200.backend import GroupLayout, link_proofs
+    py = pyoracle
+    parties, _ = ps.create_witness_statement(seed=41)
+    validity = [val.create_witness_statement(seed=50 + i, intent=parties[i].intent, balance=parties[i].input_balance)
+                for i in (0, 1)]
+    parties, statement = ps.create_witness_statement(
+        seed=41, linked=[(w.new_amount_public_share, w.post_match_balance_shares) for w, _ in validity])
+    settlement_cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
+    layouts = settlement_cs.get_circuit_layout()
+    circs = [settlement_cs.finalize_for_arithmetization()] + \
+            [val.IntentAndBalanceValidityCircuit.build(w, s, layouts).finalize_for_arithmetization() for w, s in validity]
+    assert [c.log_n for c in circs] == [12, 14, 14]
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, (1 << 14) + 3)
+    bases = ctx.load_bases(srs)
+    hints, ohints = [], []
+    for i, circ in enumerate(circs):
+        pk = PlonkKzgSnark.preprocess(ctx, bases, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+        opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs[:circ.n + 3])
+        bl = synth.splitmix_blinders(0x20 + i)
+        proof, hint = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+        rc, oproof, _, olink = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl,
+                                                  srs[:circ.n + 3], True)
+        assert rc == 0 and (proof.to_array() == oproof.to_array()).all() and (hint.linking_wire_poly == olink).all()
+        assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs,
+                                             oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
+        hints.append(hint)
+        pk.free()
+    for party in (0, 1):
+        lay = layouts[ps.PARTY_LINKS[party]]
+        v, s = hints[1 + party], hints[0]
+        lp, eta = link_proofs(ctx, bases, v, s, GroupLayout(lay.alignment, lay.offset, lay.size))
+        rc, olp, oeta = oracle.plonk_link(v.linking_wire_poly, s.linking_wire_poly, v.linking_wire_comm, s.linking_wire_comm,
+                                          lay.alignment, lay.offset, lay.size, srs)
+        assert rc == 0 and (lp.to_array() == olp.to_array()).all() and (eta == oeta).all()
+        assert oracle.plonk_link_verify_known_tau(v.linking_wire_comm, s.linking_wire_comm, lay.alignment, lay.offset, lay.size,
+                                                  oracle.LinkProof.from_buffer_copy(bytes(lp)), tau)
