@@ -164,6 +164,56 @@ def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps):
     return res
 
 
+def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
+    """What the reference proves for one private match (native_proof_manager.rs:526-584, 726-782), with the restated
+    circuits: both parties' INTENT AND BALANCE VALIDITY proofs (n = 2^14), the PRIVATE SETTLEMENT proof (n = 2^12) and
+    the two party link proofs — `bundles` of them through the pool, end to end from pinned host memory."""
+    import numpy as np
+    import torch
+    from renegade_b200 import intent_and_balance_validity as val
+    from renegade_b200 import private_settlement as ps
+    from renegade_b200 import synth
+    from renegade_b200.backend import GroupLayout, LinkingHint, PlonkKzgSnark
+    if pool is None:
+        return {"skipped": "needs the pool (concurrency > 1)"}
+    parties, _ = ps.create_witness_statement(seed=61)
+    validity = [val.create_witness_statement(seed=70 + i, intent=parties[i].intent, balance=parties[i].input_balance)
+                for i in (0, 1)]
+    parties, statement = ps.create_witness_statement(
+        seed=61, linked=[(w.new_amount_public_share, w.post_match_balance_shares) for w, _ in validity])
+    settlement_cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
+    layouts = settlement_cs.get_circuit_layout()
+    circs = [settlement_cs.finalize_for_arithmetization()] + \
+            [val.IntentAndBalanceValidityCircuit.build(w, st, layouts).finalize_for_arithmetization() for w, st in validity]
+    bases = ctx.load_bases_device(d_srs_ptr, (1 << 14) + 3)
+    pks = [PlonkKzgSnark.preprocess(ctx, bases, c.log_n, c.num_inputs, c.selectors, c.perm, c.k) for c in circs]
+    wires = [torch.from_numpy(c.wires.view(np.int64)).pin_memory() for c in circs]
+    bl = [synth.splitmix_blinders(7000 + i) for i in range(8)]
+    group = [GroupLayout(layouts[g].alignment, layouts[g].offset, layouts[g].size) for g in ps.PARTY_LINKS]
+
+    def run(count):
+        tickets = [[pool.submit_prove(pks[j], wires[j].data_ptr(), circs[j].pub_inputs, bl[(3 * b + j) % 8],
+                                      with_link_poly=True) for j in range(3)] for b in range(count)]
+        links = []
+        for b in range(count):
+            res = [pool.wait(tk) for tk in tickets[b]]
+            hints = [LinkingHint(linking_wire_poly=lp, linking_wire_comm=np.array(pr.wires_poly_comms[0], dtype=np.uint64))
+                     for pr, lp in res]
+            links += [pool.submit_link(bases, hints[1 + party], hints[0], group[party]) for party in (0, 1)]
+        for tk in links:
+            pool.wait(tk)
+    run(2)
+    t = time.perf_counter()
+    run(bundles)
+    dt = time.perf_counter() - t
+    for pk in pks:
+        pk.free()
+    bases.free()
+    return {"bundles_per_s_e2e": bundles / dt, "ms_per_bundle": dt / bundles * 1e3, "bundles": bundles, "in_flight": conc,
+            "proofs_per_bundle": {"intent_and_balance_validity (n = 2^14)": 2, "private_settlement (n = 2^12)": 1,
+                                  "link proofs": 2}}
+
+
 def base_line(args, world):
     return {"metric": METRIC, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -531,6 +581,10 @@ def main():
             out["real_statements"] = real_statement_leg(pool, ctx, d_srs.data_ptr(), conc, 300)
         except Exception as e:
             out["real_statements"] = {"error": repr(e)[:300]}
+        try:
+            out["private_match_bundle"] = private_match_bundle_leg(pool, ctx, d_srs.data_ptr(), conc, 40)
+        except Exception as e:
+            out["private_match_bundle"] = {"error": repr(e)[:300]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
