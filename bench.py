@@ -166,11 +166,13 @@ def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps):
 
 def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
     """What the reference proves for one private match (native_proof_manager.rs:526-584, 726-782), with the restated
-    circuits: both parties' INTENT AND BALANCE VALIDITY proofs (n = 2^14), the PRIVATE SETTLEMENT proof (n = 2^12) and
-    the two party link proofs — `bundles` of them through the pool, end to end from pinned host memory."""
+    circuits: both parties' INTENT AND BALANCE VALIDITY (n = 2^14) and OUTPUT BALANCE VALIDITY (n = 2^13) proofs, the
+    PRIVATE SETTLEMENT proof (n = 2^12) and the four link proofs — `bundles` of them through the pool, end to end from
+    pinned host memory."""
     import numpy as np
     import torch
     from renegade_b200 import intent_and_balance_validity as val
+    from renegade_b200 import output_balance_validity as obv
     from renegade_b200 import private_settlement as ps
     from renegade_b200 import synth
     from renegade_b200.backend import GroupLayout, LinkingHint, PlonkKzgSnark
@@ -179,27 +181,34 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
     parties, _ = ps.create_witness_statement(seed=61)
     validity = [val.create_witness_statement(seed=70 + i, intent=parties[i].intent, balance=parties[i].input_balance)
                 for i in (0, 1)]
+    out_validity = [obv.create_witness_statement(80 + i, parties[i].output_balance) for i in (0, 1)]
     parties, statement = ps.create_witness_statement(
-        seed=61, linked=[(w.new_amount_public_share, w.post_match_balance_shares) for w, _ in validity])
+        seed=61, linked=[(validity[i][0].new_amount_public_share, validity[i][0].post_match_balance_shares,
+                          out_validity[i][0].post_match_balance_shares) for i in (0, 1)])
     settlement_cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
     layouts = settlement_cs.get_circuit_layout()
     circs = [settlement_cs.finalize_for_arithmetization()] + \
-            [val.IntentAndBalanceValidityCircuit.build(w, st, layouts).finalize_for_arithmetization() for w, st in validity]
+            [val.IntentAndBalanceValidityCircuit.build(w, st, layouts).finalize_for_arithmetization() for w, st in validity] + \
+            [obv.OutputBalanceValidityCircuit.build(w, st, layouts).finalize_for_arithmetization() for w, st in out_validity]
     bases = ctx.load_bases_device(d_srs_ptr, (1 << 14) + 3)
     pks = [PlonkKzgSnark.preprocess(ctx, bases, c.log_n, c.num_inputs, c.selectors, c.perm, c.k) for c in circs]
     wires = [torch.from_numpy(c.wires.view(np.int64)).pin_memory() for c in circs]
     bl = [synth.splitmix_blinders(7000 + i) for i in range(8)]
-    group = [GroupLayout(layouts[g].alignment, layouts[g].offset, layouts[g].size) for g in ps.PARTY_LINKS]
+    # (validity proof index, link group): party groups link proofs 1, 2; output-balance groups link proofs 3, 4
+    link_plan = [(1 + p, GroupLayout(layouts[g].alignment, layouts[g].offset, layouts[g].size))
+                 for p, g in enumerate(ps.PARTY_LINKS)] + \
+                [(3 + p, GroupLayout(layouts[g].alignment, layouts[g].offset, layouts[g].size))
+                 for p, g in enumerate(ps.OUTPUT_LINKS)]
 
     def run(count):
-        tickets = [[pool.submit_prove(pks[j], wires[j].data_ptr(), circs[j].pub_inputs, bl[(3 * b + j) % 8],
-                                      with_link_poly=True) for j in range(3)] for b in range(count)]
+        tickets = [[pool.submit_prove(pks[j], wires[j].data_ptr(), circs[j].pub_inputs, bl[(5 * b + j) % 8],
+                                      with_link_poly=True) for j in range(5)] for b in range(count)]
         links = []
         for b in range(count):
             res = [pool.wait(tk) for tk in tickets[b]]
             hints = [LinkingHint(linking_wire_poly=lp, linking_wire_comm=np.array(pr.wires_poly_comms[0], dtype=np.uint64))
                      for pr, lp in res]
-            links += [pool.submit_link(bases, hints[1 + party], hints[0], group[party]) for party in (0, 1)]
+            links += [pool.submit_link(bases, hints[j], hints[0], lay) for j, lay in link_plan]
         for tk in links:
             pool.wait(tk)
     run(2)
@@ -210,8 +219,8 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
         pk.free()
     bases.free()
     return {"bundles_per_s_e2e": bundles / dt, "ms_per_bundle": dt / bundles * 1e3, "bundles": bundles, "in_flight": conc,
-            "proofs_per_bundle": {"intent_and_balance_validity (n = 2^14)": 2, "private_settlement (n = 2^12)": 1,
-                                  "link proofs": 2}}
+            "proofs_per_bundle": {"intent_and_balance_validity (n = 2^14)": 2, "output_balance_validity (n = 2^13)": 2,
+                                  "private_settlement (n = 2^12)": 1, "link proofs": 4}}
 
 
 def run_extras(args):

@@ -97,8 +97,8 @@ def fp_floor_mul(fp_repr: int, integer: int) -> int:
 def create_witness_statement(seed: int = 0, linked=None):
     """A consistent two-party match: party 0 sells token A for B, party 1 the reverse, at a price both intents accept,
     with balances that cover it; fee takes and share updates as the circuit (and the contracts) compute them.
-    `linked`: per party, None or the (amount public share, [3 post-match balance shares]) its validity proof produced —
-    the values the two proofs must agree on for the link to verify."""
+    `linked`: per party, None or (amount public share, [3 input post-match shares][, [3 output post-match shares]]) as its
+    validity proof(s) produced them — the values the linked proofs must agree on."""
     rnd = random.Random(seed)
     addr = lambda: rnd.randrange(1 << 160)
     tok_a, tok_b = addr(), addr()
@@ -118,7 +118,10 @@ def create_witness_statement(seed: int = 0, linked=None):
         pre_amount_share = rnd.randrange(R)
         pre_in, pre_out = [rnd.randrange(R) for _ in range(3)], [rnd.randrange(R) for _ in range(3)]
         if linked is not None and linked[len(parties)] is not None:
-            pre_amount_share, pre_in = linked[len(parties)][0], list(linked[len(parties)][1])
+            lk = linked[len(parties)]
+            pre_amount_share, pre_in = lk[0], list(lk[1])
+            if len(lk) > 2:                                            # the output balance's validity proof as well
+                pre_out = list(lk[2])
         relayer_take, protocol_take = fp_floor_mul(rfee, aout), fp_floor_mul(protocol_fee, aout)
         net = aout - relayer_take - protocol_take
         parties.append(PartyWitness(obligation, intent, pre_amount_share, in_bal, pre_in, out_bal, pre_out))

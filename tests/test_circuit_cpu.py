@@ -375,19 +375,22 @@ def test_private_settlement_links_to_a_validity_side_circuit(oracle, pyoracle):
 
 def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle):
     """INTENT AND BALANCE VALIDITY restated (renegade_b200/intent_and_balance_validity.py): 62 Poseidon2 permutations,
-    n = 2^14, 10 public inputs, every statement field binding.  Then the bundle the reference proves for a private
-    match (native_proof_manager.rs:526-584, 726-782): each party's validity proof, the settlement proof over the same
-    intents / balances / shares, and the link proofs between them on the party groups — proved, linked and verified on
-    the oracle."""
+    n = 2^14, 10 public inputs, every statement field binding; OUTPUT BALANCE VALIDITY (output_balance_validity.py): 34
+    permutations, n = 2^13, 5 public inputs.  Then the bundle the reference proves for a private match
+    (native_proof_manager.rs:526-584, 726-782): each party's two validity proofs, the settlement proof over the same
+    intents / balances / shares, and the FOUR link proofs between them — proved, linked and verified on the oracle."""
     from renegade_b200 import intent_and_balance_validity as val
+    from renegade_b200 import output_balance_validity as obv
     from renegade_b200 import private_settlement as ps
     py = pyoracle
     # the match first (who trades what), then each party's validity proof over ITS intent and input balance
     parties, _ = ps.create_witness_statement(seed=21)
     validity = [val.create_witness_statement(seed=30 + i, intent=parties[i].intent, balance=parties[i].input_balance)
                 for i in (0, 1)]
+    out_validity = [obv.create_witness_statement(40 + i, parties[i].output_balance) for i in (0, 1)]
     parties, statement = ps.create_witness_statement(
-        seed=21, linked=[(w.new_amount_public_share, w.post_match_balance_shares) for w, _ in validity])
+        seed=21, linked=[(validity[i][0].new_amount_public_share, validity[i][0].post_match_balance_shares,
+                          out_validity[i][0].post_match_balance_shares) for i in (0, 1)])
     settlement_cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
     settlement_cs.check_circuit_satisfiability(statement.to_scalars())
     layouts = settlement_cs.get_circuit_layout()
@@ -407,10 +410,17 @@ def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle)
     assert (names["FusedInternalSboxMDSGate"] + names["FusedExternalSboxMDSGate"]) == 62 * 195
     cs1 = val.IntentAndBalanceValidityCircuit.build(*validity[1], layouts)
     cs1.check_circuit_satisfiability(validity[1][1].to_scalars())
+    out_cs = [obv.OutputBalanceValidityCircuit.build(w, s, layouts) for w, s in out_validity]
+    for ocs, (_, s) in zip(out_cs, out_validity):
+        assert len(s.to_scalars()) == 5
+        ocs.check_circuit_satisfiability(s.to_scalars())
+    onames = Counter(r.gate.name for r in out_cs[0].rows)
+    assert (onames["FusedInternalSboxMDSGate"] + onames["FusedExternalSboxMDSGate"]) == 34 * 195
 
     tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
-    circs = [settlement_cs.finalize_for_arithmetization(), cs0.finalize_for_arithmetization(), cs1.finalize_for_arithmetization()]
-    assert [c.log_n for c in circs] == [12, 14, 14]
+    circs = [settlement_cs.finalize_for_arithmetization(), cs0.finalize_for_arithmetization(), cs1.finalize_for_arithmetization(),
+             out_cs[0].finalize_for_arithmetization(), out_cs[1].finalize_for_arithmetization()]
+    assert [c.log_n for c in circs] == [12, 14, 14, 13, 13]
     srs = oracle.srs_from_tau(tau, (1 << 14) + 3)
     hints = []
     for i, circ in enumerate(circs):
@@ -420,12 +430,11 @@ def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle)
         assert rc == 0
         assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
         hints.append((link, proof.to_array()[:8].copy()))
-    for party in (0, 1):                         # validity proof of party i <-> settlement proof, on party i's group
-        lay = layouts[ps.PARTY_LINKS[party]]
-        v = hints[1 + party]
-        rc, lp, _ = oracle.plonk_link(v[0], hints[0][0], v[1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
-        assert rc == 0
-        assert oracle.plonk_link_verify_known_tau(v[1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)
+    for party in (0, 1):                         # each validity proof of party i <-> settlement proof, on ITS group
+        for lay, v in ((layouts[ps.PARTY_LINKS[party]], hints[1 + party]), (layouts[ps.OUTPUT_LINKS[party]], hints[3 + party])):
+            rc, lp, _ = oracle.plonk_link(v[0], hints[0][0], v[1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
+            assert rc == 0
+            assert oracle.plonk_link_verify_known_tau(v[1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)
     # party 1's validity proof does not link on party 0's group: the settlement holds party 0's values there
     lay = layouts[ps.PARTY_LINKS[0]]
     rc, lp, _ = oracle.plonk_link(hints[2][0], hints[0][0], hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)

@@ -94,23 +94,27 @@ def test_private_settlement_proves_on_device(ctx, oracle, pyoracle):
 
 def test_private_match_bundle_on_device(ctx, oracle, pyoracle):
     """The bundle the reference proves for a private match (native_proof_manager.rs:526-584, 726-782; SURVEY.md §8(d)
-    config 4), with the restated circuits: both parties' INTENT AND BALANCE VALIDITY proofs (n = 2^14), the PRIVATE
-    SETTLEMENT proof (n = 2^12) and the two party link proofs — all on the device, each byte-identical to the oracle's,
-    every proof and link accepted by the restated verifiers."""
+    config 4), with the restated circuits: both parties' INTENT AND BALANCE VALIDITY (n = 2^14) and OUTPUT BALANCE
+    VALIDITY (n = 2^13) proofs, the PRIVATE SETTLEMENT proof (n = 2^12) and the four link proofs — all on the device,
+    each byte-identical to the oracle's, every proof and link accepted by the restated verifiers."""
     from renegade_b200 import intent_and_balance_validity as val
+    from renegade_b200 import output_balance_validity as obv
     from renegade_b200 import private_settlement as ps
     from renegade_b200.backend import GroupLayout, link_proofs
     py = pyoracle
     parties, _ = ps.create_witness_statement(seed=41)
     validity = [val.create_witness_statement(seed=50 + i, intent=parties[i].intent, balance=parties[i].input_balance)
                 for i in (0, 1)]
+    out_validity = [obv.create_witness_statement(60 + i, parties[i].output_balance) for i in (0, 1)]
     parties, statement = ps.create_witness_statement(
-        seed=41, linked=[(w.new_amount_public_share, w.post_match_balance_shares) for w, _ in validity])
+        seed=41, linked=[(validity[i][0].new_amount_public_share, validity[i][0].post_match_balance_shares,
+                          out_validity[i][0].post_match_balance_shares) for i in (0, 1)])
     settlement_cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
     layouts = settlement_cs.get_circuit_layout()
     circs = [settlement_cs.finalize_for_arithmetization()] + \
-            [val.IntentAndBalanceValidityCircuit.build(w, s, layouts).finalize_for_arithmetization() for w, s in validity]
-    assert [c.log_n for c in circs] == [12, 14, 14]
+            [val.IntentAndBalanceValidityCircuit.build(w, s, layouts).finalize_for_arithmetization() for w, s in validity] + \
+            [obv.OutputBalanceValidityCircuit.build(w, s, layouts).finalize_for_arithmetization() for w, s in out_validity]
+    assert [c.log_n for c in circs] == [12, 14, 14, 13, 13]
     tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
     srs = oracle.srs_from_tau(tau, (1 << 14) + 3)
     bases = ctx.load_bases(srs)
@@ -127,9 +131,9 @@ def test_private_match_bundle_on_device(ctx, oracle, pyoracle):
                                              oracle.PlonkProof.from_buffer_copy(bytes(proof)), tau)
         hints.append(hint)
         pk.free()
-    for party in (0, 1):
-        lay = layouts[ps.PARTY_LINKS[party]]
-        v, s = hints[1 + party], hints[0]
+    for lay, v in [(layouts[ps.PARTY_LINKS[p]], hints[1 + p]) for p in (0, 1)] + \
+                  [(layouts[ps.OUTPUT_LINKS[p]], hints[3 + p]) for p in (0, 1)]:
+        s = hints[0]
         lp, eta = link_proofs(ctx, bases, v, s, GroupLayout(lay.alignment, lay.offset, lay.size))
         rc, olp, oeta = oracle.plonk_link(v.linking_wire_poly, s.linking_wire_poly, v.linking_wire_comm, s.linking_wire_comm,
                                           lay.alignment, lay.offset, lay.size, srs)
