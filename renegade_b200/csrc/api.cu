@@ -412,8 +412,8 @@ int b200_msm_timing_totals(b200_ctx* ctx, int reset, double out[3]) {
 int b200_msm_tuning(b200_ctx* ctx, int throughput_mode) {
     B200_TRY
     if (!ctx) return B200_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->c.mu);
-    ctx->c.msm.reduce_chunk_log = throughput_mode ? kMsmReduceChunkLogThroughput : 0;
+    // kept for ABI compatibility: the tree reduction (msm.cu) has one setting for lone MSMs and the prover alike
+    (void)throughput_mode;
     return B200_OK;
     B200_CATCH
 }

@@ -44,6 +44,26 @@ struct DevBuf {
     }
 };
 
+// Grow-only pinned host buffer (results the host reads right after a stream wait)
+struct HostPinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B200_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes < 4096) bytes = 4096;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(HostPinned)");
+        cap = bytes;
+        return B200_OK;
+    }
+    ~HostPinned() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
 // ---- NTT ------------------------------------------------------------------------------------
 struct Domain {
     unsigned log_n = 0;
@@ -79,12 +99,19 @@ struct Bases {
     }
 };
 
-// log2 of the buckets per thread in the bucket reduction: latency-tuned (a lone MSM) / throughput-tuned (prover)
-constexpr int kMsmReduceChunkLogLatency = 2, kMsmReduceChunkLogThroughput = 4;
-
 struct MsmScratch {
-    DevBuf counts, offsets, cursor, entries, buckets, block_sums, partials, window_sums, scalars;
+    DevBuf counts, offsets, cursor, entries, buckets, window_sums, scalars;
     DevBuf seg_offsets, seg_bucket, seg_sums, heavy, seg_order;
+    DevBuf scan_state;  // ScanState header + tile status words of the single-pass scan (msm.cu)
+    DevBuf tree;        // partial sums of the row / column reduction trees
+    HostPinned h_sums;  // window sums land here (pinned), read by the host epilogue
+    cudaEvent_t done_ev = nullptr;  // recorded after the D2H of the window sums
+    bool finish_attr_set = false;
+    // the MSM batch queued by msm_launch_batch and not yet collected by msm_finish_batch
+    MsmPlan pending_plan;
+    size_t pending_n = 0;
+    unsigned pending_batch = 0;
+    uint64_t n_kernel_launches = 0;  // kernels launched by this scratch's MSMs (bench: gpu_launches)
     // optional per-phase device timing (CUDA events on the launching stream)
     bool timing = false;
     bool ev_init = false;
@@ -92,13 +119,13 @@ struct MsmScratch {
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
     // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
     double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
-    int reduce_chunk_log = 0;  // 0: latency-tuned default (a lone MSM); the prover sets the throughput value
     // borrowed from the context: low-priority stream for the accumulation kernel (null: same stream)
     cudaStream_t hv_stream = nullptr;
     cudaEvent_t hv_fork = nullptr, hv_join = nullptr;
     ~MsmScratch() {
         if (ev_init)
             for (auto& e : ev) cudaEventDestroy(e);
+        if (done_ev) cudaEventDestroy(done_ev);
     }
 };
 
@@ -114,6 +141,10 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
 int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
                      unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st, g1_affine* out,
                      int* out_inf);
+// the two halves of msm_device_batch: enqueue only / wait + host epilogue (one batch pending per scratch)
+int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
+                     unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st);
+int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf);
 // synthetic known-discrete-log bases P_i = a_i * G, a_i = SplitMix64-derived
 int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
                                cudaStream_t st);
@@ -140,6 +171,7 @@ struct Context {
     bool heavy_plonk = false;  // also route the prover's NTT passes and quotient kernel there
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf ntt_scratch2;
+    HostPinned h_small;  // pinned landing zone of the prover's small read-backs (degree flag, evaluations)
     ~Context();
 };
 

@@ -37,13 +37,7 @@ constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
 #endif
 constexpr int kSegLen = B200_SEG_LEN;  // a bucket is folded in segments of at most this many points
 constexpr int kCombineSeq = 64;    // buckets with more segments than this take the block-tree path
-// Buckets per thread (2^chunk_log) in the running-sum reduction.  A lone MSM is latency-bound there and wants
-// short serial chains (4 buckets); inside the prover, where several proofs share the GPU, the reduction's
-// OPERATION COUNT is what matters (it competes for issue slots with other proofs' accumulation) and 16
-// buckets per thread is faster overall: 247 -> 265 proofs/s, while the 2^20 MSM alone goes 3.15 -> 3.28 ms
-// (profiles/r1p_reduce_chunk_seglen_variants.log).
-constexpr int kReduceChunkLogLatency = kMsmReduceChunkLogLatency;
-constexpr int kReduceThreads = 128;
+constexpr int kReduceThreads = 128;  // block size of the heavy-bucket tree
 
 // ---- scalar digits ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t get_bits(const uint32_t* s, int pos, int c) {
@@ -105,95 +99,174 @@ __global__ void msm_scatter_kernel(const fe* scalars, size_t n, size_t stride, i
                    });
 }
 
-// ---- exclusive scan of the bucket histogram (three small kernels) -----------------------------
+// ---- fused single-pass scan of the bucket histogram ------------------------------------------------
+// One launch produces everything the later phases need from the histogram: the exclusive scan of the
+// counts (`offsets`, and its copy `cursor` for the scatter), the exclusive scan of the per-bucket segment
+// counts ceil(count / kSegLen) (`seg_offsets`), the histogram of segment lengths turned into start
+// offsets, longest first (`seg_starts`, the cursor of msm_segorder_kernel), and the clean-up for the next
+// MSM on this scratch (counts, heavy-bucket counter, tile statuses and tickets back to zero).
+// Single-pass chained scan with decoupled look-back: tiles are handed out by an atomic ticket (so a tile's
+// predecessors are always running or done), every tile publishes its aggregate and then its inclusive
+// prefix in one 64-bit status word (flag:2 | segments:30 | entries:32), and warp 0 of a tile looks back
+// over 32 predecessors at a time.  The block that finishes last owns the epilogue.
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
-constexpr int kScanChunk = kScanThreads * kScanItems;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr uint32_t kSegBins = kSegLen + 1;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t warp_sums[kScanThreads / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = v;
+struct ScanState {          // zero-initialised when the scratch is allocated; left zeroed by every launch
+    uint32_t ticket, done;
+    uint32_t seg_hist[kSegBins + 1];
+    uint32_t seg_starts[kSegBins + 1];
+    uint32_t heavy_count;
+    uint32_t pad[3];
+    // followed by n_tiles 64-bit status words (8-byte aligned: the header is 4 * (2 + 34 + 34 + 4) = 296 bytes)
+};
+static_assert(sizeof(ScanState) % 8 == 0, "status words are 8-byte aligned");
+
+__device__ __forceinline__ uint64_t status_pack(uint32_t flag, uint32_t a, uint32_t b) {
+    return ((uint64_t)flag << 62) | ((uint64_t)b << 32) | a;
+}
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kScanThreads) msm_scan_kernel(uint32_t* __restrict__ counts, uint32_t n, uint32_t n_tiles,
+                                                                ScanState* __restrict__ stt, uint64_t* __restrict__ status,
+                                                                uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                                                                uint32_t* __restrict__ seg_offsets) {
+    __shared__ uint32_t s_tile, s_last;
+    __shared__ uint32_t s_hist[kSegBins];
+    __shared__ uint32_t s_wa[kScanThreads / 32], s_wb[kScanThreads / 32];
+    __shared__ uint32_t s_pa, s_pb;  // exclusive prefix of this tile
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&stt->ticket, 1u);
+    if (tid < kSegBins) s_hist[tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kScanTile + tid * kScanItems;
+    // n is a multiple of 16 (buckets per window are a power of two >= 32): a thread's items are all in or all out
+    uint32_t v[kScanItems], sv[kScanItems];
+    uint32_t a = 0, b = 0;
+    const bool in = base < n;
+    if (in) {
+        uint4* src = reinterpret_cast<uint4*>(counts + base);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; ++k) {
+            const uint4 q = src[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            src[k] = make_uint4(0u, 0u, 0u, 0u);  // the histogram is consumed: leave it zeroed for the next MSM
+        }
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const uint32_t cnt = v[k];
+            const uint32_t segs = (cnt + (uint32_t)kSegLen - 1u) / (uint32_t)kSegLen;
+            sv[k] = segs;
+            a += cnt;
+            b += segs;
+            if (segs) {  // near-equal split: rem segments of len + 1, the others of len
+                const uint32_t len = cnt / segs, rem = cnt % segs;
+                atomicAdd(&s_hist[len], segs - rem);
+                if (rem) atomicAdd(&s_hist[len + 1], rem);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) v[k] = sv[k] = 0;
+    }
+    // block-wide exclusive scan of the (a, b) pairs
+    uint32_t ia = a, ib = b;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, d), tb = __shfl_up_sync(0xffffffffu, ib, d);
+        if ((int)lane >= d) { ia += ta; ib += tb; }
     }
-    if (lane == 31) warp_sums[wid] = incl;
+    if (lane == 31) { s_wa[wid] = ia; s_wb[wid] = ib; }
     __syncthreads();
     if (wid == 0) {
-        uint32_t ws = lane < kScanThreads / 32 ? warp_sums[lane] : 0u;
-        uint32_t wi = ws;
+        const uint32_t wa = lane < kScanThreads / 32 ? s_wa[lane] : 0u, wb = lane < kScanThreads / 32 ? s_wb[lane] : 0u;
+        uint32_t xa = wa, xb = wb;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += t;
+        for (int d = 1; d < kScanThreads / 32; d <<= 1) {
+            const uint32_t ta = __shfl_up_sync(0xffffffffu, xa, d), tb = __shfl_up_sync(0xffffffffu, xb, d);
+            if ((int)lane >= d) { xa += ta; xb += tb; }
         }
-        if (lane < kScanThreads / 32) warp_sums[lane] = wi - ws;  // exclusive warp offsets
-        if (lane == kScanThreads / 32 - 1) *total = wi;
+        if (lane < kScanThreads / 32) { s_wa[lane] = xa - wa; s_wb[lane] = xb - wb; }
+        const uint32_t tot_a = __shfl_sync(0xffffffffu, xa, kScanThreads / 32 - 1);
+        const uint32_t tot_b = __shfl_sync(0xffffffffu, xb, kScanThreads / 32 - 1);
+        // decoupled look-back
+        uint32_t pa = 0, pb = 0;
+        if (tile == 0) {
+            if (lane == 0) st_status(status, status_pack(2u, tot_a, tot_b));
+        } else {
+            if (lane == 0) st_status(status + tile, status_pack(1u, tot_a, tot_b));
+            int look = (int)tile - 1;  // lane l inspects tile look - l
+            while (true) {
+                const int t = look - (int)lane;
+                uint64_t w = 0;
+                if (t >= 0) {
+                    do { w = ld_status(status + t); } while ((w >> 62) == 0);
+                } else {
+                    w = status_pack(2u, 0u, 0u);  // before tile 0: an empty inclusive prefix
+                }
+                const uint32_t is_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2u);
+                const int stop = __ffs(is_prefix) - 1;  // nearest tile that already knows its inclusive prefix
+                uint32_t ca = (int)lane <= stop ? (uint32_t)w : 0u, cb = (int)lane <= stop ? (uint32_t)(w >> 32) & 0x3fffffffu : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    ca += __shfl_xor_sync(0xffffffffu, ca, d);
+                    cb += __shfl_xor_sync(0xffffffffu, cb, d);
+                }
+                pa += ca;
+                pb += cb;
+                if (stop >= 0) break;  // (always true once the window reaches below tile 0)
+                look -= 32;
+            }
+            if (lane == 0) st_status(status + tile, status_pack(2u, pa + tot_a, pb + tot_b));
+        }
+        if (lane == 0) { s_pa = pa; s_pb = pb; }
     }
     __syncthreads();
-    const uint32_t r = incl - v + warp_sums[wid];
+    if (in) {
+        uint32_t ea = s_pa + s_wa[wid] + (ia - a), eb = s_pb + s_wb[wid] + (ib - b);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            offsets[base + k] = ea;
+            cursor[base + k] = ea;
+            seg_offsets[base + k] = eb;
+            ea += v[k];
+            eb += sv[k];
+        }
+        if (base + kScanItems == n) {  // the last in-range thread closes both arrays
+            offsets[n] = ea;
+            seg_offsets[n] = eb;
+        }
+    }
+    if (tid < kSegBins && s_hist[tid]) atomicAdd(&stt->seg_hist[tid], s_hist[tid]);
+    __threadfence();
     __syncthreads();
-    return r;
-}
-
-// scan inputs: the bucket histogram itself, or the per-bucket segment count derived from offsets
-struct ScanCounts {
-    const uint32_t* p;
-    __device__ __forceinline__ uint32_t operator()(size_t i) const { return p[i]; }
-};
-struct ScanSegCounts {  // ceil(bucket size / kSegLen)
-    const uint32_t* offsets;
-    __device__ __forceinline__ uint32_t operator()(size_t i) const {
-        return (offsets[i + 1] - offsets[i] + (uint32_t)kSegLen - 1u) / (uint32_t)kSegLen;
-    }
-};
-
-template <class In>
-__global__ void scan_chunk_sums_kernel(In in, size_t n, uint32_t* chunk_sums) {
-    __shared__ uint32_t total;
-    const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
-        if (base + k < n) s += in(base + k);
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
-}
-
-__global__ void scan_chunk_offsets_kernel(uint32_t* chunk_sums, size_t n_chunks) {
-    // single block; serial over tiles of kScanThreads chunks
-    __shared__ uint32_t total;
-    uint32_t running = 0;
-    for (size_t base = 0; base < n_chunks; base += kScanThreads) {
-        const size_t i = base + threadIdx.x;
-        const uint32_t v = i < n_chunks ? chunk_sums[i] : 0u;
-        const uint32_t ex = block_exclusive_scan(v, &total);
-        if (i < n_chunks) chunk_sums[i] = running + ex;
-        running += total;
-        __syncthreads();
-    }
-}
-
-template <class In>
-__global__ void scan_apply_kernel(In in, size_t n, const uint32_t* chunk_offsets,
-                                  uint32_t* out /* n + 1 */) {
-    __shared__ uint32_t total;
-    const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = base + k < n ? in(base + k) : 0u;
-        s += v[k];
-    }
-    uint32_t ex = block_exclusive_scan(s, &total) + chunk_offsets[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < n) out[base + k] = ex;
-        ex += v[k];
-        if (base + k == n - 1) out[n] = ex;
+    if (tid == 0) s_last = atomicAdd(&stt->done, 1u) == n_tiles - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {  // every tile has finished its look-back and added its segment histogram
+        __threadfence();
+        for (uint32_t t = tid; t < n_tiles; t += kScanThreads) status[t] = 0;
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int l = kSegLen; l >= 0; --l) {  // start offsets, longest segments first
+                const uint32_t c = reinterpret_cast<volatile uint32_t*>(stt->seg_hist)[l];
+                stt->seg_starts[l] = run;
+                run += c;
+            }
+            for (uint32_t l = 0; l < kSegBins; ++l) stt->seg_hist[l] = 0;
+            stt->heavy_count = 0;
+            stt->ticket = 0;
+            stt->done = 0;
+        }
     }
 }
 
@@ -208,60 +281,42 @@ __device__ __forceinline__ g1_affine load_entry_point(const g1_affine* tables, s
     return g1_affine_load_ro(tables + table * n + idx);
 }
 
-// seg_bucket[s] = bucket owning segment s
-__global__ void msm_segfill_kernel(const uint32_t* __restrict__ seg_offsets, uint32_t n_buckets,
-                                   uint32_t* __restrict__ seg_bucket) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    const uint32_t s0 = seg_offsets[b], s1 = seg_offsets[b + 1];
-    for (uint32_t s = s0; s < s1; ++s) seg_bucket[s] = b;
-}
-
 // Segment lengths differ (Poisson bucket sizes); lanes of a warp that fold different numbers of
-// points idle in lockstep.  A counting sort of the segment ids by length (kSegLen+1 bins, longest
-// first) hands every warp segments of equal length.
-__device__ __forceinline__ uint32_t segment_length(const uint32_t* offsets, const uint32_t* seg_offsets, uint32_t b,
-                                                   uint32_t s) {
-    const uint32_t j = s - seg_offsets[b], k = seg_offsets[b + 1] - seg_offsets[b];
-    const uint32_t cnt = offsets[b + 1] - offsets[b];
-    return cnt / k + (j < cnt % k ? 1u : 0u);
-}
-__global__ void msm_seglen_hist_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ seg_offsets,
-                                       const uint32_t* __restrict__ seg_bucket, uint32_t n_buckets,
-                                       uint32_t* __restrict__ hist /* kSegLen + 1 bins */) {
-    __shared__ uint32_t sh[kSegLen + 1];
-    if (threadIdx.x <= kSegLen) sh[threadIdx.x] = 0;
+// points idle in lockstep.  A counting sort of the segment ids by length (kSegLen + 1 bins, longest
+// first; bin starts from msm_scan_kernel) hands every warp segments of equal length.  One thread per
+// bucket: a bucket of cnt entries in k segments has rem = cnt % k segments of cnt / k + 1 entries, then
+// k - rem of cnt / k.  Slots are claimed per block (shared-memory ranks, one global atomic per block and
+// length) and the same thread records seg_bucket[s] = bucket owning segment s.
+__global__ void __launch_bounds__(256) msm_segorder_kernel(const uint32_t* __restrict__ offsets,
+                                                           const uint32_t* __restrict__ seg_offsets, uint32_t n_buckets,
+                                                           uint32_t* __restrict__ seg_cursor /* kSegBins */,
+                                                           uint32_t* __restrict__ seg_bucket, uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_cnt[kSegBins], s_base[kSegBins];
+    if (threadIdx.x < kSegBins) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < seg_offsets[n_buckets]) atomicAdd(&sh[segment_length(offsets, seg_offsets, seg_bucket[s], s)], 1u);
-    __syncthreads();
-    if (threadIdx.x <= kSegLen && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
-}
-// hist -> start offsets, longest length first (single small block)
-__global__ void msm_seglen_starts_kernel(uint32_t* hist) {
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int l = kSegLen; l >= 0; --l) {
-            const uint32_t c = hist[l];
-            hist[l] = run;
-            run += c;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t k = 0, s0 = 0, len = 0, rem = 0, r0 = 0, r1 = 0;
+    if (b < n_buckets) {
+        s0 = seg_offsets[b];
+        k = seg_offsets[b + 1] - s0;
+        if (k) {
+            const uint32_t cnt = offsets[b + 1] - offsets[b];
+            len = cnt / k;
+            rem = cnt % k;
+            r0 = atomicAdd(&s_cnt[len], k - rem);
+            if (rem) r1 = atomicAdd(&s_cnt[len + 1], rem);
         }
     }
-}
-__global__ void msm_seglen_scatter_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ seg_offsets,
-                                          const uint32_t* __restrict__ seg_bucket, uint32_t n_buckets,
-                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= seg_offsets[n_buckets]) return;
-    const uint32_t len = segment_length(offsets, seg_offsets, seg_bucket[s], s);
-    // warp-aggregated: lanes with the same length take consecutive slots with one atomic
-    const uint32_t active = __activemask();
-    const uint32_t peers = __match_any_sync(active, len);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[len], (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    order[base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u))] = s;
+    __syncthreads();
+    if (threadIdx.x < kSegBins && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&seg_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (k) {
+        const uint32_t slot1 = rem ? s_base[len + 1] + r1 : 0u, slot0 = s_base[len] + r0;
+        for (uint32_t j = 0; j < k; ++j) {
+            seg_bucket[s0 + j] = b;
+            order[j < rem ? slot1 + j : slot0 + (j - rem)] = s0 + j;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ entries,
@@ -353,120 +408,120 @@ __global__ void __launch_bounds__(kReduceThreads) msm_heavy_combine_kernel(const
 }
 
 // ---- bucket reduction: sum_k (k+1) * B[k] per physical window -----------------------------------
-// These kernels are latency-bound (one warp per SM sub-partition walking a chain of dependent XYZZ
-// operations), so the formulation minimises the LENGTH of that chain, not the operation count:
-//   thread t = bx*T + tid owns buckets [tK, (t+1)K): running sums give S_t = sum B and
-//   A_t = sum (i+1) B[tK+i]; the window total is sum_t A_t + K * sum_t t * S_t.
-//   sum_t t*S_t = T * sum_bx bx * (sum_tid S) + sum_bx sum_tid tid * S, and a weighted sum
-//   sum_i i*X_i equals the sum of the inclusive suffix sums R_1 + R_2 + ... — a log-depth block scan
-//   instead of a per-thread double-and-add by the chunk index (2(c-1) dependent operations).
-// Chain per window: 2K (chunk) + log T (scan) + log K + 1 + log T (tree), then the same scan + tree
-// once more over the per-block totals in msm_reduce_final_kernel.
-constexpr int ilog2_c(unsigned v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
-constexpr int kReduceThreadsLog = ilog2_c(kReduceThreads);
-static_assert((1 << kReduceThreadsLog) == kReduceThreads, "reduction block size is a power of two");
+// View a window's H = 2^(c-1) buckets as a matrix M[hi][lo] with L = 2^l columns (k = hi * L + lo):
+//     sum_k (k + 1) B[k] = L * sum_hi hi * R[hi] + sum_lo (lo + 1) * C[lo],
+// R = row sums, C = column sums.  Every bucket enters exactly two additions (its row tree and its column
+// tree), and the trees are plain sums: all of their work is data-parallel with dependent chains of at most
+// 7 additions per level (fan-in <= 8) — instead of a running sum whose chain is as long as a thread's chunk.
+// What is left is two weighted sums over 2^l / 2^(c-1-l) elements (<= 256 each up to c = 17), one block per
+// window (msm_window_finish_kernel).
+//   msm_tree_kernel, one launch per level, both trees side by side:
+//     out[a * inner + b] = sum_{j < T} in[(a * T + j) * inner + b]
+//   row tree: inner = 1 (sums of T neighbours over the flat bucket array; L is a multiple of every T, so a
+//   group never straddles a row or a window); column tree: inner = L (sums of T consecutive rows).
+struct TreeLevel {
+    const g1_xyzz* in;
+    g1_xyzz* out;
+    uint32_t n_out, t_log, inner_log, n_blocks;
+};
+struct TreeArgs {
+    TreeLevel row, col;
+};
+constexpr int kTreeThreads = 128;
 
-// v_tid <- sum_{j >= tid} v_j over the block (Hillis–Steele); entries at index >= valid are the identity
-__device__ __forceinline__ g1_xyzz block_suffix_scan(g1_xyzz v, g1_xyzz* sh, uint32_t valid) {
+__global__ void __launch_bounds__(kTreeThreads) msm_tree_kernel(TreeArgs a) {
+    const bool is_row = blockIdx.x < a.row.n_blocks;
+    const TreeLevel& lv = is_row ? a.row : a.col;
+    const uint32_t t = (is_row ? blockIdx.x : blockIdx.x - a.row.n_blocks) * kTreeThreads + threadIdx.x;
+    if (t >= lv.n_out) return;
+    const uint32_t inner_mask = (1u << lv.inner_log) - 1u;
+    const size_t first = (((size_t)(t >> lv.inner_log) << lv.t_log) << lv.inner_log) | (t & inner_mask);
+    const size_t stride = (size_t)1 << lv.inner_log;
+    const uint32_t T = 1u << lv.t_log;
+    const g1_xyzz* p = lv.in + first;
+    g1_xyzz acc = g1_xyzz_load(p);
+    g1_xyzz next = T > 1 ? g1_xyzz_load(p + stride) : acc;
+#pragma unroll 1
+    for (uint32_t j = 1; j < T; ++j) {
+        const g1_xyzz cur = next;
+        if (j + 1 < T) next = g1_xyzz_load(p + (size_t)(j + 1) * stride);  // prefetch under the addition
+        acc = g1_add(acc, cur);
+    }
+    g1_xyzz_store(lv.out + t, acc);
+}
+
+// One block per window, 2 * kFinishHalf threads: threads [0, kFinishHalf) fold the column sums C (weights
+// lo + 1), threads [kFinishHalf, 2 kFinishHalf) the row sums R (weights hi), each with
+//     sum_i w_i X_i = sum_t A_t + K * sum_{t >= 1} Suf_t,
+// thread t owning K consecutive elements (K = 1 up to c = 17): S_t their sum, A_t their locally weighted sum
+// (running sums), Suf_t = sum_{u >= t} S_u from a Hillis–Steele suffix scan, then a tree over the threads.
+// Every step is "fetch one operand from shared memory, one addition", so the XYZZ addition is inlined once.
+constexpr int kFinishHalf = 256;
+constexpr int kFinishHalfLog = 8;
+
+__global__ void __launch_bounds__(2 * kFinishHalf) msm_window_finish_kernel(const g1_xyzz* __restrict__ col_sums, uint32_t l_log,
+                                                                            const g1_xyzz* __restrict__ row_sums, uint32_t r_log,
+                                                                            g1_xyzz* __restrict__ window_sums) {
+    extern __shared__ uint4 finish_smem[];
+    g1_xyzz* sh = reinterpret_cast<g1_xyzz*>(finish_smem);  // 2 * kFinishHalf entries
+    const uint32_t window = blockIdx.x;
+    const uint32_t part = threadIdx.x >> kFinishHalfLog;  // 0: columns (weights i + 1), 1: rows (weights i)
+    const uint32_t t = threadIdx.x & (kFinishHalf - 1);
+    const uint32_t n_log = part ? r_log : l_log;
+    const uint32_t k_log = n_log > (uint32_t)kFinishHalfLog ? n_log - kFinishHalfLog : 0u;  // elements per thread
+    const uint32_t K = 1u << k_log;
+    const uint32_t n_threads = 1u << (n_log - k_log);  // threads of this half that own elements
+    const g1_xyzz* X = (part ? row_sums : col_sums) + ((size_t)window << n_log);
+    g1_xyzz S = g1_xyzz_inf(), A = g1_xyzz_inf();
+    if (t < n_threads) {
+        if (K == 1) {
+            S = g1_xyzz_load(X + t);
+            if (!part) A = S;
+        } else {  // large windows only (c >= 18): local running sums
+            const g1_xyzz* c = X + ((size_t)t << k_log);
+#pragma unroll 1
+            for (int i = (int)K - 1; i >= 0; --i) {
+                if (part) A = xyzz_add(A, S);  // weights i
+                S = xyzz_add(S, g1_xyzz_load(c + i));
+                if (!part) A = xyzz_add(A, S);  // weights i + 1
+            }
+        }
+    }
+    // step list: log2(n_threads) scan steps, one "switch" step, kFinishHalfLog tree steps
+    g1_xyzz v = S;
     sh[threadIdx.x] = v;
     __syncthreads();
-    for (uint32_t d = 1; d < (uint32_t)kReduceThreads && d < valid; d <<= 1) {
-        const bool has = threadIdx.x + d < (uint32_t)kReduceThreads;
+    const int scan_steps_max = kFinishHalfLog;
+    const uint32_t half_base = part << kFinishHalfLog;
+#pragma unroll 1
+    for (int step = 0; step < 2 * scan_steps_max + 1; ++step) {
         g1_xyzz o = g1_xyzz_inf();
-        if (has) o = sh[threadIdx.x + d];
+        if (step < scan_steps_max) {  // suffix scan: v_t += v_{t + d}
+            const uint32_t d = 1u << step;
+            if (d < n_threads && t + d < n_threads) o = sh[threadIdx.x + d];
+        } else if (step == scan_steps_max) {
+            // v = Suf_t.  Switch to the summands of the final tree: K * Suf_t (t >= 1) + A_t
+            if (t == 0) v = g1_xyzz_inf();
+#pragma unroll 1
+            for (uint32_t i = 0; i < k_log; ++i) v = xyzz_dbl(v);
+            o = A;
+        } else {  // tree: v_t += v_{t + stride}
+            const uint32_t stride = (uint32_t)kFinishHalf >> (step - scan_steps_max);
+            if (t < stride) o = sh[half_base + t + stride];
+        }
         __syncthreads();
-        v = xyzz_add(v, o);
+        v = g1_add(v, o);
         sh[threadIdx.x] = v;
         __syncthreads();
     }
-    return v;
-}
-
-// partials[(window * gridDim.x + bx) * 2 + {0, 1}] = { V_bx, (K*T) * sum_tid S }  with
-// V_bx = sum_tid (A_tid + K * R_tid [tid >= 1])
-__global__ void __launch_bounds__(kReduceThreads) msm_reduce_kernel(const g1_xyzz* __restrict__ buckets,
-                                                                    uint32_t buckets_per_window, int chunk_log,
-                                                                    g1_xyzz* __restrict__ partials) {
-    __shared__ g1_xyzz sh[kReduceThreads];
-    const uint32_t window = blockIdx.y;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t chunk = 1u << chunk_log;
-    const uint32_t first = t << chunk_log;
-    const uint32_t threads_needed = (buckets_per_window + chunk - 1) >> chunk_log;
-    const uint32_t valid = min((uint32_t)kReduceThreads, threads_needed - blockIdx.x * blockDim.x);
-    g1_xyzz run = g1_xyzz_inf(), acc = g1_xyzz_inf();
-    if (first < buckets_per_window) {
-        const g1_xyzz* B = buckets + (size_t)window * buckets_per_window + first;
-        const uint32_t cnt = min(chunk, buckets_per_window - first);
-        for (int i = (int)cnt - 1; i >= 0; --i) {
-            run = xyzz_add(run, g1_xyzz_load(B + i));
-            acc = xyzz_add(acc, run);
-        }
-    }
-    const g1_xyzz R = block_suffix_scan(run, sh, valid);
-    g1_xyzz V = acc;
-    if (threadIdx.x >= 1 && threadIdx.x < valid) {
-        g1_xyzz kr = R;
+    // thread 0 holds sum (lo + 1) C[lo]; thread kFinishHalf holds sum hi R[hi], still to be scaled by L
+    if (threadIdx.x == kFinishHalf) {
 #pragma unroll 1
-        for (int i = 0; i < chunk_log; ++i) kr = xyzz_dbl(kr);
-        V = xyzz_add(V, kr);
+        for (uint32_t i = 0; i < l_log; ++i) v = xyzz_dbl(v);
+        sh[kFinishHalf] = v;
     }
-    // the block total, scaled by K*T, is produced by the last thread (its warp has no part in the tree
-    // below) while the first warps fold V: its doublings are spread over the tree levels
-    g1_xyzz Tp = g1_xyzz_inf();
-    if (threadIdx.x == kReduceThreads - 1) Tp = sh[0];
     __syncthreads();
-    sh[threadIdx.x] = V;
-    __syncthreads();
-    int dleft = chunk_log + kReduceThreadsLog, levels_left = kReduceThreadsLog;
-    for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1, --levels_left) {
-        if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
-        if (threadIdx.x == kReduceThreads - 1) {
-            const int per = (dleft + levels_left - 1) / levels_left;
-            for (int i = 0; i < per; ++i) Tp = xyzz_dbl(Tp);
-            dleft -= per;
-        }
-        __syncthreads();
-    }
-    g1_xyzz* out = partials + ((size_t)window * gridDim.x + blockIdx.x) * 2;
-    if (threadIdx.x == 0) g1_xyzz_store(out, sh[0]);
-    if (threadIdx.x == kReduceThreads - 1) g1_xyzz_store(out + 1, Tp);
-}
-
-// window sum = sum_b V_b + sum_b b * T'_b.  Thread tid owns blocks tid, tid + T, ...: with
-// p = sum_m X_m and q = sum_m m * X_m (running sums), sum_b b * X_b = sum_{tid >= 1} R_tid + T * sum_tid q_tid.
-__global__ void __launch_bounds__(kReduceThreads) msm_reduce_final_kernel(const g1_xyzz* __restrict__ partials,
-                                                                          uint32_t n_blocks,
-                                                                          g1_xyzz* __restrict__ window_sums) {
-    __shared__ g1_xyzz sh[kReduceThreads];
-    const uint32_t window = blockIdx.x;
-    const g1_xyzz* P = partials + (size_t)window * n_blocks * 2;
-    const int rounds = (int)((n_blocks + kReduceThreads - 1) / kReduceThreads);
-    g1_xyzz vsum = g1_xyzz_inf(), p = g1_xyzz_inf(), q = g1_xyzz_inf();
-    for (int m = rounds - 1; m >= 0; --m) {
-        const uint32_t j = threadIdx.x + (uint32_t)m * kReduceThreads;
-        if (j < n_blocks) {
-            vsum = xyzz_add(vsum, g1_xyzz_load(P + 2 * (size_t)j));
-            p = xyzz_add(p, g1_xyzz_load(P + 2 * (size_t)j + 1));
-        }
-        if (m > 0) q = xyzz_add(q, p);
-    }
-    const uint32_t valid = min((uint32_t)kReduceThreads, n_blocks);
-    const g1_xyzz R = block_suffix_scan(p, sh, valid);
-    g1_xyzz W = vsum;
-    if (threadIdx.x >= 1 && threadIdx.x < valid) W = xyzz_add(W, R);
-    if (rounds > 1) {
-#pragma unroll 1
-        for (int i = 0; i < kReduceThreadsLog; ++i) q = xyzz_dbl(q);
-        W = xyzz_add(W, q);
-    }
-    sh[threadIdx.x] = W;
-    __syncthreads();
-    for (int stride = kReduceThreads / 2; stride > 0; stride >>= 1) {
-        if ((int)threadIdx.x < stride) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + stride]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) g1_xyzz_store(window_sums + window, sh[0]);
+    if (threadIdx.x == 0) g1_xyzz_store(window_sums + window, xyzz_add(v, sh[kFinishHalf]));
 }
 
 // ---- window tables: table[j][i] = 2^(shift*j) * P_i (affine) -------------------------------------
@@ -644,7 +699,10 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
     if (check_on_curve) {  // srs.rs:178-179 asserts every SRS point is on the curve
         uint32_t* d_bad = nullptr;
         uint32_t h_bad = 0;
-        cudaMalloc(&d_bad, 4);
+        if ((e = cudaMalloc(&d_bad, 4)) != cudaSuccess) {
+            cudaFree(d_pts);
+            return cuda_fail(e, "cudaMalloc(on-curve flag)");
+        }
         cudaMemsetAsync(d_bad, 0, 4, st);
         g1_on_curve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pts, n, d_bad);
         cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
@@ -665,31 +723,182 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
     return rc;
 }
 
-template <class In>
-static int exclusive_scan_u32(In d_in, size_t n, uint32_t* d_out, DevBuf* chunk_buf,
-                              cudaStream_t st) {
-    const size_t n_chunks = (n + kScanChunk - 1) / kScanChunk;
-    int rc = chunk_buf->reserve(n_chunks * sizeof(uint32_t));
-    if (rc != B200_OK) return rc;
-    uint32_t* chunk = (uint32_t*)chunk_buf->p;
-    scan_chunk_sums_kernel<In><<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk);
-    scan_chunk_offsets_kernel<<<1, kScanThreads, 0, st>>>(chunk, n_chunks);
-    scan_apply_kernel<In><<<(unsigned)n_chunks, kScanThreads, 0, st>>>(d_in, n, chunk, d_out);
-    return B200_OK;
+// Bits of the column index (l) and the per-level fan-in bits of the two reduction trees.
+static void tree_shape(int c, int* l_log, int* r_log, int* levels, int row_bits[8], int col_bits[8]) {
+    const int bits = c - 1;
+    const int l = (bits + 1) / 2, r = bits - l;
+    int K = (l + 2) / 3;  // fan-in <= 8
+    if (K < 1) K = 1;
+    for (int i = 0; i < K; ++i) {
+        row_bits[i] = l / K + (i < l % K ? 1 : 0);
+        col_bits[i] = r / K + (i < r % K ? 1 : 0);
+    }
+    *l_log = l;
+    *r_log = r;
+    *levels = K;
 }
 
 // `batch` MSMs over the same bases (scalar vectors `stride` elements apart) in one pass: the
 // digit sort, the bucket folding and the reduction each run once over batch * buckets buckets,
 // which is what fills 148 SMs at the prover's 2^16-point sizes.
-int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
-                     unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st, g1_affine* out,
-                     int* out_inf) {
+//
+// msm_launch_batch only ENQUEUES (kernels + one D2H of the window sums into pinned memory);
+// msm_finish_batch waits for that copy and runs the host epilogue.  The prover queues further
+// work between the two.
+int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
+                     unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st) {
     if (base_off + n > b->n) {
         set_error("msm: base_off + n exceeds the loaded bases");
         return B200_ERR_INVALID;
     }
+    s->pending_batch = 0;
     if (batch == 0) return B200_OK;
-    if (n == 0) {
+    s->pending_plan = b->plan;
+    s->pending_n = n;
+    s->pending_batch = batch;
+    if (n == 0) return B200_OK;
+    const MsmPlan& pl = b->plan;
+    const uint32_t half = 1u << (pl.c - 1);
+    const size_t buckets_per_msm = (size_t)pl.n_phys * half;
+    const size_t n_buckets = buckets_per_msm * batch;
+    const size_t n_windows = (size_t)pl.n_phys * batch;
+    const size_t max_entries = n * (size_t)pl.n_digits * batch;
+    // segments: at most floor(entries / kSegLen) full ones plus one partial per bucket
+    const size_t max_segs = max_entries / kSegLen + n_buckets;
+    if (max_entries >= ((size_t)1 << 32) || n_buckets >= ((size_t)1 << 31) || max_segs >= ((size_t)1 << 30)) {
+        set_error("msm: batch * n * windows exceeds the 2^32-entry / 2^30-segment index space");
+        return B200_ERR_INVALID;
+    }
+    int rc;
+    const size_t n_tiles = (n_buckets + kScanTile - 1) / kScanTile;
+    if (s->counts.cap < n_buckets * 4) {  // a fresh histogram starts zeroed; every MSM leaves it zeroed
+        if ((rc = s->counts.reserve(n_buckets * 4)) != B200_OK) return rc;
+        B200_CUDA(cudaMemsetAsync(s->counts.p, 0, s->counts.cap, st));
+    }
+    if (s->scan_state.cap < sizeof(ScanState) + n_tiles * 8) {
+        if ((rc = s->scan_state.reserve(sizeof(ScanState) + n_tiles * 8 + 1024)) != B200_OK) return rc;
+        B200_CUDA(cudaMemsetAsync(s->scan_state.p, 0, s->scan_state.cap, st));
+    }
+    if ((rc = s->offsets.reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
+    if ((rc = s->cursor.reserve(n_buckets * 4)) != B200_OK) return rc;
+    if ((rc = s->entries.reserve(max_entries * 4)) != B200_OK) return rc;
+    if ((rc = s->buckets.reserve(n_buckets * sizeof(g1_xyzz))) != B200_OK) return rc;
+    const size_t max_heavy = max_segs / (kCombineSeq + 1) + 1;
+    if ((rc = s->seg_offsets.reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
+    if ((rc = s->seg_bucket.reserve(max_segs * 4)) != B200_OK) return rc;
+    if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
+    if ((rc = s->seg_order.reserve(max_segs * 4)) != B200_OK) return rc;
+    int l_log, r_log, levels, row_bits[8], col_bits[8];
+    tree_shape(pl.c, &l_log, &r_log, &levels, row_bits, col_bits);
+    // tree outputs: each level shrinks its input by its fan-in; a level with fan-in 1 is skipped
+    size_t tree_elems = 0;
+    {
+        size_t rn = n_buckets, cn = n_buckets;
+        for (int i = 0; i < levels; ++i) {
+            if (row_bits[i]) { rn >>= row_bits[i]; tree_elems += rn; }
+            if (col_bits[i]) { cn >>= col_bits[i]; tree_elems += cn; }
+        }
+    }
+    if ((rc = s->tree.reserve((tree_elems + 1) * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->h_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if (!s->done_ev) B200_CUDA(cudaEventCreateWithFlags(&s->done_ev, cudaEventDisableTiming));
+    if (!s->finish_attr_set) {
+        B200_CUDA(cudaFuncSetAttribute(msm_window_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(2 * kFinishHalf * sizeof(g1_xyzz))));
+        s->finish_attr_set = true;
+    }
+
+    uint32_t* counts = (uint32_t*)s->counts.p;
+    uint32_t* offsets = (uint32_t*)s->offsets.p;
+    uint32_t* cursor = (uint32_t*)s->cursor.p;
+    uint32_t* entries = (uint32_t*)s->entries.p;
+    g1_xyzz* buckets = (g1_xyzz*)s->buckets.p;
+    g1_xyzz* window_sums = (g1_xyzz*)s->window_sums.p;
+    uint32_t* seg_offsets = (uint32_t*)s->seg_offsets.p;
+    uint32_t* seg_bucket = (uint32_t*)s->seg_bucket.p;
+    g1_xyzz* seg_sums = (g1_xyzz*)s->seg_sums.p;
+    ScanState* stt = (ScanState*)s->scan_state.p;
+    uint64_t* status = (uint64_t*)((char*)s->scan_state.p + sizeof(ScanState));
+    uint32_t* heavy_list = (uint32_t*)s->heavy.p;
+    uint32_t* seg_order = (uint32_t*)s->seg_order.p;
+
+    if (s->timing && !s->ev_init) {
+        for (auto& e : s->ev) B200_CUDA(cudaEventCreate(&e));
+        s->ev_init = true;
+    }
+    if (s->timing) cudaEventRecord(s->ev[0], st);
+    const unsigned bs = 256;
+    const dim3 grid_n((unsigned)((n + bs - 1) / bs), batch);
+    msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)buckets_per_msm, counts);
+    msm_scan_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(counts, (uint32_t)n_buckets, (uint32_t)n_tiles, stt, status,
+                                                                offsets, cursor, seg_offsets);
+    msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)base_off,
+                                              (uint32_t)buckets_per_msm, cursor, entries);
+    msm_segorder_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(offsets, seg_offsets, (uint32_t)n_buckets,
+                                                                             stt->seg_starts, seg_bucket, seg_order);
+    // the long kernels of the MSM go to the low-priority companion stream (see b200_init)
+    cudaStream_t hv = s->hv_stream ? s->hv_stream : st;
+    if (s->timing) cudaEventRecord(s->ev[1], st);
+    if (s->hv_stream) {
+        cudaEventRecord(s->hv_fork, st);
+        cudaStreamWaitEvent(hv, s->hv_fork, 0);
+    }
+    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
+        entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
+    if (s->hv_stream) {
+        cudaEventRecord(s->hv_join, hv);
+        cudaStreamWaitEvent(st, s->hv_join, 0);
+    }
+    msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
+        seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, &stt->heavy_count, heavy_list);
+    msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 592), kReduceThreads, 0, st>>>(
+        seg_sums, seg_offsets, &stt->heavy_count, heavy_list, buckets);
+    if (s->timing) cudaEventRecord(s->ev[2], st);
+    {
+        const g1_xyzz *row_in = buckets, *col_in = buckets;
+        g1_xyzz* next = (g1_xyzz*)s->tree.p;
+        size_t rn = n_buckets, cn = n_buckets;
+        for (int i = 0; i < levels; ++i) {
+            TreeArgs a;
+            a.row = TreeLevel{row_in, next, 0, (uint32_t)row_bits[i], 0, 0};
+            if (row_bits[i]) {
+                rn >>= row_bits[i];
+                a.row.n_out = (uint32_t)rn;
+                row_in = next;
+                next += rn;
+            }
+            a.col = TreeLevel{col_in, next, 0, (uint32_t)col_bits[i], (uint32_t)l_log, 0};
+            if (col_bits[i]) {
+                cn >>= col_bits[i];
+                a.col.n_out = (uint32_t)cn;
+                col_in = next;
+                next += cn;
+            }
+            a.row.n_blocks = (a.row.n_out + kTreeThreads - 1) / kTreeThreads;
+            a.col.n_blocks = (a.col.n_out + kTreeThreads - 1) / kTreeThreads;
+            if (a.row.n_blocks + a.col.n_blocks)
+                msm_tree_kernel<<<a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st>>>(a);
+        }
+        // row_in: R[window][2^r_log], col_in: C[window][2^l_log]
+        msm_window_finish_kernel<<<(unsigned)n_windows, 2 * kFinishHalf, 2 * kFinishHalf * sizeof(g1_xyzz), st>>>(
+            col_in, (uint32_t)l_log, row_in, (uint32_t)r_log, window_sums);
+    }
+    B200_CUDA(cudaGetLastError());
+    if (s->timing) cudaEventRecord(s->ev[3], st);
+    B200_CUDA(cudaMemcpyAsync(s->h_sums.p, window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
+    if (s->timing) cudaEventRecord(s->ev[4], st);
+    B200_CUDA(cudaEventRecord(s->done_ev, st));
+    s->n_kernel_launches += 9 + (uint64_t)levels;
+    return B200_OK;
+}
+
+int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf) {
+    const unsigned batch = s->pending_batch;
+    s->pending_batch = 0;
+    if (batch == 0) return B200_OK;
+    if (s->pending_n == 0) {
         for (unsigned i = 0; i < batch; ++i) {
             out[i].x = fe_zero();
             out[i].y = fe_zero();
@@ -697,127 +906,26 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         }
         return B200_OK;
     }
-    const MsmPlan& pl = b->plan;
-    const uint32_t half = 1u << (pl.c - 1);
-    const size_t buckets_per_msm = (size_t)pl.n_phys * half;
-    const size_t n_buckets = buckets_per_msm * batch;
-    const size_t n_windows = (size_t)pl.n_phys * batch;
-    const size_t max_entries = n * (size_t)pl.n_digits * batch;
-    if (max_entries >= ((size_t)1 << 32) || n_buckets >= ((size_t)1 << 31)) {
-        set_error("msm: batch * n * windows exceeds 2^32 entries");
-        return B200_ERR_INVALID;
-    }
-    int rc;
-    if ((rc = s->counts.reserve(n_buckets * 4)) != B200_OK) return rc;
-    if ((rc = s->offsets.reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
-    if ((rc = s->cursor.reserve(n_buckets * 4)) != B200_OK) return rc;
-    if ((rc = s->entries.reserve(max_entries * 4)) != B200_OK) return rc;
-    if ((rc = s->buckets.reserve(n_buckets * sizeof(g1_xyzz))) != B200_OK) return rc;
-    // segments: at most floor(entries / kSegLen) full ones plus one partial per bucket
-    const size_t max_segs = max_entries / kSegLen + n_buckets;
-    const size_t max_heavy = max_segs / (kCombineSeq + 1) + 1;
-    if ((rc = s->seg_offsets.reserve((n_buckets + 1) * 4)) != B200_OK) return rc;
-    if ((rc = s->seg_bucket.reserve(max_segs * 4)) != B200_OK) return rc;
-    if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
-    if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
-    if ((rc = s->seg_order.reserve((max_segs + kSegLen + 2) * 4)) != B200_OK) return rc;
-    // lone MSM: short chains while the reduction is latency-bound (<= 2^16 buckets -> <= 128 blocks); with more
-    // buckets the blocks outnumber the SMs and the operation count takes over, as inside the prover
-    int chunk_log = s->reduce_chunk_log > 0 ? s->reduce_chunk_log
-                                            : std::min(kMsmReduceChunkLogThroughput, std::max(kReduceChunkLogLatency, pl.c - 15));
-    while (chunk_log > 0 && (half >> chunk_log) < 32) --chunk_log;  // tiny windows: keep a warp's worth of threads
-    const uint32_t reduce_threads_needed = (half + (1u << chunk_log) - 1) >> chunk_log;
-    const uint32_t reduce_blocks = (reduce_threads_needed + kReduceThreads - 1) / kReduceThreads;
-    if ((rc = s->partials.reserve(n_windows * reduce_blocks * 2 * sizeof(g1_xyzz))) != B200_OK) return rc;
-    if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
-
-    uint32_t* counts = (uint32_t*)s->counts.p;
-    uint32_t* offsets = (uint32_t*)s->offsets.p;
-    uint32_t* cursor = (uint32_t*)s->cursor.p;
-    uint32_t* entries = (uint32_t*)s->entries.p;
-    g1_xyzz* buckets = (g1_xyzz*)s->buckets.p;
-    g1_xyzz* partials = (g1_xyzz*)s->partials.p;
-    g1_xyzz* window_sums = (g1_xyzz*)s->window_sums.p;
-    uint32_t* seg_offsets = (uint32_t*)s->seg_offsets.p;
-    uint32_t* seg_bucket = (uint32_t*)s->seg_bucket.p;
-    g1_xyzz* seg_sums = (g1_xyzz*)s->seg_sums.p;
-    uint32_t* heavy_count = (uint32_t*)s->heavy.p;
-    uint32_t* heavy_list = heavy_count + 1;
-    uint32_t* seg_hist = (uint32_t*)s->seg_order.p;  // kSegLen + 1 bins, then the ordering itself
-    uint32_t* seg_order = seg_hist + kSegLen + 2;
-
-    if (s->timing && !s->ev_init) {
-        for (auto& e : s->ev) B200_CUDA(cudaEventCreate(&e));
-        s->ev_init = true;
-    }
-    if (s->timing) cudaEventRecord(s->ev[0], st);
-    B200_CUDA(cudaMemsetAsync(counts, 0, n_buckets * 4, st));
-    const unsigned bs = 256;
-    const dim3 grid_n((unsigned)((n + bs - 1) / bs), batch);
-    msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)buckets_per_msm, counts);
-    if ((rc = exclusive_scan_u32(ScanCounts{counts}, n_buckets, offsets, &s->block_sums, st)) != B200_OK) return rc;
-    B200_CUDA(cudaMemcpyAsync(cursor, offsets, n_buckets * 4, cudaMemcpyDeviceToDevice, st));
-    msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)base_off,
-                                              (uint32_t)buckets_per_msm, cursor, entries);
-    // the long kernels of the MSM go to the low-priority companion stream (see b200_init)
-    cudaStream_t hv = s->hv_stream ? s->hv_stream : st;
-    auto fork = [&]() {
-        if (s->hv_stream) {
-            cudaEventRecord(s->hv_fork, st);
-            cudaStreamWaitEvent(hv, s->hv_fork, 0);
-        }
-    };
-    auto join = [&]() {
-        if (s->hv_stream) {
-            cudaEventRecord(s->hv_join, hv);
-            cudaStreamWaitEvent(st, s->hv_join, 0);
-        }
-    };
-    if ((rc = exclusive_scan_u32(ScanSegCounts{offsets}, n_buckets, seg_offsets, &s->block_sums, st)) != B200_OK) return rc;
-    msm_segfill_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(seg_offsets, (uint32_t)n_buckets, seg_bucket);
-    B200_CUDA(cudaMemsetAsync(heavy_count, 0, 4, st));
-    B200_CUDA(cudaMemsetAsync(seg_hist, 0, (kSegLen + 2) * 4, st));
-    const unsigned seg_grid = (unsigned)((max_segs + 255) / 256);
-    msm_seglen_hist_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist);
-    msm_seglen_starts_kernel<<<1, 32, 0, st>>>(seg_hist);
-    msm_seglen_scatter_kernel<<<seg_grid, 256, 0, st>>>(offsets, seg_offsets, seg_bucket, (uint32_t)n_buckets, seg_hist, seg_order);
-    if (s->timing) cudaEventRecord(s->ev[1], st);
-    fork();
-    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
-        entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
-    join();
-    msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
-        seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, heavy_count, heavy_list);
-    msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 4096), kReduceThreads, 0, st>>>(
-        seg_sums, seg_offsets, heavy_count, heavy_list, buckets);
-    if (s->timing) cudaEventRecord(s->ev[2], st);
-    msm_reduce_kernel<<<dim3(reduce_blocks, (unsigned)n_windows), kReduceThreads, 0, st>>>(buckets, half, chunk_log, partials);
-    msm_reduce_final_kernel<<<(unsigned)n_windows, kReduceThreads, 0, st>>>(partials, reduce_blocks, window_sums);
-    B200_CUDA(cudaGetLastError());
-
-    std::vector<g1_xyzz> h_sums(n_windows);
-    if (s->timing) cudaEventRecord(s->ev[3], st);
-    B200_CUDA(cudaMemcpyAsync(h_sums.data(), window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
-    if (s->timing) cudaEventRecord(s->ev[4], st);
-    B200_CUDA(cudaStreamSynchronize(st));
+    const MsmPlan& pl = s->pending_plan;
+    B200_CUDA(cudaEventSynchronize(s->done_ev));
     if (s->timing) {
         cudaEventElapsedTime(&s->ms[0], s->ev[0], s->ev[4]);
         cudaEventElapsedTime(&s->ms[1], s->ev[0], s->ev[1]);
         cudaEventElapsedTime(&s->ms[2], s->ev[1], s->ev[2]);
         cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
         s->tot_acc_ms += s->ms[2];
-        s->tot_pairs += (double)n * batch;
+        s->tot_pairs += (double)s->pending_n * batch;
         s->tot_launches += 1;
     }
-
     // host epilogue: per MSM a Horner over the physical windows (none when fully precomputed), then
     // ONE field inversion for the whole batch (Montgomery's trick over the ZZZ coordinates) — a few
-    // hundred bytes of work.
+    // hundred bytes of work, read straight from the pinned copy of the window sums.
+    const g1_xyzz* h_sums = reinterpret_cast<const g1_xyzz*>(s->h_sums.p);
     std::vector<g1_xyzz> totals(batch);
     std::vector<fe> prefix(batch);
     fe run = fe_one<FqCfg>();
     for (unsigned i = 0; i < batch; ++i) {
-        const g1_xyzz* hs = h_sums.data() + (size_t)i * pl.n_phys;
+        const g1_xyzz* hs = h_sums + (size_t)i * pl.n_phys;
         g1_xyzz total = hs[pl.n_phys - 1];
         for (int p = pl.n_phys - 2; p >= 0; --p) {
             for (int k = 0; k < pl.c; ++k) total = g1_dbl(total);
@@ -844,6 +952,14 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         if (out_inf) out_inf[i] = 0;
     }
     return B200_OK;
+}
+
+int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
+                     unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st, g1_affine* out,
+                     int* out_inf) {
+    int rc = msm_launch_batch(b, base_off, d_scalars, n, stride, batch, montgomery, s, st);
+    if (rc != B200_OK) return rc;
+    return msm_finish_batch(s, out, out_inf);
 }
 
 int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, int montgomery,

@@ -233,6 +233,11 @@ Domain::~Domain() {
 
 int domain_create(unsigned log_n, cudaStream_t st, Domain** out) {
     if (log_n > 28) return B200_ERR_INVALID;
+    // every domain is created on its context's device, under that context's lock: the opt-in for the tile's
+    // shared memory is (re)applied here, per device, instead of behind a process-wide flag
+    if (cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess ||
+        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess)
+        return B200_ERR_CUDA;
     Domain* d = new Domain();
     d->log_n = log_n;
     const size_t n = (size_t)1 << log_n;
@@ -275,12 +280,6 @@ int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, u
     const int P = (L + kTileLog - 1) / kTileLog;
     const int e_log = L < kTileLog ? L : kTileLog;
     const int base = L / P, extra = L % P;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog);
-        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog);
-        attr_set = true;
-    }
     int hi = L;
     for (int p = 0; p < P; ++p) {
         const int w = base + (p < extra ? 1 : 0);

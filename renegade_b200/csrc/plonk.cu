@@ -90,6 +90,18 @@ __global__ void k_blind(fe* poly, size_t n, BlindArgs a) {
     fe_store(poly + n + i, FADD(fe_load(poly + n + i), a.b[i]));
 }
 
+// the five wire polynomials in one launch: thread (i, t) adds blinder t of wire i
+struct Blind5Args {
+    fe b[NW][2];
+};
+__global__ void k_blind_wires(fe* wpoly, size_t stride, size_t n, Blind5Args a) {
+    const int i = threadIdx.x >> 1, t = threadIdx.x & 1;
+    if (i >= NW) return;
+    fe* poly = wpoly + (size_t)i * stride;
+    fe_store(poly + t, FSUB(fe_load(poly + t), a.b[i][t]));
+    fe_store(poly + n + t, FADD(fe_load(poly + n + t), a.b[i][t]));
+}
+
 // per row j: num = prod_i (w_ij + beta k_i w^j + gamma), den = prod_i (w_ij + beta sigma_ij + gamma)
 __global__ void k_perm_num_den(const fe* __restrict__ wires, const fe* __restrict__ sig_evals,
                                const fe* __restrict__ dom, KArr k, fe beta, fe gamma, size_t n,
@@ -545,25 +557,8 @@ static Workspace carve(fe* base, size_t n) {
     return w;
 }
 
-// The prover's commitments use the throughput-tuned bucket reduction (device_ctx.h: 16 buckets per thread):
-// proofs are made several at a time per GPU, where operation count beats chain length.
-struct ProverMsmTuning {
-    MsmScratch* s;
-    int saved;
-    explicit ProverMsmTuning(MsmScratch* s_) : s(s_), saved(s_->reduce_chunk_log) {
-        static const int log = [] {
-            const char* e = std::getenv("B200_PROVER_REDUCE_CHUNK_LOG");  // tuning knob
-            const int v = e ? std::atoi(e) : 0;
-            return v >= 1 && v <= 8 ? v : kMsmReduceChunkLogThroughput;
-        }();
-        s->reduce_chunk_log = log;
-    }
-    ~ProverMsmTuning() { s->reduce_chunk_log = saved; }
-};
-
 static int commit(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, g1_affine* out) {
     int inf = 0;
-    ProverMsmTuning tune(&c->msm);
     int rc = msm_device(pk->srs, 0, d_coeffs, len, /*montgomery=*/1, &c->msm, c->stream, out, &inf);
     if (rc != B200_OK) return rc;
     if (inf) std::memset(out, 0, sizeof(*out));
@@ -575,7 +570,6 @@ static int commit_batch(Context* c, const ProvingKey* pk, const fe* d_coeffs, si
                         unsigned count, g1_affine* out) {
     int inf[32];
     if (count > 32) return B200_ERR_INVALID;
-    ProverMsmTuning tune(&c->msm);
     int rc = msm_device_batch(pk->srs, 0, d_coeffs, len, stride, count, /*montgomery=*/1, &c->msm, c->stream, out, inf);
     if (rc != B200_OK) return rc;
     for (unsigned i = 0; i < count; ++i)
@@ -724,6 +718,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     if ((rc = c->plonk_ws.reserve(workspace_elems(n) * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch.reserve((size_t)7 * m * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch2.reserve((size_t)6 * m * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->h_small.reserve(4096)) != B200_OK) return rc;
     if (!c->stream2) {
         int prio_least = 0, prio_greatest = 0;
         cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
@@ -757,25 +752,24 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 
     // ---- round 1 ------------------------------------------------------------------------------------
     B200_CUDA(cudaMemcpyAsync(w.wires_ev, h_wires, NW * n * sizeof(fe), cudaMemcpyDefault, st));  // host or device pointer (UVA)
-    B200_CUDA(cudaMemsetAsync(w.wpoly, 0, NW * S * sizeof(fe), st));
+    B200_CUDA(cudaMemsetAsync(w.wpoly, 0, (NW + 1) * S * sizeof(fe), st));  // wire slots and the public-input slot behind them
     B200_CUDA(cudaMemcpy2DAsync(w.wpoly, S * sizeof(fe), w.wires_ev, n * sizeof(fe), n * sizeof(fe), NW,
                                 cudaMemcpyDeviceToDevice, st));
-    {
-        HeavyScope hv(c, st);
-        if ((rc = ntt_device(dn, w.wpoly, nscr, 1, 0, NW, S, hv.run)) != B200_OK) return rc;
-    }
-    for (int i = 0; i < NW; ++i) {
-        BlindArgs b;
-        b.count = 2;
-        b.b[0] = h_blinders[2 * i];
-        b.b[1] = h_blinders[2 * i + 1];
-        b.b[2] = fe_zero();
-        k_blind<<<1, 32, 0, st>>>(w.wpoly + (size_t)i * S, n, b);
-    }
-    B200_CUDA(cudaMemsetAsync(w.pi_poly, 0, S * sizeof(fe), st));
     if (pk->num_inputs)
         B200_CUDA(cudaMemcpyAsync(w.pi_poly, h_pub_inputs, pk->num_inputs * sizeof(fe), cudaMemcpyHostToDevice, st));
-    if ((rc = ntt_device(dn, w.pi_poly, nscr, 1, 0, 1, n, st)) != B200_OK) return rc;
+    {
+        // wires and public inputs: evaluations -> coefficients, one batch of 6 (pi_poly sits directly behind wpoly)
+        HeavyScope hv(c, st);
+        if ((rc = ntt_device(dn, w.wpoly, nscr, 1, 0, NW + 1, S, hv.run)) != B200_OK) return rc;
+    }
+    {
+        Blind5Args b;
+        for (int i = 0; i < NW; ++i) {
+            b.b[i][0] = h_blinders[2 * i];
+            b.b[i][1] = h_blinders[2 * i + 1];
+        }
+        k_blind_wires<<<1, 32, 0, st>>>(w.wpoly, S, n, b);
+    }
     // Fork: the coset evaluations of the 5 wire polynomials and of the public-input polynomial do not
     // depend on any challenge, so they run on a second stream underneath the round-1/2 commitments
     // (whose bucket reduction and host round trip leave most SMs idle).
@@ -856,21 +850,20 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     const size_t deg = NW * (n + 1) + 2;
     B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
     k_check_degree<<<grid_for(m - deg, 256), 256, 0, st>>>(w.quot, deg, m, w.flag);
-    uint32_t h_flag = 0;
-    B200_CUDA(cudaMemcpyAsync(&h_flag, w.flag, 4, cudaMemcpyDeviceToHost, st));
+    uint32_t* h_flag = reinterpret_cast<uint32_t*>(c->h_small.p);  // pinned; read after the commitments below are in
+    B200_CUDA(cudaMemcpyAsync(h_flag, w.flag, 4, cudaMemcpyDeviceToHost, st));
     {
         SplitArgs sa;
         for (int i = 0; i < 4; ++i) sa.b[i] = h_blinders[13 + i];
         k_split_quotient<<<dim3(grid_for(n + 3, 256), NW), 256, 0, st>>>(w.quot, n, S, sa, w.split);
     }
-    B200_CUDA(cudaStreamSynchronize(st));
-    mark();  // [2] round 3: coset NTTs + quotient + split
-    if (h_flag) {
+    mark();  // [2] round 3 (enqueue only: the quotient's degree flag is read with the commitments)
+    // the last chunk has n coefficients; its tail up to n + 3 is zero, so one batch length serves
+    if ((rc = commit_batch(c, pk, w.split, n + 3, S, NW, proof->split_quot_poly_comms)) != B200_OK) return rc;
+    if (*h_flag) {  // copied before the commitments' window sums on the same stream
         set_error("WrongQuotientPolyDegree: the witness does not satisfy the circuit");
         return B200_ERR_UNSATISFIED;
     }
-    // the last chunk has n coefficients; its tail up to n + 3 is zero, so one batch length serves
-    if ((rc = commit_batch(c, pk, w.split, n + 3, S, NW, proof->split_quot_poly_comms)) != B200_OK) return rc;
     for (int i = 0; i < NW; ++i) tr.append_commitment(proof->split_quot_poly_comms[i]);
     mark();  // [3] round 3: the 5 quotient commitments
 
@@ -886,8 +879,8 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         polys[2 * NW - 1] = w.zpoly; lens[2 * NW - 1] = n + 3; pts[2 * NW - 1] = zeta_w;
         eval_batch(polys, lens, pts, 2 * NW, w.evals, w.escr, st);
     }
-    fe h_evals[2 * NW];
-    B200_CUDA(cudaMemcpyAsync(h_evals, w.evals, sizeof(h_evals), cudaMemcpyDeviceToHost, st));
+    fe* h_evals = reinterpret_cast<fe*>(reinterpret_cast<char*>(c->h_small.p) + 64);  // pinned
+    B200_CUDA(cudaMemcpyAsync(h_evals, w.evals, 2 * NW * sizeof(fe), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < NW; ++i) proof->wires_evals[i] = h_evals[i];
     for (int i = 0; i < NW - 1; ++i) proof->wire_sigma_evals[i] = h_evals[NW + i];

@@ -61,6 +61,33 @@ __global__ void k_iadd3(uint32_t* out, uint32_t a, uint32_t b) {
     for (int i = 0; i < 8; ++i) s ^= r[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// FP64 pipe: the rate that bounds a DFMA-based (52-bit limb) multiplier
+__global__ void k_dfma(double* out, double a, double b) {
+    double r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = fma(r[i], a, b);
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// FP64 and integer pipes side by side: do DFMA and IMAD.WIDE issue concurrently?
+__global__ void k_dfma_imad(double* out, double a, double b, uint32_t x, uint32_t y) {
+    double r[4];
+    uint64_t q[4];
+    for (int i = 0; i < 4; ++i) { r[i] = threadIdx.x + i; q[i] = threadIdx.x + i; }
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = fma(r[i], a, b);
+            uint32_t z = (uint32_t)q[i] ^ x;
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(q[i]) : "r"(z), "r"(y));
+        }
+    double s = 0;
+    for (int i = 0; i < 4; ++i) s += r[i] + (double)q[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <bool WIDE>
 __global__ void k_femul(fe* out) {
     fe a, b;
@@ -101,11 +128,14 @@ int main() {
     float t5 = time_ms([&] { k_femul<true><<<blocks, threads>>>((fe*)buf); });
     float t6 = time_ms([&] { k_femul<false><<<blocks, threads>>>((fe*)buf); });
     float t7 = time_ms([&] { k_madd<<<blocks, 128>>>((g1_xyzz*)buf); });
+    float t8 = time_ms([&] { k_dfma<<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9); });
+    float t9 = time_ms([&] { k_dfma_imad<<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9, 3, 5); });
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"sms\": %d, \"clock_khz\": %d, \"imad_Gops\": %.1f, \"imad_wide_Gops\": %.1f, \"imad_wide_x_Gops\": %.1f, "
-           "\"iadd3_lop_Gops\": %.1f, \"fq_mul_wide_G\": %.3f, \"fq_mul_wordserial_G\": %.3f, \"xyzz_madd_G\": %.4f}\n",
+           "\"iadd3_lop_Gops\": %.1f, \"fq_mul_wide_G\": %.3f, \"fq_mul_wordserial_G\": %.3f, \"xyzz_madd_G\": %.4f, "
+           "\"dfma_Gops\": %.1f, \"dfma_plus_imad_wide_pairs_Gops\": %.1f}\n",
            sms, clk, nthreads * ITERS * 8 / t1 / 1e6, nthreads * ITERS * 8 / t2 / 1e6, nthreads * ITERS * 8 / t3 / 1e6,
            nthreads * ITERS * 8 * 2 / t4 / 1e6, nthreads * (ITERS / 8) * 2 / t5 / 1e6, nthreads * (ITERS / 8) * 2 / t6 / 1e6,
-           (double)blocks * 128 * (ITERS / 16) / t7 / 1e6);
+           (double)blocks * 128 * (ITERS / 16) / t7 / 1e6, nthreads * ITERS * 8 / t8 / 1e6, nthreads * ITERS * 4 / t9 / 1e6);
     return 0;
 }
