@@ -110,11 +110,8 @@ int b200_msm_batch_device(b200_ctx* ctx, const b200_bases* bases, size_t base_of
                           const void* d_scalars, size_t n, size_t stride, unsigned batch,
                           int scalars_montgomery, uint64_t* out_xy, int* out_is_identity);
 
-/* Selects how the MSM entry points of this context trade latency for throughput.  0 (default): one MSM
- * at a time should finish as early as possible (short dependent chains in the bucket reduction: 4 buckets
- * per thread).  1: several MSMs are in flight on the GPU (other contexts) and the operation count matters
- * (16 buckets per thread: fewer scan operations competing with other launches' bucket accumulation).
- * Results are identical.  The prover always uses mode 1 for its own commitments. */
+/* Kept for ABI compatibility, no effect: round 1's running-sum bucket reduction had a latency and a
+ * throughput setting; the row/column tree reduction that replaced it has one shape for both uses. */
 int b200_msm_tuning(b200_ctx* ctx, int throughput_mode);
 /* Device-side phase timing (CUDA events recorded on the context's stream).  enable != 0 turns
  * it on for subsequent MSM calls; out_ms (may be NULL) receives the last call's
@@ -168,6 +165,9 @@ int b200_plonk_preprocess(b200_ctx* ctx, const b200_bases* srs, unsigned log_n, 
                           b200_pk** out);
 /* VerifyingKey commitments: 13 selector + 5 sigma commitments, 64 B each. */
 int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t* sigma_comms);
+/* Shape of a key: number of public inputs and log2 of the domain size it was preprocessed for. */
+size_t b200_pk_num_inputs(const b200_pk* pk);
+unsigned b200_pk_log_n(const b200_pk* pk);
 void b200_pk_free(b200_ctx* ctx, b200_pk* pk);
 
 /* Replaces `PlonkKzgSnark::prove_with_link_hint::<_, _, SolidityTranscript>(&mut rng, &circuit,
@@ -197,7 +197,8 @@ typedef struct {
  * vectors (Montgomery, host or device pointers; lengths may differ), comm1 / comm2 their
  * `linking_wire_comm`; (alignment, offset, size) = mpc-relation `GroupLayout`: the group sits on
  * the roots g^(offset + i), i < size, g the generator of the 2^alignment-th roots of unity.
- * eta (may be NULL) receives the Fiat–Shamir challenge. */
+ * eta (may be NULL) receives the Fiat–Shamir challenge.  Fails with B200_ERR_UNSATISFIED when a1 and a2
+ * do not agree on the group (no link proof exists: wrong layout or mismatched witnesses). */
 int b200_plonk_link(b200_ctx* ctx, const b200_bases* srs, const uint64_t* a1, size_t len1,
                     const uint64_t* a2, size_t len2, const uint64_t* comm1, const uint64_t* comm2,
                     unsigned alignment, size_t offset, size_t size, b200_link_proof* proof,
@@ -227,7 +228,8 @@ unsigned b200_pool_workers(const b200_pool* pool);
  * is running; keys created on any context of the device can be used by every worker. */
 b200_ctx* b200_pool_ctx(b200_pool* pool, unsigned worker);
 /* Queue one `b200_plonk_prove(ctx_of_some_worker, pk, wires, pub_inputs, blinders, proof,
- * link_poly, NULL)`; *ticket identifies the job. */
+ * link_poly, NULL)`; *ticket identifies the job.  num_inputs must equal the key's
+ * (b200_pk_num_inputs), else B200_ERR_INVALID. */
 int b200_pool_submit_prove(b200_pool* pool, const b200_pk* pk, const uint64_t* wires,
                            const uint64_t* pub_inputs, size_t num_inputs, const uint64_t* blinders,
                            b200_proof* proof, uint64_t* link_poly, uint64_t* ticket);

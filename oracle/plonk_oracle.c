@@ -154,16 +154,18 @@ static void poly_axpy(u64* acc, const u64* p, size_t len, const u64 s[4]) {
         ADD(acc + 4 * i, acc + 4 * i, t);
     }
 }
-/* q = p / (X - z), p has len coefficients, q has len - 1 (remainder dropped) */
-static void poly_div_linear(const u64* p, size_t len, const u64 z[4], u64* q) {
-    u64 carry[4];
+/* q = p / (X - z), p has len coefficients, q has len - 1; returns 1 when the remainder p(z) is zero */
+static int poly_div_linear(const u64* p, size_t len, const u64 z[4], u64* q) {
+    u64 carry[4], t[4];
     fr_zero(carry);
     for (size_t i = len - 1; i >= 1; --i) {
-        u64 t[4];
         MUL(t, carry, z);
         ADD(carry, p + 4 * i, t);
         fr_set(q + 4 * (i - 1), carry);
     }
+    MUL(t, carry, z);
+    ADD(carry, p, t); /* remainder = p(z) */
+    return (carry[0] | carry[1] | carry[2] | carry[3]) == 0;
 }
 
 void orc_srs_from_tau(const u64* tau, size_t n, u64* out_xy) {
@@ -701,12 +703,17 @@ int orc_plonk_link(const u64* a1, size_t len1, const u64* a2, size_t len2, const
     size_t cur_len = len;
     u64 zd_eta_roots[4];
     u64* roots = (u64*)malloc(size * 32);
+    int exact = 1; /* the two polynomials must agree on every root of the group */
     for (size_t i = 0; i < size; ++i) {
         fr_set(roots + 4 * i, root);
-        poly_div_linear(cur, cur_len, root, nxt);
+        exact &= poly_div_linear(cur, cur_len, root, nxt);
         --cur_len;
         u64* t = cur; cur = nxt; nxt = t;
         MUL(root, root, g);
+    }
+    if (!exact) {
+        free(roots); free(cur); free(nxt); free(diff);
+        return 2; /* the wire polynomials differ on the link group: no valid link proof exists */
     }
     commit(srs, cur, cur_len, proof->quotient_commitment);
     u64 eta[4];

@@ -474,6 +474,10 @@ class ProverPool:
         proof = B200Proof()
         pi = np.ascontiguousarray(pub_inputs, dtype=np.uint64)
         bl = np.ascontiguousarray(blinders, dtype=np.uint64)
+        if pi.size != 4 * pk.num_inputs:
+            raise ProverError(-1, f"submit_prove: {pi.size // 4} public inputs for a key with {pk.num_inputs}")
+        if bl.size != 4 * 17:
+            raise ProverError(-1, "submit_prove: blinders must be 17 Fr elements")
         link = np.zeros((pk.domain_size + 2, 4), dtype=np.uint64) if with_link_poly else None
         ticket = C.c_uint64()
         _lib.check(self._lib.b200_pool_submit_prove(self._h, pk._h, C.c_void_p(wires_ptr), _ptr(pi) if pi.size else None,

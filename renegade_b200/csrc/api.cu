@@ -244,7 +244,11 @@ int b200_srs_parse_ptau(const uint8_t* bytes, size_t len, const uint8_t** g1_rec
         set_error("ptau: power < 17");
         return B200_ERR_FORMAT;
     }
-    off += size;
+    if (size > len - off) {  // untrusted 64-bit length: never let `off` wrap or leave the buffer
+        set_error("ptau: section 1 longer than the file");
+        return B200_ERR_FORMAT;
+    }
+    off += (size_t)size;
     // section 2 (srs.rs:124-141)
     if (!rd_u32(bytes, len, off, &sec) || !rd_u64(bytes, len, off + 4, &size) || sec != 2) {
         set_error("Invalid section number");
@@ -430,16 +434,10 @@ int b200_msm_timing(b200_ctx* ctx, int enable, float out_ms[4]) {
 }
 
 // ---- NTT ------------------------------------------------------------------------------------
-int b200_ntt_device(b200_ctx* ctx, void* d_data, unsigned log_n, int inverse, int coset, unsigned batch,
-                    size_t stride) {
-    B200_TRY
-    if (!ctx || !d_data || log_n > 28 || batch == 0) return B200_ERR_INVALID;
+// caller holds ctx->c.mu
+static int ntt_device_locked(b200_ctx* ctx, void* d_data, unsigned log_n, int inverse, int coset, unsigned batch,
+                             size_t stride) {
     const size_t n = (size_t)1 << log_n;
-    if (stride < n) {
-        set_error("ntt: stride < n");
-        return B200_ERR_INVALID;
-    }
-    std::lock_guard<std::mutex> lk(ctx->c.mu);
     B200_CUDA(cudaSetDevice(ctx->c.device));
     Domain* d = nullptr;
     int rc = get_domain(&ctx->c, log_n, &d);
@@ -462,6 +460,18 @@ int b200_ntt_device(b200_ctx* ctx, void* d_data, unsigned log_n, int inverse, in
     B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
     cudaEventElapsedTime(&ctx->c.ntt_last_ms, ctx->c.ntt_ev[0], ctx->c.ntt_ev[1]);
     return B200_OK;
+}
+
+int b200_ntt_device(b200_ctx* ctx, void* d_data, unsigned log_n, int inverse, int coset, unsigned batch,
+                    size_t stride) {
+    B200_TRY
+    if (!ctx || !d_data || log_n > 28 || batch == 0) return B200_ERR_INVALID;
+    if (stride < ((size_t)1 << log_n)) {
+        set_error("ntt: stride < n");
+        return B200_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    return ntt_device_locked(ctx, d_data, log_n, inverse, coset, batch, stride);
     B200_CATCH
 }
 
@@ -469,16 +479,15 @@ int b200_ntt(b200_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, int cos
     B200_TRY
     if (!ctx || !data || log_n > 28) return B200_ERR_INVALID;
     const size_t n = (size_t)1 << log_n;
-    {
-        std::lock_guard<std::mutex> lk(ctx->c.mu);
-        B200_CUDA(cudaSetDevice(ctx->c.device));
-        int rc = ctx->c.ntt_data.reserve(n * sizeof(fe));
-        if (rc != B200_OK) return rc;
-        B200_CUDA(cudaMemcpyAsync(ctx->c.ntt_data.p, data, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->c.stream));
-    }
-    int rc = b200_ntt_device(ctx, ctx->c.ntt_data.p, log_n, inverse, coset, 1, n);
-    if (rc != B200_OK) return rc;
+    // one critical section: upload, transform and download cannot interleave with another caller's
+    // (whose reserve() could otherwise free the staging buffer under this call)
     std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = ctx->c.ntt_data.reserve(n * sizeof(fe));
+    if (rc != B200_OK) return rc;
+    B200_CUDA(cudaMemcpyAsync(ctx->c.ntt_data.p, data, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->c.stream));
+    rc = ntt_device_locked(ctx, ctx->c.ntt_data.p, log_n, inverse, coset, 1, n);
+    if (rc != B200_OK) return rc;
     B200_CUDA(cudaMemcpyAsync(data, ctx->c.ntt_data.p, n * sizeof(fe), cudaMemcpyDeviceToHost, ctx->c.stream));
     B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
     return B200_OK;

@@ -320,6 +320,12 @@ __global__ void k_check_degree(const fe* __restrict__ q, size_t deg, size_t m, u
     }
 }
 
+// flag |= 1 when any of the `count` elements is non-zero (single small block)
+__global__ void k_any_nonzero(const fe* __restrict__ v, size_t count, uint32_t* flag) {
+    for (size_t i = threadIdx.x; i < count; i += blockDim.x)
+        if (!fe_is_zero(fe_load_ro(v + i))) atomicOr(flag, 1u);
+}
+
 struct SplitArgs {
     fe b[4];
 };
@@ -989,14 +995,18 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     int rc;
     const size_t L = len + 8;
     const size_t scr = 4 * (L / CH + 4 * CH + 64);
-    if ((rc = c->plonk_ws.reserve((6 * L + scr + 16) * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->plonk_ws.reserve((6 * L + scr + size + 16) * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->h_small.reserve(4096)) != B200_OK) return rc;
     fe* base = reinterpret_cast<fe*>(c->plonk_ws.p);
     fe *d_a1 = base, *d_a2 = base + L, *d_diff = base + 2 * L, *d_ident = base + 3 * L;
     fe* d_pp[2] = {base + 4 * L, base + 5 * L};  // ping-pong buffers of the successive divisions
     fe* hscr = base + 6 * L;
-    fe* slot = hscr + scr;
+    fe* rems = hscr + scr;       // remainder of division i (the value of the running quotient at root i)
+    fe* slot = rems + size;      // 16 spare elements: evaluation slot, then the remainder flag
+    uint32_t* d_flag = reinterpret_cast<uint32_t*>(slot + 4);
     B200_CUDA(cudaMemcpyAsync(d_a1, h_a1, len1 * sizeof(fe), cudaMemcpyDefault, st));
     B200_CUDA(cudaMemcpyAsync(d_a2, h_a2, len2 * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
     const fe one = fe_one<Fr>();
     {
         LinArgs a;
@@ -1014,15 +1024,24 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     for (size_t i = 0; i < size; ++i) {
         roots[i] = root;
         fe* dst = d_pp[i & 1];
-        horner_suffix(cur, cur_len, root, dst, slot, hscr, st);
-        cur = dst + 1;  // drop the remainder S[0]
+        horner_suffix(cur, cur_len, root, dst, rems + i, hscr, st);
+        cur = dst + 1;  // the quotient; the remainder S[0] was also written to rems[i]
         --cur_len;
         root = FMUL(root, g);
     }
+    // a1 and a2 must agree on every root of the group, i.e. every division is exact: otherwise no link
+    // proof verifies and the reference's prover output would be rejected (silent bad proof)
+    k_any_nonzero<<<1, 256, 0, st>>>(rems, size, d_flag);
+    uint32_t* h_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_small.p) + 1024);
+    B200_CUDA(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     {
         ProvingKey tmp;  // commit() only needs the SRS
         tmp.srs = srs;
         if ((rc = commit(c, &tmp, cur, cur_len, &out->quotient_commitment)) != B200_OK) return rc;
+    }
+    if (*h_flag) {
+        set_error("link: the two wire polynomials differ on the link group (wrong layout or mismatched witnesses)");
+        return B200_ERR_UNSATISFIED;
     }
     SolidityTranscript tr;
     tr.append_commitment(comm1);
@@ -1083,6 +1102,9 @@ int b200_pk_verifying_key(const b200_pk* pk, uint64_t* selector_comms, uint64_t*
     std::memcpy(sigma_comms, pk->pk->sig_comms, sizeof(pk->pk->sig_comms));
     return B200_OK;
 }
+
+size_t b200_pk_num_inputs(const b200_pk* pk) { return pk ? pk->pk->num_inputs : 0; }
+unsigned b200_pk_log_n(const b200_pk* pk) { return pk ? pk->pk->log_n : 0; }
 
 int b200_plonk_link(b200_ctx* ctx, const b200_bases* srs, const uint64_t* a1, size_t len1, const uint64_t* a2,
                     size_t len2, const uint64_t* comm1, const uint64_t* comm2, unsigned alignment, size_t offset,

@@ -163,6 +163,10 @@ int b200_pool_submit_prove(b200_pool* pool, const b200_pk* pk, const uint64_t* w
         b200::set_error("pool_submit_prove: null argument");
         return B200_ERR_INVALID;
     }
+    if (num_inputs != b200_pk_num_inputs(pk)) {  // the worker reads exactly pk.num_inputs elements
+        b200::set_error("pool_submit_prove: num_inputs does not match the proving key");
+        return B200_ERR_INVALID;
+    }
     std::unique_ptr<Job> j(new Job());
     j->kind = Job::kProve;
     j->pk = pk;

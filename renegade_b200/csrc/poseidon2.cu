@@ -11,6 +11,8 @@
 #include <cstring>
 
 #include "b200prover.h"
+#include <mutex>
+
 #include "device_ctx.h"
 #include "poseidon2_constants.h"
 
@@ -101,16 +103,26 @@ __global__ void __launch_bounds__(128) k_poseidon2_hash(const fe* __restrict__ i
     fe_store(out + t, s[1]);
 }
 
-bool g_constants_loaded[64] = {false};
+std::once_flag g_constants_once[64];  // one upload per device, whatever context gets there first
 
 }  // namespace
 
-static int load_constants(int device) {
-    if (device >= 0 && device < 64 && g_constants_loaded[device]) return B200_OK;
+static int upload_constants() {
     B200_CUDA(cudaMemcpyToSymbol(c_full_rc, kPoseidon2FullRc, sizeof(kPoseidon2FullRc)));
     B200_CUDA(cudaMemcpyToSymbol(c_partial_rc, kPoseidon2PartialRc, sizeof(kPoseidon2PartialRc)));
-    if (device >= 0 && device < 64) g_constants_loaded[device] = true;
     return B200_OK;
+}
+static int load_constants(int device) {
+    if (device < 0 || device >= 64) return upload_constants();
+    int rc = B200_OK;
+    bool ran = false;
+    std::call_once(g_constants_once[device], [&] {
+        ran = true;
+        rc = upload_constants();
+    });
+    // a failed first upload leaves the flag set: retry directly (the context mutex does not cover other contexts)
+    if (!ran || rc == B200_OK) return rc;
+    return upload_constants();
 }
 
 }  // namespace b200

@@ -198,12 +198,17 @@ def test_link_groups_place_shared_values_and_link_on_the_oracle(oracle, pyoracle
         assert rc == 0
         assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
         hints.append((link, proof.to_array()[:8].copy()))
-    for other, ok in ((1, True), (2, False)):
-        rc, lp, _ = oracle.plonk_link(hints[0][0], hints[other][0], hints[0][1], hints[other][1], layout.alignment,
-                                      layout.offset, len(shared), srs)
-        assert rc == 0
-        assert oracle.plonk_link_verify_known_tau(hints[0][1], hints[other][1], layout.alignment, layout.offset,
-                                                  len(shared), lp, tau) == ok
+    rc, lp, _ = oracle.plonk_link(hints[0][0], hints[1][0], hints[0][1], hints[1][1], layout.alignment,
+                                  layout.offset, len(shared), srs)
+    assert rc == 0
+    assert oracle.plonk_link_verify_known_tau(hints[0][1], hints[1][1], layout.alignment, layout.offset, len(shared), lp, tau)
+    # circuit 2 holds a different value in the group: the prover refuses (a division is not exact) and the
+    # honest proof of the (0, 1) pair does not verify against circuit 2's commitment
+    rc, _, _ = oracle.plonk_link(hints[0][0], hints[2][0], hints[0][1], hints[2][1], layout.alignment, layout.offset,
+                                 len(shared), srs)
+    assert rc == 2
+    assert not oracle.plonk_link_verify_known_tau(hints[0][1], hints[2][1], layout.alignment, layout.offset,
+                                                  len(shared), lp, tau)
     # a layout that collides with the public-input rows is refused
     bad = C.PlonkCircuit()
     bad.create_link_group("g", C.GroupLayout(alignment=3, offset=0))
@@ -437,6 +442,8 @@ def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle)
             assert oracle.plonk_link_verify_known_tau(v[1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)
     # party 1's validity proof does not link on party 0's group: the settlement holds party 0's values there
     lay = layouts[ps.PARTY_LINKS[0]]
-    rc, lp, _ = oracle.plonk_link(hints[2][0], hints[0][0], hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
-    assert rc == 0
+    rc, _, _ = oracle.plonk_link(hints[2][0], hints[0][0], hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
+    assert rc == 2                               # the prover refuses: the polynomials differ on the group
+    rc, lp, _ = oracle.plonk_link(hints[1][0], hints[0][0], hints[1][1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
+    assert rc == 0                               # party 0's honest link proof does not carry over to party 1's commitment
     assert not oracle.plonk_link_verify_known_tau(hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)

@@ -43,6 +43,17 @@ def test_link_two_circuits(ctx, oracle, pyoracle):
                                               layout.offset, layout.size, oracle.LinkProof.from_buffer_copy(bytes(lp)), tau)
     # a group the two proofs do NOT share (one row further) must not verify
     wrong = GroupLayout(layout.alignment, layout.offset + 1, layout.size)
-    lp2, _ = link_proofs(ctx, bases, hints[0], hints[1], wrong)
+    import pytest
+    from renegade_b200._lib import B200Error
+    with pytest.raises(B200Error) as err:      # the prover refuses: a division by the group's roots is not exact
+        link_proofs(ctx, bases, hints[0], hints[1], wrong)
+    assert err.value.code == -7
+    rc, _, _ = oracle.plonk_link(hints[0].linking_wire_poly, hints[1].linking_wire_poly, hints[0].linking_wire_comm,
+                                 hints[1].linking_wire_comm, wrong.alignment, wrong.offset, wrong.size, srs)
+    assert rc == 2
+    # and the honest proof does not verify under the wrong layout
     assert not oracle.plonk_link_verify_known_tau(hints[0].linking_wire_comm, hints[1].linking_wire_comm, wrong.alignment,
-                                                  wrong.offset, wrong.size, oracle.LinkProof.from_buffer_copy(bytes(lp2)), tau)
+                                                  wrong.offset, wrong.size, oracle.LinkProof.from_buffer_copy(bytes(lp)), tau)
+    # the context stays usable after the refusal
+    lp3, _ = link_proofs(ctx, bases, hints[0], hints[1], layout)
+    assert (lp3.to_array() == lp.to_array()).all()

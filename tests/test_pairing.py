@@ -122,5 +122,6 @@ def test_oracle_link_proof_verifies_with_pairing(oracle, pyoracle, srs_head, g2)
     assert rc == 0
     assert _link_pairing_ok(py, pr, hints[0][1], hints[1][1], layout, lp.to_array(), eta, g2)
     wrong = (layout[0], layout[1] + 1, layout[2])
-    rc, lp2, eta2 = oracle.plonk_link(hints[0][0], hints[1][0], hints[0][1], hints[1][1], *wrong, srs_all)
-    assert not _link_pairing_ok(py, pr, hints[0][1], hints[1][1], wrong, lp2.to_array(), eta2, g2)
+    rc, _, _ = oracle.plonk_link(hints[0][0], hints[1][0], hints[0][1], hints[1][1], *wrong, srs_all)
+    assert rc == 2   # not linkable on that group: the prover refuses instead of emitting an unverifiable proof
+    assert not _link_pairing_ok(py, pr, hints[0][1], hints[1][1], wrong, lp.to_array(), eta, g2)
