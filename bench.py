@@ -247,6 +247,14 @@ def run_extras(args):
     os._exit(0)  # skip interpreter teardown: the parent only needs the line above
 
 
+def multi_plan(multi, mbases):
+    """Window plan of local device 0's shard of a sharded set of bases."""
+    import ctypes as C
+    plan = (C.c_int * 4)()
+    multi._lib.b200_multi_bases_plan(mbases._h, 0, C.byref(plan))
+    return {"window_bits": plan[0], "digits": plan[1], "physical_windows": plan[2], "tables": plan[3]}
+
+
 def base_line(args, world):
     return {"metric": METRIC, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -339,7 +347,7 @@ def main():
     import renegade_b200 as rb
     from renegade_b200 import synth
     from renegade_b200.backend import PlonkKzgSnark, ProverPool, plonk_last_timings, prove_raw
-    from renegade_b200.sharded import all_gather_partials, combine_partials, pack_partial
+    from renegade_b200.sharded import MultiGpu
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -380,7 +388,7 @@ def main():
     h_wires = torch.from_numpy(circ.wires.view(np.int64)).pin_memory()
     d_wires = h_wires.to(dev)
     torch.cuda.synchronize()
-    blinders = [synth.splitmix_blinders(1000 * rank + i) for i in range(args.steps + args.warmup + 8)]
+    blinders = [synth.splitmix_blinders(1000 * rank + i) for i in range(max(args.steps + args.warmup, args.warmup * conc, 2 * conc) + 8)]
     setup_s = time.perf_counter() - t_setup
 
     def run_proofs(count, wires_ptr, first_blinder, collect=None):
@@ -407,10 +415,12 @@ def main():
         sampler.start()
     phases = []
     barrier()
+    launches0 = ctx._lib.b200_kernel_launches()  # the library counts every kernel it launches
     t = time.perf_counter()
     proof = run_proofs(args.steps, d_wires.data_ptr(), args.warmup, phases)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t)
+    gpu_launches = int(ctx._lib.b200_kernel_launches() - launches0)
     clocks = sampler.stop() if rank == 0 else None
     acc_tot = [c.msm_timing_totals(reset=True) for c in ctxs]
     # ---- the same through the public call with HOST buffers (e2e) ---------------------------------------
@@ -499,24 +509,22 @@ def main():
     if not args.no_msm:
         nm = 1 << MSM_LOG_N
         first = rank * nm
-        d_pts = torch.empty((nm, 8), dtype=torch.int64, device=dev)
+        # the whole leg runs behind the C ABI: b200_multi_* = local Pippenger per GPU + ncclAllGather of the
+        # 128-byte partials + W-term sum on every device (world = 1: the same code without the collective)
+        multi = MultiGpu.from_torch_distributed(local_rank) if world > 1 else MultiGpu.single_process([local_rank])
+        mctx = multi.ctx(0)
+        mctx.msm_timing(True)
+        mbases = multi.known_dlog_bases(SEED_BASES, world * nm)
+        assert mbases.shard(0) == (first, first + nm)
         d_sc = torch.empty((nm, 4), dtype=torch.int64, device=dev)
         torch.cuda.synchronize()
-        ctx.known_dlog_bases_device(SEED_BASES, nm, d_pts.data_ptr(), first=first)
-        ctx.splitmix_fr_device(SEED_SCALARS, nm, d_sc.data_ptr(), montgomery=False, first=first)
-        mbases = ctx.load_bases_device(d_pts.data_ptr(), nm)
+        mctx.splitmix_fr_device(SEED_SCALARS, nm, d_sc.data_ptr(), montgomery=False, first=first)
         h_sc = torch.empty((nm, 4), dtype=torch.int64).pin_memory()
         h_sc.copy_(d_sc)
         torch.cuda.synchronize()
 
         def msm_step(host):
-            if host:
-                xy, inf = ctx.msm(mbases, h_sc.numpy().view(np.uint64), montgomery=False)
-            else:
-                xy, inf = ctx.msm_device(mbases, d_sc.data_ptr(), nm, montgomery=False)
-            if world > 1:
-                xy, inf = combine_partials(ctx, all_gather_partials(pack_partial(xy, inf), dev))
-            return xy, inf
+            return multi.msm_local(mbases, [h_sc.data_ptr() if host else d_sc.data_ptr()], on_device=not host, montgomery=False)
         for _ in range(3):
             msm_step(False)
         mph = []
@@ -524,7 +532,7 @@ def main():
         t = time.perf_counter()
         for _ in range(args.msm_steps):
             r0 = msm_step(False)
-            mph.append(ctx.msm_timing(True))
+            mph.append(mctx.msm_timing(True))
         barrier()
         mdt = max_over_ranks(time.perf_counter() - t) / args.msm_steps
         for _ in range(2):
@@ -536,11 +544,42 @@ def main():
         barrier()
         mdt_e2e = max_over_ranks(time.perf_counter() - t) / args.msm_steps
         assert (r0[0] == r1[0]).all()
+        # closed form: the bases are a_i * G, so the result must be (sum a_i s_i mod r) * G.  Every rank folds its own
+        # 2^20 products (device field multiplier, exact limb sums on the host), rank 0 adds them and checks with one
+        # scalar multiplication — product code only, no oracle
+        R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+        d_a = torch.empty((nm, 4), dtype=torch.int64, device=dev)
+        d_sm = torch.empty((nm, 4), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        mctx.splitmix_fr_device(SEED_BASES, nm, d_a.data_ptr(), montgomery=True, first=first)
+        mctx.splitmix_fr_device(SEED_SCALARS, nm, d_sm.data_ptr(), montgomery=True, first=first)
+        prod = mctx.field_op(0, 0, d_a.cpu().numpy().view(np.uint64), d_sm.cpu().numpy().view(np.uint64))  # mont(a_i s_i)
+        cols = prod.view(np.uint32).reshape(-1, 8).astype(np.uint64).sum(axis=0)
+        part = sum(int(cols[j]) << (32 * j) for j in range(8)) % R_MOD
+        parts = [part]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, part)
+        k_dlog = sum(parts) * pow(1 << 256, -1, R_MOD) % R_MOD  # out of Montgomery form
+        Q_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+        gen = np.zeros((1, 8), dtype=np.uint64)  # G = (1, 2), coordinates in Montgomery form
+        for off, v in ((0, 1), (4, 2)):
+            mv = (v << 256) % Q_MOD
+            gen[0, off:off + 4] = [(mv >> (64 * j)) & 0xffffffffffffffff for j in range(4)]
+        gb = mctx.load_bases(gen)
+        kk = np.array([[(k_dlog >> (64 * j)) & 0xffffffffffffffff for j in range(4)]], dtype=np.uint64)
+        exp_xy, exp_inf = mctx.msm(gb, kk, montgomery=False)
+        msm_verified = bool((not exp_inf) and (not r0[1]) and (r0[0] == exp_xy).all())
+        gb.free()
+        del d_a, d_sm
         macc = sum(p["accumulate"] for p in mph) / len(mph)
-        mplan = mbases.plan
+        mplan = multi_plan(multi, mbases)
         msm = {
             "workload": "2^20-point BN254 G1 Pippenger MSM per GPU (BASELINE.json configs[1]); N GPUs = one "
-                        "N*2^20-point MSM sharded by point range + NCCL all_gather of the partial sums",
+                        "N*2^20-point MSM sharded by point range behind the C ABI (b200_multi_msm_local): local Pippenger, "
+                        "ncclAllGather of the 128-byte partial sums, W-term addition on every device",
+            "verified": msm_verified,
+            "verified_how": "result == (sum a_i s_i mod r) * G for the N*2^20 known-discrete-log bases (closed form, product code only)",
             "value": world * nm * BYTES_PER_PAIR / mdt / 1e9, "unit": "GB/s", "ms_per_step": mdt * 1e3,
             "points_per_sec": world * nm / mdt, "steps": args.msm_steps,
             "e2e": {"value": world * nm * BYTES_PER_PAIR / mdt_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nm * 32,
@@ -586,10 +625,9 @@ def main():
                              "`achieved_kernel_alone` the same kernel timed alone; see DESIGN.md for the INT-pipe roofline"},
         "e2e": {"value": world * args.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": 5 * n * 32 + circ.num_inputs * 32 + 17 * 32,
                 "d2h_bytes_per_step": 1152, "ms_per_step": dt_e2e / args.steps * 1e3},
-        # 113 kernel launches per proof (ncu launch list -> tools/kernel_shares.py,
-        # profiles/r1r_proof_kernel_shares.txt): 4 batched commitments x 17 kernels + NTT passes, coset
-        # fold / combine, quotient, scans, evaluations, divisions
-        "gpu_launches": args.steps * 113,
+        # counted by the library (b200_kernel_launches) around the timed region of this rank; the ncu launch list
+        # of the same command is under profiles/ (tools/kernel_shares.py gives launches per proof)
+        "gpu_launches": gpu_launches * world, "gpu_launches_per_proof": gpu_launches / max(args.steps, 1),
         "latency_ms_one_proof_in_flight": single_ms, "latency_phases_ms": single,
         "clocks": clocks, "setup_s": setup_s, "msm": msm, "ntt": ntt,
     })

@@ -65,6 +65,8 @@ void b200_shutdown(b200_ctx* ctx);
 const char* b200_last_error(void);
 /* "libb200prover <version> sm_100a" */
 const char* b200_version(void);
+/* Kernels launched by the library in this process so far (all contexts, all threads). */
+uint64_t b200_kernel_launches(void);
 
 /* ---- SRS ------------------------------------------------------------------------------- */
 /* Replaces parse_ptau_file / read_ptau_header / read_ptau_section1 / read_ptau_section2
@@ -248,6 +250,54 @@ int b200_pool_wait(b200_pool* pool, uint64_t ticket);
 int b200_pool_wait_all(b200_pool* pool);
 /* out = { submitted, completed, failed, queued } */
 int b200_pool_stats(b200_pool* pool, uint64_t out[4]);
+
+/* ---- multi-GPU: one MSM sharded over the GPUs of a box (boundary B1's
+ * `b200_init(const int* devs, int n_dev, ...)`) ----------------------------------------------------
+ * Rank g of W owns the points [g n / W, (g + 1) n / W) (b200_shard_range) with resident window tables
+ * and gets the matching scalar slice; every GPU runs the whole Pippenger on its shard and contributes
+ * ONE group element; the exchange is one `ncclAllGather` of the W 128-byte records over NVLink and a
+ * W-term addition on every device, in rank order — the affine result is bit-identical to the
+ * single-GPU MSM (G1 addition is associative).  NTT and whole proofs do not shard: use one context /
+ * one prover pool per device for those.
+ * NCCL is bound at run time (libnccl.so.2); the calls fail with B200_ERR_INVALID when it is absent. */
+typedef struct b200_multi b200_multi;             /* contexts + NCCL communicator(s) */
+typedef struct b200_multi_bases b200_multi_bases; /* point-range shards of one set of bases */
+/* [begin, end) of rank `rank` of `world` over n items (sizes differ by at most one).  Host only. */
+void b200_shard_range(size_t n, int rank, int world, size_t* begin, size_t* end);
+/* One host process drives all `n_dev` devices (world = n_dev; rank i = devices[i]). */
+int b200_multi_init(const int* devices, int n_dev, b200_multi** out);
+/* One process per GPU (torchrun): rank 0 makes the id, the host hands it to every rank. */
+int b200_nccl_unique_id(uint8_t out[128]);
+int b200_multi_init_rank(int device, int rank, int world, const uint8_t unique_id[128], b200_multi** out);
+void b200_multi_shutdown(b200_multi* m);
+/* NCCL_VERSION_CODE of the library bound at run time. */
+int b200_nccl_version(int* version);
+int b200_multi_world(const b200_multi* m);
+/* devices driven by THIS process (n_dev, or 1 in rank mode), their contexts and global ranks */
+int b200_multi_local_devices(const b200_multi* m);
+b200_ctx* b200_multi_ctx(b200_multi* m, int local);
+int b200_multi_rank(const b200_multi* m, int local);
+/* Uploads, for each local device, its range of the n points (the full array is passed) and builds the
+ * window tables there; cf. b200_bases_load. */
+int b200_multi_bases_load(b200_multi* m, const uint8_t* points64, size_t n, int window_bits,
+                          int check_on_curve, b200_multi_bases** out);
+/* Synthetic known-discrete-log bases, generated on each device for its range. */
+int b200_multi_bases_known_dlog(b200_multi* m, uint64_t seed, size_t n, int window_bits,
+                                b200_multi_bases** out);
+void b200_multi_bases_free(b200_multi* m, b200_multi_bases* bases);
+size_t b200_multi_bases_len(const b200_multi_bases* bases);
+int b200_multi_bases_shard(const b200_multi_bases* bases, int local, size_t* begin, size_t* end);
+/* b200_bases_plan of local device `local`'s shard (zeros for an empty shard). */
+int b200_multi_bases_plan(const b200_multi_bases* bases, int local, int plan[4]);
+/* out = sum_{i<n} scalars[i] * bases[i], n = all points.  `scalars`: the FULL host vector (each local
+ * device copies its slice).  Collective: in rank mode every rank must call it; all ranks get the result. */
+int b200_multi_msm(b200_multi* m, const b200_multi_bases* bases, const uint64_t* scalars, size_t n,
+                   int scalars_montgomery, uint64_t out_xy[8], int* out_is_identity);
+/* Same, handing over only the SLICES of the local devices: scalars_local[i] = the scalars of local
+ * device i's range — host pointers (scalars_on_device = 0; copied inside the call) or device pointers on
+ * that device (1).  NULL is allowed for an empty shard. */
+int b200_multi_msm_local(b200_multi* m, const b200_multi_bases* bases, const void* const* scalars_local,
+                         int scalars_on_device, int scalars_montgomery, uint64_t out_xy[8], int* out_is_identity);
 
 /* ---- witness-side batch hashing ------------------------------------- */
 /* `batch` independent Poseidon2 sponge hashes of `len` scalars each (inputs: batch x len x 4

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200prover
 # every symbol include/b200prover.h declares (tests/test_abi.py checks this list against the
 # header and against the built library)
 EXPORTS = [
-    "b200_init", "b200_shutdown", "b200_last_error", "b200_version",
+    "b200_init", "b200_shutdown", "b200_last_error", "b200_version", "b200_kernel_launches",
     "b200_srs_parse_ptau", "b200_bases_load", "b200_bases_load_device", "b200_bases_free",
     "b200_bases_len", "b200_bases_plan",
     "b200_msm", "b200_msm_device", "b200_msm_batch_device", "b200_msm_timing", "b200_msm_timing_totals", "b200_msm_tuning", "b200_g1_sum_affine",
@@ -27,6 +27,10 @@ EXPORTS = [
     "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_workers", "b200_pool_ctx", "b200_pool_submit_prove",
     "b200_pool_submit_link", "b200_pool_wait", "b200_pool_wait_all", "b200_pool_stats",
+    "b200_shard_range", "b200_multi_init", "b200_nccl_unique_id", "b200_multi_init_rank", "b200_multi_shutdown",
+    "b200_nccl_version", "b200_multi_world", "b200_multi_local_devices", "b200_multi_ctx", "b200_multi_rank",
+    "b200_multi_bases_load", "b200_multi_bases_known_dlog", "b200_multi_bases_free", "b200_multi_bases_len",
+    "b200_multi_bases_shard", "b200_multi_bases_plan", "b200_multi_msm", "b200_multi_msm_local",
 ]
 
 
@@ -51,6 +55,8 @@ def load() -> C.CDLL:
     vp, sz, i32, u64, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint
     lib.b200_last_error.restype = C.c_char_p
     lib.b200_version.restype = C.c_char_p
+    lib.b200_kernel_launches.restype = C.c_uint64
+    lib.b200_kernel_launches.argtypes = []
     lib.b200_init.argtypes = [i32, C.POINTER(vp)]
     lib.b200_shutdown.argtypes = [vp]
     lib.b200_shutdown.restype = None
@@ -103,6 +109,29 @@ def load() -> C.CDLL:
     lib.b200_pool_wait.argtypes = [vp, u64]
     lib.b200_pool_wait_all.argtypes = [vp]
     lib.b200_pool_stats.argtypes = [vp, C.POINTER(u64 * 4)]
+    lib.b200_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+    lib.b200_shard_range.restype = None
+    lib.b200_multi_init.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    lib.b200_nccl_unique_id.argtypes = [vp]
+    lib.b200_multi_init_rank.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
+    lib.b200_multi_shutdown.argtypes = [vp]
+    lib.b200_multi_shutdown.restype = None
+    lib.b200_nccl_version.argtypes = [C.POINTER(i32)]
+    lib.b200_multi_world.argtypes = [vp]
+    lib.b200_multi_local_devices.argtypes = [vp]
+    lib.b200_multi_ctx.argtypes = [vp, i32]
+    lib.b200_multi_ctx.restype = vp
+    lib.b200_multi_rank.argtypes = [vp, i32]
+    lib.b200_multi_bases_load.argtypes = [vp, vp, sz, i32, i32, C.POINTER(vp)]
+    lib.b200_multi_bases_known_dlog.argtypes = [vp, u64, sz, i32, C.POINTER(vp)]
+    lib.b200_multi_bases_free.argtypes = [vp, vp]
+    lib.b200_multi_bases_free.restype = None
+    lib.b200_multi_bases_len.argtypes = [vp]
+    lib.b200_multi_bases_len.restype = sz
+    lib.b200_multi_bases_shard.argtypes = [vp, i32, C.POINTER(sz), C.POINTER(sz)]
+    lib.b200_multi_bases_plan.argtypes = [vp, i32, C.POINTER(i32 * 4)]
+    lib.b200_multi_msm.argtypes = [vp, vp, vp, sz, i32, vp, C.POINTER(i32)]
+    lib.b200_multi_msm_local.argtypes = [vp, vp, C.POINTER(vp), i32, i32, vp, C.POINTER(i32)]
     lib.b200_keccak256.argtypes = [C.c_char_p, sz, vp]
     lib.b200_keccak256.restype = None
     for name in EXPORTS:

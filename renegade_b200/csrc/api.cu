@@ -13,6 +13,7 @@
 namespace b200 {
 
 static thread_local std::string g_last_error;
+std::atomic<uint64_t> g_kernel_launches{0};
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -129,6 +130,8 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_last_error.c_str(); }
 const char* b200_version(void) { return "libb200prover 0.1.0 sm_100a"; }
+
+uint64_t b200_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) { Keccak256::hash(data, len, out); }
 
@@ -547,7 +550,7 @@ int b200_selftest_field(b200_ctx* ctx, uint64_t seed, size_t iters, uint64_t* mi
     unsigned long long* d_bad = nullptr;
     B200_CUDA(cudaMalloc(&d_bad, 8));
     cudaMemsetAsync(d_bad, 0, 8, ctx->c.stream);
-    if (iters) selftest_field_kernel<<<(unsigned)((iters + 127) / 128), 128, 0, ctx->c.stream>>>(seed, iters, d_bad);
+    if (iters) B200_LAUNCH(selftest_field_kernel, (unsigned)((iters + 127) / 128), 128, 0, ctx->c.stream)(seed, iters, d_bad);
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, d_bad, 8, cudaMemcpyDeviceToHost, ctx->c.stream);
     cudaError_t e = cudaStreamSynchronize(ctx->c.stream);
@@ -571,8 +574,8 @@ int b200_field_op(b200_ctx* ctx, int field, int op, const uint64_t* a, const uin
     cudaMemcpyAsync(da, a, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->c.stream);
     cudaMemcpyAsync(db, b, n * sizeof(fe), cudaMemcpyHostToDevice, ctx->c.stream);
     const unsigned bs = 128, grid = (unsigned)((n + bs - 1) / bs);
-    if (field == 0) field_op_kernel<FrCfg><<<grid, bs, 0, ctx->c.stream>>>(op, da, db, n, dout);
-    else field_op_kernel<FqCfg><<<grid, bs, 0, ctx->c.stream>>>(op, da, db, n, dout);
+    if (field == 0) B200_LAUNCH(field_op_kernel<FrCfg>, grid, bs, 0, ctx->c.stream)(op, da, db, n, dout);
+    else B200_LAUNCH(field_op_kernel<FqCfg>, grid, bs, 0, ctx->c.stream)(op, da, db, n, dout);
     cudaMemcpyAsync(out, dout, n * sizeof(fe), cudaMemcpyDeviceToHost, ctx->c.stream);
     cudaError_t e = cudaStreamSynchronize(ctx->c.stream);
     cudaFree(da);

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <map>
@@ -24,6 +25,12 @@ int cuda_fail(cudaError_t e, const char* what);  // records the message, returns
         cudaError_t _e = (expr);                                   \
         if (_e != cudaSuccess) return ::b200::cuda_fail(_e, #expr); \
     } while (0)
+
+// Process-wide count of kernel launches made by the library (bench.py's `gpu_launches` is the difference of
+// two reads around the timed region; b200_kernel_launches()).  A relaxed increment per launch.
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void note_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+#define B200_LAUNCH(kern, grid, block, smem, st) ::b200::note_launch(), kern<<<grid, block, smem, st>>>
 
 // Grow-only device buffer
 struct DevBuf {
@@ -111,7 +118,6 @@ struct MsmScratch {
     MsmPlan pending_plan;
     size_t pending_n = 0;
     unsigned pending_batch = 0;
-    uint64_t n_kernel_launches = 0;  // kernels launched by this scratch's MSMs (bench: gpu_launches)
     // optional per-phase device timing (CUDA events on the launching stream)
     bool timing = false;
     bool ev_init = false;

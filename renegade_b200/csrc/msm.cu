@@ -641,7 +641,7 @@ static int build_tables(Bases* b, cudaStream_t st) {
     const unsigned bs = 128;
     const unsigned grid = (unsigned)((b->n + bs - 1) / bs);
     for (int j = 1; j < b->plan.n_tables; ++j) {
-        msm_table_kernel<<<grid, bs, 0, st>>>(b->tables + (size_t)(j - 1) * b->n,
+        B200_LAUNCH(msm_table_kernel, grid, bs, 0, st)(b->tables + (size_t)(j - 1) * b->n,
                                               b->tables + (size_t)j * b->n, b->n, shift);
     }
     B200_CUDA(cudaGetLastError());
@@ -704,7 +704,7 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
             return cuda_fail(e, "cudaMalloc(on-curve flag)");
         }
         cudaMemsetAsync(d_bad, 0, 4, st);
-        g1_on_curve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pts, n, d_bad);
+        B200_LAUNCH(g1_on_curve_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(d_pts, n, d_bad);
         cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
         e = cudaStreamSynchronize(st);
         cudaFree(d_bad);
@@ -831,12 +831,12 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if (s->timing) cudaEventRecord(s->ev[0], st);
     const unsigned bs = 256;
     const dim3 grid_n((unsigned)((n + bs - 1) / bs), batch);
-    msm_count_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)buckets_per_msm, counts);
-    msm_scan_kernel<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(counts, (uint32_t)n_buckets, (uint32_t)n_tiles, stt, status,
+    B200_LAUNCH(msm_count_kernel, grid_n, bs, 0, st)(d_scalars, n, stride, montgomery, pl, (uint32_t)buckets_per_msm, counts);
+    B200_LAUNCH(msm_scan_kernel, (unsigned)n_tiles, kScanThreads, 0, st)(counts, (uint32_t)n_buckets, (uint32_t)n_tiles, stt, status,
                                                                 offsets, cursor, seg_offsets);
-    msm_scatter_kernel<<<grid_n, bs, 0, st>>>(d_scalars, n, stride, montgomery, pl, (uint32_t)base_off,
+    B200_LAUNCH(msm_scatter_kernel, grid_n, bs, 0, st)(d_scalars, n, stride, montgomery, pl, (uint32_t)base_off,
                                               (uint32_t)buckets_per_msm, cursor, entries);
-    msm_segorder_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(offsets, seg_offsets, (uint32_t)n_buckets,
+    B200_LAUNCH(msm_segorder_kernel, (unsigned)((n_buckets + 255) / 256), 256, 0, st)(offsets, seg_offsets, (uint32_t)n_buckets,
                                                                              stt->seg_starts, seg_bucket, seg_order);
     // the long kernels of the MSM go to the low-priority companion stream (see b200_init)
     cudaStream_t hv = s->hv_stream ? s->hv_stream : st;
@@ -845,15 +845,15 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         cudaEventRecord(s->hv_fork, st);
         cudaStreamWaitEvent(hv, s->hv_fork, 0);
     }
-    msm_accumulate_kernel<<<(unsigned)((max_segs + 127) / 128), 128, 0, hv>>>(
+    B200_LAUNCH(msm_accumulate_kernel, (unsigned)((max_segs + 127) / 128), 128, 0, hv)(
         entries, offsets, seg_offsets, seg_bucket, seg_order, b->tables, b->n, (uint32_t)n_buckets, seg_sums);
     if (s->hv_stream) {
         cudaEventRecord(s->hv_join, hv);
         cudaStreamWaitEvent(st, s->hv_join, 0);
     }
-    msm_bucket_combine_kernel<<<(unsigned)((n_buckets + 127) / 128), 128, 0, st>>>(
+    B200_LAUNCH(msm_bucket_combine_kernel, (unsigned)((n_buckets + 127) / 128), 128, 0, st)(
         seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, &stt->heavy_count, heavy_list);
-    msm_heavy_combine_kernel<<<(unsigned)std::min<size_t>(max_heavy, 592), kReduceThreads, 0, st>>>(
+    B200_LAUNCH(msm_heavy_combine_kernel, (unsigned)std::min<size_t>(max_heavy, 592), kReduceThreads, 0, st)(
         seg_sums, seg_offsets, &stt->heavy_count, heavy_list, buckets);
     if (s->timing) cudaEventRecord(s->ev[2], st);
     {
@@ -879,10 +879,10 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
             a.row.n_blocks = (a.row.n_out + kTreeThreads - 1) / kTreeThreads;
             a.col.n_blocks = (a.col.n_out + kTreeThreads - 1) / kTreeThreads;
             if (a.row.n_blocks + a.col.n_blocks)
-                msm_tree_kernel<<<a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st>>>(a);
+                B200_LAUNCH(msm_tree_kernel, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
         }
         // row_in: R[window][2^r_log], col_in: C[window][2^l_log]
-        msm_window_finish_kernel<<<(unsigned)n_windows, 2 * kFinishHalf, 2 * kFinishHalf * sizeof(g1_xyzz), st>>>(
+        B200_LAUNCH(msm_window_finish_kernel, (unsigned)n_windows, 2 * kFinishHalf, 2 * kFinishHalf * sizeof(g1_xyzz), st)(
             col_in, (uint32_t)l_log, row_in, (uint32_t)r_log, window_sums);
     }
     B200_CUDA(cudaGetLastError());
@@ -890,7 +890,6 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     B200_CUDA(cudaMemcpyAsync(s->h_sums.p, window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     if (s->timing) cudaEventRecord(s->ev[4], st);
     B200_CUDA(cudaEventRecord(s->done_ev, st));
-    s->n_kernel_launches += 9 + (uint64_t)levels;
     return B200_OK;
 }
 
@@ -970,7 +969,7 @@ int msm_device(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, i
 int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
                                cudaStream_t st) {
     if (n == 0) return B200_OK;
-    known_dlog_bases_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, first, n, d_out);
+    B200_LAUNCH(known_dlog_bases_kernel, (unsigned)((n + 127) / 128), 128, 0, st)(seed, first, n, d_out);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }
@@ -978,7 +977,7 @@ int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine*
 int splitmix_fr_device(uint64_t seed, size_t first, size_t n, int montgomery, fe* d_out,
                        cudaStream_t st) {
     if (n == 0) return B200_OK;
-    splitmix_fr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, first, n, montgomery, d_out);
+    B200_LAUNCH(splitmix_fr_kernel, (unsigned)((n + 255) / 256), 256, 0, st)(seed, first, n, montgomery, d_out);
     B200_CUDA(cudaGetLastError());
     return B200_OK;
 }

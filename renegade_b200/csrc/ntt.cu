@@ -221,7 +221,7 @@ void fill_powers(fe* d_out, size_t n, fe base, fe scale, cudaStream_t st) {
     }
     if (n == 0) return;
     const unsigned bs = 256;
-    powers_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(d_out, n, p);
+    B200_LAUNCH(powers_kernel, (unsigned)((n + bs - 1) / bs), bs, 0, st)(d_out, n, p);
 }
 
 Domain::~Domain() {
@@ -309,8 +309,8 @@ int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, u
         if (threads < 32) threads = 32;
         dim3 grid((unsigned)(((size_t)1 << L) >> e_log), batch);
         const size_t smem = (size_t)E * 32;
-        if (final_pass) ntt_pass_kernel<true><<<grid, threads, smem, st>>>(a);
-        else ntt_pass_kernel<false><<<grid, threads, smem, st>>>(a);
+        if (final_pass) B200_LAUNCH(ntt_pass_kernel<true>, grid, threads, smem, st)(a);
+        else B200_LAUNCH(ntt_pass_kernel<false>, grid, threads, smem, st)(a);
         hi -= w;
     }
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;

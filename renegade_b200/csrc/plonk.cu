@@ -459,10 +459,10 @@ static void scan_mul_exclusive(fe* data, size_t n, fe* scratch, cudaStream_t st)
         // data[0] <- 1 handled by the local kernel as well
     }
     const size_t n1 = (n + CH - 1) / CH;
-    k_scan_mul_local<<<grid_for(n1, 128), 128, 0, st>>>(data, n, scratch);
+    B200_LAUNCH(k_scan_mul_local, grid_for(n1, 128), 128, 0, st)(data, n, scratch);
     if (n1 > 1) {
         scan_mul_exclusive(scratch, n1, scratch + n1, st);
-        k_scan_mul_apply<<<grid_for(n, 256), 256, 0, st>>>(data, n, scratch);
+        B200_LAUNCH(k_scan_mul_apply, grid_for(n, 256), 256, 0, st)(data, n, scratch);
     }
 }
 
@@ -472,7 +472,7 @@ static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, f
     const size_t n1 = (len + CH - 1) / CH;
     fe* H = scratch;
     fe* T = scratch + n1;
-    k_horner_local<<<grid_for(n1, 128), 128, 0, st>>>(p, len, z, S, H);
+    B200_LAUNCH(k_horner_local, grid_for(n1, 128), 128, 0, st)(p, len, z, S, H);
     if (n1 == 1) {
         cudaMemcpyAsync(out_total, H, sizeof(fe), cudaMemcpyDeviceToDevice, st);
         return;
@@ -483,7 +483,7 @@ static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, f
         ZPow zp;
         zp.v[0] = fe_one<Fr>();
         for (int e = 1; e <= CH; ++e) zp.v[e] = FMUL(zp.v[e - 1], z);
-        k_horner_apply<<<grid_for(len, 256), 256, 0, st>>>(S, len, zp, T, n1);
+        B200_LAUNCH(k_horner_apply, grid_for(len, 256), 256, 0, st)(S, len, zp, T, n1);
     }
 }
 
@@ -517,7 +517,7 @@ static void eval_batch(const fe* const* polys, const size_t* lens, const fe* poi
             // levels alternate between the two halves of each polynomial's scratch slice
             a.H[q] = last ? out + q : scratch + (size_t)q * per_poly + (level & 1 ? region_a : 0);
         }
-        k_horner_local_batch<<<dim3(grid_for(max_chunks, 64), count), 64, 0, st>>>(a);
+        B200_LAUNCH(k_horner_local_batch, dim3(grid_for(max_chunks, 64), count), 64, 0, st)(a);
         if (last) break;
         for (int q = 0; q < count; ++q) {
             a.p[q] = a.H[q];
@@ -598,7 +598,7 @@ static int coset_evals(const ProvingKey* pk, const Domain* dn, const fe* src, si
         set_error("coset_evals: polynomial longer than 2n");
         return B200_ERR_INVALID;
     }
-    k_coset_fold<<<dim3(grid_for(n, 256), (unsigned)pk->nc, count), 256, 0, st>>>(src, src_stride, len, n, pk->nc, pk->cc,
+    B200_LAUNCH(k_coset_fold, dim3(grid_for(n, 256), (unsigned)pk->nc, count), 256, 0, st)(src, src_stride, len, n, pk->nc, pk->cc,
                                                                                  pk->cscale, dst);
     return ntt_device(dn, dst, scratch, /*inverse=*/0, /*coset=*/0, count * (unsigned)pk->nc, n, st);
 }
@@ -679,15 +679,15 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
             return fail(B200_ERR_INVALID);
         }
     }
-    k_l1_denominators<<<grid_for(m, 256), 256, 0, st>>>(pk->coset_pts, m, host_from_u64(n), pk->l1_inv);
-    k_batch_inverse<<<grid_for((m + 15) / 16, 128), 128, 0, st>>>(pk->l1_inv, pk->ce_sel /*scratch, overwritten below*/, m);
+    B200_LAUNCH(k_l1_denominators, grid_for(m, 256), 256, 0, st)(pk->coset_pts, m, host_from_u64(n), pk->l1_inv);
+    B200_LAUNCH(k_batch_inverse, grid_for((m + 15) / 16, 128), 128, 0, st)(pk->l1_inv, pk->ce_sel /*scratch, overwritten below*/, m);
 
     // selectors: evaluations -> coefficients -> commitments
     cudaMemcpyAsync(pk->sel_coeffs, h_selectors, NS * n * sizeof(fe), cudaMemcpyHostToDevice, st);
     if ((rc = ntt_device(dn, pk->sel_coeffs, scratch, 1, 0, NS, n, st)) != B200_OK) return fail(rc);
     // sigmas: permutation -> evaluations (kept for the grand product) -> coefficients
     cudaMemcpyAsync(d_perm, h_perm, NW * n * 8, cudaMemcpyHostToDevice, st);
-    k_sigma_evals<<<grid_for(NW * n, 256), 256, 0, st>>>(d_perm, pk->dom, n, pk->k, pk->sig_evals);
+    B200_LAUNCH(k_sigma_evals, grid_for(NW * n, 256), 256, 0, st)(d_perm, pk->dom, n, pk->k, pk->sig_evals);
     cudaMemcpyAsync(pk->sig_coeffs, pk->sig_evals, NW * n * sizeof(fe), cudaMemcpyDeviceToDevice, st);
     if ((rc = ntt_device(dn, pk->sig_coeffs, scratch, 1, 0, NW, n, st)) != B200_OK) return fail(rc);
     // resident evaluations of the 18 fixed polynomials on the quotient domain
@@ -774,7 +774,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
             b.b[i][0] = h_blinders[2 * i];
             b.b[i][1] = h_blinders[2 * i + 1];
         }
-        k_blind_wires<<<1, 32, 0, st>>>(w.wpoly, S, n, b);
+        B200_LAUNCH(k_blind_wires, 1, 32, 0, st)(w.wpoly, S, n, b);
     }
     // Fork: the coset evaluations of the 5 wire polynomials and of the public-input polynomial do not
     // depend on any challenge, so they run on a second stream underneath the round-1/2 commitments
@@ -806,8 +806,8 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     // ---- round 2 ------------------------------------------------------------------------------------
     const fe beta = tr.get_and_append_challenge();
     const fe gamma = tr.get_and_append_challenge();
-    k_perm_num_den<<<grid_for(n, 128), 128, 0, st>>>(w.wires_ev, pk->sig_evals, pk->dom, pk->k, beta, gamma, n, w.num, w.den);
-    k_ratio<<<grid_for((n + 15) / 16, 64), 64, 0, st>>>(w.num, w.den, w.tmp, n);
+    B200_LAUNCH(k_perm_num_den, grid_for(n, 128), 128, 0, st)(w.wires_ev, pk->sig_evals, pk->dom, pk->k, beta, gamma, n, w.num, w.den);
+    B200_LAUNCH(k_ratio, grid_for((n + 15) / 16, 64), 64, 0, st)(w.num, w.den, w.tmp, n);
     scan_mul_exclusive(w.den, n, w.scan, st);  // z(w^j) = prod_{i<j} ratio_i
     B200_CUDA(cudaMemsetAsync(w.zpoly, 0, S * sizeof(fe), st));
     B200_CUDA(cudaMemcpyAsync(w.zpoly, w.den, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
@@ -816,7 +816,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         BlindArgs b;
         b.count = 3;
         for (int i = 0; i < 3; ++i) b.b[i] = h_blinders[10 + i];
-        k_blind<<<1, 32, 0, st>>>(w.zpoly, n, b);
+        B200_LAUNCH(k_blind, 1, 32, 0, st)(w.zpoly, n, b);
     }
     if ((rc = commit(c, pk, w.zpoly, n + 3, &proof->prod_perm_poly_comm)) != B200_OK) return rc;
     tr.append_commitment(proof->prod_perm_poly_comm);
@@ -847,21 +847,21 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         q.alpha2 = fe_sqr<Fr>(alpha);
         for (int i = 0; i < 8; ++i) q.zh_inv[i] = pk->zh_inv[i];
         HeavyScope hv(c, st);
-        k_quotient<<<grid_for(m, 128), 128, 0, hv.run>>>(q);
+        B200_LAUNCH(k_quotient, grid_for(m, 128), 128, 0, hv.run)(q);
         // back to coefficients: nc size-n inverse transforms, then un-scale and un-mix the cosets
         if ((rc = ntt_device(dn, w.quot, nscr, 1, 0, (unsigned)pk->nc, n, hv.run)) != B200_OK) return rc;
-        if (pk->nc == 6) k_coset_combine<6><<<grid_for(n, 128), 128, 0, hv.run>>>(w.quot, n, pk->cscale_inv, pk->comb);
-        else k_coset_combine<8><<<grid_for(n, 128), 128, 0, hv.run>>>(w.quot, n, pk->cscale_inv, pk->comb);
+        if (pk->nc == 6) B200_LAUNCH(k_coset_combine<6>, grid_for(n, 128), 128, 0, hv.run)(w.quot, n, pk->cscale_inv, pk->comb);
+        else B200_LAUNCH(k_coset_combine<8>, grid_for(n, 128), 128, 0, hv.run)(w.quot, n, pk->cscale_inv, pk->comb);
     }
     const size_t deg = NW * (n + 1) + 2;
     B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
-    k_check_degree<<<grid_for(m - deg, 256), 256, 0, st>>>(w.quot, deg, m, w.flag);
+    B200_LAUNCH(k_check_degree, grid_for(m - deg, 256), 256, 0, st)(w.quot, deg, m, w.flag);
     uint32_t* h_flag = reinterpret_cast<uint32_t*>(c->h_small.p);  // pinned; read after the commitments below are in
     B200_CUDA(cudaMemcpyAsync(h_flag, w.flag, 4, cudaMemcpyDeviceToHost, st));
     {
         SplitArgs sa;
         for (int i = 0; i < 4; ++i) sa.b[i] = h_blinders[13 + i];
-        k_split_quotient<<<dim3(grid_for(n + 3, 256), NW), 256, 0, st>>>(w.quot, n, S, sa, w.split);
+        B200_LAUNCH(k_split_quotient, dim3(grid_for(n + 3, 256), NW), 256, 0, st)(w.quot, n, S, sa, w.split);
     }
     mark();  // [2] round 3 (enqueue only: the quotient's degree flag is read with the commitments)
     // the last chunk has n coefficients; its tail up to n + 3 is zero, so one batch length serves
@@ -947,7 +947,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
             push(pk->sig_coeffs + (size_t)i * n, n, cv);
         }
         a.count = t;
-        k_lincomb<<<grid_for(n + 3, 128), 128, 0, st>>>(a, n + 3, w.lin);
+        B200_LAUNCH(k_lincomb, grid_for(n + 3, 128), 128, 0, st)(a, n + 3, w.lin);
     }
     // opening proofs: commit((batch - batch(zeta)) / (X - zeta)) and commit((z - z(zeta w)) / (X - zeta w))
     horner_suffix(w.lin, n + 3, zeta, w.sdiv, w.evals + 16, w.hscr, st);
@@ -1013,7 +1013,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
         a.count = 2;
         a.p[0] = d_a1; a.len[0] = (uint32_t)len1; a.s[0] = one;
         a.p[1] = d_a2; a.len[1] = (uint32_t)len2; a.s[1] = fe_neg<Fr>(one);
-        k_lincomb<<<grid_for(len, 128), 128, 0, st>>>(a, len, d_diff);
+        B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_diff);
     }
     // roots of the link group's vanishing polynomial
     const fe g = host_root_of_unity(alignment);
@@ -1031,7 +1031,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     }
     // a1 and a2 must agree on every root of the group, i.e. every division is exact: otherwise no link
     // proof verifies and the reference's prover output would be rejected (silent bad proof)
-    k_any_nonzero<<<1, 256, 0, st>>>(rems, size, d_flag);
+    B200_LAUNCH(k_any_nonzero, 1, 256, 0, st)(rems, size, d_flag);
     uint32_t* h_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_small.p) + 1024);
     B200_CUDA(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     {
@@ -1056,7 +1056,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
         a.count = 2;
         a.p[0] = d_diff; a.len[0] = (uint32_t)len; a.s[0] = one;
         a.p[1] = cur; a.len[1] = (uint32_t)cur_len; a.s[1] = fe_neg<Fr>(zd);
-        k_lincomb<<<grid_for(len, 128), 128, 0, st>>>(a, len, d_ident);
+        B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_ident);
     }
     fe* d_open = d_pp[size & 1];  // the buffer that does not hold the quotient
     horner_suffix(d_ident, len, eta, d_open, slot, hscr, st);

@@ -143,7 +143,7 @@ int b200_poseidon2_permute_batch(b200_ctx* ctx, uint64_t* states, size_t batch) 
     if ((rc = ctx->c.plonk_ws.reserve(batch * 3 * sizeof(fe))) != B200_OK) return rc;
     fe* d = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
     B200_CUDA(cudaMemcpyAsync(d, states, batch * 3 * sizeof(fe), cudaMemcpyDefault, st));
-    k_poseidon2_permute<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(d, batch);
+    B200_LAUNCH(k_poseidon2_permute, (unsigned)((batch + 127) / 128), 128, 0, st)(d, batch);
     B200_CUDA(cudaMemcpyAsync(states, d, batch * 3 * sizeof(fe), cudaMemcpyDefault, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;
@@ -163,7 +163,7 @@ int b200_poseidon2_hash_batch(b200_ctx* ctx, const uint64_t* inputs, size_t batc
     fe* d_in = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
     fe* d_out = d_in + batch * len;
     if (len) B200_CUDA(cudaMemcpyAsync(d_in, inputs, batch * len * sizeof(fe), cudaMemcpyDefault, st));
-    k_poseidon2_hash<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(d_in, batch, len, d_out);
+    B200_LAUNCH(k_poseidon2_hash, (unsigned)((batch + 127) / 128), 128, 0, st)(d_in, batch, len, d_out);
     B200_CUDA(cudaMemcpyAsync(out, d_out, batch * sizeof(fe), cudaMemcpyDefault, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;

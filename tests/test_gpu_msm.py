@@ -177,7 +177,7 @@ def test_msm_2_20_known_dlog_and_sharding(ctx, oracle, pyoracle, mode):
         b, e = shard_range(n, r, 2)
         xy, pinf = ctx.msm_device(bases, d_s.data_ptr() + 32 * b, e - b, montgomery=False, base_off=b)
         recs[r, :8], recs[r, 8] = xy, int(pinf)
-    out2, inf2 = combine_partials(ctx, recs)
+    out2, inf2 = combine_partials(recs)
     assert not inf2 and (out2 == exp).all()
 
 
