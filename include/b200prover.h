@@ -206,6 +206,27 @@ int b200_plonk_link(b200_ctx* ctx, const b200_bases* srs, const uint64_t* a1, si
                     unsigned alignment, size_t offset, size_t size, b200_link_proof* proof,
                     uint64_t* eta);
 
+/* ---- verification (host only; no device is needed or used) -----------------------------------
+ * G2 points are 128-byte records x0 || x1 || y0 || y1 (Montgomery Fq), the layout of the ptau file's
+ * G2 section read by srs.rs:185-199: g2_h = `UnivariateUniversalParams.h`, g2_tau_h = `.beta_h`.
+ * *accepted = 1 / 0; a malformed (off-curve) proof element is a rejection, not an error. */
+/* Replaces `PlonkKzgSnark::<Bn254>::verify::<SolidityTranscript>(&vk, public_inputs, &proof, None)`
+ * (traits.rs:1012-1018, reached from `SingleProverCircuit::verify`, traits.rs:1003-1019).  The
+ * verifying key is passed flat: domain size 2^log_n, num_inputs, k[5], the 13 selector and 5 sigma
+ * commitments (b200_pk_verifying_key). */
+int b200_plonk_verify(unsigned log_n, size_t num_inputs, const uint64_t* k, const uint64_t* selector_comms,
+                      const uint64_t* sigma_comms, const uint64_t* pub_inputs, const b200_proof* proof,
+                      const uint64_t g2_h[16], const uint64_t g2_tau_h[16], int* accepted);
+/* Replaces `PlonkKzgSnark::verify_link_proof::<SolidityTranscript>(&comm_a, &comm_b, &link_proof,
+ * &group_layout, &open_key)` (proof_linking/intent_only.rs:77-84, `validate_*_link`). */
+int b200_plonk_verify_link(const uint64_t* comm1, const uint64_t* comm2, unsigned alignment, size_t offset,
+                           size_t size, const b200_link_proof* proof, const uint64_t g2_h[16],
+                           const uint64_t g2_tau_h[16], int* accepted);
+/* *is_one = [ prod_i e(P_i, Q_i) == 1 ] for k (G1, G2) pairs (64-byte / 128-byte records) with one
+ * final exponentiation — the primitive under both verifiers and the reference's SRS unit test
+ * (srs.rs:236-266: e(tau^i G, tau H) == e(tau^(i+1) G, H)). */
+int b200_pairing_check(const uint64_t* g1_points, const uint64_t* g2_points, size_t k, int* is_one);
+
 /* Wall-clock milliseconds of the last proof's phases on this context: round 1, round 2, round 3
  * (coset NTTs + quotient + split), round 3 commitments, round 4, round 5, then two spare slots. */
 int b200_plonk_last_timings(b200_ctx* ctx, float out_ms[8]);

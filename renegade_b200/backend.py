@@ -323,8 +323,67 @@ class ProvingKey:
             pass
 
 
+@dataclass
+class VerifyingKey:
+    """mpc-plonk `VerifyingKey<Bn254>` flattened: domain size, public-input count, coset representatives, the 13
+    selector and 5 sigma commitments, and the two G2 elements of the `open_key` (`h`, `beta_h`: 128-byte ptau
+    records x0 || x1 || y0 || y1, srs.rs:185-199).  Plain host data: verification needs no device."""
+    log_n: int
+    num_inputs: int
+    k: np.ndarray
+    selector_comms: np.ndarray
+    sigma_comms: np.ndarray
+    g2_h: np.ndarray
+    g2_tau_h: np.ndarray
+
+    @staticmethod
+    def from_proving_key(pk: "ProvingKey", g2_h: np.ndarray, g2_tau_h: np.ndarray) -> "VerifyingKey":
+        return VerifyingKey(pk.log_n, pk.num_inputs, pk.k, pk.selector_comms, pk.sigma_comms, g2_h, g2_tau_h)
+
+
+def _u64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(shape) if shape is not None else a
+
+
+def pairing_check(g1_points, g2_points) -> bool:
+    """prod e(P_i, Q_i) == 1 (`b200_pairing_check`; host only).  P_i: 8 x uint64, Q_i: 16 x uint64."""
+    lib = _lib.load()
+    p = _u64(np.stack([_u64(x) for x in g1_points]), (-1, 8))
+    q = _u64(np.stack([_u64(x) for x in g2_points]), (-1, 16))
+    if p.shape[0] != q.shape[0]:
+        raise ValueError("one G2 point per G1 point")
+    one = C.c_int(0)
+    _lib.check(lib.b200_pairing_check(_ptr(p), _ptr(q), p.shape[0], C.byref(one)))
+    return bool(one.value)
+
+
+def verify_link_proof(comm_a: np.ndarray, comm_b: np.ndarray, proof: "B200LinkProof", layout: "GroupLayout",
+                      g2_h: np.ndarray, g2_tau_h: np.ndarray) -> bool:
+    """`PlonkKzgSnark::verify_link_proof::<SolidityTranscript>` (proof_linking/intent_only.rs:77-84)."""
+    ok = C.c_int(0)
+    _lib.check(_lib.load().b200_plonk_verify_link(_ptr(_u64(comm_a)), _ptr(_u64(comm_b)), layout.alignment, layout.offset,
+                                                  layout.size, C.byref(proof), _ptr(_u64(g2_h)), _ptr(_u64(g2_tau_h)),
+                                                  C.byref(ok)))
+    return bool(ok.value)
+
+
 class PlonkKzgSnark:
-    """mpc-plonk `PlonkKzgSnark<Bn254>` as called at traits.rs:850 and traits.rs:996."""
+    """mpc-plonk `PlonkKzgSnark<Bn254>` as called at traits.rs:850, traits.rs:996 and traits.rs:1012."""
+
+    @staticmethod
+    def verify(vk: VerifyingKey, pub_inputs: np.ndarray, proof: "B200Proof") -> bool:
+        """`PlonkKzgSnark::verify::<SolidityTranscript>(&vk, &public_inputs, &proof, None)` (traits.rs:1012-1018).
+        Host only."""
+        pi = _u64(pub_inputs, (-1, 4))
+        if pi.shape[0] != vk.num_inputs:
+            return False  # the reference's verifier errors on a wrong public-input count: not accepted
+        ok = C.c_int(0)
+        _lib.check(_lib.load().b200_plonk_verify(vk.log_n, vk.num_inputs, _ptr(_u64(vk.k, (5, 4))),
+                                                 _ptr(_u64(vk.selector_comms, (13, 8))), _ptr(_u64(vk.sigma_comms, (5, 8))),
+                                                 _ptr(pi) if pi.size else None, C.byref(proof), _ptr(_u64(vk.g2_h)),
+                                                 _ptr(_u64(vk.g2_tau_h)), C.byref(ok)))
+        return bool(ok.value)
 
     @staticmethod
     def preprocess(ctx: Context, srs: Bases, log_n: int, num_inputs: int, selectors: np.ndarray,

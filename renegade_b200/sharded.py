@@ -50,6 +50,7 @@ class MultiGpu:
     def __init__(self, handle):
         self._lib = _lib.load()
         self._h = handle
+        self._borrowed = []
 
     @staticmethod
     def single_process(devices) -> "MultiGpu":
@@ -96,10 +97,13 @@ class MultiGpu:
 
     def ctx(self, local: int = 0) -> Context:
         """Borrowed view of local device `local`'s context (owned by the multi handle)."""
+        raw = self._lib.b200_multi_ctx(self._h, local)
+        if not raw:
+            raise IndexError("local device index out of range")
         c = Context.__new__(Context)
-        c._lib = self._lib
-        c._h = C.c_void_p(self._lib.b200_multi_ctx(self._h, local))
-        c._owned = False
+        c._lib, c._h, c.device, c._borrowed = self._lib, C.c_void_p(raw), local, True
+        c.close = lambda: None  # the multi handle owns it
+        self._borrowed.append(c)
         return c
 
     def load_bases(self, points: np.ndarray, window_bits: int = 0, check_on_curve: bool = False) -> MultiBases:
@@ -137,6 +141,8 @@ class MultiGpu:
         if self._h:
             self._lib.b200_multi_shutdown(self._h)
             self._h = None
+            for c in self._borrowed:  # their handles died with the multi handle
+                c._h = None
 
 
 def combine_partials(records: np.ndarray):
