@@ -31,6 +31,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "examples"))  # host_circuits: caller-side restatement of the reference's circuits
 
 LOG_N = 16                 # "~2^16 constraints"
 NUM_INPUTS = 17            # IntentAndBalancePrivateSettlementStatement
@@ -100,12 +101,12 @@ class ClockSampler:
 def make_circuit(kind, log_n, seed):
     """The proved circuit.  "synthetic" (default): renegade_b200/synth.py, random gates of the reference's mix.
     "merkle": as many height-10 Poseidon2 Merkle openings (the reference's gadgets restated in
-    renegade_b200/circuit.py, public roots) as fit the domain — 27 at n = 2^16; same prover work, real constraints."""
+    examples/host_circuits/circuit.py, public roots) as fit the domain — 27 at n = 2^16; same prover work, real constraints."""
     from renegade_b200 import synth
     if kind == "synthetic":
         return synth.synth_circuit(log_n, num_inputs=NUM_INPUTS, seed=seed)
     import random
-    from renegade_b200 import circuit as cb
+    from host_circuits import circuit as cb
     rnd = random.Random(seed)
     cs = cb.PlonkCircuit()
     per_opening = 2400  # 11 sponge hashes of 195-gate permutations plus selects and additions
@@ -120,14 +121,14 @@ def make_circuit(kind, log_n, seed):
 
 
 def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps):
-    """The reference's own statements at their own sizes (restated in renegade_b200/valid_balance_create.py and
+    """The reference's own statements at their own sizes (restated in examples/host_circuits/valid_balance_create.py and
     private_settlement.py: n = 2^13 and 2^12, not the 2^16 BASELINE.json quotes): one proof alone, and proofs/s end
     to end from pinned host memory through the pool.  Reported beside the headline, never instead of it."""
     import numpy as np
     import torch
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import private_settlement as ps
     from renegade_b200 import synth
-    from renegade_b200 import valid_balance_create as vbc
+    from host_circuits import valid_balance_create as vbc
     from renegade_b200.backend import PlonkKzgSnark, prove_raw
     w, st = vbc.create_witness_statement(1)
     parties, st2 = ps.create_witness_statement(1)
@@ -171,9 +172,9 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
     pinned host memory."""
     import numpy as np
     import torch
-    from renegade_b200 import intent_and_balance_validity as val
-    from renegade_b200 import output_balance_validity as obv
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import intent_and_balance_validity as val
+    from host_circuits import output_balance_validity as obv
+    from host_circuits import private_settlement as ps
     from renegade_b200 import synth
     from renegade_b200.backend import GroupLayout, LinkingHint, PlonkKzgSnark
     if pool is None:
@@ -326,7 +327,7 @@ def main():
                     help="skip the extra leg that proves the restated VALID BALANCE CREATE and PRIVATE SETTLEMENT circuits")
     ap.add_argument("--circuit", choices=("synthetic", "merkle"), default="synthetic",
                     help="synthetic: random gates of the reference's mix (default); merkle: height-10 Poseidon2 Merkle "
-                         "openings built with the reference's gadgets (renegade_b200/circuit.py)")
+                         "openings built with the reference's gadgets (examples/host_circuits/circuit.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

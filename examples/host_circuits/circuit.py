@@ -32,8 +32,8 @@ from typing import List, Sequence
 
 import numpy as np
 
-from .poseidon2_constants import CAPACITY, FULL_ROUND_CONSTANTS, PARTIAL_ROUND_CONSTANTS, R_F, R_P, RATE
-from .synth import N_SELECTORS, N_WIRES, Q_C, Q_ECC, Q_HASH, Q_LC, Q_MUL, Q_O, R, SynthCircuit, gate_value, to_mont_array
+from renegade_b200.poseidon2_constants import CAPACITY, FULL_ROUND_CONSTANTS, PARTIAL_ROUND_CONSTANTS, R_F, R_P, RATE
+from renegade_b200.synth import N_SELECTORS, N_WIRES, Q_C, Q_ECC, Q_HASH, Q_LC, Q_MUL, Q_O, R, SynthCircuit, gate_value, to_mont_array
 
 GATE_WIDTH = 4
 Variable = int

@@ -1,0 +1,123 @@
+"""The five restated statements as `SingleProverCircuit`s (renegade_b200/circuit_types.py), under the reference's
+circuit names — the registry the prover service (renegade_b200/service.py) and the tests use.
+
+Reference: the `SingleProverCircuit` impls at circuits-core/src/zk_circuits/valid_balance_create.rs:188-215,
+settlement/intent_and_balance_private_settlement.rs:288-330, validity_proofs/intent_and_balance.rs:262-300,
+validity_proofs/output_balance.rs (same pattern); the validity circuits take their link-group placement from the
+settlement circuit's layout (`proof_linking_groups`, intent_and_balance.rs:270-279)."""
+from __future__ import annotations
+
+from renegade_b200.circuit_types import SingleProverCircuit
+from renegade_b200.fields import scalars_to_limbs
+
+from . import intent_and_balance_validity as val
+from . import output_balance_validity as obv
+from . import private_settlement as ps
+from . import valid_balance_create as vbc
+
+
+class ValidBalanceCreate(SingleProverCircuit):
+    @classmethod
+    def name(cls):
+        return vbc.ValidBalanceCreate.name()
+
+    @classmethod
+    def synthesize(cls, witness, statement, layout):
+        return vbc.ValidBalanceCreate.build(witness, statement)
+
+    @classmethod
+    def statement_scalars(cls, statement):
+        return scalars_to_limbs(statement.to_scalars())
+
+    @classmethod
+    def dummy_instance(cls):
+        return vbc.create_witness_statement(0)
+
+
+class IntentAndBalancePrivateSettlementCircuit(SingleProverCircuit):
+    """Witness = the two `PartyWitness`es."""
+
+    @classmethod
+    def name(cls):
+        return ps.IntentAndBalancePrivateSettlementCircuit.name()
+
+    @classmethod
+    def proof_linking_groups(cls):
+        return [(g, None) for g in ps.PARTY_LINKS + ps.OUTPUT_LINKS]
+
+    @classmethod
+    def generate_layout(cls):
+        parties, statement = ps.create_witness_statement(0)
+        return ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement).get_circuit_layout()
+
+    @classmethod
+    def synthesize(cls, witness, statement, layout):
+        return ps.IntentAndBalancePrivateSettlementCircuit.build(witness, statement, layout)
+
+    @classmethod
+    def statement_scalars(cls, statement):
+        return scalars_to_limbs(statement.to_scalars())
+
+    @classmethod
+    def dummy_instance(cls):
+        return ps.create_witness_statement(0)
+
+
+class IntentAndBalanceValidityCircuit(SingleProverCircuit):
+    @classmethod
+    def name(cls):
+        return val.IntentAndBalanceValidityCircuit.name()
+
+    @classmethod
+    def proof_linking_groups(cls):
+        lay = IntentAndBalancePrivateSettlementCircuit.get_circuit_layout()
+        return [(g, lay[g]) for g in ps.PARTY_LINKS]
+
+    @classmethod
+    def generate_layout(cls):  # the settlement circuit's placement of the party groups
+        return IntentAndBalancePrivateSettlementCircuit.get_circuit_layout()
+
+    @classmethod
+    def synthesize(cls, witness, statement, layout):
+        return val.IntentAndBalanceValidityCircuit.build(witness, statement, layout)
+
+    @classmethod
+    def statement_scalars(cls, statement):
+        return scalars_to_limbs(statement.to_scalars())
+
+    @classmethod
+    def dummy_instance(cls):
+        return val.create_witness_statement(0)
+
+
+class OutputBalanceValidityCircuit(SingleProverCircuit):
+    @classmethod
+    def name(cls):
+        return obv.OutputBalanceValidityCircuit.name()
+
+    @classmethod
+    def proof_linking_groups(cls):
+        lay = IntentAndBalancePrivateSettlementCircuit.get_circuit_layout()
+        return [(g, lay[g]) for g in ps.OUTPUT_LINKS]
+
+    @classmethod
+    def generate_layout(cls):
+        return IntentAndBalancePrivateSettlementCircuit.get_circuit_layout()
+
+    @classmethod
+    def synthesize(cls, witness, statement, layout):
+        return obv.OutputBalanceValidityCircuit.build(witness, statement, layout)
+
+    @classmethod
+    def statement_scalars(cls, statement):
+        return scalars_to_limbs(statement.to_scalars())
+
+    @classmethod
+    def dummy_instance(cls):
+        parties, _ = ps.create_witness_statement(0)
+        return obv.create_witness_statement(0, parties[0].output_balance)
+
+
+# the circuits `NativeProofManager::preprocess_circuits` registers (native_proof_manager.rs:305-331) that are restated here
+REGISTERED = [ValidBalanceCreate, IntentAndBalancePrivateSettlementCircuit, IntentAndBalanceValidityCircuit,
+              OutputBalanceValidityCircuit]

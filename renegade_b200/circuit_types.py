@@ -1,0 +1,237 @@
+"""`SingleProverCircuit` surface over the B200 proving backend — the host-side mirror of
+/root/reference/crates/circuits/circuit-types/src/traits.rs:75-92, 817-1020 and
+circuits-core/src/lib.rs:112-142, so that callers (and the parity tests) read like the reference's:
+
+    proof          = singleprover_prove(ValidBalanceCreate, witness, statement)
+    proof, hint    = singleprover_prove_with_hint(C, witness, statement)
+    verify_singleprover_proof(C, statement, proof)         # raises VerifierError
+    singleprover_prove_and_verify(C, witness, statement)
+
+What this module owns (the reference's `circuit-types` side of the boundary):
+  * `SYSTEM_SRS` (`set_system_srs`): the G1 powers resident on the device + the two G2 elements of the open key;
+  * the proving/verifying key cache keyed by `C.name()` (`setup_preprocessed_keys`, traits.rs:821-855: keys are derived
+    once per circuit from a dummy instance of the right topology and shared by every prover thread) and the circuit
+    layout cache (traits.rs:914-946);
+  * prove = synthesise -> finalize -> draw the 17 blinders from the OS RNG (`thread_rng()`, traits.rs:994) ->
+    `PlonkKzgSnark.prove_with_link_hint` (device); verify = statement scalars -> `PlonkKzgSnark.verify` (host pairing);
+  * the error split `ProverError::{Circuit, Plonk, Verification}` / `VerifierError::Plonk` (errors.rs:33-58).
+
+What it does NOT own: the constraint system.  mpc-relation's `PlonkCircuit` and the gadgets are upstream / caller code
+(Rust in a deployment; the Python restatement under examples/host_circuits for tests and benches).  A circuit class
+therefore provides `synthesize(witness, statement, layout)` returning any object with `finalize_for_arithmetization()`
+(-> tables in the layout of `renegade_b200.synth.SynthCircuit`) and, for link groups, `get_circuit_layout()`.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .backend import (B200Proof, Bases, Context, LinkingHint, PlonkKzgSnark, ProvingKey, VerifyingKey)
+from .fields import SCALAR_FIELD_MODULUS, scalars_to_limbs
+
+PlonkProof = B200Proof                    # circuit-types/src/lib.rs:72-101
+ProofLinkingHint = LinkingHint
+
+
+class ProverError(Exception):
+    """circuit-types/src/errors.rs:33-47.  `kind` is one of "Circuit", "Plonk", "Verification"."""
+
+    def __init__(self, kind: str, detail: Any):
+        super().__init__(f"{kind}({detail})")
+        self.kind, self.detail = kind, detail
+
+
+class VerifierError(Exception):
+    """circuit-types/src/errors.rs:50-58 (`VerifierError::Plonk`)."""
+
+
+@dataclass
+class SystemSrs:
+    """`SYSTEM_SRS` (primitives/srs.rs:30-71): `powers_of_g` on the device, `h` / `beta_h` as 128-byte G2 records."""
+    ctx: Context
+    powers_of_g: Bases
+    g2_h: np.ndarray
+    g2_tau_h: np.ndarray
+
+
+_SYSTEM_SRS: Optional[SystemSrs] = None
+_KEY_LOCK = threading.RLock()
+_CIRCUIT_KEY_CACHE: Dict[str, Tuple[ProvingKey, VerifyingKey]] = {}
+_CIRCUIT_LAYOUT_CACHE: Dict[str, Any] = {}
+
+
+def set_system_srs(ctx: Context, powers_of_g: Bases, g2_h: np.ndarray, g2_tau_h: np.ndarray) -> SystemSrs:
+    """Install the process-wide SRS (the reference parses srs/srs00 once, lazily).  Clears the key cache: keys
+    belong to the SRS they were derived from."""
+    global _SYSTEM_SRS
+    with _KEY_LOCK:
+        clear_key_cache()
+        _SYSTEM_SRS = SystemSrs(ctx, powers_of_g, np.ascontiguousarray(g2_h, dtype=np.uint64).reshape(16),
+                                np.ascontiguousarray(g2_tau_h, dtype=np.uint64).reshape(16))
+        return _SYSTEM_SRS
+
+
+def system_srs() -> SystemSrs:
+    if _SYSTEM_SRS is None:
+        raise ProverError("Plonk", "SYSTEM_SRS is not set (call set_system_srs)")
+    return _SYSTEM_SRS
+
+
+def clear_key_cache() -> None:
+    with _KEY_LOCK:
+        for pk, _ in _CIRCUIT_KEY_CACHE.values():
+            try:
+                pk.free()
+            except Exception:
+                pass
+        _CIRCUIT_KEY_CACHE.clear()
+        _CIRCUIT_LAYOUT_CACHE.clear()
+
+
+def draw_blinders(rng=None) -> np.ndarray:
+    """The 17 field elements the prover draws (2 per wire polynomial, 3 for the permutation product, 4 for the quotient
+    split), Montgomery form.  rng = None: the OS generator, as `thread_rng()` at traits.rs:994; a `random.Random` makes
+    a proof reproducible (the parity tests do that on both sides)."""
+    if rng is None:
+        vals = [int.from_bytes(os.urandom(48), "little") % SCALAR_FIELD_MODULUS for _ in range(17)]  # 384 bits: negligible bias
+    else:
+        vals = [rng.randrange(SCALAR_FIELD_MODULUS) for _ in range(17)]
+    return scalars_to_limbs(vals)
+
+
+def setup_preprocessed_keys(circuit: type) -> Tuple[ProvingKey, VerifyingKey]:
+    """traits.rs:821-855: keys from the cache, else derived from a dummy instance of the circuit's topology."""
+    name = circuit.name()
+    with _KEY_LOCK:
+        hit = _CIRCUIT_KEY_CACHE.get(name)
+        if hit is not None:
+            return hit
+        srs = system_srs()
+        witness, statement = circuit.dummy_instance()
+        try:
+            cs = circuit.synthesize(witness, statement, circuit.get_circuit_layout())
+            circ = cs.finalize_for_arithmetization()
+        except Exception as e:  # mpc-relation CircuitError
+            raise ProverError("Circuit", e) from e
+        if circ.n + 3 > len(srs.powers_of_g):
+            raise ProverError("Plonk", f"circuit {name} needs {circ.n + 3} SRS powers, {len(srs.powers_of_g)} loaded")
+        try:
+            pk = PlonkKzgSnark.preprocess(srs.ctx, srs.powers_of_g, circ.log_n, circ.num_inputs, circ.selectors, circ.perm,
+                                          circ.k)
+        except _lib.B200Error as e:
+            raise ProverError("Plonk", e) from e
+        pair = (pk, VerifyingKey.from_proving_key(pk, srs.g2_h, srs.g2_tau_h))
+        _CIRCUIT_KEY_CACHE[name] = pair
+        return pair
+
+
+class SingleProverCircuit:
+    """traits.rs:868-1020.  Subclasses give `name()`, `synthesize`, `statement_scalars`, `dummy_instance` and, when they
+    take part in proof linking, `proof_linking_groups()` / `generate_layout`."""
+
+    # ---- what a circuit provides --------------------------------------------------------------------------
+    @classmethod
+    def name(cls) -> str:
+        raise NotImplementedError
+
+    @classmethod
+    def synthesize(cls, witness, statement, layout):
+        """`PlonkCircuit::new_turbo_plonk()` + link groups of `layout` + `create_witness` / `create_public_var` +
+        `apply_constraints` (traits.rs:976-990): returns the constraint system, not yet finalized."""
+        raise NotImplementedError
+
+    @classmethod
+    def statement_scalars(cls, statement) -> np.ndarray:
+        """`statement.to_scalars()` as (num_inputs, 4) Montgomery limbs (traits.rs:1008)."""
+        raise NotImplementedError
+
+    @classmethod
+    def dummy_instance(cls):
+        """(witness, statement) of the circuit's topology for key set-up (the reference uses zeroed scalars)."""
+        raise NotImplementedError
+
+    @classmethod
+    def proof_linking_groups(cls):
+        """[(group id, GroupLayout or None)] — none by default (traits.rs:903-905)."""
+        return []
+
+    @classmethod
+    def generate_layout(cls):
+        """Layout of the link groups (`cs.generate_layout()`, traits.rs:942); None without link groups."""
+        return None
+
+    # ---- keys -----------------------------------------------------------------------------------------------
+    @classmethod
+    def proving_key(cls) -> ProvingKey:
+        return setup_preprocessed_keys(cls)[0]
+
+    @classmethod
+    def verifying_key(cls) -> VerifyingKey:
+        return setup_preprocessed_keys(cls)[1]
+
+    @classmethod
+    def get_circuit_layout(cls):
+        """traits.rs:914-946: computed once per circuit name."""
+        name = cls.name()
+        with _KEY_LOCK:
+            if name not in _CIRCUIT_LAYOUT_CACHE:
+                _CIRCUIT_LAYOUT_CACHE[name] = cls.generate_layout()
+            return _CIRCUIT_LAYOUT_CACHE[name]
+
+    # ---- prove / verify ---------------------------------------------------------------------------------------
+    @classmethod
+    def prove(cls, witness, statement, rng=None) -> PlonkProof:
+        return cls.prove_with_link_hint(witness, statement, rng)[0]
+
+    @classmethod
+    def prove_with_link_hint(cls, witness, statement, rng=None) -> Tuple[PlonkProof, ProofLinkingHint]:
+        try:
+            cs = cls.synthesize(witness, statement, cls.get_circuit_layout())
+            circ = cs.finalize_for_arithmetization()
+        except ProverError:
+            raise
+        except Exception as e:
+            raise ProverError("Circuit", e) from e
+        pk = cls.proving_key()
+        if circ.log_n != pk.log_n or circ.num_inputs != pk.num_inputs:
+            raise ProverError("Plonk", f"{cls.name()}: instance shape differs from the preprocessed key")
+        try:
+            return PlonkKzgSnark.prove_with_link_hint(system_srs().ctx, pk, circ.wires, circ.pub_inputs, draw_blinders(rng))
+        except _lib.B200Error as e:  # WrongQuotientPolyDegree et al.
+            raise ProverError("Plonk", e) from e
+
+    @classmethod
+    def verify(cls, statement, proof: PlonkProof) -> None:
+        vk = cls.verifying_key()
+        try:
+            ok = PlonkKzgSnark.verify(vk, cls.statement_scalars(statement), proof)
+        except _lib.B200Error as e:
+            raise VerifierError(f"Plonk({e})") from e
+        if not ok:
+            raise VerifierError("Plonk(WrongProof)")
+
+
+# ---- circuits-core/src/lib.rs:112-142 ------------------------------------------------------------------------------
+def singleprover_prove(circuit: type, witness, statement, rng=None) -> PlonkProof:
+    return circuit.prove(witness, statement, rng)
+
+
+def singleprover_prove_with_hint(circuit: type, witness, statement, rng=None) -> Tuple[PlonkProof, ProofLinkingHint]:
+    return circuit.prove_with_link_hint(witness, statement, rng)
+
+
+def verify_singleprover_proof(circuit: type, statement, proof: PlonkProof) -> None:
+    circuit.verify(statement, proof)
+
+
+def singleprover_prove_and_verify(circuit: type, witness, statement, rng=None) -> None:
+    proof = circuit.prove(witness, statement, rng)
+    try:
+        circuit.verify(statement, proof)
+    except VerifierError as e:
+        raise ProverError("Verification", e) from e

@@ -6,6 +6,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "examples"))  # host_circuits (caller-side example package)
 
 
 def pytest_configure(config):
@@ -42,6 +43,28 @@ def kat():
 def srs_head():
     with open(os.path.join(ROOT, "tests", "golden", "srs_head.bin"), "rb") as f:
         return f.read()
+
+
+@pytest.fixture(scope="session")
+def srs_2_16():
+    """The reference's own SRS, first 2^16 + 3 G1 powers (tests/golden/_large/srs_2_16.bin, cut by
+    tools/cut_srs_fixture.py from /root/reference/srs/srs00; git-ignored, ships with the gpurun snapshot)."""
+    path = os.path.join(ROOT, "tests", "golden", "_large", "srs_2_16.bin")
+    if not os.path.exists(path) and os.path.exists("/root/reference/srs/srs00"):
+        import subprocess
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "cut_srs_fixture.py")])
+    if not os.path.exists(path):
+        pytest.skip("large SRS fixture absent (cut it where /root/reference exists: tools/cut_srs_fixture.py)")
+    with open(path, "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="session")
+def g2_raw():
+    """(h, tau * h): the two G2 records of the reference's SRS (tests/golden/srs_g2.bin), 16 x uint64 each."""
+    import numpy as np
+    raw = np.frombuffer(open(os.path.join(ROOT, "tests", "golden", "srs_g2.bin"), "rb").read(), dtype=np.uint64)
+    return raw[:16].copy(), raw[16:32].copy()
 
 
 @pytest.fixture(scope="session")

@@ -1,5 +1,5 @@
 """CPU: the host-side constraint system and the reference's Poseidon2 / Merkle gadgets restated on it
-(renegade_b200/circuit.py).  The native hash is checked against the oracle's Poseidon2 (itself pinned by the published
+(examples/host_circuits/circuit.py).  The native hash is checked against the oracle's Poseidon2 (itself pinned by the published
 HorizenLabs known answer with the reference's constants, tests/test_poseidon2.py); the gadget against the native hash
 and against the gate counts the reference documents; the arithmetization against the oracle prover and verifier:
 a circuit built here proves and verifies on the CPU restatement of the reference algorithm, which is what the device
@@ -9,7 +9,7 @@ import random
 
 import pytest
 
-from renegade_b200 import circuit as C
+from host_circuits import circuit as C
 from renegade_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -258,10 +258,10 @@ def test_bits_and_comparator_gadgets():
 
 
 def test_valid_balance_create_circuit(oracle, pyoracle):
-    """BASELINE.json configs[0]: VALID BALANCE CREATE restated (renegade_b200/valid_balance_create.py).  The native
+    """BASELINE.json configs[0]: VALID BALANCE CREATE restated (examples/host_circuits/valid_balance_create.py).  The native
     witness / statement satisfy the circuit; every statement field is binding; the domain is 2^13; the oracle
     prover proves it and the oracle verifier accepts."""
-    from renegade_b200 import valid_balance_create as vbc
+    from host_circuits import valid_balance_create as vbc
     py = pyoracle
     witness, statement = vbc.create_witness_statement(seed=7)
     assert statement.recovery_id == witness.initial_recovery_stream.get_ith(witness.initial_recovery_stream.index)
@@ -293,9 +293,9 @@ def test_valid_balance_create_circuit(oracle, pyoracle):
 
 def test_private_settlement_circuit(oracle, pyoracle):
     """BASELINE.json configs[3]'s statement, INTENT AND BALANCE PRIVATE SETTLEMENT, restated
-    (renegade_b200/private_settlement.py): a consistent two-party match satisfies it, each rule it encodes is binding,
+    (examples/host_circuits/private_settlement.py): a consistent two-party match satisfies it, each rule it encodes is binding,
     it has 17 public inputs and four link groups, and it is a 2^12-gate circuit; the oracle proves and verifies it."""
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import private_settlement as ps
     py = pyoracle
     parties, statement = ps.create_witness_statement(seed=11)
     build = ps.IntentAndBalancePrivateSettlementCircuit.build
@@ -347,7 +347,7 @@ def test_private_settlement_links_to_a_validity_side_circuit(oracle, pyoracle):
     """The settlement proof is linked to each party's validity proof through the values both circuits place in
     `intent_and_balance_settlement_party0` (native_proof_manager.rs:726-782).  Here the validity side is a stub circuit
     that holds the same 17 values under the same layout; the oracle links the two proofs and its verifier accepts."""
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import private_settlement as ps
     py = pyoracle
     parties, statement = ps.create_witness_statement(seed=12)
     cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
@@ -384,9 +384,9 @@ def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle)
     permutations, n = 2^13, 5 public inputs.  Then the bundle the reference proves for a private match
     (native_proof_manager.rs:526-584, 726-782): each party's two validity proofs, the settlement proof over the same
     intents / balances / shares, and the FOUR link proofs between them — proved, linked and verified on the oracle."""
-    from renegade_b200 import intent_and_balance_validity as val
-    from renegade_b200 import output_balance_validity as obv
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import intent_and_balance_validity as val
+    from host_circuits import output_balance_validity as obv
+    from host_circuits import private_settlement as ps
     py = pyoracle
     # the match first (who trades what), then each party's validity proof over ITS intent and input balance
     parties, _ = ps.create_witness_statement(seed=21)

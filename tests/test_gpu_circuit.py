@@ -1,12 +1,12 @@
 """GPU: a circuit with the reference's own gate structure — a height-10 Poseidon2 Merkle opening
-(`MERKLE_HEIGHT`, crates/constants/src/lib.rs:50; gadgets of circuits-core restated in renegade_b200/circuit.py, public
+(`MERKLE_HEIGHT`, crates/constants/src/lib.rs:50; gadgets of circuits-core restated in examples/host_circuits/circuit.py, public
 root like the VALID-* statements) — proved on the device: proof bytes identical to the oracle prover's, accepted by the
 restated verifier, wrong root rejected."""
 import random
 
 import pytest
 
-from renegade_b200 import circuit as C
+from host_circuits import circuit as C
 from renegade_b200 import synth
 from renegade_b200.backend import PlonkKzgSnark
 
@@ -43,9 +43,9 @@ def test_merkle_opening_circuit_proves_on_device(ctx, oracle, pyoracle):
 
 
 def test_valid_balance_create_proves_on_device(ctx, oracle, pyoracle):
-    """BASELINE.json configs[0]: the VALID BALANCE CREATE circuit (restated in renegade_b200/valid_balance_create.py,
+    """BASELINE.json configs[0]: the VALID BALANCE CREATE circuit (restated in examples/host_circuits/valid_balance_create.py,
     n = 2^13, 13 public inputs) — device proof bytes = oracle proof bytes, verifier accepts."""
-    from renegade_b200 import valid_balance_create as vbc
+    from host_circuits import valid_balance_create as vbc
     py = pyoracle
     witness, statement = vbc.create_witness_statement(seed=0xB200)
     cs = vbc.ValidBalanceCreate.build(witness, statement)
@@ -68,9 +68,9 @@ def test_valid_balance_create_proves_on_device(ctx, oracle, pyoracle):
 
 def test_private_settlement_proves_on_device(ctx, oracle, pyoracle):
     """BASELINE.json configs[3]'s statement at its own size: INTENT AND BALANCE PRIVATE SETTLEMENT restated
-    (renegade_b200/private_settlement.py; 17 public inputs, four link groups, n = 2^12) — device proof bytes and
+    (examples/host_circuits/private_settlement.py; 17 public inputs, four link groups, n = 2^12) — device proof bytes and
     linking hint = the oracle's, verifier accepts."""
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import private_settlement as ps
     py = pyoracle
     parties, statement = ps.create_witness_statement(seed=0xB200)
     cs = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement)
@@ -97,9 +97,9 @@ def test_private_match_bundle_on_device(ctx, oracle, pyoracle):
     config 4), with the restated circuits: both parties' INTENT AND BALANCE VALIDITY (n = 2^14) and OUTPUT BALANCE
     VALIDITY (n = 2^13) proofs, the PRIVATE SETTLEMENT proof (n = 2^12) and the four link proofs — all on the device,
     each byte-identical to the oracle's, every proof and link accepted by the restated verifiers."""
-    from renegade_b200 import intent_and_balance_validity as val
-    from renegade_b200 import output_balance_validity as obv
-    from renegade_b200 import private_settlement as ps
+    from host_circuits import intent_and_balance_validity as val
+    from host_circuits import output_balance_validity as obv
+    from host_circuits import private_settlement as ps
     from renegade_b200.backend import GroupLayout, link_proofs
     py = pyoracle
     parties, _ = ps.create_witness_statement(seed=41)

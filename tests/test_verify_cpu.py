@@ -19,12 +19,6 @@ from renegade_b200.backend import (B200LinkProof, B200Proof, GroupLayout, PlonkK
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def g2_raw():
-    raw = np.frombuffer(open(os.path.join(ROOT, "tests", "golden", "srs_g2.bin"), "rb").read(), dtype=np.uint64)
-    return raw[:16].copy(), raw[16:32].copy()  # h, tau * h
-
-
 def _g1(srs_head, i):
     return np.frombuffer(srs_head[80 + 64 * i: 80 + 64 * (i + 1)], dtype=np.uint64).copy()
 
