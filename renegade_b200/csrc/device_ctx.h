@@ -111,9 +111,9 @@ struct MsmScratch {
     DevBuf seg_offsets, seg_bucket, seg_sums, heavy, seg_order;
     DevBuf scan_state;  // ScanState header + tile status words of the single-pass scan (msm.cu)
     DevBuf tree;        // partial sums of the row / column reduction trees
+    DevBuf bit_sums;    // per window, the c - 1 bit sums T_b of the weighted tail
     HostPinned h_sums;  // window sums land here (pinned), read by the host epilogue
     cudaEvent_t done_ev = nullptr;  // recorded after the D2H of the window sums
-    bool finish_attr_set = false;
     // the MSM batch queued by msm_launch_batch and not yet collected by msm_finish_batch
     MsmPlan pending_plan;
     size_t pending_n = 0;

@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(kScanThreads) msm_scan_kernel(uint32_t* __rest
                 }
                 const uint32_t is_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2u);
                 const int stop = __ffs(is_prefix) - 1;  // nearest tile that already knows its inclusive prefix
-                uint32_t ca = (int)lane <= stop ? (uint32_t)w : 0u, cb = (int)lane <= stop ? (uint32_t)(w >> 32) & 0x3fffffffu : 0u;
+                // no prefix among the 32 inspected tiles (stop < 0): all of their aggregates count and the window moves on
+                const bool take = stop < 0 || (int)lane <= stop;
+                uint32_t ca = take ? (uint32_t)w : 0u, cb = take ? (uint32_t)(w >> 32) & 0x3fffffffu : 0u;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
                     ca += __shfl_xor_sync(0xffffffffu, ca, d);
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(kReduceThreads) msm_heavy_combine_kernel(const
 // tree), and the trees are plain sums: all of their work is data-parallel with dependent chains of at most
 // 7 additions per level (fan-in <= 8) — instead of a running sum whose chain is as long as a thread's chunk.
 // What is left is two weighted sums over 2^l / 2^(c-1-l) elements (<= 256 each up to c = 17), one block per
-// window (msm_window_finish_kernel).
+// window (msm_bitsum_kernel + msm_horner_kernel below).
 //   msm_tree_kernel, one launch per level, both trees side by side:
 //     out[a * inner + b] = sum_{j < T} in[(a * T + j) * inner + b]
 //   row tree: inner = 1 (sums of T neighbours over the flat bucket array; L is a multiple of every T, so a
@@ -450,78 +452,88 @@ __global__ void __launch_bounds__(kTreeThreads) msm_tree_kernel(TreeArgs a) {
     g1_xyzz_store(lv.out + t, acc);
 }
 
-// One block per window, 2 * kFinishHalf threads: threads [0, kFinishHalf) fold the column sums C (weights
-// lo + 1), threads [kFinishHalf, 2 kFinishHalf) the row sums R (weights hi), each with
-//     sum_i w_i X_i = sum_t A_t + K * sum_{t >= 1} Suf_t,
-// thread t owning K consecutive elements (K = 1 up to c = 17): S_t their sum, A_t their locally weighted sum
-// (running sums), Suf_t = sum_{u >= t} S_u from a Hillis–Steele suffix scan, then a tree over the threads.
-// Every step is "fetch one operand from shared memory, one addition", so the XYZZ addition is inlined once.
-constexpr int kFinishHalf = 256;
-constexpr int kFinishHalfLog = 8;
+// What is left per window are the two weighted sums.  A dependent XYZZ addition costs a warp ~3.8 us of
+// multiplier-pipe time whatever else the SM does, so this tail is arranged for the SHORTEST dependent chain, with
+// every independent piece on its own SM:
+//     L * sum_hi hi R[hi] + sum_lo (lo + 1) C[lo] = sum_b 2^b T_b,   b < c - 1,
+//     T_b = sum of the C[lo] with bit b of (lo + 1) set  +  the R[hi] with bit (b - l) of hi set,
+// msm_bitsum_kernel: one block per (window, bit) folds its <= L/2 (+ Rws/2) elements with a binary tree in
+// shared memory (log2 steps of one addition each); msm_horner_kernel: one warp per window combines the c - 1
+// bit sums pairwise — (T_b + 2 T_{b+1}), then (.. + 4 ..), (.. + 16 ..), ... — c - 2 doublings and
+// ceil(log2(c - 1)) additions on the critical path instead of a scan over hundreds of elements.
+constexpr int kBitThreads = 256;
 
-__global__ void __launch_bounds__(2 * kFinishHalf) msm_window_finish_kernel(const g1_xyzz* __restrict__ col_sums, uint32_t l_log,
-                                                                            const g1_xyzz* __restrict__ row_sums, uint32_t r_log,
-                                                                            g1_xyzz* __restrict__ window_sums) {
-    extern __shared__ uint4 finish_smem[];
-    g1_xyzz* sh = reinterpret_cast<g1_xyzz*>(finish_smem);  // 2 * kFinishHalf entries
-    const uint32_t window = blockIdx.x;
-    const uint32_t part = threadIdx.x >> kFinishHalfLog;  // 0: columns (weights i + 1), 1: rows (weights i)
-    const uint32_t t = threadIdx.x & (kFinishHalf - 1);
-    const uint32_t n_log = part ? r_log : l_log;
-    const uint32_t k_log = n_log > (uint32_t)kFinishHalfLog ? n_log - kFinishHalfLog : 0u;  // elements per thread
-    const uint32_t K = 1u << k_log;
-    const uint32_t n_threads = 1u << (n_log - k_log);  // threads of this half that own elements
-    const g1_xyzz* X = (part ? row_sums : col_sums) + ((size_t)window << n_log);
-    g1_xyzz S = g1_xyzz_inf(), A = g1_xyzz_inf();
-    if (t < n_threads) {
-        if (K == 1) {
-            S = g1_xyzz_load(X + t);
-            if (!part) A = S;
-        } else {  // large windows only (c >= 18): local running sums
-            const g1_xyzz* c = X + ((size_t)t << k_log);
+__global__ void __launch_bounds__(kBitThreads) msm_bitsum_kernel(const g1_xyzz* __restrict__ col_sums, uint32_t l_log,
+                                                                 const g1_xyzz* __restrict__ row_sums, uint32_t r_log,
+                                                                 g1_xyzz* __restrict__ bit_sums /* [window][c - 1] */) {
+    __shared__ g1_xyzz sh[kBitThreads];
+    const uint32_t b = blockIdx.x, window = blockIdx.y, n_bits = gridDim.x;
+    const g1_xyzz* C = col_sums + ((size_t)window << l_log);
+    const g1_xyzz* R = row_sums + ((size_t)window << r_log);
+    g1_xyzz acc = g1_xyzz_inf();
+    // column side: weights v = lo + 1 in [1, L]; bit b < l is set in L / 2 of them, bit l only in v = L
+    if (b < l_log) {
+        const uint32_t cnt = 1u << (l_log - 1), low_mask = (1u << b) - 1u;
 #pragma unroll 1
-            for (int i = (int)K - 1; i >= 0; --i) {
-                if (part) A = xyzz_add(A, S);  // weights i
-                S = xyzz_add(S, g1_xyzz_load(c + i));
-                if (!part) A = xyzz_add(A, S);  // weights i + 1
-            }
+        for (uint32_t j = threadIdx.x; j < cnt; j += kBitThreads) {
+            const uint32_t v = ((j >> b) << (b + 1)) | (1u << b) | (j & low_mask);  // j-th value with bit b set
+            acc = xyzz_add(acc, g1_xyzz_load(C + (v - 1u)));
+        }
+    } else if (b == l_log && threadIdx.x == 0) {
+        acc = g1_xyzz_load(C + ((1u << l_log) - 1u));
+    }
+    // row side: weights hi * L, hi < Rws: bit b >= l of the weight is bit b - l of hi
+    if (b >= l_log && r_log > 0) {
+        const uint32_t rb = b - l_log, cnt = 1u << (r_log - 1), low_mask = (1u << rb) - 1u;
+#pragma unroll 1
+        for (uint32_t j = threadIdx.x; j < cnt; j += kBitThreads) {
+            const uint32_t hi = ((j >> rb) << (rb + 1)) | (1u << rb) | (j & low_mask);
+            acc = xyzz_add(acc, g1_xyzz_load(R + hi));
         }
     }
-    // step list: log2(n_threads) scan steps, one "switch" step, kFinishHalfLog tree steps
-    g1_xyzz v = S;
-    sh[threadIdx.x] = v;
+    sh[threadIdx.x] = acc;
     __syncthreads();
-    const int scan_steps_max = kFinishHalfLog;
-    const uint32_t half_base = part << kFinishHalfLog;
 #pragma unroll 1
-    for (int step = 0; step < 2 * scan_steps_max + 1; ++step) {
+    for (uint32_t stride = kBitThreads / 2; stride > 0; stride >>= 1) {
         g1_xyzz o = g1_xyzz_inf();
-        if (step < scan_steps_max) {  // suffix scan: v_t += v_{t + d}
-            const uint32_t d = 1u << step;
-            if (d < n_threads && t + d < n_threads) o = sh[threadIdx.x + d];
-        } else if (step == scan_steps_max) {
-            // v = Suf_t.  Switch to the summands of the final tree: K * Suf_t (t >= 1) + A_t
-            if (t == 0) v = g1_xyzz_inf();
-#pragma unroll 1
-            for (uint32_t i = 0; i < k_log; ++i) v = xyzz_dbl(v);
-            o = A;
-        } else {  // tree: v_t += v_{t + stride}
-            const uint32_t stride = (uint32_t)kFinishHalf >> (step - scan_steps_max);
-            if (t < stride) o = sh[half_base + t + stride];
+        if (threadIdx.x < stride) o = sh[threadIdx.x + stride];
+        __syncthreads();
+        if (threadIdx.x < stride) {
+            acc = g1_add(acc, o);
+            sh[threadIdx.x] = acc;
         }
         __syncthreads();
-        v = g1_add(v, o);
-        sh[threadIdx.x] = v;
-        __syncthreads();
     }
-    // thread 0 holds sum (lo + 1) C[lo]; thread kFinishHalf holds sum hi R[hi], still to be scaled by L
-    if (threadIdx.x == kFinishHalf) {
+    if (threadIdx.x == 0) g1_xyzz_store(bit_sums + (size_t)window * n_bits + b, acc);
+}
+
+__device__ __forceinline__ g1_xyzz xyzz_shfl_down(const g1_xyzz& v, unsigned delta) {
+    g1_xyzz r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r.x.l[k] = __shfl_down_sync(0xffffffffu, v.x.l[k], delta);
+        r.y.l[k] = __shfl_down_sync(0xffffffffu, v.y.l[k], delta);
+        r.zz.l[k] = __shfl_down_sync(0xffffffffu, v.zz.l[k], delta);
+        r.zzz.l[k] = __shfl_down_sync(0xffffffffu, v.zzz.l[k], delta);
+    }
+    return r;
+}
+
+// window sum = sum_b 2^b T_b, n_bits <= 32: lane b starts with T_b; round s folds lane b + 2^s into lane b
+// (b a multiple of 2^(s+1)) after 2^s doublings.
+__global__ void __launch_bounds__(32) msm_horner_kernel(const g1_xyzz* __restrict__ bit_sums, uint32_t n_bits,
+                                                        g1_xyzz* __restrict__ window_sums) {
+    const uint32_t window = blockIdx.x, lane = threadIdx.x;
+    g1_xyzz v = lane < n_bits ? g1_xyzz_load(bit_sums + (size_t)window * n_bits + lane) : g1_xyzz_inf();
 #pragma unroll 1
-        for (uint32_t i = 0; i < l_log; ++i) v = xyzz_dbl(v);
-        sh[kFinishHalf] = v;
+    for (uint32_t s = 0; (1u << s) < n_bits; ++s) {
+        g1_xyzz o = xyzz_shfl_down(v, 1u << s);
+        if (lane + (1u << s) >= 32u) o = g1_xyzz_inf();
+#pragma unroll 1
+        for (uint32_t i = 0; i < (1u << s); ++i) o = xyzz_dbl(o);
+        v = g1_add(v, o);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) g1_xyzz_store(window_sums + window, xyzz_add(v, sh[kFinishHalf]));
+    if (lane == 0) g1_xyzz_store(window_sums + window, v);
 }
 
 // ---- window tables: table[j][i] = 2^(shift*j) * P_i (affine) -------------------------------------
@@ -804,11 +816,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->h_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
     if (!s->done_ev) B200_CUDA(cudaEventCreateWithFlags(&s->done_ev, cudaEventDisableTiming));
-    if (!s->finish_attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(msm_window_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(2 * kFinishHalf * sizeof(g1_xyzz))));
-        s->finish_attr_set = true;
-    }
+    if ((rc = s->bit_sums.reserve(n_windows * 32 * sizeof(g1_xyzz))) != B200_OK) return rc;
 
     uint32_t* counts = (uint32_t*)s->counts.p;
     uint32_t* offsets = (uint32_t*)s->offsets.p;
@@ -882,8 +890,11 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
                 B200_LAUNCH(msm_tree_kernel, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
         }
         // row_in: R[window][2^r_log], col_in: C[window][2^l_log]
-        B200_LAUNCH(msm_window_finish_kernel, (unsigned)n_windows, 2 * kFinishHalf, 2 * kFinishHalf * sizeof(g1_xyzz), st)(
-            col_in, (uint32_t)l_log, row_in, (uint32_t)r_log, window_sums);
+        const unsigned n_bits = (unsigned)(pl.c - 1);
+        g1_xyzz* bit_sums = (g1_xyzz*)s->bit_sums.p;
+        B200_LAUNCH(msm_bitsum_kernel, dim3(n_bits, (unsigned)n_windows), kBitThreads, 0, st)(col_in, (uint32_t)l_log, row_in,
+                                                                                               (uint32_t)r_log, bit_sums);
+        B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
     }
     B200_CUDA(cudaGetLastError());
     if (s->timing) cudaEventRecord(s->ev[3], st);

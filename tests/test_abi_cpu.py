@@ -3,6 +3,7 @@ include/b200prover.h declares, fails loudly without a GPU (no CPU fallback), and
 entry points (ptau parsing, partial-sum combination) behave like the reference's."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -161,3 +162,49 @@ def test_pool_boundary_without_a_device():
         h = C.c_void_p()
         assert lib.b200_pool_create(0, 2, C.byref(h)) == -6 and not h.value
         assert b"no CPU fallback" in lib.b200_last_error()
+
+
+def test_rust_shim_ffi_matches_the_header():
+    """shim/gpu-prover/src/ffi.rs (what the Rust host links against) declares exactly the header's entry points with
+    ABI-equivalent signatures.  The Rust file is parsed here independently of the generator and every type is mapped back
+    to its C spelling."""
+    from renegade_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_ffi as gen
+    opaque, structs, funcs, macros = gen.parse_header()
+    src = open(os.path.join(ROOT, "shim", "gpu-prover", "src", "ffi.rs")).read()
+    assert src == gen.generate(), "ffi.rs is stale: run python tools/gen_rust_ffi.py"
+    block = src[src.index('extern "C" {'):]
+    rust = {m.group(1): (m.group(2), m.group(3)) for m in
+            re.finditer(r"pub fn (b200_\w+)\((.*?)\)(?: -> ([^;]+))?;", block)}
+    assert sorted(rust) == sorted(f[0] for f in funcs) == sorted(_lib.EXPORTS)
+    back = {"c_int": "int", "c_uint": "unsigned", "usize": "size_t", "u64": "uint64_t", "u8": "uint8_t", "f32": "float",
+            "f64": "double", "c_char": "char", "c_void": "void"}
+
+    def to_c(t):
+        t = t.strip()
+        ptrs = []
+        while t.startswith("*"):
+            kind, t = t.split(" ", 1)
+            ptrs.append(kind)
+        base = back.get(t, t)
+        # innermost pointer's constness belongs to the pointee
+        const = ptrs and ptrs[-1] == "*const"
+        return ("const " if const else "") + base + "*" * len(ptrs)
+
+    def canon(c):  # header spelling -> comparable form (arrays decay, outer `* const *` dropped)
+        c = c.replace("unsigned int", "unsigned").replace(" * const *", "**").replace("* const *", "**")
+        return c.replace(" *", "*").replace("* ", "*").strip()
+
+    for name, ret, args in funcs:
+        rargs, rret = rust[name]
+        got = [to_c(a.split(":", 1)[1]) for a in rargs.split(", ") if a]
+        want = [canon(t) for _, t in args]
+        assert got == want, (name, got, want)
+        assert (to_c(rret) if rret else "void") == canon(ret), (name, rret, ret)
+    for k, v in macros.items():
+        assert re.search(rf"pub const {k}: c_int = {v};", src)
+    for sname, fields in structs.items():
+        body = re.search(rf"pub struct {sname} \{{(.*?)\}}", src, flags=re.S).group(1)
+        assert [f.strip() for f in body.strip().split(",\n") if f.strip()] == [f"pub {f}: {t}" for f, t in fields] or \
+               [x.strip().rstrip(",") for x in body.strip().splitlines()] == [f"pub {f}: {t}" for f, t in fields]
