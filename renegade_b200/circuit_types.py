@@ -57,6 +57,7 @@ class SystemSrs:
     powers_of_g: Bases
     g2_h: np.ndarray
     g2_tau_h: np.ndarray
+    pool: Any = None   # optional ProverPool: proofs then run `workers` at a time, one request thread per ticket
 
 
 _SYSTEM_SRS: Optional[SystemSrs] = None
@@ -65,14 +66,15 @@ _CIRCUIT_KEY_CACHE: Dict[str, Tuple[ProvingKey, VerifyingKey]] = {}
 _CIRCUIT_LAYOUT_CACHE: Dict[str, Any] = {}
 
 
-def set_system_srs(ctx: Context, powers_of_g: Bases, g2_h: np.ndarray, g2_tau_h: np.ndarray) -> SystemSrs:
+def set_system_srs(ctx: Context, powers_of_g: Bases, g2_h: np.ndarray, g2_tau_h: np.ndarray, pool=None) -> SystemSrs:
     """Install the process-wide SRS (the reference parses srs/srs00 once, lazily).  Clears the key cache: keys
-    belong to the SRS they were derived from."""
+    belong to the SRS they were derived from.  `pool` (a `ProverPool` on the same device, whose worker-0 context is
+    `ctx`): proofs are queued there — the shape of `NativeProofManager`'s rayon pool — instead of serialising on `ctx`."""
     global _SYSTEM_SRS
     with _KEY_LOCK:
         clear_key_cache()
         _SYSTEM_SRS = SystemSrs(ctx, powers_of_g, np.ascontiguousarray(g2_h, dtype=np.uint64).reshape(16),
-                                np.ascontiguousarray(g2_tau_h, dtype=np.uint64).reshape(16))
+                                np.ascontiguousarray(g2_tau_h, dtype=np.uint64).reshape(16), pool)
         return _SYSTEM_SRS
 
 
@@ -200,8 +202,16 @@ class SingleProverCircuit:
         pk = cls.proving_key()
         if circ.log_n != pk.log_n or circ.num_inputs != pk.num_inputs:
             raise ProverError("Plonk", f"{cls.name()}: instance shape differs from the preprocessed key")
+        srs = system_srs()
         try:
-            return PlonkKzgSnark.prove_with_link_hint(system_srs().ctx, pk, circ.wires, circ.pub_inputs, draw_blinders(rng))
+            if srs.pool is None:
+                return PlonkKzgSnark.prove_with_link_hint(srs.ctx, pk, circ.wires, circ.pub_inputs, draw_blinders(rng))
+            wires = np.ascontiguousarray(circ.wires, dtype=np.uint64)
+            tk = srs.pool.submit_prove(pk, wires.ctypes.data, circ.pub_inputs, draw_blinders(rng), with_link_poly=True,
+                                       keep=wires)
+            proof, link = srs.pool.wait(tk)
+            return proof, LinkingHint(linking_wire_poly=link,
+                                      linking_wire_comm=np.array(proof.wires_poly_comms[0], dtype=np.uint64))
         except _lib.B200Error as e:  # WrongQuotientPolyDegree et al.
             raise ProverError("Plonk", e) from e
 
