@@ -120,7 +120,7 @@ def make_circuit(kind, log_n, seed):
     return cs.finalize_for_arithmetization(min_log_n=log_n)
 
 
-def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps):
+def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps, srs_host=None, cpu_baseline=False):
     """The reference's own statements at their own sizes (restated in examples/host_circuits/valid_balance_create.py and
     private_settlement.py: n = 2^13 and 2^12, not the 2^16 BASELINE.json quotes): one proof alone, and proofs/s end
     to end from pinned host memory through the pool.  Reported beside the headline, never instead of it."""
@@ -158,14 +158,30 @@ def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps):
             t = time.perf_counter()
             run(steps)
             rate = steps / (time.perf_counter() - t)
+        cpu = None
+        if cpu_baseline:  # the oracle prover on the same tables, SRS and blinders — the only use of oracle/ in this leg
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle_c
+            oracle_c.build()
+            oracle_c.autotune_threads()
+            srs_np = srs_host[:circ.n + 3]
+            opk = oracle_c.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs_np)
+            t = time.perf_counter()
+            rc, oproof, _, _ = oracle_c.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs, bl[0], srs_np)
+            cdt = time.perf_counter() - t
+            gproof = prove_raw(ctx, pk, h_w.data_ptr(), circ.pub_inputs, bl[0])
+            cpu = {"value": 1.0 / cdt, "unit": "proofs/s", "cores": oracle_c.num_threads(), "kind": "port",
+                   "sample": "1 proof of the same circuit, SRS and blinders (%.3f s)" % cdt,
+                   "bit_exact_vs_gpu": bool(rc == 0 and bytes(oproof) == bytes(gproof))}
         res[name] = {"log_n": circ.log_n, "gates": circ.n_gates, "num_inputs": circ.num_inputs,
-                     "ms_one_proof_in_flight": single_ms, "proofs_per_s_e2e": rate, "in_flight": conc, "steps": steps}
+                     "ms_one_proof_in_flight": single_ms, "proofs_per_s_e2e": rate, "in_flight": conc, "steps": steps,
+                     "cpu_baseline": cpu}
         pk.free()
         bases.free()
     return res
 
 
-def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
+def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles, srs_host=None, cpu_baseline=False):
     """What the reference proves for one private match (native_proof_manager.rs:526-584, 726-782), with the restated
     circuits: both parties' INTENT AND BALANCE VALIDITY (n = 2^14) and OUTPUT BALANCE VALIDITY (n = 2^13) proofs, the
     PRIVATE SETTLEMENT proof (n = 2^12) and the four link proofs — `bundles` of them through the pool, end to end from
@@ -202,24 +218,49 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
                  for p, g in enumerate(ps.OUTPUT_LINKS)]
 
     def run(count):
-        tickets = [[pool.submit_prove(pks[j], wires[j].data_ptr(), circs[j].pub_inputs, bl[(5 * b + j) % 8],
-                                      with_link_poly=True) for j in range(5)] for b in range(count)]
-        links = []
-        for b in range(count):
-            res = [pool.wait(tk) for tk in tickets[b]]
-            hints = [LinkingHint(linking_wire_poly=lp, linking_wire_comm=np.array(pr.wires_poly_comms[0], dtype=np.uint64))
-                     for pr, lp in res]
-            links += [pool.submit_link(bases, hints[j], hints[0], lay) for j, lay in link_plan]
-        for tk in links:
-            pool.wait(tk)
+        # one ticket per bundle: the five proofs, then the four link proofs forked inside the pool (b200_pool_submit_bundle)
+        tickets = [pool.submit_bundle(bases, [(pks[j], wires[j].data_ptr(), circs[j].pub_inputs, bl[(5 * b + j) % 8]) for j in range(5)],
+                                      [(j, 0, lay) for j, lay in link_plan]) for b in range(count)]
+        return [pool.wait(tk) for tk in tickets]
     run(2)
     t = time.perf_counter()
-    run(bundles)
+    res = run(bundles)
     dt = time.perf_counter() - t
+    # CPU baseline: the oracle prover (the restated reference algorithm) on the same five tables and the same four
+    # links, one bundle, all host cores — the only place this leg touches oracle/
+    cpu = None
+    if cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_c
+        oracle_c.build()
+        oracle_c.autotune_threads()
+        srs_np = srs_host
+        opks = [oracle_c.plonk_preprocess(c.log_n, c.selectors, c.perm, c.k, srs_np[:c.n + 3]) for c in circs]
+        t0 = time.perf_counter()
+        oproofs, olinks = [], []
+        for j, c in enumerate(circs):
+            rc, op, _, olink = oracle_c.plonk_prove(c.log_n, c.num_inputs, c.k, opks[j], c.wires, c.pub_inputs, bl[j % 8],
+                                                    srs_np[:c.n + 3], True)
+            assert rc == 0
+            oproofs.append((op, olink))
+        for j, lay in link_plan:
+            rc, olp, _ = oracle_c.plonk_link(oproofs[j][1], oproofs[0][1], oproofs[j][0].to_array()[:8].copy(),
+                                             oproofs[0][0].to_array()[:8].copy(), lay.alignment, lay.offset, lay.size, srs_np)
+            assert rc == 0
+            olinks.append(olp)
+        cdt = time.perf_counter() - t0
+        # bundle 0 of the timed run used blinders bl[j % 8]: its proofs and link proofs must be the oracle's, byte for byte
+        g_proofs, _, g_links = res[0] if bundles >= 1 else (None, None, None)
+        exact = all(bytes(g_proofs[j]) == bytes(oproofs[j][0]) for j in range(5)) and \
+            all(bytes(g_links[i]) == bytes(olinks[i]) for i in range(4))
+        cpu = {"value": 1.0 / cdt, "unit": "bundles/s", "cores": oracle_c.num_threads(), "kind": "port",
+               "sample": "1 whole bundle (5 proofs + 4 link proofs) on the same tables, SRS and blinders (%.2f s)" % cdt,
+               "bit_exact_vs_gpu": bool(exact)}
     for pk in pks:
         pk.free()
     bases.free()
     return {"bundles_per_s_e2e": bundles / dt, "ms_per_bundle": dt / bundles * 1e3, "bundles": bundles, "in_flight": conc,
+            "cpu_baseline": cpu,
             "proofs_per_bundle": {"intent_and_balance_validity (n = 2^14)": 2, "output_balance_validity (n = 2^13)": 2,
                                   "private_settlement (n = 2^12)": 1, "link proofs": 4}}
 
@@ -227,6 +268,7 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles):
 def run_extras(args):
     """`--extras-only`: the restated statements at their own sizes and the private-match bundle, on device 0, as one JSON
     object on stdout (bench.py's main run calls this in a subprocess)."""
+    import numpy as np
     import torch
     import renegade_b200 as rb
     from renegade_b200.backend import ProverPool
@@ -239,9 +281,10 @@ def run_extras(args):
     torch.cuda.synchronize()
     ctx.known_dlog_bases_device(SEED_SRS, n_srs, d_srs.data_ptr())
     extras = {}
+    srs_host = d_srs.cpu().numpy().view(np.uint64)
     for key, leg, count in (("real_statements", real_statement_leg, 300), ("private_match_bundle", private_match_bundle_leg, 40)):
         try:
-            extras[key] = leg(pool, ctx, d_srs.data_ptr(), conc, count)
+            extras[key] = leg(pool, ctx, d_srs.data_ptr(), conc, count, srs_host, not args.no_cpu_baseline)
         except Exception as e:
             extras[key] = {"error": repr(e)[:300]}
     print(json.dumps(extras), flush=True)
@@ -655,8 +698,12 @@ def main():
     if world == 1 and not args.no_real_statements:
         # extras, in a process of their own: nothing in them — an exception, a crash, a hang — may cost the headline line
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-only", "--concurrency", str(conc)],
-                               capture_output=True, text=True, timeout=300)
+            # the real statements are 8-16x smaller than the headline circuit: latency-bound per proof, so more of them are
+            # kept in flight (B200_BENCH_EXTRAS_CONCURRENCY)
+            xconc = int(os.environ.get("B200_BENCH_EXTRAS_CONCURRENCY", str(max(conc, 16))))
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extras-only", "--concurrency", str(xconc)] +
+                               (["--no-cpu-baseline"] if args.no_cpu_baseline else []),
+                               capture_output=True, text=True, timeout=420)
             extras = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:
             extras = {"real_statements": {"error": repr(e)[:300]}}

@@ -262,6 +262,35 @@ int b200_pool_submit_link(b200_pool* pool, const b200_bases* srs, const uint64_t
                           const uint64_t* a2, size_t len2, const uint64_t* comm1, const uint64_t* comm2,
                           unsigned alignment, size_t offset, size_t size, b200_link_proof* proof,
                           uint64_t* ticket);
+/* One proof of a bundle, arguments as for b200_pool_submit_prove.  `link_poly` ((2^log_n + 2) x 4 limbs) is required
+ * for every proof a link names. */
+typedef struct {
+    const b200_pk* pk;
+    const uint64_t* wires;
+    const uint64_t* pub_inputs;
+    size_t num_inputs;
+    const uint64_t* blinders;
+    b200_proof* proof;
+    uint64_t* link_poly;
+} b200_bundle_proof;
+/* One link proof of a bundle: `b200_plonk_link` between the hints of proofs[a] and proofs[b] (in that order) on the
+ * group (alignment, offset, size). */
+typedef struct {
+    unsigned a;
+    unsigned b;
+    unsigned alignment;
+    size_t offset;
+    size_t size;
+    b200_link_proof* proof;
+} b200_bundle_link;
+/* Queue a whole proof bundle under ONE ticket: the `n_proofs` proofs run through the pool; when all of them are in,
+ * the `n_links` link proofs are forked onto the pool; the ticket completes after the last link proof (or with the
+ * first failure).  Replaces the settlement arms of `NativeProofManager::handle_proof_job`
+ * (native_proof_manager.rs:526-584) with `compute_private_settlement_link_proofs` (:726-782): e.g. a private match =
+ * 5 proofs + 4 links.  The arrays are copied at submit; the buffers they point to stay owned by the caller until
+ * the ticket has been waited for. */
+int b200_pool_submit_bundle(b200_pool* pool, const b200_bases* srs, const b200_bundle_proof* proofs, size_t n_proofs,
+                            const b200_bundle_link* links, size_t n_links, uint64_t* ticket);
 /* Blocks until the job is done and returns ITS status (B200_OK or the error the prove/link call
  * returned; b200_last_error() of the waiting thread then holds the job's message).  A ticket can
  * be waited for once. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_num_inputs", "b200_pk_log_n", "b200_pk_free", "b200_plonk_prove", "b200_plonk_link", "b200_plonk_verify", "b200_plonk_verify_link", "b200_pairing_check", "b200_plonk_last_timings", "b200_keccak256",
     "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_workers", "b200_pool_ctx", "b200_pool_submit_prove",
-    "b200_pool_submit_link", "b200_pool_wait", "b200_pool_wait_all", "b200_pool_stats",
+    "b200_pool_submit_link", "b200_pool_submit_bundle", "b200_pool_wait", "b200_pool_wait_all", "b200_pool_stats",
     "b200_shard_range", "b200_multi_init", "b200_nccl_unique_id", "b200_multi_init_rank", "b200_multi_shutdown",
     "b200_nccl_version", "b200_multi_world", "b200_multi_local_devices", "b200_multi_ctx", "b200_multi_rank",
     "b200_multi_bases_load", "b200_multi_bases_known_dlog", "b200_multi_bases_free", "b200_multi_bases_len",
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     lib.b200_pool_ctx.restype = vp
     lib.b200_pool_submit_prove.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
     lib.b200_pool_submit_link.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, u32, sz, sz, vp, C.POINTER(u64)]
+    lib.b200_pool_submit_bundle.argtypes = [vp, vp, vp, sz, vp, sz, C.POINTER(u64)]
     lib.b200_pool_wait.argtypes = [vp, u64]
     lib.b200_pool_wait_all.argtypes = [vp]
     lib.b200_pool_stats.argtypes = [vp, C.POINTER(u64 * 4)]

@@ -494,6 +494,18 @@ ProofLinkingHint = LinkingHint         # `pub type ProofLinkingHint = LinkingHin
 ProverError = _lib.B200Error           # circuit-types/src/errors.rs:33-58: a failing prove surfaces as an error value
 
 
+class BundleProof(C.Structure):
+    """b200_bundle_proof"""
+    _fields_ = [("pk", C.c_void_p), ("wires", C.c_void_p), ("pub_inputs", C.c_void_p), ("num_inputs", C.c_size_t),
+                ("blinders", C.c_void_p), ("proof", C.c_void_p), ("link_poly", C.c_void_p)]
+
+
+class BundleLink(C.Structure):
+    """b200_bundle_link"""
+    _fields_ = [("a", C.c_uint), ("b", C.c_uint), ("alignment", C.c_uint), ("offset", C.c_size_t), ("size", C.c_size_t),
+                ("proof", C.c_void_p)]
+
+
 class ProverPool:
     """b200_pool: the device-side counterpart of the reference's `NativeProofManager` thread pool
     (crates/workers/proof-manager/src/implementations/native_proof_manager.rs:138-201, `spawn_fifo`
@@ -556,6 +568,39 @@ class ProverPool:
                                                    _ptr(c1), _ptr(c2), layout.alignment, layout.offset, layout.size,
                                                    C.byref(proof), C.byref(ticket)))
         self._keep[ticket.value] = (proof, None, (a1, a2, c1, c2), srs)
+        return ticket.value
+
+    def submit_bundle(self, srs: "Bases", proofs, links) -> int:
+        """One ticket for a whole proof bundle (`b200_pool_submit_bundle`): `proofs` = [(pk, wires_ptr, pub_inputs,
+        blinders)], `links` = [(a, b, GroupLayout)] — link proof between the hints of proofs a and b, forked inside the
+        pool once every proof is in (native_proof_manager.rs:526-584, 726-782).  `wait(ticket)` returns
+        ([B200Proof], [link polys], [B200LinkProof])."""
+        n_p, n_l = len(proofs), len(links)
+        arr_p = (BundleProof * n_p)()
+        arr_l = (BundleLink * max(n_l, 1))()
+        keep, out_proofs, out_polys, out_links = [], [], [], []
+        for i, (pk, wires_ptr, pub_inputs, blinders) in enumerate(proofs):
+            pi = np.ascontiguousarray(pub_inputs, dtype=np.uint64)
+            bl = np.ascontiguousarray(blinders, dtype=np.uint64)
+            if pi.size != 4 * pk.num_inputs or bl.size != 4 * 17:
+                raise ProverError(-1, "submit_bundle: public inputs / blinders do not match the key")
+            proof = B200Proof()
+            poly = np.zeros((pk.domain_size + 2, 4), dtype=np.uint64)
+            arr_p[i].pk, arr_p[i].wires = pk._h, C.c_void_p(wires_ptr)
+            arr_p[i].pub_inputs = pi.ctypes.data_as(C.c_void_p) if pi.size else None
+            arr_p[i].num_inputs, arr_p[i].blinders = pi.size // 4, bl.ctypes.data_as(C.c_void_p)
+            arr_p[i].proof, arr_p[i].link_poly = C.cast(C.pointer(proof), C.c_void_p), poly.ctypes.data_as(C.c_void_p)
+            keep += [pi, bl, pk]
+            out_proofs.append(proof)
+            out_polys.append(poly)
+        for i, (a, b, lay) in enumerate(links):
+            lp = B200LinkProof()
+            arr_l[i].a, arr_l[i].b, arr_l[i].alignment, arr_l[i].offset, arr_l[i].size = a, b, lay.alignment, lay.offset, lay.size
+            arr_l[i].proof = C.cast(C.pointer(lp), C.c_void_p)
+            out_links.append(lp)
+        ticket = C.c_uint64()
+        _lib.check(self._lib.b200_pool_submit_bundle(self._h, srs._h, arr_p, n_p, arr_l, n_l, C.byref(ticket)))
+        self._keep[ticket.value] = ((out_proofs, out_polys, out_links), None, keep, srs)
         return ticket.value
 
     def wait(self, ticket: int):

@@ -21,6 +21,8 @@
 
 namespace {
 
+struct Bundle;
+
 struct Job {
     enum Kind { kProve, kLink } kind = kProve;
     uint64_t ticket = 0;
@@ -38,11 +40,25 @@ struct Job {
     unsigned alignment = 0;
     size_t offset = 0, size = 0;
     b200_link_proof* link_proof = nullptr;
+    std::shared_ptr<Bundle> bundle;  // set for the sub-jobs of a bundle (they carry no ticket of their own)
 };
 
 struct Done {
     int status = B200_OK;
     std::string message;
+};
+
+// A bundle: proofs first, then — once all of them are in — the link proofs between their wire-0 polynomials; one
+// ticket for the whole thing.  The device-side shape of `NativeProofManager::handle_proof_job` for the settlement jobs
+// (native_proof_manager.rs:526-584: prove, then `compute_*_link_proofs`, :726-782 forking the link proofs).
+struct Bundle {
+    uint64_t ticket = 0;
+    const b200_bases* srs = nullptr;
+    std::vector<b200_bundle_proof> proofs;
+    std::vector<b200_bundle_link> links;
+    size_t pending = 0;     // sub-jobs of the current phase still queued or running
+    bool linking = false;   // false: proof phase, true: link phase
+    Done result;            // first failure wins
 };
 
 }  // namespace
@@ -58,6 +74,26 @@ struct b200_pool {
     uint64_t next_ticket = 1;
     uint64_t n_submitted = 0, n_completed = 0, n_failed = 0, n_running = 0;
     bool stopping = false;
+
+    static std::unique_ptr<Job> make_link_job(const std::shared_ptr<Bundle>& b, const b200_bundle_link& l) {
+        const b200_bundle_proof& pa = b->proofs[l.a];
+        const b200_bundle_proof& pb = b->proofs[l.b];
+        std::unique_ptr<Job> j(new Job());
+        j->kind = Job::kLink;
+        j->bundle = b;
+        j->srs = b->srs;
+        j->a1 = pa.link_poly;
+        j->len1 = ((size_t)1 << b200_pk_log_n(pa.pk)) + 2;
+        j->a2 = pb.link_poly;
+        j->len2 = ((size_t)1 << b200_pk_log_n(pb.pk)) + 2;
+        std::memcpy(j->comm1, pa.proof->wires_poly_comms[0], sizeof j->comm1);  // `linking_wire_comm` of each hint
+        std::memcpy(j->comm2, pb.proof->wires_poly_comms[0], sizeof j->comm2);
+        j->alignment = l.alignment;
+        j->offset = l.offset;
+        j->size = l.size;
+        j->link_proof = l.proof;
+        return j;
+    }
 
     void run(unsigned w) {
         for (;;) {
@@ -81,14 +117,33 @@ struct b200_pool {
                                            job->link_proof, nullptr);
             }
             if (d.status != B200_OK) d.message = b200_last_error();  // this worker's thread-local message
+            bool new_jobs = false;
             {
                 std::lock_guard<std::mutex> lk(mu);
                 --n_running;
                 ++n_completed;
                 if (d.status != B200_OK) ++n_failed;
-                inflight.erase(job->ticket);
-                done.emplace(job->ticket, std::move(d));
+                if (!job->bundle) {
+                    inflight.erase(job->ticket);
+                    done.emplace(job->ticket, std::move(d));
+                } else {
+                    Bundle& b = *job->bundle;
+                    if (d.status != B200_OK && b.result.status == B200_OK) b.result = d;
+                    if (--b.pending == 0) {
+                        if (!b.linking && b.result.status == B200_OK && !b.links.empty()) {
+                            b.linking = true;  // every proof is in: fork the link proofs
+                            for (const b200_bundle_link& l : b.links) queue.push_back(make_link_job(job->bundle, l));
+                            b.pending = b.links.size();
+                            n_submitted += b.links.size();
+                            new_jobs = true;
+                        } else {
+                            inflight.erase(b.ticket);
+                            done.emplace(b.ticket, b.result);
+                        }
+                    }
+                }
             }
+            if (new_jobs) cv_job.notify_all();
             cv_done.notify_all();
         }
     }
@@ -202,6 +257,64 @@ int b200_pool_submit_link(b200_pool* pool, const b200_bases* srs, const uint64_t
     j->size = size;
     j->link_proof = proof;
     return pool_push(pool, std::move(j), ticket);
+    B200_CATCH
+}
+
+int b200_pool_submit_bundle(b200_pool* pool, const b200_bases* srs, const b200_bundle_proof* proofs, size_t n_proofs,
+                            const b200_bundle_link* links, size_t n_links, uint64_t* ticket) {
+    B200_TRY
+    if (!pool || !proofs || n_proofs == 0 || (n_links && (!links || !srs)) || !ticket) {
+        b200::set_error("pool_submit_bundle: null argument");
+        return B200_ERR_INVALID;
+    }
+    for (size_t i = 0; i < n_proofs; ++i) {
+        const b200_bundle_proof& p = proofs[i];
+        if (!p.pk || !p.wires || !p.blinders || !p.proof || (p.num_inputs && !p.pub_inputs) ||
+            p.num_inputs != b200_pk_num_inputs(p.pk)) {
+            b200::set_error("pool_submit_bundle: bad proof entry (null pointer or num_inputs does not match the key)");
+            return B200_ERR_INVALID;
+        }
+    }
+    for (size_t i = 0; i < n_links; ++i) {
+        const b200_bundle_link& l = links[i];
+        if (l.a >= n_proofs || l.b >= n_proofs || !l.proof || !proofs[l.a].link_poly || !proofs[l.b].link_poly) {
+            b200::set_error("pool_submit_bundle: a link names a proof that is missing or has no link_poly buffer");
+            return B200_ERR_INVALID;
+        }
+    }
+    std::shared_ptr<Bundle> b(new Bundle());
+    b->srs = srs;
+    b->proofs.assign(proofs, proofs + n_proofs);
+    b->links.assign(links, links + n_links);
+    b->pending = n_proofs;
+    std::vector<std::unique_ptr<Job>> jobs;
+    for (size_t i = 0; i < n_proofs; ++i) {
+        const b200_bundle_proof& p = proofs[i];
+        std::unique_ptr<Job> j(new Job());
+        j->kind = Job::kProve;
+        j->bundle = b;
+        j->pk = p.pk;
+        j->wires = p.wires;
+        j->pub_inputs.assign(p.pub_inputs, p.pub_inputs + 4 * p.num_inputs);
+        j->blinders.assign(p.blinders, p.blinders + 4 * 17);
+        j->proof = p.proof;
+        j->link_poly = p.link_poly;
+        jobs.push_back(std::move(j));
+    }
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        if (pool->stopping) {
+            b200::set_error("pool: shutting down");
+            return B200_ERR_INVALID;
+        }
+        b->ticket = pool->next_ticket++;
+        *ticket = b->ticket;
+        pool->n_submitted += n_proofs;
+        pool->inflight.insert(b->ticket);
+        for (auto& j : jobs) pool->queue.push_back(std::move(j));
+    }
+    pool->cv_job.notify_all();
+    return B200_OK;
     B200_CATCH
 }
 

@@ -164,3 +164,54 @@ def test_pool_submit_from_many_threads_and_link_jobs(ctx, oracle, pyoracle):
             pk.free()
     finally:
         pool.close()
+
+
+def test_pool_bundle_one_ticket_for_proofs_and_links(ctx, oracle, pyoracle):
+    """`b200_pool_submit_bundle`: three proofs and two link proofs (0 <-> 1 on one group, 2 <-> 1 on the same group) under
+    ONE ticket, the link proofs forked inside the pool once the proofs are in (the settlement arms of
+    `handle_proof_job`, native_proof_manager.rs:526-584, 726-782).  Everything equals what the single calls produce; a
+    bundle with an unsatisfied proof reports that failure and forks no links; a bad submission is refused up front."""
+    from renegade_b200._lib import B200Error
+    from renegade_b200.backend import LinkingHint
+    layout = GroupLayout(alignment=7, offset=20, size=9)
+    py = pyoracle
+    vals = [(i * 0xD1B54A32D192ED03 + 99) % py.R for i in range(layout.size)]
+    sizes = (10, 11, 10)
+    made = [make(ctx, oracle, pyoracle, lg, seed=51 + i, link=(layout.alignment, layout.offset, vals)) for i, lg in enumerate(sizes)]
+    circs = [m[0] for m in made]
+    tau, srs = made[1][1], made[1][2]          # the largest SRS serves all three
+    pool = ProverPool(0, workers=3)
+    try:
+        c0 = pool.context(0)
+        bases = c0.load_bases(srs)
+        pks = [PlonkKzgSnark.preprocess(c0, bases, lg, c.num_inputs, c.selectors, c.perm, c.k) for lg, c in zip(sizes, circs)]
+        wires = [np.ascontiguousarray(c.wires, dtype=np.uint64) for c in circs]
+        bl = [synth.splitmix_blinders(60 + i) for i in range(3)]
+        t = pool.submit_bundle(bases, [(pks[i], wires[i].ctypes.data, circs[i].pub_inputs, bl[i]) for i in range(3)],
+                               [(0, 1, layout), (2, 1, layout)])
+        proofs, polys, links = pool.wait(t)
+        for i in range(3):
+            single, hint = PlonkKzgSnark.prove_with_link_hint(c0, pks[i], circs[i].wires, circs[i].pub_inputs, bl[i])
+            assert bytes(proofs[i]) == bytes(single) and (polys[i] == hint.linking_wire_poly).all()
+        hints = [LinkingHint(linking_wire_poly=polys[i], linking_wire_comm=np.array(proofs[i].wires_poly_comms[0], dtype=np.uint64))
+                 for i in range(3)]
+        for (a, b), lp in zip(((0, 1), (2, 1)), links):
+            direct, _ = link_proofs(ctx, bases, hints[a], hints[b], layout)
+            assert bytes(lp) == bytes(direct)
+            assert oracle.plonk_link_verify_known_tau(hints[a].linking_wire_comm, hints[b].linking_wire_comm, layout.alignment,
+                                                      layout.offset, layout.size, oracle.LinkProof.from_buffer_copy(bytes(lp)), tau)
+        # an unsatisfied witness in the bundle: the ticket reports it, the pool goes on
+        bad = wires[2].copy()
+        bad[0, 5, 0] ^= np.uint64(1)
+        t = pool.submit_bundle(bases, [(pks[0], wires[0].ctypes.data, circs[0].pub_inputs, bl[0]),
+                                       (pks[2], bad.ctypes.data, circs[2].pub_inputs, bl[2])], [(0, 1, layout)])
+        with pytest.raises(B200Error) as err:
+            pool.wait(t)
+        assert err.value.code == -7
+        with pytest.raises(B200Error):      # a link naming a proof that is not in the bundle
+            pool.submit_bundle(bases, [(pks[0], wires[0].ctypes.data, circs[0].pub_inputs, bl[0])], [(0, 3, layout)])
+        assert pool.stats()["queued"] == 0
+        for pk in pks:
+            pk.free()
+    finally:
+        pool.close()
