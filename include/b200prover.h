@@ -361,6 +361,19 @@ int b200_poseidon2_hash_batch(b200_ctx* ctx, const uint64_t* inputs, size_t batc
  * poseidon2.rs:90-110). */
 int b200_poseidon2_permute_batch(b200_ctx* ctx, uint64_t* states, size_t batch);
 
+/* Roots of `batch` Merkle openings of `height` levels: leaf_hashes[i] is hashed up with its sister nodes
+ * (sisters[i * height + lvl], bottom-up); is_right[i * height + lvl] != 0 means the running hash is the RIGHT child at
+ * that level, i.e. the node is H(sister, cur), else H(cur, sister) — two-to-one Poseidon2 sponge hashes.  The native
+ * side of `PoseidonMerkleHashGadget::compute_root` (circuits-core/src/zk_gadgets/primitives/merkle.rs:13-126) /
+ * `MerkleOpening::compute_root`, for the batches witness generation walks (state_wrapper.rs:125-247). */
+int b200_poseidon2_merkle_root_batch(b200_ctx* ctx, const uint64_t* leaf_hashes, const uint64_t* sisters,
+                                     const uint8_t* is_right, size_t batch, unsigned height, uint64_t* roots);
+/* `count` consecutive outputs of `batch` Poseidon CSPRNG streams (darkpool-types/src/csprng.rs:30-75: value i of a
+ * stream is H(seed, i)): out[s * count + j] = H(seeds[s], first_index[s] + j).  The share / recovery streams behind
+ * every `StateWrapper` (stream-cipher pads, recovery identifiers). */
+int b200_poseidon2_csprng_batch(b200_ctx* ctx, const uint64_t* seeds, const uint64_t* first_index, size_t batch,
+                                size_t count, uint64_t* out);
+
 /* Keccak-256 of the transcript (host; exported so the hash can be pinned by known answers). */
 void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]);
 

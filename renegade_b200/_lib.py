@@ -24,7 +24,7 @@ EXPORTS = [
     "b200_splitmix_fr_device", "b200_known_dlog_bases_device",
     "b200_selftest_field", "b200_field_op",
     "b200_plonk_preprocess", "b200_pk_verifying_key", "b200_pk_num_inputs", "b200_pk_log_n", "b200_pk_free", "b200_plonk_prove", "b200_plonk_link", "b200_plonk_verify", "b200_plonk_verify_link", "b200_pairing_check", "b200_plonk_last_timings", "b200_keccak256",
-    "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch",
+    "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch", "b200_poseidon2_merkle_root_batch", "b200_poseidon2_csprng_batch",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_workers", "b200_pool_ctx", "b200_pool_submit_prove",
     "b200_pool_submit_link", "b200_pool_submit_bundle", "b200_pool_wait", "b200_pool_wait_all", "b200_pool_stats",
     "b200_shard_range", "b200_multi_init", "b200_nccl_unique_id", "b200_multi_init_rank", "b200_multi_shutdown",
@@ -100,6 +100,8 @@ def load() -> C.CDLL:
     lib.b200_plonk_last_timings.argtypes = [vp, C.POINTER(C.c_float * 8)]
     lib.b200_poseidon2_hash_batch.argtypes = [vp, vp, sz, sz, vp]
     lib.b200_poseidon2_permute_batch.argtypes = [vp, vp, sz]
+    lib.b200_poseidon2_merkle_root_batch.argtypes = [vp, vp, vp, vp, sz, u32, vp]
+    lib.b200_poseidon2_csprng_batch.argtypes = [vp, vp, vp, sz, sz, vp]
     lib.b200_pool_create.argtypes = [i32, u32, C.POINTER(vp)]
     lib.b200_pool_destroy.argtypes = [vp]
     lib.b200_pool_destroy.restype = None

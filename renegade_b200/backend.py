@@ -480,6 +480,31 @@ def compute_poseidon_hash_batch(ctx: Context, values: np.ndarray) -> np.ndarray:
     return out
 
 
+def merkle_root_batch(ctx: Context, leaf_hashes: np.ndarray, sisters: np.ndarray, is_right: np.ndarray) -> np.ndarray:
+    """Roots of a batch of Merkle openings (`b200_poseidon2_merkle_root_batch`): leaf_hashes (batch, 4), sisters
+    (batch, height, 4) Montgomery limbs, is_right (batch, height) booleans -> (batch, 4)."""
+    leaf = np.ascontiguousarray(leaf_hashes, dtype=np.uint64).reshape(-1, 4)
+    batch = leaf.shape[0]
+    sis = np.ascontiguousarray(sisters, dtype=np.uint64).reshape(batch, -1, 4)
+    height = sis.shape[1]
+    bits = np.ascontiguousarray(is_right, dtype=np.uint8).reshape(batch, height)
+    out = np.zeros((batch, 4), dtype=np.uint64)
+    _lib.check(ctx._lib.b200_poseidon2_merkle_root_batch(ctx._h, _ptr(leaf), _ptr(sis) if sis.size else None,
+                                                         bits.ctypes.data_as(C.c_void_p) if bits.size else None, batch, height,
+                                                         _ptr(out)))
+    return out
+
+
+def csprng_batch(ctx: Context, seeds: np.ndarray, first_index, count: int) -> np.ndarray:
+    """`count` consecutive values of each Poseidon CSPRNG stream (`b200_poseidon2_csprng_batch`): seeds (batch, 4)
+    Montgomery limbs, first_index (batch,) integers -> (batch, count, 4)."""
+    sd = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1, 4)
+    idx = np.ascontiguousarray(first_index, dtype=np.uint64).reshape(-1)
+    out = np.zeros((sd.shape[0], count, 4), dtype=np.uint64)
+    _lib.check(ctx._lib.b200_poseidon2_csprng_batch(ctx._h, _ptr(sd), _ptr(idx), sd.shape[0], count, _ptr(out)))
+    return out
+
+
 def poseidon2_permute_batch(ctx: Context, states: np.ndarray) -> np.ndarray:
     """`Poseidon2Sponge::permute` (poseidon2.rs:90-110) on (batch, 3, 4) states; returns the permuted copy."""
     s = np.array(states, dtype=np.uint64, copy=True, order="C")

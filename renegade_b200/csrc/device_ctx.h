@@ -151,6 +151,7 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
 int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
                      unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st);
 int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf);
+void msm_collect_timing(MsmScratch* s, size_t n, unsigned batch);
 // synthetic known-discrete-log bases P_i = a_i * G, a_i = SplitMix64-derived
 int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
                                cudaStream_t st);

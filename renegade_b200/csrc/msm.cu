@@ -613,16 +613,24 @@ MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
     for (int c = c_lo; c <= c_hi; ++c) {
         const int W = (255 + c - 1) / c;
         if (W > 32) continue;
-        // Cost model fitted to B200 measurements (profiles/r1b_msm_window_sweep.log), in ms:
-        // bucket phase ~ n*W mixed additions at ~5.8e6/ms, digit sort ~ n*W at ~45e6/ms, bucket
-        // reduction ~ a latency floor + 2^(c-1) buckets.  `shrt` = how many bits the top digit of
-        // a 254-bit scalar falls short of a full window: a short top digit piles n / 2^t points
-        // into 2^t buckets (hot atomics in the sort, more segments to combine).
+        // Cost model refitted to B200 measurements of the round-2 kernels (profiles/r2b_msm_window_sweep_small.log,
+        // r2b_msm_sweep.log), in ms.  A dependent curve addition costs a warp ~4-6 us of multiplier-pipe time, so at
+        // the prover's sizes every phase is a latency chain, not a throughput figure:
+        //   sort        0.042 + n W / 54e6
+        //   accumulate  max(throughput n W / 6.6e6,  chain 0.055 + 0.006 * min(load, 32) + 0.004 * segments) with
+        //               load = n W / 2^(c-1) entries per bucket, cut into segments of 32
+        //   reduce      0.13 + 0.0075 c (tree levels, bit sums, pairwise Horner) + 2^c / 4.9e6 (two additions per bucket)
+        //   short top digit: the top window of a 254-bit scalar has t = 254 - c (W - 1) bits, so n entries pile into
+        //               2^t buckets there; their n / 2^t / 32 segments are combined sequentially (up to 64)
         const int t = 254 - c * (W - 1);
-        const int shrt = t >= c - 3 ? 0 : (c - 3 - t);  // up to 2 bits short showed no penalty
         const double nw = (double)n * W;
-        const double cost = nw * (1.0 + 0.02 * shrt) / 5.8e6 + nw * (1.0 + 0.1 * shrt) / 45e6 + 0.42 +
-                            (double)((size_t)1 << (c - 1)) / 2.0e6;
+        const double load = nw / (double)((size_t)1 << (c - 1));
+        const double segs = load / 32.0;
+        const double acc = std::max(nw / 6.6e6, 0.055 + 0.006 * std::min(load, 32.0) + 0.004 * std::min(segs, 64.0));
+        const double top_segs = t < c - 1 ? (double)n / (double)((size_t)1 << t) / 32.0 : 0.0;
+        const int shrt = t >= c - 3 ? 0 : (c - 3 - t);  // hot atomics in the sort when the top digit is short
+        const double cost = 0.042 + nw * (1.0 + 0.1 * shrt) / 54e6 + acc + 0.13 + 0.0075 * c +
+                            (double)((size_t)1 << c) / 4.9e6 + 0.008 * std::min(top_segs, 64.0);
         if (cost < best_cost) {
             best_cost = cost;
             best.c = c;
@@ -904,6 +912,18 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     return B200_OK;
 }
 
+// phase times of the MSM whose events have completed (the caller has waited for the stream / done_ev)
+void msm_collect_timing(MsmScratch* s, size_t n, unsigned batch) {
+    if (!s->timing || !s->ev_init) return;
+    cudaEventElapsedTime(&s->ms[0], s->ev[0], s->ev[4]);
+    cudaEventElapsedTime(&s->ms[1], s->ev[0], s->ev[1]);
+    cudaEventElapsedTime(&s->ms[2], s->ev[1], s->ev[2]);
+    cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
+    s->tot_acc_ms += s->ms[2];
+    s->tot_pairs += (double)n * batch;
+    s->tot_launches += 1;
+}
+
 int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf) {
     const unsigned batch = s->pending_batch;
     s->pending_batch = 0;
@@ -918,15 +938,7 @@ int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf) {
     }
     const MsmPlan& pl = s->pending_plan;
     B200_CUDA(cudaEventSynchronize(s->done_ev));
-    if (s->timing) {
-        cudaEventElapsedTime(&s->ms[0], s->ev[0], s->ev[4]);
-        cudaEventElapsedTime(&s->ms[1], s->ev[0], s->ev[1]);
-        cudaEventElapsedTime(&s->ms[2], s->ev[1], s->ev[2]);
-        cudaEventElapsedTime(&s->ms[3], s->ev[2], s->ev[3]);
-        s->tot_acc_ms += s->ms[2];
-        s->tot_pairs += (double)s->pending_n * batch;
-        s->tot_launches += 1;
-    }
+    msm_collect_timing(s, s->pending_n, batch);
     // host epilogue: per MSM a Horner over the physical windows (none when fully precomputed), then
     // ONE field inversion for the whole batch (Montgomery's trick over the ZZZ coordinates) — a few
     // hundred bytes of work, read straight from the pinned copy of the window sums.

@@ -407,6 +407,7 @@ static int multi_msm(b200_multi* m, const b200_multi_bases* b, const void* const
     for (size_t i = 0; i < nl; ++i) {
         B200_CUDA(cudaSetDevice(m->locals[i].ctx->c.device));
         B200_CUDA(cudaEventSynchronize(m->locals[i].done));
+        if (b->end[i] > b->begin[i]) msm_collect_timing(&m->locals[i].ctx->c.msm, b->end[i] - b->begin[i], 1);
     }
     // 4. host: one inversion
     const g1_xyzz total = *reinterpret_cast<const g1_xyzz*>(m->locals[0].h_total.p);

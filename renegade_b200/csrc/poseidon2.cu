@@ -103,6 +103,43 @@ __global__ void __launch_bounds__(128) k_poseidon2_hash(const fe* __restrict__ i
     fe_store(out + t, s[1]);
 }
 
+// two-to-one sponge hash H(a, b): absorb two scalars at rate 2, squeeze one (one permutation)
+__device__ __forceinline__ fe hash2(const fe& a, const fe& b) {
+    fe s[3] = {fe_zero(), a, b};
+    permute(s);
+    return s[1];
+}
+
+// Merkle roots of `batch` openings (circuit-types `MerkleOpening<HEIGHT>`; native side of
+// circuits-core/src/zk_gadgets/primitives/merkle.rs:13-126): cur = leaf hash; per level the sister node and whether
+// the running hash is the RIGHT child:  cur = H(sister, cur)  or  H(cur, sister).
+__global__ void __launch_bounds__(128) k_merkle_roots(const fe* __restrict__ leaf_hashes, const fe* __restrict__ sisters,
+                                                      const uint8_t* __restrict__ is_right, size_t batch, unsigned height,
+                                                      fe* __restrict__ roots) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch) return;
+    fe cur = fe_load_ro(leaf_hashes + t);
+    for (unsigned lvl = 0; lvl < height; ++lvl) {
+        const fe sis = fe_load_ro(sisters + t * height + lvl);
+        cur = is_right[t * height + lvl] ? hash2(sis, cur) : hash2(cur, sis);
+    }
+    fe_store(roots + t, cur);
+}
+
+// `count` consecutive values of `batch` Poseidon CSPRNG streams (darkpool-types/src/csprng.rs:30-75): value i of a
+// stream is H(seed, i); out[s * count + j] = H(seed_s, first_index_s + j).  Indices are small integers (u64).
+__global__ void __launch_bounds__(128) k_csprng(const fe* __restrict__ seeds, const uint64_t* __restrict__ first_index,
+                                                size_t batch, size_t count, fe* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch * count) return;
+    const size_t sidx = t / count, j = t % count;
+    const uint64_t idx = first_index[sidx] + j;
+    fe i_canon = fe_zero();
+    i_canon.l[0] = (uint32_t)idx;
+    i_canon.l[1] = (uint32_t)(idx >> 32);
+    fe_store(out + t, hash2(fe_load_ro(seeds + sidx), fe_to_mont<Fr>(i_canon)));
+}
+
 std::once_flag g_constants_once[64];  // one upload per device, whatever context gets there first
 
 }  // namespace
@@ -165,6 +202,58 @@ int b200_poseidon2_hash_batch(b200_ctx* ctx, const uint64_t* inputs, size_t batc
     if (len) B200_CUDA(cudaMemcpyAsync(d_in, inputs, batch * len * sizeof(fe), cudaMemcpyDefault, st));
     B200_LAUNCH(k_poseidon2_hash, (unsigned)((batch + 127) / 128), 128, 0, st)(d_in, batch, len, d_out);
     B200_CUDA(cudaMemcpyAsync(out, d_out, batch * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_poseidon2_merkle_root_batch(b200_ctx* ctx, const uint64_t* leaf_hashes, const uint64_t* sisters,
+                                     const uint8_t* is_right, size_t batch, unsigned height, uint64_t* roots) {
+    B200_TRY
+    if (!ctx || !roots || (batch && (!leaf_hashes || (height && (!sisters || !is_right)))) || height > 64) return B200_ERR_INVALID;
+    if (batch == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = load_constants(ctx->c.device);
+    if (rc != B200_OK) return rc;
+    cudaStream_t st = ctx->c.stream;
+    const size_t n_sis = batch * height;
+    if ((rc = ctx->c.plonk_ws.reserve((2 * batch + n_sis + 1) * sizeof(fe) + n_sis + 64)) != B200_OK) return rc;
+    fe* d_leaf = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
+    fe* d_sis = d_leaf + batch;
+    fe* d_out = d_sis + n_sis;
+    uint8_t* d_bits = reinterpret_cast<uint8_t*>(d_out + batch);
+    B200_CUDA(cudaMemcpyAsync(d_leaf, leaf_hashes, batch * sizeof(fe), cudaMemcpyDefault, st));
+    if (n_sis) {
+        B200_CUDA(cudaMemcpyAsync(d_sis, sisters, n_sis * sizeof(fe), cudaMemcpyDefault, st));
+        B200_CUDA(cudaMemcpyAsync(d_bits, is_right, n_sis, cudaMemcpyDefault, st));
+    }
+    B200_LAUNCH(k_merkle_roots, (unsigned)((batch + 127) / 128), 128, 0, st)(d_leaf, d_sis, d_bits, batch, height, d_out);
+    B200_CUDA(cudaMemcpyAsync(roots, d_out, batch * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_poseidon2_csprng_batch(b200_ctx* ctx, const uint64_t* seeds, const uint64_t* first_index, size_t batch, size_t count,
+                                uint64_t* out) {
+    B200_TRY
+    if (!ctx || !out || (batch && (!seeds || !first_index))) return B200_ERR_INVALID;
+    if (batch == 0 || count == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = load_constants(ctx->c.device);
+    if (rc != B200_OK) return rc;
+    cudaStream_t st = ctx->c.stream;
+    const size_t total = batch * count;
+    if ((rc = ctx->c.plonk_ws.reserve((batch + total + 1) * sizeof(fe) + batch * 8 + 64)) != B200_OK) return rc;
+    fe* d_seeds = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
+    fe* d_out = d_seeds + batch;
+    uint64_t* d_idx = reinterpret_cast<uint64_t*>(d_out + total);
+    B200_CUDA(cudaMemcpyAsync(d_seeds, seeds, batch * sizeof(fe), cudaMemcpyDefault, st));
+    B200_CUDA(cudaMemcpyAsync(d_idx, first_index, batch * 8, cudaMemcpyDefault, st));
+    B200_LAUNCH(k_csprng, (unsigned)((total + 127) / 128), 128, 0, st)(d_seeds, d_idx, batch, count, d_out);
+    B200_CUDA(cudaMemcpyAsync(out, d_out, total * sizeof(fe), cudaMemcpyDefault, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;
     B200_CATCH

@@ -55,3 +55,36 @@ def test_gpu_permutation_and_hash(ctx, oracle, pyoracle):
         out = compute_poseidon_hash_batch(ctx, arr)
         exp = [py.poseidon2_hash(row, full, partial) for row in vals[:25]]
         assert from_m(out[:25]) == exp, ln
+
+
+@pytest.mark.gpu
+def test_gpu_merkle_roots_and_csprng_streams(ctx, oracle, pyoracle):
+    """The batch callers of the witness side: Merkle roots of openings of height 10 (`MERKLE_HEIGHT`,
+    constants/src/lib.rs:50) and Poseidon CSPRNG stream values H(seed, i) (darkpool-types/src/csprng.rs:30-75), device
+    vs the oracle's Poseidon2 on Python integers."""
+    import random
+    from renegade_b200.backend import csprng_batch, merkle_root_batch
+    py = pyoracle
+    full, partial = py.poseidon2_load_constants(FIX)
+    H = lambda vals: py.poseidon2_hash(vals, full, partial)
+    to_m = lambda vals: oracle.ints_to_array([py.to_mont(v, py.R) for v in vals])
+    from_m = lambda arr: [py.from_mont(v, py.R) for v in oracle.array_to_ints(arr)]
+    rnd = random.Random(11)
+    batch, height = 67, 10
+    leaves = [rnd.randrange(py.R) for _ in range(batch)]
+    sisters = [[rnd.randrange(py.R) for _ in range(height)] for _ in range(batch)]
+    bits = [[rnd.random() < 0.5 for _ in range(height)] for _ in range(batch)]
+    got = from_m(merkle_root_batch(ctx, to_m(leaves), to_m([v for row in sisters for v in row]).reshape(batch, height, 4),
+                                   np.array(bits, dtype=np.uint8)))
+    for i in range(0, batch, 7):
+        cur = leaves[i]
+        for sis, right in zip(sisters[i], bits[i]):
+            cur = H([sis, cur] if right else [cur, sis])
+        assert got[i] == cur, i
+    # height 0: the root is the leaf hash itself
+    assert from_m(merkle_root_batch(ctx, to_m(leaves[:3]), np.zeros((3, 0, 4), dtype=np.uint64), np.zeros((3, 0), dtype=np.uint8))) == leaves[:3]
+    seeds = [rnd.randrange(py.R) for _ in range(9)]
+    first = [rnd.randrange(0, 1 << 40) for _ in range(9)]
+    out = csprng_batch(ctx, to_m(seeds), first, 5)
+    for s in (0, 4, 8):
+        assert from_m(out[s]) == [H([seeds[s], first[s] + j]) for j in range(5)]
