@@ -362,7 +362,6 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
 // g1_add inlined a dozen times their code no longer fits the instruction cache (ncu: 0.67
 // "no instruction" stalls per issue).  Out-of-line copies keep those kernels small.
 __device__ __noinline__ g1_xyzz xyzz_add(const g1_xyzz& a, const g1_xyzz& b) { return g1_add(a, b); }
-__device__ __noinline__ g1_xyzz xyzz_dbl(const g1_xyzz& a) { return g1_dbl(a); }
 
 // bucket = sum of its segment sums: sequential for ordinary buckets, deferred to a block tree
 // (msm_heavy_combine_kernel) for buckets cut into more than kCombineSeq segments.
@@ -452,6 +451,60 @@ __global__ void __launch_bounds__(kTreeThreads) msm_tree_kernel(TreeArgs a) {
     g1_xyzz_store(lv.out + t, acc);
 }
 
+// Second (and last) level of both trees: what the serial level leaves — 2^g partial sums per row / column, g <= 8 —
+// is folded by a binary tree in shared memory, one addition per step on the critical path instead of 2^g - 1.
+//   rows:    out[O] = sum_j in[O * G + j]                                  (G = 2^g partials of a row are contiguous)
+//   columns: out[w * L + lo] = sum_j in[(w * G + j) * L + lo]             (the G partial rows of window w)
+struct BlockTreePart {
+    const g1_xyzz* in;
+    g1_xyzz* out;
+    uint32_t n_out, g_log, n_blocks;
+};
+struct BlockTreeArgs {
+    BlockTreePart row, col;
+    uint32_t l_log;
+};
+constexpr int kBlockTreeThreads = 256;
+
+__global__ void __launch_bounds__(kBlockTreeThreads) msm_blocktree_kernel(BlockTreeArgs a) {
+    __shared__ g1_xyzz sh[kBlockTreeThreads];
+    const bool is_row = blockIdx.x < a.row.n_blocks;
+    const BlockTreePart& p = is_row ? a.row : a.col;
+    const uint32_t blk = is_row ? blockIdx.x : blockIdx.x - a.row.n_blocks;
+    const uint32_t G = 1u << p.g_log, ob_log = 8u - p.g_log, OB = 1u << ob_log;  // outputs per block
+    const uint32_t t = threadIdx.x;
+    // rows: t = o * G + j (j fastest: contiguous loads); columns: t = j * OB + o (o fastest: adjacent columns)
+    const uint32_t j = is_row ? (t & (G - 1u)) : (t >> ob_log);
+    const uint32_t o = is_row ? (t >> p.g_log) : (t & (OB - 1u));
+    const uint32_t O = blk * OB + o;
+    const uint32_t hop = is_row ? 1u : OB;  // distance in `sh` between partials j and j + 1 of one output
+    g1_xyzz v = g1_xyzz_inf();
+    if (O < p.n_out) {
+        size_t idx;
+        if (is_row) {
+            idx = ((size_t)O << p.g_log) | j;
+        } else {
+            const uint32_t w = O >> a.l_log, lo = O & ((1u << a.l_log) - 1u);
+            idx = ((((size_t)w << p.g_log) | j) << a.l_log) | lo;
+        }
+        v = g1_xyzz_load(p.in + idx);
+    }
+    sh[t] = v;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t s = G >> 1; s > 0; s >>= 1) {
+        g1_xyzz other = g1_xyzz_inf();
+        if (j < s) other = sh[t + s * hop];
+        __syncthreads();
+        if (j < s) {
+            v = g1_add(v, other);
+            sh[t] = v;
+        }
+        __syncthreads();
+    }
+    if (j == 0 && O < p.n_out) g1_xyzz_store(p.out + O, v);
+}
+
 // What is left per window are the two weighted sums.  A dependent XYZZ addition costs a warp ~3.8 us of
 // multiplier-pipe time whatever else the SM does, so this tail is arranged for the SHORTEST dependent chain, with
 // every independent piece on its own SM:
@@ -530,7 +583,7 @@ __global__ void __launch_bounds__(32) msm_horner_kernel(const g1_xyzz* __restric
         g1_xyzz o = xyzz_shfl_down(v, 1u << s);
         if (lane + (1u << s) >= 32u) o = g1_xyzz_inf();
 #pragma unroll 1
-        for (uint32_t i = 0; i < (1u << s); ++i) o = xyzz_dbl(o);
+        for (uint32_t i = 0; i < (1u << s); ++i) o = g1_dbl(o);
         v = g1_add(v, o);
     }
     if (lane == 0) g1_xyzz_store(window_sums + window, v);
@@ -743,19 +796,16 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
     return rc;
 }
 
-// Bits of the column index (l) and the per-level fan-in bits of the two reduction trees.
-static void tree_shape(int c, int* l_log, int* r_log, int* levels, int row_bits[8], int col_bits[8]) {
+// Bits of the column index (l) and of the row index (r), and how each tree splits them: `a` bits by the serial
+// level (fan-in <= 8 per thread: the throughput part, two additions per bucket), the rest (<= 8 bits) by the
+// shared-memory binary tree of msm_blocktree_kernel.
+static void tree_shape(int c, int* l_log, int* r_log, int* a_row, int* a_col) {
     const int bits = c - 1;
     const int l = (bits + 1) / 2, r = bits - l;
-    int K = (l + 2) / 3;  // fan-in <= 8
-    if (K < 1) K = 1;
-    for (int i = 0; i < K; ++i) {
-        row_bits[i] = l / K + (i < l % K ? 1 : 0);
-        col_bits[i] = r / K + (i < r % K ? 1 : 0);
-    }
     *l_log = l;
     *r_log = r;
-    *levels = K;
+    *a_row = l < 3 ? l : 3;
+    *a_col = r < 3 ? r : 3;
 }
 
 // `batch` MSMs over the same bases (scalar vectors `stride` elements apart) in one pass: the
@@ -809,17 +859,16 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->seg_sums.reserve(max_segs * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     if ((rc = s->seg_order.reserve(max_segs * 4)) != B200_OK) return rc;
-    int l_log, r_log, levels, row_bits[8], col_bits[8];
-    tree_shape(pl.c, &l_log, &r_log, &levels, row_bits, col_bits);
-    // tree outputs: each level shrinks its input by its fan-in; a level with fan-in 1 is skipped
-    size_t tree_elems = 0;
-    {
-        size_t rn = n_buckets, cn = n_buckets;
-        for (int i = 0; i < levels; ++i) {
-            if (row_bits[i]) { rn >>= row_bits[i]; tree_elems += rn; }
-            if (col_bits[i]) { cn >>= col_bits[i]; tree_elems += cn; }
-        }
+    int l_log, r_log, a_row, a_col;
+    tree_shape(pl.c, &l_log, &r_log, &a_row, &a_col);
+    if (l_log - a_row > 8 || r_log - a_col > 8) {
+        set_error("msm: window too wide for the two-level bucket reduction");
+        return B200_ERR_INVALID;
     }
+    // tree outputs: the serial level's partials, then the row sums R and column sums C
+    const size_t row_l1 = n_buckets >> a_row, col_l1 = n_buckets >> a_col;
+    const size_t n_R = n_windows << r_log, n_C = n_windows << l_log;
+    const size_t tree_elems = row_l1 + col_l1 + n_R + n_C;
     if ((rc = s->tree.reserve((tree_elems + 1) * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->h_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
@@ -873,29 +922,31 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         seg_sums, seg_offsets, &stt->heavy_count, heavy_list, buckets);
     if (s->timing) cudaEventRecord(s->ev[2], st);
     {
+        g1_xyzz* t0 = (g1_xyzz*)s->tree.p;
+        g1_xyzz *row_p = t0, *col_p = t0 + row_l1, *R = col_p + col_l1, *Cs = R + n_R;
         const g1_xyzz *row_in = buckets, *col_in = buckets;
-        g1_xyzz* next = (g1_xyzz*)s->tree.p;
-        size_t rn = n_buckets, cn = n_buckets;
-        for (int i = 0; i < levels; ++i) {
+        if (a_row || a_col) {  // serial level: out[a * inner + b] = sum_{j < 2^a} in[(a * 2^a + j) * inner + b]
             TreeArgs a;
-            a.row = TreeLevel{row_in, next, 0, (uint32_t)row_bits[i], 0, 0};
-            if (row_bits[i]) {
-                rn >>= row_bits[i];
-                a.row.n_out = (uint32_t)rn;
-                row_in = next;
-                next += rn;
-            }
-            a.col = TreeLevel{col_in, next, 0, (uint32_t)col_bits[i], (uint32_t)l_log, 0};
-            if (col_bits[i]) {
-                cn >>= col_bits[i];
-                a.col.n_out = (uint32_t)cn;
-                col_in = next;
-                next += cn;
-            }
+            a.row = TreeLevel{buckets, row_p, a_row ? (uint32_t)row_l1 : 0u, (uint32_t)a_row, 0, 0};
+            a.col = TreeLevel{buckets, col_p, a_col ? (uint32_t)col_l1 : 0u, (uint32_t)a_col, (uint32_t)l_log, 0};
             a.row.n_blocks = (a.row.n_out + kTreeThreads - 1) / kTreeThreads;
             a.col.n_blocks = (a.col.n_out + kTreeThreads - 1) / kTreeThreads;
+            B200_LAUNCH(msm_tree_kernel, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
+            if (a_row) row_in = row_p;
+            if (a_col) col_in = col_p;
+        }
+        {   // binary trees over what is left of each row / column
+            const int gr = l_log - a_row, gc = r_log - a_col;
+            BlockTreeArgs a;
+            a.l_log = (uint32_t)l_log;
+            a.row = BlockTreePart{row_in, R, gr ? (uint32_t)n_R : 0u, (uint32_t)gr, 0};
+            a.col = BlockTreePart{col_in, Cs, gc ? (uint32_t)n_C : 0u, (uint32_t)gc, 0};
+            a.row.n_blocks = gr ? (uint32_t)((n_R + (256u >> gr) - 1) / (256u >> gr)) : 0u;
+            a.col.n_blocks = gc ? (uint32_t)((n_C + (256u >> gc) - 1) / (256u >> gc)) : 0u;
             if (a.row.n_blocks + a.col.n_blocks)
-                B200_LAUNCH(msm_tree_kernel, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
+                B200_LAUNCH(msm_blocktree_kernel, a.row.n_blocks + a.col.n_blocks, kBlockTreeThreads, 0, st)(a);
+            if (gr) row_in = R;
+            if (gc) col_in = Cs;
         }
         // row_in: R[window][2^r_log], col_in: C[window][2^l_log]
         const unsigned n_bits = (unsigned)(pl.c - 1);
