@@ -78,7 +78,10 @@ int b200_srs_parse_ptau(const uint8_t* bytes, size_t len, const uint8_t** g1_rec
 
 /* Uploads n affine points (64-byte records) and precomputes their window tables.
  * Replaces building `UnivariateUniversalParams.powers_of_g` (srs.rs:70) / the `commit_key`
- * held by `ProvingKey` (traits.rs:850).  window_bits = 0 lets the library choose.
+ * held by `ProvingKey` (traits.rs:850).  window_bits = 0 lets the library choose the Pippenger window
+ * for THROUGHPUT (several MSMs / proofs in flight on the GPU, the prover pool's regime: least multiplier
+ * work), 1 for LATENCY (one MSM at a time: shortest dependent chains; e.g. c = 16 instead of 15 at 2^13
+ * points), 8..23 fixes it.  The result does not depend on the window.
  * check_on_curve != 0 repeats the reference's `is_on_curve` assertion (srs.rs:178-179) on the
  * device and fails with B200_ERR_NOT_ON_CURVE. */
 int b200_bases_load(b200_ctx* ctx, const uint8_t* points64, size_t n, int window_bits,

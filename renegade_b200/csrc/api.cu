@@ -270,8 +270,8 @@ int b200_bases_load(b200_ctx* ctx, const uint8_t* points64, size_t n, int window
                     b200_bases** out) {
     B200_TRY
     if (!ctx || !points64 || !out) return B200_ERR_INVALID;
-    if (window_bits != 0 && (window_bits < 8 || window_bits > 23)) {
-        set_error("window_bits must be 0 (auto) or in [8, 23]");
+    if (window_bits != 0 && window_bits != 1 && (window_bits < 8 || window_bits > 23)) {
+        set_error("window_bits must be 0 (auto, throughput), 1 (auto, latency) or in [8, 23]");
         return B200_ERR_INVALID;
     }
     std::lock_guard<std::mutex> lk(ctx->c.mu);
@@ -288,8 +288,8 @@ int b200_bases_load(b200_ctx* ctx, const uint8_t* points64, size_t n, int window
 int b200_bases_load_device(b200_ctx* ctx, const void* d_points64, size_t n, int window_bits, b200_bases** out) {
     B200_TRY
     if (!ctx || !d_points64 || !out) return B200_ERR_INVALID;
-    if (window_bits != 0 && (window_bits < 8 || window_bits > 23)) {
-        set_error("window_bits must be 0 (auto) or in [8, 23]");
+    if (window_bits != 0 && window_bits != 1 && (window_bits < 8 || window_bits > 23)) {
+        set_error("window_bits must be 0 (auto, throughput), 1 (auto, latency) or in [8, 23]");
         return B200_ERR_INVALID;
     }
     std::lock_guard<std::mutex> lk(ctx->c.mu);

@@ -659,31 +659,44 @@ __global__ void known_dlog_bases_kernel(uint64_t seed, size_t first, size_t n, g
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// c_override: 0 = choose for THROUGHPUT (many MSMs / proofs in flight on the GPU, the prover pool's regime: minimise the
+// multiplier work), 1 = choose for LATENCY (one MSM at a time: minimise the dependent chains), >= 2 = that window.
 MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
     MsmPlan best;
     double best_cost = 1e300;
-    const int c_lo = c_override > 0 ? c_override : 6, c_hi = c_override > 0 ? c_override : 23;
+    const bool latency_mode = c_override == 1;
+    const int c_lo = c_override > 1 ? c_override : 6, c_hi = c_override > 1 ? c_override : 23;
     for (int c = c_lo; c <= c_hi; ++c) {
         const int W = (255 + c - 1) / c;
         if (W > 32) continue;
-        // Cost model refitted to B200 measurements of the round-2 kernels (profiles/r2b_msm_window_sweep_small.log,
-        // r2b_msm_sweep.log), in ms.  A dependent curve addition costs a warp ~4-6 us of multiplier-pipe time, so at
-        // the prover's sizes every phase is a latency chain, not a throughput figure:
-        //   sort        0.042 + n W / 54e6
-        //   accumulate  max(throughput n W / 6.6e6,  chain 0.055 + 0.006 * min(load, 32) + 0.004 * segments) with
-        //               load = n W / 2^(c-1) entries per bucket, cut into segments of 32
-        //   reduce      0.13 + 0.0075 c (tree levels, bit sums, pairwise Horner) + 2^c / 4.9e6 (two additions per bucket)
-        //   short top digit: the top window of a 254-bit scalar has t = 254 - c (W - 1) bits, so n entries pile into
-        //               2^t buckets there; their n / 2^t / 32 segments are combined sequentially (up to 64)
+        // Both models are fitted to B200 measurements of the round-2 kernels (profiles/r2b_msm_window_sweep_small.log,
+        // r2c_msm_sweep.log, r2c_bench.json), in ms.
+        // The top window of a 254-bit scalar has t = 254 - c (W - 1) bits: n entries pile into 2^t buckets there (hot
+        // atomics in the sort; n / 2^t / 32 segments combined sequentially, up to 64, before the block-tree path).
         const int t = 254 - c * (W - 1);
         const double nw = (double)n * W;
-        const double load = nw / (double)((size_t)1 << (c - 1));
-        const double segs = load / 32.0;
-        const double acc = std::max(nw / 6.6e6, 0.055 + 0.006 * std::min(load, 32.0) + 0.004 * std::min(segs, 64.0));
-        const double top_segs = t < c - 1 ? (double)n / (double)((size_t)1 << t) / 32.0 : 0.0;
-        const int shrt = t >= c - 3 ? 0 : (c - 3 - t);  // hot atomics in the sort when the top digit is short
-        const double cost = 0.042 + nw * (1.0 + 0.1 * shrt) / 54e6 + acc + 0.13 + 0.0075 * c +
-                            (double)((size_t)1 << c) / 4.9e6 + 0.008 * std::min(top_segs, 64.0);
+        const int shrt = t >= c - 6 ? 0 : (c - 6 - t);
+        double cost;
+        if (!latency_mode) {
+            // THROUGHPUT: Fq-product equivalents at the measured 66.7 G/s — 9.5 per bucket addition, ~1.6 per digit for
+            // the sort (more with a short top digit), 2 full additions (12.5) + the bit-sum pass per bucket in the
+            // reduction.  With several proofs in flight this, not the chain length, is what a proof costs the GPU: at
+            // n = 2^13 the latency-optimal c = 16 spends as much on reducing 2^15 buckets as on filling them.
+            cost = (nw * (9.5 + 1.6 * (1.0 + 0.3 * shrt)) + (double)((size_t)1 << (c - 1)) * 32.0) / 66.7e6;
+        } else {
+            // LATENCY: a dependent curve addition costs a warp ~4-6 us of multiplier-pipe time, so at the prover's sizes
+            // every phase is a chain:
+            //   sort        0.042 + n W / 54e6
+            //   accumulate  max(throughput n W / 6.6e6,  chain 0.055 + 0.006 * min(load, 32) + 0.004 * segments) with
+            //               load = n W / 2^(c-1) entries per bucket, cut into segments of 32
+            //   reduce      0.13 + 0.0075 c (tree level, block tree, bit sums, pairwise Horner) + 2^c / 4.9e6
+            const double load = nw / (double)((size_t)1 << (c - 1));
+            const double segs = load / 32.0;
+            const double acc = std::max(nw / 6.6e6, 0.055 + 0.006 * std::min(load, 32.0) + 0.004 * std::min(segs, 64.0));
+            const double top_segs = t < c - 1 ? (double)n / (double)((size_t)1 << t) / 32.0 : 0.0;
+            cost = 0.042 + nw * (1.0 + 0.1 * shrt) / 54e6 + acc + 0.13 + 0.0075 * c +
+                   (double)((size_t)1 << c) / 4.9e6 + 0.008 * std::min(top_segs, 64.0);
+        }
         if (cost < best_cost) {
             best_cost = cost;
             best.c = c;

@@ -29,7 +29,8 @@ namespace {
 
 constexpr int NW = 5;    // wire columns (GATE_WIDTH + 1)
 constexpr int NS = 13;   // q_lc[4] q_mul[2] q_hash[4] q_o q_c q_ecc
-constexpr int CH = 64;   // elements per thread in the chunked scans
+constexpr int CH = 16;   // elements per thread in the chunked scans: every level is a chain of CH dependent products
+                         // (latency-bound kernels), so short chunks and one more level beat long chunks
 
 struct KArr {
     fe v[NW];
@@ -535,7 +536,7 @@ struct Workspace {
 };
 static size_t workspace_elems(size_t n) {
     const size_t S = n + 4, m = 8 * n;
-    return NW * n + NW * S + S + S + 3 * n + (n / CH + 4 * CH + 64) + 7 * m + m + NW * S + S + 2 * (S + 8) +
+    return NW * n + NW * S + S + S + 3 * n + (2 * (n / CH) + 4 * CH + 64) + 7 * m + m + NW * S + S + 2 * (S + 8) +
            4 * (S / CH + 4 * CH + 64) + kMaxEval * (S / CH + S / CH / CH + 2 * CH + 16) + 32 + 8;
 }
 static Workspace carve(fe* base, size_t n) {
@@ -550,7 +551,7 @@ static Workspace carve(fe* base, size_t n) {
     w.num = p; p += n;
     w.den = p; p += n;
     w.tmp = p; p += n;
-    w.scan = p; p += n / CH + 4 * CH + 64;
+    w.scan = p; p += 2 * (n / CH) + 4 * CH + 64;  // all levels of the product scan: n / CH * (1 + 1/CH + ...)
     w.ext = p; p += 7 * m;
     w.quot = p; p += m;
     w.split = p; p += NW * S;

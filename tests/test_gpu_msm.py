@@ -33,8 +33,10 @@ def test_known_dlog_golden(ctx, oracle, pyoracle, kat):
         assert py.decode_g1_mont(out.tobytes(), 0) == (H(rec["result"][0]), H(rec["result"][1]))
 
 
-@pytest.mark.parametrize("n,c", [(1, 0), (31, 0), (32, 8), (1000, 0), (1000, 9), (4099, 0), (4099, 13),
-                                 (1 << 14, 0), ((1 << 16) + 3, 0), (3000, 18), (3000, 20)])
+# c = 0: window chosen for throughput, 1: for latency, >= 8: fixed (b200_bases_load)
+@pytest.mark.parametrize("n,c", [(1, 0), (31, 0), (31, 1), (32, 8), (1000, 0), (1000, 1), (1000, 9), (4099, 0), (4099, 1),
+                                 (4099, 13), (1 << 14, 0), (1 << 14, 1), ((1 << 16) + 3, 0), ((1 << 16) + 3, 1),
+                                 (3000, 18), (3000, 20), (3000, 23)])
 def test_msm_matches_oracle(ctx, oracle, n, c, mode):
     pts = oracle.known_dlog_bases(0xB200, n)
     bases = ctx.load_bases(pts, window_bits=c)
