@@ -61,17 +61,36 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     fe* out = a.out + (size_t)blockIdx.y * a.batch_stride;
 
     // ---- gather the tile -------------------------------------------------------------------
-    for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
-        uint32_t qq, m;
-        if (a.lo == 0) { qq = e >> t_log; m = e & T_mask; }   // idx = q*T + m : contiguous in e
-        else           { m = e >> q_log; qq = e & Q_mask; }   // adjacent sub-transforms adjacent
-        const uint32_t q = q_base + qq;
-        const size_t idx = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & lo_mask);
-        fe v = fe_load(in + idx);
-        if (a.pre) v = fe_mul<FrCfg>(v, fe_load_ro(a.pre + idx));
-        const uint32_t pos = (m << q_log) | qq;
-        plane_lo[pos] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        plane_hi[pos] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    // a thread's (up to) four elements are all requested before the first one is consumed: one trip to L2 / HBM per
+    // tile instead of four dependent ones
+    {
+        fe v[4];
+        uint32_t pos[4];
+        size_t gidx[4];
+        const uint32_t per = ((uint32_t)E + blockDim.x - 1) / blockDim.x;  // <= 4 (E <= 1024, blockDim = min(E / 2, 256) >= E / 4)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = threadIdx.x + (uint32_t)k * blockDim.x;
+            if ((uint32_t)k < per && e < (uint32_t)E) {
+                uint32_t qq, m;
+                if (a.lo == 0) { qq = e >> t_log; m = e & T_mask; }   // idx = q*T + m : contiguous in e
+                else           { m = e >> q_log; qq = e & Q_mask; }   // adjacent sub-transforms adjacent
+                const uint32_t q = q_base + qq;
+                gidx[k] = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & lo_mask);
+                pos[k] = (m << q_log) | qq;
+                v[k] = fe_load(in + gidx[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = threadIdx.x + (uint32_t)k * blockDim.x;
+            if ((uint32_t)k < per && e < (uint32_t)E) {
+                fe x = v[k];
+                if (a.pre) x = fe_mul<FrCfg>(x, fe_load_ro(a.pre + gidx[k]));
+                plane_lo[pos[k]] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+                plane_hi[pos[k]] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+            }
+        }
     }
     __syncthreads();
 
