@@ -121,3 +121,17 @@ class OutputBalanceValidityCircuit(SingleProverCircuit):
 # the circuits `NativeProofManager::preprocess_circuits` registers (native_proof_manager.rs:305-331) that are restated here
 REGISTERED = [ValidBalanceCreate, IntentAndBalancePrivateSettlementCircuit, IntentAndBalanceValidityCircuit,
               OutputBalanceValidityCircuit]
+
+
+# ---- collaborative counterparts (traits.rs:1103-1154) ---------------------------------------------------------------
+from renegade_b200.circuit_types import MultiProverCircuit  # noqa: E402
+
+
+class IntentAndBalancePrivateSettlementMultiprover(MultiProverCircuit):
+    """The VALID-MATCH-class statement proved jointly by the two parties of a match: each holds a share of the wire
+    table of `IntentAndBalancePrivateSettlementCircuit`; the opened proof verifies under that circuit's keys."""
+    BaseCircuit = IntentAndBalancePrivateSettlementCircuit
+
+
+class ValidBalanceCreateMultiprover(MultiProverCircuit):
+    BaseCircuit = ValidBalanceCreate

@@ -352,6 +352,19 @@ int b200_multi_msm(b200_multi* m, const b200_multi_bases* bases, const uint64_t*
 int b200_multi_msm_local(b200_multi* m, const b200_multi_bases* bases, const void* const* scalars_local,
                          int scalars_on_device, int scalars_montgomery, uint64_t out_xy[8], int* out_is_identity);
 
+/* ---- device-vector primitives (Fr, Montgomery, device pointers) -------------------------------
+ * The share arithmetic of a collaborative prover (`MultiproverPlonkKzgSnark`, traits.rs:1136) on top of
+ * b200_ntt_device / b200_msm_device: element-wise operations, batch inversion of opened values, polynomial
+ * evaluation and division by a linear factor.  Each call synchronises the context's stream. */
+/* out[i] = a[i] (op) b[i], or a[i] (op) b[0] when b_is_scalar; op 0 add, 1 sub, 2 mul. */
+int b200_fr_vec_op(b200_ctx* ctx, int op, const void* d_a, const void* d_b, int b_is_scalar, size_t n, void* d_out);
+/* data[i] <- 1 / data[i] in place (0 stays 0). */
+int b200_fr_batch_inverse_device(b200_ctx* ctx, void* d_data, size_t n);
+/* out = p(z) for the len coefficients at d_coeffs. */
+int b200_fr_poly_eval_device(b200_ctx* ctx, const void* d_coeffs, size_t len, const uint64_t z[4], uint64_t out[4]);
+/* q = p / (X - z), remainder dropped (len - 1 coefficients written to d_q). */
+int b200_fr_poly_div_linear_device(b200_ctx* ctx, const void* d_p, size_t len, const uint64_t z[4], void* d_q);
+
 /* ---- witness-side batch hashing ------------------------------------- */
 /* `batch` independent Poseidon2 sponge hashes of `len` scalars each (inputs: batch x len x 4
  * limbs, Montgomery; out: batch x 4 limbs; host or device pointers).  Each equals the reference's

@@ -245,3 +245,59 @@ def singleprover_prove_and_verify(circuit: type, witness, statement, rng=None) -
         circuit.verify(statement, proof)
     except VerifierError as e:
         raise ProverError("Verification", e) from e
+
+
+# ---- circuit-types/src/traits.rs:1103-1154, circuits-core/src/lib.rs:145-177 -------------------------------------------
+class MultiProverCircuit:
+    """`MultiProverCircuit`: the collaborative counterpart of a `SingleProverCircuit` (the reference pairs them: a
+    statement's `MultiProverCircuit` impl names its `BaseCircuit`, and the opened proof verifies under the SAME keys,
+    traits.rs:1103-1154).  Subclasses set `BaseCircuit`.
+
+    `prove_with_link_hint(witness_shares, statement)`: every party's share of the 5 x n wire table (and of the 17
+    blinders) goes into `collaborative.MultiproverPlonkKzgSnark` on the device; what comes back is the OPENED proof and
+    hint (`open_authenticated` in `multiprover_prove_and_verify`, lib.rs:166-177).  Producing the wire-table shares —
+    running the constraint system on shared values (`MpcPlonkCircuit`) — is the callers' side, like single-prover
+    synthesis; `share_witness_table` stands in for it where a test or an example starts from a clear witness."""
+    BaseCircuit: type = None
+
+    @classmethod
+    def share_witness_table(cls, witness, statement, parties: int = 2, seed: int = 0):
+        from .collaborative import share_table
+        base = cls.BaseCircuit
+        circ = base.synthesize(witness, statement, base.get_circuit_layout()).finalize_for_arithmetization()
+        return circ, share_table(np.asarray(circ.wires, dtype=np.uint64).reshape(-1, 4), parties, seed)
+
+    @classmethod
+    def prove_with_link_hint(cls, circ, wire_shares, blinder_shares=None, rng=None):
+        """`circ`: the finalized public circuit structure (selectors, permutation, public inputs); `wire_shares[p]`:
+        party p's share of its wire table.  Returns (PlonkProof, ProofLinkingHint) — opened."""
+        from . import collaborative as co
+        srs = system_srs()
+        be = co.DeviceBackend(srs.ctx, srs.powers_of_g)
+        parties = len(wire_shares)
+        if blinder_shares is None:
+            blinder_shares = co.share_table(draw_blinders(rng), parties, seed=int.from_bytes(os.urandom(8), "little"))
+        try:
+            cpk = co.CollaborativeProvingKey.build(be, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+            proof, hint, _ = co.MultiproverPlonkKzgSnark.prove_with_link_hint(be, cpk, wire_shares, circ.pub_inputs, blinder_shares)
+        except _lib.B200Error as e:
+            raise ProverError("Plonk", e) from e
+        return proof, hint
+
+    @classmethod
+    def verify(cls, statement, proof: PlonkProof) -> None:
+        cls.BaseCircuit.verify(statement, proof)
+
+
+def multiprover_prove_with_hint(circuit: type, circ, wire_shares, blinder_shares=None, rng=None):
+    return circuit.prove_with_link_hint(circ, wire_shares, blinder_shares, rng)
+
+
+def multiprover_prove_and_verify(circuit: type, witness, statement, parties: int = 2, rng=None) -> None:
+    """lib.rs:166-177: prove collaboratively, open, verify under the base circuit's verifying key."""
+    circ, shares = circuit.share_witness_table(witness, statement, parties)
+    proof, _ = circuit.prove_with_link_hint(circ, shares, rng=rng)
+    try:
+        circuit.verify(statement, proof)
+    except VerifierError as e:
+        raise ProverError("Verification", e) from e

@@ -327,6 +327,22 @@ __global__ void k_any_nonzero(const fe* __restrict__ v, size_t count, uint32_t* 
         if (!fe_is_zero(fe_load_ro(v + i))) atomicOr(flag, 1u);
 }
 
+
+// ---- element-wise Fr vector primitives (the collaborative prover's share arithmetic) ------------------------------
+// out[i] = a[i] (op) b[i]  or  a[i] (op) b[0] when b is a scalar; op: 0 add, 1 sub, 2 mul
+__global__ void k_fr_vec_op(int op, const fe* __restrict__ a, const fe* __restrict__ b, int b_scalar, size_t n, fe* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe x = fe_load(a + i), y = fe_load(b + (b_scalar ? 0 : i));
+    fe r;
+    switch (op) {
+        case 0: r = FADD(x, y); break;
+        case 1: r = FSUB(x, y); break;
+        default: r = FMUL(x, y); break;
+    }
+    fe_store(out + i, r);
+}
+
 struct SplitArgs {
     fe b[4];
 };
@@ -1150,6 +1166,81 @@ int b200_plonk_prove(b200_ctx* ctx, const b200_pk* pk, const uint64_t* wires, co
     return prove(&ctx->c, pk->pk, reinterpret_cast<const fe*>(wires), reinterpret_cast<const fe*>(pub_inputs),
                  reinterpret_cast<const fe*>(blinders), reinterpret_cast<ProofOut*>(proof),
                  reinterpret_cast<fe*>(link_poly), reinterpret_cast<fe*>(challenges));
+    B200_CATCH
+}
+
+
+/* ---- device-vector primitives (collaborative prover) ---------------------------------------------------------- */
+int b200_fr_vec_op(b200_ctx* ctx, int op, const void* d_a, const void* d_b, int b_is_scalar, size_t n, void* d_out) {
+    B200_TRY
+    if (!ctx || op < 0 || op > 2 || (n && (!d_a || !d_b || !d_out))) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    B200_LAUNCH(k_fr_vec_op, grid_for(n, 256), 256, 0, ctx->c.stream)(op, reinterpret_cast<const fe*>(d_a), reinterpret_cast<const fe*>(d_b),
+                                                                     b_is_scalar, n, reinterpret_cast<fe*>(d_out));
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_fr_batch_inverse_device(b200_ctx* ctx, void* d_data, size_t n) {
+    B200_TRY
+    if (!ctx || (n && !d_data)) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = ctx->c.ntt_scratch.reserve(n * sizeof(fe));
+    if (rc != B200_OK) return rc;
+    B200_LAUNCH(k_batch_inverse, grid_for((n + 15) / 16, 128), 128, 0, ctx->c.stream)(reinterpret_cast<fe*>(d_data),
+                                                                                      reinterpret_cast<fe*>(ctx->c.ntt_scratch.p), n);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_fr_poly_eval_device(b200_ctx* ctx, const void* d_coeffs, size_t len, const uint64_t z[4], uint64_t out[4]) {
+    B200_TRY
+    if (!ctx || !z || !out || (len && !d_coeffs)) return B200_ERR_INVALID;
+    if (len == 0) {
+        std::memset(out, 0, 32);
+        return B200_OK;
+    }
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    int rc = ctx->c.plonk_ws.reserve((2 * (len / CH + len / CH / CH) + 4 * CH + 64) * sizeof(fe));
+    if (rc != B200_OK) return rc;
+    fe* scr = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
+    fe zz;
+    std::memcpy(&zz, z, 32);
+    const fe* polys[1] = {reinterpret_cast<const fe*>(d_coeffs)};
+    const size_t lens[1] = {len};
+    eval_batch(polys, lens, &zz, 1, scr, scr + 8, ctx->c.stream);
+    B200_CUDA(cudaMemcpyAsync(out, scr, 32, cudaMemcpyDeviceToHost, ctx->c.stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_fr_poly_div_linear_device(b200_ctx* ctx, const void* d_p, size_t len, const uint64_t z[4], void* d_q) {
+    B200_TRY
+    if (!ctx || !z || len < 2 || !d_p || !d_q) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    B200_CUDA(cudaSetDevice(ctx->c.device));
+    const size_t L = len + 8;
+    int rc = ctx->c.plonk_ws.reserve((L + 4 * (L / CH + 4 * CH + 64) + 16) * sizeof(fe));
+    if (rc != B200_OK) return rc;
+    fe* S = reinterpret_cast<fe*>(ctx->c.plonk_ws.p);
+    fe* hscr = S + L;
+    fe* slot = hscr + 4 * (L / CH + 4 * CH + 64);
+    fe zz;
+    std::memcpy(&zz, z, 32);
+    horner_suffix(reinterpret_cast<const fe*>(d_p), len, zz, S, slot, hscr, ctx->c.stream);
+    B200_CUDA(cudaMemcpyAsync(d_q, S + 1, (len - 1) * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->c.stream));  // drop the remainder S[0]
+    B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return B200_OK;
     B200_CATCH
 }
 

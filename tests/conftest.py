@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "examples"))  # host_circuits (caller-side example package)
+sys.path.insert(0, os.path.join(ROOT, "tests"))     # host_backend (test infrastructure)
 
 
 def pytest_configure(config):
