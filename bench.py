@@ -299,6 +299,11 @@ def multi_plan(multi, mbases):
     return {"window_bits": plan[0], "digits": plan[1], "physical_windows": plan[2], "tables": plan[3]}
 
 
+def shared_config(args):
+    """The `config` object BOTH arms print, key for key (the driver compares them)."""
+    return {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": NUM_INPUTS, "circuit": args.circuit}
+
+
 def base_line(args, world):
     return {"metric": METRIC, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -343,7 +348,7 @@ def run_reference(args, rank, world):
     out = base_line(args, args.gpus)
     out.update({
         "impl": "reference", "value": value, "ms_per_step": dt * 1e3,
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": shared_config(args), "sample": sample,
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "restated CPU prover (C + OpenMP; arkworks msm_bigint / radix-2 FFT algorithms, "
                                  "jellyfish TurboPlonk rounds) — not the Rust reference itself"},
@@ -476,6 +481,37 @@ def main():
     dt_e2e = max_over_ranks(time.perf_counter() - t)
     if conc == 1:
         assert bytes(proof) == bytes(proof_e2e)  # same witness + blinders -> identical proof
+    # the same from PAGEABLE host memory (a plain numpy buffer): what an unregistered Rust Vec<Fr> costs
+    p_wires = np.ascontiguousarray(circ.wires, dtype=np.uint64).copy()
+    run_proofs(2 * conc, p_wires.ctypes.data, 0)
+    barrier()
+    t = time.perf_counter()
+    run_proofs(args.steps, p_wires.ctypes.data, args.warmup)
+    barrier()
+    dt_pg = max_over_ranks(time.perf_counter() - t)
+    e2e_pageable = {"value": world * args.steps / dt_pg, "unit": "proofs/s"}
+    # steady state: a K-step run with `conc` in flight ramps up and drains (about one wave of `conc` proofs at each end);
+    # the same loop over >= 200 proofs shows the rate without that edge
+    steady = None
+    if args.steps < 200:
+        ss_steps = 200
+        ss_bl = [synth.splitmix_blinders(77000 + i) for i in range(ss_steps)]
+
+        def run_ss():
+            if conc == 1:
+                for i in range(ss_steps):
+                    prove_raw(ctx, pk, d_wires.data_ptr(), circ.pub_inputs, ss_bl[i])
+                return
+            tks = [pool.submit_prove(pk, d_wires.data_ptr(), circ.pub_inputs, ss_bl[i]) for i in range(ss_steps)]
+            for tk in tks:
+                pool.wait(tk)
+        barrier()
+        t = time.perf_counter()
+        run_ss()
+        barrier()
+        dt_ss = max_over_ranks(time.perf_counter() - t)
+        steady = {"value": world * ss_steps / dt_ss, "unit": "proofs/s", "steps": ss_steps,
+                  "note": "same loop, witness resident in HBM, 200 proofs: the K-step figure above includes ramp-up and drain"}
 
     # ---- kernel-level numbers of the dominant kernel inside a proof --------------------------------------
     # bucket accumulation of the batched commitments, timed with CUDA events on the library's stream
@@ -652,13 +688,17 @@ def main():
     out = base_line(args, world)
     out.update({
         "value": world * args.steps / dt, "ms_per_step": ms_step,
-        "config": {"workload": WORKLOAD, "log_n": LOG_N, "num_inputs": circ.num_inputs, "gates_used": circ.n_gates, "circuit": args.circuit,
-                   "concurrency_per_gpu": conc, "parallelism": "one proof stream per GPU (replicas, no collective)",
-                   "msm_plan": srs.plan,
-                   "l2": "working set > L2: shared key tables 227 MB + SRS window tables 67 MB, plus per proof in flight "
-                         "7 x 12.6 MB extended polynomials and ~100 MB of MSM scratch, vs 126 MB of L2",
-                   "timing": "wall clock around K proofs, barrier + cuda synchronize on both sides, max over ranks; "
-                             "kernel times from CUDA events on the library's stream"},
+        "config": shared_config(args),
+        "run": {"gates_used": circ.n_gates, "concurrency_per_gpu": conc,
+                "parallelism": "one proof stream per GPU (replicas, no collective)", "msm_plan": srs.plan,
+                "l2": "working set > L2: shared key tables 227 MB + SRS window tables 67 MB, plus per proof in flight "
+                      "7 x 12.6 MB extended polynomials and ~100 MB of MSM scratch, vs 126 MB of L2",
+                "timing": "wall clock around K proofs, barrier + cuda synchronize on both sides, max over ranks; "
+                          "kernel times from CUDA events on the library's stream",
+                "host_buffers": "e2e passes the witness table from PINNED host memory (torch pin_memory); `e2e_pageable` "
+                                "passes a plain malloc'd table — what a Rust Vec<Fr> is unless the shim registers it "
+                                "(cudaHostRegister)"},
+        "steady_state": steady, "e2e_pageable": e2e_pageable,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "msm_accumulate_kernel (the 4 batched commitments of every timed proof)",
                      "peak_source": peak_src, "launches_timed": live_launches,
