@@ -43,6 +43,7 @@ from .backend import B200LinkProof, B200Proof, GroupLayout, LinkingHint
 from .fields import BASE_FIELD_MODULUS, SCALAR_FIELD_MODULUS, limbs_to_scalars, scalars_to_limbs
 
 HTTP_BASIC_AUTH_USER = "admin"  # prover_service_client.rs:93
+MAX_BODY_BYTES = 64 << 20
 
 # the 20 paths of prover_service_client.rs:101-147
 ALL_PATHS = [
@@ -266,7 +267,13 @@ class ProverService:
             def do_POST(self):
                 with service._lock:
                     service.stats["requests"] += 1
-                n = int(self.headers.get("Content-Length", "0"))
+                try:
+                    n = int(self.headers.get("Content-Length", "0"))
+                except ValueError:
+                    n = -1
+                if n < 0 or n > MAX_BODY_BYTES:  # the largest request (a private settlement with four link hints) is ~3 MB
+                    self.close_connection = True
+                    return self._send(413, {"error": "request body too large or Content-Length missing"})
                 raw = self.rfile.read(n)
                 if self.headers.get("Authorization") != expect:
                     return self._send(401, {"error": "unauthorized"})
