@@ -265,6 +265,44 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles, srs_host=None,
                                   "private_settlement (n = 2^12)": 1, "link proofs": 4}}
 
 
+def collaborative_leg(pool, ctx, d_srs_ptr, conc, count, srs_host=None, cpu_baseline=False):
+    """VALID MATCH MPC in the metric's own words: the VALID-MATCH-class settlement statement (n = 2^12) proved JOINTLY by two
+    parties holding additive shares of the witness table (renegade_b200/collaborative.py on the device backend: share-wise
+    NTT / MSM, Beaver multiplications for the 26 quotient products and the round-2 products).  Host-orchestrated, one
+    proof at a time; the opened proof must equal the single-prover proof of the same witness and blinders."""
+    import numpy as np
+    from host_circuits import private_settlement as ps
+    from renegade_b200 import collaborative as co
+    from renegade_b200 import synth
+    from renegade_b200.backend import PlonkKzgSnark
+    parties, statement = ps.create_witness_statement(seed=61)
+    circ = ps.IntentAndBalancePrivateSettlementCircuit.build(parties, statement).finalize_for_arithmetization()
+    bases = ctx.load_bases_device(d_srs_ptr, circ.n + 3, window_bits=1)
+    be = co.DeviceBackend(ctx, bases)
+    t = time.perf_counter()
+    cpk = co.CollaborativeProvingKey.build(be, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    setup_s = time.perf_counter() - t
+    bl = synth.splitmix_blinders(4242)
+    shares = co.share_table(np.asarray(circ.wires, dtype=np.uint64).reshape(-1, 4), 2, seed=1)
+    bsh = co.share_table(np.asarray(bl, dtype=np.uint64).reshape(-1, 4), 2, seed=2)
+    co.MultiproverPlonkKzgSnark.prove_with_link_hint(be, cpk, shares, circ.pub_inputs, bsh)  # warm-up
+    ts = []
+    for _ in range(count):
+        t = time.perf_counter()
+        proof, _, fab = co.MultiproverPlonkKzgSnark.prove_with_link_hint(be, cpk, shares, circ.pub_inputs, bsh)
+        ts.append(time.perf_counter() - t)
+    pk = PlonkKzgSnark.preprocess(ctx, bases, circ.log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+    single, _ = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, bl)
+    pk.free()
+    bases.free()
+    ts.sort()
+    return {"statement": "intent_and_balance_private_settlement, n = 2^12, 2 parties", "ms_per_joint_proof": ts[len(ts) // 2] * 1e3,
+            "joint_proofs_per_s": 1.0 / ts[len(ts) // 2], "opened_proof_equals_single_prover_proof": bytes(proof) == bytes(single),
+            "beaver_multiplications": fab.multiplications, "opened_field_elements": fab.opened_elements, "key_setup_s": setup_s,
+            "note": "arithmetic of the protocol with the transport collapsed to in-process sums; host-orchestrated (Python), "
+                    "so the figure is an upper bound on latency, not a tuned throughput"}
+
+
 def run_extras(args):
     """`--extras-only`: the restated statements at their own sizes and the private-match bundle, on device 0, as one JSON
     object on stdout (bench.py's main run calls this in a subprocess)."""
@@ -282,7 +320,8 @@ def run_extras(args):
     ctx.known_dlog_bases_device(SEED_SRS, n_srs, d_srs.data_ptr())
     extras = {}
     srs_host = d_srs.cpu().numpy().view(np.uint64)
-    for key, leg, count in (("real_statements", real_statement_leg, 300), ("private_match_bundle", private_match_bundle_leg, 40)):
+    for key, leg, count in (("real_statements", real_statement_leg, 300), ("private_match_bundle", private_match_bundle_leg, 40),
+                            ("valid_match_mpc_collaborative", collaborative_leg, 5)):
         try:
             extras[key] = leg(pool, ctx, d_srs.data_ptr(), conc, count, srs_host, not args.no_cpu_baseline)
         except Exception as e:
