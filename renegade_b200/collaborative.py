@@ -333,13 +333,13 @@ class MultiproverPlonkKzgSnark:
             tr.append_fr(v)
 
         def blind(poly_p, p: int, idx: Sequence[int], length: int):
-            """poly + (b0 + b1 X + ...) Z_H on party p's share: coefficients j and n + j."""
-            lim = be.to_limbs(poly_p)
-            ints = limbs_to_scalars(lim[:n]) + [0] * (length - n)
-            for j, bi in enumerate(idx):
-                ints[j] = (ints[j] - bl[p][bi]) % R
-                ints[n + j] = (ints[n + j] + bl[p][bi]) % R
-            return be.from_limbs(scalars_to_limbs(ints))
+            """poly + (b0 + b1 X + ...) Z_H on party p's share: coefficient j loses b_j, coefficient n + j gains it.
+            Only the 2 x len(idx) touched coefficients are built on the host."""
+            k = len(idx)
+            head = be.from_limbs(scalars_to_limbs([(R - bl[p][bi]) % R for bi in idx]))
+            tail = be.from_limbs(scalars_to_limbs([bl[p][bi] for bi in idx] + [0] * (length - n - k)))
+            delta = be.concat([head, be.zeros(n - k), tail])
+            return be.add(be.concat([poly_p, be.zeros(length - n)]), delta)
 
         # ---- round 1: wire polynomials (linear) ------------------------------------------------------------------
         wire_polys = [[blind(be.ntt(W[p][i], True, False), p, (2 * i, 2 * i + 1), n + 2) for i in range(NW)] for p in range(P)]
@@ -441,18 +441,17 @@ class MultiproverPlonkKzgSnark:
         total = NW * (n + 1) + 3
         split = [[None] * NW for _ in range(P)]
         for p in range(P):
-            qi = limbs_to_scalars(be.to_limbs(quot_c[p][:total]))
             last = 0
             for i in range(NW):
                 beg = i * (n + 2)
                 end = beg + n + 2 if i < NW - 1 else total
-                part = qi[beg:end]
-                part[0] = (part[0] - last) % R
+                part = quot_c[p][beg:end]                                  # stays on the backend
+                if last:
+                    part = be.sub(part, be.concat([be.scalar(last), be.zeros(end - beg - 1)]))
                 if i < NW - 1:
-                    now = bl[p][13 + i]
-                    part = part + [now]
-                    last = now
-                split[p][i] = be.from_limbs(scalars_to_limbs(part))
+                    last = bl[p][13 + i]
+                    part = be.concat([part, be.scalar(last)])
+                split[p][i] = part
         for i in range(NW):
             xy = opened_commitment([split[p][i] for p in range(P)])
             set_g1(proof.split_quot_poly_comms[i], xy)
