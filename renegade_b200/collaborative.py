@@ -77,6 +77,12 @@ class DeviceBackend:
         self.torch, self.ctx, self.srs, self.lib = torch, ctx, srs, ctx._lib
         self.dev = torch.device("cuda", getattr(ctx, "device", 0) or 0)
 
+    def _sync(self):
+        """torch builds / moves the vectors on ITS stream (zeros, cat, roll, clone, H2D); the library runs on its own
+        non-blocking stream: everything torch has queued must be complete before a pointer is handed over.  The library's
+        calls synchronise their stream before returning, so the other direction needs nothing."""
+        self.torch.cuda.current_stream(self.dev).synchronize()
+
     # construction / conversion
     def from_limbs(self, arr: np.ndarray):
         a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
@@ -99,6 +105,7 @@ class DeviceBackend:
 
     def random(self, seed: int, n: int):
         out = self.zeros(n)
+        self._sync()
         self.ctx.splitmix_fr_device(seed, n, out.data_ptr(), montgomery=True)
         return out
 
@@ -106,6 +113,7 @@ class DeviceBackend:
     def _op(self, op: int, a, b):
         scalar = b.shape[0] == 1 and a.shape[0] != 1
         out = self.torch.empty_like(a)
+        self._sync()
         _lib.check(self.lib.b200_fr_vec_op(self.ctx._h, op, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), int(scalar),
                                            a.shape[0], C.c_void_p(out.data_ptr())))
         return out
@@ -124,22 +132,26 @@ class DeviceBackend:
 
     def batch_inverse(self, a):
         out = a.clone()
+        self._sync()
         _lib.check(self.lib.b200_fr_batch_inverse_device(self.ctx._h, C.c_void_p(out.data_ptr()), out.shape[0]))
         return out
 
     def ntt(self, a, inverse: bool, coset: bool):
         out = a.clone()
         log_n = out.shape[0].bit_length() - 1
+        self._sync()
         self.ctx.ntt_device(out.data_ptr(), log_n, inverse=inverse, coset=coset)
         return out
 
     def commit(self, coeffs):
+        self._sync()
         xy, inf = self.ctx.msm_device(self.srs, coeffs.data_ptr(), coeffs.shape[0], montgomery=True)
         return xy, inf
 
     def poly_eval(self, coeffs, z: int) -> int:
         zz = scalars_to_limbs([z])
         out = np.zeros(4, dtype=np.uint64)
+        self._sync()
         _lib.check(self.lib.b200_fr_poly_eval_device(self.ctx._h, C.c_void_p(coeffs.data_ptr()), coeffs.shape[0],
                                                      zz.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return limbs_to_scalars(out.reshape(1, 4))[0]
@@ -147,6 +159,7 @@ class DeviceBackend:
     def div_linear(self, coeffs, z: int):
         zz = scalars_to_limbs([z])
         out = self.zeros(coeffs.shape[0] - 1)
+        self._sync()
         _lib.check(self.lib.b200_fr_poly_div_linear_device(self.ctx._h, C.c_void_p(coeffs.data_ptr()), coeffs.shape[0],
                                                            zz.ctypes.data_as(C.c_void_p), C.c_void_p(out.data_ptr())))
         return out
