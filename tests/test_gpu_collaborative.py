@@ -63,10 +63,12 @@ def test_multiprover_surface_on_the_reference_srs(ctx, srs_2_16, g2_raw):
         single = ct.singleprover_prove(C.BaseCircuit, parties, statement, rng=random.Random(9))
         assert bytes(proof) == bytes(single)
         ct.verify_singleprover_proof(C.BaseCircuit, statement, proof)
-        # a share that is off by one makes the joint witness unsatisfying: refused
+        # shares that are off by one in many places make the joint witness unsatisfying: refused (a single position can
+        # be an unconstrained padding / dummy variable, so every 97th entry of the table is disturbed)
         from renegade_b200.fields import limbs_to_scalars, scalars_to_limbs
         bad = limbs_to_scalars(shares[1])
-        bad[100] = (bad[100] + 1) % ct.SCALAR_FIELD_MODULUS
+        for i in range(0, len(bad), 97):
+            bad[i] = (bad[i] + 1) % ct.SCALAR_FIELD_MODULUS
         with pytest.raises(ct.ProverError):
             ct.multiprover_prove_with_hint(C, circ, [shares[0], scalars_to_limbs(bad)], share_table(bl, 2, seed=6))
     finally:

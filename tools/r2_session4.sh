@@ -15,7 +15,7 @@ done
 for c in 4 6 8 10 12; do
   echo "== concurrency $c"; timeout 300 python bench.py --steps 150 --warmup 5 --no-cpu-baseline --no-msm --no-real-statements --concurrency $c 2>/dev/null | python -c "
 import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print(json.dumps({'concurrency': d['config']['concurrency_per_gpu'], 'proofs_per_s': round(d['value'], 1), 'e2e': round(d['e2e']['value'], 1), 'launches_per_proof': d.get('gpu_launches_per_proof')}))" | tee -a gpurun_out/${T}_concurrency_sweep.log
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print(json.dumps({'concurrency': d['run']['concurrency_per_gpu'], 'proofs_per_s': round(d['value'], 1), 'e2e': round(d['e2e']['value'], 1), 'launches_per_proof': d.get('gpu_launches_per_proof')}))" | tee -a gpurun_out/${T}_concurrency_sweep.log
 done
 echo "== bench"; timeout 1500 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; python -c "
 import json
