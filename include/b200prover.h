@@ -304,6 +304,41 @@ int b200_pool_wait_all(b200_pool* pool);
 /* out = { submitted, completed, failed, queued } */
 int b200_pool_stats(b200_pool* pool, uint64_t out[4]);
 
+/* ---- all GPUs of a box behind one object: prover pools + replicated keys -----------------------
+ * Whole proofs are independent jobs (replicas, one proof stream per GPU, no communication): a
+ * `b200_box` holds one prover pool per device, `b200_box_srs_load` / `b200_box_preprocess` replicate the SRS tables and a
+ * proving key on every device (identical results), and every job goes to the device with the fewest unfinished jobs.
+ * What ONE host process — the relayer's `NativeProofManager` (native_proof_manager.rs:140-201) — needs to use the
+ * whole box.  A ticket encodes its device; tickets are waited for with b200_box_wait. */
+typedef struct b200_box b200_box;
+typedef struct b200_box_srs b200_box_srs;
+typedef struct b200_box_pk b200_box_pk;
+int b200_box_create(const int* devices, int n_dev, unsigned workers_per_device, b200_box** out);
+void b200_box_destroy(b200_box* box);
+int b200_box_devices(const b200_box* box);
+/* Device i's pool (b200_pool_* calls work on it directly). */
+b200_pool* b200_box_pool(b200_box* box, int i);
+int b200_box_srs_load(b200_box* box, const uint8_t* points64, size_t n, int window_bits, int check_on_curve,
+                      b200_box_srs** out);
+void b200_box_srs_free(b200_box* box, b200_box_srs* srs);
+/* b200_plonk_preprocess on every device. */
+int b200_box_preprocess(b200_box* box, const b200_box_srs* srs, unsigned log_n, size_t num_inputs,
+                        const uint64_t* selectors_evals, const uint64_t* perm, const uint64_t* k, b200_box_pk** out);
+int b200_box_pk_verifying_key(const b200_box_pk* pk, uint64_t* selector_comms, uint64_t* sigma_comms);
+void b200_box_pk_free(b200_box* box, b200_box_pk* pk);
+/* b200_pool_submit_prove on the least-loaded device. */
+int b200_box_submit_prove(b200_box* box, const b200_box_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
+                          size_t num_inputs, const uint64_t* blinders, b200_proof* proof, uint64_t* link_poly,
+                          uint64_t* ticket);
+/* b200_pool_submit_bundle on the least-loaded device: `pks[i]` is the box key of proofs[i] (the `pk` field of the
+ * entries is ignored); a bundle stays on one device. */
+int b200_box_submit_bundle(b200_box* box, const b200_box_srs* srs, const b200_box_pk* const* pks,
+                           const b200_bundle_proof* proofs, size_t n_proofs, const b200_bundle_link* links,
+                           size_t n_links, uint64_t* ticket);
+int b200_box_wait(b200_box* box, uint64_t ticket);
+/* Index (into the `devices` array) of the device a ticket ran on, -1 for a bad ticket. */
+int b200_box_ticket_device(const b200_box* box, uint64_t ticket);
+
 /* ---- multi-GPU: one MSM sharded over the GPUs of a box (boundary B1's
  * `b200_init(const int* devs, int n_dev, ...)`) ----------------------------------------------------
  * Rank g of W owns the points [g n / W, (g + 1) n / W) (b200_shard_range) with resident window tables

@@ -28,6 +28,9 @@ EXPORTS = [
     "b200_poseidon2_hash_batch", "b200_poseidon2_permute_batch", "b200_poseidon2_merkle_root_batch", "b200_poseidon2_csprng_batch",
     "b200_pool_create", "b200_pool_destroy", "b200_pool_workers", "b200_pool_ctx", "b200_pool_submit_prove",
     "b200_pool_submit_link", "b200_pool_submit_bundle", "b200_pool_wait", "b200_pool_wait_all", "b200_pool_stats",
+    "b200_box_create", "b200_box_destroy", "b200_box_devices", "b200_box_pool", "b200_box_srs_load", "b200_box_srs_free",
+    "b200_box_preprocess", "b200_box_pk_verifying_key", "b200_box_pk_free", "b200_box_submit_prove", "b200_box_submit_bundle",
+    "b200_box_wait", "b200_box_ticket_device",
     "b200_shard_range", "b200_multi_init", "b200_nccl_unique_id", "b200_multi_init_rank", "b200_multi_shutdown",
     "b200_nccl_version", "b200_multi_world", "b200_multi_local_devices", "b200_multi_ctx", "b200_multi_rank",
     "b200_multi_bases_load", "b200_multi_bases_known_dlog", "b200_multi_bases_free", "b200_multi_bases_len",
@@ -120,6 +123,23 @@ def load() -> C.CDLL:
     lib.b200_pool_wait.argtypes = [vp, u64]
     lib.b200_pool_wait_all.argtypes = [vp]
     lib.b200_pool_stats.argtypes = [vp, C.POINTER(u64 * 4)]
+    lib.b200_box_create.argtypes = [C.POINTER(i32), i32, u32, C.POINTER(vp)]
+    lib.b200_box_destroy.argtypes = [vp]
+    lib.b200_box_destroy.restype = None
+    lib.b200_box_devices.argtypes = [vp]
+    lib.b200_box_pool.argtypes = [vp, i32]
+    lib.b200_box_pool.restype = vp
+    lib.b200_box_srs_load.argtypes = [vp, vp, sz, i32, i32, C.POINTER(vp)]
+    lib.b200_box_srs_free.argtypes = [vp, vp]
+    lib.b200_box_srs_free.restype = None
+    lib.b200_box_preprocess.argtypes = [vp, vp, u32, sz, vp, vp, vp, C.POINTER(vp)]
+    lib.b200_box_pk_verifying_key.argtypes = [vp, vp, vp]
+    lib.b200_box_pk_free.argtypes = [vp, vp]
+    lib.b200_box_pk_free.restype = None
+    lib.b200_box_submit_prove.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, C.POINTER(u64)]
+    lib.b200_box_submit_bundle.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.POINTER(u64)]
+    lib.b200_box_wait.argtypes = [vp, u64]
+    lib.b200_box_ticket_device.argtypes = [vp, u64]
     lib.b200_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
     lib.b200_shard_range.restype = None
     lib.b200_multi_init.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]

@@ -660,3 +660,73 @@ class ProverPool:
             self.close()
         except Exception:
             pass
+
+
+class ProverBox:
+    """`b200_box`: every GPU of the box behind one object — one prover pool per device, the SRS tables and the proving
+    keys replicated on each, jobs routed to the least-loaded device.  The single-process counterpart of running one
+    `ProverPool` per rank under torchrun."""
+
+    def __init__(self, devices, workers_per_device: int = 6):
+        self._lib = _lib.load()
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_box_create(arr, len(devices), workers_per_device, C.byref(h)))
+        self._h, self._keep, self.devices = h, {}, list(devices)
+
+    def load_srs(self, points: np.ndarray, window_bits: int = 0, check_on_curve: bool = False):
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_box_srs_load(self._h, _ptr(pts), pts.shape[0], window_bits, int(check_on_curve), C.byref(h)))
+        return h
+
+    def preprocess(self, srs, log_n: int, num_inputs: int, selectors: np.ndarray, perm: np.ndarray, k: np.ndarray):
+        sel = np.ascontiguousarray(selectors, dtype=np.uint64).reshape(13, 1 << log_n, 4)
+        pm = np.ascontiguousarray(perm, dtype=np.uint64).reshape(5 << log_n)
+        kk = np.ascontiguousarray(k, dtype=np.uint64).reshape(5, 4)
+        h = C.c_void_p()
+        _lib.check(self._lib.b200_box_preprocess(self._h, srs, log_n, num_inputs, _ptr(sel), _ptr(pm), _ptr(kk), C.byref(h)))
+        return h
+
+    def verifying_key(self, pk):
+        sel, sig = np.zeros((13, 8), dtype=np.uint64), np.zeros((5, 8), dtype=np.uint64)
+        _lib.check(self._lib.b200_box_pk_verifying_key(pk, _ptr(sel), _ptr(sig)))
+        return sel, sig
+
+    def submit_prove(self, pk, wires_ptr: int, pub_inputs: np.ndarray, blinders: np.ndarray, log_n: int = 0, keep=None) -> int:
+        proof = B200Proof()
+        pi = np.ascontiguousarray(pub_inputs, dtype=np.uint64)
+        bl = np.ascontiguousarray(blinders, dtype=np.uint64)
+        link = np.zeros(((1 << log_n) + 2, 4), dtype=np.uint64) if log_n else None
+        ticket = C.c_uint64()
+        _lib.check(self._lib.b200_box_submit_prove(self._h, pk, C.c_void_p(wires_ptr), _ptr(pi) if pi.size else None, pi.size // 4,
+                                                   _ptr(bl), C.byref(proof), _ptr(link) if link is not None else None,
+                                                   C.byref(ticket)))
+        self._keep[ticket.value] = (proof, link, keep, pi, bl)
+        return ticket.value
+
+    def wait(self, ticket: int):
+        rc = self._lib.b200_box_wait(self._h, ticket)
+        proof, link, *_ = self._keep.pop(ticket, (None, None))
+        _lib.check(rc)
+        return (proof, link) if link is not None else proof
+
+    def ticket_device(self, ticket: int) -> int:
+        return self._lib.b200_box_ticket_device(self._h, ticket)
+
+    def free_pk(self, pk):
+        self._lib.b200_box_pk_free(self._h, pk)
+
+    def free_srs(self, srs):
+        self._lib.b200_box_srs_free(self._h, srs)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200_box_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -383,3 +383,189 @@ int b200_pool_stats(b200_pool* pool, uint64_t out[4]) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole box behind one object: one prover pool per device, the SRS tables and proving keys replicated on every
+// device (whole proofs do not shard: SURVEY.md §8(e) "independent jobs => replicas, one proof stream per GPU, no
+// communication"), each job routed to the device with the fewest unfinished jobs.  What a single Rust host process
+// (the relayer's `NativeProofManager`) needs to use all GPUs without managing devices itself.
+// ---------------------------------------------------------------------------------------------------------------
+struct b200_box {
+    std::vector<int> devices;
+    std::vector<b200_pool*> pools;
+};
+struct b200_box_srs {
+    std::vector<b200_bases*> per_dev;
+};
+struct b200_box_pk {
+    std::vector<b200_pk*> per_dev;
+};
+
+namespace {
+constexpr int kBoxTicketShift = 48;  // ticket = device index << 48 | the device pool's ticket
+
+int box_least_loaded(b200_box* box) {
+    int best = 0;
+    uint64_t best_load = ~0ull;
+    for (size_t i = 0; i < box->pools.size(); ++i) {
+        uint64_t st[4];
+        if (b200_pool_stats(box->pools[i], st) != B200_OK) continue;
+        const uint64_t load = st[0] - st[1];  // submitted - completed
+        if (load < best_load) {
+            best_load = load;
+            best = (int)i;
+        }
+    }
+    return best;
+}
+}  // namespace
+
+extern "C" {
+
+void b200_box_destroy(b200_box* box) {
+    if (!box) return;
+    for (b200_pool* p : box->pools) b200_pool_destroy(p);
+    delete box;
+}
+
+int b200_box_create(const int* devices, int n_dev, unsigned workers_per_device, b200_box** out) {
+    B200_TRY
+    if (!devices || n_dev <= 0 || n_dev > 64 || !out) {
+        b200::set_error("box_create: need 1..64 device ordinals");
+        return B200_ERR_INVALID;
+    }
+    std::unique_ptr<b200_box> box(new b200_box());
+    for (int i = 0; i < n_dev; ++i) {
+        b200_pool* p = nullptr;
+        const int rc = b200_pool_create(devices[i], workers_per_device, &p);
+        if (rc != B200_OK) {
+            b200_box_destroy(box.release());
+            return rc;
+        }
+        box->devices.push_back(devices[i]);
+        box->pools.push_back(p);
+    }
+    *out = box.release();
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_box_devices(const b200_box* box) { return box ? (int)box->pools.size() : 0; }
+b200_pool* b200_box_pool(b200_box* box, int i) {
+    if (!box || i < 0 || i >= (int)box->pools.size()) return nullptr;
+    return box->pools[i];
+}
+
+void b200_box_srs_free(b200_box* box, b200_box_srs* srs) {
+    if (!srs) return;
+    for (size_t i = 0; i < srs->per_dev.size(); ++i)
+        if (srs->per_dev[i]) b200_bases_free(box && i < box->pools.size() ? b200_pool_ctx(box->pools[i], 0) : nullptr, srs->per_dev[i]);
+    delete srs;
+}
+
+int b200_box_srs_load(b200_box* box, const uint8_t* points64, size_t n, int window_bits, int check_on_curve, b200_box_srs** out) {
+    B200_TRY
+    if (!box || !points64 || !out) return B200_ERR_INVALID;
+    std::unique_ptr<b200_box_srs> s(new b200_box_srs());
+    s->per_dev.assign(box->pools.size(), nullptr);
+    for (size_t i = 0; i < box->pools.size(); ++i) {
+        // the on-curve assertion of srs.rs:178-179 once is enough: every device gets the same bytes
+        const int rc = b200_bases_load(b200_pool_ctx(box->pools[i], 0), points64, n, window_bits, i == 0 ? check_on_curve : 0, &s->per_dev[i]);
+        if (rc != B200_OK) {
+            b200_box_srs_free(box, s.release());
+            return rc;
+        }
+    }
+    *out = s.release();
+    return B200_OK;
+    B200_CATCH
+}
+
+void b200_box_pk_free(b200_box* box, b200_box_pk* pk) {
+    if (!pk) return;
+    for (size_t i = 0; i < pk->per_dev.size(); ++i)
+        if (pk->per_dev[i]) b200_pk_free(box && i < box->pools.size() ? b200_pool_ctx(box->pools[i], 0) : nullptr, pk->per_dev[i]);
+    delete pk;
+}
+
+int b200_box_preprocess(b200_box* box, const b200_box_srs* srs, unsigned log_n, size_t num_inputs, const uint64_t* selectors_evals,
+                        const uint64_t* perm, const uint64_t* k, b200_box_pk** out) {
+    B200_TRY
+    if (!box || !srs || !out || srs->per_dev.size() != box->pools.size()) return B200_ERR_INVALID;
+    std::unique_ptr<b200_box_pk> pk(new b200_box_pk());
+    pk->per_dev.assign(box->pools.size(), nullptr);
+    for (size_t i = 0; i < box->pools.size(); ++i) {
+        const int rc = b200_plonk_preprocess(b200_pool_ctx(box->pools[i], 0), srs->per_dev[i], log_n, num_inputs, selectors_evals, perm, k,
+                                             &pk->per_dev[i]);
+        if (rc != B200_OK) {
+            b200_box_pk_free(box, pk.release());
+            return rc;
+        }
+    }
+    *out = pk.release();
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_box_pk_verifying_key(const b200_box_pk* pk, uint64_t* selector_comms, uint64_t* sigma_comms) {
+    if (!pk || pk->per_dev.empty()) return B200_ERR_INVALID;
+    return b200_pk_verifying_key(pk->per_dev[0], selector_comms, sigma_comms);  // identical on every device
+}
+
+int b200_box_submit_prove(b200_box* box, const b200_box_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs, size_t num_inputs,
+                          const uint64_t* blinders, b200_proof* proof, uint64_t* link_poly, uint64_t* ticket) {
+    B200_TRY
+    if (!box || !pk || !ticket || pk->per_dev.size() != box->pools.size()) {
+        b200::set_error("box_submit_prove: null argument or key of another box");
+        return B200_ERR_INVALID;
+    }
+    const int d = box_least_loaded(box);
+    uint64_t t = 0;
+    const int rc = b200_pool_submit_prove(box->pools[d], pk->per_dev[d], wires, pub_inputs, num_inputs, blinders, proof, link_poly, &t);
+    if (rc != B200_OK) return rc;
+    *ticket = ((uint64_t)d << kBoxTicketShift) | t;
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_box_submit_bundle(b200_box* box, const b200_box_srs* srs, const b200_box_pk* const* pks, const b200_bundle_proof* proofs,
+                           size_t n_proofs, const b200_bundle_link* links, size_t n_links, uint64_t* ticket) {
+    B200_TRY
+    if (!box || !pks || !proofs || n_proofs == 0 || !ticket || (n_links && !srs)) {
+        b200::set_error("box_submit_bundle: null argument");
+        return B200_ERR_INVALID;
+    }
+    const int d = box_least_loaded(box);  // a bundle stays on one device: its link proofs need its proofs' polynomials
+    std::vector<b200_bundle_proof> local(proofs, proofs + n_proofs);
+    for (size_t i = 0; i < n_proofs; ++i) {
+        if (!pks[i] || pks[i]->per_dev.size() != box->pools.size()) {
+            b200::set_error("box_submit_bundle: missing key");
+            return B200_ERR_INVALID;
+        }
+        local[i].pk = pks[i]->per_dev[d];
+    }
+    uint64_t t = 0;
+    const int rc = b200_pool_submit_bundle(box->pools[d], srs ? srs->per_dev[d] : nullptr, local.data(), n_proofs, links, n_links, &t);
+    if (rc != B200_OK) return rc;
+    *ticket = ((uint64_t)d << kBoxTicketShift) | t;
+    return B200_OK;
+    B200_CATCH
+}
+
+int b200_box_wait(b200_box* box, uint64_t ticket) {
+    B200_TRY
+    const uint64_t d = ticket >> kBoxTicketShift;
+    if (!box || d >= box->pools.size()) {
+        b200::set_error("box_wait: bad ticket");
+        return B200_ERR_INVALID;
+    }
+    return b200_pool_wait(box->pools[d], ticket & (((uint64_t)1 << kBoxTicketShift) - 1));
+    B200_CATCH
+}
+
+int b200_box_ticket_device(const b200_box* box, uint64_t ticket) {
+    const uint64_t d = ticket >> kBoxTicketShift;
+    return box && d < box->pools.size() ? (int)d : -1;
+}
+
+}  // extern "C"

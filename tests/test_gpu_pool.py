@@ -215,3 +215,38 @@ def test_pool_bundle_one_ticket_for_proofs_and_links(ctx, oracle, pyoracle):
             pk.free()
     finally:
         pool.close()
+
+
+def test_box_routes_jobs_over_devices_with_replicated_keys(ctx, oracle, pyoracle):
+    """`b200_box`: a pool per device, SRS and keys replicated, jobs to the least-loaded device.  On a one-GPU box the two
+    "devices" are the same GPU twice — the routing, replication and ticket logic are what is checked: every proof equals
+    the single-context proof, both pools get work, the verifying key is the same on every device."""
+    import torch
+    from renegade_b200.backend import ProverBox
+    devices = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    log_n = 11
+    circ, tau, srs = make(ctx, oracle, pyoracle, log_n, seed=71)
+    box = ProverBox(devices, workers_per_device=2)
+    try:
+        bsrs = box.load_srs(srs, check_on_curve=True)
+        pk = box.preprocess(bsrs, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+        bases = ctx.load_bases(srs)
+        spk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+        sel, sig = box.verifying_key(pk)
+        assert (sel == spk.selector_comms).all() and (sig == spk.sigma_comms).all()
+        wires = np.ascontiguousarray(circ.wires, dtype=np.uint64)
+        bl = [synth.splitmix_blinders(700 + i) for i in range(12)]
+        tickets = [box.submit_prove(pk, wires.ctypes.data, circ.pub_inputs, b, keep=wires) for b in bl]
+        used = {box.ticket_device(t) for t in tickets}
+        assert used == {0, 1}                               # 12 jobs over 2 x 2 workers: both pools took some
+        for t, b in zip(tickets, bl):
+            proof = box.wait(t)
+            single, _ = PlonkKzgSnark.prove_with_link_hint(ctx, spk, circ.wires, circ.pub_inputs, b)
+            assert bytes(proof) == bytes(single)
+        with pytest.raises(B200Error):
+            box.wait(tickets[0])                            # a ticket is consumed by its wait
+        box.free_pk(pk)
+        box.free_srs(bsrs)
+        spk.free()
+    finally:
+        box.close()
