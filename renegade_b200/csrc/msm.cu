@@ -679,10 +679,14 @@ MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
         double cost;
         if (!latency_mode) {
             // THROUGHPUT: Fq-product equivalents at the measured 66.7 G/s — 9.5 per bucket addition, ~1.6 per digit for
-            // the sort (more with a short top digit), 2 full additions (12.5) + the bit-sum pass per bucket in the
-            // reduction.  With several proofs in flight this, not the chain length, is what a proof costs the GPU: at
+            // the sort (more with a short top digit), 2 full additions (12.5 each) per bucket in the reduction.  With several proofs in flight this, not the chain length, is what a proof costs the GPU: at
             // n = 2^13 the latency-optimal c = 16 spends as much on reducing 2^15 buckets as on filling them.
-            cost = (nw * (9.5 + 1.6 * (1.0 + 0.3 * shrt)) + (double)((size_t)1 << (c - 1)) * 32.0) / 66.7e6;
+            // Buckets with more than 32 entries are cut into segments whose sums are added up afterwards: with a Poisson
+            // load of nw / buckets that is about max(0, load / 32 - 0.55) extra full additions per bucket (load 32 -> 0.45).
+            // Checked against the pool at n = 2^16: c = 17 (288 proofs/s) beats c = 16 (281), profiles/r2c_bench.json vs r2d.
+            const double buckets = (double)((size_t)1 << (c - 1));
+            const double extra_segs = std::max(0.0, nw / 32.0 - 0.55 * buckets);
+            cost = (nw * (9.5 + 1.6 * (1.0 + 0.3 * shrt)) + buckets * 25.0 + extra_segs * 12.5) / 66.7e6;
         } else {
             // LATENCY: a dependent curve addition costs a warp ~4-6 us of multiplier-pipe time, so at the prover's sizes
             // every phase is a chain:
