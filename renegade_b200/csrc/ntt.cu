@@ -17,6 +17,8 @@
 //     the n^-1 factor are fused into the first load / last store.
 // The kernel is bound by the integer-multiply pipe (≈ log2(n)/2 Montgomery products per
 // element), not by HBM: see DESIGN.md for the roofline.
+#include <cstdlib>
+
 #include "device_ctx.h"
 #include "ff.cuh"
 
@@ -42,58 +44,37 @@ struct PassArgs {
     size_t batch_stride;  // elements between consecutive transforms of a batch
 };
 
-// 80 registers -> 3 resident blocks per SM.  Forcing 4 (64 registers, 84 B of spills) was measured slower:
-// 2^20 forward 234 us vs 216 us (profiles/r1o_ntt_occupancy.log).
+struct TileGeom {
+    int E, t_log, q_log;
+    uint32_t T_mask, Q_mask, lo_mask;
+};
+__device__ __forceinline__ TileGeom tile_geom(const PassArgs& a) {
+    TileGeom g;
+    g.E = 1 << a.e_log;
+    g.t_log = a.hi - a.lo;              // sub-transform size 2^t_log
+    g.q_log = a.e_log - g.t_log;        // sub-transforms per tile
+    g.T_mask = (1u << g.t_log) - 1u;
+    g.Q_mask = (1u << g.q_log) - 1u;
+    g.lo_mask = (1u << a.lo) - 1u;
+    return g;
+}
+// element e of the tile starting at sub-transform q_base: its index in the vector and its slot in shared memory
+__device__ __forceinline__ void tile_slot(const PassArgs& a, const TileGeom& g, uint32_t q_base, uint32_t e, size_t* idx, uint32_t* pos) {
+    uint32_t qq, m;
+    if (a.lo == 0) { qq = e >> g.t_log; m = e & g.T_mask; }   // idx = q*T + m : contiguous in e
+    else           { m = e >> g.q_log; qq = e & g.Q_mask; }   // adjacent sub-transforms adjacent
+    const uint32_t q = q_base + qq;
+    *idx = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & g.lo_mask);
+    *pos = (m << g.q_log) | qq;
+}
+
+// butterfly stages of this pass on the tile held in (plane_lo, plane_hi), then the scatter to `out`
 template <bool FINAL>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
-    extern __shared__ uint4 smem[];
-    const int E = 1 << a.e_log;
-    uint4* plane_lo = smem;
-    uint4* plane_hi = smem + E;
-
-    const int t_log = a.hi - a.lo;    // sub-transform size 2^t_log
-    const int q_log = a.e_log - t_log;  // sub-transforms per tile
-    const uint32_t T_mask = (1u << t_log) - 1u;
-    const uint32_t Q_mask = (1u << q_log) - 1u;
-    const uint32_t lo_mask = (1u << a.lo) - 1u;
-    const uint32_t q_base = blockIdx.x << q_log;
-    const fe* in = a.in + (size_t)blockIdx.y * a.batch_stride;
-    fe* out = a.out + (size_t)blockIdx.y * a.batch_stride;
-
-    // ---- gather the tile -------------------------------------------------------------------
-    // a thread's (up to) four elements are all requested before the first one is consumed: one trip to L2 / HBM per
-    // tile instead of four dependent ones
-    {
-        fe v[4];
-        uint32_t pos[4];
-        size_t gidx[4];
-        const uint32_t per = ((uint32_t)E + blockDim.x - 1) / blockDim.x;  // <= 4 (E <= 1024, blockDim = min(E / 2, 256) >= E / 4)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t e = threadIdx.x + (uint32_t)k * blockDim.x;
-            if ((uint32_t)k < per && e < (uint32_t)E) {
-                uint32_t qq, m;
-                if (a.lo == 0) { qq = e >> t_log; m = e & T_mask; }   // idx = q*T + m : contiguous in e
-                else           { m = e >> q_log; qq = e & Q_mask; }   // adjacent sub-transforms adjacent
-                const uint32_t q = q_base + qq;
-                gidx[k] = ((size_t)(q >> a.lo) << a.hi) | ((size_t)m << a.lo) | (q & lo_mask);
-                pos[k] = (m << q_log) | qq;
-                v[k] = fe_load(in + gidx[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t e = threadIdx.x + (uint32_t)k * blockDim.x;
-            if ((uint32_t)k < per && e < (uint32_t)E) {
-                fe x = v[k];
-                if (a.pre) x = fe_mul<FrCfg>(x, fe_load_ro(a.pre + gidx[k]));
-                plane_lo[pos[k]] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
-                plane_hi[pos[k]] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
-            }
-        }
-    }
-    __syncthreads();
-
+__device__ __forceinline__ void tile_compute(const PassArgs& a, const TileGeom& g, uint4* plane_lo, uint4* plane_hi, uint32_t q_base,
+                                             fe* out) {
+    const int E = g.E, t_log = g.t_log, q_log = g.q_log;
+    const uint32_t T_mask = g.T_mask, Q_mask = g.Q_mask, lo_mask = g.lo_mask;
+    (void)T_mask;
     // ---- butterflies, two stages per shared-memory round trip (radix 4 in registers) ----------
     // stage s pairs indices 2^s apart: (x0, x1) -> (x0 + x1, (x0 - x1) * w^(j * n / 2^(s+1))), j = idx mod 2^s.
     auto lds = [&](uint32_t pos) {
@@ -200,6 +181,116 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     }
 }
 
+// 80 registers -> 3 resident blocks per SM.  Forcing 4 (64 registers, 84 B of spills) was measured slower:
+// 2^20 forward 234 us vs 216 us (profiles/r1o_ntt_occupancy.log).
+template <bool FINAL>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
+    extern __shared__ uint4 smem[];
+    const TileGeom g = tile_geom(a);
+    const int E = g.E;
+    uint4* plane_lo = smem;
+    uint4* plane_hi = smem + E;
+    const uint32_t q_base = blockIdx.x << g.q_log;
+    const fe* in = a.in + (size_t)blockIdx.y * a.batch_stride;
+    fe* out = a.out + (size_t)blockIdx.y * a.batch_stride;
+
+    // ---- gather the tile -------------------------------------------------------------------
+    // a thread's (up to) four elements are all requested before the first one is consumed: one trip to L2 / HBM per
+    // tile instead of four dependent ones
+    {
+        fe v[4];
+        uint32_t pos[4];
+        size_t gidx[4];
+        const uint32_t per = ((uint32_t)E + blockDim.x - 1) / blockDim.x;  // <= 4 (E <= 1024, blockDim = min(E / 2, 256) >= E / 4)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = threadIdx.x + (uint32_t)k * blockDim.x;
+            if ((uint32_t)k < per && e < (uint32_t)E) {
+                tile_slot(a, g, q_base, e, &gidx[k], &pos[k]);
+                v[k] = fe_load(in + gidx[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = threadIdx.x + (uint32_t)k * blockDim.x;
+            if ((uint32_t)k < per && e < (uint32_t)E) {
+                fe x = v[k];
+                if (a.pre) x = fe_mul<FrCfg>(x, fe_load_ro(a.pre + gidx[k]));
+                plane_lo[pos[k]] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+                plane_hi[pos[k]] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+            }
+        }
+    }
+    __syncthreads();
+    tile_compute<FINAL>(a, g, plane_lo, plane_hi, q_base, out);
+}
+
+// Persistent variant (overlap the loads with the butterflies): a block walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened (transform, tile) space; the NEXT tile is fetched with
+// `cp.async` (LDGSTS, 16 bytes per copy: the gather of an upper pass is 1024 separate 32-byte sectors 32 KB apart, so
+// neither a 1-D bulk copy nor a TMA box applies) into the other half of a double buffer while the current tile runs its
+// butterflies.  Selected with B200_NTT_PERSISTENT=1; measured against the one-tile-per-block kernel in
+// profiles/r2f_ntt_persistent_ab.log.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+template <bool FINAL>
+__global__ void __launch_bounds__(256) ntt_pass_persistent_kernel(PassArgs a, uint32_t tiles_per_transform, uint32_t total_tiles) {
+    extern __shared__ uint4 smem[];
+    const TileGeom g = tile_geom(a);
+    const int E = g.E;
+    auto issue = [&](uint32_t tile, int buf) {
+        const uint32_t batch = tile / tiles_per_transform, q_base = (tile % tiles_per_transform) << g.q_log;
+        const fe* in = a.in + (size_t)batch * a.batch_stride;
+        uint4* lo = smem + (size_t)buf * 2 * E;
+        uint4* hi = lo + E;
+        for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
+            size_t idx;
+            uint32_t pos;
+            tile_slot(a, g, q_base, e, &idx, &pos);
+            const uint4* src = reinterpret_cast<const uint4*>(in + idx);
+            cp_async_16(lo + pos, src);
+            cp_async_16(hi + pos, src + 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t tile = blockIdx.x;
+    int cur = 0;
+    if (tile < total_tiles) issue(tile, cur);
+    for (; tile < total_tiles; tile += gridDim.x) {
+        const uint32_t next = tile + gridDim.x;
+        if (next < total_tiles) {
+            issue(next, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const uint32_t batch = tile / tiles_per_transform, q_base = (tile % tiles_per_transform) << g.q_log;
+        uint4* lo = smem + (size_t)cur * 2 * E;
+        uint4* hi = lo + E;
+        if (a.pre) {  // coset factor g^i of the first pass, applied in shared memory
+            for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
+                size_t idx;
+                uint32_t pos;
+                tile_slot(a, g, q_base, e, &idx, &pos);
+                const uint4 u = lo[pos], v = hi[pos];
+                fe x;
+                x.l[0] = u.x; x.l[1] = u.y; x.l[2] = u.z; x.l[3] = u.w;
+                x.l[4] = v.x; x.l[5] = v.y; x.l[6] = v.z; x.l[7] = v.w;
+                x = fe_mul<FrCfg>(x, fe_load_ro(a.pre + idx));
+                lo[pos] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+                hi[pos] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+            }
+            __syncthreads();
+        }
+        tile_compute<FINAL>(a, g, lo, hi, q_base, a.out + (size_t)batch * a.batch_stride);
+        __syncthreads();  // the buffer is refilled two iterations from now; all reads of it are done here
+        cur ^= 1;
+    }
+}
+
 // table[i] = base^i (Montgomery), i < n: thread i multiplies the pow2[b] = base^(2^b) it needs
 struct PowArgs {
     fe pow2[32];
@@ -255,7 +346,9 @@ int domain_create(unsigned log_n, cudaStream_t st, Domain** out) {
     // every domain is created on its context's device, under that context's lock: the opt-in for the tile's
     // shared memory is (re)applied here, per device, instead of behind a process-wide flag
     if (cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess ||
-        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess)
+        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess ||
+        cudaFuncSetAttribute(ntt_pass_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << kTileLog) != cudaSuccess ||
+        cudaFuncSetAttribute(ntt_pass_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << kTileLog) != cudaSuccess)
         return B200_ERR_CUDA;
     Domain* d = new Domain();
     d->log_n = log_n;
@@ -328,8 +421,19 @@ int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, u
         if (threads < 32) threads = 32;
         dim3 grid((unsigned)(((size_t)1 << L) >> e_log), batch);
         const size_t smem = (size_t)E * 32;
-        if (final_pass) B200_LAUNCH(ntt_pass_kernel<true>, grid, threads, smem, st)(a);
-        else B200_LAUNCH(ntt_pass_kernel<false>, grid, threads, smem, st)(a);
+        static const bool persistent = [] {
+            const char* e = std::getenv("B200_NTT_PERSISTENT");
+            return e && e[0] == '1';
+        }();
+        const uint32_t tiles_per = grid.x, total = tiles_per * batch;
+        if (persistent && E == 1024 && total > 296) {  // more tiles than resident blocks (148 SMs x 2 at ~100 registers): walk them
+            if (final_pass) B200_LAUNCH(ntt_pass_persistent_kernel<true>, 296, threads, 2 * smem, st)(a, tiles_per, total);
+            else B200_LAUNCH(ntt_pass_persistent_kernel<false>, 296, threads, 2 * smem, st)(a, tiles_per, total);
+        } else if (final_pass) {
+            B200_LAUNCH(ntt_pass_kernel<true>, grid, threads, smem, st)(a);
+        } else {
+            B200_LAUNCH(ntt_pass_kernel<false>, grid, threads, smem, st)(a);
+        }
         hi -= w;
     }
     return cudaGetLastError() == cudaSuccess ? B200_OK : B200_ERR_CUDA;
