@@ -357,7 +357,13 @@ class PlonkCircuit:
 
     def finalize_for_arithmetization(self, min_log_n: int = 2) -> SynthCircuit:
         """Public-input gates first, zero padding to the next power of two, one copy-constraint cycle per variable
-        (upstream: `finalize_for_arithmetization`, traits.rs:847,991).  Returns the flat tables the C ABI takes."""
+        (upstream: `finalize_for_arithmetization`, traits.rs:847,991).  Returns the flat tables the C ABI takes.
+
+        Layout / verifying-key parity with the Rust reference is NOT claimed: this places the public-input gates by a
+        stable partition (io + rest) and uses coset representatives k_i = 5^i, while the un-vendored jellyfish fork may
+        swap gate i with IO gate i and derives k from its own generator.  Proofs made here are self-consistent and
+        verify under the key preprocessed from the same tables; a production host passes the Rust-built selector /
+        permutation tables and `vk.k` through the ABI, so the layout is the reference's."""
         self._check_open()
         io = [r for r in self.rows if r.gate.name == "IoGate"]
         rest = [r for r in self.rows if r.gate.name != "IoGate"]
