@@ -155,9 +155,12 @@ def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps, srs_host=None, cpu_bas
                 for tk in tickets:
                     pool.wait(tk)
             run(2 * conc)
+            l0, h0 = ctx._lib.b200_kernel_launches(), ctx._lib.b200_launch_host_ns()
             t = time.perf_counter()
             run(steps)
             rate = steps / (time.perf_counter() - t)
+            launches = (ctx._lib.b200_kernel_launches() - l0) / steps
+            launch_host_us = (ctx._lib.b200_launch_host_ns() - h0) / steps / 1e3
         cpu = None
         if cpu_baseline:  # the oracle prover on the same tables, SRS and blinders — the only use of oracle/ in this leg
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -175,6 +178,8 @@ def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps, srs_host=None, cpu_bas
                    "bit_exact_vs_gpu": bool(rc == 0 and bytes(oproof) == bytes(gproof))}
         res[name] = {"log_n": circ.log_n, "gates": circ.n_gates, "num_inputs": circ.num_inputs,
                      "ms_one_proof_in_flight": single_ms, "proofs_per_s_e2e": rate, "in_flight": conc, "steps": steps,
+                     "launches_per_proof": launches if pool is not None else None,
+                     "launch_host_us_per_proof": launch_host_us if pool is not None else None,
                      "cpu_baseline": cpu}
         pk.free()
         bases.free()
@@ -322,6 +327,8 @@ def run_extras(args):
     srs_host = d_srs.cpu().numpy().view(np.uint64)
     for key, leg, count in (("real_statements", real_statement_leg, 300), ("private_match_bundle", private_match_bundle_leg, 40),
                             ("valid_match_mpc_collaborative", collaborative_leg, 5)):
+        if key in os.environ.get("B200_BENCH_SKIP_LEGS", "").split(","):  # tools/small_proof_sweep.sh
+            continue
         try:
             extras[key] = leg(pool, ctx, d_srs.data_ptr(), conc, count, srs_host, not args.no_cpu_baseline)
         except Exception as e:

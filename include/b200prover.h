@@ -67,6 +67,8 @@ const char* b200_last_error(void);
 const char* b200_version(void);
 /* Kernels launched by the library in this process so far (all contexts, all threads). */
 uint64_t b200_kernel_launches(void);
+/* Host time, in nanoseconds, the calling threads spent submitting those launches (sum over threads). */
+uint64_t b200_launch_host_ns(void);
 
 /* ---- SRS ------------------------------------------------------------------------------- */
 /* Replaces parse_ptau_file / read_ptau_header / read_ptau_section1 / read_ptau_section2

@@ -14,6 +14,7 @@ namespace b200 {
 
 static thread_local std::string g_last_error;
 std::atomic<uint64_t> g_kernel_launches{0};
+std::atomic<uint64_t> g_launch_host_ns{0};
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -132,6 +133,7 @@ const char* b200_last_error(void) { return g_last_error.c_str(); }
 const char* b200_version(void) { return "libb200prover 0.1.0 sm_100a"; }
 
 uint64_t b200_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
+uint64_t b200_launch_host_ns(void) { return g_launch_host_ns.load(std::memory_order_relaxed); }
 
 void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) { Keccak256::hash(data, len, out); }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstddef>
 #include <cstdint>
 #include <map>
@@ -29,8 +30,17 @@ int cuda_fail(cudaError_t e, const char* what);  // records the message, returns
 // Process-wide count of kernel launches made by the library (bench.py's `gpu_launches` is the difference of
 // two reads around the timed region; b200_kernel_launches()).  A relaxed increment per launch.
 extern std::atomic<uint64_t> g_kernel_launches;
-inline void note_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
-#define B200_LAUNCH(kern, grid, block, smem, st) ::b200::note_launch(), kern<<<grid, block, smem, st>>>
+extern std::atomic<uint64_t> g_launch_host_ns;
+// Counts the launch and the host time its submission took: the temporary lives until the end of the launch statement.
+struct LaunchClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~LaunchClock() {
+        g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        g_launch_host_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+                                   std::memory_order_relaxed);
+    }
+};
+#define B200_LAUNCH(kern, grid, block, smem, st) ::b200::LaunchClock(), kern<<<grid, block, smem, st>>>
 
 // Grow-only device buffer
 struct DevBuf {
