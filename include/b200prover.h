@@ -69,6 +69,12 @@ const char* b200_version(void);
 uint64_t b200_kernel_launches(void);
 /* Host time, in nanoseconds, the calling threads spent submitting those launches (sum over threads). */
 uint64_t b200_launch_host_ns(void);
+/* From the second proof of a key on a context, b200_plonk_prove replays each prover round as ONE CUDA graph (same kernels,
+ * same order, same bytes out; b200_kernel_launches keeps counting the kernels executed).  b200_graph_launches: graph
+ * submissions so far.  b200_ctx_use_graphs(ctx, 0) switches the replay off for a context (default: on, or B200_GRAPHS=0
+ * in the environment). */
+uint64_t b200_graph_launches(void);
+int b200_ctx_use_graphs(b200_ctx* ctx, int on);
 
 /* ---- SRS ------------------------------------------------------------------------------- */
 /* Replaces parse_ptau_file / read_ptau_header / read_ptau_section1 / read_ptau_section2

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200prover
 # every symbol include/b200prover.h declares (tests/test_abi.py checks this list against the
 # header and against the built library)
 EXPORTS = [
-    "b200_init", "b200_shutdown", "b200_last_error", "b200_version", "b200_kernel_launches", "b200_launch_host_ns",
+    "b200_init", "b200_shutdown", "b200_last_error", "b200_version", "b200_kernel_launches", "b200_launch_host_ns", "b200_graph_launches", "b200_ctx_use_graphs",
     "b200_srs_parse_ptau", "b200_bases_load", "b200_bases_load_device", "b200_bases_free",
     "b200_bases_len", "b200_bases_plan",
     "b200_msm", "b200_msm_device", "b200_msm_batch_device", "b200_msm_timing", "b200_msm_timing_totals", "b200_msm_tuning", "b200_g1_sum_affine",
@@ -63,6 +63,10 @@ def load() -> C.CDLL:
     lib.b200_kernel_launches.argtypes = []
     lib.b200_launch_host_ns.restype = C.c_uint64
     lib.b200_launch_host_ns.argtypes = []
+    lib.b200_graph_launches.restype = C.c_uint64
+    lib.b200_graph_launches.argtypes = []
+    lib.b200_ctx_use_graphs.restype = C.c_int
+    lib.b200_ctx_use_graphs.argtypes = [C.c_void_p, C.c_int]
     lib.b200_init.argtypes = [i32, C.POINTER(vp)]
     lib.b200_shutdown.argtypes = [vp]
     lib.b200_shutdown.restype = None

@@ -51,6 +51,17 @@ class Context:
         except Exception:
             pass
 
+    def use_graphs(self, on: bool = True):
+        """Replay the prover's rounds as CUDA graphs from the second proof of a key on (default: on; B200_GRAPHS=0)."""
+        _lib.check(self._lib.b200_ctx_use_graphs(self._h, int(on)))
+
+    def kernel_launches(self) -> int:
+        """Kernels the library has launched (or replayed inside graphs) in this process so far."""
+        return int(self._lib.b200_kernel_launches())
+
+    def graph_launches(self) -> int:
+        return int(self._lib.b200_graph_launches())
+
     # ---- bases / SRS ------------------------------------------------------------------------
     def load_bases(self, points, window_bits: int = 0, check_on_curve: bool = False) -> "Bases":
         """points: (n, 8) uint64 array or bytes of 64-byte records."""

@@ -15,6 +15,9 @@ namespace b200 {
 static thread_local std::string g_last_error;
 std::atomic<uint64_t> g_kernel_launches{0};
 std::atomic<uint64_t> g_launch_host_ns{0};
+std::atomic<uint64_t> g_graph_launches{0};
+std::atomic<uint64_t> g_alloc_epoch{1};
+thread_local uint64_t t_kernel_launches = 0;
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -24,6 +27,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 Context::~Context() {
+    for (ProofGraphSet* g : graph_sets) delete g;
     for (auto& kv : domains) delete kv.second;
     if (ntt_ev_init) {
         cudaEventDestroy(ntt_ev[0]);
@@ -134,6 +138,13 @@ const char* b200_version(void) { return "libb200prover 0.1.0 sm_100a"; }
 
 uint64_t b200_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 uint64_t b200_launch_host_ns(void) { return g_launch_host_ns.load(std::memory_order_relaxed); }
+uint64_t b200_graph_launches(void) { return g_graph_launches.load(std::memory_order_relaxed); }
+int b200_ctx_use_graphs(b200_ctx* ctx, int on) {
+    if (!ctx) return B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    ctx->c.use_graphs = on ? 1 : 0;
+    return B200_OK;
+}
 
 void b200_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) { Keccak256::hash(data, len, out); }
 

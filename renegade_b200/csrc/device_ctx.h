@@ -10,6 +10,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "ec.cuh"
 #include "ff.cuh"
@@ -31,11 +32,15 @@ int cuda_fail(cudaError_t e, const char* what);  // records the message, returns
 // two reads around the timed region; b200_kernel_launches()).  A relaxed increment per launch.
 extern std::atomic<uint64_t> g_kernel_launches;
 extern std::atomic<uint64_t> g_launch_host_ns;
+extern std::atomic<uint64_t> g_graph_launches;  // cudaGraphLaunch calls (a replayed prover round is one submission)
+extern std::atomic<uint64_t> g_alloc_epoch;     // bumped whenever a DevBuf / HostPinned changes address: captured graphs go stale
+extern thread_local uint64_t t_kernel_launches; // this thread's launches (what a stream capture recorded)
 // Counts the launch and the host time its submission took: the temporary lives until the end of the launch statement.
 struct LaunchClock {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     ~LaunchClock() {
         g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+        ++t_kernel_launches;
         g_launch_host_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
                                    std::memory_order_relaxed);
     }
@@ -48,6 +53,7 @@ struct DevBuf {
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return B200_OK;
+        g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -67,6 +73,7 @@ struct HostPinned {
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return B200_OK;
+        g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
@@ -135,6 +142,9 @@ struct MsmScratch {
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
     // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
     double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
+    // set by a caller that captures / replays the launches as a CUDA graph: timing events become graph nodes, and the
+    // caller records done_ev itself
+    bool in_graph = false;
     // borrowed from the context: low-priority stream for the accumulation kernel (null: same stream)
     cudaStream_t hv_stream = nullptr;
     cudaEvent_t hv_fork = nullptr, hv_join = nullptr;
@@ -161,12 +171,29 @@ int msm_device_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
 int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
                      unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st);
 int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf);
+void msm_mark_pending(const Bases* b, size_t n, unsigned batch, MsmScratch* s);
 void msm_collect_timing(MsmScratch* s, size_t n, unsigned batch);
 // synthetic known-discrete-log bases P_i = a_i * G, a_i = SplitMix64-derived
 int g1_known_dlog_bases_device(uint64_t seed, size_t first, size_t n, g1_affine* d_out,
                                cudaStream_t st);
 int splitmix_fr_device(uint64_t seed, size_t first, size_t n, int montgomery, fe* d_out,
                        cudaStream_t st);
+
+// ---- prover rounds as CUDA graphs -----------------------------------------------------------------
+// One set per (context, proving key): the launches of each prover segment, captured on the second proof of that key
+// on that context (the first sizes every buffer) and replayed afterwards.  Stale when any buffer moved (alloc epoch).
+constexpr int kProofSegs = 7;
+struct ProofGraphSet {
+    uint64_t pk_id = 0, epoch = 0, last_use = 0;
+    unsigned proofs_seen = 0;
+    bool timing = false;  // captured with the MSM's timing events as graph nodes
+    cudaGraphExec_t exec[kProofSegs] = {};
+    uint64_t kernels[kProofSegs] = {};
+    ~ProofGraphSet() {
+        for (auto& e : exec)
+            if (e) cudaGraphExecDestroy(e);
+    }
+};
 
 // ---- context --------------------------------------------------------------------------------
 struct Context {
@@ -189,6 +216,12 @@ struct Context {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf ntt_scratch2;
     HostPinned h_small;  // pinned landing zone of the prover's small read-backs (degree flag, evaluations)
+    // per-proof scalars of the prover (plonk.cu ProofParams): pinned staging copy and the device copy the kernels read
+    HostPinned h_params;
+    DevBuf d_params;
+    int use_graphs = -1;  // 1 / 0: replay prover rounds as CUDA graphs or not; -1: B200_GRAPHS from the environment (default on)
+    std::vector<ProofGraphSet*> graph_sets;
+    uint64_t graph_clock = 0;
     ~Context();
 };
 

@@ -906,11 +906,18 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     uint32_t* heavy_list = (uint32_t*)s->heavy.p;
     uint32_t* seg_order = (uint32_t*)s->seg_order.p;
 
-    if (s->timing && !s->ev_init) {
+    const bool timing = s->timing;
+    if (timing && !s->ev_init) {
         for (auto& e : s->ev) B200_CUDA(cudaEventCreate(&e));
         s->ev_init = true;
     }
-    if (s->timing) cudaEventRecord(s->ev[0], st);
+    // inside a stream capture a timing event has to become a node of the graph (external record), or a replay would not record it
+    auto stamp = [&](int i) {
+        if (!timing) return;
+        if (s->in_graph) cudaEventRecordWithFlags(s->ev[i], st, cudaEventRecordExternal);
+        else cudaEventRecord(s->ev[i], st);
+    };
+    stamp(0);
     const unsigned bs = 256;
     const dim3 grid_n((unsigned)((n + bs - 1) / bs), batch);
     B200_LAUNCH(msm_count_kernel, grid_n, bs, 0, st)(d_scalars, n, stride, montgomery, pl, (uint32_t)buckets_per_msm, counts);
@@ -922,7 +929,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
                                                                              stt->seg_starts, seg_bucket, seg_order);
     // the long kernels of the MSM go to the low-priority companion stream (see b200_init)
     cudaStream_t hv = s->hv_stream ? s->hv_stream : st;
-    if (s->timing) cudaEventRecord(s->ev[1], st);
+    stamp(1);
     if (s->hv_stream) {
         cudaEventRecord(s->hv_fork, st);
         cudaStreamWaitEvent(hv, s->hv_fork, 0);
@@ -937,7 +944,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         seg_sums, seg_offsets, (uint32_t)n_buckets, buckets, &stt->heavy_count, heavy_list);
     B200_LAUNCH(msm_heavy_combine_kernel, (unsigned)std::min<size_t>(max_heavy, 592), kReduceThreads, 0, st)(
         seg_sums, seg_offsets, &stt->heavy_count, heavy_list, buckets);
-    if (s->timing) cudaEventRecord(s->ev[2], st);
+    stamp(2);
     {
         g1_xyzz* t0 = (g1_xyzz*)s->tree.p;
         g1_xyzz *row_p = t0, *col_p = t0 + row_l1, *R = col_p + col_l1, *Cs = R + n_R;
@@ -973,11 +980,18 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
     }
     B200_CUDA(cudaGetLastError());
-    if (s->timing) cudaEventRecord(s->ev[3], st);
+    stamp(3);
     B200_CUDA(cudaMemcpyAsync(s->h_sums.p, window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
-    if (s->timing) cudaEventRecord(s->ev[4], st);
-    B200_CUDA(cudaEventRecord(s->done_ev, st));
+    stamp(4);
+    if (!s->in_graph) B200_CUDA(cudaEventRecord(s->done_ev, st));  // a replaying caller records it after the graph launch
     return B200_OK;
+}
+
+// What msm_launch_batch leaves for msm_finish_batch, for a caller that replays the launches from a captured graph.
+void msm_mark_pending(const Bases* b, size_t n, unsigned batch, MsmScratch* s) {
+    s->pending_plan = b->plan;
+    s->pending_n = n;
+    s->pending_batch = batch;
 }
 
 // phase times of the MSM whose events have completed (the caller has waited for the stream / done_ev)

@@ -79,36 +79,41 @@ __global__ void k_batch_inverse(fe* __restrict__ data, fe* __restrict__ scratch,
 }
 
 // ---- round 1 / 2 helpers -------------------------------------------------------------------------
+// Per-proof scalars (blinders, challenges and what the host derives from them) reach the prover's kernels through
+// `dyn`: a pointer into the context's device copy of ProofParams, so that the kernel ARGUMENTS are the same for every
+// proof of a key and a round can be replayed as a CUDA graph.  dyn == nullptr: the by-value fields are used (link
+// proofs, the stand-alone polynomial entry points).
 struct BlindArgs {
     fe b[3];
     int count;
+    const fe* dyn;
 };
 // poly += (b0 + b1 X + ...) * (X^n - 1)
 __global__ void k_blind(fe* poly, size_t n, BlindArgs a) {
     const int i = threadIdx.x;
     if (i >= a.count) return;
-    fe_store(poly + i, FSUB(fe_load(poly + i), a.b[i]));
-    fe_store(poly + n + i, FADD(fe_load(poly + n + i), a.b[i]));
+    const fe b = a.dyn ? fe_load_ro(a.dyn + i) : a.b[i];
+    fe_store(poly + i, FSUB(fe_load(poly + i), b));
+    fe_store(poly + n + i, FADD(fe_load(poly + n + i), b));
 }
 
 // the five wire polynomials in one launch: thread (i, t) adds blinder t of wire i
-struct Blind5Args {
-    fe b[NW][2];
-};
-__global__ void k_blind_wires(fe* wpoly, size_t stride, size_t n, Blind5Args a) {
+__global__ void k_blind_wires(fe* wpoly, size_t stride, size_t n, const fe* __restrict__ dyn /* [NW][2] */) {
     const int i = threadIdx.x >> 1, t = threadIdx.x & 1;
     if (i >= NW) return;
     fe* poly = wpoly + (size_t)i * stride;
-    fe_store(poly + t, FSUB(fe_load(poly + t), a.b[i][t]));
-    fe_store(poly + n + t, FADD(fe_load(poly + n + t), a.b[i][t]));
+    const fe b = fe_load_ro(dyn + 2 * i + t);
+    fe_store(poly + t, FSUB(fe_load(poly + t), b));
+    fe_store(poly + n + t, FADD(fe_load(poly + n + t), b));
 }
 
 // per row j: num = prod_i (w_ij + beta k_i w^j + gamma), den = prod_i (w_ij + beta sigma_ij + gamma)
 __global__ void k_perm_num_den(const fe* __restrict__ wires, const fe* __restrict__ sig_evals,
-                               const fe* __restrict__ dom, KArr k, fe beta, fe gamma, size_t n,
+                               const fe* __restrict__ dom, KArr k, const fe* __restrict__ beta_gamma, size_t n,
                                fe* __restrict__ num, fe* __restrict__ den) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    const fe beta = fe_load_ro(beta_gamma), gamma = fe_load_ro(beta_gamma + 1);
     const fe bw = FMUL(beta, fe_load_ro(dom + j));
     fe a = fe_one<Fr>(), b = fe_one<Fr>();
 #pragma unroll
@@ -163,11 +168,13 @@ __global__ void k_scan_mul_apply(fe* __restrict__ data, size_t n, const fe* __re
 
 // ---- Horner suffix scan: S[j] = sum_{i >= j} p[i] z^(i-j) -------------------------------------------
 // S[0] = p(z) (evaluation) and S[1..] are the coefficients of p(X) / (X - z) (synthetic division).
-__global__ void k_horner_local(const fe* __restrict__ p, size_t len, fe z, fe* __restrict__ S, fe* __restrict__ H) {
+__global__ void k_horner_local(const fe* __restrict__ p, size_t len, fe z_val, const fe* __restrict__ z_dyn, fe* __restrict__ S,
+                               fe* __restrict__ H) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t beg = t * CH;
     if (beg >= len) return;
     const size_t end = beg + CH < len ? beg + CH : len;
+    const fe z = z_dyn ? fe_load_ro(z_dyn) : z_val;
     fe run = fe_zero();
     for (size_t i = end; i-- > beg;) {
         run = FADD(FMUL(run, z), fe_load_ro(p + i));
@@ -182,6 +189,7 @@ struct EvalArgs {
     fe* H[kMaxEval];
     fe z[kMaxEval];
     uint32_t len[kMaxEval];
+    const fe* dyn;  // z[] of this level in device memory, or null
 };
 __global__ void k_horner_local_batch(EvalArgs a) {
     const int q = blockIdx.y;
@@ -189,7 +197,7 @@ __global__ void k_horner_local_batch(EvalArgs a) {
     const size_t beg = t * CH, len = a.len[q];
     if (beg >= len) return;
     const size_t end = beg + CH < len ? beg + CH : len;
-    const fe z = a.z[q];
+    const fe z = a.dyn ? fe_load_ro(a.dyn + q) : a.z[q];
     const fe* p = a.p[q];
     fe run = fe_zero();
     for (size_t i = end; i-- > beg;) run = FADD(FMUL(run, z), fe_load_ro(p + i));
@@ -199,12 +207,14 @@ __global__ void k_horner_local_batch(EvalArgs a) {
 struct ZPow {
     fe v[CH + 1];
 };
-__global__ void k_horner_apply(fe* __restrict__ S, size_t len, ZPow zp, const fe* __restrict__ T, size_t n_chunks) {
+__global__ void k_horner_apply(fe* __restrict__ S, size_t len, ZPow zp, const fe* __restrict__ zp_dyn, const fe* __restrict__ T,
+                               size_t n_chunks) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t t = j / CH;
     if (j >= len || t + 1 >= n_chunks) return;  // the last chunk has no carry
     const size_t e = (t + 1) * CH - j;
-    fe_store(S + j, FADD(fe_load(S + j), FMUL(zp.v[e], fe_load_ro(T + t + 1))));
+    const fe ze = zp_dyn ? fe_load_ro(zp_dyn + e) : zp.v[e];
+    fe_store(S + j, FADD(fe_load(S + j), FMUL(ze, fe_load_ro(T + t + 1))));
 }
 
 // ---- round 3: quotient over nc cosets s_j * H_n of the 8n-th roots' coset g * H_8n ---------------------
@@ -264,7 +274,7 @@ struct QuotArgs {
     size_t m;        // nc * n
     unsigned log_n;
     KArr k;
-    fe beta, gamma, alpha, alpha2;
+    const fe* chal;  // device: beta, gamma, alpha, alpha^2
     fe zh_inv[8];    // 1 / (c_j - 1)
 };
 // k_quotient chains ~60 field products; fully unrolled it is ~180 KB of code and starves on the
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.m) return;
     const size_t m = a.m;
+    const fe beta = fe_load_ro(a.chal), gamma = fe_load_ro(a.chal + 1);
     fe w[NW];
 #pragma unroll
     for (int j = 0; j < NW; ++j) w[j] = fe_load_ro(a.ext + j * m + i);
@@ -294,18 +305,18 @@ __global__ void __launch_bounds__(128) k_quotient(QuotArgs a) {
     const fe zx = fe_load_ro(a.ext + 6 * m + i);
     const size_t nmask = ((size_t)1 << a.log_n) - 1;
     const fe zxw = fe_load_ro(a.ext + 6 * m + ((i & ~nmask) | ((i + 1) & nmask)));  // z(w x): next point of the same coset
-    const fe bx = FMUL(a.beta, fe_load_ro(a.pts + i));
+    const fe bx = FMUL(beta, fe_load_ro(a.pts + i));
     fe p1 = zx, p2 = zxw;
 #pragma unroll 1
     for (int j = 0; j < NW; ++j) {
-        const fe t = FADD(w[j], a.gamma);
+        const fe t = FADD(w[j], gamma);
         p1 = FMUL(p1, FADD(t, FMUL(a.k.v[j], bx)));
-        p2 = FMUL(p2, FADD(t, FMUL(a.beta, fe_load_ro(a.sig + j * m + i))));
+        p2 = FMUL(p2, FADD(t, FMUL(beta, fe_load_ro(a.sig + j * m + i))));
     }
-    acc = FADD(acc, FMUL(a.alpha, FSUB(p1, p2)));
+    acc = FADD(acc, FMUL(fe_load_ro(a.chal + 2), FSUB(p1, p2)));
     acc = FMUL(acc, a.zh_inv[i >> a.log_n]);
     // alpha^2 (z - 1) L1(x) / Z_H(x)
-    acc = FADD(acc, FMUL(FMUL(a.alpha2, FSUB(zx, fe_one<Fr>())), fe_load_ro(a.l1_inv + i)));
+    acc = FADD(acc, FMUL(FMUL(fe_load_ro(a.chal + 3), FSUB(zx, fe_one<Fr>())), fe_load_ro(a.l1_inv + i)));
     fe_store(a.out + i, acc);
 }
 
@@ -343,18 +354,17 @@ __global__ void k_fr_vec_op(int op, const fe* __restrict__ a, const fe* __restri
     fe_store(out + i, r);
 }
 
-struct SplitArgs {
-    fe b[4];
-};
+
 // t_i = quot[i(n+2) .. ) - b_{i-1} + b_i X^(n+2)   (the last chunk has n coefficients)
-__global__ void k_split_quotient(const fe* __restrict__ quot, size_t n, size_t stride, SplitArgs a, fe* __restrict__ out) {
+__global__ void k_split_quotient(const fe* __restrict__ quot, size_t n, size_t stride, const fe* __restrict__ dyn /* b[4] */,
+                                 fe* __restrict__ out) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= n + 3) return;
     const size_t len = i < NW - 1 ? n + 2 : n;
     fe v = j < len ? fe_load_ro(quot + (size_t)i * (n + 2) + j) : fe_zero();
-    if (j == 0 && i > 0) v = FSUB(v, a.b[i - 1]);
-    if (j == n + 2 && i < NW - 1) v = a.b[i];
+    if (j == 0 && i > 0) v = FSUB(v, fe_load_ro(dyn + i - 1));
+    if (j == n + 2 && i < NW - 1) v = fe_load_ro(dyn + i);
     fe_store(out + (size_t)i * stride + j, v);
 }
 
@@ -365,15 +375,35 @@ struct LinArgs {
     uint32_t len[kMaxLin];
     fe s[kMaxLin];
     int count;
+    const fe* dyn;  // s[] in device memory, or null
 };
 __global__ void k_lincomb(LinArgs a, size_t out_len, fe* __restrict__ out) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= out_len) return;
     fe acc = fe_zero();
     for (int t = 0; t < a.count; ++t)
-        if (j < a.len[t]) acc = FADD(acc, FMUL(a.s[t], fe_load_ro(a.p[t] + j)));
+        if (j < a.len[t]) acc = FADD(acc, FMUL(a.dyn ? fe_load_ro(a.dyn + t) : a.s[t], fe_load_ro(a.p[t] + j)));
     fe_store(out + j, acc);
 }
+
+// ---- per-proof scalars ------------------------------------------------------------------------------------
+// Everything a proof's kernels need that is not a function of (context, proving key): blinders, Fiat–Shamir challenges
+// and the host-side values derived from them.  The host fills the pinned copy between rounds; each round's first
+// operation copies it to the device copy the kernels read (see `dyn` above).
+constexpr int kLevels = 8;  // levels of the chunked Horner scans: CH^8 = 2^32 coefficients
+struct OpenParams {
+    fe z[kLevels];     // the point raised to CH^level
+    ZPow zp[kLevels];  // powers 0..CH of z[level]
+};
+struct ProofParams {
+    fe blind_w[NW][2];             // round 1
+    fe chal[4];                    // beta, gamma (round 2), alpha, alpha^2 (round 3)
+    fe blind_z[4];                 // 3 used
+    fe blind_q[4];                 // round 3
+    fe eval_z[kLevels][kMaxEval];  // round 4
+    fe lin_s[kMaxLin];             // round 5
+    OpenParams open[2];            // zeta, zeta * w
+};
 
 inline unsigned grid_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
@@ -382,7 +412,10 @@ inline unsigned grid_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1)
 // ---------------------------------------------------------------------------------------------
 // host-side structures
 // ---------------------------------------------------------------------------------------------
+static std::atomic<uint64_t> g_pk_ids{1};
+
 struct ProvingKey {
+    uint64_t id = g_pk_ids.fetch_add(1);  // never reused: what a context's captured graphs are keyed by
     unsigned log_n = 0;
     size_t n = 0, m = 0, num_inputs = 0;
     KArr k;
@@ -485,34 +518,39 @@ static void scan_mul_exclusive(fe* data, size_t n, fe* scratch, cudaStream_t st)
 
 // Horner suffix scan; S may be null (evaluation only).  The value p(z) ends up at out_total (device).
 // scratch >= 2 * (len/CH + len/CH^2 + 2*CH + 8) elements
-static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, fe* scratch, cudaStream_t st) {
+// `dyn` (device, or null): the point and its powers per level come from there instead of `z` (see ProofParams).
+static void horner_suffix(const fe* p, size_t len, fe z, fe* S, fe* out_total, fe* scratch, cudaStream_t st,
+                          const OpenParams* dyn = nullptr, int level = 0) {
     const size_t n1 = (len + CH - 1) / CH;
     fe* H = scratch;
     fe* T = scratch + n1;
-    B200_LAUNCH(k_horner_local, grid_for(n1, 128), 128, 0, st)(p, len, z, S, H);
+    B200_LAUNCH(k_horner_local, grid_for(n1, 128), 128, 0, st)(p, len, z, dyn ? &dyn->z[level] : nullptr, S, H);
     if (n1 == 1) {
         cudaMemcpyAsync(out_total, H, sizeof(fe), cudaMemcpyDeviceToDevice, st);
         return;
     }
-    const fe zc = host_pow(z, CH);
-    horner_suffix(H, n1, zc, S ? T : nullptr, out_total, scratch + 2 * n1, st);
+    const fe zc = dyn ? z : host_pow(z, CH);
+    horner_suffix(H, n1, zc, S ? T : nullptr, out_total, scratch + 2 * n1, st, dyn, level + 1);
     if (S) {
-        ZPow zp;
-        zp.v[0] = fe_one<Fr>();
-        for (int e = 1; e <= CH; ++e) zp.v[e] = FMUL(zp.v[e - 1], z);
-        B200_LAUNCH(k_horner_apply, grid_for(len, 256), 256, 0, st)(S, len, zp, T, n1);
+        ZPow zp{};
+        if (!dyn) {
+            zp.v[0] = fe_one<Fr>();
+            for (int e = 1; e <= CH; ++e) zp.v[e] = FMUL(zp.v[e - 1], z);
+        }
+        B200_LAUNCH(k_horner_apply, grid_for(len, 256), 256, 0, st)(S, len, zp, dyn ? dyn->zp[level].v : nullptr, T, n1);
     }
 }
 
 // p_q(z_q) for up to kMaxEval polynomials, written to out[q];
 // scratch: count * (max_len/CH + max_len/CH^2 + 2*CH + 16)
+// `dyn_z` (device, or null): [level][kMaxEval] evaluation points, points[q]^(CH^level); `points` is unused then.
 static void eval_batch(const fe* const* polys, const size_t* lens, const fe* points, int count, fe* out, fe* scratch,
-                       cudaStream_t st) {
+                       cudaStream_t st, const fe (*dyn_z)[kMaxEval] = nullptr) {
     EvalArgs a;
     size_t cur_len[kMaxEval], max_len = 0;
     for (int q = 0; q < count; ++q) {
         a.p[q] = polys[q];
-        a.z[q] = points[q];
+        a.z[q] = dyn_z ? fe_zero() : points[q];
         cur_len[q] = lens[q];
         max_len = lens[q] > max_len ? lens[q] : max_len;
     }
@@ -534,11 +572,12 @@ static void eval_batch(const fe* const* polys, const size_t* lens, const fe* poi
             // levels alternate between the two halves of each polynomial's scratch slice
             a.H[q] = last ? out + q : scratch + (size_t)q * per_poly + (level & 1 ? region_a : 0);
         }
+        a.dyn = dyn_z ? &dyn_z[level][0] : nullptr;
         B200_LAUNCH(k_horner_local_batch, dim3(grid_for(max_chunks, 64), count), 64, 0, st)(a);
         if (last) break;
         for (int q = 0; q < count; ++q) {
             a.p[q] = a.H[q];
-            a.z[q] = host_pow(a.z[q], CH);
+            if (!dyn_z) a.z[q] = host_pow(a.z[q], CH);
             cur_len[q] = (cur_len[q] + CH - 1) / CH;
         }
         ++level;
@@ -732,6 +771,106 @@ struct ProofOut {  // same field order and layout as b200_proof / PlonkProofDef
 };
 static_assert(sizeof(ProofOut) == sizeof(b200_proof), "proof layout");
 
+// ---- prover rounds as CUDA graphs ---------------------------------------------------------------
+// The launches of a proof depend on (context, key) only — every per-proof value travels through ProofParams — so each
+// segment between two host synchronisations is captured once (second proof of a key on a context; the first runs
+// eagerly and sizes every buffer) and replayed as ONE submission afterwards: ~90 kernel launches per proof become 7
+// graph launches.  Same kernels, same order, same bytes out.
+static ProofGraphSet* graph_set_for(Context* c, const ProvingKey* pk) {
+    int on = c->use_graphs;
+    if (on < 0) {
+        static const bool env_on = [] {
+            const char* e = std::getenv("B200_GRAPHS");
+            return !(e && e[0] == '0');
+        }();
+        on = env_on ? 1 : 0;
+    }
+    if (!on) return nullptr;
+    ProofGraphSet* gs = nullptr;
+    for (ProofGraphSet* g : c->graph_sets)
+        if (g->pk_id == pk->id) gs = g;
+    if (!gs) {
+        if (c->graph_sets.size() >= 8) {  // keys come and go: drop the least recently used set
+            size_t lru = 0;
+            for (size_t i = 1; i < c->graph_sets.size(); ++i)
+                if (c->graph_sets[i]->last_use < c->graph_sets[lru]->last_use) lru = i;
+            delete c->graph_sets[lru];
+            c->graph_sets.erase(c->graph_sets.begin() + (long)lru);
+        }
+        gs = new ProofGraphSet();
+        gs->pk_id = pk->id;
+        c->graph_sets.push_back(gs);
+    }
+    gs->last_use = ++c->graph_clock;
+    const uint64_t epoch = g_alloc_epoch.load(std::memory_order_relaxed);
+    if (gs->epoch != epoch || gs->timing != c->msm.timing) {  // a buffer moved since the capture (any context), or the
+                                                              // MSM timing events were switched: capture again
+        gs->timing = c->msm.timing;
+        for (auto& e : gs->exec)
+            if (e) {
+                cudaGraphExecDestroy(e);
+                e = nullptr;
+            }
+        gs->epoch = epoch;
+    }
+    return gs;
+}
+
+// Runs `fn` (which only enqueues work on `st` and on streams it forks from / joins back to `st`): directly when `gs`
+// is null, else through the segment's graph, capturing it first if need be.
+template <class F>
+static int run_segment(ProofGraphSet* gs, int idx, cudaStream_t st, F&& fn) {
+    if (!gs) return fn();
+    if (!gs->exec[idx]) {
+        const uint64_t k0 = t_kernel_launches;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamBeginCapture");
+        const int rc = fn();
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamEndCapture(st, &graph);
+        if (rc != B200_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc != B200_OK ? rc : cuda_fail(e, "cudaStreamEndCapture");
+        }
+        e = cudaGraphInstantiate(&gs->exec[idx], graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            gs->exec[idx] = nullptr;
+            return cuda_fail(e, "cudaGraphInstantiate");
+        }
+        gs->kernels[idx] = t_kernel_launches - k0;
+    } else {
+        g_kernel_launches.fetch_add(gs->kernels[idx], std::memory_order_relaxed);  // the kernels this submission runs
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaGraphLaunch(gs->exec[idx], st);
+    g_launch_host_ns.fetch_add(
+        (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+        std::memory_order_relaxed);
+    g_graph_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+    return B200_OK;
+}
+
+static int commit_collect(Context* c, unsigned count, g1_affine* out) {
+    int inf[32];
+    if (count > 32) return B200_ERR_INVALID;
+    const int rc = msm_finish_batch(&c->msm, out, inf);
+    if (rc != B200_OK) return rc;
+    for (unsigned i = 0; i < count; ++i)
+        if (inf[i]) std::memset(&out[i], 0, sizeof(out[i]));
+    return B200_OK;
+}
+
+static void fill_open_params(OpenParams* o, fe z) {
+    for (int l = 0; l < kLevels; ++l) {
+        o->z[l] = z;
+        o->zp[l].v[0] = fe_one<Fr>();
+        for (int e = 1; e <= CH; ++e) o->zp[l].v[e] = FMUL(o->zp[l].v[e - 1], z);
+        z = o->zp[l].v[CH];
+    }
+}
+
 static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* h_pub_inputs, const fe* h_blinders,
                  ProofOut* proof, fe* h_link_poly, fe* h_challenges) {
     const size_t n = pk->n, m = pk->m;
@@ -742,6 +881,8 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     if ((rc = c->ntt_scratch.reserve((size_t)7 * m * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch2.reserve((size_t)6 * m * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->h_small.reserve(4096)) != B200_OK) return rc;
+    if ((rc = c->h_params.reserve(sizeof(ProofParams))) != B200_OK) return rc;
+    if ((rc = c->d_params.reserve(sizeof(ProofParams))) != B200_OK) return rc;
     if (!c->stream2) {
         int prio_least = 0, prio_greatest = 0;
         cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
@@ -755,6 +896,37 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     Domain* dn = nullptr;
     if ((rc = get_domain(c, log_n, &dn)) != B200_OK) return rc;
     const fe one = fe_one<Fr>();
+
+    // graphs: only once a proof of this key has run eagerly on this context (every buffer has its final size then)
+    ProofGraphSet* gset = graph_set_for(c, pk);
+    ProofGraphSet* gs = gset && gset->proofs_seen > 0 ? gset : nullptr;
+    c->msm.in_graph = gs != nullptr;
+    struct InGraphReset {
+        MsmScratch& s;
+        ~InGraphReset() { s.in_graph = false; }
+    } in_graph_reset{c->msm};
+    ProofParams* hp = reinterpret_cast<ProofParams*>(c->h_params.p);  // pinned staging copy
+    ProofParams* dp = reinterpret_cast<ProofParams*>(c->d_params.p);  // what the kernels read
+    // first operation of every segment that follows a host update of *hp
+    auto push_params = [&]() -> int {
+        B200_CUDA(cudaMemcpyAsync(dp, hp, sizeof(ProofParams), cudaMemcpyHostToDevice, st));
+        return B200_OK;
+    };
+    // enqueue `count` commitments (segment idx), leaving the batch pending for commit_collect
+    auto commit_enqueue = [&](int idx, const fe* d_coeffs, size_t len, size_t stride, unsigned count, auto&& before) -> int {
+        int r = run_segment(gs, idx, st, [&]() -> int {
+            int r2 = before();
+            if (r2 != B200_OK) return r2;
+            return msm_launch_batch(pk->srs, 0, d_coeffs, len, stride, count, /*montgomery=*/1, &c->msm, st);
+        });
+        if (r != B200_OK) return r;
+        if (gs) {  // what msm_launch_batch leaves behind when it runs outside a capture
+            msm_mark_pending(pk->srs, len, count, &c->msm);
+            B200_CUDA(cudaEventRecord(c->msm.done_ev, st));
+        }
+        return B200_OK;
+    };
+    auto nothing = []() -> int { return B200_OK; };
 
     using clk = std::chrono::steady_clock;
     auto t_prev = clk::now();
@@ -774,25 +946,29 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     for (size_t i = 0; i < pk->num_inputs; ++i) tr.append_field_elem(h_pub_inputs[i]);
 
     // ---- round 1 ------------------------------------------------------------------------------------
+    // caller-owned buffers are copied outside the graphs (their addresses change from proof to proof)
     B200_CUDA(cudaMemcpyAsync(w.wires_ev, h_wires, NW * n * sizeof(fe), cudaMemcpyDefault, st));  // host or device pointer (UVA)
     B200_CUDA(cudaMemsetAsync(w.wpoly, 0, (NW + 1) * S * sizeof(fe), st));  // wire slots and the public-input slot behind them
-    B200_CUDA(cudaMemcpy2DAsync(w.wpoly, S * sizeof(fe), w.wires_ev, n * sizeof(fe), n * sizeof(fe), NW,
-                                cudaMemcpyDeviceToDevice, st));
     if (pk->num_inputs)
         B200_CUDA(cudaMemcpyAsync(w.pi_poly, h_pub_inputs, pk->num_inputs * sizeof(fe), cudaMemcpyHostToDevice, st));
-    {
-        // wires and public inputs: evaluations -> coefficients, one batch of 6 (pi_poly sits directly behind wpoly)
-        HeavyScope hv(c, st);
-        if ((rc = ntt_device(dn, w.wpoly, nscr, 1, 0, NW + 1, S, hv.run)) != B200_OK) return rc;
+    for (int i = 0; i < NW; ++i) {
+        hp->blind_w[i][0] = h_blinders[2 * i];
+        hp->blind_w[i][1] = h_blinders[2 * i + 1];
     }
-    {
-        Blind5Args b;
-        for (int i = 0; i < NW; ++i) {
-            b.b[i][0] = h_blinders[2 * i];
-            b.b[i][1] = h_blinders[2 * i + 1];
+    rc = run_segment(gs, 0, st, [&]() -> int {
+        int r = push_params();
+        if (r != B200_OK) return r;
+        B200_CUDA(cudaMemcpy2DAsync(w.wpoly, S * sizeof(fe), w.wires_ev, n * sizeof(fe), n * sizeof(fe), NW,
+                                    cudaMemcpyDeviceToDevice, st));
+        {
+            // wires and public inputs: evaluations -> coefficients, one batch of 6 (pi_poly sits directly behind wpoly)
+            HeavyScope hv(c, st);
+            if ((r = ntt_device(dn, w.wpoly, nscr, 1, 0, NW + 1, S, hv.run)) != B200_OK) return r;
         }
-        B200_LAUNCH(k_blind_wires, 1, 32, 0, st)(w.wpoly, S, n, b);
-    }
+        B200_LAUNCH(k_blind_wires, 1, 32, 0, st)(w.wpoly, S, n, &dp->blind_w[0][0]);
+        return B200_OK;
+    });
+    if (rc != B200_OK) return rc;
     // Fork: the coset evaluations of the 5 wire polynomials and of the public-input polynomial do not
     // depend on any challenge, so they run on a second stream underneath the round-1/2 commitments
     // (whose bucket reduction and host round trip leave most SMs idle).
@@ -809,13 +985,15 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         B200_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
         side.pending = true;
         // 5 wire polynomials (n + 2 coefficients) and the public-input polynomial (n, zero tail) in one batch
-        if ((rc = coset_evals(pk, dn, w.wpoly, S, n + 2, NW + 1, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), s2)) !=
-            B200_OK)
-            return rc;
+        rc = run_segment(gs, 1, s2, [&]() -> int {
+            return coset_evals(pk, dn, w.wpoly, S, n + 2, NW + 1, w.ext, reinterpret_cast<fe*>(c->ntt_scratch2.p), s2);
+        });
+        if (rc != B200_OK) return rc;
         B200_CUDA(cudaEventRecord(c->ev_join, s2));
     }
-    if ((rc = commit_batch(c, pk, w.wpoly, n + 2, S, NW, proof->wires_poly_comms)) != B200_OK) return rc;
-    if (h_link_poly)
+    if ((rc = commit_enqueue(2, w.wpoly, n + 2, S, NW, nothing)) != B200_OK) return rc;
+    if ((rc = commit_collect(c, NW, proof->wires_poly_comms)) != B200_OK) return rc;
+    if (h_link_poly)  // completes under round 2; the stream is synchronised several times before this call returns
         B200_CUDA(cudaMemcpyAsync(h_link_poly, w.wpoly, (n + 2) * sizeof(fe), cudaMemcpyDeviceToHost, st));
     for (int i = 0; i < NW; ++i) tr.append_commitment(proof->wires_poly_comms[i]);
     mark();  // [0] round 1
@@ -823,76 +1001,86 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     // ---- round 2 ------------------------------------------------------------------------------------
     const fe beta = tr.get_and_append_challenge();
     const fe gamma = tr.get_and_append_challenge();
-    B200_LAUNCH(k_perm_num_den, grid_for(n, 128), 128, 0, st)(w.wires_ev, pk->sig_evals, pk->dom, pk->k, beta, gamma, n, w.num, w.den);
-    B200_LAUNCH(k_ratio, grid_for((n + 15) / 16, 64), 64, 0, st)(w.num, w.den, w.tmp, n);
-    scan_mul_exclusive(w.den, n, w.scan, st);  // z(w^j) = prod_{i<j} ratio_i
-    B200_CUDA(cudaMemsetAsync(w.zpoly, 0, S * sizeof(fe), st));
-    B200_CUDA(cudaMemcpyAsync(w.zpoly, w.den, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    if ((rc = ntt_device(dn, w.zpoly, nscr, 1, 0, 1, S, st)) != B200_OK) return rc;
-    {
-        BlindArgs b;
+    hp->chal[0] = beta;
+    hp->chal[1] = gamma;
+    for (int i = 0; i < 3; ++i) hp->blind_z[i] = h_blinders[10 + i];
+    rc = commit_enqueue(3, w.zpoly, n + 3, n + 3, 1, [&]() -> int {
+        int r = push_params();
+        if (r != B200_OK) return r;
+        B200_LAUNCH(k_perm_num_den, grid_for(n, 128), 128, 0, st)(w.wires_ev, pk->sig_evals, pk->dom, pk->k, &dp->chal[0], n, w.num, w.den);
+        B200_LAUNCH(k_ratio, grid_for((n + 15) / 16, 64), 64, 0, st)(w.num, w.den, w.tmp, n);
+        scan_mul_exclusive(w.den, n, w.scan, st);  // z(w^j) = prod_{i<j} ratio_i
+        B200_CUDA(cudaMemsetAsync(w.zpoly, 0, S * sizeof(fe), st));
+        B200_CUDA(cudaMemcpyAsync(w.zpoly, w.den, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+        if ((r = ntt_device(dn, w.zpoly, nscr, 1, 0, 1, S, st)) != B200_OK) return r;
+        BlindArgs b{};
         b.count = 3;
-        for (int i = 0; i < 3; ++i) b.b[i] = h_blinders[10 + i];
+        b.dyn = &dp->blind_z[0];
         B200_LAUNCH(k_blind, 1, 32, 0, st)(w.zpoly, n, b);
-    }
-    if ((rc = commit(c, pk, w.zpoly, n + 3, &proof->prod_perm_poly_comm)) != B200_OK) return rc;
+        return B200_OK;
+    });
+    if (rc != B200_OK) return rc;
+    if ((rc = commit_collect(c, 1, &proof->prod_perm_poly_comm)) != B200_OK) return rc;
     tr.append_commitment(proof->prod_perm_poly_comm);
     mark();  // [1] round 2
 
     // ---- round 3 ------------------------------------------------------------------------------------
     const fe alpha = tr.get_and_append_challenge();
-    {
-        HeavyScope hv(c, st);
-        if ((rc = coset_evals(pk, dn, w.zpoly, S, n + 3, 1, w.ext + 6 * m, nscr, hv.run)) != B200_OK) return rc;
-    }
+    hp->chal[2] = alpha;
+    hp->chal[3] = fe_sqr<Fr>(alpha);
+    for (int i = 0; i < 4; ++i) hp->blind_q[i] = h_blinders[13 + i];
     B200_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));  // join: wire / PI coset evaluations are ready
     side.pending = false;
-    {
-        QuotArgs q;
-        q.sel = pk->ce_sel;
-        q.sig = pk->ce_sig;
-        q.ext = w.ext;
-        q.pts = pk->coset_pts;
-        q.l1_inv = pk->l1_inv;
-        q.out = w.quot;
-        q.m = m;
-        q.log_n = log_n;
-        q.k = pk->k;
-        q.beta = beta;
-        q.gamma = gamma;
-        q.alpha = alpha;
-        q.alpha2 = fe_sqr<Fr>(alpha);
-        for (int i = 0; i < 8; ++i) q.zh_inv[i] = pk->zh_inv[i];
-        HeavyScope hv(c, st);
-        B200_LAUNCH(k_quotient, grid_for(m, 128), 128, 0, hv.run)(q);
-        // back to coefficients: nc size-n inverse transforms, then un-scale and un-mix the cosets
-        if ((rc = ntt_device(dn, w.quot, nscr, 1, 0, (unsigned)pk->nc, n, hv.run)) != B200_OK) return rc;
-        if (pk->nc == 6) B200_LAUNCH(k_coset_combine<6>, grid_for(n, 128), 128, 0, hv.run)(w.quot, n, pk->cscale_inv, pk->comb);
-        else B200_LAUNCH(k_coset_combine<8>, grid_for(n, 128), 128, 0, hv.run)(w.quot, n, pk->cscale_inv, pk->comb);
-    }
     const size_t deg = NW * (n + 1) + 2;
-    B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
-    B200_LAUNCH(k_check_degree, grid_for(m - deg, 256), 256, 0, st)(w.quot, deg, m, w.flag);
     uint32_t* h_flag = reinterpret_cast<uint32_t*>(c->h_small.p);  // pinned; read after the commitments below are in
-    B200_CUDA(cudaMemcpyAsync(h_flag, w.flag, 4, cudaMemcpyDeviceToHost, st));
-    {
-        SplitArgs sa;
-        for (int i = 0; i < 4; ++i) sa.b[i] = h_blinders[13 + i];
-        B200_LAUNCH(k_split_quotient, dim3(grid_for(n + 3, 256), NW), 256, 0, st)(w.quot, n, S, sa, w.split);
-    }
-    mark();  // [2] round 3 (enqueue only: the quotient's degree flag is read with the commitments)
+    mark();  // [2] round 3 (host part)
     // the last chunk has n coefficients; its tail up to n + 3 is zero, so one batch length serves
-    if ((rc = commit_batch(c, pk, w.split, n + 3, S, NW, proof->split_quot_poly_comms)) != B200_OK) return rc;
+    rc = commit_enqueue(4, w.split, n + 3, S, NW, [&]() -> int {
+        int r = push_params();
+        if (r != B200_OK) return r;
+        {
+            HeavyScope hv(c, st);
+            if ((r = coset_evals(pk, dn, w.zpoly, S, n + 3, 1, w.ext + 6 * m, nscr, hv.run)) != B200_OK) return r;
+        }
+        {
+            QuotArgs q;
+            q.sel = pk->ce_sel;
+            q.sig = pk->ce_sig;
+            q.ext = w.ext;
+            q.pts = pk->coset_pts;
+            q.l1_inv = pk->l1_inv;
+            q.out = w.quot;
+            q.m = m;
+            q.log_n = log_n;
+            q.k = pk->k;
+            q.chal = &dp->chal[0];
+            for (int i = 0; i < 8; ++i) q.zh_inv[i] = pk->zh_inv[i];
+            HeavyScope hv(c, st);
+            B200_LAUNCH(k_quotient, grid_for(m, 128), 128, 0, hv.run)(q);
+            // back to coefficients: nc size-n inverse transforms, then un-scale and un-mix the cosets
+            if ((r = ntt_device(dn, w.quot, nscr, 1, 0, (unsigned)pk->nc, n, hv.run)) != B200_OK) return r;
+            if (pk->nc == 6) B200_LAUNCH(k_coset_combine<6>, grid_for(n, 128), 128, 0, hv.run)(w.quot, n, pk->cscale_inv, pk->comb);
+            else B200_LAUNCH(k_coset_combine<8>, grid_for(n, 128), 128, 0, hv.run)(w.quot, n, pk->cscale_inv, pk->comb);
+        }
+        B200_CUDA(cudaMemsetAsync(w.flag, 0, 4, st));
+        B200_LAUNCH(k_check_degree, grid_for(m - deg, 256), 256, 0, st)(w.quot, deg, m, w.flag);
+        B200_CUDA(cudaMemcpyAsync(h_flag, w.flag, 4, cudaMemcpyDeviceToHost, st));
+        B200_LAUNCH(k_split_quotient, dim3(grid_for(n + 3, 256), NW), 256, 0, st)(w.quot, n, S, &dp->blind_q[0], w.split);
+        return B200_OK;
+    });
+    if (rc != B200_OK) return rc;
+    if ((rc = commit_collect(c, NW, proof->split_quot_poly_comms)) != B200_OK) return rc;
     if (*h_flag) {  // copied before the commitments' window sums on the same stream
         set_error("WrongQuotientPolyDegree: the witness does not satisfy the circuit");
         return B200_ERR_UNSATISFIED;
     }
     for (int i = 0; i < NW; ++i) tr.append_commitment(proof->split_quot_poly_comms[i]);
-    mark();  // [3] round 3: the 5 quotient commitments
+    mark();  // [3] round 3: quotient and its 5 commitments
 
     // ---- round 4 ------------------------------------------------------------------------------------
     const fe zeta = tr.get_and_append_challenge();
     const fe zeta_w = FMUL(zeta, pk->group_gen);
+    fe* h_evals = reinterpret_cast<fe*>(reinterpret_cast<char*>(c->h_small.p) + 64);  // pinned
     {
         const fe* polys[kMaxEval];
         size_t lens[kMaxEval];
@@ -900,10 +1088,22 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         for (int i = 0; i < NW; ++i) { polys[i] = w.wpoly + (size_t)i * S; lens[i] = n + 2; pts[i] = zeta; }
         for (int i = 0; i < NW - 1; ++i) { polys[NW + i] = pk->sig_coeffs + (size_t)i * n; lens[NW + i] = n; pts[NW + i] = zeta; }
         polys[2 * NW - 1] = w.zpoly; lens[2 * NW - 1] = n + 3; pts[2 * NW - 1] = zeta_w;
-        eval_batch(polys, lens, pts, 2 * NW, w.evals, w.escr, st);
+        for (int q = 0; q < 2 * NW; ++q) {
+            fe z = pts[q];
+            for (int l = 0; l < kLevels; ++l) {
+                hp->eval_z[l][q] = z;
+                z = host_pow(z, CH);
+            }
+        }
+        rc = run_segment(gs, 5, st, [&]() -> int {
+            int r = push_params();
+            if (r != B200_OK) return r;
+            eval_batch(polys, lens, pts, 2 * NW, w.evals, w.escr, st, dp->eval_z);
+            B200_CUDA(cudaMemcpyAsync(h_evals, w.evals, 2 * NW * sizeof(fe), cudaMemcpyDeviceToHost, st));
+            return B200_OK;
+        });
+        if (rc != B200_OK) return rc;
     }
-    fe* h_evals = reinterpret_cast<fe*>(reinterpret_cast<char*>(c->h_small.p) + 64);  // pinned
-    B200_CUDA(cudaMemcpyAsync(h_evals, w.evals, 2 * NW * sizeof(fe), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < NW; ++i) proof->wires_evals[i] = h_evals[i];
     for (int i = 0; i < NW - 1; ++i) proof->wire_sigma_evals[i] = h_evals[NW + i];
@@ -915,15 +1115,15 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 
     // ---- round 5 ------------------------------------------------------------------------------------
     const fe v = tr.get_and_append_challenge();
+    LinArgs la{};
     {
         const fe* we = proof->wires_evals;
         const fe* se = proof->wire_sigma_evals;
-        LinArgs a;
         int t = 0;
-        auto push = [&](const fe* p, size_t len, const fe& s) {
-            a.p[t] = p;
-            a.len[t] = (uint32_t)len;
-            a.s[t] = s;
+        auto push = [&](const fe* p, size_t len, const fe& s) {  // pointers and lengths: launch arguments; scalars: ProofParams
+            la.p[t] = p;
+            la.len[t] = (uint32_t)len;
+            hp->lin_s[t] = s;
             ++t;
         };
         auto pow5 = [&](const fe& x) { return FMUL(fe_sqr<Fr>(fe_sqr<Fr>(x)), x); };
@@ -963,19 +1163,27 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
             cv = FMUL(cv, v);
             push(pk->sig_coeffs + (size_t)i * n, n, cv);
         }
-        a.count = t;
-        B200_LAUNCH(k_lincomb, grid_for(n + 3, 128), 128, 0, st)(a, n + 3, w.lin);
+        la.count = t;
+        la.dyn = &dp->lin_s[0];
     }
-    // opening proofs: commit((batch - batch(zeta)) / (X - zeta)) and commit((z - z(zeta w)) / (X - zeta w))
-    horner_suffix(w.lin, n + 3, zeta, w.sdiv, w.evals + 16, w.hscr, st);
-    horner_suffix(w.zpoly, n + 3, zeta_w, w.sdiv + (S + 8), w.evals + 17, w.hscr, st);
-    {
-        g1_affine open2[2];
-        if ((rc = commit_batch(c, pk, w.sdiv + 1, n + 2, S + 8, 2, open2)) != B200_OK) return rc;
-        proof->opening_proof = open2[0];
-        proof->shifted_opening_proof = open2[1];
-    }
+    fill_open_params(&hp->open[0], zeta);
+    fill_open_params(&hp->open[1], zeta_w);
+    g1_affine open2[2];
+    rc = commit_enqueue(6, w.sdiv + 1, n + 2, S + 8, 2, [&]() -> int {
+        int r = push_params();
+        if (r != B200_OK) return r;
+        B200_LAUNCH(k_lincomb, grid_for(n + 3, 128), 128, 0, st)(la, n + 3, w.lin);
+        // opening proofs: commit((batch - batch(zeta)) / (X - zeta)) and commit((z - z(zeta w)) / (X - zeta w))
+        horner_suffix(w.lin, n + 3, zeta, w.sdiv, w.evals + 16, w.hscr, st, &dp->open[0]);
+        horner_suffix(w.zpoly, n + 3, zeta_w, w.sdiv + (S + 8), w.evals + 17, w.hscr, st, &dp->open[1]);
+        return B200_OK;
+    });
+    if (rc != B200_OK) return rc;
+    if ((rc = commit_collect(c, 2, open2)) != B200_OK) return rc;
+    proof->opening_proof = open2[0];
+    proof->shifted_opening_proof = open2[1];
     mark();  // [5] round 5
+    if (gset && !gs) gset->proofs_seen = 1;  // this key has now run eagerly on this context: later proofs replay graphs
     if (h_challenges) {
         tr.append_commitment(proof->opening_proof);
         tr.append_commitment(proof->shifted_opening_proof);
@@ -1026,7 +1234,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     B200_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
     const fe one = fe_one<Fr>();
     {
-        LinArgs a;
+        LinArgs a{};
         a.count = 2;
         a.p[0] = d_a1; a.len[0] = (uint32_t)len1; a.s[0] = one;
         a.p[1] = d_a2; a.len[1] = (uint32_t)len2; a.s[1] = fe_neg<Fr>(one);
@@ -1069,7 +1277,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     fe zd = one;
     for (size_t i = 0; i < size; ++i) zd = FMUL(zd, FSUB(eta, roots[i]));
     {
-        LinArgs a;
+        LinArgs a{};
         a.count = 2;
         a.p[0] = d_diff; a.len[0] = (uint32_t)len; a.s[0] = one;
         a.p[1] = cur; a.len[1] = (uint32_t)cur_len; a.s[1] = fe_neg<Fr>(zd);
