@@ -332,6 +332,20 @@ __global__ void k_check_degree(const fe* __restrict__ q, size_t deg, size_t m, u
     }
 }
 
+// out[j] = prod_i (x_j - roots[i]), x_j = g * w^j the j-th point of the coset g * H_N (tw[k] = w^k, k < N/2)
+__global__ void k_vanishing_on_coset(const fe* __restrict__ tw, size_t N, fe g, const fe* __restrict__ roots, size_t count,
+                                     fe* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const size_t half = N >> 1;
+    fe wj = fe_load_ro(tw + (j < half ? j : j - half));
+    if (j >= half) wj = fe_neg<Fr>(wj);
+    const fe x = FMUL(g, wj);
+    fe acc = fe_one<Fr>();
+    for (size_t i = 0; i < count; ++i) acc = FMUL(acc, FSUB(x, fe_load_ro(roots + i)));
+    fe_store(out + j, acc);
+}
+
 // flag |= 1 when any of the `count` elements is non-zero (single small block)
 __global__ void k_any_nonzero(const fe* __restrict__ v, size_t count, uint32_t* flag) {
     for (size_t i = threadIdx.x; i < count; i += blockDim.x)
@@ -1199,8 +1213,9 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
 // &group_layout, &commit_key)` (circuits-core/src/zk_circuits/proof_linking/intent_only.rs:42-47,
 // intent_and_balance.rs:66-72): q = (a1 - a2) / Z_D with Z_D = prod_{i<size} (X - g^(offset+i)),
 // g the generator of the 2^alignment roots of unity (`GroupLayout`); eta from the transcript;
-// opening of a1 - a2 - Z_D(eta) q at eta.  Division by Z_D = `size` synthetic divisions (Horner suffix
-// scans ping-ponging between two buffers).
+// opening of a1 - a2 - Z_D(eta) q at eta.  The reference divides by the `size` linear factors in turn; here the
+// division runs on an evaluation domain (coset transform, pointwise division by Z_D, inverse transform): the same
+// quotient, and an inexact division shows as a quotient of too high a degree.
 // ---------------------------------------------------------------------------------------------
 struct LinkOut {
     g1_affine quotient_commitment;
@@ -1218,16 +1233,30 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     }
     cudaStream_t st = c->stream;
     int rc;
-    const size_t L = len + 8;
+    // Division by Z_D on an evaluation domain: N = 2^k >= len points of the coset g * H_N (Z_D has no root there).
+    // diff / Z_D pointwise, back to coefficients: the quotient when the division is exact — and exact it is iff the
+    // interpolant's degree is len - 1 - size (p * Z_D - diff has degree < N and vanishes on N points).  Two transforms,
+    // one batch inversion and three element-wise kernels instead of `size` dependent synthetic divisions.
+    unsigned log_N = 1;
+    while (((size_t)1 << log_N) < len) ++log_N;
+    if (log_N > 28) {
+        set_error("link: polynomial too long");
+        return B200_ERR_INVALID;
+    }
+    const size_t N = (size_t)1 << log_N;
+    const size_t L = len + 8, NL = N + 8;
     const size_t scr = 4 * (L / CH + 4 * CH + 64);
-    if ((rc = c->plonk_ws.reserve((6 * L + scr + size + 16) * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->plonk_ws.reserve((5 * L + 3 * NL + scr + size + 16) * sizeof(fe))) != B200_OK) return rc;
+    if ((rc = c->ntt_scratch.reserve(N * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->h_small.reserve(4096)) != B200_OK) return rc;
+    Domain* dN = nullptr;
+    if ((rc = get_domain(c, log_N, &dN)) != B200_OK) return rc;
     fe* base = reinterpret_cast<fe*>(c->plonk_ws.p);
-    fe *d_a1 = base, *d_a2 = base + L, *d_diff = base + 2 * L, *d_ident = base + 3 * L;
-    fe* d_pp[2] = {base + 4 * L, base + 5 * L};  // ping-pong buffers of the successive divisions
-    fe* hscr = base + 6 * L;
-    fe* rems = hscr + scr;       // remainder of division i (the value of the running quotient at root i)
-    fe* slot = rems + size;      // 16 spare elements: evaluation slot, then the remainder flag
+    fe *d_a1 = base, *d_a2 = base + L, *d_diff = base + 2 * L, *d_ident = base + 3 * L, *d_open = base + 4 * L;
+    fe *d_E = base + 5 * L, *d_Z = d_E + NL, *d_ZS = d_Z + NL;  // evaluations / quotient, Z_D on the coset, inversion scratch
+    fe* hscr = d_ZS + NL;
+    fe* d_roots = hscr + scr;    // the `size` roots of the group's vanishing polynomial
+    fe* slot = d_roots + size;   // 16 spare elements: evaluation slot, then the exactness flag
     uint32_t* d_flag = reinterpret_cast<uint32_t*>(slot + 4);
     B200_CUDA(cudaMemcpyAsync(d_a1, h_a1, len1 * sizeof(fe), cudaMemcpyDefault, st));
     B200_CUDA(cudaMemcpyAsync(d_a2, h_a2, len2 * sizeof(fe), cudaMemcpyDefault, st));
@@ -1240,23 +1269,29 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
         a.p[1] = d_a2; a.len[1] = (uint32_t)len2; a.s[1] = fe_neg<Fr>(one);
         B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_diff);
     }
-    // roots of the link group's vanishing polynomial
+    // roots of the link group's vanishing polynomial: g_a^(offset + i), g_a the generator of the 2^alignment roots of unity
     const fe g = host_root_of_unity(alignment);
     std::vector<fe> roots(size);
     fe root = host_pow(g, (uint64_t)offset);
-    const fe* cur = d_diff;
-    size_t cur_len = len;
+    fill_powers(d_roots, size, g, root, st);
     for (size_t i = 0; i < size; ++i) {
         roots[i] = root;
-        fe* dst = d_pp[i & 1];
-        horner_suffix(cur, cur_len, root, dst, rems + i, hscr, st);
-        cur = dst + 1;  // the quotient; the remainder S[0] was also written to rems[i]
-        --cur_len;
         root = FMUL(root, g);
     }
-    // a1 and a2 must agree on every root of the group, i.e. every division is exact: otherwise no link
-    // proof verifies and the reference's prover output would be rejected (silent bad proof)
-    B200_LAUNCH(k_any_nonzero, 1, 256, 0, st)(rems, size, d_flag);
+    B200_CUDA(cudaMemsetAsync(d_E, 0, N * sizeof(fe), st));
+    B200_CUDA(cudaMemcpyAsync(d_E, d_diff, len * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    fe* nscr = reinterpret_cast<fe*>(c->ntt_scratch.p);
+    if ((rc = ntt_device(dN, d_E, nscr, /*inverse=*/0, /*coset=*/1, 1, N, st)) != B200_OK) return rc;
+    B200_LAUNCH(k_vanishing_on_coset, grid_for(N, 128), 128, 0, st)(dN->tw_fwd, N, fe_from_u32<Fr>(5), d_roots, size, d_Z);
+    B200_LAUNCH(k_batch_inverse, grid_for((N + 15) / 16, 64), 64, 0, st)(d_Z, d_ZS, N);
+    fe* d_Q = d_ZS;  // the inversion's scratch is free again: quotient evaluations, then coefficients
+    B200_LAUNCH(k_fr_vec_op, grid_for(N, 256), 256, 0, st)(2, d_E, d_Z, 0, N, d_Q);
+    if ((rc = ntt_device(dN, d_Q, nscr, /*inverse=*/1, /*coset=*/1, 1, N, st)) != B200_OK) return rc;
+    const fe* cur = d_Q;  // the quotient
+    const size_t cur_len = len - size;
+    // a1 and a2 must agree on every root of the group, i.e. the division is exact: otherwise no link proof verifies
+    // and the reference's prover output would be rejected (silent bad proof)
+    B200_LAUNCH(k_any_nonzero, 1, 256, 0, st)(d_Q + cur_len, N - cur_len, d_flag);
     uint32_t* h_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_small.p) + 1024);
     B200_CUDA(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     {
@@ -1283,7 +1318,6 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
         a.p[1] = cur; a.len[1] = (uint32_t)cur_len; a.s[1] = fe_neg<Fr>(zd);
         B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_ident);
     }
-    fe* d_open = d_pp[size & 1];  // the buffer that does not hold the quotient
     horner_suffix(d_ident, len, eta, d_open, slot, hscr, st);
     {
         ProvingKey tmp;
