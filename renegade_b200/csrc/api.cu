@@ -16,7 +16,7 @@ static thread_local std::string g_last_error;
 std::atomic<uint64_t> g_kernel_launches{0};
 std::atomic<uint64_t> g_launch_host_ns{0};
 std::atomic<uint64_t> g_graph_launches{0};
-std::atomic<uint64_t> g_alloc_epoch{1};
+std::atomic<uint64_t> g_object_ids{1};
 thread_local uint64_t t_kernel_launches = 0;
 
 void set_error(const std::string& msg) { g_last_error = msg; }

@@ -33,7 +33,6 @@ int cuda_fail(cudaError_t e, const char* what);  // records the message, returns
 extern std::atomic<uint64_t> g_kernel_launches;
 extern std::atomic<uint64_t> g_launch_host_ns;
 extern std::atomic<uint64_t> g_graph_launches;  // cudaGraphLaunch calls (a replayed prover round is one submission)
-extern std::atomic<uint64_t> g_alloc_epoch;     // bumped whenever a DevBuf / HostPinned changes address: captured graphs go stale
 extern thread_local uint64_t t_kernel_launches; // this thread's launches (what a stream capture recorded)
 // Counts the launch and the host time its submission took: the temporary lives until the end of the launch statement.
 struct LaunchClock {
@@ -53,7 +52,6 @@ struct DevBuf {
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return B200_OK;
-        g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -73,7 +71,6 @@ struct HostPinned {
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return B200_OK;
-        g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
@@ -114,7 +111,10 @@ struct MsmPlan {
     int n_tables = 0; // F = ceil(W / Wp); table j holds 2^(c*Wp*j) * P
 };
 
+extern std::atomic<uint64_t> g_object_ids;  // proving keys and base sets: never reused, what captured graphs are keyed by
+
 struct Bases {
+    uint64_t id = g_object_ids.fetch_add(1);
     size_t n = 0;
     MsmPlan plan;
     g1_affine* tables = nullptr;  // n_tables * n affine points, table-major
@@ -181,10 +181,11 @@ int splitmix_fr_device(uint64_t seed, size_t first, size_t n, int montgomery, fe
 
 // ---- prover rounds as CUDA graphs -----------------------------------------------------------------
 // One set per (context, proving key): the launches of each prover segment, captured on the second proof of that key
-// on that context (the first sizes every buffer) and replayed afterwards.  Stale when any buffer moved (alloc epoch).
+// on that context (the first sizes every buffer) and replayed afterwards.  Stale when a buffer of the context moved
+// (`buffers`: a fingerprint of the addresses the launches refer to).
 constexpr int kProofSegs = 7;
 struct ProofGraphSet {
-    uint64_t pk_id = 0, epoch = 0, last_use = 0;
+    uint64_t key = 0, sub[6] = {}, buffers = 0, last_use = 0;  // proofs: key = the proving key's id; link proofs: see link()
     unsigned proofs_seen = 0;
     bool timing = false;  // captured with the MSM's timing events as graph nodes
     cudaGraphExec_t exec[kProofSegs] = {};

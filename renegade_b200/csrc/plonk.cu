@@ -419,6 +419,11 @@ struct ProofParams {
     OpenParams open[2];            // zeta, zeta * w
 };
 
+struct LinkParams {  // the same for a link proof
+    fe lin_s[4];      // 1, -Z_D(eta)
+    OpenParams open;  // eta
+};
+
 inline unsigned grid_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -426,10 +431,8 @@ inline unsigned grid_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1)
 // ---------------------------------------------------------------------------------------------
 // host-side structures
 // ---------------------------------------------------------------------------------------------
-static std::atomic<uint64_t> g_pk_ids{1};
-
 struct ProvingKey {
-    uint64_t id = g_pk_ids.fetch_add(1);  // never reused: what a context's captured graphs are keyed by
+    uint64_t id = g_object_ids.fetch_add(1);  // never reused: what a context's captured graphs are keyed by
     unsigned log_n = 0;
     size_t n = 0, m = 0, num_inputs = 0;
     KArr k;
@@ -633,14 +636,6 @@ static Workspace carve(fe* base, size_t n) {
     return w;
 }
 
-static int commit(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, g1_affine* out) {
-    int inf = 0;
-    int rc = msm_device(pk->srs, 0, d_coeffs, len, /*montgomery=*/1, &c->msm, c->stream, out, &inf);
-    if (rc != B200_OK) return rc;
-    if (inf) std::memset(out, 0, sizeof(*out));
-    return B200_OK;
-}
-
 // `count` commitments to polynomials `stride` coefficients apart, in one batched MSM
 static int commit_batch(Context* c, const ProvingKey* pk, const fe* d_coeffs, size_t len, size_t stride,
                         unsigned count, g1_affine* out) {
@@ -790,7 +785,22 @@ static_assert(sizeof(ProofOut) == sizeof(b200_proof), "proof layout");
 // segment between two host synchronisations is captured once (second proof of a key on a context; the first runs
 // eagerly and sizes every buffer) and replayed as ONE submission afterwards: ~90 kernel launches per proof become 7
 // graph launches.  Same kernels, same order, same bytes out.
-static ProofGraphSet* graph_set_for(Context* c, const ProvingKey* pk) {
+// the addresses a captured segment refers to besides the key's: every grow-only buffer of the context
+static uint64_t buffer_fingerprint(const Context* c) {
+    const MsmScratch& m = c->msm;
+    const void* ps[] = {c->plonk_ws.p, c->ntt_scratch.p, c->ntt_scratch2.p, c->h_small.p, c->h_params.p, c->d_params.p,
+                        m.counts.p, m.offsets.p, m.cursor.p, m.entries.p, m.buckets.p, m.window_sums.p, m.scalars.p,
+                        m.seg_offsets.p, m.seg_bucket.p, m.seg_sums.p, m.heavy.p, m.seg_order.p, m.scan_state.p, m.tree.p,
+                        m.bit_sums.p, m.h_sums.p};
+    uint64_t h = 1469598103934665603ull;
+    for (const void* p : ps) {
+        h ^= (uint64_t)(uintptr_t)p;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+static ProofGraphSet* graph_set_for(Context* c, uint64_t key, const uint64_t* sub = nullptr) {
     int on = c->use_graphs;
     if (on < 0) {
         static const bool env_on = [] {
@@ -801,10 +811,12 @@ static ProofGraphSet* graph_set_for(Context* c, const ProvingKey* pk) {
     }
     if (!on) return nullptr;
     ProofGraphSet* gs = nullptr;
+    const uint64_t no_sub[6] = {};
+    if (!sub) sub = no_sub;
     for (ProofGraphSet* g : c->graph_sets)
-        if (g->pk_id == pk->id) gs = g;
+        if (g->key == key && std::memcmp(g->sub, sub, sizeof(g->sub)) == 0) gs = g;
     if (!gs) {
-        if (c->graph_sets.size() >= 8) {  // keys come and go: drop the least recently used set
+        if (c->graph_sets.size() >= 32) {  // keys come and go: drop the least recently used set
             size_t lru = 0;
             for (size_t i = 1; i < c->graph_sets.size(); ++i)
                 if (c->graph_sets[i]->last_use < c->graph_sets[lru]->last_use) lru = i;
@@ -812,20 +824,21 @@ static ProofGraphSet* graph_set_for(Context* c, const ProvingKey* pk) {
             c->graph_sets.erase(c->graph_sets.begin() + (long)lru);
         }
         gs = new ProofGraphSet();
-        gs->pk_id = pk->id;
+        gs->key = key;
+        std::memcpy(gs->sub, sub, sizeof(gs->sub));
         c->graph_sets.push_back(gs);
     }
     gs->last_use = ++c->graph_clock;
-    const uint64_t epoch = g_alloc_epoch.load(std::memory_order_relaxed);
-    if (gs->epoch != epoch || gs->timing != c->msm.timing) {  // a buffer moved since the capture (any context), or the
-                                                              // MSM timing events were switched: capture again
+    const uint64_t buffers = buffer_fingerprint(c);
+    if (gs->buffers != buffers || gs->timing != c->msm.timing) {  // a buffer moved since the capture (a larger key grew
+                                                                  // it), or the MSM timing events were switched
         gs->timing = c->msm.timing;
         for (auto& e : gs->exec)
             if (e) {
                 cudaGraphExecDestroy(e);
                 e = nullptr;
             }
-        gs->epoch = epoch;
+        gs->buffers = buffers;
     }
     return gs;
 }
@@ -863,6 +876,24 @@ static int run_segment(ProofGraphSet* gs, int idx, cudaStream_t st, F&& fn) {
         std::memory_order_relaxed);
     g_graph_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+    return B200_OK;
+}
+
+// Enqueue `count` commitments as segment `idx` (after `before`'s launches), leaving the batch pending for commit_collect.
+template <class F>
+static int commit_enqueue(Context* c, const Bases* srs, ProofGraphSet* gs, int idx, const fe* d_coeffs, size_t len, size_t stride,
+                          unsigned count, F&& before) {
+    cudaStream_t st = c->stream;
+    const int r = run_segment(gs, idx, st, [&]() -> int {
+        const int r2 = before();
+        if (r2 != B200_OK) return r2;
+        return msm_launch_batch(srs, 0, d_coeffs, len, stride, count, /*montgomery=*/1, &c->msm, st);
+    });
+    if (r != B200_OK) return r;
+    if (gs) {  // what msm_launch_batch leaves behind when it runs outside a capture
+        msm_mark_pending(srs, len, count, &c->msm);
+        B200_CUDA(cudaEventRecord(c->msm.done_ev, st));
+    }
     return B200_OK;
 }
 
@@ -912,7 +943,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
     const fe one = fe_one<Fr>();
 
     // graphs: only once a proof of this key has run eagerly on this context (every buffer has its final size then)
-    ProofGraphSet* gset = graph_set_for(c, pk);
+    ProofGraphSet* gset = graph_set_for(c, pk->id);
     ProofGraphSet* gs = gset && gset->proofs_seen > 0 ? gset : nullptr;
     c->msm.in_graph = gs != nullptr;
     struct InGraphReset {
@@ -926,19 +957,8 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         B200_CUDA(cudaMemcpyAsync(dp, hp, sizeof(ProofParams), cudaMemcpyHostToDevice, st));
         return B200_OK;
     };
-    // enqueue `count` commitments (segment idx), leaving the batch pending for commit_collect
     auto commit_enqueue = [&](int idx, const fe* d_coeffs, size_t len, size_t stride, unsigned count, auto&& before) -> int {
-        int r = run_segment(gs, idx, st, [&]() -> int {
-            int r2 = before();
-            if (r2 != B200_OK) return r2;
-            return msm_launch_batch(pk->srs, 0, d_coeffs, len, stride, count, /*montgomery=*/1, &c->msm, st);
-        });
-        if (r != B200_OK) return r;
-        if (gs) {  // what msm_launch_batch leaves behind when it runs outside a capture
-            msm_mark_pending(pk->srs, len, count, &c->msm);
-            B200_CUDA(cudaEventRecord(c->msm.done_ev, st));
-        }
-        return B200_OK;
+        return b200::commit_enqueue(c, pk->srs, gs, idx, d_coeffs, len, stride, count, before);
     };
     auto nothing = []() -> int { return B200_OK; };
 
@@ -1249,56 +1269,72 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     if ((rc = c->plonk_ws.reserve((5 * L + 3 * NL + scr + size + 16) * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch.reserve(N * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->h_small.reserve(4096)) != B200_OK) return rc;
+    if ((rc = c->h_params.reserve(sizeof(ProofParams))) != B200_OK) return rc;
+    if ((rc = c->d_params.reserve(sizeof(ProofParams))) != B200_OK) return rc;
     Domain* dN = nullptr;
     if ((rc = get_domain(c, log_N, &dN)) != B200_OK) return rc;
     fe* base = reinterpret_cast<fe*>(c->plonk_ws.p);
     fe *d_a1 = base, *d_a2 = base + L, *d_diff = base + 2 * L, *d_ident = base + 3 * L, *d_open = base + 4 * L;
-    fe *d_E = base + 5 * L, *d_Z = d_E + NL, *d_ZS = d_Z + NL;  // evaluations / quotient, Z_D on the coset, inversion scratch
+    fe *d_E = base + 5 * L, *d_Z = d_E + NL, *d_ZS = d_Z + NL;  // evaluations, Z_D on the coset, inversion scratch / quotient
     fe* hscr = d_ZS + NL;
     fe* d_roots = hscr + scr;    // the `size` roots of the group's vanishing polynomial
     fe* slot = d_roots + size;   // 16 spare elements: evaluation slot, then the exactness flag
     uint32_t* d_flag = reinterpret_cast<uint32_t*>(slot + 4);
-    B200_CUDA(cudaMemcpyAsync(d_a1, h_a1, len1 * sizeof(fe), cudaMemcpyDefault, st));
+    fe* nscr = reinterpret_cast<fe*>(c->ntt_scratch.p);
+    uint32_t* h_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_small.p) + 1024);
+    // the launches depend on (context, SRS, lengths, layout) only: two graph segments, like the prover's rounds
+    const uint64_t sub[6] = {srs->id, (uint64_t)len1, (uint64_t)len2, (uint64_t)alignment, (uint64_t)offset, (uint64_t)size};
+    ProofGraphSet* gset = graph_set_for(c, ~(uint64_t)0, sub);
+    ProofGraphSet* gs = gset && gset->proofs_seen > 0 ? gset : nullptr;
+    c->msm.in_graph = gs != nullptr;
+    struct InGraphReset {
+        MsmScratch& s;
+        ~InGraphReset() { s.in_graph = false; }
+    } in_graph_reset{c->msm};
+    LinkParams* hp = reinterpret_cast<LinkParams*>(c->h_params.p);
+    LinkParams* dp = reinterpret_cast<LinkParams*>(c->d_params.p);
+    static_assert(sizeof(LinkParams) <= sizeof(ProofParams), "one parameter block serves both");
+
+    B200_CUDA(cudaMemcpyAsync(d_a1, h_a1, len1 * sizeof(fe), cudaMemcpyDefault, st));  // caller-owned: outside the graphs
     B200_CUDA(cudaMemcpyAsync(d_a2, h_a2, len2 * sizeof(fe), cudaMemcpyDefault, st));
-    B200_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
     const fe one = fe_one<Fr>();
-    {
-        LinArgs a{};
-        a.count = 2;
-        a.p[0] = d_a1; a.len[0] = (uint32_t)len1; a.s[0] = one;
-        a.p[1] = d_a2; a.len[1] = (uint32_t)len2; a.s[1] = fe_neg<Fr>(one);
-        B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_diff);
-    }
     // roots of the link group's vanishing polynomial: g_a^(offset + i), g_a the generator of the 2^alignment roots of unity
     const fe g = host_root_of_unity(alignment);
     std::vector<fe> roots(size);
     fe root = host_pow(g, (uint64_t)offset);
-    fill_powers(d_roots, size, g, root, st);
+    const fe root0 = root;
     for (size_t i = 0; i < size; ++i) {
         roots[i] = root;
         root = FMUL(root, g);
     }
-    B200_CUDA(cudaMemsetAsync(d_E, 0, N * sizeof(fe), st));
-    B200_CUDA(cudaMemcpyAsync(d_E, d_diff, len * sizeof(fe), cudaMemcpyDeviceToDevice, st));
-    fe* nscr = reinterpret_cast<fe*>(c->ntt_scratch.p);
-    if ((rc = ntt_device(dN, d_E, nscr, /*inverse=*/0, /*coset=*/1, 1, N, st)) != B200_OK) return rc;
-    B200_LAUNCH(k_vanishing_on_coset, grid_for(N, 128), 128, 0, st)(dN->tw_fwd, N, fe_from_u32<Fr>(5), d_roots, size, d_Z);
-    B200_LAUNCH(k_batch_inverse, grid_for((N + 15) / 16, 64), 64, 0, st)(d_Z, d_ZS, N);
-    fe* d_Q = d_ZS;  // the inversion's scratch is free again: quotient evaluations, then coefficients
-    B200_LAUNCH(k_fr_vec_op, grid_for(N, 256), 256, 0, st)(2, d_E, d_Z, 0, N, d_Q);
-    if ((rc = ntt_device(dN, d_Q, nscr, /*inverse=*/1, /*coset=*/1, 1, N, st)) != B200_OK) return rc;
-    const fe* cur = d_Q;  // the quotient
-    const size_t cur_len = len - size;
-    // a1 and a2 must agree on every root of the group, i.e. the division is exact: otherwise no link proof verifies
-    // and the reference's prover output would be rejected (silent bad proof)
-    B200_LAUNCH(k_any_nonzero, 1, 256, 0, st)(d_Q + cur_len, N - cur_len, d_flag);
-    uint32_t* h_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->h_small.p) + 1024);
-    B200_CUDA(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
-    {
-        ProvingKey tmp;  // commit() only needs the SRS
-        tmp.srs = srs;
-        if ((rc = commit(c, &tmp, cur, cur_len, &out->quotient_commitment)) != B200_OK) return rc;
-    }
+    fe* d_Q = d_ZS;  // the inversion's scratch is free again after it: quotient evaluations, then coefficients
+    const size_t q_len = len - size;
+    rc = commit_enqueue(c, srs, gs, 0, d_Q, q_len, q_len, 1, [&]() -> int {
+        int r;
+        B200_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+        {
+            LinArgs a{};
+            a.count = 2;
+            a.p[0] = d_a1; a.len[0] = (uint32_t)len1; a.s[0] = one;
+            a.p[1] = d_a2; a.len[1] = (uint32_t)len2; a.s[1] = fe_neg<Fr>(one);
+            B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_diff);
+        }
+        fill_powers(d_roots, size, g, root0, st);
+        B200_CUDA(cudaMemsetAsync(d_E, 0, N * sizeof(fe), st));
+        B200_CUDA(cudaMemcpyAsync(d_E, d_diff, len * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+        if ((r = ntt_device(dN, d_E, nscr, /*inverse=*/0, /*coset=*/1, 1, N, st)) != B200_OK) return r;
+        B200_LAUNCH(k_vanishing_on_coset, grid_for(N, 128), 128, 0, st)(dN->tw_fwd, N, fe_from_u32<Fr>(5), d_roots, size, d_Z);
+        B200_LAUNCH(k_batch_inverse, grid_for((N + 15) / 16, 64), 64, 0, st)(d_Z, d_ZS, N);
+        B200_LAUNCH(k_fr_vec_op, grid_for(N, 256), 256, 0, st)(2, d_E, d_Z, 0, N, d_Q);
+        if ((r = ntt_device(dN, d_Q, nscr, /*inverse=*/1, /*coset=*/1, 1, N, st)) != B200_OK) return r;
+        // a1 and a2 must agree on every root of the group, i.e. the division is exact: otherwise no link proof verifies
+        // and the reference's prover output would be rejected (silent bad proof)
+        B200_LAUNCH(k_any_nonzero, 1, 256, 0, st)(d_Q + q_len, N - q_len, d_flag);
+        B200_CUDA(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+        return B200_OK;
+    });
+    if (rc != B200_OK) return rc;
+    if ((rc = commit_collect(c, 1, &out->quotient_commitment)) != B200_OK) return rc;
     if (*h_flag) {
         set_error("link: the two wire polynomials differ on the link group (wrong layout or mismatched witnesses)");
         return B200_ERR_UNSATISFIED;
@@ -1311,19 +1347,23 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     if (h_eta) *h_eta = eta;
     fe zd = one;
     for (size_t i = 0; i < size; ++i) zd = FMUL(zd, FSUB(eta, roots[i]));
-    {
+    hp->lin_s[0] = one;
+    hp->lin_s[1] = fe_neg<Fr>(zd);
+    fill_open_params(&hp->open, eta);
+    rc = commit_enqueue(c, srs, gs, 1, d_open + 1, len - 1, len - 1, 1, [&]() -> int {
+        B200_CUDA(cudaMemcpyAsync(dp, hp, sizeof(LinkParams), cudaMemcpyHostToDevice, st));
         LinArgs a{};
         a.count = 2;
-        a.p[0] = d_diff; a.len[0] = (uint32_t)len; a.s[0] = one;
-        a.p[1] = cur; a.len[1] = (uint32_t)cur_len; a.s[1] = fe_neg<Fr>(zd);
+        a.p[0] = d_diff; a.len[0] = (uint32_t)len;
+        a.p[1] = d_Q; a.len[1] = (uint32_t)q_len;
+        a.dyn = &dp->lin_s[0];
         B200_LAUNCH(k_lincomb, grid_for(len, 128), 128, 0, st)(a, len, d_ident);
-    }
-    horner_suffix(d_ident, len, eta, d_open, slot, hscr, st);
-    {
-        ProvingKey tmp;
-        tmp.srs = srs;
-        if ((rc = commit(c, &tmp, d_open + 1, len - 1, &out->opening_proof)) != B200_OK) return rc;
-    }
+        horner_suffix(d_ident, len, eta, d_open, slot, hscr, st, &dp->open);
+        return B200_OK;
+    });
+    if (rc != B200_OK) return rc;
+    if ((rc = commit_collect(c, 1, &out->opening_proof)) != B200_OK) return rc;
+    if (gset && !gs) gset->proofs_seen = 1;
     return B200_OK;
 }
 

@@ -98,3 +98,42 @@ def test_graphs_off_is_eager(ctx, oracle, pyoracle):
         ctx.use_graphs(True)
     pk.free()
     bases.free()
+
+
+def test_link_proofs_replayed(ctx, oracle, pyoracle):
+    """A link proof's launches depend on (SRS, lengths, layout) only: two graph segments from the second call on.  Different
+    witnesses (hence different eta) every time; each must equal the oracle's link proof; a wrong layout is still refused."""
+    from renegade_b200.backend import GroupLayout, link_proofs
+    py = pyoracle
+    layout = GroupLayout(alignment=7, offset=20, size=9)
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, (1 << 10) + 3)
+    bases = ctx.load_bases(srs)
+    ctx.use_graphs(True)
+    g0 = ctx.graph_launches()
+    for rnd in range(4):
+        vals = [(i * 0x9E3779B97F4A7C15 + 777 * rnd + 5) % py.R for i in range(layout.size)]
+        hints = []
+        for log_n, seed in ((9, 3), (10, 4)):  # a fresh key every round (the selectors may depend on the pinned values)
+            circ = synth.synth_circuit(log_n, num_inputs=5, seed=seed, check=True, link=(layout.alignment, layout.offset, vals))
+            pk = PlonkKzgSnark.preprocess(ctx, bases, log_n, circ.num_inputs, circ.selectors, circ.perm, circ.k)
+            _, hint = PlonkKzgSnark.prove_with_link_hint(ctx, pk, circ.wires, circ.pub_inputs, synth.splitmix_blinders(seed + rnd))
+            pk.free()
+            hints.append(hint)
+        lp, eta = link_proofs(ctx, bases, hints[0], hints[1], layout)
+        rc, olp, oeta = oracle.plonk_link(hints[0].linking_wire_poly, hints[1].linking_wire_poly, hints[0].linking_wire_comm,
+                                          hints[1].linking_wire_comm, layout.alignment, layout.offset, layout.size, srs)
+        assert rc == 0
+        assert (lp.to_array() == olp.to_array()).all() and (eta == oeta).all(), rnd
+        if rnd == 2:  # a REPLAYED first segment must still flag an inexact division: last round's second polynomial
+            with pytest.raises(B200Error) as err:
+                link_proofs(ctx, bases, hints[0], prev[1], layout)
+            assert err.value.code == -7
+            with pytest.raises(B200Error) as err:  # and a layout the proofs do not share (a key of its own: eager)
+                link_proofs(ctx, bases, hints[0], hints[1], GroupLayout(layout.alignment, layout.offset + 1, layout.size))
+            assert err.value.code == -7
+        prev = hints
+    # rounds 1..3: the link proof's 2 segments replayed, plus the first segment of the refused call; round 0 eager; the
+    # proofs use fresh keys (eager)
+    assert ctx.graph_launches() - g0 == 3 * 2 + 1
+    bases.free()
