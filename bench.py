@@ -510,12 +510,14 @@ def main():
         sampler.start()
     phases = []
     barrier()
-    launches0 = ctx._lib.b200_kernel_launches()  # the library counts every kernel it launches
+    launches0 = ctx._lib.b200_kernel_launches()  # the library counts every kernel it launches (replayed graph nodes included)
+    graphs0 = ctx._lib.b200_graph_launches()
     t = time.perf_counter()
     proof = run_proofs(args.steps, d_wires.data_ptr(), args.warmup, phases)
     barrier()
     dt = max_over_ranks(time.perf_counter() - t)
     gpu_launches = int(ctx._lib.b200_kernel_launches() - launches0)
+    graph_launches = int(ctx._lib.b200_graph_launches() - graphs0)
     clocks = sampler.stop() if rank == 0 else None
     acc_tot = [c.msm_timing_totals(reset=True) for c in ctxs]
     # ---- the same through the public call with HOST buffers (e2e) ---------------------------------------
@@ -758,6 +760,8 @@ def main():
         # counted by the library (b200_kernel_launches) around the timed region of this rank; the ncu launch list
         # of the same command is under profiles/ (tools/kernel_shares.py gives launches per proof)
         "gpu_launches": gpu_launches * world, "gpu_launches_per_proof": gpu_launches / max(args.steps, 1),
+        # host submissions: from the second proof of a key on a worker each prover round is one CUDA-graph launch
+        "graph_launches_per_proof": graph_launches / max(args.steps, 1),
         "latency_ms_one_proof_in_flight": single_ms, "latency_phases_ms": single,
         "clocks": clocks, "setup_s": setup_s, "msm": msm, "ntt": ntt,
     })
