@@ -142,6 +142,9 @@ struct MsmScratch {
     float ms[4] = {0, 0, 0, 0};  // total, sort (count+scan+scatter), accumulate, reduce
     // running totals since timing was switched on: accumulate ms, (point, scalar) pairs, launches
     double tot_acc_ms = 0, tot_pairs = 0, tot_launches = 0;
+    // the final weighted sum of each window's bit sums runs on the host (msm_finish_batch); false: msm_horner_kernel leaves the
+    // window sums on the device (the multi-GPU path adds them there)
+    bool host_horner = true;
     // set by a caller that captures / replays the launches as a CUDA graph: timing events become graph nodes, and the
     // caller records done_ev itself
     bool in_graph = false;

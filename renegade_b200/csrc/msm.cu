@@ -888,7 +888,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     const size_t tree_elems = row_l1 + col_l1 + n_R + n_C;
     if ((rc = s->tree.reserve((tree_elems + 1) * sizeof(g1_xyzz))) != B200_OK) return rc;
     if ((rc = s->window_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
-    if ((rc = s->h_sums.reserve(n_windows * sizeof(g1_xyzz))) != B200_OK) return rc;
+    if ((rc = s->h_sums.reserve(n_windows * 32 * sizeof(g1_xyzz))) != B200_OK) return rc;  // window sums, or their c - 1 bit sums
     if (!s->done_ev) B200_CUDA(cudaEventCreateWithFlags(&s->done_ev, cudaEventDisableTiming));
     if ((rc = s->bit_sums.reserve(n_windows * 32 * sizeof(g1_xyzz))) != B200_OK) return rc;
 
@@ -977,11 +977,16 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         g1_xyzz* bit_sums = (g1_xyzz*)s->bit_sums.p;
         B200_LAUNCH(msm_bitsum_kernel, dim3(n_bits, (unsigned)n_windows), kBitThreads, 0, st)(col_in, (uint32_t)l_log, row_in,
                                                                                                (uint32_t)r_log, bit_sums);
-        B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
+        // The last step, sum_b 2^b T_b, is a chain of c - 2 dependent doublings whoever runs it: ~5 us per operation for a lone
+        // warp, ~0.5 us for a host core.  The host takes it (msm_finish_batch) unless the sums are consumed on the device.
+        if (!s->host_horner) B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
     }
     B200_CUDA(cudaGetLastError());
     stamp(3);
-    B200_CUDA(cudaMemcpyAsync(s->h_sums.p, window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
+    if (s->host_horner)
+        B200_CUDA(cudaMemcpyAsync(s->h_sums.p, s->bit_sums.p, n_windows * (size_t)(pl.c - 1) * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
+    else
+        B200_CUDA(cudaMemcpyAsync(s->h_sums.p, window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     stamp(4);
     if (!s->in_graph) B200_CUDA(cudaEventRecord(s->done_ev, st));  // a replaying caller records it after the graph launch
     return B200_OK;
@@ -1025,6 +1030,19 @@ int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf) {
     // ONE field inversion for the whole batch (Montgomery's trick over the ZZZ coordinates) — a few
     // hundred bytes of work, read straight from the pinned copy of the window sums.
     const g1_xyzz* h_sums = reinterpret_cast<const g1_xyzz*>(s->h_sums.p);
+    std::vector<g1_xyzz> wsum;
+    if (s->host_horner) {  // window sum = sum_b 2^b T_b from the c - 1 bit sums of each window
+        const int n_bits = pl.c - 1;
+        const size_t n_windows = (size_t)batch * pl.n_phys;
+        wsum.resize(n_windows);
+        for (size_t w = 0; w < n_windows; ++w) {
+            const g1_xyzz* T = h_sums + w * (size_t)n_bits;
+            g1_xyzz acc = T[n_bits - 1];
+            for (int b = n_bits - 2; b >= 0; --b) acc = g1_add(g1_dbl(acc), T[b]);
+            wsum[w] = acc;
+        }
+        h_sums = wsum.data();
+    }
     std::vector<g1_xyzz> totals(batch);
     std::vector<fe> prefix(batch);
     fe run = fe_one<FqCfg>();

@@ -371,7 +371,10 @@ static int multi_msm(b200_multi* m, const b200_multi_bases* b, const void* const
         g1_xyzz* partial = reinterpret_cast<g1_xyzz*>(l.partial.p);
         if (cnt) {
             const Bases* bs = b->shard[i]->b;
-            if ((rc = msm_launch_batch(bs, 0, d_scalars, cnt, cnt, 1, montgomery, &c.msm, c.stream)) != B200_OK) return rc;
+            c.msm.host_horner = false;  // the window sums stay on the device
+            rc = msm_launch_batch(bs, 0, d_scalars, cnt, cnt, 1, montgomery, &c.msm, c.stream);
+            c.msm.host_horner = true;
+            if (rc != B200_OK) return rc;
             c.msm.pending_batch = 0;  // the window sums are consumed on the device, not by msm_finish_batch
             B200_LAUNCH(k_windows_to_point, 1, 32, 0, c.stream)(reinterpret_cast<const g1_xyzz*>(c.msm.window_sums.p), bs->plan.n_phys,
                                                       bs->plan.c, 0, partial);
