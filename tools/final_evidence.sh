@@ -16,7 +16,9 @@ for lg in 12 13 14 16; do timeout 200 python tools/prove_bench.py $lg 10 1 2>&1 
 echo "== bench (default)"; timeout 1200 python bench.py > gpurun_out/${T}_bench_default.json 2> gpurun_out/${T}_bench_default.err; tail -c 700 gpurun_out/${T}_bench_default.json; tail -3 gpurun_out/${T}_bench_default.err
 echo "== bench --impl reference"; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; tail -c 400 gpurun_out/${T}_bench_reference.json
 echo "== ncu launch lists"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/${T}_launches_bench.csv \
+# B200_GRAPHS=0: ncu dies (SIGSEGV, no message) when several host threads capture streams while it serialises kernels
+# (profiles/README.md, r2k); the kernels are the same eager or replayed, and one worker with graphs on profiles fine
+B200_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/${T}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-real-statements > gpurun_out/${T}_ncu_bench.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${T}_launches_proof16.csv \
     python tools/prove_bench.py 16 2 > gpurun_out/${T}_ncu_proof16.log 2>&1
