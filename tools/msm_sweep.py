@@ -1,6 +1,6 @@
 """Window-size / size sweep of the device MSM (device-resident inputs, CUDA-event phase times)."""
 import json
-import sys, os
+import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import renegade_b200 as rb
@@ -22,15 +22,19 @@ def main():
             bases = ctx.load_bases_device(d_pts.data_ptr(), n, window_bits=c)
             for _ in range(3):
                 out = ctx.msm_device(bases, d_s.data_ptr(), n)
-            ph = []
+            ph, wall = [], []
             for _ in range(5):
+                t0 = time.perf_counter()
                 out = ctx.msm_device(bases, d_s.data_ptr(), n)
+                wall.append((time.perf_counter() - t0) * 1e3)
                 ph.append(ctx.msm_timing(True))
             if ref is None:
                 ref = out
             ok = bool((out[0] == ref[0]).all())
             best = min(ph, key=lambda p: p["total"])
-            print(json.dumps({"log_n": lg, "plan": bases.plan, "ms": {k: round(v, 4) for k, v in best.items()}, "same_result": ok}), flush=True)
+            print(json.dumps({"log_n": lg, "plan": bases.plan, "ms": {k: round(v, 4) for k, v in best.items()},
+                              "wall_ms_call": round(min(wall), 4),  # the whole call: device phases + read-back + host epilogue (Horner over the bit sums, inversion)
+                              "same_result": ok}), flush=True)
             bases.free()
 
 if __name__ == "__main__":
