@@ -832,6 +832,15 @@ static void tree_shape(int c, int* l_log, int* r_log, int* a_row, int* a_col) {
 // msm_launch_batch only ENQUEUES (kernels + one D2H of the window sums into pinned memory);
 // msm_finish_batch waits for that copy and runs the host epilogue.  The prover queues further
 // work between the two.
+// B200_HOST_HORNER=0 keeps the last step of the reduction on the device (A/B measurements)
+static bool use_host_horner(const MsmScratch* s) {
+    static const bool env_on = [] {
+        const char* e = std::getenv("B200_HOST_HORNER");
+        return !(e && e[0] == '0');
+    }();
+    return s->host_horner && env_on;
+}
+
 int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_t n, size_t stride,
                      unsigned batch, int montgomery, MsmScratch* s, cudaStream_t st) {
     if (base_off + n > b->n) {
@@ -979,11 +988,11 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
                                                                                                (uint32_t)r_log, bit_sums);
         // The last step, sum_b 2^b T_b, is a chain of c - 2 dependent doublings whoever runs it: ~5 us per operation for a lone
         // warp, ~0.5 us for a host core.  The host takes it (msm_finish_batch) unless the sums are consumed on the device.
-        if (!s->host_horner) B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
+        if (!use_host_horner(s)) B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
     }
     B200_CUDA(cudaGetLastError());
     stamp(3);
-    if (s->host_horner)
+    if (use_host_horner(s))
         B200_CUDA(cudaMemcpyAsync(s->h_sums.p, s->bit_sums.p, n_windows * (size_t)(pl.c - 1) * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     else
         B200_CUDA(cudaMemcpyAsync(s->h_sums.p, window_sums, n_windows * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
@@ -1031,7 +1040,7 @@ int msm_finish_batch(MsmScratch* s, g1_affine* out, int* out_inf) {
     // hundred bytes of work, read straight from the pinned copy of the window sums.
     const g1_xyzz* h_sums = reinterpret_cast<const g1_xyzz*>(s->h_sums.p);
     std::vector<g1_xyzz> wsum;
-    if (s->host_horner) {  // window sum = sum_b 2^b T_b from the c - 1 bit sums of each window
+    if (use_host_horner(s)) {  // window sum = sum_b 2^b T_b from the c - 1 bit sums of each window
         const int n_bits = pl.c - 1;
         const size_t n_windows = (size_t)batch * pl.n_phys;
         wsum.resize(n_windows);
