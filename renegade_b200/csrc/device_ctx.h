@@ -109,6 +109,7 @@ struct MsmPlan {
     int n_digits = 0; // W = ceil(255 / c)
     int n_phys = 0;   // physical bucket windows Wp
     int n_tables = 0; // F = ceil(W / Wp); table j holds 2^(c*Wp*j) * P
+    int latency = 0;  // chosen for one MSM at a time (shortest dependent chains) rather than for throughput
 };
 
 extern std::atomic<uint64_t> g_object_ids;  // proving keys and base sets: never reused, what captured graphs are keyed by
@@ -222,6 +223,7 @@ struct Context {
     HostPinned h_small;  // pinned landing zone of the prover's small read-backs (degree flag, evaluations)
     // per-proof scalars of the prover (plonk.cu ProofParams): pinned staging copy and the device copy the kernels read
     HostPinned h_params;
+    HostPinned h_inv;  // mailbox of the batch inversion: block totals out, their inverses back (plonk.cu InvMailbox)
     DevBuf d_params;
     int use_graphs = -1;  // 1 / 0: replay prover rounds as CUDA graphs or not; -1: B200_GRAPHS from the environment (default on)
     std::vector<ProofGraphSet*> graph_sets;

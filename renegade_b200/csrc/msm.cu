@@ -705,6 +705,7 @@ MsmPlan msm_choose_plan(size_t n, int c_override, size_t mem_budget_bytes) {
             best_cost = cost;
             best.c = c;
             best.n_digits = W;
+            best.latency = latency_mode ? 1 : 0;
         }
     }
     // full precompute (one physical window) unless the tables exceed the memory budget;
@@ -816,13 +817,20 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
 // Bits of the column index (l) and of the row index (r), and how each tree splits them: `a` bits by the serial
 // level (fan-in <= 8 per thread: the throughput part, two additions per bucket), the rest (<= 8 bits) by the
 // shared-memory binary tree of msm_blocktree_kernel.
-static void tree_shape(int c, int* l_log, int* r_log, int* a_row, int* a_col) {
+// A latency plan skips the serial level when the binary tree can take the whole row / column (<= 8 bits): 8 dependent
+// additions instead of 7 + 5.
+static void tree_shape(int c, int latency, int* l_log, int* r_log, int* a_row, int* a_col) {
     const int bits = c - 1;
     const int l = (bits + 1) / 2, r = bits - l;
     *l_log = l;
     *r_log = r;
-    *a_row = l < 3 ? l : 3;
-    *a_col = r < 3 ? r : 3;
+    if (latency) {
+        *a_row = l > 8 ? l - 8 : 0;
+        *a_col = r > 8 ? r - 8 : 0;
+    } else {
+        *a_row = l < 3 ? l : 3;
+        *a_col = r < 3 ? r : 3;
+    }
 }
 
 // `batch` MSMs over the same bases (scalar vectors `stride` elements apart) in one pass: the
@@ -886,7 +894,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     if ((rc = s->seg_order.reserve(max_segs * 4)) != B200_OK) return rc;
     int l_log, r_log, a_row, a_col;
-    tree_shape(pl.c, &l_log, &r_log, &a_row, &a_col);
+    tree_shape(pl.c, pl.latency, &l_log, &r_log, &a_row, &a_col);
     if (l_log - a_row > 8 || r_log - a_col > 8) {
         set_error("msm: window too wide for the two-level bucket reduction");
         return B200_ERR_INVALID;
