@@ -767,12 +767,7 @@ FF_HD bool limbs_is_one(const uint32_t* x) {
 // dependency chain than the 380-product Fermat ladder, which matters in the latency-bound kernels).
 // Input a*R, output a^-1 * R; inv(0) = 0.  Invariants: b*a == u, c*a == v (mod p).
 template <class C>
-FF_HD fe fe_inv(const fe& a) {
-#if defined(__CUDA_ARCH__)
-    // On the device the data-dependent branches of the binary algorithm diverge inside a warp
-    // (ncu: k_ratio 257 us vs 206 us with the branch-free ladder), so kernels keep Fermat.
-    return fe_inv_fermat<C>(a);
-#else
+FF_HD fe fe_inv_euclid(const fe& a) {
     if (fe_is_zero(a)) return fe_zero();
     uint32_t u[8], v[8];
     fe b = fe_zero(), c = fe_zero();
@@ -806,6 +801,17 @@ FF_HD fe fe_inv(const fe& a) {
     const fe x = limbs_is_one(u) ? b : c;  // x * (a R) = 1  =>  x = a^-1 R^-1
     const fe r3 = fe_mul<C>(fe_r2<C>(), fe_r2<C>());  // R^3 (Montgomery product of R^2 by R^2)
     return fe_mul<C>(x, r3);                     // a^-1 R^-1 * R^3 * R^-1 = a^-1 R
+}
+
+template <class C>
+FF_HD fe fe_inv(const fe& a) {
+#if defined(__CUDA_ARCH__)
+    // When every lane of a warp inverts its own element the data-dependent branches of the binary algorithm diverge
+    // (ncu: k_ratio 257 us vs 206 us with the branch-free ladder), so per-thread inversions keep Fermat; a kernel that
+    // needs ONE inversion calls fe_inv_euclid from a single lane.
+    return fe_inv_fermat<C>(a);
+#else
+    return fe_inv_euclid<C>(a);
 #endif
 }
 

@@ -817,20 +817,16 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
 // Bits of the column index (l) and of the row index (r), and how each tree splits them: `a` bits by the serial
 // level (fan-in <= 8 per thread: the throughput part, two additions per bucket), the rest (<= 8 bits) by the
 // shared-memory binary tree of msm_blocktree_kernel.
-// A latency plan skips the serial level when the binary tree can take the whole row / column (<= 8 bits): 8 dependent
-// additions instead of 7 + 5.
 static void tree_shape(int c, int latency, int* l_log, int* r_log, int* a_row, int* a_col) {
     const int bits = c - 1;
     const int l = (bits + 1) / 2, r = bits - l;
     *l_log = l;
     *r_log = r;
-    if (latency) {
-        *a_row = l > 8 ? l - 8 : 0;
-        *a_col = r > 8 ? r - 8 : 0;
-    } else {
-        *a_row = l < 3 ? l : 3;
-        *a_col = r < 3 ? r : 3;
-    }
+    // (a latency plan without the serial level — the whole row / column in the shared-memory tree — was measured and lost:
+    // msm_blocktree_kernel 729 us vs 534 us for tree + block tree per 2^13 proof, profiles/r2n_*)
+    (void)latency;
+    *a_row = l < 3 ? l : 3;
+    *a_col = r < 3 ? r : 3;
 }
 
 // `batch` MSMs over the same bases (scalar vectors `stride` elements apart) in one pass: the

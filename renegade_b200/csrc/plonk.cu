@@ -134,17 +134,65 @@ template <bool RATIO>
 __global__ void __launch_bounds__(kInvThreads) k_inverse_down(const fe* __restrict__ num, fe* __restrict__ data,
                                                               const fe* __restrict__ scratch, const fe* __restrict__ chunk_ctx,
                                                               size_t n, const InvMailbox* box) {
+    __shared__ fe s_binv;
     const unsigned t = threadIdx.x;
+    if (t < 8) {  // one 32-byte read of host memory per block; written by the host a moment ago: no cached copy
+        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(&box->inverses[blockIdx.x]);
+        s_binv.l[t] = src[t];
+    }
+    __syncthreads();
     const size_t beg = ((size_t)blockIdx.x * kInvThreads + t) * kInvChunk;
     if (beg >= n) return;
     const size_t end = beg + kInvChunk < n ? beg + kInvChunk : n;
-    fe binv;
-    {
-        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(&box->inverses[blockIdx.x]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) binv.l[k] = src[k];  // written by the host a moment ago: no cached copy
+    fe inv = FMUL(s_binv, fe_load(chunk_ctx + (size_t)blockIdx.x * kInvThreads + t));
+    for (size_t i = end; i-- > beg;) {
+        const fe d = fe_load(data + i);
+        const bool zero = fe_is_zero(d);
+        fe r = FMUL(inv, fe_load(scratch + i));
+        if (RATIO) r = FMUL(fe_load_ro(num + i), r);
+        fe_store(data + i, zero ? fe_zero() : r);
+        if (!zero) inv = FMUL(inv, d);
     }
-    fe inv = FMUL(binv, fe_load(chunk_ctx + (size_t)blockIdx.x * kInvThreads + t));
+}
+
+// The same on two levels inside ONE kernel: thread 0 of each block inverts the block total with the binary Euclid (a single
+// lane: nothing to diverge from).  B200_INVERSE=device selects it (A/B against the host mailbox).
+template <bool RATIO>
+__global__ void __launch_bounds__(kInvThreads) k_block_inverse(const fe* __restrict__ num, fe* __restrict__ data,
+                                                               fe* __restrict__ scratch, size_t n) {
+    __shared__ fe pre[kInvThreads], suf[kInvThreads];
+    __shared__ fe binv;
+    const unsigned t = threadIdx.x;
+    const size_t beg = ((size_t)blockIdx.x * kInvThreads + t) * kInvChunk;
+    const size_t end = beg + kInvChunk < n ? beg + kInvChunk : n;
+    const fe one = fe_one<Fr>();
+    fe run = one;
+    for (size_t i = beg; i < end; ++i) {
+        fe_store(scratch + i, run);
+        const fe d = fe_load(data + i);
+        if (!fe_is_zero(d)) run = FMUL(run, d);
+    }
+    fe p = run, s = run;
+    pre[t] = p;
+    suf[t] = s;
+    __syncthreads();
+#pragma unroll 1
+    for (unsigned off = 1; off < kInvThreads; off <<= 1) {
+        fe pp = one, ss = one;
+        if (t >= off) pp = pre[t - off];
+        if (t + off < kInvThreads) ss = suf[t + off];
+        __syncthreads();
+        if (t >= off) p = FMUL(p, pp);
+        if (t + off < kInvThreads) s = FMUL(s, ss);
+        pre[t] = p;
+        suf[t] = s;
+        __syncthreads();
+    }
+    if (t == 0) binv = fe_inv_euclid<Fr>(pre[kInvThreads - 1]);
+    __syncthreads();
+    fe inv = binv;
+    if (t > 0) inv = FMUL(inv, pre[t - 1]);
+    if (t + 1 < kInvThreads) inv = FMUL(inv, suf[t + 1]);
     for (size_t i = end; i-- > beg;) {
         const fe d = fe_load(data + i);
         const bool zero = fe_is_zero(d);
@@ -490,6 +538,15 @@ static size_t inverse_chunk_elems(size_t n) { return (size_t)grid_for(n < (size_
 
 // data[i] <- 1 / data[i] (num == nullptr) or num[i] / data[i]; enqueue only.
 static int batch_inverse_enqueue(Context* c, const fe* num, fe* data, fe* scratch, fe* chunk_scratch, size_t n, cudaStream_t st) {
+    static const bool on_device = [] {
+        const char* e = std::getenv("B200_INVERSE");
+        return e && e[0] == 'd';
+    }();
+    if (on_device) {
+        if (num) B200_LAUNCH(k_block_inverse<true>, grid_for(n, kInvBlock), kInvThreads, 0, st)(num, data, scratch, n);
+        else B200_LAUNCH(k_block_inverse<false>, grid_for(n, kInvBlock), kInvThreads, 0, st)(nullptr, data, scratch, n);
+        return B200_OK;
+    }
     int rc;
     if ((rc = c->h_inv.reserve(sizeof(InvMailbox))) != B200_OK) return rc;
     InvMailbox* box = reinterpret_cast<InvMailbox*>(c->h_inv.p);
