@@ -223,7 +223,6 @@ struct Context {
     HostPinned h_small;  // pinned landing zone of the prover's small read-backs (degree flag, evaluations)
     // per-proof scalars of the prover (plonk.cu ProofParams): pinned staging copy and the device copy the kernels read
     HostPinned h_params;
-    HostPinned h_inv;  // mailbox of the batch inversion: block totals out, their inverses back (plonk.cu InvMailbox)
     DevBuf d_params;
     int use_graphs = -1;  // 1 / 0: replay prover rounds as CUDA graphs or not; -1: B200_GRAPHS from the environment (default on)
     std::vector<ProofGraphSet*> graph_sets;

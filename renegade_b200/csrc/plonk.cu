@@ -58,105 +58,16 @@ __global__ void k_l1_denominators(const fe* __restrict__ pts, size_t m, fe n_mon
     fe_store(out + i, FMUL(FSUB(fe_load_ro(pts + i), fe_one<Fr>()), n_mont));
 }
 
-// Batch inversion, Montgomery's trick on THREE levels with the one true inversion on the host.  Every thread multiplies up
-// its chunk of 16, the 256 chunk totals of a block are scanned in shared memory (prefix and suffix products at once), the
-// block totals go to pinned host memory; a host function queued on the stream (a host node when the stream is being
-// captured) inverts them — one binary-Euclid inversion and 3 products per block, microseconds on a CPU core — and the
-// second kernel fans the inverses back out.  A field inversion is a chain of ~380 dependent products (Fermat) or ~500
-// dependent shift / subtract steps (Euclid) whatever the batch: ~180 us on a GPU lane, ~3 us on the host.
+// Batch inversion with ONE field inversion per block of 4096 elements (Montgomery's trick on two levels): every thread
+// multiplies up its chunk of 16, the 256 chunk totals are scanned in shared memory (prefix and suffix products at once),
+// thread 0 inverts the block total with the binary extended Euclid — a single lane, so its data-dependent branches have
+// nobody to diverge from: ~20 us, against ~180 us for the 380 dependent products of a Fermat ladder (what a per-thread
+// inversion costs whatever the batch size) — and the chunk inverses fan back out.  ~5 products per element.
+// Measured against the alternatives on B200 (profiles/r2o_inverse_ab.log, round 2 of a 2^13 proof): Fermat per 16
+// elements 0.68 ms, one-lane Fermat per block 0.65, block totals inverted on the host through a pinned mailbox and a host
+// node 0.57, this 0.55.
 // data[i] <- 1 / data[i], or num[i] / data[i] (RATIO); zeros stay zero and do not disturb their neighbours.
-constexpr int kInvThreads = 256, kInvChunk = 16, kInvBlock = kInvThreads * kInvChunk, kInvMaxBlocks = 4096;
-struct InvMailbox {  // pinned host memory, device-visible at the same address (UVA)
-    uint64_t count, pad[3];
-    fe totals[kInvMaxBlocks];
-    fe inverses[kInvMaxBlocks];
-};
-
-__global__ void __launch_bounds__(kInvThreads) k_inverse_up(const fe* __restrict__ data, fe* __restrict__ scratch,
-                                                            fe* __restrict__ chunk_ctx, size_t n, InvMailbox* box) {
-    __shared__ fe pre[kInvThreads], suf[kInvThreads];
-    const unsigned t = threadIdx.x;
-    const size_t beg = ((size_t)blockIdx.x * kInvThreads + t) * kInvChunk;
-    const size_t end = beg + kInvChunk < n ? beg + kInvChunk : n;  // beg >= n: an empty chunk (total 1)
-    const fe one = fe_one<Fr>();
-    fe run = one;
-    for (size_t i = beg; i < end; ++i) {
-        fe_store(scratch + i, run);
-        const fe d = fe_load(data + i);
-        if (!fe_is_zero(d)) run = FMUL(run, d);
-    }
-    fe p = run, s = run;  // become the inclusive prefix / suffix products of the chunk totals
-    pre[t] = p;
-    suf[t] = s;
-    __syncthreads();
-#pragma unroll 1
-    for (unsigned off = 1; off < kInvThreads; off <<= 1) {
-        fe pp = one, ss = one;
-        if (t >= off) pp = pre[t - off];
-        if (t + off < kInvThreads) ss = suf[t + off];
-        __syncthreads();
-        if (t >= off) p = FMUL(p, pp);
-        if (t + off < kInvThreads) s = FMUL(s, ss);
-        pre[t] = p;
-        suf[t] = s;
-        __syncthreads();
-    }
-    // 1 / (chunk total) = 1 / (block total) * (product of the chunks before) * (product of the chunks after)
-    fe ctxv = one;
-    if (t > 0) ctxv = pre[t - 1];
-    if (t + 1 < kInvThreads) ctxv = FMUL(ctxv, suf[t + 1]);
-    fe_store(chunk_ctx + (size_t)blockIdx.x * kInvThreads + t, ctxv);
-    if (t == 0) {
-        box->totals[blockIdx.x] = pre[kInvThreads - 1];
-        if (blockIdx.x == 0) box->count = gridDim.x;
-        __threadfence_system();
-    }
-}
-
-// host side of the mailbox: inverses[j] = 1 / totals[j] (no CUDA calls in here: it runs on the driver's callback thread)
-static void CUDART_CB host_invert_totals(void* user) {
-    InvMailbox* box = static_cast<InvMailbox*>(user);
-    const size_t cnt = box->count <= (uint64_t)kInvMaxBlocks ? (size_t)box->count : 0;
-    fe run = fe_one<Fr>();
-    for (size_t j = 0; j < cnt; ++j) {  // totals are products of non-zero elements: never zero
-        box->inverses[j] = run;
-        run = FMUL(run, box->totals[j]);
-    }
-    fe r = fe_inv<Fr>(run);
-    for (size_t j = cnt; j-- > 0;) {
-        const fe t = FMUL(r, box->inverses[j]);
-        r = FMUL(r, box->totals[j]);
-        box->inverses[j] = t;
-    }
-}
-
-template <bool RATIO>
-__global__ void __launch_bounds__(kInvThreads) k_inverse_down(const fe* __restrict__ num, fe* __restrict__ data,
-                                                              const fe* __restrict__ scratch, const fe* __restrict__ chunk_ctx,
-                                                              size_t n, const InvMailbox* box) {
-    __shared__ fe s_binv;
-    const unsigned t = threadIdx.x;
-    if (t < 8) {  // one 32-byte read of host memory per block; written by the host a moment ago: no cached copy
-        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(&box->inverses[blockIdx.x]);
-        s_binv.l[t] = src[t];
-    }
-    __syncthreads();
-    const size_t beg = ((size_t)blockIdx.x * kInvThreads + t) * kInvChunk;
-    if (beg >= n) return;
-    const size_t end = beg + kInvChunk < n ? beg + kInvChunk : n;
-    fe inv = FMUL(s_binv, fe_load(chunk_ctx + (size_t)blockIdx.x * kInvThreads + t));
-    for (size_t i = end; i-- > beg;) {
-        const fe d = fe_load(data + i);
-        const bool zero = fe_is_zero(d);
-        fe r = FMUL(inv, fe_load(scratch + i));
-        if (RATIO) r = FMUL(fe_load_ro(num + i), r);
-        fe_store(data + i, zero ? fe_zero() : r);
-        if (!zero) inv = FMUL(inv, d);
-    }
-}
-
-// The same on two levels inside ONE kernel: thread 0 of each block inverts the block total with the binary Euclid (a single
-// lane: nothing to diverge from).  B200_INVERSE=device selects it (A/B against the host mailbox).
+constexpr int kInvThreads = 256, kInvChunk = 16, kInvBlock = kInvThreads * kInvChunk;
 template <bool RATIO>
 __global__ void __launch_bounds__(kInvThreads) k_block_inverse(const fe* __restrict__ num, fe* __restrict__ data,
                                                                fe* __restrict__ scratch, size_t n) {
@@ -533,33 +444,10 @@ inline unsigned grid_for(size_t n, unsigned bs) { return (unsigned)((n + bs - 1)
 
 }  // namespace
 
-// elements of chunk scratch batch_inverse_enqueue needs beside the n-element `scratch`
-static size_t inverse_chunk_elems(size_t n) { return (size_t)grid_for(n < (size_t)kInvBlock * kInvMaxBlocks ? n : (size_t)kInvBlock * kInvMaxBlocks, kInvBlock) * kInvThreads; }
-
-// data[i] <- 1 / data[i] (num == nullptr) or num[i] / data[i]; enqueue only.
-static int batch_inverse_enqueue(Context* c, const fe* num, fe* data, fe* scratch, fe* chunk_scratch, size_t n, cudaStream_t st) {
-    static const bool on_device = [] {
-        const char* e = std::getenv("B200_INVERSE");
-        return e && e[0] == 'd';
-    }();
-    if (on_device) {
-        if (num) B200_LAUNCH(k_block_inverse<true>, grid_for(n, kInvBlock), kInvThreads, 0, st)(num, data, scratch, n);
-        else B200_LAUNCH(k_block_inverse<false>, grid_for(n, kInvBlock), kInvThreads, 0, st)(nullptr, data, scratch, n);
-        return B200_OK;
-    }
-    int rc;
-    if ((rc = c->h_inv.reserve(sizeof(InvMailbox))) != B200_OK) return rc;
-    InvMailbox* box = reinterpret_cast<InvMailbox*>(c->h_inv.p);
-    const size_t span = (size_t)kInvBlock * kInvMaxBlocks;  // elements one mailbox round serves (16.7 M)
-    for (size_t off = 0; off < n; off += span) {
-        const size_t cnt = n - off < span ? n - off : span;
-        const unsigned blocks = grid_for(cnt, kInvBlock);
-        B200_LAUNCH(k_inverse_up, blocks, kInvThreads, 0, st)(data + off, scratch + off, chunk_scratch, cnt, box);
-        B200_CUDA(cudaLaunchHostFunc(st, host_invert_totals, box));
-        if (num) B200_LAUNCH(k_inverse_down<true>, blocks, kInvThreads, 0, st)(num + off, data + off, scratch + off, chunk_scratch, cnt, box);
-        else B200_LAUNCH(k_inverse_down<false>, blocks, kInvThreads, 0, st)(nullptr, data + off, scratch + off, chunk_scratch, cnt, box);
-    }
-    return B200_OK;
+// data[i] <- 1 / data[i] (num == nullptr) or num[i] / data[i]; enqueue only.  scratch: n elements.
+static void batch_inverse_enqueue(const fe* num, fe* data, fe* scratch, size_t n, cudaStream_t st) {
+    if (num) B200_LAUNCH(k_block_inverse<true>, grid_for(n, kInvBlock), kInvThreads, 0, st)(num, data, scratch, n);
+    else B200_LAUNCH(k_block_inverse<false>, grid_for(n, kInvBlock), kInvThreads, 0, st)(nullptr, data, scratch, n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -742,7 +630,7 @@ struct Workspace {
 };
 static size_t workspace_elems(size_t n) {
     const size_t S = n + 4, m = 8 * n;
-    return NW * n + NW * S + S + S + 3 * n + (2 * (n / CH) + 4 * CH + 64 + kInvThreads) + 7 * m + m + NW * S + S + 2 * (S + 8) +
+    return NW * n + NW * S + S + S + 3 * n + (2 * (n / CH) + 4 * CH + 64) + 7 * m + m + NW * S + S + 2 * (S + 8) +
            4 * (S / CH + 4 * CH + 64) + kMaxEval * (S / CH + S / CH / CH + 2 * CH + 16) + 32 + 8;
 }
 static Workspace carve(fe* base, size_t n) {
@@ -757,8 +645,7 @@ static Workspace carve(fe* base, size_t n) {
     w.num = p; p += n;
     w.den = p; p += n;
     w.tmp = p; p += n;
-    w.scan = p; p += 2 * (n / CH) + 4 * CH + 64 + kInvThreads;  // all levels of the product scan: n / CH * (1 + 1/CH + ...);
-                                                                // before that, the chunk context of the batch inversion
+    w.scan = p; p += 2 * (n / CH) + 4 * CH + 64;  // all levels of the product scan: n / CH * (1 + 1/CH + ...)
     w.ext = p; p += 7 * m;
     w.quot = p; p += m;
     w.split = p; p += NW * S;
@@ -880,7 +767,7 @@ static int preprocess(Context* c, const Bases* srs, unsigned log_n, size_t num_i
         }
     }
     B200_LAUNCH(k_l1_denominators, grid_for(m, 256), 256, 0, st)(pk->coset_pts, m, host_from_u64(n), pk->l1_inv);
-    if ((rc = batch_inverse_enqueue(c, nullptr, pk->l1_inv, pk->ce_sel /*scratch, overwritten below*/, pk->ce_sel + m, m, st)) != B200_OK) return fail(rc);
+    batch_inverse_enqueue(nullptr, pk->l1_inv, pk->ce_sel /*scratch, overwritten below*/, m, st);
 
     // selectors: evaluations -> coefficients -> commitments
     cudaMemcpyAsync(pk->sel_coeffs, h_selectors, NS * n * sizeof(fe), cudaMemcpyHostToDevice, st);
@@ -923,7 +810,7 @@ static_assert(sizeof(ProofOut) == sizeof(b200_proof), "proof layout");
 // the addresses a captured segment refers to besides the key's: every grow-only buffer of the context
 static uint64_t buffer_fingerprint(const Context* c) {
     const MsmScratch& m = c->msm;
-    const void* ps[] = {c->plonk_ws.p, c->ntt_scratch.p, c->ntt_scratch2.p, c->h_small.p, c->h_params.p, c->d_params.p, c->h_inv.p,
+    const void* ps[] = {c->plonk_ws.p, c->ntt_scratch.p, c->ntt_scratch2.p, c->h_small.p, c->h_params.p, c->d_params.p,
                         m.counts.p, m.offsets.p, m.cursor.p, m.entries.p, m.buckets.p, m.window_sums.p, m.scalars.p,
                         m.seg_offsets.p, m.seg_bucket.p, m.seg_sums.p, m.heavy.p, m.seg_order.p, m.scan_state.p, m.tree.p,
                         m.bit_sums.p, m.h_sums.p};
@@ -1177,7 +1064,7 @@ static int prove(Context* c, const ProvingKey* pk, const fe* h_wires, const fe* 
         int r = push_params();
         if (r != B200_OK) return r;
         B200_LAUNCH(k_perm_num_den, grid_for(n, 128), 128, 0, st)(w.wires_ev, pk->sig_evals, pk->dom, pk->k, &dp->chal[0], n, w.num, w.den);
-        if ((r = batch_inverse_enqueue(c, w.num, w.den, w.tmp, w.scan, n, st)) != B200_OK) return r;  // w.scan: free until the scan below
+        batch_inverse_enqueue(w.num, w.den, w.tmp, n, st);
         scan_mul_exclusive(w.den, n, w.scan, st);  // z(w^j) = prod_{i<j} ratio_i
         B200_CUDA(cudaMemsetAsync(w.zpoly, 0, S * sizeof(fe), st));
         B200_CUDA(cudaMemcpyAsync(w.zpoly, w.den, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
@@ -1400,8 +1287,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
     }
     const size_t N = (size_t)1 << log_N;
     const size_t L = len + 8, NL = N + 8;
-    size_t scr = 4 * (L / CH + 4 * CH + 64);
-    if (scr < inverse_chunk_elems(N)) scr = inverse_chunk_elems(N);
+    const size_t scr = 4 * (L / CH + 4 * CH + 64);
     if ((rc = c->plonk_ws.reserve((5 * L + 3 * NL + scr + size + 16) * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->ntt_scratch.reserve(N * sizeof(fe))) != B200_OK) return rc;
     if ((rc = c->h_small.reserve(4096)) != B200_OK) return rc;
@@ -1460,7 +1346,7 @@ static int link(Context* c, const Bases* srs, const fe* h_a1, size_t len1, const
         B200_CUDA(cudaMemcpyAsync(d_E, d_diff, len * sizeof(fe), cudaMemcpyDeviceToDevice, st));
         if ((r = ntt_device(dN, d_E, nscr, /*inverse=*/0, /*coset=*/1, 1, N, st)) != B200_OK) return r;
         B200_LAUNCH(k_vanishing_on_coset, grid_for(N, 128), 128, 0, st)(dN->tw_fwd, N, fe_from_u32<Fr>(5), d_roots, size, d_Z);
-        if ((r = batch_inverse_enqueue(c, nullptr, d_Z, d_ZS, hscr, N, st)) != B200_OK) return r;  // hscr: free until the opening
+        batch_inverse_enqueue(nullptr, d_Z, d_ZS, N, st);
         B200_LAUNCH(k_fr_vec_op, grid_for(N, 256), 256, 0, st)(2, d_E, d_Z, 0, N, d_Q);
         if ((r = ntt_device(dN, d_Q, nscr, /*inverse=*/1, /*coset=*/1, 1, N, st)) != B200_OK) return r;
         // a1 and a2 must agree on every root of the group, i.e. the division is exact: otherwise no link proof verifies
@@ -1609,10 +1495,9 @@ int b200_fr_batch_inverse_device(b200_ctx* ctx, void* d_data, size_t n) {
     if (n == 0) return B200_OK;
     std::lock_guard<std::mutex> lk(ctx->c.mu);
     B200_CUDA(cudaSetDevice(ctx->c.device));
-    int rc = ctx->c.ntt_scratch.reserve((n + inverse_chunk_elems(n)) * sizeof(fe));
+    int rc = ctx->c.ntt_scratch.reserve(n * sizeof(fe));
     if (rc != B200_OK) return rc;
-    fe* scr = reinterpret_cast<fe*>(ctx->c.ntt_scratch.p);
-    if ((rc = batch_inverse_enqueue(&ctx->c, nullptr, reinterpret_cast<fe*>(d_data), scr, scr + n, n, ctx->c.stream)) != B200_OK) return rc;
+    batch_inverse_enqueue(nullptr, reinterpret_cast<fe*>(d_data), reinterpret_cast<fe*>(ctx->c.ntt_scratch.p), n, ctx->c.stream);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaStreamSynchronize(ctx->c.stream));
     return B200_OK;
