@@ -154,7 +154,7 @@ def real_statement_leg(pool, ctx, d_srs_ptr, conc, steps, srs_host=None, cpu_bas
                 tickets = [pool.submit_prove(pk, h_w.data_ptr(), circ.pub_inputs, bl[i % 8]) for i in range(count)]
                 for tk in tickets:
                     pool.wait(tk)
-            run(4 * conc)
+            run(8 * conc)  # steady state: every worker has its buffers sized and its rounds captured as graphs
             l0, h0 = ctx._lib.b200_kernel_launches(), ctx._lib.b200_launch_host_ns()
             t = time.perf_counter()
             run(steps)
@@ -227,7 +227,7 @@ def private_match_bundle_leg(pool, ctx, d_srs_ptr, conc, bundles, srs_host=None,
         tickets = [pool.submit_bundle(bases, [(pks[j], wires[j].data_ptr(), circs[j].pub_inputs, bl[(5 * b + j) % 8]) for j in range(5)],
                                       [(j, 0, lay) for j, lay in link_plan]) for b in range(count)]
         return [pool.wait(tk) for tk in tickets]
-    run(max(2, 3 * conc))  # steady state: every worker has proved every key (buffers sized, rounds captured as graphs)
+    run(max(2, 6 * conc))  # steady state: every worker has proved every key twice (buffers sized, rounds captured as graphs)
     t = time.perf_counter()
     res = run(bundles)
     dt = time.perf_counter() - t
@@ -325,7 +325,7 @@ def run_extras(args):
     ctx.known_dlog_bases_device(SEED_SRS, n_srs, d_srs.data_ptr())
     extras = {}
     srs_host = d_srs.cpu().numpy().view(np.uint64)
-    for key, leg, count in (("real_statements", real_statement_leg, 300), ("private_match_bundle", private_match_bundle_leg, 80),
+    for key, leg, count in (("real_statements", real_statement_leg, 600), ("private_match_bundle", private_match_bundle_leg, 160),
                             ("valid_match_mpc_collaborative", collaborative_leg, 5)):
         if key in os.environ.get("B200_BENCH_SKIP_LEGS", "").split(","):  # tools/small_proof_sweep.sh
             continue
