@@ -225,71 +225,11 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(PassArgs a) {
     tile_compute<FINAL>(a, g, plane_lo, plane_hi, q_base, out);
 }
 
-// Persistent variant (overlap the loads with the butterflies): a block walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened (transform, tile) space; the NEXT tile is fetched with
-// `cp.async` (LDGSTS, 16 bytes per copy: the gather of an upper pass is 1024 separate 32-byte sectors 32 KB apart, so
-// neither a 1-D bulk copy nor a TMA box applies) into the other half of a double buffer while the current tile runs its
-// butterflies.  Selected with B200_NTT_PERSISTENT=1; measured against the one-tile-per-block kernel in
-// profiles/r2f_ntt_persistent_ab.log.
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
-}
-template <bool FINAL>
-__global__ void __launch_bounds__(256) ntt_pass_persistent_kernel(PassArgs a, uint32_t tiles_per_transform, uint32_t total_tiles) {
-    extern __shared__ uint4 smem[];
-    const TileGeom g = tile_geom(a);
-    const int E = g.E;
-    auto issue = [&](uint32_t tile, int buf) {
-        const uint32_t batch = tile / tiles_per_transform, q_base = (tile % tiles_per_transform) << g.q_log;
-        const fe* in = a.in + (size_t)batch * a.batch_stride;
-        uint4* lo = smem + (size_t)buf * 2 * E;
-        uint4* hi = lo + E;
-        for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
-            size_t idx;
-            uint32_t pos;
-            tile_slot(a, g, q_base, e, &idx, &pos);
-            const uint4* src = reinterpret_cast<const uint4*>(in + idx);
-            cp_async_16(lo + pos, src);
-            cp_async_16(hi + pos, src + 1);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    uint32_t tile = blockIdx.x;
-    int cur = 0;
-    if (tile < total_tiles) issue(tile, cur);
-    for (; tile < total_tiles; tile += gridDim.x) {
-        const uint32_t next = tile + gridDim.x;
-        if (next < total_tiles) {
-            issue(next, cur ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const uint32_t batch = tile / tiles_per_transform, q_base = (tile % tiles_per_transform) << g.q_log;
-        uint4* lo = smem + (size_t)cur * 2 * E;
-        uint4* hi = lo + E;
-        if (a.pre) {  // coset factor g^i of the first pass, applied in shared memory
-            for (uint32_t e = threadIdx.x; e < (uint32_t)E; e += blockDim.x) {
-                size_t idx;
-                uint32_t pos;
-                tile_slot(a, g, q_base, e, &idx, &pos);
-                const uint4 u = lo[pos], v = hi[pos];
-                fe x;
-                x.l[0] = u.x; x.l[1] = u.y; x.l[2] = u.z; x.l[3] = u.w;
-                x.l[4] = v.x; x.l[5] = v.y; x.l[6] = v.z; x.l[7] = v.w;
-                x = fe_mul<FrCfg>(x, fe_load_ro(a.pre + idx));
-                lo[pos] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
-                hi[pos] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
-            }
-            __syncthreads();
-        }
-        tile_compute<FINAL>(a, g, lo, hi, q_base, a.out + (size_t)batch * a.batch_stride);
-        __syncthreads();  // the buffer is refilled two iterations from now; all reads of it are done here
-        cur ^= 1;
-    }
-}
+// A persistent variant of this pass (296 blocks walking the tiles, the next tile prefetched with cp.async into the other
+// half of a double buffer) was built, passed the parity suite and lost on B200: 2^20 forward 264 us vs 206 us — 98-102
+// registers and twice the shared memory leave 2 resident blocks per SM instead of 3, and the pass is bound by the
+// integer-multiply pipe, not by load latency (profiles/r2f_ntt_persistent_ab.log, profiles/r2z_ncu_summary.md; the code is in
+// the history at commit bd42500).
 
 // table[i] = base^i (Montgomery), i < n: thread i multiplies the pow2[b] = base^(2^b) it needs
 struct PowArgs {
@@ -346,9 +286,7 @@ int domain_create(unsigned log_n, cudaStream_t st, Domain** out) {
     // every domain is created on its context's device, under that context's lock: the opt-in for the tile's
     // shared memory is (re)applied here, per device, instead of behind a process-wide flag
     if (cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess ||
-        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess ||
-        cudaFuncSetAttribute(ntt_pass_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << kTileLog) != cudaSuccess ||
-        cudaFuncSetAttribute(ntt_pass_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << kTileLog) != cudaSuccess)
+        cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kTileLog) != cudaSuccess)
         return B200_ERR_CUDA;
     Domain* d = new Domain();
     d->log_n = log_n;
@@ -421,15 +359,7 @@ int ntt_device(const Domain* d, fe* data, fe* scratch, int inverse, int coset, u
         if (threads < 32) threads = 32;
         dim3 grid((unsigned)(((size_t)1 << L) >> e_log), batch);
         const size_t smem = (size_t)E * 32;
-        static const bool persistent = [] {
-            const char* e = std::getenv("B200_NTT_PERSISTENT");
-            return e && e[0] == '1';
-        }();
-        const uint32_t tiles_per = grid.x, total = tiles_per * batch;
-        if (persistent && E == 1024 && total > 296) {  // more tiles than resident blocks (148 SMs x 2 at ~100 registers): walk them
-            if (final_pass) B200_LAUNCH(ntt_pass_persistent_kernel<true>, 296, threads, 2 * smem, st)(a, tiles_per, total);
-            else B200_LAUNCH(ntt_pass_persistent_kernel<false>, 296, threads, 2 * smem, st)(a, tiles_per, total);
-        } else if (final_pass) {
+        if (final_pass) {
             B200_LAUNCH(ntt_pass_kernel<true>, grid, threads, smem, st)(a);
         } else {
             B200_LAUNCH(ntt_pass_kernel<false>, grid, threads, smem, st)(a);

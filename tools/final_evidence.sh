@@ -33,8 +33,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:msm_
     python tools/prove_bench.py 16 2 > gpurun_out/${T}_ncu_full_e.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 4 -c 2 -f -o gpurun_out/${T}_prof_ntt_2_20 \
     python tools/ntt_bench.py 20 1 > gpurun_out/${T}_ncu_full_b.log 2>&1
-B200_NTT_PERSISTENT=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_pass_persistent -s 4 -c 2 -f -o gpurun_out/${T}_prof_ntt_persistent_2_20 \
-    python tools/ntt_bench.py 20 1 > gpurun_out/${T}_ncu_full_c.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:msm_tree_kernel -s 8 -c 1 -f -o gpurun_out/${T}_prof_msm_tree \
     python tools/prove_bench.py 16 2 > gpurun_out/${T}_ncu_full_d.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:msm_blocktree_kernel -s 8 -c 1 -f -o gpurun_out/${T}_prof_msm_blocktree \
