@@ -29,6 +29,11 @@ import sys
 import threading
 import time
 
+# A prover pool keeps 3 streams per worker busy; with the default 8 hardware queues unrelated streams share a queue and
+# wait for each other.  Must be in the environment before the process's first CUDA call (profiles/r2r_max_connections.log:
+# +3 % on the 2^12 statement and the bundle, nothing at 2^16).  A host application sets it the same way.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "examples"))  # host_circuits: caller-side restatement of the reference's circuits
