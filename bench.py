@@ -747,6 +747,8 @@ def main():
         "value": world * args.steps / dt, "ms_per_step": ms_step,
         "config": shared_config(args),
         "run": {"gates_used": circ.n_gates, "concurrency_per_gpu": conc,
+                "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
+                "prover_rounds": "replayed as CUDA graphs from the second proof of a key on a worker (B200_GRAPHS=%s)" % os.environ.get("B200_GRAPHS", "1"),
                 "parallelism": "one proof stream per GPU (replicas, no collective)", "msm_plan": srs.plan,
                 "l2": "working set > L2: shared key tables 227 MB + SRS window tables 67 MB, plus per proof in flight "
                       "7 x 12.6 MB extended polynomials and ~100 MB of MSM scratch, vs 126 MB of L2",
