@@ -363,6 +363,77 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
 // "no instruction" stalls per issue).  Out-of-line copies keep those kernels small.
 __device__ __noinline__ g1_xyzz xyzz_add(const g1_xyzz& a, const g1_xyzz& b) { return g1_add(a, b); }
 
+// ---- one XYZZ addition by the four lanes of a quad ------------------------------------------------------------
+// The tails of the bucket reduction are chains of DEPENDENT additions with almost nobody else on the SM: one lane
+// walks through the 14 field products of g1_add in ~5 us while the lanes beside it idle.  The 14 products are only
+// four deep, so a quad (lanes 4k .. 4k+3) takes one product per lane and stage and trades the results by shuffle:
+//   stage 1   u1 = X1*ZZ2      u2 = X2*ZZ1     s1 = Y1*ZZZ2      s2 = Y2*ZZZ1        P = u2 - u1, R = s2 - s1
+//   stage 2   pp = P^2         r2 = R^2        zz = ZZ1*ZZ2      zzz = ZZZ1*ZZZ2
+//   stage 3   ppp = P*pp       q = u1*pp       ZZ3 = zz*pp       w = zzz*pp          X3 = r2 - ppp - 2q
+//   stage 4   t1 = R*(q - X3)  t2 = s1*ppp     (nothing)         ZZZ3 = w*P          Y3 = t1 - t2
+// (same formulas as g1_add, EFD add-2008-s, with Y3 as two products instead of the fused pair — any correct group
+// addition gives the same affine point).  Operands live in shared memory as arrays of four field elements; the sum
+// replaces operand a.  Identity operands and P = 0 (doubling / cancellation) are decided identically by the four lanes
+// and take the exact paths of g1_add.  All 32 lanes of a warp call this together (the shuffles are warp-wide): quads
+// with nothing to add pass on = false and operands nobody writes during the call.
+__device__ __forceinline__ fe fe_quad_bcast(const fe& v, int src) {
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = __shfl_sync(0xffffffffu, v.l[k], src, 4);
+    return r;
+}
+__device__ __forceinline__ fe fe_pick3(uint32_t q, const fe& a0, const fe& a1, const fe& rest) {  // q = 0 ? a0 : q = 1 ? a1 : rest
+    fe r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = q == 0u ? a0.l[k] : (q == 1u ? a1.l[k] : rest.l[k]);
+    return r;
+}
+__device__ __forceinline__ void xyzz_add_quad(g1_xyzz* sh, uint32_t ia, uint32_t ib, bool on) {
+    fe* F = reinterpret_cast<fe*>(sh);  // point i = F[4 i .. 4 i + 3] = x, y, zz, zzz
+    const uint32_t q = threadIdx.x & 3u;
+    const uint32_t hi = q | 2u;  // lanes 2 and 3 multiply the zz / zzz pair in stage 2
+    const fe a_hi = fe_load(F + 4u * ia + hi), b_hi = fe_load(F + 4u * ib + hi);
+    const bool a_inf = fe_is_zero(fe_load(F + 4u * ia + 2u)), b_inf = fe_is_zero(fe_load(F + 4u * ib + 2u));
+    // nothing but copies in the whole warp (empty slots of a padded tree): skip the arithmetic
+    if (__all_sync(0xffffffffu, !on || a_inf || b_inf)) {
+        if (on && a_inf && !b_inf) fe_store(F + 4u * ia + q, fe_load(F + 4u * ib + q));
+        return;
+    }
+    // stage 1: lane 0 X1*ZZ2, lane 1 X2*ZZ1, lane 2 Y1*ZZZ2, lane 3 Y2*ZZZ1
+    const uint32_t i1 = (q & 1u) ? ib : ia, i2 = (q & 1u) ? ia : ib;
+    const fe m1 = fe_mul<Fq>(fe_load(F + 4u * i1 + (q >> 1)), fe_load(F + 4u * i2 + 2u + (q >> 1)));
+    const fe u1 = fe_quad_bcast(m1, 0), u2 = fe_quad_bcast(m1, 1), s1 = fe_quad_bcast(m1, 2), s2 = fe_quad_bcast(m1, 3);
+    const fe pd = fe_sub<Fq>(u2, u1), rd = fe_sub<Fq>(s2, s1);
+    const bool p0 = fe_is_zero(pd);
+    // stage 2
+    const fe m2 = fe_mul<Fq>(fe_pick3(q, pd, rd, a_hi), fe_pick3(q, pd, rd, b_hi));
+    const fe pp = fe_quad_bcast(m2, 0);
+    // stage 3
+    const fe m3 = fe_mul<Fq>(fe_pick3(q, pd, u1, m2), pp);
+    const fe ppp = fe_quad_bcast(m3, 0), qq = fe_quad_bcast(m3, 1), r2 = fe_quad_bcast(m2, 1);
+    const fe x3 = fe_sub<Fq>(fe_sub<Fq>(r2, ppp), fe_dbl<Fq>(qq));
+    // stage 4 (lane 2's product is not used)
+    const fe m4 = fe_mul<Fq>(fe_pick3(q, rd, s1, m3), fe_pick3(q, fe_sub<Fq>(qq, x3), ppp, pd));
+    const fe t2 = fe_quad_bcast(m4, 1);
+    // every lane of the warp has passed its last read of the operands (the shuffles above): the sum may replace a
+    if (!on || b_inf) return;
+    if (a_inf) {
+        fe_store(F + 4u * ia + q, fe_load(F + 4u * ib + q));
+    } else if (p0) {  // a = +-b: exact doubling / identity, by one lane
+        if (q == 0u) {
+            const g1_xyzz r = xyzz_add(sh[ia], sh[ib]);
+            sh[ia] = r;
+        }
+    } else if (q == 0u) {
+        fe_store(F + 4u * ia, x3);
+        fe_store(F + 4u * ia + 1u, fe_sub<Fq>(m4, t2));
+    } else if (q == 2u) {
+        fe_store(F + 4u * ia + 2u, m3);
+    } else if (q == 3u) {
+        fe_store(F + 4u * ia + 3u, m4);
+    }
+}
+
 // bucket = sum of its segment sums: sequential for ordinary buckets, deferred to a block tree
 // (msm_heavy_combine_kernel) for buckets cut into more than kCombineSeq segments.
 __global__ void __launch_bounds__(128) msm_bucket_combine_kernel(const g1_xyzz* __restrict__ seg_sums,
@@ -429,6 +500,7 @@ struct TreeArgs {
     TreeLevel row, col;
 };
 constexpr int kTreeThreads = 128;
+constexpr size_t kQuadTreeMaxOutputs = 16384;  // msm_tree_quad_kernel up to this many outputs (65536 lanes), see msm_launch_batch
 
 __global__ void __launch_bounds__(kTreeThreads) msm_tree_kernel(TreeArgs a) {
     const bool is_row = blockIdx.x < a.row.n_blocks;
@@ -451,6 +523,43 @@ __global__ void __launch_bounds__(kTreeThreads) msm_tree_kernel(TreeArgs a) {
     g1_xyzz_store(lv.out + t, acc);
 }
 
+// The same level with four lanes per output (xyzz_add_quad): the chain of T - 1 additions is ~3x shorter and a quad's
+// loads are one contiguous 128-byte point.  Per quad two shared-memory slots: the running sum and the next operand, whose
+// successor is fetched (one coordinate per lane) under the addition.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) msm_tree_quad_kernel(TreeArgs a) {
+    __shared__ g1_xyzz sh[kThreads / 2];
+    constexpr uint32_t kQuads = kThreads / 4;
+    const bool is_row = blockIdx.x < a.row.n_blocks;
+    const TreeLevel& lv = is_row ? a.row : a.col;
+    const uint32_t blk = is_row ? blockIdx.x : blockIdx.x - a.row.n_blocks;
+    const uint32_t ql = threadIdx.x >> 2, q = threadIdx.x & 3u;
+    const uint32_t t = blk * kQuads + ql;
+    const bool on = t < lv.n_out;
+    if (__all_sync(0xffffffffu, !on)) return;  // a warp without outputs
+    const uint32_t inner_mask = (1u << lv.inner_log) - 1u;
+    const uint32_t tt = on ? t : 0u;
+    const size_t first = (((size_t)(tt >> lv.inner_log) << lv.t_log) << lv.inner_log) | (tt & inner_mask);
+    const size_t stride = (size_t)1 << lv.inner_log;
+    const uint32_t T = 1u << lv.t_log;
+    const fe* p = reinterpret_cast<const fe*>(lv.in + first) + q;  // coordinate q of the quad's inputs
+    const size_t hop = stride * 4;                                 // in field elements
+    fe* F = reinterpret_cast<fe*>(sh);
+    const uint32_t sa = 2u * ql, sb = sa + 1u;
+    fe_store(F + 4u * sa + q, fe_load(p));
+    fe next = T > 1 ? fe_load(p + hop) : fe_zero();
+#pragma unroll 1
+    for (uint32_t j = 1; j < T; ++j) {
+        fe_store(F + 4u * sb + q, next);
+        __syncwarp();
+        if (j + 1 < T) next = fe_load(p + (size_t)(j + 1) * hop);
+        xyzz_add_quad(sh, sa, sb, on);
+        __syncwarp();
+    }
+    __syncwarp();
+    if (on) fe_store(reinterpret_cast<fe*>(lv.out + t) + q, fe_load(F + 4u * sa + q));
+}
+
 // Second (and last) level of both trees: what the serial level leaves — 2^g partial sums per row / column, g <= 8 —
 // is folded by a binary tree in shared memory, one addition per step on the critical path instead of 2^g - 1.
 //   rows:    out[O] = sum_j in[O * G + j]                                  (G = 2^g partials of a row are contiguous)
@@ -466,6 +575,7 @@ struct BlockTreeArgs {
 };
 constexpr int kBlockTreeThreads = 256;
 
+template <bool QUAD>
 __global__ void __launch_bounds__(kBlockTreeThreads) msm_blocktree_kernel(BlockTreeArgs a) {
     __shared__ g1_xyzz sh[kBlockTreeThreads];
     const bool is_row = blockIdx.x < a.row.n_blocks;
@@ -491,18 +601,25 @@ __global__ void __launch_bounds__(kBlockTreeThreads) msm_blocktree_kernel(BlockT
     }
     sh[t] = v;
     __syncthreads();
+    // level s folds partial j + s into partial j (j < s): the writers of a level own slots nobody reads in it
 #pragma unroll 1
-    for (uint32_t s = G >> 1; s > 0; s >>= 1) {
-        g1_xyzz other = g1_xyzz_inf();
-        if (j < s) other = sh[t + s * hop];
-        __syncthreads();
-        if (j < s) {
-            v = g1_add(v, other);
-            sh[t] = v;
+    for (uint32_t s = G >> 1, s_log = p.g_log - 1u; s > 0; s >>= 1, --s_log) {
+        const uint32_t pairs = OB * s;  // additions of this level
+        if (!QUAD || pairs * 4u > (uint32_t)kBlockTreeThreads) {  // more additions than quads: one lane each
+            if (j < s) {
+                v = g1_add(v, sh[t + s * hop]);
+                sh[t] = v;
+            }
+        } else if ((t & ~31u) < pairs * 4u) {  // warps with at least one addition; four lanes per addition
+            const uint32_t pr = t >> 2;
+            const bool on = pr < pairs;
+            // rows: pair -> (o, j) = (pr / s, pr % s), slot o * G + j; columns: slot j * OB + o = pr
+            const uint32_t ia = !on ? (uint32_t)kBlockTreeThreads - 1u : (is_row ? (((pr >> s_log) << p.g_log) | (pr & (s - 1u))) : pr);
+            xyzz_add_quad(sh, ia, on ? ia + s * hop : ia, on);
         }
         __syncthreads();
     }
-    if (j == 0 && O < p.n_out) g1_xyzz_store(p.out + O, v);
+    if (j == 0 && O < p.n_out) g1_xyzz_store(p.out + O, QUAD ? sh[t] : v);
 }
 
 // What is left per window are the two weighted sums.  A dependent XYZZ addition costs a warp ~3.8 us of
@@ -516,6 +633,7 @@ __global__ void __launch_bounds__(kBlockTreeThreads) msm_blocktree_kernel(BlockT
 // ceil(log2(c - 1)) additions on the critical path instead of a scan over hundreds of elements.
 constexpr int kBitThreads = 256;
 
+template <bool QUAD>
 __global__ void __launch_bounds__(kBitThreads) msm_bitsum_kernel(const g1_xyzz* __restrict__ col_sums, uint32_t l_log,
                                                                  const g1_xyzz* __restrict__ row_sums, uint32_t r_log,
                                                                  g1_xyzz* __restrict__ bit_sums /* [window][c - 1] */) {
@@ -524,9 +642,11 @@ __global__ void __launch_bounds__(kBitThreads) msm_bitsum_kernel(const g1_xyzz* 
     const g1_xyzz* C = col_sums + ((size_t)window << l_log);
     const g1_xyzz* R = row_sums + ((size_t)window << r_log);
     g1_xyzz acc = g1_xyzz_inf();
+    uint32_t live = 1;  // threads 0 .. live - 1 may hold a point
     // column side: weights v = lo + 1 in [1, L]; bit b < l is set in L / 2 of them, bit l only in v = L
     if (b < l_log) {
         const uint32_t cnt = 1u << (l_log - 1), low_mask = (1u << b) - 1u;
+        live = cnt;
 #pragma unroll 1
         for (uint32_t j = threadIdx.x; j < cnt; j += kBitThreads) {
             const uint32_t v = ((j >> b) << (b + 1)) | (1u << b) | (j & low_mask);  // j-th value with bit b set
@@ -538,6 +658,7 @@ __global__ void __launch_bounds__(kBitThreads) msm_bitsum_kernel(const g1_xyzz* 
     // row side: weights hi * L, hi < Rws: bit b >= l of the weight is bit b - l of hi
     if (b >= l_log && r_log > 0) {
         const uint32_t rb = b - l_log, cnt = 1u << (r_log - 1), low_mask = (1u << rb) - 1u;
+        live = cnt;
 #pragma unroll 1
         for (uint32_t j = threadIdx.x; j < cnt; j += kBitThreads) {
             const uint32_t hi = ((j >> rb) << (rb + 1)) | (1u << rb) | (j & low_mask);
@@ -546,18 +667,27 @@ __global__ void __launch_bounds__(kBitThreads) msm_bitsum_kernel(const g1_xyzz* 
     }
     sh[threadIdx.x] = acc;
     __syncthreads();
+    // binary tree over the live slots (a power of two); the empty upper levels of the 256-slot tree are skipped
+    uint32_t stride = kBitThreads / 2;
+    if (QUAD) {
+        if (live > (uint32_t)kBitThreads) live = kBitThreads;
+        while (stride >= live && stride > 0) stride >>= 1;  // live = 1: nothing to fold
+    }
 #pragma unroll 1
-    for (uint32_t stride = kBitThreads / 2; stride > 0; stride >>= 1) {
-        g1_xyzz o = g1_xyzz_inf();
-        if (threadIdx.x < stride) o = sh[threadIdx.x + stride];
-        __syncthreads();
-        if (threadIdx.x < stride) {
-            acc = g1_add(acc, o);
-            sh[threadIdx.x] = acc;
+    for (; stride > 0; stride >>= 1) {
+        if (!QUAD || stride * 4u > (uint32_t)kBitThreads) {  // more additions than quads: one lane each
+            if (threadIdx.x < stride) {
+                acc = g1_add(acc, sh[threadIdx.x + stride]);
+                sh[threadIdx.x] = acc;
+            }
+        } else if ((threadIdx.x & ~31u) < stride * 4u) {  // four lanes per addition
+            const uint32_t pr = threadIdx.x >> 2;
+            const bool on = pr < stride;
+            xyzz_add_quad(sh, on ? pr : (uint32_t)kBitThreads - 1u, on ? pr + stride : (uint32_t)kBitThreads - 1u, on);
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) g1_xyzz_store(bit_sums + (size_t)window * n_bits + b, acc);
+    if (threadIdx.x == 0) g1_xyzz_store(bit_sums + (size_t)window * n_bits + b, QUAD ? sh[0] : acc);
 }
 
 __device__ __forceinline__ g1_xyzz xyzz_shfl_down(const g1_xyzz& v, unsigned delta) {
@@ -837,6 +967,16 @@ static void tree_shape(int c, int latency, int* l_log, int* r_log, int* a_row, i
 // msm_finish_batch waits for that copy and runs the host epilogue.  The prover queues further
 // work between the two.
 // B200_HOST_HORNER=0 keeps the last step of the reduction on the device (A/B measurements)
+// B200_QUAD_ADD: 0 = one lane per addition everywhere (the round-1/2 kernels, kept for A/B measurements), 1 = four lanes per
+// addition (xyzz_add_quad) in the two tail kernels, 2 (default) = and in the serial tree level of a latency plan with few outputs
+static int quad_mode() {
+    static const int mode = [] {
+        const char* e = std::getenv("B200_QUAD_ADD");
+        return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2;
+    }();
+    return mode;
+}
+
 static bool use_host_horner(const MsmScratch* s) {
     static const bool env_on = [] {
         const char* e = std::getenv("B200_HOST_HORNER");
@@ -959,6 +1099,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
         seg_sums, seg_offsets, &stt->heavy_count, heavy_list, buckets);
     stamp(2);
     {
+        const bool quad = quad_mode() >= 1;
         g1_xyzz* t0 = (g1_xyzz*)s->tree.p;
         g1_xyzz *row_p = t0, *col_p = t0 + row_l1, *R = col_p + col_l1, *Cs = R + n_R;
         const g1_xyzz *row_in = buckets, *col_in = buckets;
@@ -968,7 +1109,18 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
             a.col = TreeLevel{buckets, col_p, a_col ? (uint32_t)col_l1 : 0u, (uint32_t)a_col, (uint32_t)l_log, 0};
             a.row.n_blocks = (a.row.n_out + kTreeThreads - 1) / kTreeThreads;
             a.col.n_blocks = (a.col.n_out + kTreeThreads - 1) / kTreeThreads;
-            B200_LAUNCH(msm_tree_kernel, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
+            // four lanes per output only where the level is a latency chain: a latency plan (one MSM alone) with fewer outputs
+            // than the machine has lanes.  As throughput work the quad form just adds its exchange overhead — with it
+            // everywhere the 2^20-point MSM's reduce went 0.40 -> 0.53 ms and the headline 286 -> 274 proofs/s (r2s), and with
+            // the size rule alone the pool's small statements lost 1.5 % against the tail kernels only (r2t)
+            if (quad_mode() >= 2 && pl.latency && (size_t)a.row.n_out + a.col.n_out <= kQuadTreeMaxOutputs) {
+                constexpr unsigned kQ = kTreeThreads / 4;  // outputs per block
+                a.row.n_blocks = (a.row.n_out + kQ - 1) / kQ;
+                a.col.n_blocks = (a.col.n_out + kQ - 1) / kQ;
+                B200_LAUNCH(msm_tree_quad_kernel<kTreeThreads>, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
+            } else {
+                B200_LAUNCH(msm_tree_kernel, a.row.n_blocks + a.col.n_blocks, kTreeThreads, 0, st)(a);
+            }
             if (a_row) row_in = row_p;
             if (a_col) col_in = col_p;
         }
@@ -981,15 +1133,18 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
             a.row.n_blocks = gr ? (uint32_t)((n_R + (256u >> gr) - 1) / (256u >> gr)) : 0u;
             a.col.n_blocks = gc ? (uint32_t)((n_C + (256u >> gc) - 1) / (256u >> gc)) : 0u;
             if (a.row.n_blocks + a.col.n_blocks)
-                B200_LAUNCH(msm_blocktree_kernel, a.row.n_blocks + a.col.n_blocks, kBlockTreeThreads, 0, st)(a);
+                if (quad) B200_LAUNCH(msm_blocktree_kernel<true>, a.row.n_blocks + a.col.n_blocks, kBlockTreeThreads, 0, st)(a);
+                else B200_LAUNCH(msm_blocktree_kernel<false>, a.row.n_blocks + a.col.n_blocks, kBlockTreeThreads, 0, st)(a);
             if (gr) row_in = R;
             if (gc) col_in = Cs;
         }
         // row_in: R[window][2^r_log], col_in: C[window][2^l_log]
         const unsigned n_bits = (unsigned)(pl.c - 1);
         g1_xyzz* bit_sums = (g1_xyzz*)s->bit_sums.p;
-        B200_LAUNCH(msm_bitsum_kernel, dim3(n_bits, (unsigned)n_windows), kBitThreads, 0, st)(col_in, (uint32_t)l_log, row_in,
-                                                                                               (uint32_t)r_log, bit_sums);
+        if (quad) B200_LAUNCH(msm_bitsum_kernel<true>, dim3(n_bits, (unsigned)n_windows), kBitThreads, 0, st)(col_in, (uint32_t)l_log, row_in,
+                                                                                                     (uint32_t)r_log, bit_sums);
+        else B200_LAUNCH(msm_bitsum_kernel<false>, dim3(n_bits, (unsigned)n_windows), kBitThreads, 0, st)(col_in, (uint32_t)l_log, row_in,
+                                                                                                      (uint32_t)r_log, bit_sums);
         // The last step, sum_b 2^b T_b, is a chain of c - 2 dependent doublings whoever runs it: ~5 us per operation for a lone
         // warp, ~0.5 us for a host core.  The host takes it (msm_finish_batch) unless the sums are consumed on the device.
         if (!use_host_horner(s)) B200_LAUNCH(msm_horner_kernel, (unsigned)n_windows, 32, 0, st)(bit_sums, n_bits, window_sums);
