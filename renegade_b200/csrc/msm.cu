@@ -500,6 +500,7 @@ struct TreeArgs {
     TreeLevel row, col;
 };
 constexpr int kTreeThreads = 128;
+constexpr size_t kSmallTreeBuckets = (size_t)1 << 17;  // latency plans up to this many buckets: fan-in 4 in the serial level, see tree_shape
 constexpr size_t kQuadTreeMaxOutputs = 16384;  // msm_tree_quad_kernel up to this many outputs (65536 lanes), see msm_launch_batch
 
 __global__ void __launch_bounds__(kTreeThreads) msm_tree_kernel(TreeArgs a) {
@@ -947,16 +948,26 @@ int bases_create(const g1_affine* h_points, size_t n, int c_override, int check_
 // Bits of the column index (l) and of the row index (r), and how each tree splits them: `a` bits by the serial
 // level (fan-in <= 8 per thread: the throughput part, two additions per bucket), the rest (<= 8 bits) by the
 // shared-memory binary tree of msm_blocktree_kernel.
-static void tree_shape(int c, int latency, int* l_log, int* r_log, int* a_row, int* a_col) {
+static void tree_shape(int c, int latency, size_t n_buckets, int* l_log, int* r_log, int* a_row, int* a_col) {
     const int bits = c - 1;
     const int l = (bits + 1) / 2, r = bits - l;
     *l_log = l;
     *r_log = r;
-    // (a latency plan without the serial level — the whole row / column in the shared-memory tree — was measured and lost:
-    // msm_blocktree_kernel 729 us vs 534 us for tree + block tree per 2^13 proof, profiles/r2n_*)
-    (void)latency;
-    *a_row = l < 3 ? l : 3;
-    *a_col = r < 3 ? r : 3;
+    // Fan-in 8 for the serial level, except in a latency plan with few buckets (one MSM alone up to c = 18; the 2^12
+    // statement's batch of five): there fan-in 4 and one more quad level in the shared-memory tree is the shorter chain
+    // (profiles/r2u_tree_fanin_ab.log: reduce of a lone 2^16-point MSM 0.155 -> 0.136 ms, 2^14 0.128 -> 0.110 ms; with more
+    // buckets the doubled block-tree work costs more than the chain saves: 2^14 proof 2.83 -> 2.93 ms).  No serial level
+    // at all was measured and lost in round 2 (profiles/r2n_*), fan-in 2 loses everywhere above 2^13 (r2u).
+    // B200_TREE_FANIN_LOG = 1 | 2 | 3 forces the fan-in of latency plans (A/B measurements).
+    static const int forced = [] {
+        const char* e = std::getenv("B200_TREE_FANIN_LOG");
+        return e && e[0] >= '1' && e[0] <= '3' ? e[0] - '0' : 0;
+    }();
+    int a = 3;
+    if (latency) a = forced ? forced : (n_buckets <= kSmallTreeBuckets ? 2 : 3);
+    if (l - a > 8) a = l - 8;  // the shared-memory tree takes at most 8 bits
+    *a_row = l < a ? l : a;
+    *a_col = r < a ? r : a;
 }
 
 // `batch` MSMs over the same bases (scalar vectors `stride` elements apart) in one pass: the
@@ -1030,7 +1041,7 @@ int msm_launch_batch(const Bases* b, size_t base_off, const fe* d_scalars, size_
     if ((rc = s->heavy.reserve((max_heavy + 1) * 4)) != B200_OK) return rc;
     if ((rc = s->seg_order.reserve(max_segs * 4)) != B200_OK) return rc;
     int l_log, r_log, a_row, a_col;
-    tree_shape(pl.c, pl.latency, &l_log, &r_log, &a_row, &a_col);
+    tree_shape(pl.c, pl.latency, n_buckets, &l_log, &r_log, &a_row, &a_col);
     if (l_log - a_row > 8 || r_log - a_col > 8) {
         set_error("msm: window too wide for the two-level bucket reduction");
         return B200_ERR_INVALID;
