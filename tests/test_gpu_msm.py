@@ -132,6 +132,26 @@ def test_msm_edge_cases(ctx, oracle, pyoracle, mode):
     assert (out == exp).all()
 
 
+@pytest.mark.parametrize("c", [0, 1, 12, 16])
+def test_msm_equal_partial_sums(ctx, oracle, pyoracle, mode, c):
+    """One base repeated, scalars 1 + 8 i: every eighth bucket holds the same point, so the reduction trees keep meeting
+    EQUAL operands (doubling) — and, with alternating signs, OPPOSITE ones (cancellation to the identity) — at every level,
+    including the levels that run four lanes per addition (xyzz_add_quad: the P = 0 paths and identity operands)."""
+    py = pyoracle
+    n = 256
+    one = oracle.known_dlog_bases(0xB200, 1)
+    pts = np.repeat(one, n, axis=0)
+    bases = ctx.load_bases(pts, window_bits=c)
+    same = [1 + 8 * i for i in range(n)]
+    alt = [(1 + 8 * i) if i % 2 == 0 else py.R - (1 + 8 * i) for i in range(n)]
+    wide = [((1 + 8 * i) << 100) + (1 + 8 * (n - 1 - i)) for i in range(n)]
+    for vals in (same, alt, wide):
+        s = oracle.ints_to_array(vals)
+        exp, einf = oracle.msm(pts, s)
+        out, inf = ctx.msm(bases, s)
+        assert inf == einf and (out == exp).all()
+
+
 def test_msm_skewed_scalars(ctx, oracle, pyoracle, mode):
     """Digit distributions that pile points into few buckets: identical scalars (one bucket per
     window holds every point -> block-tree combine path), small scalars (only the low windows),
