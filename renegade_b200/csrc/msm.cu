@@ -396,6 +396,7 @@ __device__ __forceinline__ void xyzz_add_quad(g1_xyzz* sh, uint32_t ia, uint32_t
     const bool a_inf = fe_is_zero(fe_load(F + 4u * ia + 2u)), b_inf = fe_is_zero(fe_load(F + 4u * ib + 2u));
     // nothing but copies in the whole warp (empty slots of a padded tree): skip the arithmetic
     if (__all_sync(0xffffffffu, !on || a_inf || b_inf)) {
+        __syncwarp();  // the quad's reads of a above, before its lanes overwrite a
         if (on && a_inf && !b_inf) fe_store(F + 4u * ia + q, fe_load(F + 4u * ib + q));
         return;
     }
@@ -415,7 +416,9 @@ __device__ __forceinline__ void xyzz_add_quad(g1_xyzz* sh, uint32_t ia, uint32_t
     // stage 4 (lane 2's product is not used)
     const fe m4 = fe_mul<Fq>(fe_pick3(q, rd, s1, m3), fe_pick3(q, fe_sub<Fq>(qq, x3), ppp, pd));
     const fe t2 = fe_quad_bcast(m4, 1);
-    // every lane of the warp has passed its last read of the operands (the shuffles above): the sum may replace a
+    // every lane of the warp has passed its last read of the operands; the barrier orders those reads before the
+    // stores that replace a (a shuffle synchronises execution, not shared memory)
+    __syncwarp();
     if (!on || b_inf) return;
     if (a_inf) {
         fe_store(F + 4u * ia + q, fe_load(F + 4u * ib + q));

@@ -8,6 +8,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/${T}_gpu.txt 2>&1
 lscpu | grep -E 'Model name|^CPU\(s\)' >> gpurun_out/${T}_gpu.txt
 echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -6 | tee gpurun_out/${T}_pytest_gpu.log
+if grep -qE "failed|error" gpurun_out/${T}_pytest_gpu.log; then echo "parity suite not green: stopping here"; exit 1; fi
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2 | tee gpurun_out/${T}_smoke.log
 for lg in 12 13 14 16; do timeout 200 python tools/prove_bench.py $lg 20 1 2>&1 | tail -1 | tee -a gpurun_out/${T}_prove_bench_latency_plan.log | cut -c1-200; done
 echo "== msm sweep (throughput plan)"; timeout 300 python tools/msm_sweep.py 12,13,14,16,18,20,22,24 0 2>&1 | tee gpurun_out/${T}_msm_size_sweep_1gpu.log | cut -c1-230
