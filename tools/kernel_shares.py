@@ -38,7 +38,8 @@ def main(path: str) -> None:
     for n, v in window:
         c, t = agg.get(n, (0, 0.0))
         agg[n] = (c + 1, t + v)
-    print("# kernel time per proof (n = 2^16), ncu launch list, serialised & cold-cache: compare shares")
+    lg = sys.argv[2] if len(sys.argv) > 2 else "16"
+    print(f"# kernel time per proof (n = 2^{lg}), ncu launch list, serialised & cold-cache: compare shares")
     print(f"launches {len(window)}  total {total:.1f} us")
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{n:42s} n={c:3d} {t:9.1f} us {100 * t / total:5.1f}%")
