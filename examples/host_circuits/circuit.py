@@ -889,6 +889,24 @@ class StateElementRotationGadget:
         cs.enforce_equal(NullifierGadget.compute_nullifier(old_version, cs), nullifier)
 
 
+    @staticmethod
+    def rotate_version(old_version: "StateWrapperVar", old_private_share, old_opening: "MerkleOpeningVar",
+                       merkle_root: Variable, nullifier: Variable, new_version: "StateWrapperVar", new_private_share,
+                       new_commitment: Variable, recovery_id: Variable, cs: PlonkCircuit) -> None:
+        """state_rotation.rs:81-121 (`rotate_version`): as above with the FULL commitment of the new version
+        (commitment.rs:193-224, `compute_commitments_with_shared_prefix`: both public chains run to the end)."""
+        cs.enforce_equal(RecoveryIdGadget.compute_recovery_id(new_version.recovery_stream, cs), recovery_id)
+        pc_old, pc_new = SharedPrefixCommitmentGadget.compute_private_commitments(old_private_share, new_private_share,
+                                                                                  old_version, new_version, cs)
+        pub_old, pub_new = SharedPrefixCommitmentGadget.compute_public_partial_commitments(
+            len(new_version.public_share), old_version.public_share, new_version.public_share, cs)
+        old_commitment = PoseidonHashGadget(cs.zero()).hash([pc_old, pub_old], cs)
+        cs.enforce_equal(PoseidonHashGadget(cs.zero()).hash([pc_new, pub_new], cs), new_commitment)
+        root = PoseidonMerkleHashGadget.compute_root_prehashed(old_commitment, old_opening, cs)
+        cs.enforce_equal(merkle_root, root)
+        cs.enforce_equal(NullifierGadget.compute_nullifier(old_version, cs), nullifier)
+
+
 class AmountGadget:
     """primitives/bitlength.rs:9-17."""
 

@@ -1,6 +1,6 @@
 """`/prove-*` routes of the GPU prover service (renegade_b200/service.py) for the statements restated in this package:
 the request decoders (`{statement, witness[, link hints]}`, api_types.rs:141-264) bound to the `SingleProverCircuit`s of
-statements.py.  The other sixteen paths of prover_service_client.rs:101-147 are not registered here (their circuits are
+statements.py.  The other thirteen paths of prover_service_client.rs:101-147 are not registered here (their circuits are
 not restated); the service answers 501 for them.
 
     python -m host_circuits.service_routes --port 3000 --password PW --srs /path/to/ptau [--device 0 --workers 6]
@@ -14,6 +14,7 @@ from renegade_b200.service import Route, from_json
 from . import intent_and_balance_validity as val
 from . import output_balance_validity as obv
 from . import private_settlement as ps
+from . import state_updates as su
 from . import statements as st
 from . import valid_balance_create as vbc
 
@@ -23,6 +24,15 @@ def routes():
         "/prove-valid-balance-create": Route(
             st.ValidBalanceCreate, lambda d: from_json(vbc.ValidBalanceCreateWitness, d),
             lambda d: from_json(vbc.ValidBalanceCreateStatement, d), "proof"),
+        "/prove-valid-deposit": Route(
+            st.ValidDeposit, lambda d: from_json(su.BalanceUpdateWitness, d), lambda d: from_json(su.ValidDepositStatement, d),
+            "proof"),
+        "/prove-valid-withdrawal": Route(
+            st.ValidWithdrawal, lambda d: from_json(su.BalanceUpdateWitness, d),
+            lambda d: from_json(su.ValidWithdrawalStatement, d), "proof"),
+        "/prove-valid-order-cancellation": Route(
+            st.ValidOrderCancellationCircuit, lambda d: from_json(su.ValidOrderCancellationWitness, d),
+            lambda d: from_json(su.ValidOrderCancellationStatement, d), "proof"),
         "/prove-intent-and-balance-validity": Route(
             st.IntentAndBalanceValidityCircuit, lambda d: from_json(val.Witness, d), lambda d: from_json(val.Statement, d),
             "proof_and_hint"),

@@ -1,4 +1,4 @@
-"""The five restated statements as `SingleProverCircuit`s (renegade_b200/circuit_types.py), under the reference's
+"""The restated statements as `SingleProverCircuit`s (renegade_b200/circuit_types.py), under the reference's
 circuit names — the registry the prover service (renegade_b200/service.py) and the tests use.
 
 Reference: the `SingleProverCircuit` impls at circuits-core/src/zk_circuits/valid_balance_create.rs:188-215,
@@ -13,6 +13,7 @@ from renegade_b200.fields import scalars_to_limbs
 from . import intent_and_balance_validity as val
 from . import output_balance_validity as obv
 from . import private_settlement as ps
+from . import state_updates as su
 from . import valid_balance_create as vbc
 
 
@@ -118,9 +119,36 @@ class OutputBalanceValidityCircuit(SingleProverCircuit):
         return obv.create_witness_statement(0, parties[0].output_balance)
 
 
+def _plain(mod_circuit, make_instance):
+    """A statement without link groups: name, synthesis, public inputs and a dummy instance."""
+    class _C(SingleProverCircuit):
+        @classmethod
+        def name(cls):
+            return mod_circuit.name()
+
+        @classmethod
+        def synthesize(cls, witness, statement, layout):
+            return mod_circuit.build(witness, statement)
+
+        @classmethod
+        def statement_scalars(cls, statement):
+            return scalars_to_limbs(statement.to_scalars())
+
+        @classmethod
+        def dummy_instance(cls):
+            return make_instance(0)
+    _C.__name__ = _C.__qualname__ = mod_circuit.__name__
+    return _C
+
+
+# valid_deposit.rs:177-195, valid_withdrawal.rs:189-207, valid_order_cancellation.rs:109-127
+ValidDeposit = _plain(su.ValidDeposit, su.create_deposit_witness_statement)
+ValidWithdrawal = _plain(su.ValidWithdrawal, su.create_withdrawal_witness_statement)
+ValidOrderCancellationCircuit = _plain(su.ValidOrderCancellationCircuit, su.create_cancellation_witness_statement)
+
 # the circuits `NativeProofManager::preprocess_circuits` registers (native_proof_manager.rs:305-331) that are restated here
-REGISTERED = [ValidBalanceCreate, IntentAndBalancePrivateSettlementCircuit, IntentAndBalanceValidityCircuit,
-              OutputBalanceValidityCircuit]
+REGISTERED = [ValidBalanceCreate, ValidDeposit, ValidWithdrawal, ValidOrderCancellationCircuit,
+              IntentAndBalancePrivateSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit]
 
 
 # ---- collaborative counterparts (traits.rs:1103-1154) ---------------------------------------------------------------

@@ -447,3 +447,70 @@ def test_intent_and_balance_validity_and_the_settlement_bundle(oracle, pyoracle)
     rc, lp, _ = oracle.plonk_link(hints[1][0], hints[0][0], hints[1][1], hints[0][1], lay.alignment, lay.offset, lay.size, srs)
     assert rc == 0                               # party 0's honest link proof does not carry over to party 1's commitment
     assert not oracle.plonk_link_verify_known_tau(hints[2][1], hints[0][1], lay.alignment, lay.offset, lay.size, lp, tau)
+
+
+@pytest.mark.parametrize("which", ["deposit", "withdrawal", "cancellation"])
+def test_state_update_circuits(oracle, pyoracle, which):
+    """VALID DEPOSIT, VALID WITHDRAWAL and VALID ORDER CANCELLATION restated (examples/host_circuits/state_updates.py): the
+    native witness / statement satisfy the circuit, every statement field is binding, the rules the reference tests
+    (valid_deposit.rs / valid_withdrawal.rs / valid_order_cancellation.rs `mod test`) are enforced, and the oracle
+    prover's proof is accepted by the oracle verifier."""
+    from host_circuits import state_updates as su
+    py = pyoracle
+    make, circuit, n_inputs, gates = {
+        "deposit": (su.create_deposit_witness_statement, su.ValidDeposit, 8, (6500, 7200)),
+        "withdrawal": (su.create_withdrawal_witness_statement, su.ValidWithdrawal, 8, (6500, 7200)),
+        "cancellation": (su.create_cancellation_witness_statement, su.ValidOrderCancellationCircuit, 3, (4200, 4700)),
+    }[which]
+    witness, statement = make(11)
+    cs = circuit.build(witness, statement)
+    pub = statement.to_scalars()
+    assert cs.public_input() == pub and len(pub) == n_inputs
+    cs.check_circuit_satisfiability(pub)
+    for i in range(len(pub)):                     # no statement field is free
+        bad = list(pub)
+        bad[i] = (bad[i] + 1) % C.R
+        with pytest.raises(C.CircuitError):
+            cs.check_circuit_satisfiability(bad)
+
+    def unsatisfied(w, s):
+        with pytest.raises(C.CircuitError):
+            circuit.build(w, s).check_circuit_satisfiability(s.to_scalars())
+
+    if which == "deposit":
+        # a deposit that overflows the amount range (valid_deposit.rs: test_invalid_deposit__amount_overflow)
+        w, s = make(12)
+        w.old_balance.inner[su.AMOUNT_IDX] = (1 << C.AMOUNT_BITS) - 1
+        unsatisfied(w, s)
+        # a deposit of another token / from another owner than the balance's
+        w, s = make(13)
+        s.deposit.token ^= 1
+        unsatisfied(w, s)
+    elif which == "withdrawal":
+        # outstanding fees block a withdrawal; a zero withdrawal and one above the balance are refused
+        w, s = make(12)
+        w.old_balance.inner[5] = 1
+        unsatisfied(w, s)
+        w, s = make(13)
+        s.withdrawal.amount = 0
+        unsatisfied(w, s)
+        w, s = make(14)
+        s.withdrawal.amount = w.old_balance.inner[su.AMOUNT_IDX] + 1
+        unsatisfied(w, s)
+    else:
+        # somebody else's intent, a forged opening
+        w, s = make(12)
+        s.owner ^= 1
+        unsatisfied(w, s)
+        w, s = make(13)
+        w.old_intent_opening.elems[3] ^= 1
+        unsatisfied(w, s)
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == 13 and circ.num_inputs == n_inputs and gates[0] < circ.n_gates < gates[1]
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    rc, proof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                         synth.splitmix_blinders(0xBA2), srs)
+    assert rc == 0
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)

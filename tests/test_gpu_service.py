@@ -87,3 +87,42 @@ def test_prove_paths_over_http(srs_2_16, g2_raw):
         server.shutdown()
         ct.clear_key_cache()
         pool.close()
+
+
+def test_state_update_paths_over_http(srs_2_16, g2_raw):
+    """VALID DEPOSIT, VALID WITHDRAWAL and VALID ORDER CANCELLATION (`ProofResponse` paths, prover_service_client.rs:
+    101-147) through the service: the proofs verify with the pairing under the circuits' cached keys; a request whose
+    statement does not belong to its witness comes back as a prover error."""
+    import renegade_b200 as rb
+    from host_circuits import service_routes
+    from host_circuits import state_updates as su
+    from host_circuits import statements as st
+    from renegade_b200 import circuit_types as ct
+    from renegade_b200 import service as sv
+    from renegade_b200.backend import ProverPool
+    h, tau_h = g2_raw
+    pool = ProverPool(0, workers=3)
+    ctx = pool.context(0)
+    params = rb.parse_ptau_file(ctx, srs_2_16, count=(1 << 14) + 3)
+    ct.set_system_srs(ctx, params.powers_of_g, h, tau_h, pool=pool)
+    service = sv.ProverService(service_routes.routes(), password="pw", pool=pool)
+    server = service.make_server("127.0.0.1", 0)
+    threading.Thread(target=server.serve_forever, daemon=True).start()
+    try:
+        client = sv.ProofServiceClient(f"http://127.0.0.1:{server.server_address[1]}", "pw")
+        for path, circuit, make in (("/prove-valid-deposit", st.ValidDeposit, su.create_deposit_witness_statement),
+                                    ("/prove-valid-withdrawal", st.ValidWithdrawal, su.create_withdrawal_witness_statement),
+                                    ("/prove-valid-order-cancellation", st.ValidOrderCancellationCircuit,
+                                     su.create_cancellation_witness_statement)):
+            w, s = make(41)
+            code, body = client.send_request(path, {"statement": sv.to_json(s), "witness": sv.to_json(w)})
+            assert code == 200 and set(body) == {"proof"}, (path, body)
+            ct.verify_singleprover_proof(circuit, s, sv.decode_proof(body["proof"]))
+            _, s_other = make(42)
+            code, body = client.send_request(path, {"statement": sv.to_json(s_other), "witness": sv.to_json(w)})
+            assert code == 500 and "ProverError" in body["error"], path
+        assert service.stats["proofs"] == 3
+    finally:
+        server.shutdown()
+        ct.clear_key_cache()
+        pool.close()

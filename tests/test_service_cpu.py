@@ -30,6 +30,14 @@ def test_witness_statement_codec_round_trips():
     assert sv.from_json(val.Statement, sv.to_json(s2)) == s2
     w3, s3 = obv.create_witness_statement(9, parties[0].output_balance)
     assert sv.from_json(obv.Witness, sv.to_json(w3)) == w3 and sv.from_json(obv.Statement, sv.to_json(s3)) == s3
+    from host_circuits import state_updates as su
+    for tp_w, tp_s, make in ((su.BalanceUpdateWitness, su.ValidDepositStatement, su.create_deposit_witness_statement),
+                             (su.BalanceUpdateWitness, su.ValidWithdrawalStatement, su.create_withdrawal_witness_statement),
+                             (su.ValidOrderCancellationWitness, su.ValidOrderCancellationStatement, su.create_cancellation_witness_statement)):
+        w4, s4 = make(11)
+        assert sv.from_json(tp_w, json.loads(json.dumps(sv.to_json(w4)))) == w4
+        assert sv.from_json(tp_s, json.loads(json.dumps(sv.to_json(s4)))) == s4
+    assert set(sv.to_json(su.create_withdrawal_witness_statement(1)[1])["withdrawal"]) == {"to", "token", "amount"}
     # scalars are accepted as decimal, hex and 32-byte big-endian arrays
     v = 0x1234567890abcdef1234567890abcdef
     assert sv.decode_scalar(str(v)) == sv.decode_scalar(hex(v)) == sv.decode_scalar(list(v.to_bytes(32, "big"))) == v
@@ -75,10 +83,47 @@ def test_auth_and_routing_without_a_gpu():
         url = f"http://127.0.0.1:{server.server_address[1]}"
         good, bad = sv.ProofServiceClient(url, "hunter2"), sv.ProofServiceClient(url, "wrong")
         assert bad.send_request("/prove-valid-balance-create", {})[0] == 401
-        assert good.send_request("/prove-valid-deposit", {})[0] == 501            # a reference path whose circuit is not restated
+        assert good.send_request("/prove-valid-note-redemption", {})[0] == 501    # a reference path whose circuit is not restated
         assert good.send_request("/prove-something-else", {})[0] == 404
         code, body = good.send_request("/prove-valid-balance-create", {"statement": {}})  # malformed: no witness
         assert code == 400 and "bad request" in body["error"]
         assert service.stats["requests"] == 4 and service.stats["proofs"] == 0
     finally:
         server.shutdown()
+
+
+def test_every_route_decodes_and_synthesizes_the_keyed_structure():
+    """What the service does before the device call, for every registered path: decode the JSON request, synthesize,
+    arithmetize.  The circuit STRUCTURE (selectors, copy permutation, public-input count) of a fresh instance must be the
+    one the key was preprocessed from (`dummy_instance`, traits.rs:821-855: keys are cached by circuit name) — i.e.
+    synthesis is witness-independent — and the instance must satisfy it."""
+    import json
+    from host_circuits import state_updates as su
+    from host_circuits import statements as st
+    routes = service_routes.routes()
+    assert len(routes) == 7
+    parties, _ = ps.create_witness_statement(31)
+    fresh = {
+        "/prove-valid-balance-create": vbc.create_witness_statement(31),
+        "/prove-valid-deposit": su.create_deposit_witness_statement(31),
+        "/prove-valid-withdrawal": su.create_withdrawal_witness_statement(31),
+        "/prove-valid-order-cancellation": su.create_cancellation_witness_statement(31),
+        "/prove-intent-and-balance-validity": val.create_witness_statement(31),
+        "/prove-output-balance-validity": obv.create_witness_statement(31, parties[0].output_balance),
+        "/prove-intent-and-balance-private-settlement": ps.create_witness_statement(31),
+    }
+    assert set(fresh) == set(routes)
+    for path, route in routes.items():
+        C = route.circuit
+        assert C in st.REGISTERED
+        w, s = fresh[path]
+        body = json.loads(json.dumps({"witness": sv.to_json(w), "statement": sv.to_json(s)}))
+        w2, s2 = route.decode_witness(body["witness"]), route.decode_statement(body["statement"])
+        layout = C.get_circuit_layout()
+        cs = C.synthesize(w2, s2, layout)
+        cs.check_circuit_satisfiability(s2.to_scalars())
+        circ = cs.finalize_for_arithmetization()
+        key_circ = C.synthesize(*C.dummy_instance(), layout).finalize_for_arithmetization()
+        assert (circ.log_n, circ.num_inputs) == (key_circ.log_n, key_circ.num_inputs), path
+        assert (circ.selectors == key_circ.selectors).all() and (circ.perm == key_circ.perm).all(), path
+        assert (C.statement_scalars(s2) == circ.pub_inputs).all(), path
