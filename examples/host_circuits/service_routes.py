@@ -1,6 +1,6 @@
 """`/prove-*` routes of the GPU prover service (renegade_b200/service.py) for the statements restated in this package:
 the request decoders (`{statement, witness[, link hints]}`, api_types.rs:141-264) bound to the `SingleProverCircuit`s of
-statements.py.  The other thirteen paths of prover_service_client.rs:101-147 are not registered here (their circuits are
+statements.py.  The other nine paths of prover_service_client.rs:101-147 are not registered here (their circuits are
 not restated); the service answers 501 for them.
 
     python -m host_circuits.service_routes --port 3000 --password PW --srs /path/to/ptau [--device 0 --workers 6]
@@ -12,6 +12,7 @@ from typing import List
 from renegade_b200.service import Route, from_json
 
 from . import intent_and_balance_validity as val
+from . import intent_only as io
 from . import output_balance_validity as obv
 from . import private_settlement as ps
 from . import state_updates as su
@@ -33,6 +34,21 @@ def routes():
         "/prove-valid-order-cancellation": Route(
             st.ValidOrderCancellationCircuit, lambda d: from_json(su.ValidOrderCancellationWitness, d),
             lambda d: from_json(su.ValidOrderCancellationStatement, d), "proof"),
+        "/prove-intent-only-validity": Route(
+            st.IntentOnlyValidityCircuit, lambda d: from_json(io.ValidityWitness, d), lambda d: from_json(io.ValidityStatement, d),
+            "proof_and_hint"),
+        "/prove-intent-only-first-fill-validity": Route(
+            st.IntentOnlyFirstFillValidityCircuit, lambda d: from_json(io.FirstFillWitness, d),
+            lambda d: from_json(io.FirstFillStatement, d), "proof_and_hint"),
+        # SettlementProofResponse {proof, link_proof}: the request carries the validity proof's hint (api_types.rs:279-299)
+        "/prove-intent-only-public-settlement": Route(
+            st.IntentOnlyPublicSettlementCircuit, lambda d: from_json(io.PublicSettlementWitness, d),
+            lambda d: from_json(io.PublicSettlementStatement, d), "settlement",
+            links=[("validity_link_hint", "link_proof", io.INTENT_ONLY_SETTLEMENT_LINK)]),
+        "/prove-intent-only-bounded-settlement": Route(
+            st.IntentOnlyBoundedSettlementCircuit, lambda d: from_json(io.PublicSettlementWitness, d),
+            lambda d: from_json(io.BoundedSettlementStatement, d), "settlement",
+            links=[("validity_link_hint", "link_proof", io.INTENT_ONLY_SETTLEMENT_LINK)]),
         "/prove-intent-and-balance-validity": Route(
             st.IntentAndBalanceValidityCircuit, lambda d: from_json(val.Witness, d), lambda d: from_json(val.Statement, d),
             "proof_and_hint"),

@@ -11,6 +11,7 @@ from renegade_b200.circuit_types import SingleProverCircuit
 from renegade_b200.fields import scalars_to_limbs
 
 from . import intent_and_balance_validity as val
+from . import intent_only as io
 from . import output_balance_validity as obv
 from . import private_settlement as ps
 from . import state_updates as su
@@ -146,8 +147,75 @@ ValidDeposit = _plain(su.ValidDeposit, su.create_deposit_witness_statement)
 ValidWithdrawal = _plain(su.ValidWithdrawal, su.create_withdrawal_witness_statement)
 ValidOrderCancellationCircuit = _plain(su.ValidOrderCancellationCircuit, su.create_cancellation_witness_statement)
 
+# ---- the intent-only family: one link group, placed by INTENT ONLY PUBLIC SETTLEMENT and inherited by the other three
+# (intent_only_public_settlement.rs:120-123, intent_only_bounded_settlement.rs, intent_only.rs:223-229,
+#  intent_only_first_fill.rs:168-174)
+class IntentOnlyPublicSettlementCircuit(SingleProverCircuit):
+    @classmethod
+    def name(cls):
+        return io.IntentOnlyPublicSettlementCircuit.name()
+
+    @classmethod
+    def proof_linking_groups(cls):
+        return [(io.INTENT_ONLY_SETTLEMENT_LINK, None)]
+
+    @classmethod
+    def generate_layout(cls):
+        return io.IntentOnlyPublicSettlementCircuit.build(*io.create_public_settlement_witness_statement(0)).get_circuit_layout()
+
+    @classmethod
+    def synthesize(cls, witness, statement, layout):
+        return io.IntentOnlyPublicSettlementCircuit.build(witness, statement, layout[io.INTENT_ONLY_SETTLEMENT_LINK])
+
+    @classmethod
+    def statement_scalars(cls, statement):
+        return scalars_to_limbs(statement.to_scalars())
+
+    @classmethod
+    def dummy_instance(cls):
+        return io.create_public_settlement_witness_statement(0)
+
+
+def _intent_only_inheritor(mod_circuit, make_instance):
+    class _C(SingleProverCircuit):
+        @classmethod
+        def name(cls):
+            return mod_circuit.name()
+
+        @classmethod
+        def proof_linking_groups(cls):
+            lay = IntentOnlyPublicSettlementCircuit.get_circuit_layout()
+            return [(io.INTENT_ONLY_SETTLEMENT_LINK, lay[io.INTENT_ONLY_SETTLEMENT_LINK])]
+
+        @classmethod
+        def generate_layout(cls):
+            return IntentOnlyPublicSettlementCircuit.get_circuit_layout()
+
+        @classmethod
+        def synthesize(cls, witness, statement, layout):
+            return mod_circuit.build(witness, statement, layout[io.INTENT_ONLY_SETTLEMENT_LINK])
+
+        @classmethod
+        def statement_scalars(cls, statement):
+            return scalars_to_limbs(statement.to_scalars())
+
+        @classmethod
+        def dummy_instance(cls):
+            return make_instance(0)
+    _C.__name__ = _C.__qualname__ = mod_circuit.__name__
+    return _C
+
+
+IntentOnlyBoundedSettlementCircuit = _intent_only_inheritor(io.IntentOnlyBoundedSettlementCircuit,
+                                                            io.create_bounded_settlement_witness_statement)
+IntentOnlyValidityCircuit = _intent_only_inheritor(io.IntentOnlyValidityCircuit, io.create_validity_witness_statement)
+IntentOnlyFirstFillValidityCircuit = _intent_only_inheritor(io.IntentOnlyFirstFillValidityCircuit,
+                                                            io.create_first_fill_witness_statement)
+
 # the circuits `NativeProofManager::preprocess_circuits` registers (native_proof_manager.rs:305-331) that are restated here
 REGISTERED = [ValidBalanceCreate, ValidDeposit, ValidWithdrawal, ValidOrderCancellationCircuit,
+              IntentOnlyValidityCircuit, IntentOnlyFirstFillValidityCircuit, IntentOnlyPublicSettlementCircuit,
+              IntentOnlyBoundedSettlementCircuit,
               IntentAndBalancePrivateSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit]
 
 

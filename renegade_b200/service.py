@@ -186,8 +186,8 @@ def decode_link_proof(d: Dict[str, Any]) -> B200LinkProof:
 @dataclasses.dataclass
 class Route:
     """One `/prove-*` path: the circuit, how to decode its witness / statement, and the response kind
-    ("proof" = ProofResponse, "proof_and_hint" = ProofAndHintResponse, "private_settlement" =
-    PrivateSettlementProofResponse; api_types.rs:81-130)."""
+    ("proof" = ProofResponse, "proof_and_hint" = ProofAndHintResponse, "settlement" = SettlementProofResponse — one link
+    proof —, "private_settlement" = PrivateSettlementProofResponse — four; api_types.rs:81-130)."""
     circuit: type
     decode_witness: Callable[[Any], Any]
     decode_statement: Callable[[Any], Any]
@@ -214,7 +214,7 @@ class ProverService:
             return {"proof": encode_proof(proof)}
         if route.response == "proof_and_hint":
             return {"proof": encode_proof(proof), "link_hint": encode_link_hint(hint)}
-        if route.response == "private_settlement":
+        if route.response in ("settlement", "private_settlement"):  # SettlementProofResponse / PrivateSettlementProofResponse
             layouts = route.circuit.get_circuit_layout()
             out = {"proof": encode_proof(proof)}
             jobs = []

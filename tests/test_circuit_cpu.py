@@ -7,6 +7,7 @@ prover is bit-exact with."""
 import os
 import random
 
+import numpy as np
 import pytest
 
 from host_circuits import circuit as C
@@ -514,3 +515,93 @@ def test_state_update_circuits(oracle, pyoracle, which):
                                          synth.splitmix_blinders(0xBA2), srs)
     assert rc == 0
     assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)
+
+
+def test_intent_only_family_and_its_link(oracle, pyoracle):
+    """INTENT ONLY VALIDITY / FIRST FILL VALIDITY / PUBLIC SETTLEMENT / BOUNDED SETTLEMENT restated
+    (examples/host_circuits/intent_only.py): each satisfied by its native witness / statement with every statement field
+    binding and the rules of the reference's tests enforced; the four share ONE link group placed by the public
+    settlement circuit; the oracle proves a validity proof and a settlement proof of the same intent, links them
+    (proof_linking/intent_only.rs:34-49: validity hint first) and the link verifies — and does not for another intent."""
+    from host_circuits import intent_only as io
+    py = pyoracle
+    rnd = random.Random(77)
+    intent = io.Intent(rnd.randrange(1 << 160), rnd.randrange(1 << 160), rnd.randrange(1 << 160),
+                       rnd.randrange(1, 1 << 80), rnd.randrange(1 << 40, 1 << 70))
+    cases = {
+        "validity": (io.IntentOnlyValidityCircuit, io.create_validity_witness_statement(5, intent), 13, 7),
+        "first_fill": (io.IntentOnlyFirstFillValidityCircuit, io.create_first_fill_witness_statement(6, intent), 11, 8),
+        "public": (io.IntentOnlyPublicSettlementCircuit, io.create_public_settlement_witness_statement(7, intent), 9, 6),
+        "bounded": (io.IntentOnlyBoundedSettlementCircuit, io.create_bounded_settlement_witness_statement(8, intent), 9, 9),
+    }
+    circs, layout = {}, None
+    for key, (circuit, (w, s), log_n, n_inputs) in cases.items():
+        cs = circuit.build(w, s)
+        pub = s.to_scalars()
+        assert cs.public_input() == pub and len(pub) == n_inputs
+        cs.check_circuit_satisfiability(pub)
+        for i in range(len(pub)):
+            bad = list(pub)
+            bad[i] = (bad[i] + 1) % C.R
+            with pytest.raises(C.CircuitError):
+                cs.check_circuit_satisfiability(bad)
+        lay = cs.get_circuit_layout()[io.INTENT_ONLY_SETTLEMENT_LINK]
+        assert (lay.alignment, lay.offset, lay.size) == (9, 16, 5)
+        layout = layout or lay
+        circs[key] = cs.finalize_for_arithmetization()
+        assert circs[key].log_n == log_n, key
+
+    def unsatisfied(circuit, w, s):
+        with pytest.raises(C.CircuitError):
+            circuit.build(w, s).check_circuit_satisfiability(s.to_scalars())
+
+    # settlement: more than the intent allows, a worse price, the wrong pair
+    w, s = io.create_public_settlement_witness_statement(9, intent)
+    s.settlement_obligation.amount_in = intent.amount_in + 1
+    unsatisfied(io.IntentOnlyPublicSettlementCircuit, w, s)
+    w, s = io.create_public_settlement_witness_statement(9, intent)
+    s.settlement_obligation.amount_out = ((intent.min_price * s.settlement_obligation.amount_in) >> 63) - 1
+    unsatisfied(io.IntentOnlyPublicSettlementCircuit, w, s)
+    w, s = io.create_bounded_settlement_witness_statement(9, intent)
+    s.bounded_match_result.price = intent.min_price - 1
+    unsatisfied(io.IntentOnlyBoundedSettlementCircuit, w, s)
+    w, s = io.create_bounded_settlement_witness_statement(9, intent)
+    s.bounded_match_result.max_internal_party_amount_in = intent.amount_in + 1
+    unsatisfied(io.IntentOnlyBoundedSettlementCircuit, w, s)
+    # validity: the linked copy must be the state's intent; first fill: amount / price ranges, the owner
+    w, s = io.create_validity_witness_statement(10, intent)
+    w.intent = io.Intent(intent.in_token, intent.out_token, intent.owner, intent.min_price, intent.amount_in + 1)
+    unsatisfied(io.IntentOnlyValidityCircuit, w, s)
+    for field, value in (("amount_in", 1 << C.AMOUNT_BITS), ("min_price", 1 << io.PRICE_BITS)):
+        bad_intent = io.Intent(**{**intent.__dict__, field: value})
+        unsatisfied(io.IntentOnlyFirstFillValidityCircuit, *io.create_first_fill_witness_statement(11, bad_intent))
+    w, s = io.create_first_fill_witness_statement(12, intent)
+    s.owner ^= 1
+    unsatisfied(io.IntentOnlyFirstFillValidityCircuit, w, s)
+
+    # prove validity (2^13) and public settlement (2^9) on one SRS, link the group, verify the link
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, (1 << 13) + 3)
+
+    def prove(c, seed):
+        opk = oracle.plonk_preprocess(c.log_n, c.selectors, c.perm, c.k, srs[:c.n + 3])
+        rc, proof, _, link = oracle.plonk_prove(c.log_n, c.num_inputs, c.k, opk, c.wires, c.pub_inputs,
+                                                synth.splitmix_blinders(seed), srs[:c.n + 3], True)
+        assert rc == 0 and oracle.plonk_verify_known_tau(c.log_n, c.num_inputs, c.k, opk, c.pub_inputs, proof, tau)
+        return link, proof.to_array()[:8].copy()           # (linking wire polynomial, its commitment)
+
+    validity, settlement = prove(circs["validity"], 0xC0), prove(circs["public"], 0xC1)
+    for j, v in enumerate(intent.to_scalars()):          # both circuits hold the intent on the group's rows
+        for key in ("validity", "public", "first_fill", "bounded"):
+            c = circs[key]
+            assert c.wires_int[0][(layout.offset + j) << (c.log_n - layout.alignment)] == v
+    rc, lp, _ = oracle.plonk_link(validity[0], settlement[0], validity[1], settlement[1], layout.alignment, layout.offset,
+                                  layout.size, srs)
+    assert rc == 0
+    assert oracle.plonk_link_verify_known_tau(validity[1], settlement[1], layout.alignment, layout.offset, layout.size, lp, tau)
+    # a settlement proof about ANOTHER intent does not link: the prover refuses, the honest link proof does not transfer
+    other = prove(io.IntentOnlyPublicSettlementCircuit.build(*io.create_public_settlement_witness_statement(13))
+                  .finalize_for_arithmetization(), 0xC2)
+    rc, _, _ = oracle.plonk_link(validity[0], other[0], validity[1], other[1], layout.alignment, layout.offset, layout.size, srs)
+    assert rc == 2
+    assert not oracle.plonk_link_verify_known_tau(validity[1], other[1], layout.alignment, layout.offset, layout.size, lp, tau)

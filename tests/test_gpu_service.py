@@ -126,3 +126,59 @@ def test_state_update_paths_over_http(srs_2_16, g2_raw):
         server.shutdown()
         ct.clear_key_cache()
         pool.close()
+
+
+def test_intent_only_paths_over_http(srs_2_16, g2_raw):
+    """The intent-only flow as the relayer drives it (prover_service_client.rs:101-147): INTENT ONLY VALIDITY and FIRST FILL
+    VALIDITY (`ProofAndHintResponse`), then INTENT ONLY PUBLIC / BOUNDED SETTLEMENT with the validity proof's hint in the
+    request (`SettlementProofResponse {proof, link_proof}`, api_types.rs:97-104, 279-299).  Proofs verify with the
+    pairing under the cached keys; the link proofs verify against the two proofs' first wire commitments on the
+    group the public settlement circuit places."""
+    import renegade_b200 as rb
+    from host_circuits import intent_only as io
+    from host_circuits import service_routes
+    from host_circuits import statements as st
+    from renegade_b200 import circuit_types as ct
+    from renegade_b200 import service as sv
+    from renegade_b200.backend import GroupLayout, ProverPool, verify_link_proof
+    h, tau_h = g2_raw
+    pool = ProverPool(0, workers=3)
+    ctx = pool.context(0)
+    params = rb.parse_ptau_file(ctx, srs_2_16, count=(1 << 14) + 3)
+    ct.set_system_srs(ctx, params.powers_of_g, h, tau_h, pool=pool)
+    service = sv.ProverService(service_routes.routes(), password="pw", pool=pool)
+    server = service.make_server("127.0.0.1", 0)
+    threading.Thread(target=server.serve_forever, daemon=True).start()
+    try:
+        client = sv.ProofServiceClient(f"http://127.0.0.1:{server.server_address[1]}", "pw")
+        intent = io.create_public_settlement_witness_statement(51)[0].intent
+        lay = st.IntentOnlyPublicSettlementCircuit.get_circuit_layout()[io.INTENT_ONLY_SETTLEMENT_LINK]
+        group = GroupLayout(lay.alignment, lay.offset, lay.size)
+        hints, comms = {}, {}
+        for key, path, circuit, (w, s) in (
+                ("validity", "/prove-intent-only-validity", st.IntentOnlyValidityCircuit, io.create_validity_witness_statement(52, intent)),
+                ("first_fill", "/prove-intent-only-first-fill-validity", st.IntentOnlyFirstFillValidityCircuit,
+                 io.create_first_fill_witness_statement(53, intent))):
+            code, body = client.send_request(path, {"statement": sv.to_json(s), "witness": sv.to_json(w)})
+            assert code == 200 and set(body) == {"proof", "link_hint"}, (path, body)
+            proof = sv.decode_proof(body["proof"])
+            ct.verify_singleprover_proof(circuit, s, proof)
+            hints[key], comms[key] = body["link_hint"], sv.decode_link_hint(body["link_hint"]).linking_wire_comm
+            assert (comms[key] == np.array(proof.wires_poly_comms[0], dtype=np.uint64)).all()
+        for path, circuit, (w, s), hint_key in (
+                ("/prove-intent-only-public-settlement", st.IntentOnlyPublicSettlementCircuit,
+                 io.create_public_settlement_witness_statement(54, intent), "validity"),
+                ("/prove-intent-only-bounded-settlement", st.IntentOnlyBoundedSettlementCircuit,
+                 io.create_bounded_settlement_witness_statement(55, intent), "first_fill")):
+            code, body = client.send_request(path, {"statement": sv.to_json(s), "witness": sv.to_json(w),
+                                                    "validity_link_hint": hints[hint_key]})
+            assert code == 200 and set(body) == {"proof", "link_proof"}, (path, body)
+            proof = sv.decode_proof(body["proof"])
+            ct.verify_singleprover_proof(circuit, s, proof)
+            s_comm = np.array(proof.wires_poly_comms[0], dtype=np.uint64)
+            assert verify_link_proof(comms[hint_key], s_comm, sv.decode_link_proof(body["link_proof"]), group, h, tau_h)
+        assert service.stats["proofs"] == 4 and service.stats["link_proofs"] == 2
+    finally:
+        server.shutdown()
+        ct.clear_key_cache()
+        pool.close()

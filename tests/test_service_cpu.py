@@ -98,16 +98,21 @@ def test_every_route_decodes_and_synthesizes_the_keyed_structure():
     one the key was preprocessed from (`dummy_instance`, traits.rs:821-855: keys are cached by circuit name) — i.e.
     synthesis is witness-independent — and the instance must satisfy it."""
     import json
+    from host_circuits import intent_only as io
     from host_circuits import state_updates as su
     from host_circuits import statements as st
     routes = service_routes.routes()
-    assert len(routes) == 7
+    assert len(routes) == 11
     parties, _ = ps.create_witness_statement(31)
     fresh = {
         "/prove-valid-balance-create": vbc.create_witness_statement(31),
         "/prove-valid-deposit": su.create_deposit_witness_statement(31),
         "/prove-valid-withdrawal": su.create_withdrawal_witness_statement(31),
         "/prove-valid-order-cancellation": su.create_cancellation_witness_statement(31),
+        "/prove-intent-only-validity": io.create_validity_witness_statement(31),
+        "/prove-intent-only-first-fill-validity": io.create_first_fill_witness_statement(31),
+        "/prove-intent-only-public-settlement": io.create_public_settlement_witness_statement(31),
+        "/prove-intent-only-bounded-settlement": io.create_bounded_settlement_witness_statement(31),
         "/prove-intent-and-balance-validity": val.create_witness_statement(31),
         "/prove-output-balance-validity": obv.create_witness_statement(31, parties[0].output_balance),
         "/prove-intent-and-balance-private-settlement": ps.create_witness_statement(31),
