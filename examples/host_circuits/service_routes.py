@@ -1,6 +1,6 @@
 """`/prove-*` routes of the GPU prover service (renegade_b200/service.py) for the statements restated in this package:
 the request decoders (`{statement, witness[, link hints]}`, api_types.rs:141-264) bound to the `SingleProverCircuit`s of
-statements.py.  The other nine paths of prover_service_client.rs:101-147 are not registered here (their circuits are
+statements.py.  The other seven paths of prover_service_client.rs:101-147 are not registered here (their circuits are
 not restated); the service answers 501 for them.
 
     python -m host_circuits.service_routes --port 3000 --password PW --srs /path/to/ptau [--device 0 --workers 6]
@@ -15,6 +15,7 @@ from . import intent_and_balance_validity as val
 from . import intent_only as io
 from . import output_balance_validity as obv
 from . import private_settlement as ps
+from . import public_settlement as pub
 from . import state_updates as su
 from . import statements as st
 from . import valid_balance_create as vbc
@@ -55,6 +56,17 @@ def routes():
         "/prove-output-balance-validity": Route(
             st.OutputBalanceValidityCircuit, lambda d: from_json(obv.Witness, d), lambda d: from_json(obv.Statement, d),
             "proof_and_hint"),
+        # PublicSettlementProofResponse {proof, validity_link_proof, output_balance_link_proof} (api_types.rs:126-137, 238-277)
+        "/prove-intent-and-balance-public-settlement": Route(
+            st.IntentAndBalancePublicSettlementCircuit, lambda d: from_json(pub.Witness, d),
+            lambda d: from_json(pub.PublicStatement, d), "settlement",
+            links=[("validity_link_hint", "validity_link_proof", pub.PARTY_LINK),
+                   ("output_balance_link_hint", "output_balance_link_proof", pub.OUTPUT_LINK)]),
+        "/prove-intent-and-balance-bounded-settlement": Route(
+            st.IntentAndBalanceBoundedSettlementCircuit, lambda d: from_json(pub.Witness, d),
+            lambda d: from_json(pub.BoundedStatement, d), "settlement",
+            links=[("validity_link_hint", "validity_link_proof", pub.PARTY_LINK),
+                   ("output_balance_link_hint", "output_balance_link_proof", pub.OUTPUT_LINK)]),
         "/prove-intent-and-balance-private-settlement": Route(
             st.IntentAndBalancePrivateSettlementCircuit, lambda d: from_json(List[ps.PartyWitness], d),
             lambda d: from_json(ps.Statement, d), "private_settlement",

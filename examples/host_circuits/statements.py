@@ -14,6 +14,7 @@ from . import intent_and_balance_validity as val
 from . import intent_only as io
 from . import output_balance_validity as obv
 from . import private_settlement as ps
+from . import public_settlement as pub
 from . import state_updates as su
 from . import valid_balance_create as vbc
 
@@ -147,6 +148,45 @@ ValidDeposit = _plain(su.ValidDeposit, su.create_deposit_witness_statement)
 ValidWithdrawal = _plain(su.ValidWithdrawal, su.create_withdrawal_witness_statement)
 ValidOrderCancellationCircuit = _plain(su.ValidOrderCancellationCircuit, su.create_cancellation_witness_statement)
 
+# ---- one party's side settled in the open: both inherit the PARTY 0 groups of the private settlement circuit's layout
+# (intent_and_balance_public_settlement.rs:204-213, intent_and_balance_bounded_settlement.rs:189-198)
+def _party0_inheritor(mod_circuit, make_instance):
+    class _C(SingleProverCircuit):
+        @classmethod
+        def name(cls):
+            return mod_circuit.name()
+
+        @classmethod
+        def proof_linking_groups(cls):
+            lay = IntentAndBalancePrivateSettlementCircuit.get_circuit_layout()
+            return [(g, lay[g]) for g in (pub.PARTY_LINK, pub.OUTPUT_LINK)]
+
+        @classmethod
+        def generate_layout(cls):
+            lay = IntentAndBalancePrivateSettlementCircuit.get_circuit_layout()
+            return {g: lay[g] for g in (pub.PARTY_LINK, pub.OUTPUT_LINK)}
+
+        @classmethod
+        def synthesize(cls, witness, statement, layout):
+            return mod_circuit.build(witness, statement, layout)
+
+        @classmethod
+        def statement_scalars(cls, statement):
+            return scalars_to_limbs(statement.to_scalars())
+
+        @classmethod
+        def dummy_instance(cls):
+            return make_instance(0)
+    _C.__name__ = _C.__qualname__ = mod_circuit.__name__
+    return _C
+
+
+IntentAndBalancePublicSettlementCircuit = _party0_inheritor(pub.IntentAndBalancePublicSettlementCircuit,
+                                                            pub.create_public_witness_statement)
+IntentAndBalanceBoundedSettlementCircuit = _party0_inheritor(pub.IntentAndBalanceBoundedSettlementCircuit,
+                                                             pub.create_bounded_witness_statement)
+
+
 # ---- the intent-only family: one link group, placed by INTENT ONLY PUBLIC SETTLEMENT and inherited by the other three
 # (intent_only_public_settlement.rs:120-123, intent_only_bounded_settlement.rs, intent_only.rs:223-229,
 #  intent_only_first_fill.rs:168-174)
@@ -216,7 +256,8 @@ IntentOnlyFirstFillValidityCircuit = _intent_only_inheritor(io.IntentOnlyFirstFi
 REGISTERED = [ValidBalanceCreate, ValidDeposit, ValidWithdrawal, ValidOrderCancellationCircuit,
               IntentOnlyValidityCircuit, IntentOnlyFirstFillValidityCircuit, IntentOnlyPublicSettlementCircuit,
               IntentOnlyBoundedSettlementCircuit,
-              IntentAndBalancePrivateSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit]
+              IntentAndBalancePrivateSettlementCircuit, IntentAndBalancePublicSettlementCircuit,
+              IntentAndBalanceBoundedSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit]
 
 
 # ---- collaborative counterparts (traits.rs:1103-1154) ---------------------------------------------------------------

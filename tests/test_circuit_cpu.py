@@ -605,3 +605,84 @@ def test_intent_only_family_and_its_link(oracle, pyoracle):
     rc, _, _ = oracle.plonk_link(validity[0], other[0], validity[1], other[1], layout.alignment, layout.offset, layout.size, srs)
     assert rc == 2
     assert not oracle.plonk_link_verify_known_tau(validity[1], other[1], layout.alignment, layout.offset, layout.size, lp, tau)
+
+
+def test_public_and_bounded_settlement_circuits(oracle, pyoracle):
+    """INTENT AND BALANCE PUBLIC SETTLEMENT / BOUNDED SETTLEMENT restated (examples/host_circuits/public_settlement.py):
+    satisfied by party 0 of a consistent match, every statement field binding, the rules the reference's tests exercise
+    enforced, the PARTY 0 groups of the private settlement layout inherited — so the validity proof that links to a
+    private settlement links to the public one as well (checked on the oracle)."""
+    from host_circuits import intent_and_balance_validity as val
+    from host_circuits import private_settlement as ps
+    from host_circuits import public_settlement as pub
+    py = pyoracle
+    layouts = ps.IntentAndBalancePrivateSettlementCircuit.build(*ps.create_witness_statement(0)).get_circuit_layout()
+    built = {}
+    for key, make, circuit, n_inputs in (("public", pub.create_public_witness_statement, pub.IntentAndBalancePublicSettlementCircuit, 14),
+                                         ("bounded", pub.create_bounded_witness_statement, pub.IntentAndBalanceBoundedSettlementCircuit, 16)):
+        w, s = make(21)
+        cs = circuit.build(w, s, layouts)
+        pubs = s.to_scalars()
+        assert cs.public_input() == pubs and len(pubs) == n_inputs
+        cs.check_circuit_satisfiability(pubs)
+        for i in range(len(pubs)):
+            bad = list(pubs)
+            bad[i] = (bad[i] + 1) % C.R
+            with pytest.raises(C.CircuitError):
+                cs.check_circuit_satisfiability(bad)
+        lay = cs.get_circuit_layout()
+        assert {g: (l.alignment, l.offset, l.size) for g, l in lay.items()} == \
+            {pub.PARTY_LINK: (layouts[pub.PARTY_LINK].alignment, layouts[pub.PARTY_LINK].offset, 17),
+             pub.OUTPUT_LINK: (layouts[pub.OUTPUT_LINK].alignment, layouts[pub.OUTPUT_LINK].offset, 11)}
+        built[key] = (w, s, cs.finalize_for_arithmetization())
+        assert built[key][2].log_n == 12
+
+    def unsatisfied(circuit, w, s):
+        with pytest.raises(C.CircuitError):
+            circuit.build(w, s, layouts).check_circuit_satisfiability(s.to_scalars())
+
+    P, B = pub.IntentAndBalancePublicSettlementCircuit, pub.IntentAndBalanceBoundedSettlementCircuit
+    w, s = pub.create_public_witness_statement(22)          # the balance does not cover the obligation
+    w.in_balance.amount = s.settlement_obligation.amount_in - 1
+    unsatisfied(P, w, s)
+    w, s = pub.create_public_witness_statement(22)          # the receive balance would overflow
+    w.out_balance.amount = (1 << C.AMOUNT_BITS) - 1
+    unsatisfied(P, w, s)
+    w, s = pub.create_public_witness_statement(22)          # someone else's output balance
+    w.out_balance.owner ^= 1
+    unsatisfied(P, w, s)
+    w, s = pub.create_public_witness_statement(22)          # a leaked share that is not the linked one
+    s.in_balance_public_shares[2] = (s.in_balance_public_shares[2] + 1) % C.R
+    unsatisfied(P, w, s)
+    w, s = pub.create_bounded_witness_statement(22)         # the bound exceeds the capitalising balance
+    w.in_balance.amount = s.bounded_match_result.max_internal_party_amount_in - 1
+    unsatisfied(B, w, s)
+    w, s = pub.create_bounded_witness_statement(22)         # a price below the intent's worst case
+    s.bounded_match_result.price = w.intent.min_price - 1
+    unsatisfied(B, w, s)
+
+    # the party's validity proof links to the PUBLIC settlement proof on the inherited party-0 group
+    w, s, circ = built["public"]
+    vw, vs = val.create_witness_statement(23, intent=w.intent, balance=w.in_balance)
+    w2 = pub.Witness(w.intent, vw.new_amount_public_share, w.in_balance, list(vw.post_match_balance_shares), w.out_balance,
+                     w.pre_settlement_out_balance_shares)
+    s2 = pub.PublicStatement(s.settlement_obligation, w2.pre_settlement_amount_public_share, list(w2.pre_settlement_in_balance_shares),
+                             list(s.out_balance_public_shares), s.relayer_fee_rate, s.protocol_fee_rate, s.relayer_fee_recipient)
+    cs2 = P.build(w2, s2, layouts)
+    cs2.check_circuit_satisfiability(s2.to_scalars())
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, (1 << 14) + 3)
+
+    def prove(c, seed):
+        opk = oracle.plonk_preprocess(c.log_n, c.selectors, c.perm, c.k, srs[:c.n + 3])
+        rc, proof, _, link = oracle.plonk_prove(c.log_n, c.num_inputs, c.k, opk, c.wires, c.pub_inputs,
+                                                synth.splitmix_blinders(seed), srs[:c.n + 3], True)
+        assert rc == 0 and oracle.plonk_verify_known_tau(c.log_n, c.num_inputs, c.k, opk, c.pub_inputs, proof, tau)
+        return link, proof.to_array()[:8].copy()
+
+    validity = prove(val.IntentAndBalanceValidityCircuit.build(vw, vs, layouts).finalize_for_arithmetization(), 0xD0)
+    settlement = prove(cs2.finalize_for_arithmetization(), 0xD1)
+    g = layouts[pub.PARTY_LINK]
+    rc, lp, _ = oracle.plonk_link(validity[0], settlement[0], validity[1], settlement[1], g.alignment, g.offset, 17, srs)
+    assert rc == 0
+    assert oracle.plonk_link_verify_known_tau(validity[1], settlement[1], g.alignment, g.offset, 17, lp, tau)

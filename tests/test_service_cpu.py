@@ -99,10 +99,11 @@ def test_every_route_decodes_and_synthesizes_the_keyed_structure():
     synthesis is witness-independent — and the instance must satisfy it."""
     import json
     from host_circuits import intent_only as io
+    from host_circuits import public_settlement as pub
     from host_circuits import state_updates as su
     from host_circuits import statements as st
     routes = service_routes.routes()
-    assert len(routes) == 11
+    assert len(routes) == 13
     parties, _ = ps.create_witness_statement(31)
     fresh = {
         "/prove-valid-balance-create": vbc.create_witness_statement(31),
@@ -116,6 +117,8 @@ def test_every_route_decodes_and_synthesizes_the_keyed_structure():
         "/prove-intent-and-balance-validity": val.create_witness_statement(31),
         "/prove-output-balance-validity": obv.create_witness_statement(31, parties[0].output_balance),
         "/prove-intent-and-balance-private-settlement": ps.create_witness_statement(31),
+        "/prove-intent-and-balance-public-settlement": pub.create_public_witness_statement(31),
+        "/prove-intent-and-balance-bounded-settlement": pub.create_bounded_witness_statement(31),
     }
     assert set(fresh) == set(routes)
     for path, route in routes.items():
