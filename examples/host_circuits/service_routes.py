@@ -1,7 +1,7 @@
 """`/prove-*` routes of the GPU prover service (renegade_b200/service.py) for the statements restated in this package:
 the request decoders (`{statement, witness[, link hints]}`, api_types.rs:141-264) bound to the `SingleProverCircuit`s of
-statements.py.  The other seven paths of prover_service_client.rs:101-147 are not registered here (their circuits are
-not restated); the service answers 501 for them.
+statements.py.  The other four paths of prover_service_client.rs:101-147 are not registered here (their circuits verify Schnorr
+signatures / ElGamal ciphertexts on BabyJubJub in-circuit and are not restated); the service answers 501 for them.
 
     python -m host_circuits.service_routes --port 3000 --password PW --srs /path/to/ptau [--device 0 --workers 6]
 """
@@ -11,6 +11,7 @@ from typing import List
 
 from renegade_b200.service import Route, from_json
 
+from . import fees
 from . import intent_and_balance_validity as val
 from . import intent_only as io
 from . import output_balance_validity as obv
@@ -35,6 +36,15 @@ def routes():
         "/prove-valid-order-cancellation": Route(
             st.ValidOrderCancellationCircuit, lambda d: from_json(su.ValidOrderCancellationWitness, d),
             lambda d: from_json(su.ValidOrderCancellationStatement, d), "proof"),
+        "/prove-valid-note-redemption": Route(
+            st.ValidNoteRedemption, lambda d: from_json(fees.NoteRedemptionWitness, d),
+            lambda d: from_json(fees.NoteRedemptionStatement, d), "proof"),
+        "/prove-valid-public-protocol-fee-payment": Route(
+            st.ValidPublicProtocolFeePayment, lambda d: from_json(su.BalanceUpdateWitness, d),
+            lambda d: from_json(fees.PublicFeePaymentStatement, d), "proof"),
+        "/prove-valid-public-relayer-fee-payment": Route(
+            st.ValidPublicRelayerFeePayment, lambda d: from_json(su.BalanceUpdateWitness, d),
+            lambda d: from_json(fees.PublicFeePaymentStatement, d), "proof"),
         "/prove-intent-only-validity": Route(
             st.IntentOnlyValidityCircuit, lambda d: from_json(io.ValidityWitness, d), lambda d: from_json(io.ValidityStatement, d),
             "proof_and_hint"),

@@ -10,6 +10,7 @@ from __future__ import annotations
 from renegade_b200.circuit_types import SingleProverCircuit
 from renegade_b200.fields import scalars_to_limbs
 
+from . import fees
 from . import intent_and_balance_validity as val
 from . import intent_only as io
 from . import output_balance_validity as obv
@@ -148,6 +149,12 @@ ValidDeposit = _plain(su.ValidDeposit, su.create_deposit_witness_statement)
 ValidWithdrawal = _plain(su.ValidWithdrawal, su.create_withdrawal_witness_statement)
 ValidOrderCancellationCircuit = _plain(su.ValidOrderCancellationCircuit, su.create_cancellation_witness_statement)
 
+# fees/valid_note_redemption.rs:78-96, fees/valid_public_protocol_fee_payment.rs:166-186, fees/valid_public_relayer_fee_payment.rs
+ValidNoteRedemption = _plain(fees.ValidNoteRedemption, fees.create_note_redemption_witness_statement)
+ValidPublicProtocolFeePayment = _plain(fees.ValidPublicProtocolFeePayment, fees.create_public_protocol_fee_payment_witness_statement)
+ValidPublicRelayerFeePayment = _plain(fees.ValidPublicRelayerFeePayment, fees.create_public_relayer_fee_payment_witness_statement)
+
+
 # ---- one party's side settled in the open: both inherit the PARTY 0 groups of the private settlement circuit's layout
 # (intent_and_balance_public_settlement.rs:204-213, intent_and_balance_bounded_settlement.rs:189-198)
 def _party0_inheritor(mod_circuit, make_instance):
@@ -257,7 +264,10 @@ REGISTERED = [ValidBalanceCreate, ValidDeposit, ValidWithdrawal, ValidOrderCance
               IntentOnlyValidityCircuit, IntentOnlyFirstFillValidityCircuit, IntentOnlyPublicSettlementCircuit,
               IntentOnlyBoundedSettlementCircuit,
               IntentAndBalancePrivateSettlementCircuit, IntentAndBalancePublicSettlementCircuit,
-              IntentAndBalanceBoundedSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit]
+              IntentAndBalanceBoundedSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit,
+              ValidNoteRedemption, ValidPublicProtocolFeePayment, ValidPublicRelayerFeePayment]
+# not restated: INTENT AND BALANCE FIRST FILL VALIDITY and NEW OUTPUT BALANCE VALIDITY (in-circuit Schnorr verification on
+# BabyJubJub), VALID PRIVATE PROTOCOL / RELAYER FEE PAYMENT (in-circuit ElGamal on BabyJubJub)
 
 
 # ---- collaborative counterparts (traits.rs:1103-1154) ---------------------------------------------------------------

@@ -686,3 +686,64 @@ def test_public_and_bounded_settlement_circuits(oracle, pyoracle):
     rc, lp, _ = oracle.plonk_link(validity[0], settlement[0], validity[1], settlement[1], g.alignment, g.offset, 17, srs)
     assert rc == 0
     assert oracle.plonk_link_verify_known_tau(validity[1], settlement[1], g.alignment, g.offset, 17, lp, tau)
+
+
+@pytest.mark.parametrize("which", ["note_redemption", "public_protocol_fee", "public_relayer_fee"])
+def test_fee_circuits(oracle, pyoracle, which):
+    """VALID NOTE REDEMPTION and the two PUBLIC fee payments restated (examples/host_circuits/fees.py): satisfied, every
+    statement field binding, the rules of the reference's tests (fees/*.rs `mod test`) enforced; oracle proof + verify."""
+    from host_circuits import fees
+    py = pyoracle
+    make, circuit, n_inputs, log_n = {
+        "note_redemption": (fees.create_note_redemption_witness_statement, fees.ValidNoteRedemption, 6, 12),
+        "public_protocol_fee": (fees.create_public_protocol_fee_payment_witness_statement, fees.ValidPublicProtocolFeePayment, 9, 13),
+        "public_relayer_fee": (fees.create_public_relayer_fee_payment_witness_statement, fees.ValidPublicRelayerFeePayment, 9, 13),
+    }[which]
+    witness, statement = make(15)
+    cs = circuit.build(witness, statement)
+    pub = statement.to_scalars()
+    assert cs.public_input() == pub and len(pub) == n_inputs
+    cs.check_circuit_satisfiability(pub)
+    for i in range(len(pub)):
+        bad = list(pub)
+        bad[i] = (bad[i] + 1) % C.R
+        with pytest.raises(C.CircuitError):
+            cs.check_circuit_satisfiability(bad)
+
+    def unsatisfied(w, s):
+        with pytest.raises(C.CircuitError):
+            circuit.build(w, s).check_circuit_satisfiability(s.to_scalars())
+
+    if which == "note_redemption":
+        w, s = make(16)                            # a nullifier of another blinder, a forged opening
+        s.note.blinder ^= 1
+        unsatisfied(w, s)
+        w, s = make(16)
+        w.note_opening.elems[0] ^= 1
+        unsatisfied(w, s)
+    else:
+        idx = fees.PROTOCOL_FEE_IDX if which == "public_protocol_fee" else fees.RELAYER_FEE_IDX
+        w, s = make(16)                            # nothing to pay: a zero fee balance is refused
+        w.old_balance.inner[idx] = 0
+        unsatisfied(w, s)
+        w, s = make(16)                            # a note of another amount / mint
+        s.note.amount += 1
+        unsatisfied(w, s)
+        w, s = make(16)
+        s.note.mint ^= 1
+        unsatisfied(w, s)
+        w, s = make(16)                            # the receiver: free for the protocol fee, bound for the relayer fee
+        s.note.receiver ^= 1
+        if which == "public_relayer_fee":
+            unsatisfied(w, s)
+        else:
+            circuit.build(w, s).check_circuit_satisfiability(s.to_scalars())
+    circ = cs.finalize_for_arithmetization()
+    assert circ.log_n == log_n and circ.num_inputs == n_inputs
+    tau = oracle.int_to_limbs(py.to_mont(TAU % py.R, py.R))
+    srs = oracle.srs_from_tau(tau, circ.n + 3)
+    opk = oracle.plonk_preprocess(circ.log_n, circ.selectors, circ.perm, circ.k, srs)
+    rc, proof, _, _ = oracle.plonk_prove(circ.log_n, circ.num_inputs, circ.k, opk, circ.wires, circ.pub_inputs,
+                                         synth.splitmix_blinders(0xBA3), srs)
+    assert rc == 0
+    assert oracle.plonk_verify_known_tau(circ.log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, proof, tau)

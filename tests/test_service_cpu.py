@@ -83,7 +83,7 @@ def test_auth_and_routing_without_a_gpu():
         url = f"http://127.0.0.1:{server.server_address[1]}"
         good, bad = sv.ProofServiceClient(url, "hunter2"), sv.ProofServiceClient(url, "wrong")
         assert bad.send_request("/prove-valid-balance-create", {})[0] == 401
-        assert good.send_request("/prove-valid-note-redemption", {})[0] == 501    # a reference path whose circuit is not restated
+        assert good.send_request("/prove-valid-private-protocol-fee-payment", {})[0] == 501    # a reference path whose circuit is not restated
         assert good.send_request("/prove-something-else", {})[0] == 404
         code, body = good.send_request("/prove-valid-balance-create", {"statement": {}})  # malformed: no witness
         assert code == 400 and "bad request" in body["error"]
@@ -98,18 +98,22 @@ def test_every_route_decodes_and_synthesizes_the_keyed_structure():
     one the key was preprocessed from (`dummy_instance`, traits.rs:821-855: keys are cached by circuit name) — i.e.
     synthesis is witness-independent — and the instance must satisfy it."""
     import json
+    from host_circuits import fees
     from host_circuits import intent_only as io
     from host_circuits import public_settlement as pub
     from host_circuits import state_updates as su
     from host_circuits import statements as st
     routes = service_routes.routes()
-    assert len(routes) == 13
+    assert len(routes) == 16
     parties, _ = ps.create_witness_statement(31)
     fresh = {
         "/prove-valid-balance-create": vbc.create_witness_statement(31),
         "/prove-valid-deposit": su.create_deposit_witness_statement(31),
         "/prove-valid-withdrawal": su.create_withdrawal_witness_statement(31),
         "/prove-valid-order-cancellation": su.create_cancellation_witness_statement(31),
+        "/prove-valid-note-redemption": fees.create_note_redemption_witness_statement(31),
+        "/prove-valid-public-protocol-fee-payment": fees.create_public_protocol_fee_payment_witness_statement(31),
+        "/prove-valid-public-relayer-fee-payment": fees.create_public_relayer_fee_payment_witness_statement(31),
         "/prove-intent-only-validity": io.create_validity_witness_statement(31),
         "/prove-intent-only-first-fill-validity": io.create_first_fill_witness_statement(31),
         "/prove-intent-only-public-settlement": io.create_public_settlement_witness_statement(31),
