@@ -266,8 +266,9 @@ REGISTERED = [ValidBalanceCreate, ValidDeposit, ValidWithdrawal, ValidOrderCance
               IntentAndBalancePrivateSettlementCircuit, IntentAndBalancePublicSettlementCircuit,
               IntentAndBalanceBoundedSettlementCircuit, IntentAndBalanceValidityCircuit, OutputBalanceValidityCircuit,
               ValidNoteRedemption, ValidPublicProtocolFeePayment, ValidPublicRelayerFeePayment]
-# not restated: INTENT AND BALANCE FIRST FILL VALIDITY and NEW OUTPUT BALANCE VALIDITY (in-circuit Schnorr verification on
-# BabyJubJub), VALID PRIVATE PROTOCOL / RELAYER FEE PAYMENT (in-circuit ElGamal on BabyJubJub)
+# not restated: INTENT AND BALANCE FIRST FILL VALIDITY and NEW OUTPUT BALANCE VALIDITY (their constraints call jf-primitives'
+# Schnorr `SignatureGadget`, zk_gadgets/primitives/schnorr.rs:20-24), VALID PRIVATE PROTOCOL / RELAYER FEE PAYMENT
+# (jf-primitives' `ElGamalEncryptionGadget`, zk_gadgets/primitives/elgamal.rs:41-47) — gadgets of the un-vendored fork
 
 
 # ---- collaborative counterparts (traits.rs:1103-1154) ---------------------------------------------------------------
