@@ -38,6 +38,7 @@ from typing import Any, Callable, Dict, Optional
 
 import numpy as np
 
+from . import _lib
 from . import circuit_types as ct
 from .backend import B200LinkProof, B200Proof, GroupLayout, LinkingHint
 from .fields import BASE_FIELD_MODULUS, SCALAR_FIELD_MODULUS, limbs_to_scalars, scalars_to_limbs
@@ -222,9 +223,15 @@ class ProverService:
                 other = decode_link_hint(body[req_field])
                 lay = GroupLayout(layouts[group].alignment, layouts[group].offset, layouts[group].size)
                 # validity / output-balance hint first, settlement hint second (intent_and_balance.rs:57-72)
-                jobs.append((resp_field, self._submit_link(other, hint, lay)))
+                try:
+                    jobs.append((resp_field, self._submit_link(other, hint, lay)))
+                except _lib.B200Error as e:
+                    raise ct.ProverError("Plonk", e) from e
             for resp_field, job in jobs:
-                out[resp_field] = encode_link_proof(job())
+                try:
+                    out[resp_field] = encode_link_proof(job())
+                except _lib.B200Error as e:  # the two proofs do not hold the same values on the group (PlonkError)
+                    raise ct.ProverError("Plonk", e) from e
             with self._lock:
                 self.stats["link_proofs"] += len(jobs)
             return out
