@@ -227,11 +227,14 @@ class ProverService:
                     jobs.append((resp_field, self._submit_link(other, hint, lay)))
                 except _lib.B200Error as e:
                     raise ct.ProverError("Plonk", e) from e
-            for resp_field, job in jobs:
+            failure = None
+            for resp_field, job in jobs:  # every queued job is waited for, also after a failure (its buffers live until then)
                 try:
                     out[resp_field] = encode_link_proof(job())
                 except _lib.B200Error as e:  # the two proofs do not hold the same values on the group (PlonkError)
-                    raise ct.ProverError("Plonk", e) from e
+                    failure = failure or e
+            if failure is not None:
+                raise ct.ProverError("Plonk", failure) from failure
             with self._lock:
                 self.stats["link_proofs"] += len(jobs)
             return out

@@ -119,3 +119,49 @@ def public_settlement_flow(client, service, g2, which=("public", "bounded")):
             other = sv.decode_link_hint(hints[hk])
             assert verify_link_proof(other.linking_wire_comm, s_comm, sv.decode_link_proof(body[field]), lay, h, tau_h)
     assert service.stats["link_proofs"] == links0 + 2 * len(which)
+
+
+def private_match_flow(client, service, g2):
+    """The private match: both parties' INTENT AND BALANCE VALIDITY and OUTPUT BALANCE VALIDITY proofs
+    (`ProofAndHintResponse`), then INTENT AND BALANCE PRIVATE SETTLEMENT carrying the four hints
+    (`PrivateSettlementProofResponse`, api_types.rs:106-124, 249-266) — the sequence tests/test_gpu_service.py::
+    test_prove_paths_over_http drives on the device (there with the validity requests in flight together)."""
+    from host_circuits import private_settlement as ps
+    h, tau_h = g2
+    links0 = service.stats["link_proofs"]
+    parties, _ = ps.create_witness_statement(seed=61)
+    validity = [val.create_witness_statement(seed=70 + i, intent=parties[i].intent, balance=parties[i].input_balance) for i in (0, 1)]
+    out_validity = [obv.create_witness_statement(80 + i, parties[i].output_balance) for i in (0, 1)]
+    parties, statement = ps.create_witness_statement(
+        seed=61, linked=[(validity[i][0].new_amount_public_share, validity[i][0].post_match_balance_shares,
+                          out_validity[i][0].post_match_balance_shares) for i in (0, 1)])
+    hints = {}
+    for kind, path, C, insts in (("v", "/prove-intent-and-balance-validity", st.IntentAndBalanceValidityCircuit, validity),
+                                 ("o", "/prove-output-balance-validity", st.OutputBalanceValidityCircuit, out_validity)):
+        for i, (w_, s_) in enumerate(insts):
+            code, body = client.send_request(path, {"statement": sv.to_json(s_), "witness": sv.to_json(w_)})
+            assert code == 200 and set(body) == {"proof", "link_hint"}, (path, body)
+            ct.verify_singleprover_proof(C, s_, sv.decode_proof(body["proof"]))
+            hints[(kind, i)] = body["link_hint"]
+    req = {"statement": sv.to_json(statement), "witness": sv.to_json(parties),
+           "validity_link_hint_0": hints[("v", 0)], "validity_link_hint_1": hints[("v", 1)],
+           "output_balance_link_hint_0": hints[("o", 0)], "output_balance_link_hint_1": hints[("o", 1)]}
+    code, body = client.send_request("/prove-intent-and-balance-private-settlement", req)
+    assert code == 200 and set(body) == {"proof", "validity_link_proof_0", "validity_link_proof_1",
+                                         "output_balance_link_proof_0", "output_balance_link_proof_1"}, body
+    S = st.IntentAndBalancePrivateSettlementCircuit
+    sp = sv.decode_proof(body["proof"])
+    ct.verify_singleprover_proof(S, statement, sp)
+    layouts = S.get_circuit_layout()
+    s_comm = np.array(sp.wires_poly_comms[0], dtype=np.uint64)
+    for field, key, gid in (("validity_link_proof_0", ("v", 0), ps.PARTY_LINKS[0]), ("validity_link_proof_1", ("v", 1), ps.PARTY_LINKS[1]),
+                            ("output_balance_link_proof_0", ("o", 0), ps.OUTPUT_LINKS[0]),
+                            ("output_balance_link_proof_1", ("o", 1), ps.OUTPUT_LINKS[1])):
+        lay = GroupLayout(layouts[gid].alignment, layouts[gid].offset, layouts[gid].size)
+        other = sv.decode_link_hint(hints[key])
+        assert verify_link_proof(other.linking_wire_comm, s_comm, sv.decode_link_proof(body[field]), lay, h, tau_h)
+    # party 1's validity hint in party 0's slot: the group values differ, the prover refuses
+    req_bad = dict(req, validity_link_hint_0=hints[("v", 1)])
+    code, body = client.send_request("/prove-intent-and-balance-private-settlement", req_bad)
+    assert code == 500 and "ProverError" in body["error"], body
+    assert service.stats["link_proofs"] == links0 + 4

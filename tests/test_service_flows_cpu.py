@@ -81,3 +81,7 @@ def test_intent_only_flow(served, g2_raw):
 
 def test_public_settlement_flow(served, g2_raw):
     service_flows.public_settlement_flow(*served, g2_raw, which=("public",))
+
+
+def test_private_match_flow(served, g2_raw):
+    service_flows.private_match_flow(*served, g2_raw)
