@@ -16,8 +16,9 @@
 //   * pairing: Fq12 = Fq[w] / (w^12 - 18 w^6 + 82) (so Fq2 = Fq[u]/(u^2 + 1) sits inside as u = w^6 - 9),
 //     G2 on the sextic twist y^2 = x^3 + 3 / (9 + u), Miller loop over 6x + 2 with x = 4965661367192848881 and
 //     the two Frobenius line steps, lines evaluated as sparse elements -y_P + (m x_P) w + (y_R - m x_R) w^3,
-//     final exponentiation split into the easy part (q^6 - 1)(q^2 + 1) and a square-and-multiply hard part.
-// Clarity over speed: a verification is a few tens of milliseconds of host time.
+//     final exponentiation split into the easy part (q^6 - 1)(q^2 + 1) and the hard part by the x-addition chain of
+//     Fuentes-Castaneda et al. (three exponentiations by x and Frobenius maps).
+// Clarity first: flat Fq12 arithmetic, affine Miller steps; a verification is ~6 ms of host time.
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -92,6 +93,26 @@ fq12 fq12_mul(const fq12& a, const fq12& b) {
     for (int i = 0; i < 12; ++i) r.c[i] = t[i];
     return r;
 }
+// a^2 with the symmetric products taken once: 78 field products instead of 144
+fq12 fq12_sqr(const fq12& a) {
+    fe t[23];
+    for (auto& v : t) v = fe_zero();
+    for (int i = 0; i < 12; ++i) {
+        if (fe_is_zero(a.c[i])) continue;
+        t[2 * i] = fe_add<Fq>(t[2 * i], fe_sqr<Fq>(a.c[i]));
+        const fe twice = fe_dbl<Fq>(a.c[i]);
+        for (int j = i + 1; j < 12; ++j) t[i + j] = fe_add<Fq>(t[i + j], fe_mul<Fq>(twice, a.c[j]));
+    }
+    const fe c18 = fe_from_u32<Fq>(18), c82 = fe_from_u32<Fq>(82);
+    for (int k = 22; k >= 12; --k) {
+        if (fe_is_zero(t[k])) continue;
+        t[k - 6] = fe_add<Fq>(t[k - 6], fe_mul<Fq>(c18, t[k]));
+        t[k - 12] = fe_sub<Fq>(t[k - 12], fe_mul<Fq>(c82, t[k]));
+    }
+    fq12 r;
+    for (int i = 0; i < 12; ++i) r.c[i] = t[i];
+    return r;
+}
 // a + b u placed at w^k: u = w^6 - 9
 void fq12_put(fq12* f, int k, const fq2& v) {
     const fe nine_b = fe_mul<Fq>(fe_from_u32<Fq>(9), v.b);
@@ -151,7 +172,7 @@ fq12 fq12_pow(const fq12& a, const uint64_t* e, int limbs) {
     fq12 r = fq12_one();
     bool started = false;
     for (int i = limbs * 64 - 1; i >= 0; --i) {
-        if (started) r = fq12_mul(r, r);
+        if (started) r = fq12_sqr(r);
         if ((e[i >> 6] >> (i & 63)) & 1) {
             r = started ? fq12_mul(r, a) : a;
             started = true;
@@ -165,6 +186,7 @@ fq12 fq12_pow(const fq12& a, const uint64_t* e, int limbs) {
 struct PairingConsts {
     fe gamma_pow[6];  // gamma^k
     fq2 twist_frob_x, twist_frob_y;
+    fq2 frob1[12];    // (w^k)^q = frob1[k] w^k: powers of xi^((q-1)/6), xi = w^6 = 9 + u
 };
 fq2 fq2_pow(const fq2& a, const uint64_t* e, int limbs) {
     fq2 r = {fe_one<Fq>(), fe_zero()};
@@ -203,6 +225,11 @@ const PairingConsts& pairing_consts() {
         const fq2 xi = {fe_from_u32<Fq>(9), fe_one<Fq>()};
         pc.twist_frob_x = fq2_pow(xi, third, 4);
         pc.twist_frob_y = fq2_pow(xi, halfe, 4);
+        uint64_t sixth[4];  // (q - 1) / 6 = ((q - 1) / 3) / 2
+        for (int i = 0; i < 4; ++i) sixth[i] = (third[i] >> 1) | (i < 3 ? third[i + 1] << 63 : 0);
+        pc.frob1[0] = {fe_one<Fq>(), fe_zero()};
+        pc.frob1[1] = fq2_pow(xi, sixth, 4);
+        for (int k = 2; k < 12; ++k) pc.frob1[k] = fq2_mul(pc.frob1[k - 1], pc.frob1[1]);
     });
     return pc;
 }
@@ -211,6 +238,28 @@ fq12 fq12_frob2(const fq12& a) {
     const PairingConsts& pc = pairing_consts();
     fq12 r;
     for (int k = 0; k < 12; ++k) r.c[k] = fe_mul<Fq>(a.c[k], pc.gamma_pow[k % 6]);
+    return r;
+}
+// x -> x^q: the coefficients are in Fq, so x^q = sum_k c_k (w^q)^k = sum_k c_k frob1[k] w^k with frob1[k] in Fq2 = Fq[u],
+// u = w^6 - 9; the products land on w^k and w^(k+6) and fold back with w^12 = 18 w^6 - 82
+fq12 fq12_frob1(const fq12& a) {
+    const PairingConsts& pc = pairing_consts();
+    fe t[18];
+    for (auto& v : t) v = fe_zero();
+    const fe nine = fe_from_u32<Fq>(9);
+    for (int k = 0; k < 12; ++k) {
+        if (fe_is_zero(a.c[k])) continue;
+        const fq2& g = pc.frob1[k];
+        t[k] = fe_add<Fq>(t[k], fe_mul<Fq>(a.c[k], fe_sub<Fq>(g.a, fe_mul<Fq>(nine, g.b))));
+        t[k + 6] = fe_add<Fq>(t[k + 6], fe_mul<Fq>(a.c[k], g.b));
+    }
+    const fe c18 = fe_from_u32<Fq>(18), c82 = fe_from_u32<Fq>(82);
+    for (int k = 17; k >= 12; --k) {
+        t[k - 6] = fe_add<Fq>(t[k - 6], fe_mul<Fq>(c18, t[k]));
+        t[k - 12] = fe_sub<Fq>(t[k - 12], fe_mul<Fq>(c82, t[k]));
+    }
+    fq12 r;
+    for (int i = 0; i < 12; ++i) r.c[i] = t[i];
     return r;
 }
 g2_affine g2_frobenius(const g2_affine& p) {
@@ -236,7 +285,7 @@ void line_and_add(fq12* f, g2_affine* r, const g2_affine& s, const fe& px, const
         if (!fq2_eq(r->y, s.y) || fq2_is_zero(r->y)) {  // vertical line x_P - x_R w^2
             line.c[0] = px;
             fq12_put(&line, 2, fq2_neg(r->x));
-            *f = fq12_mul(*f, line);
+            *f = fq12_mul(line, *f);
             r->inf = true;
             return;
         }
@@ -249,41 +298,77 @@ void line_and_add(fq12* f, g2_affine* r, const g2_affine& s, const fe& px, const
     line.c[0] = fe_neg<Fq>(py);
     fq12_put(&line, 1, fq2_mul_fq(m, px));
     fq12_put(&line, 3, fq2_sub(r->y, fq2_mul(m, r->x)));
-    *f = fq12_mul(*f, line);
+    *f = fq12_mul(line, *f);  // sparse operand first: fq12_mul skips its zero coefficients
     const fq2 nx = fq2_sub(fq2_sub(fq2_sqr(m), r->x), s.x);
     const fq2 ny = fq2_sub(fq2_mul(m, fq2_sub(r->x, nx)), r->y);
     r->x = nx;
     r->y = ny;
 }
 
-// Miller function of (P in G1, Q in G2) before the final exponentiation
-fq12 miller_loop(const g1_affine& p, const g2_affine& q) {
+// Product of the Miller functions of k pairs (P_i in G1, Q_i in G2) before the final exponentiation: one accumulator, so
+// the 64 squarings are shared by all pairs
+fq12 miller_loop_product(const g1_affine* ps, const g2_affine* qs, size_t k) {
     fq12 f = fq12_one();
-    if (g1_affine_is_inf(p) || q.inf) return f;
+    std::vector<size_t> live;
+    for (size_t i = 0; i < k; ++i)
+        if (!g1_affine_is_inf(ps[i]) && !qs[i].inf) live.push_back(i);  // a pair with an identity contributes 1
+    if (live.empty()) return f;
     static const uint64_t ate[2] = {0x9d797039be763ba8ULL, 0x1ULL};  // 6x + 2, 65 bits
-    g2_affine r = q;
+    std::vector<g2_affine> r(live.size());
+    for (size_t j = 0; j < live.size(); ++j) r[j] = qs[live[j]];
     for (int i = 63; i >= 0; --i) {
-        f = fq12_mul(f, f);
-        line_and_add(&f, &r, r, p.x, p.y);
-        if ((ate[i >> 6] >> (i & 63)) & 1) line_and_add(&f, &r, q, p.x, p.y);
+        f = fq12_sqr(f);
+        const bool bit = (ate[i >> 6] >> (i & 63)) & 1;
+        for (size_t j = 0; j < live.size(); ++j) {
+            const g1_affine& p = ps[live[j]];
+            line_and_add(&f, &r[j], r[j], p.x, p.y);
+            if (bit) line_and_add(&f, &r[j], qs[live[j]], p.x, p.y);
+        }
     }
-    const g2_affine q1 = g2_frobenius(q);
-    g2_affine nq2 = g2_frobenius(q1);
-    nq2.y = fq2_neg(nq2.y);
-    line_and_add(&f, &r, q1, p.x, p.y);
-    line_and_add(&f, &r, nq2, p.x, p.y);
+    for (size_t j = 0; j < live.size(); ++j) {
+        const g1_affine& p = ps[live[j]];
+        const g2_affine q1 = g2_frobenius(qs[live[j]]);
+        g2_affine nq2 = g2_frobenius(q1);
+        nq2.y = fq2_neg(nq2.y);
+        line_and_add(&f, &r[j], q1, p.x, p.y);
+        line_and_add(&f, &r[j], nq2, p.x, p.y);
+    }
     return f;
 }
 
+// t^x for the curve parameter x = 4965661367192848881 (63 bits, 28 of them set)
+fq12 fq12_pow_x(const fq12& t) {
+    static const uint64_t x[1] = {0x44e992b44a6909f1ULL};
+    return fq12_pow(t, x, 1);
+}
+
 fq12 final_exponentiation(const fq12& f) {
-    // easy part: f^((q^6 - 1)(q^2 + 1))
+    // easy part: f^((q^6 - 1)(q^2 + 1)); afterwards t is in the cyclotomic subgroup, where the inverse is the conjugate
     fq12 t = fq12_mul(fq12_conj(f), fq12_inv(f));
     t = fq12_mul(fq12_frob2(t), t);
-    // hard part: (q^4 - q^2 + 1) / r
-    static const uint64_t hard[12] = {0xe81bb482ccdf42b1ULL, 0x5abf5cc4f49c36d4ULL, 0xf1154e7e1da014fdULL, 0xdcc7b44c87cdbacfULL,
-                                      0xaaa441e3954bcf8aULL, 0x6b887d56d5095f23ULL, 0x79581e16f3fd90c6ULL, 0x3b1b1355d189227dULL,
-                                      0x4e529a5861876f6bULL, 0x6c0eb522d5b12278ULL, 0x331ec15183177fafULL, 0x01baaa710b0759adULL};
-    return fq12_pow(t, hard, 12);
+    // hard part (q^4 - q^2 + 1) / r by the addition chain of Fuentes-Castaneda, Knapp and Rodriguez-Henriquez ("Faster
+    // hashing to G2", SAC 2011; the schedule ark-ec's bn model uses): three exponentiations by x, Frobenius maps and a
+    // dozen products instead of a 762-bit square-and-multiply.  It raises t to c (q^4 - q^2 + 1) / r with a c prime to r
+    // (checked on the exponents: tests/test_pairing.py), which is one exactly when the reduced pairing is.
+    auto neg_x = [](const fq12& a) { return fq12_conj(fq12_pow_x(a)); };  // a^(-x)
+    const fq12 y0 = neg_x(t);
+    const fq12 y1 = fq12_sqr(y0);
+    const fq12 y2 = fq12_sqr(y1);
+    fq12 y3 = fq12_mul(y2, y1);
+    const fq12 y4 = neg_x(y3);
+    const fq12 y5 = fq12_sqr(y4);
+    fq12 y6 = neg_x(y5);
+    y3 = fq12_conj(y3);
+    y6 = fq12_conj(y6);
+    const fq12 y7 = fq12_mul(y6, y4);
+    const fq12 y8 = fq12_mul(y7, y3);
+    const fq12 y9 = fq12_mul(y8, y1);
+    const fq12 y10 = fq12_mul(y8, y4);
+    const fq12 y11 = fq12_mul(y10, t);
+    const fq12 y13 = fq12_mul(fq12_frob1(y9), y11);
+    const fq12 y14 = fq12_mul(fq12_frob2(y8), y13);
+    const fq12 y15 = fq12_mul(fq12_conj(t), y9);
+    return fq12_mul(fq12_frob1(fq12_frob2(y15)), y14);  // q^3 = q o q^2
 }
 
 bool g2_on_curve(const g2_affine& p) {
@@ -311,9 +396,25 @@ g1_affine g1_load(const uint64_t xy[8]) {
 }
 
 // ---- G1 helpers of the verifier (host XYZZ arithmetic of ec.cuh) -------------------------------------------
-void g1_acc(g1_xyzz* acc, const g1_affine& p, const fe& s_mont) {
-    if (g1_affine_is_inf(p)) return;
-    *acc = g1_add(*acc, g1_mul_bits(p, fe_from_mont<Fr>(s_mont), 254));
+// sum_i s_i P_i, collected first and evaluated with ONE chain of doublings (Straus: 254 doublings in all and a mixed
+// addition per set scalar bit, instead of 254 doublings per term)
+struct G1Sum {
+    std::vector<g1_affine> pts;
+    std::vector<fe> scalars;  // canonical (non-Montgomery) limbs
+    g1_xyzz eval() const {
+        g1_xyzz acc = g1_xyzz_inf();
+        for (int bit = 253; bit >= 0; --bit) {
+            acc = g1_dbl(acc);
+            for (size_t i = 0; i < pts.size(); ++i)
+                if ((scalars[i].l[bit >> 5] >> (bit & 31)) & 1u) acc = g1_add_mixed(acc, pts[i]);
+        }
+        return acc;
+    }
+};
+void g1_acc(G1Sum* acc, const g1_affine& p, const fe& s_mont) {
+    if (g1_affine_is_inf(p) || fe_is_zero(s_mont)) return;
+    acc->pts.push_back(p);
+    acc->scalars.push_back(fe_from_mont<Fr>(s_mont));
 }
 inline fe fr_pow_u64(fe a, uint64_t e) {
     fe r = fe_one<Fr>();
@@ -340,9 +441,7 @@ struct ProofIn {  // layout of b200_proof
 static_assert(sizeof(ProofIn) == sizeof(b200_proof), "proof layout");
 
 bool pairing_product_is_one(const g1_affine* ps, const g2_affine* qs, size_t k) {
-    fq12 f = fq12_one();
-    for (size_t i = 0; i < k; ++i) f = fq12_mul(f, miller_loop(ps[i], qs[i]));
-    return fq12_is_one(final_exponentiation(f));
+    return fq12_is_one(final_exponentiation(miller_loop_product(ps, qs, k)));
 }
 
 }  // namespace
@@ -447,7 +546,7 @@ int b200_plonk_verify(unsigned log_n, size_t num_inputs, const uint64_t* k, cons
     const fe r0 = fe_sub<Fr>(fe_sub<Fr>(pi_eval, fe_mul<Fr>(alpha2, l1)), prod4);
 
     // ---- D: linearisation commitment ---------------------------------------------------------------------------
-    g1_xyzz D = g1_xyzz_inf();
+    G1Sum D;  // F and B below only add terms to it: one evaluation at the end
     auto pow5 = [](const fe& x) { return fe_mul<Fr>(fe_sqr<Fr>(fe_sqr<Fr>(x)), x); };
     for (int j = 0; j < 4; ++j) g1_acc(&D, sel[j], we[j]);
     g1_acc(&D, sel[4], fe_mul<Fr>(we[0], we[1]));
@@ -469,7 +568,7 @@ int b200_plonk_verify(unsigned log_n, size_t num_inputs, const uint64_t* k, cons
         c = fe_mul<Fr>(c, zn2);
     }
     // ---- F, E: batched opening at zeta -------------------------------------------------------------------------
-    g1_xyzz F = D;
+    G1Sum& F = D;
     fe E = fe_neg<Fr>(r0), vp = one;
     for (int i = 0; i < NW; ++i) {
         vp = fe_mul<Fr>(vp, v);
@@ -485,16 +584,17 @@ int b200_plonk_verify(unsigned log_n, size_t num_inputs, const uint64_t* k, cons
     g1_affine G;
     G.x = fe_one<Fq>();
     G.y = fe_from_u32<Fq>(2);
-    g1_xyzz A = g1_xyzz_from_affine(proof.opening_proof);
+    G1Sum A;
+    g1_acc(&A, proof.opening_proof, one);
     g1_acc(&A, proof.shifted_opening_proof, u);
-    g1_xyzz B = F;
+    G1Sum& B = F;
     g1_acc(&B, G, fe_neg<Fr>(E));
     g1_acc(&B, proof.opening_proof, zeta);
     g1_acc(&B, proof.shifted_opening_proof, fe_mul<Fr>(u, fe_mul<Fr>(zeta, w)));
     g1_acc(&B, proof.prod_perm_poly_comm, u);
     g1_acc(&B, G, fe_neg<Fr>(fe_mul<Fr>(u, proof.perm_next_eval)));
     // e(A, [tau]_2) == e(B, [1]_2)   <=>   e(A, [tau]_2) * e(-B, [1]_2) == 1
-    const g1_affine ps[2] = {g1_to_affine(A), g1_affine_neg(g1_to_affine(B))};
+    const g1_affine ps[2] = {g1_to_affine(A.eval()), g1_affine_neg(g1_to_affine(B.eval()))};
     const g2_affine qs[2] = {g2_load(g2_tau_h), g2_load(g2_h)};
     if (!g2_on_curve(qs[0]) || !g2_on_curve(qs[1])) {
         set_error("verify: G2 point not on curve");
@@ -525,11 +625,12 @@ int b200_plonk_verify_link(const uint64_t* comm1, const uint64_t* comm2, unsigne
         root = fe_mul<Fr>(root, g);
     }
     // (tau - eta) pi == C1 - C2 - Z_D(eta) Cq   <=>   e(pi, [tau]_2) == e(C1 - C2 - Z_D(eta) Cq + eta pi, [1]_2)
-    g1_xyzz B = g1_xyzz_from_affine(c1);
-    B = g1_add_mixed(B, g1_affine_neg(c2));
+    G1Sum B;
+    g1_acc(&B, c1, fe_one<Fr>());
+    g1_acc(&B, g1_affine_neg(c2), fe_one<Fr>());
     g1_acc(&B, cq, fe_neg<Fr>(zd));
     g1_acc(&B, op, eta);
-    const g1_affine ps[2] = {op, g1_affine_neg(g1_to_affine(B))};
+    const g1_affine ps[2] = {op, g1_affine_neg(g1_to_affine(B.eval()))};
     const g2_affine qs[2] = {g2_load(g2_tau_h), g2_load(g2_h)};
     if (!g2_on_curve(qs[0]) || !g2_on_curve(qs[1])) {
         set_error("verify_link: G2 point not on curve");

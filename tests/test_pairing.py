@@ -125,3 +125,39 @@ def test_oracle_link_proof_verifies_with_pairing(oracle, pyoracle, srs_head, g2)
     rc, _, _ = oracle.plonk_link(hints[0][0], hints[1][0], hints[0][1], hints[1][1], *wrong, srs_all)
     assert rc == 2   # not linkable on that group: the prover refuses instead of emitting an unverifiable proof
     assert not _link_pairing_ok(py, pr, hints[0][1], hints[1][1], wrong, lp.to_array(), eta, g2)
+
+
+def test_hard_part_addition_chain_exponent():
+    """The final exponentiation of renegade_b200/csrc/verify.cu takes the hard part by the x-addition chain of
+    Fuentes-Castaneda et al. (the schedule of `final_exponentiation` there, restated here on EXPONENTS: a product adds,
+    a squaring doubles, a conjugation — the inverse in the cyclotomic subgroup — negates, a q^k-Frobenius multiplies by
+    q^k, all modulo the subgroup order q^4 - q^2 + 1).  The chain must raise to c (q^4 - q^2 + 1) / r with c prime to r:
+    then its result is one exactly when the reduced pairing is."""
+    q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    r = 0x30644e72e131a029b85045b68181585d2833e84879b97091_43e1f593f0000001
+    x = 4965661367192848881
+    assert x == 0x44e992b44a6909f1            # the constant of fq12_pow_x
+    phi = q ** 4 - q ** 2 + 1
+    assert phi % r == 0
+    h = phi // r
+    neg_x = lambda e: -x * e % phi
+    frob = lambda e, k: e * pow(q, k, phi) % phi
+    t = 1
+    y0 = neg_x(t)
+    y1 = 2 * y0 % phi
+    y2 = 2 * y1 % phi
+    y3 = (y2 + y1) % phi
+    y4 = neg_x(y3)
+    y5 = 2 * y4 % phi
+    y6 = neg_x(y5)
+    y3, y6 = -y3 % phi, -y6 % phi
+    y7 = (y6 + y4) % phi
+    y8 = (y7 + y3) % phi
+    y9 = (y8 + y1) % phi
+    y10 = (y8 + y4) % phi
+    y11 = (y10 + t) % phi
+    y13 = (frob(y9, 1) + y11) % phi
+    y14 = (frob(y8, 2) + y13) % phi
+    y15 = (-t + y9) % phi
+    e = (frob(y15, 3) + y14) % phi
+    assert e % h == 0 and (e // h) % r != 0
