@@ -43,6 +43,16 @@ def test_prove_matches_oracle_bit_exact(ctx, oracle, pyoracle, log_n):
     assert (ch.reshape(-1) == np.frombuffer(bytes(och), dtype=np.uint64)).all()
     assert (hint.linking_wire_poly == olink).all()
     assert (hint.linking_wire_comm == ours[:8]).all()
+    if log_n == 5:  # the committed proof fixture was cut with exactly these parameters (tests/golden/make_proof_golden.py)
+        import hashlib
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proof_kat.json")) as f:
+            want = json.load(f)
+        assert (want["params"]["circuit_seed"], want["params"]["blinder_seed"], int(want["params"]["tau"], 16)) == (105, 0xB11D + 5, TAU)
+        assert bytes(proof).hex() == want["proof_hex"]
+        assert hashlib.sha256(np.ascontiguousarray(hint.linking_wire_poly).tobytes()).hexdigest() == want["link_poly_sha256"]
+        assert hashlib.sha256(pk.selector_comms.tobytes() + pk.sigma_comms.tobytes()).hexdigest() == want["vk_sha256"]
     # the restated verifier accepts the device proof; tampering is rejected
     op = oracle.PlonkProof.from_buffer_copy(bytes(proof))
     assert oracle.plonk_verify_known_tau(log_n, circ.num_inputs, circ.k, opk, circ.pub_inputs, op, tau)

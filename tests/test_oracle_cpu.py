@@ -200,3 +200,19 @@ def test_quotient_domain_of_six_cosets_matches_the_8n_coset(pyoracle):
     for j in range(nc):
         folded = [(a[i] + (c[j] * a[n + i] if n + i < len(a) else 0)) * pow(s[j], i, py.R) % py.R for i in range(n)]
         assert py.ntt(folded) == [a_on_8n[8 * h + j] for h in range(n)], j
+
+
+def test_oracle_prover_reproduces_the_committed_proof():
+    """tests/golden/proof_kat.json: proof bytes, Fiat-Shamir challenges, verifying key and linking polynomial of one seeded
+    circuit as the oracle prover produced them when the fixture was cut (tests/golden/make_proof_golden.py).  A regression
+    pin of the restated rounds / transcript / blinding order — not a vector of the Rust reference.
+    tests/test_gpu_plonk.py compares the device proof with the same bytes."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_proof_golden
+    with open(os.path.join(here, "golden", "proof_kat.json")) as f:
+        want = json.load(f)
+    assert make_proof_golden.compute(want["params"]) == want
