@@ -16,9 +16,12 @@
 //   * digits are counting-sorted by bucket (histogram -> scan -> scatter, L2-resident atomics),
 //     then one thread per bucket folds its points with XYZZ mixed additions (8M+2S, no
 //     inversion), prefetching the next 64-byte point while the current addition runs;
-//   * bucket sums are folded with a chunked running sum + block tree; the last few hundred
-//     bytes go to the host, which does the final Horner (only when windows are not fully
-//     precomputed) and the single field inversion.
+//   * sum_k (k+1) B_k without a running sum: the buckets of a window form a matrix whose row and
+//     column sums carry the weights, so every bucket enters two plain additions (one serial level of
+//     fan-in 8 / 4, then shared-memory binary trees), and the two weighted sums that remain become
+//     c - 1 per-bit sums; the dependent additions of those tails run on four lanes each
+//     (xyzz_add_quad); the last ~2 KB go to the host, which runs the Horner over the bit sums and
+//     the single field inversion of the batch.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
