@@ -355,7 +355,7 @@ class PlonkCircuit:
     def public_input(self) -> List[int]:
         return [self.witness_values[v] for v in self.pub_input_vars]
 
-    def finalize_for_arithmetization(self, min_log_n: int = 2) -> SynthCircuit:
+    def finalize_for_arithmetization(self, min_log_n: int = 2, wires_only: bool = False) -> SynthCircuit:
         """Public-input gates first, zero padding to the next power of two, one copy-constraint cycle per variable
         (upstream: `finalize_for_arithmetization`, traits.rs:847,991).  Returns the flat tables the C ABI takes.
 
@@ -389,29 +389,33 @@ class PlonkCircuit:
                 rows.append(_Row([pinned[r]] + [self._zero] * GATE_WIDTH, Gate("LinkGate")))
             else:
                 rows.append(next(pending, None) or _Row([self._zero] * (GATE_WIDTH + 1), PaddingGate()))
-        sel = [[0] * n for _ in range(N_SELECTORS)]
-        wire_var = [[0] * n for _ in range(N_WIRES)]
+        # `wires_only` (f4 of SURVEY 8(f): the structure is witness-independent and lives in the preprocessed key; per proof
+        # only the 5 x n value table changes): skip the selector columns and the copy permutation, keep their fingerprint
+        gate_sels = [tuple(row.gate.selectors()) for row in rows]
+        digest = hash((n, tuple(tuple(row.wires) for row in rows), tuple(gate_sels))) or 1
+        wires_int = [[self.witness_values[row.wires[w]] for row in rows] for w in range(N_WIRES)]
+        pub = self.public_input()
+        k_int = [pow(5, i, R) for i in range(N_WIRES)]
+        wires = np.stack([to_mont_array(col) for col in wires_int])
+        pub_arr = to_mont_array(pub) if pub else np.zeros((0, 4), dtype=np.uint64)
+        self._finalized = True
+        if wires_only:
+            return SynthCircuit(log_n=log_n, num_inputs=len(pub), k=to_mont_array(k_int), selectors=None, perm=None,
+                                wires=wires, pub_inputs=pub_arr, n_gates=n_gates, selectors_int=None, wires_int=wires_int,
+                                pub_inputs_int=pub, structure_digest=digest)
+        sel = [[q[s] for q in gate_sels] for s in range(N_SELECTORS)]
         positions: List[List] = [[] for _ in self.witness_values]
         for r, row in enumerate(rows):
-            q = row.gate.selectors()
-            for s in range(N_SELECTORS):
-                sel[s][r] = q[s]
             for wcol, var in enumerate(row.wires):
-                wire_var[wcol][r] = var
                 positions[var].append((wcol, r))
         perm = np.empty(N_WIRES * n, dtype=np.uint64)
         for occ in positions:
             for a, b in zip(occ, occ[1:] + occ[:1]):
                 perm[a[0] * n + a[1]] = b[0] * n + b[1]
-        wires_int = [[self.witness_values[wire_var[w][r]] for r in range(n)] for w in range(N_WIRES)]
-        pub = self.public_input()
-        k_int = [pow(5, i, R) for i in range(N_WIRES)]
-        self._finalized = True
         return SynthCircuit(log_n=log_n, num_inputs=len(pub), k=to_mont_array(k_int),
-                            selectors=np.stack([to_mont_array(col) for col in sel]), perm=perm,
-                            wires=np.stack([to_mont_array(col) for col in wires_int]),
-                            pub_inputs=to_mont_array(pub) if pub else np.zeros((0, 4), dtype=np.uint64),
-                            n_gates=n_gates, selectors_int=sel, wires_int=wires_int, pub_inputs_int=pub)
+                            selectors=np.stack([to_mont_array(col) for col in sel]), perm=perm, wires=wires,
+                            pub_inputs=pub_arr, n_gates=n_gates, selectors_int=sel, wires_int=wires_int, pub_inputs_int=pub,
+                            structure_digest=digest)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -64,6 +64,7 @@ _SYSTEM_SRS: Optional[SystemSrs] = None
 _KEY_LOCK = threading.RLock()
 _CIRCUIT_KEY_CACHE: Dict[str, Tuple[ProvingKey, VerifyingKey]] = {}
 _CIRCUIT_LAYOUT_CACHE: Dict[str, Any] = {}
+_CIRCUIT_STRUCTURE: Dict[str, int] = {}  # name -> fingerprint of the structure its key was preprocessed from (0: unknown)
 
 
 def set_system_srs(ctx: Context, powers_of_g: Bases, g2_h: np.ndarray, g2_tau_h: np.ndarray, pool=None) -> SystemSrs:
@@ -93,6 +94,7 @@ def clear_key_cache() -> None:
                 pass
         _CIRCUIT_KEY_CACHE.clear()
         _CIRCUIT_LAYOUT_CACHE.clear()
+        _CIRCUIT_STRUCTURE.clear()
 
 
 def draw_blinders(rng=None) -> np.ndarray:
@@ -128,6 +130,7 @@ def setup_preprocessed_keys(circuit: type) -> Tuple[ProvingKey, VerifyingKey]:
         except _lib.B200Error as e:
             raise ProverError("Plonk", e) from e
         pair = (pk, VerifyingKey.from_proving_key(pk, srs.g2_h, srs.g2_tau_h))
+        _CIRCUIT_STRUCTURE[name] = int(getattr(circ, "structure_digest", 0) or 0)
         _CIRCUIT_KEY_CACHE[name] = pair
         return pair
 
@@ -192,16 +195,25 @@ class SingleProverCircuit:
 
     @classmethod
     def prove_with_link_hint(cls, witness, statement, rng=None) -> Tuple[PlonkProof, ProofLinkingHint]:
+        pk = cls.proving_key()
+        keyed = _CIRCUIT_STRUCTURE.get(cls.name(), 0)
         try:
             cs = cls.synthesize(witness, statement, cls.get_circuit_layout())
-            circ = cs.finalize_for_arithmetization()
+            # the key holds the witness-independent structure; per proof only the value tables are arithmetized
+            # (SURVEY 8(f) f4), with a fingerprint of the structure to compare against the key's
+            try:
+                circ = cs.finalize_for_arithmetization(wires_only=True) if keyed else cs.finalize_for_arithmetization()
+            except TypeError:  # a constraint system without the wires-only form
+                circ = cs.finalize_for_arithmetization()
         except ProverError:
             raise
         except Exception as e:
             raise ProverError("Circuit", e) from e
-        pk = cls.proving_key()
         if circ.log_n != pk.log_n or circ.num_inputs != pk.num_inputs:
             raise ProverError("Plonk", f"{cls.name()}: instance shape differs from the preprocessed key")
+        if keyed and getattr(circ, "structure_digest", 0) and circ.structure_digest != keyed:
+            raise ProverError("Circuit", f"{cls.name()}: the instance's gates / wiring differ from the circuit its key was "
+                                         "preprocessed from (synthesis must be witness-independent)")
         srs = system_srs()
         try:
             if srs.pool is None:

@@ -25,16 +25,13 @@ Q_LC, Q_MUL, Q_HASH, Q_O, Q_C, Q_ECC = 0, 4, 6, 10, 11, 12
 
 
 def to_mont_array(vals) -> np.ndarray:
-    """list of ints (< r) -> (len, 4) uint64 Montgomery limbs."""
-    out = np.empty((len(vals), 4), dtype=np.uint64)
-    mask = (1 << 64) - 1
-    for i, v in enumerate(vals):
-        m = (v << 256) % R
-        out[i, 0] = m & mask
-        out[i, 1] = (m >> 64) & mask
-        out[i, 2] = (m >> 128) & mask
-        out[i, 3] = m >> 192
-    return out
+    """list of ints (< r) -> (len, 4) uint64 Montgomery limbs (little-endian, the ABI's layout)."""
+    vals = list(vals)
+    if not vals:
+        return np.zeros((0, 4), dtype=np.uint64)
+    zero = bytes(32)
+    buf = b"".join(((v << 256) % R).to_bytes(32, "little") if v else zero for v in vals)
+    return np.frombuffer(buf, dtype="<u8").reshape(len(vals), 4).astype(np.uint64, copy=True)
 
 
 @dataclass
@@ -51,6 +48,10 @@ class SynthCircuit:
     selectors_int: list
     wires_int: list
     pub_inputs_int: list
+    # fingerprint of the witness-independent part (gate placement, wiring, selector values), comparable within one
+    # process; 0 = not computed.  A constraint system may also be finalized `wires_only` (selectors / perm left None)
+    # when the caller only needs the per-proof tables: the key already holds the structure.
+    structure_digest: int = 0
 
     @property
     def n(self) -> int:

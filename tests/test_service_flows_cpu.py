@@ -85,3 +85,19 @@ def test_public_settlement_flow(served, g2_raw):
 
 def test_private_match_flow(served, g2_raw):
     service_flows.private_match_flow(*served, g2_raw)
+
+
+def test_structure_fingerprint_guards_the_key_cache(served, monkeypatch):
+    """Keys are cached by circuit name and, per proof, only the value tables are arithmetized (`wires_only`).
+    A synthesis that yields OTHER gates / wiring than the key was preprocessed from — same domain size, same number of
+    public inputs, so the shape check alone would let it through — is refused as `ProverError::Circuit`."""
+    from host_circuits import state_updates as su
+    from host_circuits import statements as st
+    w, s = su.create_deposit_witness_statement(71)
+    proof, _ = st.ValidDeposit.prove_with_link_hint(w, s)          # sets the key and its fingerprint up, proves wires-only
+    ct.verify_singleprover_proof(st.ValidDeposit, s, proof)
+    assert ct._CIRCUIT_STRUCTURE[st.ValidDeposit.name()] != 0
+    w2, s2 = su.create_withdrawal_witness_statement(72)             # 2^13 rows and 8 public inputs as well
+    monkeypatch.setattr(st.ValidDeposit, "synthesize", classmethod(lambda cls, w_, s_, lay: su.ValidWithdrawal.build(w_, s_)))
+    with pytest.raises(ct.ProverError, match="gates / wiring differ"):
+        st.ValidDeposit.prove_with_link_hint(w2, s2)
