@@ -30,6 +30,7 @@ from __future__ import annotations
 
 import base64
 import dataclasses
+import hmac
 import json
 import threading
 import typing
@@ -285,7 +286,7 @@ class ProverService:
                     self.close_connection = True
                     return self._send(413, {"error": "request body too large or Content-Length missing"})
                 raw = self.rfile.read(n)
-                if self.headers.get("Authorization") != expect:
+                if not hmac.compare_digest((self.headers.get("Authorization") or "").encode(), expect.encode()):
                     return self._send(401, {"error": "unauthorized"})
                 if self.path not in ALL_PATHS:
                     return self._send(404, {"error": f"unknown path {self.path}"})
