@@ -97,6 +97,10 @@ def test_structure_fingerprint_guards_the_key_cache(served, monkeypatch):
     proof, _ = st.ValidDeposit.prove_with_link_hint(w, s)          # sets the key and its fingerprint up, proves wires-only
     ct.verify_singleprover_proof(st.ValidDeposit, s, proof)
     assert ct._CIRCUIT_STRUCTURE[st.ValidDeposit.name()] != 0
+    _, s_other = su.create_deposit_witness_statement(73)           # the right circuit with somebody else's statement: the PROVER's
+    with pytest.raises(ct.ProverError) as err:                      # refusal (WrongQuotientPolyDegree), not a structure error
+        st.ValidDeposit.prove_with_link_hint(w, s_other)
+    assert err.value.kind == "Plonk"
     w2, s2 = su.create_withdrawal_witness_statement(72)             # 2^13 rows and 8 public inputs as well
     monkeypatch.setattr(st.ValidDeposit, "synthesize", classmethod(lambda cls, w_, s_, lay: su.ValidWithdrawal.build(w_, s_)))
     with pytest.raises(ct.ProverError, match="gates / wiring differ"):
